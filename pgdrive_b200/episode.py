@@ -1,0 +1,118 @@
+"""Per-seed episode template (host side): everything ``reset(force_seed=s)`` decides before the
+first physics step -- ego parameters and route, traffic slots (type, lane, longitude, sampled
+parameters, IDM seed / overtake timer, route) and the trigger road of every block.
+
+The draw order over the reference's RNG streams is SURVEY.md appendix A; sources:
+engine/base_engine.py:92-112,300-304 (object seeds), base_class/base_runnable.py:81-88 (parameters),
+manager/traffic_manager.py:239-290,311-314 (traffic), component/vehicle_module/navigation.py:99-153
+(destination + route), policy/idm_policy.py:180-188 (IDM seed, overtake timer).
+
+Checked against tests/golden/reset_*.json.gz, produced by the unmodified reference.
+"""
+import math
+
+from . import rng
+from .roadnet import is_negative
+
+VEHICLE_GAP = 10  # traffic_manager.py:30
+
+# utils/space.py:219-255 -- bounds in the literal (positional) order of the reference: low, high
+VEHICLE_SPACE = {
+    "default": dict(wheel_friction=("c", 0.9), max_engine_force=("f", 850, 750), max_brake_force=("f", 180, 80),
+                    max_steering=("c", 40), max_speed=("c", 80)),
+    "s": dict(wheel_friction=("c", 0.9), max_engine_force=("f", 550, 350), max_brake_force=("f", 80, 35),
+              max_steering=("c", 50), max_speed=("c", 80)),
+    "m": dict(wheel_friction=("c", 0.75), max_engine_force=("f", 850, 650), max_brake_force=("f", 150, 60),
+              max_steering=("c", 45), max_speed=("c", 80)),
+    "l": dict(wheel_friction=("c", 0.8), max_engine_force=("f", 650, 450), max_brake_force=("f", 120, 60),
+              max_steering=("c", 40), max_speed=("c", 80)),
+    "xl": dict(wheel_friction=("c", 0.7), max_engine_force=("f", 700, 500), max_brake_force=("f", 100, 50),
+               max_steering=("c", 35), max_speed=("c", 80)),
+}
+# component/vehicle/vehicle_type.py:7-78: LENGTH, WIDTH, HEIGHT, MASS, front / rear wheelbase, tyre radius, track/2
+VEHICLE_BODY = {
+    "default": (4.51, 1.852, 1.19, 1100.0, 1.05234, 1.4166, 0.313, 0.815),
+    "xl": (5.8, 2.3, 2.8, 1600.0, 1.726, 1.075, 0.37, 0.831),
+    "l": (4.5, 1.86, 1.85, 1300.0, 1.391, 1.10751, 0.39, 0.75),
+    "m": (4.4, 1.85, 1.37, 1200.0, 1.285, 1.203, 0.39, 0.803),
+    "s": (4.25, 1.7, 1.7, 800.0, 1.4126, 1.07, 0.376, 0.7),
+}
+TYPE_KEYS = ["s", "m", "l", "xl", "default"]
+TYPE_PROB = [0.2, 0.3, 0.3, 0.2, 0]
+
+
+def sample_vehicle(vtype, seed):
+    """Randomizable(seed) -> sample_parameters()."""
+    return rng.sample_space(VEHICLE_SPACE[vtype], rng.seeded(seed))
+
+
+def route_for(pgmap, lane_index, seed, final_node=None):
+    """Navigation.update + set_route: destination = random socket of the last block (first block for
+    vehicles born on a negative road), route = first breadth-first path."""
+    start = lane_index[0]
+    if final_node is None:
+        negative = is_negative((lane_index[0], lane_index[1]))
+        block = pgmap.blocks[0] if negative else pgmap.blocks[-1]
+        sockets = list(block.sockets.values())
+        sock = sockets[int(rng.seeded(seed).choice(len(sockets)))]
+        if len(sockets) > 1 and start in (sock.pos[0], sock.pos[1], sock.neg[0], sock.neg[1]):
+            # navigation.py:114-121 loops forever / raises in this case; PG maps never reach it
+            raise ValueError("Can not set a destination!")
+        final_node = sock.neg[1] if negative else sock.pos[1]
+    path = pgmap.net.shortest_path(start, final_node)
+    if len(path) <= 2:
+        path = [lane_index[0], lane_index[1]]
+    return path
+
+
+class VehicleSlot:
+    __slots__ = ("type", "lane", "long", "seed", "params", "idm_seed", "overtake_timer", "checkpoints")
+
+
+class EpisodeTemplate:
+    def __init__(self, seed, density):
+        self.seed = seed
+        self.density = density
+        self.ego_seed = None
+        self.ego_params = None
+        self.ego_checkpoints = None
+        self.block_vehicles = []  # [(trigger_road, [VehicleSlot])], LAST element triggers first
+
+
+def make_episode(pgmap, seed, density=0.1, spawn_lane=(">", ">>", 0)):
+    engine_rs = rng.seeded(seed)
+    traffic_rs = rng.seeded(seed)
+    ep = EpisodeTemplate(seed, density)
+    ep.ego_seed = rng.draw_seed(engine_rs)
+    ep.ego_params = sample_vehicle("default", ep.ego_seed)
+    ep.ego_checkpoints = route_for(pgmap, spawn_lane, seed)
+    if abs(density) < 1e-2:
+        return ep
+    lane_index = {}
+    for (frm, to), lanes in pgmap.net.roads():
+        for i, ln in enumerate(lanes):
+            lane_index[id(ln)] = (frm, to, i)
+    for block in pgmap.blocks[1:]:
+        spawn = block.spawn_lanes()
+        cand = []
+        for lanes in spawn:
+            for ln in lanes:
+                for k in range(int(ln.length / VEHICLE_GAP)):
+                    cand.append((lane_index[id(ln)], k * VEHICLE_GAP))
+        total_length = sum(ln.length for lanes in spawn for ln in lanes)
+        total = int(math.floor(int(math.floor(total_length / VEHICLE_GAP)) * density))
+        traffic_rs.shuffle(cand)
+        slots = []
+        for lane, lon in cand[:min(total, len(cand))]:
+            v = VehicleSlot()
+            v.type = TYPE_KEYS[int(traffic_rs.choice(len(TYPE_KEYS), p=TYPE_PROB))]
+            v.lane, v.long = lane, float(lon)
+            v.seed = rng.draw_seed(engine_rs)
+            v.params = sample_vehicle(v.type, v.seed)
+            v.checkpoints = route_for(pgmap, lane, seed)
+            v.idm_seed = rng.draw_seed(traffic_rs)
+            v.overtake_timer = int(rng.seeded(v.idm_seed).randint(0, 50))
+            slots.append(v)
+        ep.block_vehicles.append((block.pre_socket.pos, slots))
+    ep.block_vehicles.reverse()
+    return ep

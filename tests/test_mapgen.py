@@ -1,0 +1,72 @@
+"""Seed -> map determinism against fixtures made by the unmodified reference (tools/make_golden.py).
+
+Mirrors the reference's own pins: test_loading_map_from_json.py:8-50 (JSON == live BIG) and
+test_random_engine.py:20-52 (same seed => same map)."""
+import pytest
+
+from pgdrive_b200 import mapgen, rng
+
+
+def _lanes(m):
+    return [(f, t, i, ln) for (f, t), ls in m.net.roads() for i, ln in enumerate(ls)]
+
+
+def test_known_seed_hashes():
+    # SURVEY.md appendix A known-answer values, computed with the reference's random_utils
+    assert rng.hash_seed(1000) == 6064680319747761938
+    assert rng.hash_seed(1001) == 12325696033393922275
+    assert rng.draw_seed(rng.seeded(1000)) == 61626
+    assert rng.draw_seed(rng.seeded(1001)) == 40898
+
+
+def test_block_sequences_match_reference(golden_maps):
+    for s, d in golden_maps.items():
+        seq = mapgen.search_sequence(int(s))
+        gold = d["block_sequence"]
+        assert [b["id"] for b in seq] == [b["id"] for b in gold], s
+        for a, b in zip(seq, gold):
+            assert a["pre_block_socket_index"] == b["pre_block_socket_index"]
+            for k, v in b.items():
+                if k not in ("id", "pre_block_socket_index"):
+                    assert float(a[k]) == float(v), (s, k)
+
+
+def test_lanes_match_reference_bit_for_bit(golden_maps):
+    for s, d in golden_maps.items():
+        m = mapgen.generate_map(int(s))
+        mine = _lanes(m)
+        assert len(mine) == len(d["lanes"]), s
+        for (f, t, i, ln), g in zip(mine, d["lanes"]):
+            assert (f, t, i, ln.kind) == (g["frm"], g["to"], g["idx"], g["kind"]), s
+            assert [str(x) for x in ln.line_types] == g["line_types"], (s, f, t, i)
+            colour = ["Y" if abs(c[0] - 1) > 1e-6 else "G" for c in g["line_color"]]
+            assert list(ln.line_color) == colour, (s, f, t, i)
+            a = [ln.sx, ln.sy, ln.ex, ln.ey, ln.length, ln.width, ln.speed_limit]
+            b = g["start"] + g["end"] + [g["length"], g["width"], g["speed_limit"]]
+            if ln.kind == "C":
+                a += [ln.cx, ln.cy, ln.radius, ln.ph0, ln.ph1, ln.dir]
+                b += g["center"] + [g["radius"], g["start_phase"], g["end_phase"], g["direction"]]
+            assert [float(x) for x in a] == [float(x) for x in b], (s, f, t, i)
+
+
+def test_sockets_spawn_lanes_trigger_roads(golden_maps):
+    for s, d in golden_maps.items():
+        m = mapgen.generate_map(int(s))
+        index = {id(ln): [f, t, i] for f, t, i, ln in _lanes(m)}
+        for b, g in zip(m.blocks, d["blocks"]):
+            socks = [dict(index=x.index, pos=list(x.pos), neg=list(x.neg)) for x in b.sockets.values()]
+            assert socks == g["sockets"], (s, b.name)
+            assert [list(r) for r in b.respawn] == g["respawn_roads"], (s, b.name)
+            assert list(b.pre_socket.pos) == g["trigger_road"]
+            if b.idx:
+                assert [[index[id(ln)] for ln in ls] for ls in b.spawn_lanes()] == g["spawn_lanes"], (s, b.name)
+
+
+def test_same_seed_same_map_and_named_sequence():
+    a = mapgen.generate_map(1003)
+    b = mapgen.generate_map(1003)
+    assert [(x.sx, x.sy, x.ex, x.ey) for *_, x in _lanes(a)] == [(x.sx, x.sy, x.ex, x.ey) for *_, x in _lanes(b)]
+    m = mapgen.generate_map(0, sequence="SSS")  # the reference's map="SSS" shorthand
+    assert [b.id for b in m.blocks] == list("ISSS")
+    with pytest.raises(KeyError):
+        mapgen.generate_map(0, sequence="Q")
