@@ -1,0 +1,128 @@
+/* Plain-old-data tables read by the step kernel (and, for checking, by oracle/).
+ *
+ * DATA FORMATS ONLY -- no algorithm lives in this header.  pgdrive_b200/tables.py writes these
+ * records (numpy structured dtypes with the same field order); every id stored in a record is
+ * map-local and PgdMap carries the offsets into the concatenated arrays.
+ *
+ * Reference objects each record flattens (paths under /root/reference/pgdrive):
+ *   PgdLane     StraightLane / CircularLane            component/lane/straight_lane.py:13-67, circular_lane.py:9-67
+ *   PgdRoad     Road + RoadNetwork.graph[from][to]     component/road/road.py:11-48, road_network.py:18-56
+ *   PgdBox      Bullet static primitives of a block    component/blocks/base_block.py:181-463
+ *   PgdSlot     one vehicle as reset() creates it      component/vehicle/base_vehicle.py:292-339, vehicle_type.py:7-78,
+ *                                                      manager/traffic_manager.py:239-290, policy/idm_policy.py:180-188
+ *   PgdEpisode  what reset(force_seed=s) decides       envs/base_env.py:269-301
+ */
+#ifndef PGD_TABLES_H
+#define PGD_TABLES_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { PGD_LANE_STRAIGHT = 0, PGD_LANE_ARC = 1 };
+enum { PGD_BOX_LANE = 0, PGD_BOX_WHITE = 1, PGD_BOX_YELLOW = 2, PGD_BOX_BROKEN = 3, PGD_BOX_SIDEWALK = 4 };
+enum { PGD_MAX_SLOTS = 32, PGD_MAX_GROUPS = 11, PGD_N_RND25 = 16, PGD_OBS_DIM = 274, PGD_LIDAR_BEAMS = 240 };
+
+typedef struct {          /* 64 B */
+  float sx, sy, ex, ey;   /* start / end point of the centre line */
+  float ax, ay;           /* straight: unit direction; arc: centre */
+  float length, width;
+  float radius, ph0;      /* arc: radius, start phase */
+  float dir;              /* arc: +1 clockwise, -1 counter-clockwise; straight: 0 */
+  float heading;          /* straight: atan2(direction) */
+  int32_t road, idx, kind, pad;
+} PgdLane;
+
+typedef struct {          /* 32 B */
+  int32_t first_lane, n_lanes, start_node, end_node, negative, pad[3];
+} PgdRoad;
+
+typedef struct {          /* 32 B: rectangle centre, unit axis, half extents */
+  float cx, cy, ux, uy, hl, hw;
+  int32_t kind, lane;
+} PgdBox;
+
+typedef struct {          /* 64 B */
+  int32_t lane_off, n_lanes, road_off, n_roads, box_off, n_boxes;
+  int32_t cell_off, entry_off, nx, ny;   /* bucket grid: cell_start[cell_off + c], cell_entries[entry_off + k] */
+  float x0, y0, inv_cell;
+  float lane_width;       /* map_config lane_width */
+  int32_t lane_num, pad;
+} PgdMap;
+
+typedef struct {          /* 96 B */
+  float x, y, heading;    /* spawn pose */
+  float length, width, mass, lf, lr;
+  float max_engine, max_brake, max_steer, friction;   /* max_steer in radians */
+  int32_t lane, type, group, drop_substeps, overtake_timer, route_off, route_len, pad;
+  uint8_t rnd25[PGD_N_RND25];   /* successive randint(0, 25) draws of the slot's IDM stream */
+} PgdSlot;
+
+typedef struct {          /* 64 B */
+  int32_t map, seed, slot_off, n_slots, n_groups;
+  int32_t trigger_road[PGD_MAX_GROUPS];  /* group g wakes when the ego is on this road (in order) */
+} PgdEpisode;
+
+/* Host-side view of a whole table set (pointers into caller-owned memory). */
+typedef struct {
+  const PgdMap* maps;            int32_t n_maps;
+  const PgdLane* lanes;          int32_t n_lanes;
+  const PgdRoad* roads;          int32_t n_roads;
+  const PgdBox* boxes;           int32_t n_boxes;
+  const int32_t* cell_start;     int32_t n_cell_start;
+  const int32_t* cell_entries;   int32_t n_cell_entries;
+  const PgdEpisode* episodes;    int32_t n_episodes;
+  const PgdSlot* slots;          int32_t n_slots;
+  const int32_t* route_nodes;    /* route_len node ids per slot */
+  const int32_t* route_roads;    /* road id of (node[k], node[k+1]); -1 after the last node */
+  int32_t n_route;
+} PgdTables;
+
+/* Reward / termination scheme (envs/pgdrive_env.py:93-108) and stepping (envs/base_env.py:33,70). */
+typedef struct {
+  int32_t num_envs;
+  int32_t num_slots;        /* vehicle slots per env: 16 or 32 */
+  int32_t decision_repeat;  /* physics sub-steps per env step (5) */
+  int32_t horizon;          /* 0 = none */
+  float dt;                 /* physics_world_step_size (0.02) */
+  float success_reward, out_of_road_penalty, crash_vehicle_penalty;
+  float driving_reward, speed_reward;
+  float out_of_road_cost, crash_vehicle_cost;
+  int32_t use_lateral, out_of_route_done;
+  int32_t auto_reset;       /* 1: an env that reported done is reset at its next step (action ignored) */
+  int32_t pad;
+} PgdConfig;
+
+/* per-step info (base_vehicle.py:262-272, pgdrive_env.py:165-207, base_env.py:335-339) */
+enum {
+  PGD_F_CRASH_VEHICLE = 1 << 0, PGD_F_OUT_OF_ROAD = 1 << 1, PGD_F_ARRIVE_DEST = 1 << 2, PGD_F_MAX_STEP = 1 << 3,
+  PGD_F_ON_YELLOW = 1 << 4, PGD_F_ON_WHITE = 1 << 5, PGD_F_ON_BROKEN = 1 << 6, PGD_F_CRASH_SIDEWALK = 1 << 7,
+  PGD_F_ON_LANE = 1 << 8, PGD_F_OUT_OF_ROUTE = 1 << 9, PGD_F_WAS_RESET = 1 << 10
+};
+typedef struct {          /* 40 B */
+  float velocity, steering, acceleration, step_energy, episode_energy;
+  float step_reward, episode_reward, cost;
+  int32_t episode_length;
+  uint32_t flags;
+} PgdInfo;
+
+/* Exchange format for pgd_get_state / pgd_set_state (parity debugging; not the device layout). */
+enum { PGD_V_ALIVE = 1, PGD_V_ACTIVE = 2, PGD_V_ON_LANE = 4 };
+typedef struct {          /* 80 B */
+  float x, y, heading, speed;
+  float steer, throttle;
+  float pid_hp, pid_hi, pid_lp, pid_li;   /* heading / lateral PID: last error, summed error */
+  float target_speed;
+  int32_t lane, ck0, ck1, rt_lane, timer, rnd_n, airborne, flags, pad;
+} PgdVehState;
+typedef struct {
+  int32_t episode, next_group, done, ep_len;
+  float prev_steer, prev_throttle, ep_reward, energy;
+  PgdVehState veh[PGD_MAX_SLOTS];
+} PgdEnvState;
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,97 @@
+"""ctypes wrapper of the CPU oracle (oracle/pgd_oracle.c).  TEST INFRASTRUCTURE: imported only by
+tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs."""
+import ctypes as C
+import os
+import subprocess
+import threading
+
+import numpy as np
+
+from pgdrive_b200 import cabi
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "_build", "libpgd_oracle.so")
+
+
+def build(force=False):
+    src = os.path.join(HERE, "pgd_oracle.c")
+    hdr = os.path.join(os.path.dirname(HERE), "include", "pgd_tables.h")
+    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(["make", "-C", HERE, "-B"], stdout=subprocess.DEVNULL)
+    return LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(LIB)
+        vp, i32 = C.c_void_p, C.c_int32
+        L.orc_create.restype = vp
+        L.orc_create.argtypes = [C.POINTER(cabi.PgdTables), C.POINTER(cabi.PgdConfig)]
+        L.orc_destroy.argtypes = [vp]
+        L.orc_reset.argtypes = [vp, i32, i32, vp, vp]
+        L.orc_step.argtypes = [vp, i32, vp, vp, vp, vp, vp]
+        L.orc_step_range.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp]
+        L.orc_get_state.argtypes = [vp, i32, vp]
+        L.orc_set_state.argtypes = [vp, i32, vp]
+        L.orc_lane_local.argtypes = [vp, C.c_float, C.c_float, vp]
+        L.orc_lane_position.argtypes = [vp, C.c_float, C.c_float, vp]
+        L.orc_lane_heading_at.argtypes = [vp, C.c_float]
+        L.orc_lane_heading_at.restype = C.c_float
+        L.orc_ray_rect.argtypes = [C.c_float] * 9
+        L.orc_ray_rect.restype = C.c_float
+        _lib = L
+    return _lib
+
+
+class Oracle:
+    """N independent environments stepped one after the other on the CPU."""
+    def __init__(self, T, num_envs, **cfg):
+        self.L = lib()
+        self.tables, self._keep = cabi.pack_tables(T)
+        self.cfg = cabi.make_config(num_envs, **cfg)
+        self.n = num_envs
+        self.h = self.L.orc_create(C.byref(self.tables), C.byref(self.cfg))
+        self.obs = np.zeros((num_envs, cabi.OBS_DIM), np.float32)
+        self.reward = np.zeros(num_envs, np.float32)
+        self.done = np.zeros(num_envs, np.uint8)
+        self.info = np.zeros(num_envs, cabi.INFO_DT)
+
+    def close(self):
+        if self.h:
+            self.L.orc_destroy(self.h)
+            self.h = None
+
+    def reset(self, env_ids, episode_ids):
+        for e, ep in zip(env_ids, episode_ids):
+            self.L.orc_reset(self.h, int(e), int(ep), self.obs[e].ctypes.data, self.info[e:e + 1].ctypes.data)
+        return self.obs
+
+    def step(self, actions, threads=1):
+        a = np.ascontiguousarray(actions, np.float32).reshape(self.n, 2)
+        args = (a.ctypes.data, self.obs.ctypes.data, self.reward.ctypes.data, self.done.ctypes.data,
+                self.info.ctypes.data)
+        if threads <= 1:
+            self.L.orc_step_range(self.h, 0, self.n, *args)
+        else:  # ctypes drops the GIL during the call
+            cuts = np.linspace(0, self.n, threads + 1).astype(int)
+            ts = [
+                threading.Thread(target=self.L.orc_step_range, args=(self.h, int(cuts[i]), int(cuts[i + 1])) + args)
+                for i in range(threads)
+            ]
+            [t.start() for t in ts]
+            [t.join() for t in ts]
+        return self.obs, self.reward, self.done, self.info
+
+    def get_state(self, env):
+        s = np.zeros(1, cabi.ENV_STATE_DT)
+        self.L.orc_get_state(self.h, int(env), s.ctypes.data)
+        return s
+
+    def set_state(self, env, s):
+        s = np.ascontiguousarray(s)
+        self.L.orc_set_state(self.h, int(env), s.ctypes.data)
