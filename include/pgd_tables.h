@@ -114,7 +114,8 @@ typedef struct {          /* 80 B */
   float steer, throttle;
   float pid_hp, pid_hi, pid_lp, pid_li;   /* heading / lateral PID: last error, summed error */
   float target_speed;
-  int32_t lane, ck0, ck1, rt_lane, timer, rnd_n, airborne, flags, pad;
+  int32_t lane, ck0, ck1, rt_lane, timer, rnd_n, airborne, flags;
+  float yaw_rate;
 } PgdVehState;
 typedef struct {
   int32_t episode, next_group, done, ep_len;

@@ -1,0 +1,70 @@
+/* C-ABI of the B200 batched driving simulator: the drop-in boundary for PGDriveEnv's reset/step.
+ *
+ * The reference's only native boundary is the Cython module pgdrive.cutils (cutils.pyx:60-142,
+ * cutils_perceive: one lidar sweep that calls back into Python-wrapped Bullet once per ray).  A C
+ * replacement for that op alone cannot be faster than its per-ray call-backs, so the boundary is moved
+ * up to the environment step.  Each entry point names the reference interface it replaces
+ * (paths under /root/reference/pgdrive).
+ *
+ * Conventions: every function returns 0 on success or a negative error code; pgd_last_error() gives
+ * the message of the calling thread's last failure.  One host thread per handle; handles are
+ * independent (one per GPU).  All device work is enqueued on the caller's CUDA stream (cudaStream_t
+ * passed as void*, NULL = default stream) and the *_dev calls do not synchronise.  Pointers are
+ * borrowed for the duration of the call only.  No torch types appear here.
+ */
+#ifndef PGDRIVE_B200_H
+#define PGDRIVE_B200_H
+#include <stdint.h>
+
+#include "pgd_tables.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct PgdHandle PgdHandle;
+
+/* engine/engine_utils.py:8-15 initialize_engine + envs/base_env.py:166-178 lazy_init: allocate the
+ * structure-of-arrays state of cfg->num_envs environments x cfg->num_slots vehicle slots on `device`. */
+int pgd_create(const PgdConfig* cfg, int device, PgdHandle** out);
+
+/* envs/base_env.py:402-407 close() */
+int pgd_destroy(PgdHandle* h);
+
+/* manager/map_manager.py:98-155 update_map (map cache) + manager/traffic_manager.py:239-290: upload
+ * maps and per-seed episode templates (host pointers; copied to the device before returning). */
+int pgd_load_tables(PgdHandle* h, const PgdTables* tables);
+
+/* envs/base_env.py:269-301 reset(force_seed): environments env_ids[i] (host int32[n]) restart on episode
+ * template episode_ids[i]; their rows of obs_dev [num_envs, 274] f32 (and info_dev, may be NULL) are
+ * rewritten with the reset observation.  env_ids == NULL means environments 0..n-1. */
+int pgd_reset(PgdHandle* h, const int32_t* env_ids, const int32_t* episode_ids, int32_t n, float* obs_dev,
+              PgdInfo* info_dev, void* stream);
+
+/* envs/base_env.py:184-224,303-344 step(): one decision step of every environment in ONE kernel launch.
+ * actions_dev [num_envs, 2] f32 (steering, throttle); outputs obs_dev [num_envs, 274] f32,
+ * reward_dev [num_envs] f32, done_dev [num_envs] u8, info_dev [num_envs] PgdInfo (may be NULL). */
+int pgd_step(PgdHandle* h, const float* actions_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev,
+             PgdInfo* info_dev, void* stream);
+
+/* Same step with HOST buffers (the call a gym user makes): actions are staged through pinned memory,
+ * results copied back, and the call returns when they are valid. */
+int pgd_step_host(PgdHandle* h, const float* actions, float* obs, float* reward, uint8_t* done, PgdInfo* info);
+
+/* component/vehicle/base_vehicle.py:683-698 get_state / set_state, for the whole environment (debugging
+ * and parity tests; synchronous). */
+int pgd_get_state(PgdHandle* h, int32_t env, PgdEnvState* out);
+int pgd_set_state(PgdHandle* h, int32_t env, const PgdEnvState* in);
+
+/* measurement helpers */
+int64_t pgd_state_bytes_per_env(PgdHandle* h);   /* bytes of simulator state kept per environment */
+int64_t pgd_launch_count(PgdHandle* h);          /* kernels launched by this handle so far */
+int pgd_set_timing(PgdHandle* h, int32_t on);    /* bracket the step kernel with CUDA events */
+float pgd_last_kernel_ms(PgdHandle* h);          /* duration of the last timed step kernel (syncs) */
+
+const char* pgd_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

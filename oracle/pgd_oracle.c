@@ -37,9 +37,10 @@
 #define IDM_LANE_CHANGE_FREQ 50
 #define IDM_SPEED_INCREASE 10.0f
 #define IDM_MAX_SPEED 100.0f
+#define YAW_TAU 0.1f
 
 typedef struct {
-  float x, y, h, v;
+  float x, y, h, v, w; /* pose, speed [m/s], yaw rate [rad/s] */
   float steer, throttle;
   float hp, hi, lp, li;
   float target_speed;
@@ -442,12 +443,12 @@ static void physics_substep(Veh* v, float dt, int overspeed) {
   }
   float delta = clipf(-v->steer * s->max_steer, -1.4f, 1.4f); /* +steering = left = heading decreases */
   float tb = s->lr / (s->lf + s->lr) * tanf(delta);
-  float sb = tb / sqrtf(1.0f + tb * tb);
-  float yaw = speed * sb / s->lr;
-  if (speed * fabsf(yaw) > mu_g) { /* tyres cannot give more than mu*g of lateral acceleration */
-    yaw = copysignf(mu_g / speed, yaw);
-    sb = yaw * s->lr / speed;
-  }
+  float sb0 = tb / sqrtf(1.0f + tb * tb);
+  /* yaw rate relaxes towards the kinematic-bicycle value (tyre relaxation + yaw inertia, tau = 0.1 s) ... */
+  float yaw = v->w + (speed * sb0 / s->lr - v->w) * (dt / YAW_TAU);
+  /* ... and the tyres cannot give more than mu*g of lateral acceleration */
+  if (speed * fabsf(yaw) > mu_g) yaw = copysignf(mu_g / speed, yaw);
+  float sb = speed > 1e-3f ? clipf(yaw * s->lr / speed, -1.0f, 1.0f) : 0.0f;
   float cb = sqrtf(fmaxf(1.0f - sb * sb, 0.0f));
   float ch = cosf(v->h), sh = sinf(v->h);
   v->x += speed * (ch * cb - sh * sb) * dt;
@@ -455,6 +456,7 @@ static void physics_substep(Veh* v, float dt, int overspeed) {
   float h = v->h + yaw * dt;
   if (h > PI_F) h -= TWO_PI_F;
   if (h < -PI_F) h += TWO_PI_F;
+  v->w = yaw;
   v->h = h;
   v->v = speed;
 }
@@ -573,10 +575,9 @@ static void post_step(Oracle* o, Env* e, float last_x, float last_y, float last_
   obs[4] = clipf((ego->steer / 60.0f + 1.0f) / 2.0f, 0.0f, 1.0f);
   obs[5] = clipf((e->prev_steer + 1.0f) / 2.0f, 0.0f, 1.0f);
   obs[6] = clipf((e->prev_throttle + 1.0f) / 2.0f, 0.0f, 1.0f);
-  {
-    float cb = cosf(ego->h) * cosf(last_h) + sinf(ego->h) * sinf(last_h);
-    obs[7] = clipf(acosf(clipf(cb, 0.0f, 1.0f)) / 0.1f, 0.0f, 1.0f);
-  }
+  /* yaw rate: arccos(clip(cos(angle between headings), 0, 1)) / 0.1 (state_obs.py:87-94).  arccos is
+   * ill-conditioned near 1 in float32, so the identical quantity min(|wrapped heading change|, pi/2) is used. */
+  obs[7] = clipf(fminf(fabsf(wrap_to_pi(ego->h - last_h)), PI_F / 2) / 0.1f, 0.0f, 1.0f);
   navi_info(o, m, ego, cur_road_id, n_ref, obs + 8);
   navi_info(o, m, ego, route_road(o, ego, ego->ck1), n_ref, obs + 13);
   /* 4 nearest vehicles (lidar.py:55-77) */
@@ -804,7 +805,7 @@ void orc_get_state(void* h, int env, PgdEnvState* out) {
     s->pid_hp = v->hp; s->pid_hi = v->hi; s->pid_lp = v->lp; s->pid_li = v->li;
     s->target_speed = v->target_speed;
     s->lane = v->lane; s->ck0 = v->ck0; s->ck1 = v->ck1; s->rt_lane = v->rt_lane;
-    s->timer = v->timer; s->rnd_n = v->rnd_n; s->airborne = v->airborne;
+    s->timer = v->timer; s->rnd_n = v->rnd_n; s->airborne = v->airborne; s->yaw_rate = v->w;
     s->flags = (v->alive ? PGD_V_ALIVE : 0) | (v->active ? PGD_V_ACTIVE : 0) | (v->on_lane ? PGD_V_ON_LANE : 0);
   }
 }
@@ -828,7 +829,7 @@ void orc_set_state(void* h, int env, const PgdEnvState* in) {
     v->hp = s->pid_hp; v->hi = s->pid_hi; v->lp = s->pid_lp; v->li = s->pid_li;
     v->target_speed = s->target_speed;
     v->lane = s->lane; v->ck0 = s->ck0; v->ck1 = s->ck1; v->rt_lane = s->rt_lane;
-    v->timer = s->timer; v->rnd_n = s->rnd_n; v->airborne = s->airborne;
+    v->timer = s->timer; v->rnd_n = s->rnd_n; v->airborne = s->airborne; v->w = s->yaw_rate;
     v->alive = !!(s->flags & PGD_V_ALIVE); v->active = !!(s->flags & PGD_V_ACTIVE);
     v->on_lane = !!(s->flags & PGD_V_ON_LANE);
   }

@@ -22,7 +22,7 @@ VEH_STATE_DT = np.dtype([
     ("x", "f4"), ("y", "f4"), ("heading", "f4"), ("speed", "f4"), ("steer", "f4"), ("throttle", "f4"), ("pid_hp", "f4"),
     ("pid_hi", "f4"), ("pid_lp", "f4"), ("pid_li", "f4"), ("target_speed", "f4"), ("lane", "i4"), ("ck0", "i4"),
     ("ck1", "i4"), ("rt_lane", "i4"), ("timer", "i4"), ("rnd_n", "i4"), ("airborne", "i4"), ("flags", "i4"),
-    ("pad", "i4")
+    ("yaw_rate", "f4")
 ])
 ENV_STATE_DT = np.dtype([
     ("episode", "i4"), ("next_group", "i4"), ("done", "i4"), ("ep_len", "i4"), ("prev_steer", "f4"),

@@ -1,0 +1,1121 @@
+// Fused environment step for sm_100a: one launch advances every environment by one decision step.
+//
+// Thread mapping: V threads (V = vehicle slots per env, 16 or 32) cooperate on one environment; thread s owns
+// vehicle slot s (slot 0 = ego).  A 128-thread CTA therefore holds 8 (V=16) or 4 (V=32) environments.
+// State lives in HBM as structure-of-arrays over the flat index env * V + slot (16-byte vectors, so a warp
+// reads/writes 512 contiguous bytes per field); per-environment poses are mirrored in shared memory for the
+// all-pairs phases (IDM neighbour search, chassis contacts, lidar).  Map tables are read-only and shared by all
+// environments on the same seed, i.e. L2-resident.
+//
+// Phases (reference call stack):
+//   A  load state, or copy the episode template when the env is being reset   base_env.py:269-301
+//   B  ego action clip + traffic trigger                                       env_input_policy.py:17-26, traffic_manager.py:71-89
+//   C  IDM / PID action of every awake traffic vehicle                         idm_policy.py:83-353
+//   D  5 physics sub-steps + chassis contact                                   base_engine.py:206-232, collision_callback.py:7-35
+//   E  localisation, checkpoints, line / sidewalk contacts                     navigation.py:155-344, base_vehicle.py:615-644
+//   F  observation (state, navi, 4 neighbours, 240-beam lidar), reward, done   state_obs.py:58-170, pgdrive_env.py:162-258
+//   G  store state
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <string>
+
+#include "../../include/pgdrive_b200.h"
+
+#define PI_F 3.14159265358979323846f
+#define TWO_PI_F 6.28318530717958647692f
+#define GRAVITY 9.81f
+#define LIDAR_RANGE 50.0f
+#define MAX_SPEED_KMH 80.0f
+#define IDM_MAX_LONG 30.0f
+#define IDM_NORMAL_SPEED 30.0f
+#define IDM_CREEP_SPEED 5.0f
+#define IDM_SAFE_DIST 15.0f
+#define IDM_LANE_CHANGE_FREQ 50
+#define IDM_SPEED_INCREASE 10.0f
+#define IDM_MAX_SPEED 100.0f
+#define YAW_TAU 0.1f
+
+#define CTA_THREADS 128
+#define DONE_PENDING_RESET 2
+
+struct DevTables {
+  const PgdMap* maps;
+  const PgdLane* lanes;
+  const PgdRoad* roads;
+  const PgdBox* boxes;
+  const int32_t* cell_start;
+  const int32_t* cell_entries;
+  const PgdEpisode* episodes;
+  const PgdSlot* slots;
+  const int32_t* route_nodes;
+  const int32_t* route_roads;
+};
+
+// SoA state; index = env * V + slot for the per-slot arrays, env for the per-env ones.
+struct DevState {
+  float4* pose;  // x, y, heading, speed
+  float4* ctrl;  // steer, throttle, heading-PID last error, heading-PID summed error
+  float4* pidl;  // lateral-PID last error, summed error, IDM target speed, yaw rate
+  int4* nav;     // lane, ck0 | ck1 << 16, routing target lane, overtake timer
+  int4* misc;    // rnd draws used, airborne sub-steps left, PGD_V_* flags, -
+  int4* envi;    // episode, next trigger group, done, episode length
+  float4* envf;  // previous steering, previous throttle, episode reward, episode energy
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float clipf(float a, float lo, float hi) { return fminf(fmaxf(a, lo), hi); }
+
+__device__ __forceinline__ float wrap_to_pi(float x) {
+  float m = fmodf(x + PI_F, TWO_PI_F);
+  if (m < 0.0f) m += TWO_PI_F;
+  return m - PI_F;
+}
+
+struct Lane {  // registers copy of a PgdLane (4 x 16 B loads)
+  float sx, sy, ex, ey, ax, ay, length, width, radius, ph0, dir, heading;
+  int road, idx, kind;
+};
+
+__device__ __forceinline__ Lane load_lane(const PgdLane* p) {
+  const float4* q = reinterpret_cast<const float4*>(p);
+  float4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+  int4 d = __ldg(reinterpret_cast<const int4*>(q + 3));
+  Lane l;
+  l.sx = a.x; l.sy = a.y; l.ex = a.z; l.ey = a.w;
+  l.ax = b.x; l.ay = b.y; l.length = b.z; l.width = b.w;
+  l.radius = c.x; l.ph0 = c.y; l.dir = c.z; l.heading = c.w;
+  l.road = d.x; l.idx = d.y; l.kind = d.z;
+  return l;
+}
+
+__device__ __forceinline__ void lane_local(const Lane& l, float x, float y, float& lon, float& lat) {
+  if (l.kind == PGD_LANE_STRAIGHT) {
+    float dx = x - l.sx, dy = y - l.sy;
+    lon = dx * l.ax + dy * l.ay;
+    lat = dx * -l.ay + dy * l.ax;
+  } else {
+    float dx = x - l.ax, dy = y - l.ay;
+    float phi = atan2f(dy, dx);
+    phi = l.ph0 + wrap_to_pi(phi - l.ph0);
+    float r = sqrtf(dx * dx + dy * dy);
+    lon = l.dir * (phi - l.ph0) * l.radius;
+    lat = l.dir * (l.radius - r);
+  }
+}
+
+__device__ __forceinline__ void lane_position(const Lane& l, float lon, float lat, float& x, float& y) {
+  if (l.kind == PGD_LANE_STRAIGHT) {
+    x = l.sx + lon * l.ax + lat * -l.ay;
+    y = l.sy + lon * l.ay + lat * l.ax;
+  } else {
+    float phi = l.dir * lon / l.radius + l.ph0;
+    float r = l.radius - lat * l.dir;
+    float s, c;
+    sincosf(phi, &s, &c);
+    x = l.ax + r * c;
+    y = l.ay + r * s;
+  }
+}
+
+__device__ __forceinline__ float lane_heading_at(const Lane& l, float lon) {
+  if (l.kind == PGD_LANE_STRAIGHT) return l.heading;
+  float phi = l.dir * lon / l.radius + l.ph0;
+  return phi + PI_F / 2 * l.dir;
+}
+
+__device__ __forceinline__ bool precedes(float ex, float ey, float sx, float sy) {
+  float dx = ex - sx, dy = ey - sy;
+  return sqrtf(dx * dx + dy * dy) < 1e-1f;
+}
+
+struct Rect {
+  float cx, cy, ux, uy, hl, hw;
+};
+
+__device__ __forceinline__ bool rect_overlap(const Rect& a, const Rect& b) {
+  float dx = b.cx - a.cx, dy = b.cy - a.cy;
+  float c = fabsf(a.ux * b.ux + a.uy * b.uy);
+  float s = fabsf(a.ux * b.uy - a.uy * b.ux);
+  if (fabsf(dx * a.ux + dy * a.uy) > a.hl + b.hl * c + b.hw * s) return false;
+  if (fabsf(-dx * a.uy + dy * a.ux) > a.hw + b.hl * s + b.hw * c) return false;
+  if (fabsf(dx * b.ux + dy * b.uy) > b.hl + a.hl * c + a.hw * s) return false;
+  if (fabsf(-dx * b.uy + dy * b.ux) > b.hw + a.hl * s + a.hw * c) return false;
+  return true;
+}
+
+__device__ __forceinline__ float ray_rect(float ox, float oy, float dx, float dy, const Rect& r) {
+  float px = ox - r.cx, py = oy - r.cy;
+  float lo0 = px * r.ux + py * r.uy, lo1 = -px * r.uy + py * r.ux;
+  float ld0 = dx * r.ux + dy * r.uy, ld1 = -dx * r.uy + dy * r.ux;
+  float t0 = 0.0f, t1 = 1.0f;
+  if (fabsf(ld0) < 1e-12f) {
+    if (fabsf(lo0) > r.hl) return 1.0f;
+  } else {
+    float inv = 1.0f / ld0;
+    float ta = (-r.hl - lo0) * inv, tb = (r.hl - lo0) * inv;
+    t0 = fmaxf(t0, fminf(ta, tb));
+    t1 = fminf(t1, fmaxf(ta, tb));
+    if (t0 > t1) return 1.0f;
+  }
+  if (fabsf(ld1) < 1e-12f) {
+    if (fabsf(lo1) > r.hw) return 1.0f;
+  } else {
+    float inv = 1.0f / ld1;
+    float ta = (-r.hw - lo1) * inv, tb = (r.hw - lo1) * inv;
+    t0 = fmaxf(t0, fminf(ta, tb));
+    t1 = fminf(t1, fmaxf(ta, tb));
+    if (t0 > t1) return 1.0f;
+  }
+  return t0;
+}
+
+__device__ __forceinline__ void project(float hx, float hy, float vx, float vy, float& fwd, float& side) {
+  const float n = 1.0f + 1e-6f;
+  fwd = (vx * hx + vy * hy) / n;
+  side = (vx * -hy + vy * hx) / n;
+}
+
+__device__ __forceinline__ float pid(float& p_err, float& i_err, float kp, float ki, float kd, float err) {
+  i_err += err;
+  float d = err - p_err;
+  p_err = err;
+  return -kp * p_err - ki * i_err - kd * d;
+}
+
+// Per-environment shared mirror of what the all-pairs phases need from every slot.
+template <int V>
+struct EnvShared {
+  float x[V], y[V], h[V], v[V];    // pose at the start of the step (IDM) / current (contacts, lidar)
+  float ux[V], uy[V];              // heading unit vector
+  float hl[V], hw[V];              // chassis half extents
+  int lane[V];
+  int alive[V];
+  float sx[V], sy[V], ex[V], ey[V], llen[V];  // start / end / length of the lane each vehicle is on
+  float navi[10];
+  float red[4];
+  int ired[4];
+};
+
+struct Sub {  // what one physics sub-step needs, hoisted out of the sub-step loop
+  float accel;      // >0: engine acceleration [m/s^2]; else brake
+  float brake_dv;   // speed removed per sub-step when braking
+  float sb;         // sin(slip angle) of the kinematic bicycle
+  float mu_g;
+  float lr;
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+template <int V>
+__global__ void __launch_bounds__(CTA_THREADS)
+pgd_step_kernel(DevTables T, DevState S, PgdConfig cfg, int mode, const float2* __restrict__ actions,
+                float* __restrict__ obs, float* __restrict__ reward, uint8_t* __restrict__ done,
+                PgdInfo* __restrict__ info) {
+  constexpr int ENVS_PER_CTA = CTA_THREADS / V;
+  __shared__ EnvShared<V> sh_all[ENVS_PER_CTA];
+  const int slot = threadIdx.x % V;
+  const int env_in_cta = threadIdx.x / V;
+  const int env_raw = blockIdx.x * ENVS_PER_CTA + env_in_cta;
+  const bool env_valid = env_raw < cfg.num_envs;
+  const int env = env_valid ? env_raw : cfg.num_envs - 1;  // clamp: surplus threads shadow the last env, no stores
+  EnvShared<V>& sh = sh_all[env_in_cta];
+  const unsigned lane_id = threadIdx.x & 31;
+  const unsigned group_mask = (V == 32) ? 0xffffffffu : (0xffffu << (lane_id & 16));
+  const int gi = env * V + slot;
+
+  // ---- phase A: load ------------------------------------------------------------------------------------------
+  int4 envi = S.envi[env];
+  float4 envf = S.envf[env];
+  const bool pending = envi.z == DONE_PENDING_RESET;
+  bool fresh;  // this call (re)starts the episode instead of stepping it
+  if (mode == 1) {
+    fresh = pending;
+  } else {
+    fresh = pending || (cfg.auto_reset && envi.z == 1);
+  }
+  const bool skip = !env_valid || (mode == 1 && !pending);  // nothing is written for skipped envs
+
+  const PgdEpisode* ep = T.episodes + envi.x;
+  const int map_id = __ldg(&ep->map);
+  const int n_slots = __ldg(&ep->n_slots);
+  const int n_groups = __ldg(&ep->n_groups);
+  const PgdMap mp = T.maps[map_id];
+  const PgdLane* lanes = T.lanes + mp.lane_off;
+  const PgdRoad* roads = T.roads + mp.road_off;
+  const PgdBox* boxes = T.boxes + mp.box_off;
+  const bool has_slot = slot < n_slots;
+  const PgdSlot* tpl = T.slots + __ldg(&ep->slot_off) + (has_slot ? slot : 0);
+  // template constants of this slot
+  const float4 t0 = __ldg(reinterpret_cast<const float4*>(tpl));       // x, y, heading, length
+  const float4 t1 = __ldg(reinterpret_cast<const float4*>(tpl) + 1);   // width, mass, lf, lr
+  const float4 t2 = __ldg(reinterpret_cast<const float4*>(tpl) + 2);   // max_engine, max_brake, max_steer, friction
+  const int4 t3 = __ldg(reinterpret_cast<const int4*>(tpl) + 3);       // lane, type, group, drop_substeps
+  const int4 t4 = __ldg(reinterpret_cast<const int4*>(tpl) + 4);       // overtake_timer, route_off, route_len, pad
+  const int route_off = t4.y, route_len = t4.z;
+  const int32_t* rnodes = T.route_nodes + route_off;
+  const int32_t* rroads = T.route_roads + route_off;
+
+  float x, y, h, v, yaw_rate, steer, throttle, hp, hi, lp, li, target_speed;
+  int lane, ck0, ck1, rt_lane, timer, rnd_n, airborne, vflags;
+  if (fresh) {
+    x = t0.x; y = t0.y; h = t0.z; v = 0.0f; yaw_rate = 0.0f;
+    steer = throttle = hp = hi = lp = li = 0.0f;
+    target_speed = IDM_NORMAL_SPEED;
+    lane = t3.x; ck0 = 0; ck1 = route_len > 2 ? 1 : 0; rt_lane = -1;
+    timer = t4.x; rnd_n = 0; airborne = t3.w;
+    vflags = has_slot ? (PGD_V_ALIVE | PGD_V_ON_LANE | (slot == 0 ? PGD_V_ACTIVE : 0)) : 0;
+    envi.y = 0; envi.z = 0; envi.w = 0;
+    envf = make_float4(0.f, 0.f, 0.f, 0.f);
+  } else {
+    float4 p = S.pose[gi], c = S.ctrl[gi], q = S.pidl[gi];
+    int4 n = S.nav[gi], m = S.misc[gi];
+    x = p.x; y = p.y; h = p.z; v = p.w;
+    steer = c.x; throttle = c.y; hp = c.z; hi = c.w;
+    lp = q.x; li = q.y; target_speed = q.z; yaw_rate = q.w;
+    lane = n.x; ck0 = n.y & 0xffff; ck1 = n.y >> 16; rt_lane = n.z; timer = n.w;
+    rnd_n = m.x; airborne = m.y; vflags = m.z;
+  }
+  const float half_l = t0.w * 0.5f, half_w = t1.x * 0.5f;
+  bool alive = (vflags & PGD_V_ALIVE) != 0;
+  bool active = (vflags & PGD_V_ACTIVE) != 0;
+
+  // publish start-of-step poses
+  {
+    float s, c;
+    sincosf(h, &s, &c);
+    sh.x[slot] = x; sh.y[slot] = y; sh.h[slot] = h; sh.v[slot] = v;
+    sh.ux[slot] = c; sh.uy[slot] = s;
+    sh.hl[slot] = half_l; sh.hw[slot] = half_w;
+    sh.lane[slot] = lane; sh.alive[slot] = alive;
+    if (alive) {
+      const Lane l = load_lane(lanes + lane);
+      sh.sx[slot] = l.sx; sh.sy[slot] = l.sy; sh.ex[slot] = l.ex; sh.ey[slot] = l.ey; sh.llen[slot] = l.length;
+    }
+  }
+  __syncwarp(group_mask);
+
+  const float last_x = sh.x[0], last_y = sh.y[0], last_h = sh.h[0];
+  int crash = 0;
+
+  if (!fresh && !skip) {
+    // ---- phase B: ego action + traffic trigger --------------------------------------------------------------
+    if (slot == 0) {
+      float2 a = actions[env];
+      envf.x = steer;  // last_current_action[0] after the push
+      envf.y = throttle;
+      steer = clipf(a.x, -1.0f, 1.0f);  // fminf/fmaxf drop NaN -> -1, like the compiled cutils_clip
+      throttle = clipf(a.y, -1.0f, 1.0f);
+    }
+    if (envi.y < n_groups) {
+      const int ego_road = __ldg(&lanes[sh.lane[0]].road);
+      if (ego_road == __ldg(&ep->trigger_road[envi.y])) {
+        if (has_slot && t3.z == envi.y) active = true;
+        envi.y += 1;
+      }
+    }
+
+    // ---- phase C: IDM ------------------------------------------------------------------------------------------
+    if (alive && active && slot != 0) {
+      const int cur_road_id = __ldg(&rroads[ck0]);
+      const PgdRoad cur_road = roads[cur_road_id];
+      bool ok;
+      if (rt_lane < 0) {
+        rt_lane = lane;
+        ok = __ldg(&lanes[rt_lane].road) == cur_road_id;
+      } else if (__ldg(&lanes[rt_lane].road) != cur_road_id) {
+        ok = false;
+        const float rex = __ldg(&lanes[rt_lane].ex), rey = __ldg(&lanes[rt_lane].ey);
+        for (int k = 0; k < cur_road.n_lanes; ++k) {
+          const PgdLane* c = lanes + cur_road.first_lane + k;
+          if (precedes(rex, rey, __ldg(&c->sx), __ldg(&c->sy))) {
+            rt_lane = cur_road.first_lane + k;
+            ok = true;
+            break;
+          }
+        }
+      } else if (__ldg(&lanes[lane].road) == cur_road_id && rt_lane != lane) {
+        rt_lane = lane;
+        timer = reinterpret_cast<const uint8_t*>(tpl)[80 + (rnd_n % PGD_N_RND25)];
+        rnd_n++;
+        ok = true;
+      } else {
+        ok = true;
+      }
+      // front / back search on the routing lane and (when routed) its two neighbours
+      const Lane rl = load_lane(lanes + rt_lane);
+      int cand[3] = {-1, rt_lane, -1};
+      if (ok) {
+        const PgdRoad rr = roads[rl.road];
+        if (rl.idx > 0) cand[0] = rr.first_lane + rl.idx - 1;
+        if (rl.idx + 1 < rr.n_lanes) cand[2] = rr.first_lane + rl.idx + 1;
+      }
+      int front[3], back[3];
+      float fdist[3], bdist[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        front[i] = back[i] = -1;
+        fdist[i] = bdist[i] = IDM_MAX_LONG;
+        if (cand[i] < 0) continue;
+        const Lane l = (i == 1) ? rl : load_lane(lanes + cand[i]);
+        float cur_long, lat;
+        lane_local(l, x, y, cur_long, lat);
+        const float left_long = l.length - cur_long;
+        bool found_front = false, found_back = false;
+        for (int j = 0; j < n_slots; ++j) {
+          if (j == slot || !sh.alive[j]) continue;
+          const float ox = sh.x[j], oy = sh.y[j];
+          const float ddx = ox - x, ddy = oy - y;
+          if (!(ddx * ddx + ddy * ddy < LIDAR_RANGE * LIDAR_RANGE)) continue;
+          if (sh.lane[j] == cand[i]) {
+            float lg;
+            lane_local(l, ox, oy, lg, lat);
+            lg -= cur_long;
+            if (fdist[i] > lg && lg > 0.0f) { fdist[i] = lg; front[i] = j; found_front = true; }
+            if (lg < 0.0f && fabsf(lg) < bdist[i]) { bdist[i] = fabsf(lg); back[i] = j; found_back = true; }
+          } else if (!found_front && precedes(l.ex, l.ey, sh.sx[j], sh.sy[j])) {
+            const Lane ol = load_lane(lanes + sh.lane[j]);
+            float lg;
+            lane_local(ol, ox, oy, lg, lat);
+            lg += left_long;
+            if (fdist[i] > lg && lg > 0.0f) { fdist[i] = lg; front[i] = j; }
+          } else if (!found_back && precedes(sh.ex[j], sh.ey[j], l.sx, l.sy)) {
+            const Lane ol = load_lane(lanes + sh.lane[j]);
+            float lg;
+            lane_local(ol, ox, oy, lg, lat);
+            lg = ol.length - lg + cur_long;
+            if (bdist[i] > lg) { bdist[i] = lg; back[i] = j; }
+          }
+        }
+      }
+      int front_obj = front[1], steer_lane = rt_lane;
+      float front_dist = fdist[1];
+      if (ok) {  // lane_change_policy
+        const int n_cur = cur_road.n_lanes;
+        int lo = 0, hi_idx = n_cur - 1;
+        bool decided = false;
+        const int idx = rl.idx;
+        if (ck0 != ck1) {
+          const PgdRoad nxt = roads[__ldg(&rroads[ck1])];
+          const int diff = n_cur - nxt.n_lanes;
+          if (diff > 0) {
+            const PgdLane* c0 = lanes + cur_road.first_lane;
+            const PgdLane* n0 = lanes + nxt.first_lane;
+            if (precedes(__ldg(&c0->ex), __ldg(&c0->ey), __ldg(&n0->sx), __ldg(&n0->sy))) {
+              lo = 0; hi_idx = nxt.n_lanes - 1;
+            } else {
+              lo = diff; hi_idx = n_cur - 1;
+            }
+            if (idx < lo || idx > hi_idx) {
+              decided = true;
+              const int side = idx > hi_idx ? 0 : 2;
+              if (bdist[side] < IDM_SAFE_DIST || fdist[side] < 5.0f) {
+                target_speed = IDM_CREEP_SPEED;
+              } else {
+                target_speed = IDM_NORMAL_SPEED;
+                front_obj = front[side];
+                front_dist = fdist[side];
+                steer_lane = cur_road.first_lane + idx + (side == 0 ? -1 : 1);
+              }
+            }
+          }
+        }
+        if (!decided) {
+          const float my_speed = clipf(v * 3.6f, 0.0f, 100000.0f);
+          if (fabsf(my_speed - IDM_NORMAL_SPEED) > 3.0f && front[1] >= 0 &&
+              fabsf(clipf(sh.v[front[1]] * 3.6f, 0.0f, 100000.0f) - IDM_NORMAL_SPEED) > 3.0f &&
+              timer > IDM_LANE_CHANGE_FREQ) {
+            float side_speed[3] = {0.f, 0.f, 0.f};
+            bool side_ok[3] = {false, false, false};
+#pragma unroll
+            for (int sd = 0; sd < 3; sd += 2) {
+              if (front[sd] >= 0) {
+                side_speed[sd] = clipf(sh.v[front[sd]] * 3.6f, 0.0f, 100000.0f);
+                side_ok[sd] = true;
+              } else if (cand[sd] >= 0 && fdist[sd] > IDM_SAFE_DIST && bdist[sd] > IDM_SAFE_DIST) {
+                side_speed[sd] = IDM_MAX_SPEED;
+                side_ok[sd] = true;
+              }
+            }
+            const float front_speed = clipf(sh.v[front[1]] * 3.6f, 0.0f, 100000.0f);
+            if (side_ok[0] && side_speed[0] - front_speed > IDM_SPEED_INCREASE && idx - 1 >= lo && idx - 1 <= hi_idx) {
+              decided = true;
+              front_obj = front[0]; front_dist = fdist[0];
+              steer_lane = cur_road.first_lane + idx - 1;
+            } else if (side_ok[2] && side_speed[2] - front_speed > IDM_SPEED_INCREASE && idx + 1 >= lo &&
+                       idx + 1 <= hi_idx) {
+              decided = true;
+              front_obj = front[2]; front_dist = fdist[2];
+              steer_lane = cur_road.first_lane + idx + 1;
+            }
+          }
+        }
+        if (!decided) {
+          target_speed = IDM_NORMAL_SPEED;
+          timer += 1;
+        }
+      }
+      // steering_control
+      {
+        const Lane tl = (steer_lane == rt_lane) ? rl : load_lane(lanes + steer_lane);
+        float lon, lat;
+        lane_local(tl, x, y, lon, lat);
+        const float lane_heading = lane_heading_at(tl, lon + 1.0f);
+        float st = pid(hp, hi, 1.7f, 0.01f, 3.5f, wrap_to_pi(lane_heading - h));
+        st += pid(lp, li, 0.3f, 0.002f, 0.05f, -lat);
+        steer = st;
+      }
+      // acceleration
+      {
+        const float sp = clipf(v * 3.6f, 0.0f, 100000.0f);
+        float acc = 1.0f - powf(fmaxf(sp, 0.0f) / target_speed, 10.0f);
+        if (front_obj >= 0) {
+          const float hx = sh.ux[slot], hy = sh.uy[slot];
+          const float fs = clipf(sh.v[front_obj] * 3.6f, 0.0f, 100000.0f);
+          const float dvx = sp * hx - fs * sh.ux[front_obj], dvy = sp * hy - fs * sh.uy[front_obj];
+          const float dv = dvx * hx + dvy * hy;
+          const float d_star = 10.0f + sp * 1.5f + sp * dv / (2.0f * sqrtf(5.0f));
+          float d = front_dist;
+          if (!(fabsf(d) > 1e-2f)) d = d > 0.0f ? 1e-2f : -1e-2f;
+          const float ratio = d_star / d;
+          acc -= ratio * ratio;
+        }
+        throttle = acc;
+      }
+    }
+
+    // ---- phase D: physics sub-steps + chassis contact ----------------------------------------------------------
+    Sub sub;
+    {
+      sub.mu_g = t2.w * GRAVITY;
+      sub.lr = t1.w;
+      const bool overspeed = clipf(v * 3.6f, 0.0f, 100000.0f) > MAX_SPEED_KMH;
+      if (throttle > 0.0f && !overspeed) {
+        sub.accel = fminf(4.0f * t2.x * throttle / t1.y, sub.mu_g);
+        sub.brake_dv = 0.0f;
+      } else {
+        sub.accel = 0.0f;
+        const float imp = throttle >= 0.0f ? 2.0f : -throttle * t2.y;
+        sub.brake_dv = fminf(4.0f * imp / t1.y, sub.mu_g * cfg.dt);
+      }
+      const float delta = clipf(-steer * t2.z, -1.4f, 1.4f);
+      const float tb = t1.w / (t1.z + t1.w) * tanf(delta);
+      sub.sb = tb / sqrtf(1.0f + tb * tb);
+    }
+    for (int k = 0; k < cfg.decision_repeat; ++k) {
+      if (alive) {
+        if (airborne > 0) {
+          airborne--;
+        } else {
+          float speed = v;
+          if (sub.accel > 0.0f) speed += sub.accel * cfg.dt;
+          else speed = fmaxf(speed - sub.brake_dv, 0.0f);
+          float yaw = yaw_rate + (speed * sub.sb / sub.lr - yaw_rate) * (cfg.dt / YAW_TAU);
+          if (speed * fabsf(yaw) > sub.mu_g) yaw = copysignf(sub.mu_g / speed, yaw);
+          const float sb = speed > 1e-3f ? clipf(yaw * sub.lr / speed, -1.0f, 1.0f) : 0.0f;
+          const float cb = sqrtf(fmaxf(1.0f - sb * sb, 0.0f));
+          float sh_, ch_;
+          sincosf(h, &sh_, &ch_);
+          x += speed * (ch_ * cb - sh_ * sb) * cfg.dt;
+          y += speed * (sh_ * cb + ch_ * sb) * cfg.dt;
+          float nh = h + yaw * cfg.dt;
+          if (nh > PI_F) nh -= TWO_PI_F;
+          if (nh < -PI_F) nh += TWO_PI_F;
+          yaw_rate = yaw;
+          h = nh;
+          v = speed;
+        }
+      }
+      // contact of every chassis with the ego's
+      float s, c;
+      sincosf(h, &s, &c);
+      if (slot == 0) { sh.x[0] = x; sh.y[0] = y; sh.ux[0] = c; sh.uy[0] = s; }
+      __syncwarp(group_mask);
+      if (alive && slot != 0) {
+        Rect me = {x, y, c, s, half_l, half_w};
+        Rect eg = {sh.x[0], sh.y[0], sh.ux[0], sh.uy[0], sh.hl[0], sh.hw[0]};
+        if (rect_overlap(eg, me)) crash = 1;
+      }
+      __syncwarp(group_mask);
+    }
+    crash = (__ballot_sync(group_mask, crash) & group_mask) != 0;
+  }
+
+  // ---- phase E: after_step -------------------------------------------------------------------------------------
+  float hs, hc;
+  sincosf(h, &hs, &hc);
+  // localisation of every moving vehicle (ego always; traffic once awake)
+  if (alive && active) {
+    const int cur_road = __ldg(&rroads[ck0]);
+    const int next_road = (ck0 == ck1) ? -1 : __ldg(&rroads[ck1]);
+    int first_any = -1, first_cur = -1, first_next = -1;
+    const int cx = (int)floorf((x - mp.x0) * mp.inv_cell), cy = (int)floorf((y - mp.y0) * mp.inv_cell);
+    if (cx >= 0 && cy >= 0 && cx < mp.nx && cy < mp.ny) {
+      const int cell = mp.cell_off + cy * mp.nx + cx;
+      const int b0 = __ldg(&T.cell_start[cell]), b1 = __ldg(&T.cell_start[cell + 1]);
+      const int32_t* ent = T.cell_entries + mp.entry_off;
+      for (int k = b0; k < b1; ++k) {
+        const int b = __ldg(&ent[k]);
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(boxes + b));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(boxes + b) + 1);  // hl, hw, kind, lane
+        if (__float_as_int(g1.z) != PGD_BOX_LANE) continue;
+        const float dx = x - g0.x, dy = y - g0.y;
+        if (!(fabsf(dx * g0.z + dy * g0.w) <= g1.x && fabsf(-dx * g0.w + dy * g0.z) <= g1.y)) continue;
+        const int bl = __float_as_int(g1.w);
+        const Lane l = load_lane(lanes + bl);
+        float lon, lat;
+        lane_local(l, x, y, lon, lat);
+        const float lh = lane_heading_at(l, lon);
+        float ls, lc;
+        sincosf(lh, &ls, &lc);
+        if (!(lc * hc + ls * hs > 0.0f)) continue;
+        if (first_any < 0) first_any = bl;
+        if (first_cur < 0 && l.road == cur_road) first_cur = bl;
+        if (first_next < 0 && l.road == next_road) first_next = bl;
+      }
+    }
+    int nl = first_cur >= 0 ? first_cur : (first_next >= 0 ? first_next : first_any);
+    bool on_lane = true;
+    if (nl < 0) { on_lane = false; nl = lane; }
+    lane = nl;
+    if (ck0 != ck1) {
+      const Lane l = load_lane(lanes + lane);
+      float lon, lat;
+      lane_local(l, x, y, lon, lat);
+      const int start = __ldg(&roads[l.road].start_node);
+      if (lon < 5.0f) {
+        for (int j = ck1; j < route_len - 1; ++j) {
+          if (__ldg(&rnodes[j]) == start) {
+            ck0 = j;
+            ck1 = (j + 1 == route_len - 1) ? j : j + 1;
+            break;
+          }
+        }
+      }
+    }
+    vflags = on_lane ? (vflags | PGD_V_ON_LANE) : (vflags & ~PGD_V_ON_LANE);
+    if (slot != 0 && !on_lane) alive = false;  // traffic_manager.py:91-109
+  }
+  // publish end-of-step chassis rectangles
+  sh.x[slot] = x; sh.y[slot] = y; sh.h[slot] = h; sh.v[slot] = v;
+  sh.ux[slot] = hc; sh.uy[slot] = hs;
+  sh.alive[slot] = alive;
+  if (slot == 0) { sh.lane[0] = lane; sh.ired[0] = ck0; sh.ired[1] = ck1; sh.ired[2] = vflags; }
+  __syncwarp(group_mask);
+
+  // ego chassis vs line ghosts / sidewalks: the ego's bucket is scanned by all V threads
+  const float ex_ = sh.x[0], ey_ = sh.y[0], eux = sh.ux[0], euy = sh.uy[0], eh = sh.h[0], ev = sh.v[0];
+  uint32_t flags = 0;
+  {
+    const Rect er = {ex_, ey_, eux, euy, sh.hl[0], sh.hw[0]};
+    const int cx = (int)floorf((ex_ - mp.x0) * mp.inv_cell), cy = (int)floorf((ey_ - mp.y0) * mp.inv_cell);
+    if (cx >= 0 && cy >= 0 && cx < mp.nx && cy < mp.ny) {
+      const int cell = mp.cell_off + cy * mp.nx + cx;
+      const int b0 = __ldg(&T.cell_start[cell]), b1 = __ldg(&T.cell_start[cell + 1]);
+      const int32_t* ent = T.cell_entries + mp.entry_off;
+      for (int k = b0 + slot; k < b1; k += V) {
+        const int b = __ldg(&ent[k]);
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(boxes + b));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(boxes + b) + 1);
+        const int kind = __float_as_int(g1.z);
+        if (kind == PGD_BOX_LANE) continue;
+        const Rect r = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y};
+        if (!rect_overlap(er, r)) continue;
+        flags |= kind == PGD_BOX_WHITE ? PGD_F_ON_WHITE
+               : kind == PGD_BOX_YELLOW ? PGD_F_ON_YELLOW
+               : kind == PGD_BOX_BROKEN ? PGD_F_ON_BROKEN : PGD_F_CRASH_SIDEWALK;
+      }
+    }
+#pragma unroll
+    for (int o = V / 2; o > 0; o >>= 1) flags |= __shfl_xor_sync(group_mask, flags, o, V);
+  }
+
+  // ---- phase F: observation, reward, done -----------------------------------------------------------------------
+  float* ob = obs + (size_t)env * PGD_OBS_DIM;
+  // lidar: beam i = slot + V * k, against every other live chassis
+  if (!skip) {
+    for (int i = slot; i < PGD_LIDAR_BEAMS; i += V) {
+      const float ang = (float)i * (TWO_PI_F / (float)PGD_LIDAR_BEAMS) + eh;
+      float s, c;
+      sincosf(ang, &s, &c);
+      const float dx = c * LIDAR_RANGE, dy = s * LIDAR_RANGE;
+      float best = 1.0f;
+      for (int j = 1; j < n_slots; ++j) {
+        if (!sh.alive[j]) continue;
+        const Rect r = {sh.x[j], sh.y[j], sh.ux[j], sh.uy[j], sh.hl[j], sh.hw[j]};
+        best = fminf(best, ray_rect(ex_, ey_, dx, dy, r));
+      }
+      ob[34 + i] = best;
+    }
+  }
+  if (slot == 0) {
+    const int eck0 = ck0, eck1 = ck1;
+    const bool on_lane = (vflags & PGD_V_ON_LANE) != 0;
+    if (on_lane) flags |= PGD_F_ON_LANE;
+    if (crash) flags |= PGD_F_CRASH_VEHICLE;
+    const int cur_road_id = __ldg(&rroads[eck0]);
+    const PgdRoad cur_road = roads[cur_road_id];
+    const int n_ref = cur_road.n_lanes;
+    const Lane ref0 = load_lane(lanes + cur_road.first_lane);
+    float lon0, lat0;
+    lane_local(ref0, x, y, lon0, lat0);
+    const float to_left = lat0 + mp.lane_width / 2.0f;
+    const float to_right = mp.lane_width * (float)n_ref - to_left;
+    if (to_left < 0.0f || to_right < 0.0f) flags |= PGD_F_OUT_OF_ROUTE;
+    {
+      const PgdRoad fr = roads[__ldg(&rroads[route_len - 2])];
+      const Lane fl = load_lane(lanes + fr.first_lane + fr.n_lanes - 1);
+      float lon, lat;
+      lane_local(fl, x, y, lon, lat);
+      if (fl.length - 5.0f < lon && lon < fl.length + 5.0f && mp.lane_width / 2.0f >= lat &&
+          lat >= (0.5f - (float)n_ref) * mp.lane_width)
+        flags |= PGD_F_ARRIVE_DEST;
+    }
+    bool out_of_road = (flags & (PGD_F_ON_YELLOW | PGD_F_ON_WHITE | PGD_F_CRASH_SIDEWALK)) || !on_lane;
+    if (cfg.out_of_route_done && (flags & PGD_F_OUT_OF_ROUTE)) out_of_road = true;
+    if (out_of_road) flags |= PGD_F_OUT_OF_ROAD;
+
+    const float sp = clipf(v * 3.6f, 0.0f, 100000.0f);
+    float o18[18];
+    o18[0] = clipf(to_left / 18.0f, 0.0f, 1.0f);
+    o18[1] = clipf(to_right / 18.0f, 0.0f, 1.0f);
+    {  // heading_diff against the right-most reference lane
+      const Lane l = n_ref == 1 ? ref0 : load_lane(lanes + cur_road.first_lane + n_ref - 1);
+      float lx, ly;
+      if (l.kind == PGD_LANE_STRAIGHT) { lx = -l.ay; ly = l.ax; }
+      else if (l.dir < 0.0f) { lx = x - l.ax; ly = y - l.ay; }
+      else { lx = l.ax - x; ly = l.ay - y; }
+      const float ln = sqrtf(lx * lx + ly * ly);
+      o18[2] = ln > 0.0f ? clipf((hc * lx + hs * ly) / ln, -1.0f, 1.0f) / 2.0f + 0.5f : 0.0f;
+    }
+    o18[3] = clipf((sp + 1.0f) / (MAX_SPEED_KMH + 1.0f), 0.0f, 1.0f);
+    o18[4] = clipf((steer / 60.0f + 1.0f) / 2.0f, 0.0f, 1.0f);
+    o18[5] = clipf((envf.x + 1.0f) / 2.0f, 0.0f, 1.0f);
+    o18[6] = clipf((envf.y + 1.0f) / 2.0f, 0.0f, 1.0f);
+    // yaw rate = arccos(clip(cos(heading change), 0, 1)) / 0.1, evaluated as min(|change|, pi/2) (well-conditioned)
+    o18[7] = clipf(fminf(fabsf(wrap_to_pi(h - last_h)), PI_F / 2) / 0.1f, 0.0f, 1.0f);
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {  // navigation info of the two target roads
+      const PgdRoad road = which == 0 ? cur_road : roads[__ldg(&rroads[eck1])];
+      const Lane ref = which == 0 ? ref0 : load_lane(lanes + road.first_lane);
+      const float later_middle = ((float)n_ref / 2.0f - 0.5f) * mp.lane_width;
+      float px, py;
+      lane_position(ref, ref.length, later_middle, px, py);
+      float dx = px - x, dy = py - y;
+      const float dn = sqrtf(dx * dx + dy * dy);
+      if (dn > 50.0f) { dx = dx / dn * 50.0f; dy = dy / dn * 50.0f; }
+      float ph, ps;
+      project(hc, hs, dx, dy, ph, ps);
+      float bend = 0.0f, dir = 0.0f, angle = 0.0f;
+      if (ref.kind == PGD_LANE_ARC) {
+        bend = ref.radius / (60.0f + (float)n_ref * mp.lane_width);
+        dir = ref.dir;
+        angle = ref.length / ref.radius;
+      }
+      float* q = o18 + 8 + 5 * which;
+      q[0] = clipf((ph / 50.0f + 1.0f) / 2.0f, 0.0f, 1.0f);
+      q[1] = clipf((ps / 50.0f + 1.0f) / 2.0f, 0.0f, 1.0f);
+      q[2] = clipf(bend, 0.0f, 1.0f);
+      q[3] = clipf((dir + 1.0f) / 2.0f, 0.0f, 1.0f);
+      q[4] = clipf((angle * (180.0f / PI_F) / 135.0f + 1.0f) / 2.0f, 0.0f, 1.0f);
+    }
+    // the 4 nearest vehicles inside the 50 m cylinder
+    float o16[16];
+    {
+      unsigned taken = 1u;  // slot 0 = self
+      for (int q4 = 0; q4 < 4; ++q4) {
+        int best = -1;
+        float bd = LIDAR_RANGE * LIDAR_RANGE;
+        for (int j = 1; j < n_slots; ++j) {
+          if (!sh.alive[j] || (taken >> j & 1u)) continue;
+          const float dx = sh.x[j] - x, dy = sh.y[j] - y;
+          const float d2 = dx * dx + dy * dy;
+          if (d2 < bd) { bd = d2; best = j; }
+        }
+        float* q = o16 + 4 * q4;
+        if (best < 0) { q[0] = q[1] = q[2] = q[3] = 0.0f; continue; }
+        taken |= 1u << best;
+        float pf, ps, vf, vs;
+        project(hc, hs, sh.x[best] - x, sh.y[best] - y, pf, ps);
+        const float ws = clipf(sh.v[best] * 3.6f, 0.0f, 100000.0f);
+        project(hc, hs, ws * sh.ux[best] - sp * hc, ws * sh.uy[best] - sp * hs, vf, vs);
+        q[0] = clipf((pf / LIDAR_RANGE + 1.0f) / 2.0f, 0.0f, 1.0f);
+        q[1] = clipf((ps / LIDAR_RANGE + 1.0f) / 2.0f, 0.0f, 1.0f);
+        q[2] = clipf((vf / MAX_SPEED_KMH + 1.0f) / 2.0f, 0.0f, 1.0f);
+        q[3] = clipf((vs / MAX_SPEED_KMH + 1.0f) / 2.0f, 0.0f, 1.0f);
+      }
+    }
+    // reward / cost / done
+    float r = 0.0f, step_reward = 0.0f, cost = 0.0f, step_energy = 0.0f;
+    int is_done = 0;
+    if (!fresh) {
+      const Lane el = load_lane(lanes + lane);
+      float sign = 1.0f;
+      bool use_ego_lane = el.road == cur_road_id;
+      if (!use_ego_lane) sign = __ldg(&roads[el.road].negative) ? -1.0f : 1.0f;
+      const Lane rl = use_ego_lane ? el : ref0;
+      float long_last, long_now, lat_last, lat_now;
+      lane_local(rl, last_x, last_y, long_last, lat_last);
+      lane_local(rl, x, y, long_now, lat_now);
+      float lateral_factor = 1.0f;
+      if (cfg.use_lateral) lateral_factor = clipf(1.0f - 2.0f * fabsf(lat_now) / mp.lane_width, 0.0f, 1.0f);
+      r += cfg.driving_reward * (long_now - long_last) * lateral_factor * sign;
+      r += cfg.speed_reward * (sp / MAX_SPEED_KMH) * sign;
+      step_reward = r;
+      if (flags & PGD_F_ARRIVE_DEST) r = cfg.success_reward;
+      else if (out_of_road) r = -cfg.out_of_road_penalty;
+      else if (crash) r = -cfg.crash_vehicle_penalty;
+      if (out_of_road) cost = cfg.out_of_road_cost;
+      else if (crash) cost = cfg.crash_vehicle_cost;
+      is_done = ((flags & PGD_F_ARRIVE_DEST) || out_of_road || crash) ? 1 : 0;
+      const float ddx = last_x - x, ddy = last_y - y;
+      step_energy = 3.25f * expf(0.01f * sp) * (sqrtf(ddx * ddx + ddy * ddy) / 1000.0f) / 100.0f * 1000.0f;
+      envf.w += step_energy;
+      envf.z += r;
+      envi.w += 1;
+      if (cfg.horizon > 0 && envi.w >= cfg.horizon) { is_done = 1; flags |= PGD_F_MAX_STEP; }
+      if (envi.z == 1) is_done = 1;  // sticky
+      envi.z = is_done;
+    } else {
+      flags |= PGD_F_WAS_RESET;
+    }
+    if (!skip) {
+#pragma unroll
+      for (int k = 0; k < 18; ++k) ob[k] = o18[k];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) ob[18 + k] = o16[k];
+      if (mode == 0) {
+        reward[env] = r;
+        done[env] = (uint8_t)is_done;
+      }
+      if (info) {
+        PgdInfo inf;
+        inf.velocity = sp; inf.steering = steer; inf.acceleration = throttle;
+        inf.step_energy = step_energy; inf.episode_energy = envf.w;
+        inf.step_reward = step_reward; inf.episode_reward = envf.z; inf.cost = cost;
+        inf.episode_length = envi.w; inf.flags = flags;
+        info[env] = inf;
+      }
+      S.envi[env] = envi;
+      S.envf[env] = envf;
+    }
+  }
+
+  // ---- phase G: store --------------------------------------------------------------------------------------------
+  if (!skip) {
+    vflags = (vflags & PGD_V_ON_LANE) | (alive ? PGD_V_ALIVE : 0) | (active ? PGD_V_ACTIVE : 0);
+    S.pose[gi] = make_float4(x, y, h, v);
+    S.ctrl[gi] = make_float4(steer, throttle, hp, hi);
+    S.pidl[gi] = make_float4(lp, li, target_speed, yaw_rate);
+    S.nav[gi] = make_int4(lane, ck0 | (ck1 << 16), rt_lane, timer);
+    S.misc[gi] = make_int4(rnd_n, airborne, vflags, 0);
+  }
+}
+
+// marks environments for a forced reset on the given episode templates
+__global__ void pgd_mark_reset_kernel(DevState S, const int32_t* env_ids, const int32_t* episode_ids, int n,
+                                      int num_envs) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int e = env_ids ? env_ids[i] : i;
+  if (e < 0 || e >= num_envs) return;
+  int4 v = S.envi[e];
+  v.x = episode_ids[i];
+  v.z = DONE_PENDING_RESET;
+  S.envi[e] = v;
+}
+
+// ===================================================================================================================
+// host side: C-ABI
+// ===================================================================================================================
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CU(call)                                                                                  \
+  do {                                                                                            \
+    cudaError_t e_ = (call);                                                                      \
+    if (e_ != cudaSuccess) return fail(-2, std::string(#call) + ": " + cudaGetErrorString(e_));   \
+  } while (0)
+
+struct PgdHandle {
+  PgdConfig cfg;
+  int device;
+  DevTables T;
+  void* table_mem[10];
+  int n_episodes;
+  DevState S;
+  void* state_mem[7];
+  bool tables_loaded;
+  int64_t launches;
+  // reset scratch
+  int32_t* d_ids;
+  int32_t* d_eps;
+  int scratch_cap;
+  // pinned staging + device buffers for the host-buffer step
+  float *h_act, *h_obs, *h_rew;
+  uint8_t* h_done;
+  PgdInfo* h_info;
+  float *d_act, *d_obs, *d_rew;
+  uint8_t* d_done;
+  PgdInfo* d_info;
+  cudaStream_t own_stream;
+  // timing
+  int timing;
+  cudaEvent_t ev0, ev1;
+};
+
+extern "C" const char* pgd_last_error(void) { return g_err.c_str(); }
+
+extern "C" int pgd_create(const PgdConfig* cfg, int device, PgdHandle** out) {
+  if (!cfg || !out) return fail(-1, "pgd_create: null argument");
+  if (cfg->num_envs <= 0) return fail(-1, "pgd_create: num_envs must be positive");
+  if (cfg->num_slots != 16 && cfg->num_slots != 32) return fail(-1, "pgd_create: num_slots must be 16 or 32");
+  CU(cudaSetDevice(device));
+  PgdHandle* h = new PgdHandle();
+  memset(h, 0, sizeof(*h));
+  h->cfg = *cfg;
+  h->device = device;
+  const size_t nv = (size_t)cfg->num_envs * cfg->num_slots, n = (size_t)cfg->num_envs;
+  const size_t sizes[7] = {nv * 16, nv * 16, nv * 16, nv * 16, nv * 16, n * 16, n * 16};
+  for (int i = 0; i < 7; ++i) {
+    CU(cudaMalloc(&h->state_mem[i], sizes[i]));
+    CU(cudaMemset(h->state_mem[i], 0, sizes[i]));
+  }
+  h->S.pose = (float4*)h->state_mem[0];
+  h->S.ctrl = (float4*)h->state_mem[1];
+  h->S.pidl = (float4*)h->state_mem[2];
+  h->S.nav = (int4*)h->state_mem[3];
+  h->S.misc = (int4*)h->state_mem[4];
+  h->S.envi = (int4*)h->state_mem[5];
+  h->S.envf = (float4*)h->state_mem[6];
+  CU(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  CU(cudaEventCreate(&h->ev0));
+  CU(cudaEventCreate(&h->ev1));
+  *out = h;
+  return 0;
+}
+
+extern "C" int pgd_destroy(PgdHandle* h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  for (int i = 0; i < 7; ++i) cudaFree(h->state_mem[i]);
+  for (int i = 0; i < 10; ++i) cudaFree(h->table_mem[i]);
+  cudaFree(h->d_ids); cudaFree(h->d_eps);
+  cudaFreeHost(h->h_act); cudaFreeHost(h->h_obs); cudaFreeHost(h->h_rew); cudaFreeHost(h->h_done);
+  cudaFreeHost(h->h_info);
+  cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_done); cudaFree(h->d_info);
+  cudaStreamDestroy(h->own_stream);
+  cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
+  delete h;
+  return 0;
+}
+
+extern "C" int pgd_load_tables(PgdHandle* h, const PgdTables* t) {
+  if (!h || !t) return fail(-1, "pgd_load_tables: null argument");
+  CU(cudaSetDevice(h->device));
+  for (int i = 0; i < t->n_episodes; ++i) {
+    if (t->episodes[i].n_slots > h->cfg.num_slots)
+      return fail(-3, "pgd_load_tables: an episode needs more vehicle slots than num_slots");
+    if (t->episodes[i].n_groups > PGD_MAX_GROUPS) return fail(-3, "pgd_load_tables: too many trigger groups");
+  }
+  const void* src[10] = {t->maps, t->lanes, t->roads, t->boxes, t->cell_start, t->cell_entries,
+                         t->episodes, t->slots, t->route_nodes, t->route_roads};
+  const size_t bytes[10] = {(size_t)t->n_maps * sizeof(PgdMap), (size_t)t->n_lanes * sizeof(PgdLane),
+                            (size_t)t->n_roads * sizeof(PgdRoad), (size_t)t->n_boxes * sizeof(PgdBox),
+                            (size_t)t->n_cell_start * 4, (size_t)t->n_cell_entries * 4,
+                            (size_t)t->n_episodes * sizeof(PgdEpisode), (size_t)t->n_slots * sizeof(PgdSlot),
+                            (size_t)t->n_route * 4, (size_t)t->n_route * 4};
+  CU(cudaDeviceSynchronize());
+  for (int i = 0; i < 10; ++i) {
+    cudaFree(h->table_mem[i]);
+    h->table_mem[i] = nullptr;
+    CU(cudaMalloc(&h->table_mem[i], bytes[i] ? bytes[i] : 16));
+    if (bytes[i]) CU(cudaMemcpy(h->table_mem[i], src[i], bytes[i], cudaMemcpyHostToDevice));
+  }
+  h->T.maps = (const PgdMap*)h->table_mem[0];
+  h->T.lanes = (const PgdLane*)h->table_mem[1];
+  h->T.roads = (const PgdRoad*)h->table_mem[2];
+  h->T.boxes = (const PgdBox*)h->table_mem[3];
+  h->T.cell_start = (const int32_t*)h->table_mem[4];
+  h->T.cell_entries = (const int32_t*)h->table_mem[5];
+  h->T.episodes = (const PgdEpisode*)h->table_mem[6];
+  h->T.slots = (const PgdSlot*)h->table_mem[7];
+  h->T.route_nodes = (const int32_t*)h->table_mem[8];
+  h->T.route_roads = (const int32_t*)h->table_mem[9];
+  h->n_episodes = t->n_episodes;
+  h->tables_loaded = true;
+  return 0;
+}
+
+static int launch_step(PgdHandle* h, int mode, const float* actions, float* obs, float* reward, uint8_t* done,
+                       PgdInfo* info, cudaStream_t st) {
+  const int V = h->cfg.num_slots;
+  const int envs_per_cta = CTA_THREADS / V;
+  const int grid = (h->cfg.num_envs + envs_per_cta - 1) / envs_per_cta;
+  if (h->timing && mode == 0) cudaEventRecord(h->ev0, st);
+  if (V == 16)
+    pgd_step_kernel<16><<<grid, CTA_THREADS, 0, st>>>(h->T, h->S, h->cfg, mode, (const float2*)actions, obs, reward,
+                                                      done, info);
+  else
+    pgd_step_kernel<32><<<grid, CTA_THREADS, 0, st>>>(h->T, h->S, h->cfg, mode, (const float2*)actions, obs, reward,
+                                                      done, info);
+  if (h->timing && mode == 0) cudaEventRecord(h->ev1, st);
+  h->launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int pgd_reset(PgdHandle* h, const int32_t* env_ids, const int32_t* episode_ids, int32_t n, float* obs_dev,
+                         PgdInfo* info_dev, void* stream) {
+  if (!h || !episode_ids || !obs_dev) return fail(-1, "pgd_reset: null argument");
+  if (!h->tables_loaded) return fail(-3, "pgd_reset: no tables loaded");
+  if (n <= 0 || n > h->cfg.num_envs) return fail(-1, "pgd_reset: n out of range");
+  for (int i = 0; i < n; ++i) {
+    if (episode_ids[i] < 0 || episode_ids[i] >= h->n_episodes) return fail(-1, "pgd_reset: episode id out of range");
+    if (env_ids && (env_ids[i] < 0 || env_ids[i] >= h->cfg.num_envs)) return fail(-1, "pgd_reset: env id out of range");
+  }
+  CU(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n > h->scratch_cap) {
+    cudaFree(h->d_ids); cudaFree(h->d_eps);
+    CU(cudaMalloc(&h->d_ids, (size_t)n * 4));
+    CU(cudaMalloc(&h->d_eps, (size_t)n * 4));
+    h->scratch_cap = n;
+  }
+  // pageable-host copies: cudaMemcpyAsync returns after staging, so the caller's arrays may be reused
+  if (env_ids) CU(cudaMemcpyAsync(h->d_ids, env_ids, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(h->d_eps, episode_ids, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  pgd_mark_reset_kernel<<<(n + 255) / 256, 256, 0, st>>>(h->S, env_ids ? h->d_ids : nullptr, h->d_eps, n,
+                                                         h->cfg.num_envs);
+  h->launches++;
+  CU(cudaGetLastError());
+  return launch_step(h, 1, nullptr, obs_dev, nullptr, nullptr, info_dev, st);
+}
+
+extern "C" int pgd_step(PgdHandle* h, const float* actions_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev,
+                        PgdInfo* info_dev, void* stream) {
+  if (!h || !actions_dev || !obs_dev || !reward_dev || !done_dev) return fail(-1, "pgd_step: null argument");
+  if (!h->tables_loaded) return fail(-3, "pgd_step: no tables loaded");
+  CU(cudaSetDevice(h->device));
+  return launch_step(h, 0, actions_dev, obs_dev, reward_dev, done_dev, info_dev, (cudaStream_t)stream);
+}
+
+static int ensure_staging(PgdHandle* h) {
+  if (h->h_act) return 0;
+  const size_t n = (size_t)h->cfg.num_envs;
+  CU(cudaMallocHost(&h->h_act, n * 8));
+  CU(cudaMallocHost(&h->h_obs, n * PGD_OBS_DIM * 4));
+  CU(cudaMallocHost(&h->h_rew, n * 4));
+  CU(cudaMallocHost(&h->h_done, n));
+  CU(cudaMallocHost(&h->h_info, n * sizeof(PgdInfo)));
+  CU(cudaMalloc(&h->d_act, n * 8));
+  CU(cudaMalloc(&h->d_obs, n * PGD_OBS_DIM * 4));
+  CU(cudaMalloc(&h->d_rew, n * 4));
+  CU(cudaMalloc(&h->d_done, n));
+  CU(cudaMalloc(&h->d_info, n * sizeof(PgdInfo)));
+  return 0;
+}
+
+extern "C" int pgd_step_host(PgdHandle* h, const float* actions, float* obs, float* reward, uint8_t* done,
+                             PgdInfo* info) {
+  if (!h || !actions || !obs || !reward || !done) return fail(-1, "pgd_step_host: null argument");
+  if (!h->tables_loaded) return fail(-3, "pgd_step_host: no tables loaded");
+  CU(cudaSetDevice(h->device));
+  int rc = ensure_staging(h);
+  if (rc) return rc;
+  const size_t n = (size_t)h->cfg.num_envs;
+  cudaStream_t st = h->own_stream;
+  memcpy(h->h_act, actions, n * 8);
+  CU(cudaMemcpyAsync(h->d_act, h->h_act, n * 8, cudaMemcpyHostToDevice, st));
+  rc = launch_step(h, 0, h->d_act, h->d_obs, h->d_rew, h->d_done, info ? h->d_info : nullptr, st);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(h->h_obs, h->d_obs, n * PGD_OBS_DIM * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(h->h_rew, h->d_rew, n * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(h->h_done, h->d_done, n, cudaMemcpyDeviceToHost, st));
+  if (info) CU(cudaMemcpyAsync(h->h_info, h->d_info, n * sizeof(PgdInfo), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  memcpy(obs, h->h_obs, n * PGD_OBS_DIM * 4);
+  memcpy(reward, h->h_rew, n * 4);
+  memcpy(done, h->h_done, n);
+  if (info) memcpy(info, h->h_info, n * sizeof(PgdInfo));
+  return 0;
+}
+
+extern "C" int pgd_get_state(PgdHandle* h, int32_t env, PgdEnvState* out) {
+  if (!h || !out) return fail(-1, "pgd_get_state: null argument");
+  if (env < 0 || env >= h->cfg.num_envs) return fail(-1, "pgd_get_state: env out of range");
+  CU(cudaSetDevice(h->device));
+  CU(cudaDeviceSynchronize());
+  const int V = h->cfg.num_slots;
+  float4 pose[PGD_MAX_SLOTS], ctrl[PGD_MAX_SLOTS], pidl[PGD_MAX_SLOTS], envf;
+  int4 nav[PGD_MAX_SLOTS], misc[PGD_MAX_SLOTS], envi;
+  CU(cudaMemcpy(pose, h->S.pose + (size_t)env * V, V * 16, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(ctrl, h->S.ctrl + (size_t)env * V, V * 16, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(pidl, h->S.pidl + (size_t)env * V, V * 16, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(nav, h->S.nav + (size_t)env * V, V * 16, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(misc, h->S.misc + (size_t)env * V, V * 16, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(&envi, h->S.envi + env, 16, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(&envf, h->S.envf + env, 16, cudaMemcpyDeviceToHost));
+  memset(out, 0, sizeof(*out));
+  out->episode = envi.x; out->next_group = envi.y; out->done = envi.z; out->ep_len = envi.w;
+  out->prev_steer = envf.x; out->prev_throttle = envf.y; out->ep_reward = envf.z; out->energy = envf.w;
+  for (int i = 0; i < V; ++i) {
+    PgdVehState* s = &out->veh[i];
+    s->x = pose[i].x; s->y = pose[i].y; s->heading = pose[i].z; s->speed = pose[i].w;
+    s->steer = ctrl[i].x; s->throttle = ctrl[i].y; s->pid_hp = ctrl[i].z; s->pid_hi = ctrl[i].w;
+    s->pid_lp = pidl[i].x; s->pid_li = pidl[i].y; s->target_speed = pidl[i].z; s->yaw_rate = pidl[i].w;
+    s->lane = nav[i].x; s->ck0 = nav[i].y & 0xffff; s->ck1 = nav[i].y >> 16; s->rt_lane = nav[i].z;
+    s->timer = nav[i].w; s->rnd_n = misc[i].x; s->airborne = misc[i].y; s->flags = misc[i].z;
+  }
+  return 0;
+}
+
+extern "C" int pgd_set_state(PgdHandle* h, int32_t env, const PgdEnvState* in) {
+  if (!h || !in) return fail(-1, "pgd_set_state: null argument");
+  if (env < 0 || env >= h->cfg.num_envs) return fail(-1, "pgd_set_state: env out of range");
+  if (in->episode < 0 || in->episode >= h->n_episodes) return fail(-1, "pgd_set_state: episode out of range");
+  CU(cudaSetDevice(h->device));
+  CU(cudaDeviceSynchronize());
+  const int V = h->cfg.num_slots;
+  float4 pose[PGD_MAX_SLOTS], ctrl[PGD_MAX_SLOTS], pidl[PGD_MAX_SLOTS], envf;
+  int4 nav[PGD_MAX_SLOTS], misc[PGD_MAX_SLOTS], envi;
+  envi = make_int4(in->episode, in->next_group, in->done, in->ep_len);
+  envf = make_float4(in->prev_steer, in->prev_throttle, in->ep_reward, in->energy);
+  for (int i = 0; i < V; ++i) {
+    const PgdVehState* s = &in->veh[i];
+    pose[i] = make_float4(s->x, s->y, s->heading, s->speed);
+    ctrl[i] = make_float4(s->steer, s->throttle, s->pid_hp, s->pid_hi);
+    pidl[i] = make_float4(s->pid_lp, s->pid_li, s->target_speed, s->yaw_rate);
+    nav[i] = make_int4(s->lane, s->ck0 | (s->ck1 << 16), s->rt_lane, s->timer);
+    misc[i] = make_int4(s->rnd_n, s->airborne, s->flags, 0);
+  }
+  CU(cudaMemcpy(h->S.pose + (size_t)env * V, pose, V * 16, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->S.ctrl + (size_t)env * V, ctrl, V * 16, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->S.pidl + (size_t)env * V, pidl, V * 16, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->S.nav + (size_t)env * V, nav, V * 16, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->S.misc + (size_t)env * V, misc, V * 16, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->S.envi + env, &envi, 16, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->S.envf + env, &envf, 16, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+extern "C" int64_t pgd_state_bytes_per_env(PgdHandle* h) { return h ? (int64_t)h->cfg.num_slots * 80 + 32 : 0; }
+extern "C" int64_t pgd_launch_count(PgdHandle* h) { return h ? h->launches : 0; }
+extern "C" int pgd_set_timing(PgdHandle* h, int32_t on) {
+  if (!h) return fail(-1, "pgd_set_timing: null handle");
+  h->timing = on;
+  return 0;
+}
+extern "C" float pgd_last_kernel_ms(PgdHandle* h) {
+  if (!h || !h->timing) return -1.0f;
+  float ms = -1.0f;
+  if (cudaEventSynchronize(h->ev1) != cudaSuccess) return -1.0f;
+  if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) != cudaSuccess) return -1.0f;
+  return ms;
+}

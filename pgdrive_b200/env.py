@@ -1,0 +1,415 @@
+"""The gym surface of the reference over the batched CUDA step.
+
+``PGDriveEnv``     drop-in for /root/reference/pgdrive/envs/pgdrive_env.py:112-336 (one environment;
+                   ``reset(force_seed=)``, ``step(a) -> (obs, reward, done, info)``, spaces, ``seed``,
+                   ``current_seed``, ``close``; same config dict and KeyError on unknown keys).
+``VecPGDriveEnv``  the same environment batched: ``num_envs`` copies advanced by ONE kernel launch per
+                   step, observations / rewards / dones as ``[N, ...]`` arrays.
+
+Both call the C-ABI of include/pgdrive_b200.h through ctypes; torch tensors are only the device-buffer
+container.  There is no CPU path: constructing either class without the CUDA library or without a
+CUDA device raises.
+"""
+import ctypes as C
+import hashlib
+import os
+import pickle
+
+import numpy as np
+
+from . import cabi, episode, mapgen, tables
+from .config import ENGINE_CONFIG, Config, check_supported, default_config
+from .spaces import Box
+
+ENVIRONMENTS = {  # /root/reference/pgdrive/register.py:7-40
+    "PGDrive-test-v0": dict(start_seed=0, environment_num=200),
+    "PGDrive-validation-v0": dict(start_seed=200, environment_num=800),
+    "PGDrive-v0": dict(start_seed=1000, environment_num=100),
+    "PGDrive-10envs-v0": dict(start_seed=1000, environment_num=10),
+    "PGDrive-1000envs-v0": dict(start_seed=1000, environment_num=1000),
+    "PGDrive-training0-v0": dict(start_seed=3000, environment_num=1000),
+    "PGDrive-training1-v0": dict(start_seed=5000, environment_num=1000),
+    "PGDrive-training2-v0": dict(start_seed=7000, environment_num=1000),
+}
+
+INFO_FLAGS = dict(
+    crash_vehicle=cabi.F_CRASH_VEHICLE, out_of_road=cabi.F_OUT_OF_ROAD, arrive_dest=cabi.F_ARRIVE_DEST,
+    max_step=cabi.F_MAX_STEP
+)
+
+
+def parse_map_config(cfg):
+    """component/map/base_map.py:16-35: ``map`` shorthand (int = block count, str = block ids) unless the
+    user overrode ``map_config``."""
+    mc = cfg["map_config"].get_dict()
+    default_mc = default_config()["map_config"].get_dict()
+    if mc != default_mc:
+        out = dict(default_mc)
+        out.update(mc)
+        return out
+    easy = cfg["map"]
+    if isinstance(easy, bool) or not isinstance(easy, (int, str)):
+        raise ValueError("Unkown easy map config: {} and original map config: {}".format(easy, mc))
+    mc["type"] = "block_num" if isinstance(easy, int) else "block_sequence"
+    mc["config"] = easy
+    return mc
+
+
+def _seed_tables(args):
+    seed, mc, density, spawn = args
+    kw = dict(lane_num=mc["lane_num"], lane_width=mc["lane_width"], exit_length=mc["exit_length"])
+    if mc["type"] == "block_num":
+        pgmap = mapgen.generate_map(seed, block_num=mc["config"], **kw)
+    elif mc["type"] == "block_sequence":
+        pgmap = mapgen.generate_map(seed, sequence=mc["config"], **kw)
+    else:
+        raise ValueError("Map can not be created by {}".format(mc["type"]))
+    ts = tables.TableSet()
+    mid = ts.add_map(pgmap)
+    lane, lon, lat = spawn
+    ts.add_episode(pgmap, mid, episode.make_episode(pgmap, seed, density, tuple(lane)), tuple(lane), lon, lat)
+    return ts.finish()
+
+
+def merge_tables(parts):
+    """Concatenate per-seed table sets, rebasing the offsets stored in the records."""
+    keys = ["maps", "lanes", "roads", "boxes", "cell_start", "cell_entries", "episodes", "slots", "route_nodes",
+            "route_roads"]
+    off = {k: 0 for k in keys}
+    out = {k: [] for k in keys}
+    for p in parts:
+        maps, eps, slots = p["maps"].copy(), p["episodes"].copy(), p["slots"].copy()
+        maps["lane_off"] += off["lanes"]
+        maps["road_off"] += off["roads"]
+        maps["box_off"] += off["boxes"]
+        maps["cell_off"] += off["cell_start"]
+        maps["entry_off"] += off["cell_entries"]
+        eps["map"] += off["maps"]
+        eps["slot_off"] += off["slots"]
+        slots["route_off"] += off["route_nodes"]
+        for k, a in (("maps", maps), ("episodes", eps), ("slots", slots)):
+            out[k].append(a)
+        for k in keys:
+            if k not in ("maps", "episodes", "slots"):
+                out[k].append(p[k])
+            off[k] += len(p[k])
+    T = {k: np.concatenate(v) if v else None for k, v in out.items()}
+    T["max_slots"] = int(T["episodes"]["n_slots"].max())
+    return T
+
+
+def build_seed_tables(seeds, map_config, density, spawn, workers=None):
+    """Tables for a list of seeds, built in worker processes when there are many, with an optional
+    on-disk cache ($PGDRIVE_B200_CACHE) because map search costs ~50 ms per seed."""
+    seeds = [int(s) for s in seeds]
+    jobs = [(s, map_config, density, spawn) for s in seeds]
+    cache_dir = os.environ.get("PGDRIVE_B200_CACHE")
+    path = None
+    if cache_dir:
+        src = b"".join(open(os.path.join(os.path.dirname(__file__), f), "rb").read()
+                       for f in ("mapgen.py", "roadnet.py", "episode.py", "tables.py", "rng.py"))
+        key = hashlib.sha1(repr(jobs).encode() + src).hexdigest()
+        path = os.path.join(cache_dir, "tables_%s.pkl" % key)
+        if os.path.exists(path):
+            with open(path, "rb") as f:
+                return pickle.load(f)
+    if workers is None:
+        workers = min(len(os.sched_getaffinity(0)), 32) if len(seeds) >= 256 else 1
+    if workers > 1:
+        # fork (not spawn): children only run numpy code, and spawn would re-import the caller's __main__
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(workers) as pool:
+            parts = pool.map(_seed_tables, jobs, chunksize=max(1, len(jobs) // (workers * 4)))
+    else:
+        parts = [_seed_tables(j) for j in jobs]
+    T = merge_tables(parts)
+    if path:
+        os.makedirs(cache_dir, exist_ok=True)
+        with open(path, "wb") as f:
+            pickle.dump(T, f)
+    return T
+
+
+class _Engine:
+    """One C-ABI handle + its loaded tables."""
+    def __init__(self, cfg, num_envs, num_slots, device, auto_reset):
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("pgdrive_b200 needs a CUDA device (there is no CPU fallback)")
+        self.torch = torch
+        self.lib = cabi.load_library()
+        self.device = torch.device("cuda", device)
+        horizon = cfg["horizon"] or 0
+        self.pcfg = cabi.make_config(
+            num_envs, num_slots, cfg["decision_repeat"], horizon, cfg["physics_world_step_size"],
+            cfg["success_reward"], cfg["out_of_road_penalty"], cfg["crash_vehicle_penalty"], cfg["driving_reward"],
+            cfg["speed_reward"], cfg["out_of_road_cost"], cfg["crash_vehicle_cost"], cfg["use_lateral"],
+            cfg["out_of_route_done"], auto_reset
+        )
+        self.h = C.c_void_p()
+        cabi.check(self.lib, self.lib.pgd_create(C.byref(self.pcfg), device, C.byref(self.h)))
+        self.num_envs, self.num_slots = num_envs, num_slots
+
+    def load(self, T):
+        t, keep = cabi.pack_tables(T)
+        cabi.check(self.lib, self.lib.pgd_load_tables(self.h, C.byref(t)))
+
+    def stream(self):
+        return self.torch.cuda.current_stream(self.device).cuda_stream
+
+    def close(self):
+        if self.h:
+            self.lib.pgd_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+class VecPGDriveEnv:
+    """``num_envs`` PGDrive environments advanced together.
+
+    Environment ``i`` plays seed ``start_seed + i % environment_num`` unless ``reset(seeds=...)`` says
+    otherwise.  With ``auto_reset`` (default) an environment that reported ``done`` restarts on the
+    same seed at its next ``step`` (that step ignores the action and returns the reset observation
+    with reward 0 -- the "next-step" convention of vector environments); the reference itself never
+    resets on its own (README.md:96-101).
+    """
+    def __init__(self, config=None, tables_dict=None, obs_out=None):
+        merged = default_config()
+        merged.update(ENGINE_CONFIG)
+        self.config = merged.update(config or {}, allow_add_new_key=False)
+        check_supported(self.config)
+        cfg = self.config
+        self.num_envs = int(cfg["num_envs"])
+        self.start_seed, self.env_num = int(cfg["start_seed"]), int(cfg["environment_num"])
+        self.map_config = parse_map_config(cfg)
+        vc = cfg["vehicle_config"]
+        self._spawn = (tuple(vc["spawn_lane_index"]), float(vc["spawn_longitude"]), float(vc["spawn_lateral"]))
+        seeds = list(range(self.start_seed, self.start_seed + self.env_num))
+        self.T = tables_dict if tables_dict is not None else build_seed_tables(
+            seeds, self.map_config, cfg["traffic_density"], self._spawn
+        )
+        self.episode_of_seed = {int(s): i for i, s in enumerate(self.T["episodes"]["seed"])}
+        need = int(self.T["max_slots"])
+        slots = cfg["num_slots"] or (16 if need <= 16 else 32)
+        if need > slots:
+            raise ValueError("the loaded seeds need %d vehicle slots; num_slots=%d" % (need, slots))
+        self.engine = _Engine(cfg, self.num_envs, slots, int(cfg["device"]), bool(cfg["auto_reset"]))
+        self.engine.load(self.T)
+        torch = self.engine.torch
+        dev = self.engine.device
+        n = self.num_envs
+        self.obs = obs_out if obs_out is not None else torch.empty((n, cabi.OBS_DIM), dtype=torch.float32, device=dev)
+        self.reward = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.done = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self.info = torch.zeros((n, cabi.INFO_DT.itemsize // 4), dtype=torch.int32, device=dev)
+        self._h_obs = np.empty((n, cabi.OBS_DIM), np.float32)
+        self._h_reward = np.empty(n, np.float32)
+        self._h_done = np.empty(n, np.uint8)
+        self._h_info = np.empty(n, cabi.INFO_DT)
+        self.observation_space = Box(-0.0, 1.0, shape=(cabi.OBS_DIM, ), dtype=np.float32)
+        self.action_space = Box(-1.0, 1.0, shape=(2, ), dtype=np.float32)
+        self.env_seeds = np.array([self.start_seed + i % self.env_num for i in range(n)], dtype=np.int64)
+
+    # -- reset / step ------------------------------------------------------------------------------
+    def reset(self, seeds=None, env_ids=None):
+        """Restart ``env_ids`` (default: all) on ``seeds`` (default: each env's current seed).  Returns the
+        ``[N, 274]`` observation tensor (rows of untouched environments keep their last observation)."""
+        if env_ids is None:
+            env_ids = np.arange(self.num_envs, dtype=np.int32)
+        env_ids = np.ascontiguousarray(env_ids, dtype=np.int32)
+        if seeds is not None:
+            self.env_seeds[env_ids] = np.broadcast_to(np.asarray(seeds, dtype=np.int64), env_ids.shape)
+        try:
+            eps = np.array([self.episode_of_seed[int(s)] for s in self.env_seeds[env_ids]], dtype=np.int32)
+        except KeyError as e:
+            raise KeyError("seed %s is outside [start_seed, start_seed + environment_num)" % e)
+        e = self.engine
+        cabi.check(
+            e.lib,
+            e.lib.pgd_reset(e.h, env_ids.ctypes.data, eps.ctypes.data, len(env_ids), self.obs.data_ptr(),
+                            self.info.data_ptr(), e.stream())
+        )
+        return self.obs
+
+    def step(self, actions):
+        """``actions``: ``[N, 2]`` float32, either a CUDA tensor (device path: returns CUDA tensors, no
+        synchronisation) or a numpy array (host path: pinned staging, returns numpy arrays)."""
+        e = self.engine
+        torch = e.torch
+        if isinstance(actions, torch.Tensor):
+            if actions.device != e.device or actions.dtype != torch.float32 or tuple(actions.shape) != (self.num_envs, 2):
+                raise ValueError("actions must be a float32 [num_envs, 2] tensor on %s" % e.device)
+            a = actions.contiguous()
+            cabi.check(
+                e.lib,
+                e.lib.pgd_step(e.h, a.data_ptr(), self.obs.data_ptr(), self.reward.data_ptr(), self.done.data_ptr(),
+                               self.info.data_ptr(), e.stream())
+            )
+            return self.obs, self.reward, self.done, self.info
+        a = np.ascontiguousarray(actions, dtype=np.float32)
+        if a.shape != (self.num_envs, 2):
+            raise ValueError("actions must have shape [num_envs, 2]")
+        cabi.check(
+            e.lib,
+            e.lib.pgd_step_host(e.h, a.ctypes.data, self._h_obs.ctypes.data, self._h_reward.ctypes.data,
+                                self._h_done.ctypes.data, self._h_info.ctypes.data)
+        )
+        return self._h_obs, self._h_reward, self._h_done, self._h_info
+
+    def info_numpy(self):
+        """Device info of the last device-path step/reset as a structured array (synchronises)."""
+        return self.info.cpu().numpy().view(cabi.INFO_DT).reshape(self.num_envs)
+
+    # -- state exchange (parity debugging) -----------------------------------------------------------
+    def get_state(self, env):
+        s = np.zeros(1, cabi.ENV_STATE_DT)
+        e = self.engine
+        cabi.check(e.lib, e.lib.pgd_get_state(e.h, int(env), s.ctypes.data))
+        return s
+
+    def set_state(self, env, state):
+        s = np.ascontiguousarray(state)
+        e = self.engine
+        cabi.check(e.lib, e.lib.pgd_set_state(e.h, int(env), s.ctypes.data))
+
+    @property
+    def launch_count(self):
+        return int(self.engine.lib.pgd_launch_count(self.engine.h))
+
+    def close(self):
+        self.engine.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class PGDriveEnv:
+    """Single-environment drop-in (a ``num_envs=1`` view of the batched engine).  Maps are built lazily,
+    one seed at a time, like the reference's map manager (manager/map_manager.py:98-155)."""
+    DEFAULT_AGENT = "default_agent"
+
+    @classmethod
+    def default_config(cls):
+        return default_config()
+
+    def __init__(self, config=None):
+        self.config = self.default_config().update(config or {}, allow_add_new_key=False)
+        check_supported(self.config)
+        self.start_seed, self.env_num = int(self.config["start_seed"]), int(self.config["environment_num"])
+        self.map_config = parse_map_config(self.config)
+        vc = self.config["vehicle_config"]
+        self._spawn = (tuple(vc["spawn_lane_index"]), float(vc["spawn_longitude"]), float(vc["spawn_lateral"]))
+        self.observation_space = Box(-0.0, 1.0, shape=(cabi.OBS_DIM, ), dtype=np.float32)
+        self.action_space = Box(-1.0, 1.0, shape=(2, ), dtype=np.float32)
+        self._parts, self._episode_of_seed = [], {}
+        self._engine = None
+        self._seed = None
+        self._rs = np.random.RandomState()
+        self.episode_steps = 0
+        self._obs = self._reward = self._done = self._info = None
+
+    # lazily create the engine the first time reset() runs (base_env.py:166-178)
+    def _ensure_seed(self, seed):
+        if seed in self._episode_of_seed:
+            return
+        part = _seed_tables((seed, self.map_config, self.config["traffic_density"], self._spawn))
+        self._parts.append(part)
+        self._episode_of_seed[seed] = len(self._parts) - 1
+        T = merge_tables(self._parts)
+        need = int(T["max_slots"])
+        slots = 16 if need <= 16 else 32
+        if self._engine is not None and self._engine.num_slots < slots:
+            self._engine.close()
+            self._engine = None
+        if self._engine is None:
+            self._engine = _Engine(self.config, 1, slots, int(os.environ.get("PGDRIVE_B200_DEVICE", 0)), False)
+            torch = self._engine.torch
+            dev = self._engine.device
+            self._obs = torch.empty((1, cabi.OBS_DIM), dtype=torch.float32, device=dev)
+            self._reward = torch.zeros(1, dtype=torch.float32, device=dev)
+            self._done = torch.zeros(1, dtype=torch.uint8, device=dev)
+            self._info = torch.zeros((1, cabi.INFO_DT.itemsize // 4), dtype=torch.int32, device=dev)
+            self._act = torch.zeros((1, 2), dtype=torch.float32, device=dev)
+        self._engine.load(T)
+
+    def seed(self, seed=None):
+        if seed is not None:
+            self._seed = int(seed)
+
+    @property
+    def current_seed(self):
+        return self._seed
+
+    def reset(self, episode_data=None, force_seed=None):
+        if episode_data is not None:
+            raise NotImplementedError("episode replay is not supported")
+        if force_seed is not None:
+            seed = int(force_seed)
+        else:  # base_env.py:451-458: an unseeded generator picks the map
+            seed = int(self._rs.randint(self.start_seed, self.start_seed + self.env_num))
+        self._seed = seed
+        self._ensure_seed(seed)
+        e = self._engine
+        ids = np.zeros(1, np.int32)
+        eps = np.array([self._episode_of_seed[seed]], np.int32)
+        cabi.check(
+            e.lib,
+            e.lib.pgd_reset(e.h, ids.ctypes.data, eps.ctypes.data, 1, self._obs.data_ptr(), self._info.data_ptr(),
+                            e.stream())
+        )
+        self.episode_steps = 0
+        # the reference returns float64 although the space says float32 (state_obs.py:146,150)
+        return self._obs[0].cpu().numpy().astype(np.float64)
+
+    def step(self, action):
+        if self._engine is None:
+            raise RuntimeError("call reset() before step()")
+        e = self._engine
+        self.episode_steps += 1
+        a = np.asarray(action, dtype=np.float32).reshape(2)
+        self._act.copy_(e.torch.from_numpy(a).reshape(1, 2))
+        cabi.check(
+            e.lib,
+            e.lib.pgd_step(e.h, self._act.data_ptr(), self._obs.data_ptr(), self._reward.data_ptr(),
+                           self._done.data_ptr(), self._info.data_ptr(), e.stream())
+        )
+        obs = self._obs[0].cpu().numpy().astype(np.float64)
+        rec = self._info.cpu().numpy().view(cabi.INFO_DT).reshape(-1)[0]
+        flags = int(rec["flags"])
+        info = {k: bool(flags & bit) for k, bit in INFO_FLAGS.items()}
+        info.update(
+            crash_object=False, crash_building=False, crash=bool(flags & cabi.F_CRASH_VEHICLE),
+            cost=float(rec["cost"]), velocity=float(rec["velocity"]), steering=float(rec["steering"]),
+            acceleration=float(rec["acceleration"]), step_energy=float(rec["step_energy"]),
+            episode_energy=float(rec["episode_energy"]), step_reward=float(rec["step_reward"]),
+            episode_reward=float(rec["episode_reward"]), episode_length=int(rec["episode_length"]),
+            raw_action=(float(a[0]), float(a[1])), overtake_vehicle_num=0,
+            on_yellow_continuous_line=bool(flags & cabi.F_ON_YELLOW), on_white_continuous_line=bool(flags & cabi.F_ON_WHITE),
+            on_broken_line=bool(flags & cabi.F_ON_BROKEN), crash_sidewalk=bool(flags & cabi.F_CRASH_SIDEWALK),
+            on_lane=bool(flags & cabi.F_ON_LANE), out_of_route=bool(flags & cabi.F_OUT_OF_ROUTE)
+        )
+        return obs, float(self._reward.item()), bool(self._done.item()), info
+
+    def get_state(self):
+        s = np.zeros(1, cabi.ENV_STATE_DT)
+        cabi.check(self._engine.lib, self._engine.lib.pgd_get_state(self._engine.h, 0, s.ctypes.data))
+        return s
+
+    def render(self, *a, **k):
+        raise NotImplementedError("the batched simulator is headless")
+
+    def close(self):
+        if self._engine is not None:
+            self._engine.close()
+            self._engine = None
+
+
+def make(env_id, **overrides):
+    """``gym.make(id)`` for the ids the reference registers (register.py:7-43)."""
+    if env_id not in ENVIRONMENTS:
+        raise KeyError("unknown environment id %r; known: %s" % (env_id, sorted(ENVIRONMENTS)))
+    cfg = dict(ENVIRONMENTS[env_id])
+    cfg.update(overrides)
+    return PGDriveEnv(cfg)

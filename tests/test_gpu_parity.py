@@ -1,0 +1,236 @@
+"""CUDA step vs the CPU oracle, through the C-ABI (run on the B200 box: pytest -m gpu).
+
+Bar: done / contact flags bit-exact, floats within 1e-3 (north_star); observations are in [0, 1] so the
+tolerance is absolute there and relative + absolute for rewards."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+OBS_TOL = 1e-3
+FLAG_MASK = 0x7ff
+
+
+def _pair(n, seeds, density=0.1, auto_reset=True, **cfg):
+    import torch  # noqa: F401
+    from oracle.oracle import Oracle
+    from pgdrive_b200 import VecPGDriveEnv
+    env = VecPGDriveEnv(
+        dict(start_seed=seeds[0], environment_num=len(seeds), num_envs=n, traffic_density=density,
+             auto_reset=auto_reset, **cfg)
+    )
+    ref = Oracle(env.T, n, auto_reset=auto_reset, num_slots=env.engine.num_slots,
+                 horizon=cfg.get("horizon", 0) or 0)
+    return env, ref
+
+
+def _reset_both(env, ref):
+    obs = env.reset().cpu().numpy().copy()
+    ro = ref.reset(range(env.num_envs), [env.episode_of_seed[int(s)] for s in env.env_seeds]).copy()
+    return obs, ro
+
+
+def _rollout(env, ref, steps, action_fn, check_state_every=0):
+    import torch
+    n = env.num_envs
+    dones = 0
+    grazing = beams = 0
+    for t in range(steps):
+        a = action_fn(t).astype(np.float32)
+        o, r, d, _ = env.step(torch.from_numpy(a).cuda())
+        o, r, d = o.cpu().numpy(), r.cpu().numpy(), d.cpu().numpy()
+        info = env.info_numpy()
+        ro, rr, rd, rinfo = ref.step(a)
+        bad = np.nonzero(d != rd)[0]
+        assert len(bad) == 0, "step %d: done differs in envs %s" % (t, bad[:8])
+        fl = (info["flags"] & FLAG_MASK) != (rinfo["flags"] & FLAG_MASK)
+        assert not fl.any(), "step %d: flags differ in envs %s: %s vs %s" % (
+            t, np.nonzero(fl)[0][:8], info["flags"][fl][:8], rinfo["flags"][fl][:8])
+        err = np.abs(o - ro)
+        assert err[:, :34].max() < OBS_TOL, "step %d: obs differs by %g at %s" % (
+            t, err[:, :34].max(), np.unravel_index(err[:, :34].argmax(), err[:, :34].shape))
+        grazing += _check_lidar(o[:, 34:], ro[:, 34:], t)
+        beams += o[:, 34:].size
+        np.testing.assert_allclose(r, rr, rtol=1e-3, atol=1e-3, err_msg="step %d reward" % t)
+        np.testing.assert_allclose(info["velocity"], rinfo["velocity"], rtol=1e-3, atol=1e-3)
+        np.testing.assert_array_equal(info["episode_length"], rinfo["episode_length"])
+        np.testing.assert_allclose(info["episode_reward"], rinfo["episode_reward"], rtol=1e-3, atol=2e-3)
+        dones += int(d.sum())
+        if check_state_every and t % check_state_every == 0:
+            for e in range(0, n, max(1, n // 8)):
+                sg, sr = env.get_state(e)["veh"][0], ref.get_state(e)["veh"][0]
+                k = env.T["episodes"][env.episode_of_seed[int(env.env_seeds[e])]]["n_slots"]
+                for f in ("lane", "ck0", "ck1", "rt_lane", "timer", "rnd_n", "airborne", "flags"):
+                    np.testing.assert_array_equal(sg[f][:k], sr[f][:k], err_msg="state %s env %d step %d" % (f, e, t))
+                for f in ("x", "y", "heading", "speed"):
+                    np.testing.assert_allclose(sg[f][:k], sr[f][:k], rtol=1e-4, atol=2e-3)
+    assert grazing <= max(2, beams * 2e-5), "too many ill-conditioned lidar beams: %d of %d" % (grazing, beams)
+    return dones
+
+
+def _check_lidar(gpu, ref, t):
+    """Beams must agree to 1e-3 of the 50 m range.  The one exception is a ray that grazes a chassis side at a
+    very shallow angle: there d(range)/d(pose) is unbounded and float32 pose round-off (3e-5 m at x ~ 300 m)
+    moves the hit point by centimetres.  Such a beam must still lie between the oracle's neighbouring beams,
+    and the caller bounds how many there may be."""
+    bad = np.abs(gpu - ref) >= OBS_TOL
+    if not bad.any():
+        return 0
+    lo = np.minimum(np.minimum(np.roll(ref, 1, axis=1), np.roll(ref, -1, axis=1)), ref) - OBS_TOL
+    hi = np.maximum(np.maximum(np.roll(ref, 1, axis=1), np.roll(ref, -1, axis=1)), ref) + OBS_TOL
+    inside = (gpu >= lo) & (gpu <= hi)
+    assert inside[bad].all(), "step %d: lidar beam differs by %g and is not a grazing hit" % (
+        t, np.abs(gpu - ref)[bad & ~inside].max())
+    return int(bad.sum())
+
+
+def test_reset_observation_matches_oracle():
+    seeds = list(range(1000, 1100))
+    env, ref = _pair(100, seeds)
+    obs, ro = _reset_both(env, ref)
+    assert np.abs(obs - ro).max() < 1e-5
+    assert obs.min() >= 0.0 and obs.max() <= 1.0
+    # spawn: lane 0 centre of a 3 x 3.5 m road, heading aligned, at rest
+    np.testing.assert_allclose(obs[:, 0], 1.75 / 18, atol=1e-6)
+    np.testing.assert_allclose(obs[:, 1], 8.75 / 18, atol=1e-6)
+    np.testing.assert_allclose(obs[:, 2], 0.5, atol=1e-6)
+    env.close()
+
+
+def test_random_policy_rollout_with_autoreset():
+    seeds = list(range(1000, 1100))
+    n = 400
+    env, ref = _pair(n, seeds)
+    _reset_both(env, ref)
+    rs = np.random.RandomState(1)
+    # BASELINE.json's action distribution: uniform [-1, 1]^2 (half the throttles brake, so cars crawl)
+    _rollout(env, ref, 100, lambda t: rs.uniform(-1, 1, (n, 2)), check_state_every=50)
+
+    def forward(t):  # same steering noise but never braking: leaves the road within tens of steps
+        a = rs.uniform(-1, 1, (n, 2))
+        a[:, 1] = np.abs(a[:, 1])
+        return a
+
+    dones = _rollout(env, ref, 250, forward, check_state_every=50)
+    assert dones > n  # the auto-reset path is exercised many times per env
+    env.close()
+
+
+def test_lane_following_rollout_meets_traffic():
+    """Gentle steering + throttle keeps the ego on the road for hundreds of steps, so traffic is triggered,
+    IDM runs, vehicles are removed at their destination and the lidar sees chassis."""
+    seeds = list(range(1000, 1100))
+    n = 200
+    env, ref = _pair(n, seeds)
+    _reset_both(env, ref)
+    rs = np.random.RandomState(2)
+
+    def act(t):
+        a = np.zeros((n, 2))
+        a[:, 0] = rs.uniform(-0.05, 0.05, n)
+        a[:, 1] = rs.uniform(0.2, 1.0, n)
+        return a
+
+    _rollout(env, ref, 400, act, check_state_every=40)
+    env.close()
+
+
+def test_config1_single_env_seed_1000_no_traffic():
+    """BASELINE.json configs[0]: 1 env, seed 1000, traffic_density 0, RandomState(0) actions, 1000 steps,
+    reset(force_seed=1000) on done -- through the PGDriveEnv drop-in class."""
+    from oracle.oracle import Oracle
+    from pgdrive_b200 import PGDriveEnv
+    from pgdrive_b200.env import build_seed_tables, default_config, parse_map_config
+    env = PGDriveEnv(dict(start_seed=1000, environment_num=100, traffic_density=0.0))
+    T = build_seed_tables([1000], parse_map_config(default_config()), 0.0, ((">", ">>", 0), 5.0, 0.0))
+    ref = Oracle(T, 1, auto_reset=False)
+    o = env.reset(force_seed=1000)
+    ro = ref.reset([0], [0])[0]
+    assert o.dtype == np.float64 and o.shape == (274, )
+    assert np.abs(o - ro).max() < 1e-5
+    actions = np.random.RandomState(0).uniform(-1, 1, (1000, 2)).astype(np.float32)
+    episodes = 0
+    for t in range(1000):
+        o, r, d, info = env.step(actions[t])
+        ro, rr, rd, rinfo = ref.step(actions[t][None])
+        assert d == bool(rd[0]), t
+        assert np.abs(o - ro[0]).max() < OBS_TOL, t
+        assert abs(r - rr[0]) < 1e-3 * max(1.0, abs(rr[0])), t
+        assert info["out_of_road"] == bool(rinfo["flags"][0] & 2)
+        assert env.observation_space.contains(o.astype(np.float32))
+        if d:
+            episodes += 1
+            o = env.reset(force_seed=1000)
+            ro = ref.reset([0], [0])[0]
+            assert np.abs(o - ro).max() < 1e-5
+    assert episodes >= 1
+    env.close()
+
+
+def test_nan_action_is_treated_as_minus_one():
+    """cutils_clip(nan, -1, 1) == -1 (tests/test_component/test_utils.py, test_ego_vehicle.py:78-84)."""
+    import torch
+    env, ref = _pair(4, [1000, 1001])
+    _reset_both(env, ref)
+    a = np.array([[np.nan, 1.0], [0.0, np.nan], [np.nan, np.nan], [5.0, -7.0]], np.float32)
+    for _ in range(12):
+        o, r, d, _ = env.step(torch.from_numpy(a).cuda())
+        ro, rr, rd, _ = ref.step(a)
+        assert np.isfinite(o.cpu().numpy()).all()
+        assert np.abs(o.cpu().numpy() - ro).max() < OBS_TOL
+    info = env.info_numpy()
+    np.testing.assert_allclose(info["steering"], [-1, 0, -1, 1])
+    np.testing.assert_allclose(info["acceleration"], [1, -1, -1, -1])
+    env.close()
+
+
+def test_host_buffer_step_equals_device_step():
+    import torch
+    env_a, _ = _pair(64, [1000, 1001, 1002, 1003])
+    env_b, _ = _pair(64, [1000, 1001, 1002, 1003])
+    env_a.reset()
+    env_b.reset()
+    rs = np.random.RandomState(5)
+    for _ in range(30):
+        a = rs.uniform(-1, 1, (64, 2)).astype(np.float32)
+        o1, r1, d1, i1 = env_a.step(a)
+        o2, r2, d2, _ = env_b.step(torch.from_numpy(a).cuda())
+        np.testing.assert_array_equal(o1, o2.cpu().numpy())
+        np.testing.assert_array_equal(r1, r2.cpu().numpy())
+        np.testing.assert_array_equal(d1, d2.cpu().numpy())
+        np.testing.assert_array_equal(i1["flags"], env_b.info_numpy()["flags"])
+    env_a.close()
+    env_b.close()
+
+
+def test_horizon_and_partial_reset():
+    import torch
+    env, ref = _pair(8, [1000, 1001], horizon=5, auto_reset=False)
+    _reset_both(env, ref)
+    a = np.zeros((8, 2), np.float32)
+    for t in range(5):
+        o, r, d, _ = env.step(torch.from_numpy(a).cuda())
+    assert d.cpu().numpy().all()
+    assert (env.info_numpy()["flags"] & 8).all()  # max_step
+    before = env.obs.cpu().numpy().copy()
+    env.reset(env_ids=[1, 3], seeds=[1001, 1000])
+    after = env.obs.cpu().numpy()
+    assert np.array_equal(before[[0, 2, 4, 5, 6, 7]], after[[0, 2, 4, 5, 6, 7]])
+    assert (env.info_numpy()["flags"][[1, 3]] & 1024).all()  # was_reset
+    o, r, d, _ = env.step(torch.from_numpy(a).cuda())
+    d = d.cpu().numpy()
+    assert not d[1] and not d[3] and d[0]  # done is sticky for the others
+    env.close()
+
+
+def test_state_round_trip_and_v32_slots():
+    import torch
+    env, ref = _pair(6, [1000, 1001, 1002], num_slots=32)
+    _reset_both(env, ref)
+    rs = np.random.RandomState(3)
+    _rollout(env, ref, 40, lambda t: np.c_[rs.uniform(-0.1, 0.1, 6), rs.uniform(0.3, 1, 6)])
+    s = env.get_state(2)
+    env.set_state(4, s)
+    s2 = env.get_state(4)
+    assert s.tobytes() == s2.tobytes()
+    env.close()
