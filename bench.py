@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: env-steps/s of the fused step kernel (BASELINE.json's metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--envs E]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Own arm: every rank steps `--envs` (default 65 536) PGDrive-v0 environments (seeds 1000..1099, traffic density
+0.1, 240-beam lidar, 16 vehicle slots); a "step" is ONE kernel launch advancing all of them by one decision step
+(5 physics sub-steps + observation + reward/done, auto-reset of finished episodes).  Weak scaling: with N ranks
+the job simulates N x 65 536 environments and the observation / reward / done batches are all-gathered (NCCL, in
+place) every step so that rank 0 holds the whole batch.
+  value      device-resident: actions pre-generated in HBM, CUDA-event time of K steps, max over ranks
+  e2e        same steps through the public VecPGDriveEnv.step(numpy) -> pgd_step_host: pinned H2D of the actions
+             and D2H of obs / reward / done / info inside the timed region
+  roofline   algorithmic bytes per env-step (DESIGN.md "Bytes") x envs / average kernel time vs measured HBM peak
+  cpu_baseline  the CPU oracle (oracle/pgd_oracle.c, a scalar port of the same step) on all host cores, bounded sample
+
+Reference arm (--impl reference): the reference's own step runs on Panda3D/Bullet, which is neither vendored nor
+installable offline, so this arm times the CPU oracle port on all host cores on the same config and metric.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOAD = "65536 envs PGDrive-v0 (seeds 1000-1099), traffic_density=0.1, 240-beam lidar, 16 vehicle slots"
+OBS_DIM = 274
+INFO_BYTES = 40
+
+
+def algorithmic_bytes_per_env_step(num_slots):
+    """DESIGN.md 'Bytes moved per env-step': action 8 R + obs 1096 W + reward 4 W + done 1 W + info 40 W, the
+    structure-of-arrays state read and written once (80 B per vehicle slot + 32 B per env, each way), and the
+    map / template records amortised over the environments sharing a map (~80 B, L2-resident)."""
+    io = 8 + 4 * OBS_DIM + 4 + 1 + INFO_BYTES
+    state = 2 * (80 * num_slots + 32)
+    return io + state + 80
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms",
+                 "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True
+            )
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def host_threads():
+    return len(os.sched_getaffinity(0))
+
+
+def cpu_oracle_rate(T, n_envs, steps, warmup, threads, episode_ids, seed=0):
+    """env-steps/s of the CPU oracle on `threads` host threads (uniform [-1,1]^2 actions, auto-reset)."""
+    from oracle.oracle import Oracle
+    ref = Oracle(T, n_envs, auto_reset=True)
+    ref.reset(range(n_envs), episode_ids)
+    rs = np.random.RandomState(seed)
+    acts = rs.uniform(-1, 1, (warmup + steps, n_envs, 2)).astype(np.float32)
+    for t in range(warmup):
+        ref.step(acts[t], threads=threads)
+    t0 = time.perf_counter()
+    for t in range(warmup, warmup + steps):
+        ref.step(acts[t], threads=threads)
+    dt = time.perf_counter() - t0
+    ref.close()
+    return n_envs * steps / dt, dt
+
+
+def build_tables():
+    from pgdrive_b200.env import build_seed_tables, default_config, parse_map_config
+    return build_seed_tables(range(1000, 1100), parse_map_config(default_config()), 0.1, ((">", ">>", 0), 5.0, 0.0))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import oracle as orc
+    orc.build()
+    T = build_tables()
+    threads = host_threads()
+    # calibrate, then size the per-step sample so that warmup + steps finish in about 100 s
+    rate0, _ = cpu_oracle_rate(T, 1024, 4, 1, threads, [i % 100 for i in range(1024)])
+    n = int(min(args.envs, max(256, rate0 * 100.0 / (args.steps + args.warmup))))
+    n = max(100, n // 100 * 100)
+    rate, dt = cpu_oracle_rate(T, n, args.steps, args.warmup, threads, [i % 100 for i in range(n)])
+    sample = "%d of %d envs per step x %d steps, %d host threads" % (n, args.envs, args.steps, threads)
+    line = dict(
+        impl="reference", metric="env-steps/s", value=rate, unit="env-steps/s", n_gpus=args.gpus, steps=args.steps,
+        warmup=args.warmup, ms_per_step=dt / args.steps * 1e3, higher_is_better=True, scaling="weak",
+        vs_baseline=None, dtype="f32", data="synthetic",
+        config=dict(workload=WORKLOAD, envs_per_gpu=args.envs, actions="uniform[-1,1]^2, RandomState(0)",
+                    note="reference step needs Panda3D/Bullet (not installable offline): CPU oracle port timed instead"),
+        cpu_baseline=dict(value=rate, unit="env-steps/s", cores=threads, kind="port", sample=sample),
+        e2e=dict(value=rate, unit="env-steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+    )
+    print(json.dumps(line))
+    return 0
+
+
+def run_own(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus %d needs `python -m torch.distributed.run --nproc-per-node %d`" % (args.gpus, args.gpus))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    import __graft_entry__
+    if rank == 0:
+        __graft_entry__.build()
+    if world > 1:
+        dist.barrier()
+    from pgdrive_b200 import VecPGDriveEnv, cabi
+    n, K, W = args.envs, args.steps, args.warmup
+    T = build_tables()
+    # weak scaling: rank r owns environments [r*n, (r+1)*n) of the global batch; the kernel writes its observations
+    # straight into this rank's slice of the gather buffer (in-place all-gather, no packing kernel)
+    g_obs = torch.empty((world * n, OBS_DIM), dtype=torch.float32, device=dev)
+    g_rew = torch.empty(world * n, dtype=torch.float32, device=dev)
+    g_done = torch.empty(world * n, dtype=torch.uint8, device=dev)
+    env = VecPGDriveEnv(
+        dict(start_seed=1000, environment_num=100, num_envs=n, traffic_density=0.1, device=local_rank, num_slots=16),
+        tables_dict=T, obs_out=g_obs[rank * n:(rank + 1) * n]
+    )
+    env.reset()
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)  # Philox counter-based stream, one per rank
+    actions = torch.rand((W + K, n, 2), generator=gen, device=dev, dtype=torch.float32) * 2 - 1
+
+    def gather():
+        if world > 1:
+            g_rew[rank * n:(rank + 1) * n].copy_(env.reward)
+            g_done[rank * n:(rank + 1) * n].copy_(env.done)
+            dist.all_gather_into_tensor(g_obs, g_obs[rank * n:(rank + 1) * n])
+            dist.all_gather_into_tensor(g_rew, g_rew[rank * n:(rank + 1) * n])
+            dist.all_gather_into_tensor(g_done, g_done[rank * n:(rank + 1) * n])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for t in range(W):
+        env.step(actions[t])
+        gather()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+        time.sleep(0.3)
+    launches0 = env.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    barrier()
+    ev0.record()
+    for t in range(K):
+        k_ev[t][0].record()
+        env.step(actions[W + t])
+        k_ev[t][1].record()
+        gather()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in k_ev]))
+    launches = env.launch_count - launches0
+    clk = clocks.stop() if rank == 0 else None
+    done_rate = float(env.done.float().mean().item())
+
+    # ---- end to end through the public host-buffer API (pinned H2D actions, D2H results every step) ----
+    h_actions = actions[W:W + K].cpu().numpy()
+    e2e_steps = min(K, 64)
+    for t in range(min(W, 4)):
+        env.step(h_actions[t])
+    barrier()
+    t0 = time.perf_counter()
+    for t in range(e2e_steps):
+        o, r, d, i = env.step(h_actions[t])
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    checksum = float(o[:, :8].sum())
+
+    times = torch.tensor([ms, e2e_s * 1e3, kernel_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms, e2e_ms, kernel_ms = [float(x) for x in times.tolist()]
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    total_envs = world * n
+    value = total_envs * K / (ms * 1e-3)
+    b_step = algorithmic_bytes_per_env_step(16)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    achieved = b_step * n / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("bytes_per_launch")
+
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        threads = host_threads()
+        cn, cs = 8192, 24
+        rate, dt = cpu_oracle_rate(T, cn, cs, 2, threads, [i % 100 for i in range(cn)])
+        cpu = dict(value=rate, unit="env-steps/s", cores=threads, kind="port",
+                   sample="%d of %d envs x %d steps (%.1f s), CPU oracle on %d host threads" % (cn, n, cs, dt, threads))
+
+    line = dict(
+        metric="env-steps/s", value=value, unit="env-steps/s", n_gpus=world, steps=K, warmup=W,
+        ms_per_step=ms / K, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+        config=dict(
+            workload=WORKLOAD, envs_per_gpu=n, total_envs=total_envs, parallelism="env-sharded x%d" % world,
+            actions="uniform[-1,1]^2, Philox, pre-generated in HBM",
+            l2="no flush: state + observations touched per step = %.0f MB > 126 MB L2" % (
+                (2 * (80 * 16 + 32) + 4 * OBS_DIM) * n / 1e6),
+            collective="in-place NCCL all-gather of obs/reward/done every step" if world > 1 else "none",
+            done_rate_last_step=done_rate,
+        ),
+        roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
+                      kernel="pgd_step_kernel<16>", kernel_ms=kernel_ms, bytes_per_env_step=b_step, peak_source=peak_src),
+        cpu_baseline=cpu,
+        e2e=dict(value=total_envs * e2e_steps / (e2e_ms * 1e-3), unit="env-steps/s",
+                 h2d_bytes_per_step=n * 8, d2h_bytes_per_step=n * (4 * OBS_DIM + 4 + 1 + INFO_BYTES),
+                 steps=e2e_steps, api="VecPGDriveEnv.step(numpy) -> pgd_step_host", checksum=checksum),
+        gpu_launches=int(launches), clocks=clk,
+    )
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=256)
+    ap.add_argument("--warmup", type=int, default=32)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--envs", type=int, default=65536, help="environments per GPU")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_own(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -194,8 +194,7 @@ struct EnvShared {
   int lane[V];
   int alive[V];
   float sx[V], sy[V], ex[V], ey[V], llen[V];  // start / end / length of the lane each vehicle is on
-  float navi[10];
-  float red[4];
+  int blo[V], bn[V];               // lidar: first beam index and beam count each chassis can intersect
   int ired[4];
 };
 
@@ -633,20 +632,59 @@ pgd_step_kernel(DevTables T, DevState S, PgdConfig cfg, int mode, const float2* 
 
   // ---- phase F: observation, reward, done -----------------------------------------------------------------------
   float* ob = obs + (size_t)env * PGD_OBS_DIM;
-  // lidar: beam i = slot + V * k, against every other live chassis
-  if (!skip) {
-    for (int i = slot; i < PGD_LIDAR_BEAMS; i += V) {
-      const float ang = (float)i * (TWO_PI_F / (float)PGD_LIDAR_BEAMS) + eh;
-      float s, c;
-      sincosf(ang, &s, &c);
-      const float dx = c * LIDAR_RANGE, dy = s * LIDAR_RANGE;
-      float best = 1.0f;
-      for (int j = 1; j < n_slots; ++j) {
-        if (!sh.alive[j]) continue;
-        const Rect r = {sh.x[j], sh.y[j], sh.ux[j], sh.uy[j], sh.hl[j], sh.hw[j]};
-        best = fminf(best, ray_rect(ex_, ey_, dx, dy, r));
+  // lidar: beam i = slot + V * k.  Each chassis first publishes the (conservative) arc of beams that can reach it:
+  // it lies inside the disc of radius half-diagonal around its centre, so only beams within asin(hd / d) of its
+  // bearing and only chassis closer than 50 m + hd matter.  The cull never changes a result (the reference's own
+  // angular mask has the same property, tests/test_component/test_detector_mask.py:308-311).
+  {
+    int blo = 0, bn = -1;
+    if (alive && slot != 0) {
+      const float dx = x - ex_, dy = y - ey_;
+      const float d2 = dx * dx + dy * dy;
+      const float hd = sqrtf(half_l * half_l + half_w * half_w);
+      const float reach = LIDAR_RANGE + hd;
+      if (d2 < reach * reach) {
+        const float d = sqrtf(d2);
+        bn = PGD_LIDAR_BEAMS;
+        if (d > hd * 1.001f) {
+          const float per_rad = (float)PGD_LIDAR_BEAMS / TWO_PI_F;
+          const float c = (atan2f(dy, dx) - eh) * per_rad;
+          const float w = asinf(fminf(hd / d, 1.0f)) * per_rad;
+          const int n = (int)ceilf(2.0f * w) + 3;
+          if (n < PGD_LIDAR_BEAMS) {
+            bn = n;
+            blo = ((int)floorf(c - w) - 1) % PGD_LIDAR_BEAMS;
+            if (blo < 0) blo += PGD_LIDAR_BEAMS;
+          }
+        }
       }
-      ob[34 + i] = best;
+    }
+    sh.blo[slot] = blo;
+    sh.bn[slot] = bn;
+    __syncwarp(group_mask);
+    const unsigned near_all = __ballot_sync(group_mask, bn >= 0);
+    const unsigned near = (V == 32) ? near_all : ((near_all >> (lane_id & 16)) & 0xffffu);
+    if (!skip) {
+      for (int i = slot; i < PGD_LIDAR_BEAMS; i += V) {
+        float best = 1.0f;
+        unsigned m = near;
+        if (m) {
+          const float ang = (float)i * (TWO_PI_F / (float)PGD_LIDAR_BEAMS) + eh;
+          float s, c;
+          sincosf(ang, &s, &c);
+          const float dx = c * LIDAR_RANGE, dy = s * LIDAR_RANGE;
+          while (m) {
+            const int j = __ffs(m) - 1;
+            m &= m - 1;
+            int rel = i - sh.blo[j];
+            if (rel < 0) rel += PGD_LIDAR_BEAMS;
+            if (rel > sh.bn[j]) continue;
+            const Rect r = {sh.x[j], sh.y[j], sh.ux[j], sh.uy[j], sh.hl[j], sh.hw[j]};
+            best = fminf(best, ray_rect(ex_, ey_, dx, dy, r));
+          }
+        }
+        ob[34 + i] = best;
+      }
     }
   }
   if (slot == 0) {
@@ -1022,6 +1060,15 @@ static int ensure_staging(PgdHandle* h) {
   return 0;
 }
 
+static bool is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
 extern "C" int pgd_step_host(PgdHandle* h, const float* actions, float* obs, float* reward, uint8_t* done,
                              PgdInfo* info) {
   if (!h || !actions || !obs || !reward || !done) return fail(-1, "pgd_step_host: null argument");
@@ -1031,19 +1078,23 @@ extern "C" int pgd_step_host(PgdHandle* h, const float* actions, float* obs, flo
   if (rc) return rc;
   const size_t n = (size_t)h->cfg.num_envs;
   cudaStream_t st = h->own_stream;
+  // Page-locked caller buffers are DMA targets themselves; pageable ones go through the handle's pinned staging.
+  const bool direct = is_pinned(obs) && is_pinned(reward) && is_pinned(done) && (!info || is_pinned(info));
   memcpy(h->h_act, actions, n * 8);
   CU(cudaMemcpyAsync(h->d_act, h->h_act, n * 8, cudaMemcpyHostToDevice, st));
   rc = launch_step(h, 0, h->d_act, h->d_obs, h->d_rew, h->d_done, info ? h->d_info : nullptr, st);
   if (rc) return rc;
-  CU(cudaMemcpyAsync(h->h_obs, h->d_obs, n * PGD_OBS_DIM * 4, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(h->h_rew, h->d_rew, n * 4, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(h->h_done, h->d_done, n, cudaMemcpyDeviceToHost, st));
-  if (info) CU(cudaMemcpyAsync(h->h_info, h->d_info, n * sizeof(PgdInfo), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(direct ? obs : h->h_obs, h->d_obs, n * PGD_OBS_DIM * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(direct ? reward : h->h_rew, h->d_rew, n * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(direct ? done : h->h_done, h->d_done, n, cudaMemcpyDeviceToHost, st));
+  if (info) CU(cudaMemcpyAsync(direct ? info : h->h_info, h->d_info, n * sizeof(PgdInfo), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
-  memcpy(obs, h->h_obs, n * PGD_OBS_DIM * 4);
-  memcpy(reward, h->h_rew, n * 4);
-  memcpy(done, h->h_done, n);
-  if (info) memcpy(info, h->h_info, n * sizeof(PgdInfo));
+  if (!direct) {
+    memcpy(obs, h->h_obs, n * PGD_OBS_DIM * 4);
+    memcpy(reward, h->h_rew, n * 4);
+    memcpy(done, h->h_done, n);
+    if (info) memcpy(info, h->h_info, n * sizeof(PgdInfo));
+  }
   return 0;
 }
 

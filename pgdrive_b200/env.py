@@ -201,10 +201,15 @@ class VecPGDriveEnv:
         self.reward = torch.zeros(n, dtype=torch.float32, device=dev)
         self.done = torch.zeros(n, dtype=torch.uint8, device=dev)
         self.info = torch.zeros((n, cabi.INFO_DT.itemsize // 4), dtype=torch.int32, device=dev)
-        self._h_obs = np.empty((n, cabi.OBS_DIM), np.float32)
-        self._h_reward = np.empty(n, np.float32)
-        self._h_done = np.empty(n, np.uint8)
-        self._h_info = np.empty(n, cabi.INFO_DT)
+        # host-path results live in page-locked memory so that pgd_step_host can DMA straight into them
+        self._pinned = [
+            torch.empty((n, cabi.OBS_DIM), dtype=torch.float32, pin_memory=True),
+            torch.empty(n, dtype=torch.float32, pin_memory=True),
+            torch.empty(n, dtype=torch.uint8, pin_memory=True),
+            torch.empty((n, cabi.INFO_DT.itemsize // 4), dtype=torch.int32, pin_memory=True),
+        ]
+        self._h_obs, self._h_reward, self._h_done = [t.numpy() for t in self._pinned[:3]]
+        self._h_info = self._pinned[3].numpy().view(cabi.INFO_DT).reshape(n)
         self.observation_space = Box(-0.0, 1.0, shape=(cabi.OBS_DIM, ), dtype=np.float32)
         self.action_space = Box(-1.0, 1.0, shape=(2, ), dtype=np.float32)
         self.env_seeds = np.array([self.start_seed + i % self.env_num for i in range(n)], dtype=np.int64)
