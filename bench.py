@@ -173,12 +173,11 @@ def run_own(args):
     T = build_tables()
     # weak scaling: rank r owns environments [r*n, (r+1)*n) of the global batch; the kernel writes its observations
     # straight into this rank's slice of the gather buffer (in-place all-gather, no packing kernel)
-    g_obs = torch.empty((world * n, OBS_DIM), dtype=torch.float32, device=dev)
-    g_rew = torch.empty(world * n, dtype=torch.float32, device=dev)
-    g_done = torch.empty(world * n, dtype=torch.uint8, device=dev)
+    from pgdrive_b200.sharding import GatherBuffers
+    buf = GatherBuffers(torch, n, world, rank, dev, obs_dim=OBS_DIM)
     env = VecPGDriveEnv(
         dict(start_seed=1000, environment_num=100, num_envs=n, traffic_density=0.1, device=local_rank, num_slots=16),
-        tables_dict=T, obs_out=g_obs[rank * n:(rank + 1) * n]
+        tables_dict=T, obs_out=buf.local(buf.obs)
     )
     env.reset()
     gen = torch.Generator(device=dev)
@@ -187,11 +186,9 @@ def run_own(args):
 
     def gather():
         if world > 1:
-            g_rew[rank * n:(rank + 1) * n].copy_(env.reward)
-            g_done[rank * n:(rank + 1) * n].copy_(env.done)
-            dist.all_gather_into_tensor(g_obs, g_obs[rank * n:(rank + 1) * n])
-            dist.all_gather_into_tensor(g_rew, g_rew[rank * n:(rank + 1) * n])
-            dist.all_gather_into_tensor(g_done, g_done[rank * n:(rank + 1) * n])
+            buf.local(buf.reward).copy_(env.reward)
+            buf.local(buf.done).copy_(env.done)
+            buf.all_gather(dist)
 
     def barrier():
         if world > 1:

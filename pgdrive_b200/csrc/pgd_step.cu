@@ -16,6 +16,7 @@
 //   F  observation (state, navi, 4 neighbours, 240-beam lidar), reward, done   state_obs.py:58-170, pgdrive_env.py:162-258
 //   G  store state
 #include <cuda_runtime.h>
+#include <limits.h>
 #include <math_constants.h>
 #include <stdint.h>
 #include <string.h>
@@ -195,6 +196,8 @@ struct EnvShared {
   int alive[V];
   float sx[V], sy[V], ex[V], ey[V], llen[V];  // start / end / length of the lane each vehicle is on
   int blo[V], bn[V];               // lidar: first beam index and beam count each chassis can intersect
+  int croad[V], nroad[V];          // localisation: current / next route road of each moving vehicle
+  float d2[V];                     // squared centre distance to the ego (neighbour ranking)
   int ired[4];
 };
 
@@ -544,91 +547,95 @@ pgd_step_kernel(DevTables T, DevState S, PgdConfig cfg, int mode, const float2* 
   // ---- phase E: after_step -------------------------------------------------------------------------------------
   float hs, hc;
   sincosf(h, &hs, &hc);
-  // localisation of every moving vehicle (ego always; traffic once awake)
-  if (alive && active) {
-    const int cur_road = __ldg(&rroads[ck0]);
-    const int next_road = (ck0 == ck1) ? -1 : __ldg(&rroads[ck1]);
-    int first_any = -1, first_cur = -1, first_next = -1;
-    const int cx = (int)floorf((x - mp.x0) * mp.inv_cell), cy = (int)floorf((y - mp.y0) * mp.inv_cell);
-    if (cx >= 0 && cy >= 0 && cx < mp.nx && cy < mp.ny) {
-      const int cell = mp.cell_off + cy * mp.nx + cx;
-      const int b0 = __ldg(&T.cell_start[cell]), b1 = __ldg(&T.cell_start[cell + 1]);
-      const int32_t* ent = T.cell_entries + mp.entry_off;
-      for (int k = b0; k < b1; ++k) {
-        const int b = __ldg(&ent[k]);
-        const float4 g0 = __ldg(reinterpret_cast<const float4*>(boxes + b));
-        const float4 g1 = __ldg(reinterpret_cast<const float4*>(boxes + b) + 1);  // hl, hw, kind, lane
-        if (__float_as_int(g1.z) != PGD_BOX_LANE) continue;
-        const float dx = x - g0.x, dy = y - g0.y;
-        if (!(fabsf(dx * g0.z + dy * g0.w) <= g1.x && fabsf(-dx * g0.w + dy * g0.z) <= g1.y)) continue;
-        const int bl = __float_as_int(g1.w);
-        const Lane l = load_lane(lanes + bl);
-        float lon, lat;
-        lane_local(l, x, y, lon, lat);
-        const float lh = lane_heading_at(l, lon);
-        float ls, lc;
-        sincosf(lh, &ls, &lc);
-        if (!(lc * hc + ls * hs > 0.0f)) continue;
-        if (first_any < 0) first_any = bl;
-        if (first_cur < 0 && l.road == cur_road) first_cur = bl;
-        if (first_next < 0 && l.road == next_road) first_next = bl;
-      }
-    }
-    int nl = first_cur >= 0 ? first_cur : (first_next >= 0 ? first_next : first_any);
-    bool on_lane = true;
-    if (nl < 0) { on_lane = false; nl = lane; }
-    lane = nl;
-    if (ck0 != ck1) {
-      const Lane l = load_lane(lanes + lane);
-      float lon, lat;
-      lane_local(l, x, y, lon, lat);
-      const int start = __ldg(&roads[l.road].start_node);
-      if (lon < 5.0f) {
-        for (int j = ck1; j < route_len - 1; ++j) {
-          if (__ldg(&rnodes[j]) == start) {
-            ck0 = j;
-            ck1 = (j + 1 == route_len - 1) ? j : j + 1;
-            break;
+  const bool moving = alive && active;  // vehicles that get an after_step: the ego always, traffic once awake
+  // publish end-of-step poses and what localisation needs from each moving vehicle
+  sh.x[slot] = x; sh.y[slot] = y; sh.h[slot] = h; sh.v[slot] = v;
+  sh.ux[slot] = hc; sh.uy[slot] = hs;
+  sh.croad[slot] = moving ? __ldg(&rroads[ck0]) : -1;
+  sh.nroad[slot] = (moving && ck0 != ck1) ? __ldg(&rroads[ck1]) : -1;
+  __syncwarp(group_mask);
+  const float ex_ = sh.x[0], ey_ = sh.y[0], eux = sh.ux[0], euy = sh.uy[0], eh = sh.h[0];
+  uint32_t flags = 0;
+  {
+    // The V threads scan one vehicle's bucket together (entry k = b0 + slot, + V, ...): point-in-rectangle against
+    // lane surfaces for localisation and, for the ego, chassis-vs-rectangle for line ghosts and sidewalks.  The
+    // candidate kept per category is the one with the lowest table index, as a sequential scan would find first.
+    const unsigned need_all = __ballot_sync(group_mask, moving);
+    unsigned need = (V == 32) ? need_all : ((need_all >> (lane_id & 16)) & 0xffffu);
+    const Rect er = {ex_, ey_, eux, euy, sh.hl[0], sh.hw[0]};
+    const int32_t* ent = T.cell_entries + mp.entry_off;
+    int my_any = INT_MAX, my_cur = INT_MAX, my_next = INT_MAX;
+    while (need) {
+      const int t = __ffs(need) - 1;
+      need &= need - 1;
+      const float vx = sh.x[t], vy = sh.y[t], vc = sh.ux[t], vs = sh.uy[t];
+      const int cur_road = sh.croad[t], next_road = sh.nroad[t];
+      int b_any = INT_MAX, b_cur = INT_MAX, b_next = INT_MAX;
+      const int cx = (int)floorf((vx - mp.x0) * mp.inv_cell), cy = (int)floorf((vy - mp.y0) * mp.inv_cell);
+      if (cx >= 0 && cy >= 0 && cx < mp.nx && cy < mp.ny) {
+        const int cell = mp.cell_off + cy * mp.nx + cx;
+        const int b0 = __ldg(&T.cell_start[cell]), b1 = __ldg(&T.cell_start[cell + 1]);
+        for (int k = b0 + slot; k < b1; k += V) {
+          const int b = __ldg(&ent[k]);
+          const float4 g0 = __ldg(reinterpret_cast<const float4*>(boxes + b));
+          const float4 g1 = __ldg(reinterpret_cast<const float4*>(boxes + b) + 1);  // hl, hw, kind, lane
+          const int kind = __float_as_int(g1.z);
+          if (kind == PGD_BOX_LANE) {
+            const float dx = vx - g0.x, dy = vy - g0.y;
+            if (!(fabsf(dx * g0.z + dy * g0.w) <= g1.x && fabsf(-dx * g0.w + dy * g0.z) <= g1.y)) continue;
+            const Lane l = load_lane(lanes + __float_as_int(g1.w));
+            float lon, lat;
+            lane_local(l, vx, vy, lon, lat);
+            float ls, lc;
+            sincosf(lane_heading_at(l, lon), &ls, &lc);
+            if (!(lc * vc + ls * vs > 0.0f)) continue;
+            b_any = min(b_any, b);
+            if (l.road == cur_road) b_cur = min(b_cur, b);
+            if (l.road == next_road) b_next = min(b_next, b);
+          } else if (t == 0) {
+            const Rect r = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y};
+            if (!rect_overlap(er, r)) continue;
+            flags |= kind == PGD_BOX_WHITE ? PGD_F_ON_WHITE
+                   : kind == PGD_BOX_YELLOW ? PGD_F_ON_YELLOW
+                   : kind == PGD_BOX_BROKEN ? PGD_F_ON_BROKEN : PGD_F_CRASH_SIDEWALK;
           }
         }
       }
-    }
-    vflags = on_lane ? (vflags | PGD_V_ON_LANE) : (vflags & ~PGD_V_ON_LANE);
-    if (slot != 0 && !on_lane) alive = false;  // traffic_manager.py:91-109
-  }
-  // publish end-of-step chassis rectangles
-  sh.x[slot] = x; sh.y[slot] = y; sh.h[slot] = h; sh.v[slot] = v;
-  sh.ux[slot] = hc; sh.uy[slot] = hs;
-  sh.alive[slot] = alive;
-  if (slot == 0) { sh.lane[0] = lane; sh.ired[0] = ck0; sh.ired[1] = ck1; sh.ired[2] = vflags; }
-  __syncwarp(group_mask);
-
-  // ego chassis vs line ghosts / sidewalks: the ego's bucket is scanned by all V threads
-  const float ex_ = sh.x[0], ey_ = sh.y[0], eux = sh.ux[0], euy = sh.uy[0], eh = sh.h[0], ev = sh.v[0];
-  uint32_t flags = 0;
-  {
-    const Rect er = {ex_, ey_, eux, euy, sh.hl[0], sh.hw[0]};
-    const int cx = (int)floorf((ex_ - mp.x0) * mp.inv_cell), cy = (int)floorf((ey_ - mp.y0) * mp.inv_cell);
-    if (cx >= 0 && cy >= 0 && cx < mp.nx && cy < mp.ny) {
-      const int cell = mp.cell_off + cy * mp.nx + cx;
-      const int b0 = __ldg(&T.cell_start[cell]), b1 = __ldg(&T.cell_start[cell + 1]);
-      const int32_t* ent = T.cell_entries + mp.entry_off;
-      for (int k = b0 + slot; k < b1; k += V) {
-        const int b = __ldg(&ent[k]);
-        const float4 g0 = __ldg(reinterpret_cast<const float4*>(boxes + b));
-        const float4 g1 = __ldg(reinterpret_cast<const float4*>(boxes + b) + 1);
-        const int kind = __float_as_int(g1.z);
-        if (kind == PGD_BOX_LANE) continue;
-        const Rect r = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y};
-        if (!rect_overlap(er, r)) continue;
-        flags |= kind == PGD_BOX_WHITE ? PGD_F_ON_WHITE
-               : kind == PGD_BOX_YELLOW ? PGD_F_ON_YELLOW
-               : kind == PGD_BOX_BROKEN ? PGD_F_ON_BROKEN : PGD_F_CRASH_SIDEWALK;
+#pragma unroll
+      for (int o = V / 2; o > 0; o >>= 1) {
+        b_any = min(b_any, __shfl_xor_sync(group_mask, b_any, o, V));
+        b_cur = min(b_cur, __shfl_xor_sync(group_mask, b_cur, o, V));
+        b_next = min(b_next, __shfl_xor_sync(group_mask, b_next, o, V));
       }
+      if (slot == t) { my_any = b_any; my_cur = b_cur; my_next = b_next; }
     }
 #pragma unroll
     for (int o = V / 2; o > 0; o >>= 1) flags |= __shfl_xor_sync(group_mask, flags, o, V);
+    if (moving) {
+      const int nb = my_cur != INT_MAX ? my_cur : (my_next != INT_MAX ? my_next : my_any);
+      bool on_lane = nb != INT_MAX;
+      if (on_lane) lane = __ldg(&boxes[nb].lane);
+      if (ck0 != ck1) {  // _update_target_checkpoints
+        const Lane l = load_lane(lanes + lane);
+        float lon, lat;
+        lane_local(l, x, y, lon, lat);
+        const int start = __ldg(&roads[l.road].start_node);
+        if (lon < 5.0f) {
+          for (int j = ck1; j < route_len - 1; ++j) {
+            if (__ldg(&rnodes[j]) == start) {
+              ck0 = j;
+              ck1 = (j + 1 == route_len - 1) ? j : j + 1;
+              break;
+            }
+          }
+        }
+      }
+      vflags = on_lane ? (vflags | PGD_V_ON_LANE) : (vflags & ~PGD_V_ON_LANE);
+      if (slot != 0 && !on_lane) alive = false;  // traffic_manager.py:91-109
+    }
   }
+  sh.alive[slot] = alive;
+  __syncwarp(group_mask);
 
   // ---- phase F: observation, reward, done -----------------------------------------------------------------------
   float* ob = obs + (size_t)env * PGD_OBS_DIM;
@@ -684,6 +691,48 @@ pgd_step_kernel(DevTables T, DevState S, PgdConfig cfg, int mode, const float2* 
           }
         }
         ob[34 + i] = best;
+      }
+    }
+  }
+  // the 4 nearest vehicles inside the 50 m cylinder (lidar.py:55-77): every chassis ranks itself by centre distance
+  // (ties -> lower slot, like a stable selection) and the 4 best write their own features
+  {
+    float myd2 = CUDART_INF_F;
+    if (alive && slot != 0) {
+      const float dx = x - ex_, dy = y - ey_;
+      const float d2 = dx * dx + dy * dy;
+      if (d2 < LIDAR_RANGE * LIDAR_RANGE) myd2 = d2;
+    }
+    sh.d2[slot] = myd2;
+    __syncwarp(group_mask);
+    const bool in_range = myd2 < CUDART_INF_F;
+    const unsigned near_all = __ballot_sync(group_mask, in_range);
+    const int n_near = __popc((V == 32) ? near_all : ((near_all >> (lane_id & 16)) & 0xffffu));
+    if (!skip) {
+      if (in_range) {
+        int rank = 0;
+        for (int j = 1; j < V; ++j) {
+          const float o = sh.d2[j];
+          rank += (o < myd2 || (o == myd2 && j < slot)) ? 1 : 0;
+        }
+        if (rank < 4) {
+          const float esp = clipf(sh.v[0] * 3.6f, 0.0f, 100000.0f);
+          float pf, ps, vf, vs;
+          project(eux, euy, x - ex_, y - ey_, pf, ps);
+          const float ws = clipf(v * 3.6f, 0.0f, 100000.0f);
+          project(eux, euy, ws * hc - esp * eux, ws * hs - esp * euy, vf, vs);
+          float4 q;
+          q.x = clipf((pf / LIDAR_RANGE + 1.0f) / 2.0f, 0.0f, 1.0f);
+          q.y = clipf((ps / LIDAR_RANGE + 1.0f) / 2.0f, 0.0f, 1.0f);
+          q.z = clipf((vf / MAX_SPEED_KMH + 1.0f) / 2.0f, 0.0f, 1.0f);
+          q.w = clipf((vs / MAX_SPEED_KMH + 1.0f) / 2.0f, 0.0f, 1.0f);
+          float* o4 = ob + 18 + 4 * rank;
+          o4[0] = q.x; o4[1] = q.y; o4[2] = q.z; o4[3] = q.w;
+        }
+      }
+      if (slot < 4 && slot >= n_near) {
+        float* o4 = ob + 18 + 4 * slot;
+        o4[0] = o4[1] = o4[2] = o4[3] = 0.0f;
       }
     }
   }
@@ -758,32 +807,6 @@ pgd_step_kernel(DevTables T, DevState S, PgdConfig cfg, int mode, const float2* 
       q[3] = clipf((dir + 1.0f) / 2.0f, 0.0f, 1.0f);
       q[4] = clipf((angle * (180.0f / PI_F) / 135.0f + 1.0f) / 2.0f, 0.0f, 1.0f);
     }
-    // the 4 nearest vehicles inside the 50 m cylinder
-    float o16[16];
-    {
-      unsigned taken = 1u;  // slot 0 = self
-      for (int q4 = 0; q4 < 4; ++q4) {
-        int best = -1;
-        float bd = LIDAR_RANGE * LIDAR_RANGE;
-        for (int j = 1; j < n_slots; ++j) {
-          if (!sh.alive[j] || (taken >> j & 1u)) continue;
-          const float dx = sh.x[j] - x, dy = sh.y[j] - y;
-          const float d2 = dx * dx + dy * dy;
-          if (d2 < bd) { bd = d2; best = j; }
-        }
-        float* q = o16 + 4 * q4;
-        if (best < 0) { q[0] = q[1] = q[2] = q[3] = 0.0f; continue; }
-        taken |= 1u << best;
-        float pf, ps, vf, vs;
-        project(hc, hs, sh.x[best] - x, sh.y[best] - y, pf, ps);
-        const float ws = clipf(sh.v[best] * 3.6f, 0.0f, 100000.0f);
-        project(hc, hs, ws * sh.ux[best] - sp * hc, ws * sh.uy[best] - sp * hs, vf, vs);
-        q[0] = clipf((pf / LIDAR_RANGE + 1.0f) / 2.0f, 0.0f, 1.0f);
-        q[1] = clipf((ps / LIDAR_RANGE + 1.0f) / 2.0f, 0.0f, 1.0f);
-        q[2] = clipf((vf / MAX_SPEED_KMH + 1.0f) / 2.0f, 0.0f, 1.0f);
-        q[3] = clipf((vs / MAX_SPEED_KMH + 1.0f) / 2.0f, 0.0f, 1.0f);
-      }
-    }
     // reward / cost / done
     float r = 0.0f, step_reward = 0.0f, cost = 0.0f, step_energy = 0.0f;
     int is_done = 0;
@@ -821,8 +844,6 @@ pgd_step_kernel(DevTables T, DevState S, PgdConfig cfg, int mode, const float2* 
     if (!skip) {
 #pragma unroll
       for (int k = 0; k < 18; ++k) ob[k] = o18[k];
-#pragma unroll
-      for (int k = 0; k < 16; ++k) ob[18 + k] = o16[k];
       if (mode == 0) {
         reward[env] = r;
         done[env] = (uint8_t)is_done;
