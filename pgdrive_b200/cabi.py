@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libpgdrive_b200.so")
+LIB_PATH = os.environ.get("PGDRIVE_B200_LIB") or os.path.join(HERE, "csrc", "libpgdrive_b200.so")
 
 OBS_DIM = 274
 MAX_SLOTS = 32

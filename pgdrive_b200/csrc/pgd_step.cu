@@ -40,6 +40,9 @@
 #define YAW_TAU 0.1f
 
 #define CTA_THREADS 128
+#ifndef MIN_CTAS_PER_SM
+#define MIN_CTAS_PER_SM 4
+#endif
 #define DONE_PENDING_RESET 2
 
 struct DevTables {
@@ -195,6 +198,7 @@ struct EnvShared {
   int lane[V];
   int alive[V];
   float sx[V], sy[V], ex[V], ey[V], llen[V];  // start / end / length of the lane each vehicle is on
+  float olong[V];                  // longitudinal coordinate of each vehicle on its own lane (start of step)
   int blo[V], bn[V];               // lidar: first beam index and beam count each chassis can intersect
   int croad[V], nroad[V];          // localisation: current / next route road of each moving vehicle
   float d2[V];                     // squared centre distance to the ego (neighbour ranking)
@@ -211,7 +215,7 @@ struct Sub {  // what one physics sub-step needs, hoisted out of the sub-step lo
 
 // ------------------------------------------------------------------------------------------------------------------
 template <int V>
-__global__ void __launch_bounds__(CTA_THREADS)
+__global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PER_SM)
 pgd_step_kernel(DevTables T, DevState S, PgdConfig cfg, int mode, const float2* __restrict__ actions,
                 float* __restrict__ obs, float* __restrict__ reward, uint8_t* __restrict__ done,
                 PgdInfo* __restrict__ info) {
@@ -294,6 +298,9 @@ pgd_step_kernel(DevTables T, DevState S, PgdConfig cfg, int mode, const float2* 
     if (alive) {
       const Lane l = load_lane(lanes + lane);
       sh.sx[slot] = l.sx; sh.sy[slot] = l.sy; sh.ex[slot] = l.ex; sh.ey[slot] = l.ey; sh.llen[slot] = l.length;
+      float lon, lat;
+      lane_local(l, x, y, lon, lat);
+      sh.olong[slot] = lon;
     }
   }
   __syncwarp(group_mask);
@@ -370,23 +377,17 @@ pgd_step_kernel(DevTables T, DevState S, PgdConfig cfg, int mode, const float2* 
           const float ox = sh.x[j], oy = sh.y[j];
           const float ddx = ox - x, ddy = oy - y;
           if (!(ddx * ddx + ddy * ddy < LIDAR_RANGE * LIDAR_RANGE)) continue;
+          // every branch needs only the neighbour's longitudinal coordinate ON ITS OWN LANE (published by its
+          // thread): same lane -> directly; following lane -> + what is left of mine; preceding lane -> its remainder
           if (sh.lane[j] == cand[i]) {
-            float lg;
-            lane_local(l, ox, oy, lg, lat);
-            lg -= cur_long;
+            const float lg = sh.olong[j] - cur_long;
             if (fdist[i] > lg && lg > 0.0f) { fdist[i] = lg; front[i] = j; found_front = true; }
             if (lg < 0.0f && fabsf(lg) < bdist[i]) { bdist[i] = fabsf(lg); back[i] = j; found_back = true; }
           } else if (!found_front && precedes(l.ex, l.ey, sh.sx[j], sh.sy[j])) {
-            const Lane ol = load_lane(lanes + sh.lane[j]);
-            float lg;
-            lane_local(ol, ox, oy, lg, lat);
-            lg += left_long;
+            const float lg = sh.olong[j] + left_long;
             if (fdist[i] > lg && lg > 0.0f) { fdist[i] = lg; front[i] = j; }
           } else if (!found_back && precedes(sh.ex[j], sh.ey[j], l.sx, l.sy)) {
-            const Lane ol = load_lane(lanes + sh.lane[j]);
-            float lg;
-            lane_local(ol, ox, oy, lg, lat);
-            lg = ol.length - lg + cur_long;
+            const float lg = sh.llen[j] - sh.olong[j] + cur_long;
             if (bdist[i] > lg) { bdist[i] = lg; back[i] = j; }
           }
         }

@@ -1,0 +1,23 @@
+"""Device-resident timing of the step kernel only (A/B of kernel variants):  PGDRIVE_B200_LIB=... python tools/quick_bench.py"""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import bench
+from pgdrive_b200 import VecPGDriveEnv
+n = int(os.environ.get("ENVS", 65536)); K = int(os.environ.get("STEPS", 200)); W = 40
+T = bench.build_tables()
+env = VecPGDriveEnv(dict(start_seed=1000, environment_num=100, num_envs=n, traffic_density=0.1, num_slots=16), tables_dict=T)
+env.reset()
+mode = os.environ.get("ACTIONS", "uniform")
+g = torch.Generator(device="cuda"); g.manual_seed(1)
+a = torch.rand((W + K, n, 2), generator=g, device="cuda") * 2 - 1
+if mode == "forward":
+    a[..., 1] = a[..., 1].abs(); a[..., 0] *= 0.1
+for t in range(W): env.step(a[t])
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for t in range(K): env.step(a[W + t])
+e1.record(); torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / K
+print("%s actions=%s: %.4f ms/step, %.1f M env-steps/s" % (os.environ.get("PGDRIVE_B200_LIB", "default"), mode, ms, n / ms / 1e3))
