@@ -72,7 +72,21 @@ struct DevState {
 // ------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float clipf(float a, float lo, float hi) { return fminf(fmaxf(a, lo), hi); }
 
-__device__ __forceinline__ float wrap_to_pi(float x) {
+__device__ __noinline__ float2 sincos2(float a) {  // (sin, cos); single out-of-line copy of the accurate sincosf
+  float s, c;
+  sincosf(a, &s, &c);
+  return make_float2(s, c);
+}
+#define SINCOS(angle, s_out, c_out)          \
+  do {                                       \
+    const float2 sc_ = sincos2(angle);       \
+    (s_out) = sc_.x;                         \
+    (c_out) = sc_.y;                         \
+  } while (0)
+
+// Out-of-line on purpose: fmodf / atan2f / sincosf expand to hundreds of instructions each and were inlined at a
+// dozen call sites; the kernel then missed the instruction cache for 64 % of its issue slots (profiles/r01d).
+__device__ __noinline__ float wrap_to_pi(float x) {
   float m = fmodf(x + PI_F, TWO_PI_F);
   if (m < 0.0f) m += TWO_PI_F;
   return m - PI_F;
@@ -95,18 +109,23 @@ __device__ __forceinline__ Lane load_lane(const PgdLane* p) {
   return l;
 }
 
+__device__ __noinline__ float2 arc_local(float cx, float cy, float ph0, float dir, float radius, float x, float y) {
+  float dx = x - cx, dy = y - cy;
+  float phi = atan2f(dy, dx);
+  phi = ph0 + wrap_to_pi(phi - ph0);
+  float r = sqrtf(dx * dx + dy * dy);
+  return make_float2(dir * (phi - ph0) * radius, dir * (radius - r));
+}
+
 __device__ __forceinline__ void lane_local(const Lane& l, float x, float y, float& lon, float& lat) {
   if (l.kind == PGD_LANE_STRAIGHT) {
     float dx = x - l.sx, dy = y - l.sy;
     lon = dx * l.ax + dy * l.ay;
     lat = dx * -l.ay + dy * l.ax;
   } else {
-    float dx = x - l.ax, dy = y - l.ay;
-    float phi = atan2f(dy, dx);
-    phi = l.ph0 + wrap_to_pi(phi - l.ph0);
-    float r = sqrtf(dx * dx + dy * dy);
-    lon = l.dir * (phi - l.ph0) * l.radius;
-    lat = l.dir * (l.radius - r);
+    const float2 r = arc_local(l.ax, l.ay, l.ph0, l.dir, l.radius, x, y);
+    lon = r.x;
+    lat = r.y;
   }
 }
 
@@ -118,7 +137,7 @@ __device__ __forceinline__ void lane_position(const Lane& l, float lon, float la
     float phi = l.dir * lon / l.radius + l.ph0;
     float r = l.radius - lat * l.dir;
     float s, c;
-    sincosf(phi, &s, &c);
+    SINCOS(phi, s, c);
     x = l.ax + r * c;
     y = l.ay + r * s;
   }
@@ -290,7 +309,7 @@ pgd_step_kernel(DevTables T, DevState S, PgdConfig cfg, int mode, const float2* 
   // publish start-of-step poses
   {
     float s, c;
-    sincosf(h, &s, &c);
+    SINCOS(h, s, c);
     sh.x[slot] = x; sh.y[slot] = y; sh.h[slot] = h; sh.v[slot] = v;
     sh.ux[slot] = c; sh.uy[slot] = s;
     sh.hl[slot] = half_l; sh.hw[slot] = half_w;
@@ -519,7 +538,7 @@ pgd_step_kernel(DevTables T, DevState S, PgdConfig cfg, int mode, const float2* 
           const float sb = speed > 1e-3f ? clipf(yaw * sub.lr / speed, -1.0f, 1.0f) : 0.0f;
           const float cb = sqrtf(fmaxf(1.0f - sb * sb, 0.0f));
           float sh_, ch_;
-          sincosf(h, &sh_, &ch_);
+          SINCOS(h, sh_, ch_);
           x += speed * (ch_ * cb - sh_ * sb) * cfg.dt;
           y += speed * (sh_ * cb + ch_ * sb) * cfg.dt;
           float nh = h + yaw * cfg.dt;
@@ -532,7 +551,7 @@ pgd_step_kernel(DevTables T, DevState S, PgdConfig cfg, int mode, const float2* 
       }
       // contact of every chassis with the ego's
       float s, c;
-      sincosf(h, &s, &c);
+      SINCOS(h, s, c);
       if (slot == 0) { sh.x[0] = x; sh.y[0] = y; sh.ux[0] = c; sh.uy[0] = s; }
       __syncwarp(group_mask);
       if (alive && slot != 0) {
@@ -547,7 +566,7 @@ pgd_step_kernel(DevTables T, DevState S, PgdConfig cfg, int mode, const float2* 
 
   // ---- phase E: after_step -------------------------------------------------------------------------------------
   float hs, hc;
-  sincosf(h, &hs, &hc);
+  SINCOS(h, hs, hc);
   const bool moving = alive && active;  // vehicles that get an after_step: the ego always, traffic once awake
   // publish end-of-step poses and what localisation needs from each moving vehicle
   sh.x[slot] = x; sh.y[slot] = y; sh.h[slot] = h; sh.v[slot] = v;
@@ -588,7 +607,7 @@ pgd_step_kernel(DevTables T, DevState S, PgdConfig cfg, int mode, const float2* 
             float lon, lat;
             lane_local(l, vx, vy, lon, lat);
             float ls, lc;
-            sincosf(lane_heading_at(l, lon), &ls, &lc);
+            SINCOS(lane_heading_at(l, lon), ls, lc);
             if (!(lc * vc + ls * vs > 0.0f)) continue;
             b_any = min(b_any, b);
             if (l.road == cur_road) b_cur = min(b_cur, b);
@@ -679,7 +698,7 @@ pgd_step_kernel(DevTables T, DevState S, PgdConfig cfg, int mode, const float2* 
         if (m) {
           const float ang = (float)i * (TWO_PI_F / (float)PGD_LIDAR_BEAMS) + eh;
           float s, c;
-          sincosf(ang, &s, &c);
+          SINCOS(ang, s, c);
           const float dx = c * LIDAR_RANGE, dy = s * LIDAR_RANGE;
           while (m) {
             const int j = __ffs(m) - 1;
