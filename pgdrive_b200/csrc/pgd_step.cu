@@ -39,7 +39,19 @@
 #define IDM_MAX_SPEED 100.0f
 #define YAW_TAU 0.1f
 
+#ifndef CTA_THREADS
 #define CTA_THREADS 128
+#endif
+// Phase barriers keep the warps of a CTA inside the same code region, so one instruction-cache fill serves all
+// of them (the kernel body is larger than the 32 KB L1.5 instruction cache).
+#ifndef PHASE_BARRIERS
+#define PHASE_BARRIERS 1
+#endif
+#if PHASE_BARRIERS
+#define PHASE_SYNC() __syncthreads()
+#else
+#define PHASE_SYNC()
+#endif
 #ifndef MIN_CTAS_PER_SM
 #define MIN_CTAS_PER_SM 4
 #endif
@@ -327,7 +339,9 @@ pgd_step_kernel(DevTables T, DevState S, PgdConfig cfg, int mode, const float2* 
   const float last_x = sh.x[0], last_y = sh.y[0], last_h = sh.h[0];
   int crash = 0;
 
-  if (!fresh && !skip) {
+  const bool stepping = !fresh && !skip;
+  PHASE_SYNC();
+  if (stepping) {
     // ---- phase B: ego action + traffic trigger --------------------------------------------------------------
     if (slot == 0) {
       float2 a = actions[env];
@@ -344,6 +358,9 @@ pgd_step_kernel(DevTables T, DevState S, PgdConfig cfg, int mode, const float2* 
       }
     }
 
+  }
+  PHASE_SYNC();
+  if (stepping) {
     // ---- phase C: IDM ------------------------------------------------------------------------------------------
     if (alive && active && slot != 0) {
       const int cur_road_id = __ldg(&rroads[ck0]);
@@ -507,6 +524,9 @@ pgd_step_kernel(DevTables T, DevState S, PgdConfig cfg, int mode, const float2* 
       }
     }
 
+  }
+  PHASE_SYNC();
+  if (stepping) {
     // ---- phase D: physics sub-steps + chassis contact ----------------------------------------------------------
     Sub sub;
     {
@@ -564,6 +584,7 @@ pgd_step_kernel(DevTables T, DevState S, PgdConfig cfg, int mode, const float2* 
     crash = (__ballot_sync(group_mask, crash) & group_mask) != 0;
   }
 
+  PHASE_SYNC();
   // ---- phase E: after_step -------------------------------------------------------------------------------------
   float hs, hc;
   SINCOS(h, hs, hc);
@@ -657,6 +678,7 @@ pgd_step_kernel(DevTables T, DevState S, PgdConfig cfg, int mode, const float2* 
   sh.alive[slot] = alive;
   __syncwarp(group_mask);
 
+  PHASE_SYNC();
   // ---- phase F: observation, reward, done -----------------------------------------------------------------------
   float* ob = obs + (size_t)env * PGD_OBS_DIM;
   // lidar: beam i = slot + V * k.  Each chassis first publishes the (conservative) arc of beams that can reach it:
@@ -714,6 +736,7 @@ pgd_step_kernel(DevTables T, DevState S, PgdConfig cfg, int mode, const float2* 
       }
     }
   }
+  PHASE_SYNC();
   // the 4 nearest vehicles inside the 50 m cylinder (lidar.py:55-77): every chassis ranks itself by centre distance
   // (ties -> lower slot, like a stable selection) and the 4 best write their own features
   {
