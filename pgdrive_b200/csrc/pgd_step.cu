@@ -163,7 +163,7 @@ __device__ __forceinline__ float lane_heading_at(const Lane& l, float lon) {
 
 __device__ __forceinline__ bool precedes(float ex, float ey, float sx, float sy) {
   float dx = ex - sx, dy = ey - sy;
-  return sqrtf(dx * dx + dy * dy) < 1e-1f;
+  return dx * dx + dy * dy < 1e-2f;  // norm < 0.1 (abs_lane.py:114-119); lane ends either coincide or are metres apart
 }
 
 struct Rect {
@@ -318,10 +318,12 @@ pgd_step_kernel(DevTables T, DevState S, PgdConfig cfg, int mode, const float2* 
   bool alive = (vflags & PGD_V_ALIVE) != 0;
   bool active = (vflags & PGD_V_ACTIVE) != 0;
 
-  // publish start-of-step poses
+  // publish start-of-step poses; (hc, hs) = heading unit vector, kept current through the sub-steps
+  float hs, hc;
   {
     float s, c;
     SINCOS(h, s, c);
+    hs = s; hc = c;
     sh.x[slot] = x; sh.y[slot] = y; sh.h[slot] = h; sh.v[slot] = v;
     sh.ux[slot] = c; sh.uy[slot] = s;
     sh.hl[slot] = half_l; sh.hw[slot] = half_w;
@@ -557,27 +559,29 @@ pgd_step_kernel(DevTables T, DevState S, PgdConfig cfg, int mode, const float2* 
           if (speed * fabsf(yaw) > sub.mu_g) yaw = copysignf(sub.mu_g / speed, yaw);
           const float sb = speed > 1e-3f ? clipf(yaw * sub.lr / speed, -1.0f, 1.0f) : 0.0f;
           const float cb = sqrtf(fmaxf(1.0f - sb * sb, 0.0f));
-          float sh_, ch_;
-          SINCOS(h, sh_, ch_);
-          x += speed * (ch_ * cb - sh_ * sb) * cfg.dt;
-          y += speed * (sh_ * cb + ch_ * sb) * cfg.dt;
+          x += speed * (hc * cb - hs * sb) * cfg.dt;
+          y += speed * (hs * cb + hc * sb) * cfg.dt;
           float nh = h + yaw * cfg.dt;
           if (nh > PI_F) nh -= TWO_PI_F;
           if (nh < -PI_F) nh += TWO_PI_F;
           yaw_rate = yaw;
+          if (nh != h) SINCOS(nh, hs, hc);
           h = nh;
           v = speed;
         }
       }
       // contact of every chassis with the ego's
-      float s, c;
-      SINCOS(h, s, c);
-      if (slot == 0) { sh.x[0] = x; sh.y[0] = y; sh.ux[0] = c; sh.uy[0] = s; }
+      if (slot == 0) { sh.x[0] = x; sh.y[0] = y; sh.ux[0] = hc; sh.uy[0] = hs; }
       __syncwarp(group_mask);
       if (alive && slot != 0) {
-        Rect me = {x, y, c, s, half_l, half_w};
-        Rect eg = {sh.x[0], sh.y[0], sh.ux[0], sh.uy[0], sh.hl[0], sh.hw[0]};
-        if (rect_overlap(eg, me)) crash = 1;
+        // rectangles whose centres are further apart than their half-diagonals add up to cannot touch
+        const float ddx = x - sh.x[0], ddy = y - sh.y[0];
+        const float reach = sh.hl[0] + sh.hw[0] + half_l + half_w;
+        if (ddx * ddx + ddy * ddy <= reach * reach) {
+          Rect me = {x, y, hc, hs, half_l, half_w};
+          Rect eg = {sh.x[0], sh.y[0], sh.ux[0], sh.uy[0], sh.hl[0], sh.hw[0]};
+          if (rect_overlap(eg, me)) crash = 1;
+        }
       }
       __syncwarp(group_mask);
     }
@@ -586,8 +590,6 @@ pgd_step_kernel(DevTables T, DevState S, PgdConfig cfg, int mode, const float2* 
 
   PHASE_SYNC();
   // ---- phase E: after_step -------------------------------------------------------------------------------------
-  float hs, hc;
-  SINCOS(h, hs, hc);
   const bool moving = alive && active;  // vehicles that get an after_step: the ego always, traffic once awake
   // publish end-of-step poses and what localisation needs from each moving vehicle
   sh.x[slot] = x; sh.y[slot] = y; sh.h[slot] = h; sh.v[slot] = v;
