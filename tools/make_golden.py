@@ -296,3 +296,231 @@ if __name__ == "__main__":
         cmd_reset([0, 1, 2, 99, 1500, 1999, 2999, 12345, 29999], "misc")
     elif what == "probe":
         print(json.dumps(dump_reset(int(sys.argv[2])), indent=1)[:6000])
+
+
+# =================================================================================================
+# step-level vectors: the reference's OWN Python (IDM + PID, navigation info, checkpoint update, state
+# observation, neighbour features, reward, arrive_destination) evaluated on simulator states.
+# States come from a roll-out of this repo's CPU oracle (they are just inputs); every expected value
+# in the fixture is computed by unmodified reference code running under tools/ref_stub.py.
+# =================================================================================================
+def cmd_step(seeds, tag, steps=260, every=4):
+    import base64
+    from collections import deque
+    sys.path.insert(0, os.path.dirname(HERE))
+    from oracle.oracle import Oracle
+    from pgdrive_b200 import cabi, tables as ptables, mapgen, episode as pepisode
+    from pgdrive.component.vehicle.base_vehicle import BaseVehicle
+    from pgdrive.component.vehicle_module.navigation import Navigation
+    from pgdrive.component.vehicle_module.lidar import Lidar
+    from pgdrive.component.road.road import Road
+    from pgdrive.obs.state_obs import StateObservation
+    from pgdrive.policy.idm_policy import IDMPolicy
+    from pgdrive.policy.base_policy import BasePolicy
+    from pgdrive.envs.pgdrive_env import PGDriveEnv
+    from pgdrive.utils.math_utils import Vector
+    import pgdrive.policy.idm_policy as idm_mod
+
+    class FakeVehicle:
+        """Exactly the attributes the reference's pure-Python step code reads from a BaseVehicle."""
+        MAX_STEERING = 60
+        max_speed = 80
+        heading_diff = BaseVehicle.heading_diff
+        projection = BaseVehicle.projection
+        _dist_to_route_left_right = BaseVehicle._dist_to_route_left_right
+        arrive_destination = BaseVehicle.arrive_destination
+
+        def __init__(self, st, slot_rec, ref_lanes, world):
+            self.position = np.array([float(st["x"]), float(st["y"])])
+            self.heading_theta = float(st["heading"])
+            self.heading = Vector((math.cos(self.heading_theta), math.sin(self.heading_theta)))
+            self.speed = float(np.clip(st["speed"] * 3.6, 0.0, 100000.0))
+            self.velocity = self.speed * np.asarray([math.cos(self.heading_theta), math.sin(self.heading_theta)])
+            self.lane = ref_lanes[int(st["lane"])]
+            self.lane_index = self.lane.index
+            self.LENGTH, self.WIDTH = float(slot_rec["length"]), float(slot_rec["width"])
+            self.world = world
+            self.lidar = self
+            self.engine = None
+
+        @property
+        def current_road(self):
+            return Road(*self.lane_index[0:-1])
+
+        def get_surrounding_objects(self, vehicle):  # Lidar.get_surrounding_objects stand-in (50 m, centre distance)
+            return [o for o in self.world if o is not vehicle and
+                    (o.position[0] - vehicle.position[0])**2 + (o.position[1] - vehicle.position[1])**2 < 2500.0]
+
+    import math
+    out = []
+    for seed in seeds:
+        eng, m = build_map(seed)
+        eng.global_config["traffic_density"] = 0.1
+        pgmap = mapgen.generate_map(seed)
+        ts = ptables.TableSet()
+        mid = ts.add_map(pgmap)
+        ts.add_episode(pgmap, mid, pepisode.make_episode(pgmap, seed, 0.1))
+        T = ts.finish()
+        mi = ts.index[0]
+        ref_lanes = []
+        for (frm, to, first, n) in mi.road_list:
+            for i in range(n):
+                ln = m.road_network.graph[frm][to][i]
+                ln.index = (frm, to, i)
+                ref_lanes.append(ln)
+        node_name = {v: k for k, v in mi.nodes.items()}
+        slots = T["slots"]
+        n_slots = int(T["episodes"][0]["n_slots"])
+        orc = Oracle(T, 1, auto_reset=False)
+        orc.reset([0], [0])
+        rs = np.random.RandomState(seed)
+        policies = {}
+
+        def make_nav(st, slot):
+            nav = Navigation.__new__(Navigation)
+            nav.map = m
+            off, ln = int(slots[slot]["route_off"]), int(slots[slot]["route_len"])
+            nav.checkpoints = [node_name[int(x)] for x in T["route_nodes"][off:off + ln]]
+            nav._target_checkpoints_index = [int(st["ck0"]), int(st["ck1"])]
+            c = nav.checkpoints
+            i0, i1 = nav._target_checkpoints_index
+            nav.current_ref_lanes = m.road_network.graph[c[i0]][c[i0 + 1]]
+            nav.current_road = Road(c[i0], c[i0 + 1])
+            if i0 == i1:
+                nav.next_ref_lanes, nav.next_road = None, None
+            else:
+                nav.next_ref_lanes, nav.next_road = m.road_network.graph[c[i1]][c[i1 + 1]], Road(c[i1], c[i1 + 1])
+            nav.final_road = Road(c[-2], c[-1])
+            nav.final_lane = nav.final_road.get_lanes(m.road_network)[-1]
+            nav._navi_info = np.zeros((10, ))
+            nav._show_navi_info = False
+            return nav
+
+        lat_err = 0.0
+        for t in range(steps):
+            s0 = orc.get_state(0)
+            v0 = s0["veh"][0]
+            # a lane-following ego (keeps the episode alive so that traffic wakes up); any policy would do
+            ego_lane = ref_lanes[int(v0[0]["lane"])]
+            lon, lat = ego_lane.local_coordinates((float(v0[0]["x"]), float(v0[0]["y"])))
+            herr = ((ego_lane.heading_at(lon + 2.0) - float(v0[0]["heading"]) + np.pi) % (2 * np.pi)) - np.pi
+            a = np.array([[np.clip(-1.5 * herr + 0.25 * lat + rs.uniform(-0.03, 0.03), -1, 1),
+                           np.clip(0.6 - float(v0[0]["speed"]) / 15.0 + rs.uniform(-0.1, 0.1), -1, 1)]], np.float32)
+            obs, rew, done, info = orc.step(a)
+            s1 = orc.get_state(0)
+            v1 = s1["veh"][0]
+            if t % every == 0 and t > 0:
+                rec = dict(seed=seed, t=t, s0=base64.b64encode(s0.tobytes()).decode(), action=[float(a[0, 0]), float(a[0, 1])])
+                # ---- world before the step (IDM inputs) ----
+                world0 = {}
+                for i in range(n_slots):
+                    if int(v0[i]["flags"]) & cabi.V_ALIVE:
+                        world0[i] = FakeVehicle(v0[i], slots[i], ref_lanes, None)
+                for fv in world0.values():
+                    fv.world = list(world0.values())
+                idm = []
+                for i in range(1, n_slots):
+                    ran = (int(v1[i]["flags"]) & cabi.V_ACTIVE) and (int(v0[i]["flags"]) & cabi.V_ALIVE)
+                    if not ran:
+                        continue
+                    fv = world0[i]
+                    fv.navigation = make_nav(v0[i], i)
+                    pol = IDMPolicy.__new__(IDMPolicy)
+                    BasePolicy.__init__(pol, control_object=fv, random_seed=0)
+                    # the policy's own stream, advanced to where this vehicle's stream stands
+                    from pgdrive.utils.random_utils import get_np_random
+                    idm_seed = None
+                    pol.np_random = None
+                    pol.target_speed = float(v0[i]["target_speed"])
+                    pol.routing_target_lane = None if int(v0[i]["rt_lane"]) < 0 else ref_lanes[int(v0[i]["rt_lane"])]
+                    pol.available_routing_index_range = None
+                    pol.overtake_timer = int(v0[i]["timer"])
+                    from pgdrive.component.vehicle_module.PID_controller import PIDController
+                    pol.heading_pid = PIDController(1.7, 0.01, 3.5)
+                    pol.lateral_pid = PIDController(0.3, .002, 0.05)
+                    pol.heading_pid.p_error, pol.heading_pid.i_error = float(v0[i]["pid_hp"]), float(v0[i]["pid_hi"])
+                    pol.lateral_pid.p_error, pol.lateral_pid.i_error = float(v0[i]["pid_lp"]), float(v0[i]["pid_li"])
+
+                    class _Stream:  # replays the tabulated randint(0, 25) draws of this vehicle's IDM stream
+                        def __init__(self, draws, n):
+                            self.draws, self.n = draws, n
+
+                        def randint(self, lo, hi):
+                            assert (lo, hi) == (0, 25)
+                            v = int(self.draws[self.n % len(self.draws)])
+                            self.n += 1
+                            return v
+
+                    pol.np_random = _Stream(slots[i]["rnd25"], int(v0[i]["rnd_n"]))
+                    steering, acc = pol.act()
+                    idm.append(dict(
+                        slot=i, steering=float(steering), acc=float(acc), target_speed=float(pol.target_speed),
+                        timer=int(pol.overtake_timer), rt_lane=ref_lanes.index(pol.routing_target_lane),
+                        pid=[float(pol.heading_pid.p_error), float(pol.heading_pid.i_error),
+                             float(pol.lateral_pid.p_error), float(pol.lateral_pid.i_error)]
+                    ))
+                rec["idm"] = idm
+                # ---- world after the step (observation / reward inputs) ----
+                world1 = {}
+                for i in range(n_slots):
+                    if int(v1[i]["flags"]) & cabi.V_ALIVE:
+                        world1[i] = FakeVehicle(v1[i], slots[i], ref_lanes, None)
+                for fv in world1.values():
+                    fv.world = list(world1.values())
+                ego = world1[0]
+                ego.navigation = make_nav(v1[0], 0)
+                # checkpoint advance: reference rule applied to the pre-step indices and the post-step lane
+                nav0 = make_nav(v0[0], 0)
+                lon1, _ = ego.lane.local_coordinates(ego.position)
+                nav0._update_target_checkpoints(ego.lane_index, lon1)
+                rec["ck"] = [int(x) for x in nav0._target_checkpoints_index]
+                navi = ego.navigation._get_info_for_checkpoint(0, ego.navigation.current_ref_lanes, ego)[0]
+                c = ego.navigation.checkpoints
+                i1 = ego.navigation._target_checkpoints_index[1]
+                navi += ego.navigation._get_info_for_checkpoint(1, m.road_network.graph[c[i1]][c[i1 + 1]], ego)[0]
+                rec["navi"] = [float(x) for x in navi]
+                ego.dist_to_left_side, ego.dist_to_right_side = ego._dist_to_route_left_right()
+                ego.steering = float(v1[0]["steer"])
+                ego.throttle_brake = float(v1[0]["throttle"])
+                ego.last_current_action = deque([(float(s1["prev_steer"][0]), float(s1["prev_throttle"][0])),
+                                                 (ego.steering, ego.throttle_brake)], maxlen=2)
+                ego.last_position = np.array([float(v0[0]["x"]), float(v0[0]["y"])])
+                h0 = float(v0[0]["heading"])
+                ego.last_heading_dir = Vector((math.cos(h0), math.sin(h0)))
+
+                class _Off:
+                    available = False
+
+                ego.side_detector = ego.lane_line_detector = _Off()
+                ego.navigation.map = type("M", (), dict(MAX_LANE_NUM=3, MAX_LANE_WIDTH=4.5, _config=m._config,
+                                                        LANE_WIDTH="lane_width", road_network=m.road_network))()
+                so = StateObservation.__new__(StateObservation)
+                so.config = dict(random_agent_model=False)
+                rec["state"] = [float(x) for x in so.vehicle_state(ego)]
+                lid = type("L", (), dict(perceive_distance=50, get_surrounding_vehicles=staticmethod(lambda objs: set(objs))))()
+                rec["neighbours"] = [float(x) for x in Lidar.get_surrounding_vehicles_info(
+                    lid, ego, ego.get_surrounding_objects(ego), 4)]
+                ego.on_yellow_continuous_line = ego.on_white_continuous_line = ego.crash_sidewalk = False
+                ego.on_lane = True
+                ego.crash_vehicle = ego.crash_object = ego.out_of_route = False
+                fenv = type("E", (), dict(vehicles={"default_agent": ego}, config=dict(
+                    use_lateral=False, driving_reward=1.0, speed_reward=0.1, success_reward=10.0,
+                    out_of_road_penalty=5.0, crash_vehicle_penalty=5.0, crash_object_penalty=5.0,
+                    out_of_route_done=False), _is_out_of_road=lambda self, v: False))()
+                r, rinfo = PGDriveEnv.reward_function(fenv, "default_agent")
+                rec["step_reward"] = float(rinfo["step_reward"])
+                rec["arrive_dest"] = bool(ego.arrive_destination.fget(ego) if isinstance(
+                    ego.arrive_destination, property) else FakeVehicle.arrive_destination.fget(ego))
+                out.append(rec)
+            if done[0]:
+                break
+        orc.close()
+        print("seed", seed, "steps", t + 1, "records so far", len(out), "idm samples", sum(len(r["idm"]) for r in out))
+    path = os.path.join(GOLD, "step_%s.json.gz" % tag)
+    with gzip.open(path, "wt") as f:
+        json.dump(out, f)
+    print("wrote", path, os.path.getsize(path))
+
+
+if __name__ == "__main__" and sys.argv[1] == "step":
+    cmd_step([1000, 1003, 1008, 1015, 1021, 1042, 1055, 1077], "v0")

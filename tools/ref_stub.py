@@ -80,7 +80,7 @@ def install():
     names = (
         "panda3d panda3d.core panda3d.bullet gym gym.spaces gym.envs gym.envs.registration seaborn pygame "
         "gltf direct direct.showbase direct.showbase.ShowBase direct.gui direct.gui.OnscreenImage "
-        "direct.controls direct.controls.InputState simplepbr"
+        "direct.controls direct.controls.InputState simplepbr evdev"
     ).split()
     for name in names:
         sys.modules[name] = _Stub(name)
