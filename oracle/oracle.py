@@ -37,6 +37,7 @@ def lib():
         L.orc_step.argtypes = [vp, i32, vp, vp, vp, vp, vp]
         L.orc_step_range.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp]
         L.orc_get_state.argtypes = [vp, i32, vp]
+        L.orc_observe.argtypes = [vp, i32, vp, vp]
         L.orc_set_state.argtypes = [vp, i32, vp]
         L.orc_lane_local.argtypes = [vp, C.c_float, C.c_float, vp]
         L.orc_lane_position.argtypes = [vp, C.c_float, C.c_float, vp]
@@ -86,6 +87,13 @@ class Oracle:
             [t.start() for t in ts]
             [t.join() for t in ts]
         return self.obs, self.reward, self.done, self.info
+
+    def observe(self, env):
+        """Observation of the current state of ``env`` (no stepping, no mutation)."""
+        obs = np.zeros(cabi.OBS_DIM, np.float32)
+        info = np.zeros(1, cabi.INFO_DT)
+        self.L.orc_observe(self.h, int(env), obs.ctypes.data, info.ctypes.data)
+        return obs, info[0]
 
     def get_state(self, env):
         s = np.zeros(1, cabi.ENV_STATE_DT)

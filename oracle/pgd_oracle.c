@@ -835,6 +835,13 @@ void orc_set_state(void* h, int env, const PgdEnvState* in) {
   }
 }
 
+/* observation of the CURRENT state without stepping or mutating it (golden-vector tests) */
+void orc_observe(void* h, int env, float* obs, PgdInfo* info) {
+  Oracle* o = (Oracle*)h;
+  Env tmp = o->envs[env];
+  post_step(o, &tmp, tmp.v[0].x, tmp.v[0].y, tmp.v[0].h, 0, 1, obs, NULL, NULL, info);
+}
+
 /* small probes used by the golden-vector tests */
 void orc_lane_local(const PgdLane* l, float x, float y, float* out) { lane_local(l, x, y, out, out + 1); }
 void orc_lane_position(const PgdLane* l, float lon, float lat, float* out) { lane_position(l, lon, lat, out, out + 1); }

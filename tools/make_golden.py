@@ -524,3 +524,104 @@ def cmd_step(seeds, tag, steps=260, every=4):
 
 if __name__ == "__main__" and sys.argv[1] == "step":
     cmd_step([1000, 1003, 1008, 1015, 1021, 1042, 1055, 1077], "v0")
+
+
+# =================================================================================================
+# lidar vectors: the reference's own per-beam loop (the Python twin of cutils_perceive that ships in
+# pgdrive/utils/cutils.py:36-97) driven by a 2-D stand-in for Bullet's rayTestClosest that intersects the
+# beam with the four edges of every chassis rectangle analytically (segment / segment, the construction
+# the reference's own mask test uses, tests/test_component/test_detector_mask.py:132-154).
+# =================================================================================================
+def cmd_lidar(tag, n_scenes=40):
+    import base64
+    import math
+    sys.path.insert(0, os.path.dirname(HERE))
+    from oracle.oracle import Oracle
+    from pgdrive_b200 import cabi, tables as ptables
+    from pgdrive.utils.cutils import _get_fake_cutils
+    fake = _get_fake_cutils()
+
+    class Hit:
+        def __init__(self, node, frac, pos):
+            self.node, self.frac, self.pos = node, frac, pos
+
+        def getNode(self):
+            return self.node
+
+        def getHitFraction(self):
+            return self.frac
+
+        def hasHit(self):
+            return self.node is not None
+
+        def getHitPos(self):
+            return self.pos
+
+    class World2D:
+        """rayTestClosest over chassis rectangles given in PGDrive coordinates; arguments arrive in Panda
+        coordinates (x, -y, z) exactly as cutils_perceive passes them."""
+        def __init__(self, boxes):
+            self.edges = []
+            for k, (x, y, h, length, width) in enumerate(boxes):
+                c, s = math.cos(h), math.sin(h)
+                pts = [(x + c * a * length / 2 - s * b * width / 2, y + s * a * length / 2 + c * b * width / 2)
+                       for a, b in ((1, 1), (1, -1), (-1, -1), (-1, 1))]
+                for i in range(4):
+                    self.edges.append((k, pts[i], pts[(i + 1) % 4]))
+
+        def rayTestClosest(self, start, end, mask):
+            p = (start[0], -start[1])
+            r = (end[0] - start[0], -(end[1] - start[1]))
+            best, node = 1.0, None
+            for k, a, b in self.edges:
+                sx, sy = b[0] - a[0], b[1] - a[1]
+                den = r[0] * sy - r[1] * sx
+                if den == 0:
+                    continue
+                qx, qy = a[0] - p[0], a[1] - p[1]
+                t = (qx * sy - qy * sx) / den
+                u = (qx * r[1] - qy * r[0]) / den
+                if 0.0 <= t <= 1.0 and 0.0 <= u <= 1.0 and t < best:
+                    best, node = t, k
+            return Hit(node, best, (p[0] + best * r[0], -(p[1] + best * r[1]), start[2]))
+
+    T = ptables.build_tables([1003]).finish()
+    n_slots = int(T["episodes"][0]["n_slots"])
+    slots = T["slots"]
+    orc = Oracle(T, 1, auto_reset=False)
+    rs = np.random.RandomState(7)
+    lidar_range = np.arange(0, 240) * (2 * np.pi / 240)
+    out = []
+    for scene in range(n_scenes):
+        orc.reset([0], [0])
+        s = orc.get_state(0)
+        v = s["veh"][0]
+        ex, ey = float(v[0]["x"]) + rs.uniform(-3, 3), float(v[0]["y"]) + rs.uniform(-1, 1)
+        eh = rs.uniform(-np.pi, np.pi)
+        v[0]["x"], v[0]["y"], v[0]["heading"] = ex, ey, eh
+        boxes = []
+        for i in range(1, n_slots):
+            d, ang = rs.uniform(4.5, 58.0), rs.uniform(-np.pi, np.pi)
+            v[i]["x"], v[i]["y"] = ex + d * math.cos(ang), ey + d * math.sin(ang)
+            v[i]["heading"] = rs.uniform(-np.pi, np.pi)
+            alive = rs.rand() > 0.15
+            v[i]["flags"] = (cabi.V_ALIVE | cabi.V_ON_LANE) if alive else 0
+            if alive:  # float32 poses, as the simulator stores them
+                boxes.append((float(v[i]["x"]), float(v[i]["y"]), float(v[i]["heading"]), float(slots[i]["length"]),
+                              float(slots[i]["width"])))
+        s["veh"][0] = v
+        cloud = np.ones(240)
+        cloud, _, _ = fake.cutils_perceive(
+            cloud, None, None, lidar_range, 50.0, float(v[0]["heading"]), float(v[0]["x"]), float(v[0]["y"]), 240, 1.2,
+            World2D(boxes), set(), False, True, 0, 0, 0)
+        out.append(dict(state=base64.b64encode(s.tobytes()).decode(), cloud=[float(x) for x in cloud],
+                        hits=int((cloud < 1.0).sum())))
+    orc.close()
+    path = os.path.join(GOLD, "lidar_%s.json.gz" % tag)
+    with gzip.open(path, "wt") as f:
+        json.dump(out, f)
+    print("wrote", path, os.path.getsize(path), "beams hitting:", sum(r["hits"] for r in out))
+
+
+if __name__ == "__main__" and sys.argv[1] == "lidar":
+    cmd_lidar("v0")
