@@ -235,21 +235,34 @@ class VecPGDriveEnv:
         )
         return self.obs
 
-    def step(self, actions):
+    def step(self, actions, out=None):
         """``actions``: ``[N, 2]`` float32, either a CUDA tensor (device path: returns CUDA tensors, no
-        synchronisation) or a numpy array (host path: pinned staging, returns numpy arrays)."""
+        synchronisation) or a numpy array (host path: pinned staging, returns numpy arrays).  ``out`` (device path
+        only) = ``(obs, reward, done)`` tensors to write into instead of the environment's own buffers, e.g. this
+        rank's rows of an all-gather buffer."""
         e = self.engine
         torch = e.torch
         if isinstance(actions, torch.Tensor):
             if actions.device != e.device or actions.dtype != torch.float32 or tuple(actions.shape) != (self.num_envs, 2):
                 raise ValueError("actions must be a float32 [num_envs, 2] tensor on %s" % e.device)
             a = actions.contiguous()
+            obs, reward, done = out if out is not None else (self.obs, self.reward, self.done)
+            if out is not None:
+                n = self.num_envs
+                ok = (tuple(obs.shape) == (n, cabi.OBS_DIM) and obs.dtype == torch.float32 and obs.is_contiguous()
+                      and tuple(reward.shape) == (n, ) and reward.dtype == torch.float32 and reward.is_contiguous()
+                      and tuple(done.shape) == (n, ) and done.dtype == torch.uint8 and done.is_contiguous()
+                      and obs.device == reward.device == done.device == e.device)
+                if not ok:
+                    raise ValueError("out must be contiguous (f32 [N,274], f32 [N], u8 [N]) tensors on %s" % e.device)
             cabi.check(
                 e.lib,
-                e.lib.pgd_step(e.h, a.data_ptr(), self.obs.data_ptr(), self.reward.data_ptr(), self.done.data_ptr(),
+                e.lib.pgd_step(e.h, a.data_ptr(), obs.data_ptr(), reward.data_ptr(), done.data_ptr(),
                                self.info.data_ptr(), e.stream())
             )
-            return self.obs, self.reward, self.done, self.info
+            return obs, reward, done, self.info
+        if out is not None:
+            raise ValueError("out= is only supported with device actions")
         a = np.ascontiguousarray(actions, dtype=np.float32)
         if a.shape != (self.num_envs, 2):
             raise ValueError("actions must have shape [num_envs, 2]")
