@@ -309,7 +309,7 @@ def run_own(args):
     cpu = None
     if world == 1 and not args.no_cpu:
         threads = host_threads()
-        cn, cs = 8192, 24
+        cn, cs = 32768, 128  # ~4.2M env-steps: 10-30 s of CPU work on a 16-thread host
         rate, dt = cpu_oracle_rate(T, cn, cs, 2, threads, [i % 100 for i in range(cn)])
         cpu = dict(value=rate, unit="env-steps/s", cores=threads, kind="port",
                    sample="%d of %d envs x %d steps (%.1f s), CPU oracle on %d host threads" % (cn, n, cs, dt, threads))

@@ -234,3 +234,38 @@ def test_state_round_trip_and_v32_slots():
     s2 = env.get_state(4)
     assert s.tobytes() == s2.tobytes()
     env.close()
+
+
+def test_full_size_65536_envs_replicas_and_oracle():
+    """BASELINE.json configs[2] size.  Environments i and j with i = j (mod 100) play the same seed; fed the same
+    actions they must stay BIT-identical (size-independent property), and the first 100 are checked against the
+    oracle every step, so all 65 536 are pinned transitively."""
+    import torch
+    seeds = list(range(1000, 1100))
+    n = 65536
+    env, _ = _pair(n, seeds)
+    from oracle.oracle import Oracle
+    ref = Oracle(env.T, 100, auto_reset=True)
+    env.reset()
+    ref.reset(range(100), range(100))
+    rs = np.random.RandomState(11)
+    idx = torch.arange(n, device="cuda") % 100
+    total_done = 0
+    for t in range(150):
+        a100 = rs.uniform(-1, 1, (100, 2)).astype(np.float32)
+        a100[:, 1] = np.abs(a100[:, 1])
+        a100[:, 0] *= 0.3
+        a = torch.from_numpy(a100).cuda()[idx].contiguous()
+        o, r, d, _ = env.step(a)
+        assert torch.equal(o, o[:100][idx]), "step %d: replicas of a seed diverged (obs)" % t
+        assert torch.equal(r, r[:100][idx]) and torch.equal(d, d[:100][idx]), "step %d: replicas diverged" % t
+        ro, rr, rd, _ = ref.step(a100)
+        o100, r100, d100 = o[:100].cpu().numpy(), r[:100].cpu().numpy(), d[:100].cpu().numpy()
+        assert np.array_equal(d100, rd), "step %d" % t
+        assert np.abs(o100[:, :34] - ro[:, :34]).max() < OBS_TOL, "step %d" % t
+        _check_lidar(o100[:, 34:], ro[:, 34:], t)
+        np.testing.assert_allclose(r100, rr, rtol=1e-3, atol=1e-3)
+        assert float(o.min()) >= 0.0 and float(o.max()) <= 1.0
+        total_done += int(d.sum().item())
+    assert total_done > n // 4
+    env.close()
