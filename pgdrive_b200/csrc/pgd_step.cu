@@ -247,16 +247,17 @@ struct Sub {  // what one physics sub-step needs, hoisted out of the sub-step lo
 // ------------------------------------------------------------------------------------------------------------------
 template <int V>
 __global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PER_SM)
-pgd_step_kernel(DevTables T, DevState S, PgdConfig cfg, int mode, const float2* __restrict__ actions,
+pgd_step_kernel(DevTables T, DevState S, PgdConfig cfg, int mode, int env_begin, int env_end,
+                const float2* __restrict__ actions,
                 float* __restrict__ obs, float* __restrict__ reward, uint8_t* __restrict__ done,
                 PgdInfo* __restrict__ info) {
   constexpr int ENVS_PER_CTA = CTA_THREADS / V;
   __shared__ EnvShared<V> sh_all[ENVS_PER_CTA];
   const int slot = threadIdx.x % V;
   const int env_in_cta = threadIdx.x / V;
-  const int env_raw = blockIdx.x * ENVS_PER_CTA + env_in_cta;
-  const bool env_valid = env_raw < cfg.num_envs;
-  const int env = env_valid ? env_raw : cfg.num_envs - 1;  // clamp: surplus threads shadow the last env, no stores
+  const int env_raw = env_begin + blockIdx.x * ENVS_PER_CTA + env_in_cta;  // this launch covers [env_begin, env_end)
+  const bool env_valid = env_raw < env_end;
+  const int env = env_valid ? env_raw : env_end - 1;  // clamp: surplus threads shadow the last env, no stores
   EnvShared<V>& sh = sh_all[env_in_cta];
   const unsigned lane_id = threadIdx.x & 31;
   const unsigned group_mask = (V == 32) ? 0xffffffffu : (0xffffu << (lane_id & 16));
@@ -967,7 +968,8 @@ struct PgdHandle {
   float *d_act, *d_obs, *d_rew;
   uint8_t* d_done;
   PgdInfo* d_info;
-  cudaStream_t own_stream;
+  cudaStream_t own_stream, own_stream2;
+  cudaEvent_t ev_act;
   // timing
   int timing;
   cudaEvent_t ev0, ev1;
@@ -998,6 +1000,8 @@ extern "C" int pgd_create(const PgdConfig* cfg, int device, PgdHandle** out) {
   h->S.envi = (int4*)h->state_mem[5];
   h->S.envf = (float4*)h->state_mem[6];
   CU(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&h->own_stream2, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&h->ev_act, cudaEventDisableTiming));
   CU(cudaEventCreate(&h->ev0));
   CU(cudaEventCreate(&h->ev1));
   *out = h;
@@ -1015,6 +1019,8 @@ extern "C" int pgd_destroy(PgdHandle* h) {
   cudaFreeHost(h->h_info);
   cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_done); cudaFree(h->d_info);
   cudaStreamDestroy(h->own_stream);
+  cudaStreamDestroy(h->own_stream2);
+  cudaEventDestroy(h->ev_act);
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
   delete h;
   return 0;
@@ -1057,18 +1063,18 @@ extern "C" int pgd_load_tables(PgdHandle* h, const PgdTables* t) {
   return 0;
 }
 
-static int launch_step(PgdHandle* h, int mode, const float* actions, float* obs, float* reward, uint8_t* done,
-                       PgdInfo* info, cudaStream_t st) {
+static int launch_step(PgdHandle* h, int mode, int env_begin, int env_end, const float* actions, float* obs,
+                       float* reward, uint8_t* done, PgdInfo* info, cudaStream_t st) {
   const int V = h->cfg.num_slots;
   const int envs_per_cta = CTA_THREADS / V;
-  const int grid = (h->cfg.num_envs + envs_per_cta - 1) / envs_per_cta;
+  const int grid = (env_end - env_begin + envs_per_cta - 1) / envs_per_cta;
   if (h->timing && mode == 0) cudaEventRecord(h->ev0, st);
   if (V == 16)
-    pgd_step_kernel<16><<<grid, CTA_THREADS, 0, st>>>(h->T, h->S, h->cfg, mode, (const float2*)actions, obs, reward,
-                                                      done, info);
+    pgd_step_kernel<16><<<grid, CTA_THREADS, 0, st>>>(h->T, h->S, h->cfg, mode, env_begin, env_end,
+                                                      (const float2*)actions, obs, reward, done, info);
   else
-    pgd_step_kernel<32><<<grid, CTA_THREADS, 0, st>>>(h->T, h->S, h->cfg, mode, (const float2*)actions, obs, reward,
-                                                      done, info);
+    pgd_step_kernel<32><<<grid, CTA_THREADS, 0, st>>>(h->T, h->S, h->cfg, mode, env_begin, env_end,
+                                                      (const float2*)actions, obs, reward, done, info);
   if (h->timing && mode == 0) cudaEventRecord(h->ev1, st);
   h->launches++;
   CU(cudaGetLastError());
@@ -1099,7 +1105,7 @@ extern "C" int pgd_reset(PgdHandle* h, const int32_t* env_ids, const int32_t* ep
                                                          h->cfg.num_envs);
   h->launches++;
   CU(cudaGetLastError());
-  return launch_step(h, 1, nullptr, obs_dev, nullptr, nullptr, info_dev, st);
+  return launch_step(h, 1, 0, h->cfg.num_envs, nullptr, obs_dev, nullptr, nullptr, info_dev, st);
 }
 
 extern "C" int pgd_step(PgdHandle* h, const float* actions_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev,
@@ -1107,7 +1113,8 @@ extern "C" int pgd_step(PgdHandle* h, const float* actions_dev, float* obs_dev, 
   if (!h || !actions_dev || !obs_dev || !reward_dev || !done_dev) return fail(-1, "pgd_step: null argument");
   if (!h->tables_loaded) return fail(-3, "pgd_step: no tables loaded");
   CU(cudaSetDevice(h->device));
-  return launch_step(h, 0, actions_dev, obs_dev, reward_dev, done_dev, info_dev, (cudaStream_t)stream);
+  return launch_step(h, 0, 0, h->cfg.num_envs, actions_dev, obs_dev, reward_dev, done_dev, info_dev,
+                     (cudaStream_t)stream);
 }
 
 static int ensure_staging(PgdHandle* h) {
@@ -1146,15 +1153,34 @@ extern "C" int pgd_step_host(PgdHandle* h, const float* actions, float* obs, flo
   cudaStream_t st = h->own_stream;
   // Page-locked caller buffers are DMA targets themselves; pageable ones go through the handle's pinned staging.
   const bool direct = is_pinned(obs) && is_pinned(reward) && is_pinned(done) && (!info || is_pinned(info));
+  float* o_dst = direct ? obs : h->h_obs;
+  float* r_dst = direct ? reward : h->h_rew;
+  uint8_t* d_dst = direct ? done : h->h_done;
+  PgdInfo* i_dst = direct ? info : h->h_info;
   memcpy(h->h_act, actions, n * 8);
   CU(cudaMemcpyAsync(h->d_act, h->h_act, n * 8, cudaMemcpyHostToDevice, st));
-  rc = launch_step(h, 0, h->d_act, h->d_obs, h->d_rew, h->d_done, info ? h->d_info : nullptr, st);
-  if (rc) return rc;
-  CU(cudaMemcpyAsync(direct ? obs : h->h_obs, h->d_obs, n * PGD_OBS_DIM * 4, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(direct ? reward : h->h_rew, h->d_rew, n * 4, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(direct ? done : h->h_done, h->d_done, n, cudaMemcpyDeviceToHost, st));
-  if (info) CU(cudaMemcpyAsync(direct ? info : h->h_info, h->d_info, n * sizeof(PgdInfo), cudaMemcpyDeviceToHost, st));
+  // The step is cut into chunks of environments on two streams so that the device-to-host copy of one chunk (the
+  // PCIe-bound part: 1.1 KB per environment) overlaps the kernel of the next.
+  const int chunks = n >= 8192 ? 4 : 1;
+  if (chunks > 1) {
+    CU(cudaEventRecord(h->ev_act, st));
+    CU(cudaStreamWaitEvent(h->own_stream2, h->ev_act, 0));
+  }
+  const int per = (int)((n / chunks + 7) / 8 * 8);
+  for (int c = 0; c < chunks; ++c) {
+    const int b = c * per, e = (c == chunks - 1) ? (int)n : (c + 1) * per;
+    cudaStream_t cs = (c & 1) ? h->own_stream2 : st;
+    rc = launch_step(h, 0, b, e, h->d_act, h->d_obs, h->d_rew, h->d_done, info ? h->d_info : nullptr, cs);
+    if (rc) return rc;
+    const size_t m = (size_t)(e - b);
+    CU(cudaMemcpyAsync(o_dst + (size_t)b * PGD_OBS_DIM, h->d_obs + (size_t)b * PGD_OBS_DIM, m * PGD_OBS_DIM * 4,
+                       cudaMemcpyDeviceToHost, cs));
+    CU(cudaMemcpyAsync(r_dst + b, h->d_rew + b, m * 4, cudaMemcpyDeviceToHost, cs));
+    CU(cudaMemcpyAsync(d_dst + b, h->d_done + b, m, cudaMemcpyDeviceToHost, cs));
+    if (info) CU(cudaMemcpyAsync(i_dst + b, h->d_info + b, m * sizeof(PgdInfo), cudaMemcpyDeviceToHost, cs));
+  }
   CU(cudaStreamSynchronize(st));
+  if (chunks > 1) CU(cudaStreamSynchronize(h->own_stream2));
   if (!direct) {
     memcpy(obs, h->h_obs, n * PGD_OBS_DIM * 4);
     memcpy(reward, h->h_rew, n * 4);

@@ -184,15 +184,17 @@ def test_nan_action_is_treated_as_minus_one():
     env.close()
 
 
-def test_host_buffer_step_equals_device_step():
+@pytest.mark.parametrize("n", [64, 8192 + 24])  # the larger batch takes the chunked two-stream pipeline
+def test_host_buffer_step_equals_device_step(n):
     import torch
-    env_a, _ = _pair(64, [1000, 1001, 1002, 1003])
-    env_b, _ = _pair(64, [1000, 1001, 1002, 1003])
+    env_a, _ = _pair(n, [1000, 1001, 1002, 1003])
+    env_b, _ = _pair(n, [1000, 1001, 1002, 1003])
     env_a.reset()
     env_b.reset()
     rs = np.random.RandomState(5)
     for _ in range(30):
-        a = rs.uniform(-1, 1, (64, 2)).astype(np.float32)
+        a = rs.uniform(-1, 1, (n, 2)).astype(np.float32)
+        a[:, 1] = np.abs(a[:, 1])
         o1, r1, d1, i1 = env_a.step(a)
         o2, r2, d2, _ = env_b.step(torch.from_numpy(a).cuda())
         np.testing.assert_array_equal(o1, o2.cpu().numpy())
