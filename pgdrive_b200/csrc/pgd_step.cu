@@ -548,11 +548,14 @@ pgd_step_kernel(DevTables T, DevState S, PgdConfig cfg, int mode, int env_begin,
       const float tb = t1.w / (t1.z + t1.w) * tanf(delta);
       sub.sb = tb / sqrtf(1.0f + tb * tb);
     }
+    // A vehicle at rest with no yaw rate and no engine force (parked traffic, a braking ego) is a fixed point of the
+    // sub-step below: speed = max(0 - dv, 0) = 0, yaw stays 0, the pose does not move.  Skipping it is exact.
+    const bool at_rest = v == 0.0f && yaw_rate == 0.0f && !(sub.accel > 0.0f);
     for (int k = 0; k < cfg.decision_repeat; ++k) {
       if (alive) {
         if (airborne > 0) {
           airborne--;
-        } else {
+        } else if (!at_rest) {
           float speed = v;
           if (sub.accel > 0.0f) speed += sub.accel * cfg.dt;
           else speed = fmaxf(speed - sub.brake_dv, 0.0f);

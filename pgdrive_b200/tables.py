@@ -270,7 +270,9 @@ class TableSet:
             rs.randint(0, 50)  # the constructor's overtake_timer draw (idm_policy.py:185)
             rnd[:] = [rs.randint(0, 25) for _ in range(N_RND25)]  # move_to_next_road draws (idm_policy.py:239)
         off, n = self._route(mi, checkpoints)
-        self.slots.append((x, y, ln.heading_at(lon), length, width, mass, lf, lr, params["max_engine_force"],
+        # spawn heading wrapped into [-pi, pi): the simulator keeps headings wrapped (Panda's getH() does too)
+        heading = (ln.heading_at(lon) + math.pi) % (2 * math.pi) - math.pi
+        self.slots.append((x, y, heading, length, width, mass, lf, lr, params["max_engine_force"],
                            params["max_brake_force"], math.radians(params["max_steering"]), params["wheel_friction"],
                            mi.lane_of[tuple(lane_index)], TYPE_ID[vtype], group, drop_substeps(vtype), timer, off, n, 0,
                            rnd))
