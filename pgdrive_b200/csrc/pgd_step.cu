@@ -232,6 +232,8 @@ struct EnvShared {
   float olong[V];                  // longitudinal coordinate of each vehicle on its own lane (start of step)
   int blo[V], bn[V];               // lidar: first beam index and beam count each chassis can intersect
   int croad[V], nroad[V];          // localisation: current / next route road of each moving vehicle
+  int qlane[8];                    // ego queries: lane ids
+  float qlon[8], qlat[8];          // ego queries: Frenet results
   float d2[V];                     // squared centre distance to the ego (neighbour ranking)
   int ired[4];
 };
@@ -785,26 +787,79 @@ pgd_step_kernel(DevTables T, DevState S, PgdConfig cfg, int mode, int env_begin,
       }
     }
   }
+  // Ego bookkeeping.  Its seven independent geometric queries (four Frenet projections, two checkpoint features,
+  // the heading difference) are spread over threads 0..6 of the group so that they issue side by side.
   if (slot == 0) {
-    const int eck0 = ck0, eck1 = ck1;
+    const int cur_road_id = __ldg(&rroads[ck0]);
+    const PgdRoad cur_road = roads[cur_road_id];
+    const PgdRoad fr = roads[__ldg(&rroads[route_len - 2])];
+    const int el_road = __ldg(&lanes[lane].road);
+    const bool use_ego_lane = el_road == cur_road_id;
+    const int reward_lane = use_ego_lane ? lane : cur_road.first_lane;
+    sh.qlane[0] = cur_road.first_lane;                 // to_left / to_right
+    sh.qlane[1] = fr.first_lane + fr.n_lanes - 1;      // arrive_destination
+    sh.qlane[2] = reward_lane;                         // reward: longitudinal of the last position
+    sh.qlane[3] = reward_lane;                         //         and of the current one
+    sh.qlane[4] = cur_road.first_lane;                 // navigation info of the current road
+    sh.qlane[5] = __ldg(&roads[__ldg(&rroads[ck1])].first_lane);  // and of the next one
+    sh.qlane[6] = cur_road.first_lane + cur_road.n_lanes - 1;     // heading_diff: right-most reference lane
+    sh.ired[0] = cur_road.n_lanes;
+    sh.ired[1] = use_ego_lane ? 0 : (__ldg(&roads[el_road].negative) ? -1 : 1);
+    sh.ired[2] = cur_road_id;
+  }
+  __syncwarp(group_mask);
+  if (slot < 7 && !skip) {
+    const int n_ref = sh.ired[0];
+    const Lane l = load_lane(lanes + sh.qlane[slot]);
+    if (slot < 4) {
+      const bool last = slot == 2;
+      float lon, lat;
+      lane_local(l, last ? last_x : ex_, last ? last_y : ey_, lon, lat);
+      sh.qlon[slot] = lon;
+      sh.qlat[slot] = lat;
+      if (slot == 1) sh.qlon[4] = l.length;  // final lane length
+    } else if (slot < 6) {  // navigation.py:213-260
+      const float later_middle = ((float)n_ref / 2.0f - 0.5f) * mp.lane_width;
+      float px, py;
+      lane_position(l, l.length, later_middle, px, py);
+      float dx = px - ex_, dy = py - ey_;
+      const float dn = sqrtf(dx * dx + dy * dy);
+      if (dn > 50.0f) { dx = dx / dn * 50.0f; dy = dy / dn * 50.0f; }
+      float ph, ps;
+      project(eux, euy, dx, dy, ph, ps);
+      float bend = 0.0f, dir = 0.0f, angle = 0.0f;
+      if (l.kind == PGD_LANE_ARC) {
+        bend = l.radius / (60.0f + (float)n_ref * mp.lane_width);
+        dir = l.dir;
+        angle = l.length / l.radius;
+      }
+      float* q = ob + 8 + 5 * (slot - 4);
+      q[0] = clipf((ph / 50.0f + 1.0f) / 2.0f, 0.0f, 1.0f);
+      q[1] = clipf((ps / 50.0f + 1.0f) / 2.0f, 0.0f, 1.0f);
+      q[2] = clipf(bend, 0.0f, 1.0f);
+      q[3] = clipf((dir + 1.0f) / 2.0f, 0.0f, 1.0f);
+      q[4] = clipf((angle * (180.0f / PI_F) / 135.0f + 1.0f) / 2.0f, 0.0f, 1.0f);
+    } else {  // heading_diff (base_vehicle.py:433-458)
+      float lx, ly;
+      if (l.kind == PGD_LANE_STRAIGHT) { lx = -l.ay; ly = l.ax; }
+      else if (l.dir < 0.0f) { lx = ex_ - l.ax; ly = ey_ - l.ay; }
+      else { lx = l.ax - ex_; ly = l.ay - ey_; }
+      const float ln = sqrtf(lx * lx + ly * ly);
+      ob[2] = ln > 0.0f ? clipf((eux * lx + euy * ly) / ln, -1.0f, 1.0f) / 2.0f + 0.5f : 0.0f;
+    }
+  }
+  __syncwarp(group_mask);
+  if (slot == 0) {
     const bool on_lane = (vflags & PGD_V_ON_LANE) != 0;
     if (on_lane) flags |= PGD_F_ON_LANE;
     if (crash) flags |= PGD_F_CRASH_VEHICLE;
-    const int cur_road_id = __ldg(&rroads[eck0]);
-    const PgdRoad cur_road = roads[cur_road_id];
-    const int n_ref = cur_road.n_lanes;
-    const Lane ref0 = load_lane(lanes + cur_road.first_lane);
-    float lon0, lat0;
-    lane_local(ref0, x, y, lon0, lat0);
-    const float to_left = lat0 + mp.lane_width / 2.0f;
+    const int n_ref = sh.ired[0];
+    const float to_left = sh.qlat[0] + mp.lane_width / 2.0f;
     const float to_right = mp.lane_width * (float)n_ref - to_left;
     if (to_left < 0.0f || to_right < 0.0f) flags |= PGD_F_OUT_OF_ROUTE;
     {
-      const PgdRoad fr = roads[__ldg(&rroads[route_len - 2])];
-      const Lane fl = load_lane(lanes + fr.first_lane + fr.n_lanes - 1);
-      float lon, lat;
-      lane_local(fl, x, y, lon, lat);
-      if (fl.length - 5.0f < lon && lon < fl.length + 5.0f && mp.lane_width / 2.0f >= lat &&
+      const float lon = sh.qlon[1], lat = sh.qlat[1], flen = sh.qlon[4];
+      if (flen - 5.0f < lon && lon < flen + 5.0f && mp.lane_width / 2.0f >= lat &&
           lat >= (0.5f - (float)n_ref) * mp.lane_width)
         flags |= PGD_F_ARRIVE_DEST;
     }
@@ -813,61 +868,21 @@ pgd_step_kernel(DevTables T, DevState S, PgdConfig cfg, int mode, int env_begin,
     if (out_of_road) flags |= PGD_F_OUT_OF_ROAD;
 
     const float sp = clipf(v * 3.6f, 0.0f, 100000.0f);
-    float o18[18];
-    o18[0] = clipf(to_left / 18.0f, 0.0f, 1.0f);
-    o18[1] = clipf(to_right / 18.0f, 0.0f, 1.0f);
-    {  // heading_diff against the right-most reference lane
-      const Lane l = n_ref == 1 ? ref0 : load_lane(lanes + cur_road.first_lane + n_ref - 1);
-      float lx, ly;
-      if (l.kind == PGD_LANE_STRAIGHT) { lx = -l.ay; ly = l.ax; }
-      else if (l.dir < 0.0f) { lx = x - l.ax; ly = y - l.ay; }
-      else { lx = l.ax - x; ly = l.ay - y; }
-      const float ln = sqrtf(lx * lx + ly * ly);
-      o18[2] = ln > 0.0f ? clipf((hc * lx + hs * ly) / ln, -1.0f, 1.0f) / 2.0f + 0.5f : 0.0f;
-    }
-    o18[3] = clipf((sp + 1.0f) / (MAX_SPEED_KMH + 1.0f), 0.0f, 1.0f);
-    o18[4] = clipf((steer / 60.0f + 1.0f) / 2.0f, 0.0f, 1.0f);
-    o18[5] = clipf((envf.x + 1.0f) / 2.0f, 0.0f, 1.0f);
-    o18[6] = clipf((envf.y + 1.0f) / 2.0f, 0.0f, 1.0f);
+    float o8[8];
+    o8[0] = clipf(to_left / 18.0f, 0.0f, 1.0f);
+    o8[1] = clipf(to_right / 18.0f, 0.0f, 1.0f);
+    o8[3] = clipf((sp + 1.0f) / (MAX_SPEED_KMH + 1.0f), 0.0f, 1.0f);
+    o8[4] = clipf((steer / 60.0f + 1.0f) / 2.0f, 0.0f, 1.0f);
+    o8[5] = clipf((envf.x + 1.0f) / 2.0f, 0.0f, 1.0f);
+    o8[6] = clipf((envf.y + 1.0f) / 2.0f, 0.0f, 1.0f);
     // yaw rate = arccos(clip(cos(heading change), 0, 1)) / 0.1, evaluated as min(|change|, pi/2) (well-conditioned)
-    o18[7] = clipf(fminf(fabsf(wrap_to_pi(h - last_h)), PI_F / 2) / 0.1f, 0.0f, 1.0f);
-#pragma unroll
-    for (int which = 0; which < 2; ++which) {  // navigation info of the two target roads
-      const PgdRoad road = which == 0 ? cur_road : roads[__ldg(&rroads[eck1])];
-      const Lane ref = which == 0 ? ref0 : load_lane(lanes + road.first_lane);
-      const float later_middle = ((float)n_ref / 2.0f - 0.5f) * mp.lane_width;
-      float px, py;
-      lane_position(ref, ref.length, later_middle, px, py);
-      float dx = px - x, dy = py - y;
-      const float dn = sqrtf(dx * dx + dy * dy);
-      if (dn > 50.0f) { dx = dx / dn * 50.0f; dy = dy / dn * 50.0f; }
-      float ph, ps;
-      project(hc, hs, dx, dy, ph, ps);
-      float bend = 0.0f, dir = 0.0f, angle = 0.0f;
-      if (ref.kind == PGD_LANE_ARC) {
-        bend = ref.radius / (60.0f + (float)n_ref * mp.lane_width);
-        dir = ref.dir;
-        angle = ref.length / ref.radius;
-      }
-      float* q = o18 + 8 + 5 * which;
-      q[0] = clipf((ph / 50.0f + 1.0f) / 2.0f, 0.0f, 1.0f);
-      q[1] = clipf((ps / 50.0f + 1.0f) / 2.0f, 0.0f, 1.0f);
-      q[2] = clipf(bend, 0.0f, 1.0f);
-      q[3] = clipf((dir + 1.0f) / 2.0f, 0.0f, 1.0f);
-      q[4] = clipf((angle * (180.0f / PI_F) / 135.0f + 1.0f) / 2.0f, 0.0f, 1.0f);
-    }
+    o8[7] = clipf(fminf(fabsf(wrap_to_pi(h - last_h)), PI_F / 2) / 0.1f, 0.0f, 1.0f);
     // reward / cost / done
     float r = 0.0f, step_reward = 0.0f, cost = 0.0f, step_energy = 0.0f;
     int is_done = 0;
     if (!fresh) {
-      const Lane el = load_lane(lanes + lane);
-      float sign = 1.0f;
-      bool use_ego_lane = el.road == cur_road_id;
-      if (!use_ego_lane) sign = __ldg(&roads[el.road].negative) ? -1.0f : 1.0f;
-      const Lane rl = use_ego_lane ? el : ref0;
-      float long_last, long_now, lat_last, lat_now;
-      lane_local(rl, last_x, last_y, long_last, lat_last);
-      lane_local(rl, x, y, long_now, lat_now);
+      const float sign = sh.ired[1] == 0 ? 1.0f : (float)sh.ired[1];
+      const float long_last = sh.qlon[2], long_now = sh.qlon[3], lat_now = sh.qlat[3];
       float lateral_factor = 1.0f;
       if (cfg.use_lateral) lateral_factor = clipf(1.0f - 2.0f * fabsf(lat_now) / mp.lane_width, 0.0f, 1.0f);
       r += cfg.driving_reward * (long_now - long_last) * lateral_factor * sign;
@@ -891,8 +906,9 @@ pgd_step_kernel(DevTables T, DevState S, PgdConfig cfg, int mode, int env_begin,
       flags |= PGD_F_WAS_RESET;
     }
     if (!skip) {
+      ob[0] = o8[0]; ob[1] = o8[1];
 #pragma unroll
-      for (int k = 0; k < 18; ++k) ob[k] = o18[k];
+      for (int k = 3; k < 8; ++k) ob[k] = o8[k];
       if (mode == 0) {
         reward[env] = r;
         done[env] = (uint8_t)is_done;
