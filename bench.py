@@ -116,9 +116,19 @@ def cpu_oracle_rate(T, n_envs, steps, warmup, threads, episode_ids, seed=0):
     return n_envs * steps / dt, dt
 
 
-def build_tables():
+WORKLOADS = {
+    # name: (first seed, number of seeds, vehicle slots, description)
+    "v0": (1000, 100, 16, WORKLOAD),
+    "1000envs": (1000, 1000, 32, "65536 envs PGDrive-1000envs-v0 (seeds 1000-1999, 1000 distinct maps), "
+                                 "traffic_density=0.1, 240-beam lidar, 32 vehicle slots"),
+}
+
+
+def build_tables(workload="v0"):
     from pgdrive_b200.env import build_seed_tables, default_config, parse_map_config
-    return build_seed_tables(range(1000, 1100), parse_map_config(default_config()), 0.1, ((">", ">>", 0), 5.0, 0.0))
+    first, count, _, _ = WORKLOADS[workload]
+    return build_seed_tables(range(first, first + count), parse_map_config(default_config()), 0.1,
+                             ((">", ">>", 0), 5.0, 0.0))
 
 
 def run_reference(args):
@@ -127,19 +137,20 @@ def run_reference(args):
         return 0
     from oracle import oracle as orc
     orc.build()
-    T = build_tables()
+    T = build_tables(args.workload)
     threads = host_threads()
+    n_seeds = WORKLOADS[args.workload][1]
     # calibrate, then size the per-step sample so that warmup + steps finish in about 100 s
-    rate0, _ = cpu_oracle_rate(T, 1024, 4, 1, threads, [i % 100 for i in range(1024)])
+    rate0, _ = cpu_oracle_rate(T, 1024, 4, 1, threads, [i % n_seeds for i in range(1024)])
     n = int(min(args.envs, max(256, rate0 * 100.0 / (args.steps + args.warmup))))
     n = max(100, n // 100 * 100)
-    rate, dt = cpu_oracle_rate(T, n, args.steps, args.warmup, threads, [i % 100 for i in range(n)])
+    rate, dt = cpu_oracle_rate(T, n, args.steps, args.warmup, threads, [i % n_seeds for i in range(n)])
     sample = "%d of %d envs per step x %d steps, %d host threads" % (n, args.envs, args.steps, threads)
     line = dict(
         impl="reference", metric="env-steps/s", value=rate, unit="env-steps/s", n_gpus=args.gpus, steps=args.steps,
         warmup=args.warmup, ms_per_step=dt / args.steps * 1e3, higher_is_better=True, scaling="weak",
         vs_baseline=None, dtype="f32", data="synthetic",
-        config=dict(workload=WORKLOAD, envs_per_gpu=args.envs, actions="uniform[-1,1]^2, RandomState(0)",
+        config=dict(workload=WORKLOADS[args.workload][3], envs_per_gpu=args.envs, actions="uniform[-1,1]^2, RandomState(0)",
                     note="reference step needs Panda3D/Bullet (not installable offline): CPU oracle port timed instead"),
         cpu_baseline=dict(value=rate, unit="env-steps/s", cores=threads, kind="port", sample=sample),
         e2e=dict(value=rate, unit="env-steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
@@ -177,7 +188,8 @@ def run_own(args):
         dist.barrier()
     from pgdrive_b200 import VecPGDriveEnv, cabi
     n, K, W = args.envs, args.steps, args.warmup
-    T = build_tables()
+    first_seed, n_seeds, n_slots, workload_name = WORKLOADS[args.workload]
+    T = build_tables(args.workload)
     # weak scaling: rank r owns environments [r*n, (r+1)*n) of the global batch; the kernel writes its observations
     # straight into this rank's slice of the gather buffer (in-place all-gather, no packing kernel)
     from pgdrive_b200.sharding import GatherBuffers
@@ -186,7 +198,8 @@ def run_own(args):
     bufs = [GatherBuffers(torch, n, world, rank, dev, obs_dim=OBS_DIM) for _ in range(2 if world > 1 else 1)]
     side = torch.cuda.Stream(device=dev, priority=-1) if world > 1 else None
     env = VecPGDriveEnv(
-        dict(start_seed=1000, environment_num=100, num_envs=n, traffic_density=0.1, device=local_rank, num_slots=16),
+        dict(start_seed=first_seed, environment_num=n_seeds, num_envs=n, traffic_density=0.1, device=local_rank,
+             num_slots=n_slots),
         tables_dict=T, obs_out=bufs[0].local(bufs[0].obs)
     )
     env.reset()
@@ -294,7 +307,7 @@ def run_own(args):
 
     total_envs = world * n
     value = total_envs * K / (ms * 1e-3)
-    b_step = algorithmic_bytes_per_env_step(16)
+    b_step = algorithmic_bytes_per_env_step(n_slots)
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
@@ -310,7 +323,7 @@ def run_own(args):
     if world == 1 and not args.no_cpu:
         threads = host_threads()
         cn, cs = 32768, 128  # ~4.2M env-steps: 10-30 s of CPU work on a 16-thread host
-        rate, dt = cpu_oracle_rate(T, cn, cs, 2, threads, [i % 100 for i in range(cn)])
+        rate, dt = cpu_oracle_rate(T, cn, cs, 2, threads, [i % n_seeds for i in range(cn)])
         cpu = dict(value=rate, unit="env-steps/s", cores=threads, kind="port",
                    sample="%d of %d envs x %d steps (%.1f s), CPU oracle on %d host threads" % (cn, n, cs, dt, threads))
 
@@ -318,17 +331,17 @@ def run_own(args):
         metric="env-steps/s", value=value, unit="env-steps/s", n_gpus=world, steps=K, warmup=W,
         ms_per_step=ms / K, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
         config=dict(
-            workload=WORKLOAD, envs_per_gpu=n, total_envs=total_envs, parallelism="env-sharded x%d" % world,
+            workload=workload_name, envs_per_gpu=n, total_envs=total_envs, parallelism="env-sharded x%d" % world,
             actions="uniform[-1,1]^2, Philox, pre-generated in HBM",
             l2="no flush: state + observations touched per step = %.0f MB > 126 MB L2" % (
-                (2 * (80 * 16 + 32) + 4 * OBS_DIM) * n / 1e6),
+                (2 * (80 * n_slots + 32) + 4 * OBS_DIM) * n / 1e6),
             collective=("in-place NCCL all-gather of obs/reward/done every step, double-buffered on a side stream so "
                         "that it overlaps the next step's kernel") if world > 1 else "none",
             done_rate_last_step=done_rate,
             driving_policy_env_steps_per_s_per_gpu=fwd_rate,
         ),
         roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
-                      kernel="pgd_step_kernel<16>", kernel_ms=kernel_ms, bytes_per_env_step=b_step, peak_source=peak_src),
+                      kernel="pgd_step_kernel<%d>" % n_slots, kernel_ms=kernel_ms, bytes_per_env_step=b_step, peak_source=peak_src),
         cpu_baseline=cpu,
         e2e=dict(value=total_envs * e2e_steps / (e2e_ms * 1e-3), unit="env-steps/s",
                  h2d_bytes_per_step=n * 8, d2h_bytes_per_step=n * (4 * OBS_DIM + 4 + 1 + INFO_BYTES),
@@ -349,6 +362,8 @@ def main():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--envs", type=int, default=65536, help="environments per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--workload", default="v0", choices=sorted(WORKLOADS), help="v0 = BASELINE.json configs[2] (the metric's "
+                    "configuration); 1000envs = configs[3]")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

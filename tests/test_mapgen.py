@@ -70,3 +70,46 @@ def test_same_seed_same_map_and_named_sequence():
     assert [b.id for b in m.blocks] == list("ISSS")
     with pytest.raises(KeyError):
         mapgen.generate_map(0, sequence="Q")
+
+
+def test_thousand_seeds_match_reference_digests():
+    """PGDrive-1000envs-v0 (seeds 1000..1999): lanes, sockets, spawn lanes and every reset decision hashed bit-exactly
+    (tools/golden_hash.py) against digests computed from the unmodified reference (tools/make_golden.py digests)."""
+    import os
+    import sys
+    from multiprocessing import get_context
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from conftest import load_golden
+    gold = load_golden("digests_1000_1999.json.gz")
+    seeds = sorted(int(s) for s in gold)
+    with get_context("fork").Pool(min(8, os.cpu_count() or 1)) as pool:
+        got = pool.map(_digest_of_seed, seeds, chunksize=16)
+    bad = [s for s, g in zip(seeds, got) if list(g) != gold[str(s)]]
+    assert not bad, "seeds whose map / reset digests differ from the reference: %s" % bad[:10]
+
+
+def _digest_of_seed(seed):
+    import golden_hash
+    from pgdrive_b200 import episode
+    m = mapgen.generate_map(seed)
+    index = {id(ln): [f, t, i] for f, t, i, ln in _lanes(m)}
+    lanes = []
+    for f, t, i, ln in _lanes(m):
+        rec = dict(frm=f, to=t, idx=i, kind=ln.kind, line_types=[str(x) for x in ln.line_types],
+                   colours=list(ln.line_color), start=[ln.sx, ln.sy], end=[ln.ex, ln.ey], length=ln.length,
+                   width=ln.width, speed_limit=ln.speed_limit)
+        if ln.kind == "C":
+            rec.update(center=[ln.cx, ln.cy], radius=ln.radius, start_phase=ln.ph0, end_phase=ln.ph1, direction=ln.dir)
+        lanes.append(rec)
+    blocks = []
+    for b in m.blocks:
+        spawn = [[index[id(ln)] for ln in ls] for ls in b.spawn_lanes()] if b.idx else []
+        blocks.append([b.id, [[x.index, list(x.pos), list(x.neg)] for x in b.sockets.values()],
+                       [list(r) for r in b.respawn], list(b.pre_socket.pos), spawn])
+    ep = episode.make_episode(m, seed, 0.1)
+    rec = dict(ego_seed=ep.ego_seed, ego_params=ep.ego_params, ego_checkpoints=ep.ego_checkpoints,
+               block_vehicles=[(list(tr), [dict(type=v.type, lane=list(v.lane), long=v.long, seed=v.seed,
+                                                params=v.params, idm_seed=v.idm_seed,
+                                                overtake_timer=v.overtake_timer, checkpoints=v.checkpoints)
+                                           for v in vs]) for tr, vs in ep.block_vehicles])
+    return golden_hash.map_digest(lanes, blocks), golden_hash.episode_digest(rec), "".join(b.id for b in m.blocks)

@@ -625,3 +625,34 @@ def cmd_lidar(tag, n_scenes=40):
 
 if __name__ == "__main__" and sys.argv[1] == "lidar":
     cmd_lidar("v0")
+
+
+def cmd_digests(seeds, tag):
+    """Compact fixtures for many seeds: one sha1 per seed over the reference's lanes / sockets and one over its
+    reset decisions (tools/golden_hash.py defines what is hashed)."""
+    import golden_hash
+    out = {}
+    for s in seeds:
+        d = dump_map(s)
+        lanes = []
+        for l in d["lanes"]:
+            l = dict(l)
+            l["colours"] = ["Y" if abs(c[0] - 1) > 1e-6 else "G" for c in l.pop("line_color")]
+            lanes.append(l)
+        blocks = [[b["id"], [[x["index"], x["pos"], x["neg"]] for x in b["sockets"]], b["respawn_roads"],
+                   b["trigger_road"], b["spawn_lanes"]] for b in d["blocks"]]
+        r = dump_reset(s)
+        rec = dict(ego_seed=r["ego_seed"], ego_params=r["ego_params"], ego_checkpoints=r["ego_checkpoints"],
+                   block_vehicles=[(g["trigger_road"], g["vehicles"]) for g in r["block_vehicles"]])
+        out[str(s)] = [golden_hash.map_digest(lanes, blocks), golden_hash.episode_digest(rec),
+                       "".join(b["id"] for b in d["block_sequence"])]
+        if s % 100 == 0:
+            print(s, out[str(s)])
+    path = os.path.join(GOLD, "digests_%s.json.gz" % tag)
+    with gzip.open(path, "wt") as f:
+        json.dump(out, f)
+    print("wrote", path, os.path.getsize(path))
+
+
+if __name__ == "__main__" and sys.argv[1] == "digests":
+    cmd_digests(list(range(1000, 2000)), "1000_1999")
