@@ -202,6 +202,24 @@ def run_own(args):
              num_slots=n_slots),
         tables_dict=T, obs_out=bufs[0].local(bufs[0].obs)
     )
+    # N > 1, default: the gather to rank 0 is fused into the step kernel (results stored straight into rank 0's HBM
+    # through CUDA-IPC peer mappings over NVLink; pgdrive_b200.sharding.PeerGather).  --gather nccl selects the plain
+    # in-place NCCL all-gather instead; it is also the fall-back when peer mapping is not permitted on the box.
+    peer = None
+    gather_mode = "none"
+    if world > 1:
+        gather_mode = args.gather
+        if gather_mode == "peer":
+            from pgdrive_b200.sharding import PeerGather
+            ok = torch.ones(1, dtype=torch.int32, device=dev)
+            try:
+                peer = PeerGather(env, torch, dist, n, world, rank)
+            except Exception as exc:  # noqa: BLE001
+                sys.stderr.write("rank %d: peer gather unavailable (%s)\n" % (rank, exc))
+                ok.zero_()
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                peer, gather_mode = None, "nccl (peer mapping unavailable)"
     env.reset()
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)  # Philox counter-based stream, one per rank
@@ -216,8 +234,16 @@ def run_own(args):
             return
         i = counter[0] % 2
         counter[0] += 1
-        b = bufs[i]
         cur = torch.cuda.current_stream(dev)
+        if peer is not None:
+            env.step_into(a, *peer.pointers(i))
+            ready = torch.cuda.Event()
+            ready.record(cur)
+            side.wait_event(ready)
+            with torch.cuda.stream(side):
+                peer.completion_barrier()
+            return
+        b = bufs[i]
         if free[i] is not None:
             cur.wait_event(free[i])
         env.step(a, out=(b.local(b.obs), b.local(b.reward), b.local(b.done)))
@@ -262,7 +288,12 @@ def run_own(args):
     kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in k_ev]))
     launches = env.launch_count - launches0
     clk = clocks.stop() if rank == 0 else None
-    last_done = env.done if world == 1 else bufs[0].local(bufs[0].done)
+    if world == 1 or (peer is not None and rank != 0):
+        last_done = env.done
+    elif peer is not None:
+        last_done = peer.tensors(0)[2][:n]
+    else:
+        last_done = bufs[0].local(bufs[0].done)
     done_rate = float(last_done.float().mean().item())
 
     # ---- the same kernel under a policy that actually drives (traffic awake, lidar hits, frequent resets): reported
@@ -335,8 +366,12 @@ def run_own(args):
             actions="uniform[-1,1]^2, Philox, pre-generated in HBM",
             l2="no flush: state + observations touched per step = %.0f MB > 126 MB L2" % (
                 (2 * (80 * n_slots + 32) + 4 * OBS_DIM) * n / 1e6),
-            collective=("in-place NCCL all-gather of obs/reward/done every step, double-buffered on a side stream so "
-                        "that it overlaps the next step's kernel") if world > 1 else "none",
+            collective={"none": "none",
+                        "peer": "gather to rank 0 fused into the step kernel: obs/reward/done stored into rank 0's HBM "
+                                "through CUDA-IPC peer mappings over NVLink; one 4-byte all-reduce per step as the "
+                                "completion barrier (side stream)"}.get(
+                gather_mode, "in-place NCCL all-gather of obs/reward/done every step, double-buffered on a high-"
+                             "priority side stream so that it overlaps the next step's kernel [%s]" % gather_mode),
             done_rate_last_step=done_rate,
             driving_policy_env_steps_per_s_per_gpu=fwd_rate,
         ),
@@ -362,6 +397,7 @@ def main():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--envs", type=int, default=65536, help="environments per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"], help="N > 1: how rank 0 gets the whole batch")
     ap.add_argument("--workload", default="v0", choices=sorted(WORKLOADS), help="v0 = BASELINE.json configs[2] (the metric's "
                     "configuration); 1000envs = configs[3]")
     args = ap.parse_args()

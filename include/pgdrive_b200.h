@@ -56,6 +56,15 @@ int pgd_step_host(PgdHandle* h, const float* actions, float* obs, float* reward,
 int pgd_get_state(PgdHandle* h, int32_t env, PgdEnvState* out);
 int pgd_set_state(PgdHandle* h, int32_t env, const PgdEnvState* in);
 
+/* Cross-process peer memory (one process per GPU, NVLink / NVSwitch).  The owner allocates a device buffer and
+ * exports a 64-byte handle; every other rank opens it and passes `base + its row offset` as obs_dev / reward_dev /
+ * done_dev of pgd_step, so the step kernel stores its results straight into the owner's HBM over NVLink: the gather
+ * of the observation batch to rank 0 (BASELINE.json north_star) is fused into the kernel and no collective moves
+ * payload.  (The reference has no multi-process path at all: engine/engine_utils.py:8-15.) */
+int pgd_peer_alloc(PgdHandle* h, uint64_t bytes, void** dev_ptr, unsigned char handle_out[64]);
+int pgd_peer_open(PgdHandle* h, const unsigned char handle[64], void** dev_ptr);
+int pgd_peer_release(PgdHandle* h, void* dev_ptr, int32_t is_owner);
+
 /* measurement helpers */
 int64_t pgd_state_bytes_per_env(PgdHandle* h);   /* bytes of simulator state kept per environment */
 int64_t pgd_launch_count(PgdHandle* h);          /* kernels launched by this handle so far */

@@ -1267,6 +1267,36 @@ extern "C" int pgd_set_state(PgdHandle* h, int32_t env, const PgdEnvState* in) {
   return 0;
 }
 
+extern "C" int pgd_peer_alloc(PgdHandle* h, uint64_t bytes, void** dev_ptr, unsigned char handle_out[64]) {
+  if (!h || !dev_ptr || !handle_out) return fail(-1, "pgd_peer_alloc: null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  CU(cudaSetDevice(h->device));
+  CU(cudaMalloc(dev_ptr, bytes));
+  CU(cudaMemset(*dev_ptr, 0, bytes));
+  cudaIpcMemHandle_t ipc;
+  CU(cudaIpcGetMemHandle(&ipc, *dev_ptr));
+  memcpy(handle_out, &ipc, 64);
+  return 0;
+}
+
+extern "C" int pgd_peer_open(PgdHandle* h, const unsigned char handle[64], void** dev_ptr) {
+  if (!h || !dev_ptr || !handle) return fail(-1, "pgd_peer_open: null argument");
+  CU(cudaSetDevice(h->device));
+  cudaIpcMemHandle_t ipc;
+  memcpy(&ipc, handle, 64);
+  CU(cudaIpcOpenMemHandle(dev_ptr, ipc, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+
+extern "C" int pgd_peer_release(PgdHandle* h, void* dev_ptr, int32_t is_owner) {
+  if (!h || !dev_ptr) return fail(-1, "pgd_peer_release: null argument");
+  CU(cudaSetDevice(h->device));
+  CU(cudaDeviceSynchronize());
+  if (is_owner) CU(cudaFree(dev_ptr));
+  else CU(cudaIpcCloseMemHandle(dev_ptr));
+  return 0;
+}
+
 extern "C" int64_t pgd_state_bytes_per_env(PgdHandle* h) { return h ? (int64_t)h->cfg.num_slots * 80 + 32 : 0; }
 extern "C" int64_t pgd_launch_count(PgdHandle* h) { return h ? h->launches : 0; }
 extern "C" int pgd_set_timing(PgdHandle* h, int32_t on) {

@@ -235,6 +235,17 @@ class VecPGDriveEnv:
         )
         return self.obs
 
+    def step_into(self, actions, obs_ptr, reward_ptr, done_ptr):
+        """Device step writing results to raw device pointers (e.g. this rank's rows of a peer-mapped gather buffer,
+        pgdrive_b200.sharding.PeerGather).  ``actions``: float32 CUDA tensor [N, 2]."""
+        e = self.engine
+        a = actions.contiguous()
+        cabi.check(
+            e.lib,
+            e.lib.pgd_step(e.h, a.data_ptr(), int(obs_ptr), int(reward_ptr), int(done_ptr), self.info.data_ptr(),
+                           e.stream())
+        )
+
     def step(self, actions, out=None):
         """``actions``: ``[N, 2]`` float32, either a CUDA tensor (device path: returns CUDA tensors, no
         synchronisation) or a numpy array (host path: pinned staging, returns numpy arrays).  ``out`` (device path

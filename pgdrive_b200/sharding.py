@@ -39,3 +39,66 @@ class GatherBuffers:
             return
         for t in (self.obs, self.reward, self.done):
             dist.all_gather_into_tensor(t, self.local(t), group=group)
+
+
+class _DevArray:
+    """Lets torch wrap a raw device pointer (``torch.as_tensor``) through ``__cuda_array_interface__``."""
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = dict(shape=tuple(shape), typestr=typestr, data=(int(ptr), False), version=2)
+
+
+class PeerGather:
+    """Gather to rank 0 fused into the step kernel: rank 0 owns ``depth`` whole-batch buffers, every other rank maps
+    them through CUDA IPC and hands the step kernel pointers to ITS rows, so observations / rewards / dones are
+    written over NVLink as they are produced.  No collective carries payload; a per-step ``completion_barrier``
+    (a 4-byte all-reduce) tells rank 0 that every rank's kernel for that buffer has finished."""
+    def __init__(self, env, torch, dist, n_local, world_size, rank, obs_dim=274, depth=2):
+        import ctypes as C
+        from . import cabi
+        self.env, self.torch, self.dist = env, torch, dist
+        self.n, self.world, self.rank, self.depth, self.obs_dim = n_local, world_size, rank, depth, obs_dim
+        rows = world_size * n_local
+        self.obs_bytes, self.rew_bytes = rows * obs_dim * 4, rows * 4
+        self.done_bytes = (rows + 255) // 256 * 256
+        self.stride = self.obs_bytes + self.rew_bytes + self.done_bytes
+        e = env.engine
+        self._lib, self._h = e.lib, e.h
+        base = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        if rank == 0:
+            cabi.check(e.lib, e.lib.pgd_peer_alloc(e.h, self.stride * depth, C.byref(base), handle))
+        blob = [handle.raw if rank == 0 else None]
+        if world_size > 1:
+            dist.broadcast_object_list(blob, src=0)
+        if rank != 0:
+            cabi.check(e.lib, e.lib.pgd_peer_open(e.h, blob[0], C.byref(base)))
+        self.base = base.value
+        self._flag = torch.zeros(1, dtype=torch.int32, device=e.device)
+
+    def pointers(self, i):
+        """(obs, reward, done) device pointers of THIS rank's rows in buffer ``i``."""
+        b = self.base + (i % self.depth) * self.stride
+        return (b + self.rank * self.n * self.obs_dim * 4, b + self.obs_bytes + self.rank * self.n * 4,
+                b + self.obs_bytes + self.rew_bytes + self.rank * self.n)
+
+    def completion_barrier(self):
+        """Enqueue (on the current stream) a barrier after which rank 0 may read the buffer written last."""
+        if self.world > 1:
+            self.dist.all_reduce(self._flag)
+
+    def tensors(self, i):
+        """Rank 0 only: the whole-batch (obs, reward, done) tensors of buffer ``i``."""
+        assert self.rank == 0
+        t = self.torch
+        rows = self.world * self.n
+        b = self.base + (i % self.depth) * self.stride
+        obs = t.as_tensor(_DevArray(b, (rows, self.obs_dim), "<f4"), device=self.env.engine.device)
+        rew = t.as_tensor(_DevArray(b + self.obs_bytes, (rows, ), "<f4"), device=self.env.engine.device)
+        done = t.as_tensor(_DevArray(b + self.obs_bytes + self.rew_bytes, (rows, ), "|u1"), device=self.env.engine.device)
+        return obs, rew, done
+
+    def close(self):
+        import ctypes as C
+        if self.base:
+            self._lib.pgd_peer_release(self._h, C.c_void_p(self.base), 1 if self.rank == 0 else 0)
+            self.base = 0
