@@ -232,6 +232,7 @@ struct EnvShared {
   float olong[V];                  // longitudinal coordinate of each vehicle on its own lane (start of step)
   int blo[V], bn[V];               // lidar: first beam index and beam count each chassis can intersect
   int croad[V], nroad[V];          // localisation: current / next route road of each moving vehicle
+  float2 obs2[PGD_OBS_DIM / 2];    // the observation row is assembled here and streamed out with 8-byte stores
   int qlane[8];                    // ego queries: lane ids
   float qlon[8], qlat[8];          // ego queries: Frenet results
   float d2[V];                     // squared centre distance to the ego (neighbour ranking)
@@ -688,7 +689,7 @@ pgd_step_kernel(DevTables T, DevState S, PgdConfig cfg, int mode, int env_begin,
 
   PHASE_SYNC();
   // ---- phase F: observation, reward, done -----------------------------------------------------------------------
-  float* ob = obs + (size_t)env * PGD_OBS_DIM;
+  float* ob = reinterpret_cast<float*>(sh.obs2);  // staged row; copied to obs[env] at the end of phase F
   // lidar: beam i = slot + V * k.  Each chassis first publishes the (conservative) arc of beams that can reach it:
   // it lies inside the disc of radius half-diagonal around its centre, so only beams within asin(hd / d) of its
   // bearing and only chassis closer than 50 m + hd matter.  The cull never changes a result (the reference's own
@@ -924,6 +925,15 @@ pgd_step_kernel(DevTables T, DevState S, PgdConfig cfg, int mode, int env_begin,
       S.envi[env] = envi;
       S.envf[env] = envf;
     }
+  }
+
+  // stream the staged observation row out: 137 x 8 B per environment, consecutive threads -> consecutive addresses
+  // (full 32 B sectors whether the destination is local HBM or a peer-mapped gather buffer on another GPU)
+  __syncwarp(group_mask);
+  if (!skip) {
+    float2* dst = reinterpret_cast<float2*>(obs + (size_t)env * PGD_OBS_DIM);
+#pragma unroll 3
+    for (int k = slot; k < PGD_OBS_DIM / 2; k += V) dst[k] = sh.obs2[k];
   }
 
   // ---- phase G: store --------------------------------------------------------------------------------------------
