@@ -144,3 +144,35 @@ def test_world_size_2_gather_under_gloo(tmp_path):
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, o
         assert "rank %d ok" % r in o
+
+
+def test_abi_argument_errors_without_a_gpu():
+    """Error behaviour of the C-ABI that does not need a device: negative code + message (include/pgdrive_b200.h)."""
+    import __graft_entry__
+    __graft_entry__.build()
+    from pgdrive_b200 import cabi
+    lib = cabi.load_library()
+    h = ctypes.c_void_p()
+    assert lib.pgd_create(None, 0, ctypes.byref(h)) == -1
+    assert b"null" in lib.pgd_last_error()
+    bad = cabi.make_config(0)
+    assert lib.pgd_create(ctypes.byref(bad), 0, ctypes.byref(h)) == -1
+    assert b"num_envs" in lib.pgd_last_error()
+    bad = cabi.make_config(4, num_slots=12)
+    assert lib.pgd_create(ctypes.byref(bad), 0, ctypes.byref(h)) == -1
+    assert b"num_slots" in lib.pgd_last_error()
+    assert lib.pgd_step(None, None, None, None, None, None, None) == -1
+    assert lib.pgd_reset(None, None, None, 0, None, None, None) == -1
+    assert lib.pgd_destroy(None) == 0
+    assert lib.pgd_launch_count(None) == 0
+
+
+def test_vec_env_rejects_unsupported_options():
+    from pgdrive_b200 import VecPGDriveEnv
+    for cfg in (dict(traffic_mode="respawn"), dict(random_traffic=True), dict(num_agents=2),
+                dict(vehicle_config=dict(lidar=dict(num_lasers=120))),
+                dict(vehicle_config=dict(side_detector=dict(num_lasers=8)))):
+        with pytest.raises(NotImplementedError):
+            VecPGDriveEnv(cfg)
+    with pytest.raises(KeyError):
+        VecPGDriveEnv(dict(no_such_key=True))
