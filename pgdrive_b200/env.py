@@ -56,9 +56,12 @@ def parse_map_config(cfg):
 
 
 def _seed_tables(args):
-    seed, mc, density, spawn = args
+    seed, mc, density, spawn = args[:4]
+    stored = args[4] if len(args) > 4 else None
     kw = dict(lane_num=mc["lane_num"], lane_width=mc["lane_width"], exit_length=mc["exit_length"])
-    if mc["type"] == "block_num":
+    if stored is not None:  # restored from a map file: no block search (pg_map.py:48-71)
+        pgmap = mapgen.build_from_sequence(seed, stored, **kw)
+    elif mc["type"] == "block_num":
         pgmap = mapgen.generate_map(seed, block_num=mc["config"], **kw)
     elif mc["type"] == "block_sequence":
         pgmap = mapgen.generate_map(seed, sequence=mc["config"], **kw)
@@ -98,11 +101,44 @@ def merge_tables(parts):
     return T
 
 
-def build_seed_tables(seeds, map_config, density, spawn, workers=None):
+def load_map_file(path_or_dict, map_config, seeds):
+    """The reference's map-collection format (``PGDriveEnv.dump_all_maps``, envs/pgdrive_env.py:260-288; read back by
+    manager/map_manager.py:43-91): ``{"map_config": {...}, "map_data": {seed: {"block_sequence": [...]}}}``.
+    Returns {seed: block_sequence} when the file's map_config equals ours and it covers ``seeds``, else None
+    (the reference then falls back to generating the maps, map_manager.py:55-64)."""
+    import json
+    data = path_or_dict
+    if not isinstance(data, dict):
+        with open(path_or_dict) as f:
+            data = json.load(f)
+    if set(data.keys()) != {"map_config", "map_data"}:
+        raise ValueError("a map file holds exactly the keys map_config and map_data")
+    have = {int(k): v for k, v in data["map_data"].items()}
+    if dict(data["map_config"]) != dict(map_config) or not set(int(s) for s in seeds).issubset(have):
+        return None
+    return {s: have[s]["block_sequence"] for s in have}
+
+
+def dump_maps(seeds, map_config):
+    """``dump_all_maps``: block sequences of ``seeds`` in the reference's JSON-serialisable format."""
+    kw = dict(lane_num=map_config["lane_num"], lane_width=map_config["lane_width"],
+              exit_length=map_config["exit_length"])
+    out = {}
+    for s in seeds:
+        if map_config["type"] == "block_num":
+            seq = mapgen.search_sequence(int(s), block_num=map_config["config"], **kw)
+        else:
+            seq = mapgen.search_sequence(int(s), sequence=map_config["config"], **kw)
+        out[int(s)] = {"block_sequence": seq}
+    return dict(map_config=dict(map_config), map_data=out)
+
+
+def build_seed_tables(seeds, map_config, density, spawn, workers=None, stored=None):
     """Tables for a list of seeds, built in worker processes when there are many, with an optional
-    on-disk cache ($PGDRIVE_B200_CACHE) because map search costs ~50 ms per seed."""
+    on-disk cache ($PGDRIVE_B200_CACHE) because map search costs ~50 ms per seed.  ``stored`` = {seed: block
+    sequence} restored from a map file."""
     seeds = [int(s) for s in seeds]
-    jobs = [(s, map_config, density, spawn) for s in seeds]
+    jobs = [(s, map_config, density, spawn, (stored or {}).get(s)) for s in seeds]
     cache_dir = os.environ.get("PGDRIVE_B200_CACHE")
     path = None
     if cache_dir:
@@ -184,8 +220,11 @@ class VecPGDriveEnv:
         vc = cfg["vehicle_config"]
         self._spawn = (tuple(vc["spawn_lane_index"]), float(vc["spawn_longitude"]), float(vc["spawn_lateral"]))
         seeds = list(range(self.start_seed, self.start_seed + self.env_num))
+        stored = None
+        if cfg["load_map_from_json"] and cfg["_load_map_from_json"] is not None:
+            stored = load_map_file(cfg["_load_map_from_json"], self.map_config, seeds)
         self.T = tables_dict if tables_dict is not None else build_seed_tables(
-            seeds, self.map_config, cfg["traffic_density"], self._spawn
+            seeds, self.map_config, cfg["traffic_density"], self._spawn, stored=stored
         )
         self.episode_of_seed = {int(s): i for i, s in enumerate(self.T["episodes"]["seed"])}
         need = int(self.T["max_slots"])
@@ -333,6 +372,10 @@ class PGDriveEnv:
         self.observation_space = Box(-0.0, 1.0, shape=(cabi.OBS_DIM, ), dtype=np.float32)
         self.action_space = Box(-1.0, 1.0, shape=(2, ), dtype=np.float32)
         self._parts, self._episode_of_seed = [], {}
+        self._stored = None
+        if self.config["load_map_from_json"] and self.config["_load_map_from_json"] is not None:
+            self._stored = load_map_file(self.config["_load_map_from_json"], self.map_config,
+                                         range(self.start_seed, self.start_seed + self.env_num))
         self._engine = None
         self._seed = None
         self._rs = np.random.RandomState()
@@ -343,7 +386,8 @@ class PGDriveEnv:
     def _ensure_seed(self, seed):
         if seed in self._episode_of_seed:
             return
-        part = _seed_tables((seed, self.map_config, self.config["traffic_density"], self._spawn))
+        part = _seed_tables((seed, self.map_config, self.config["traffic_density"], self._spawn,
+                             (self._stored or {}).get(seed)))
         self._parts.append(part)
         self._episode_of_seed[seed] = len(self._parts) - 1
         T = merge_tables(self._parts)
@@ -362,6 +406,10 @@ class PGDriveEnv:
             self._info = torch.zeros((1, cabi.INFO_DT.itemsize // 4), dtype=torch.int32, device=dev)
             self._act = torch.zeros((1, 2), dtype=torch.float32, device=dev)
         self._engine.load(T)
+
+    def dump_all_maps(self):
+        """envs/pgdrive_env.py:260-288: every map of [start_seed, start_seed + environment_num) as block sequences."""
+        return dump_maps(range(self.start_seed, self.start_seed + self.env_num), self.map_config)
 
     def seed(self, seed=None):
         if seed is not None:

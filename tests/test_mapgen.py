@@ -113,3 +113,36 @@ def _digest_of_seed(seed):
                                                 overtake_timer=v.overtake_timer, checkpoints=v.checkpoints)
                                            for v in vs]) for tr, vs in ep.block_vehicles])
     return golden_hash.map_digest(lanes, blocks), golden_hash.episode_digest(rec), "".join(b.id for b in m.blocks)
+
+
+def test_map_file_round_trip_in_the_reference_format(golden_maps, tmp_path):
+    """dump_all_maps -> JSON -> load (test_loading_map_from_json.py:8-63): the dumped block sequences are the
+    reference's, and tables built from the file equal tables built by the live block search."""
+    import json
+    import numpy as np
+    from pgdrive_b200 import PGDriveEnv
+    from pgdrive_b200.env import build_seed_tables, load_map_file, parse_map_config
+    env = PGDriveEnv(dict(start_seed=1000, environment_num=4))
+    data = env.dump_all_maps()
+    assert set(data) == {"map_config", "map_data"} and sorted(data["map_data"]) == [1000, 1001, 1002, 1003]
+    for s in data["map_data"]:
+        gold = golden_maps[str(s)]["block_sequence"]
+        mine = data["map_data"][s]["block_sequence"]
+        assert [b["id"] for b in mine] == [b["id"] for b in gold]
+        assert json.loads(json.dumps(mine)) == gold  # same keys, same float values after a JSON round trip
+    path = tmp_path / "maps.json"
+    path.write_text(json.dumps(data))
+    mc = parse_map_config(env.config)
+    stored = load_map_file(str(path), mc, [1000, 1001, 1002, 1003])
+    assert stored is not None
+    spawn = ((">", ">>", 0), 5.0, 0.0)
+    a = build_seed_tables([1000, 1001, 1002, 1003], mc, 0.1, spawn, stored=stored)
+    b = build_seed_tables([1000, 1001, 1002, 1003], mc, 0.1, spawn)
+    for k in a:
+        if hasattr(a[k], "tobytes"):
+            assert a[k].tobytes() == b[k].tobytes(), k
+    # a file made for another map_config, or not covering the seeds, is ignored (the reference falls back to BIG)
+    assert load_map_file(str(path), dict(mc, lane_num=2), [1000]) is None
+    assert load_map_file(str(path), mc, [1000, 1999]) is None
+    env2 = PGDriveEnv(dict(start_seed=1000, environment_num=4, _load_map_from_json=str(path)))
+    assert env2._stored is not None and 1002 in env2._stored
