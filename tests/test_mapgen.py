@@ -146,3 +146,30 @@ def test_map_file_round_trip_in_the_reference_format(golden_maps, tmp_path):
     assert load_map_file(str(path), mc, [1000, 1999]) is None
     env2 = PGDriveEnv(dict(start_seed=1000, environment_num=4, _load_map_from_json=str(path)))
     assert env2._stored is not None and 1002 in env2._stored
+
+
+REF_JSON = "/root/reference/pgdrive/assets/maps/20210814_generated_maps_start_seed_0_environment_num_30000.json"
+
+
+def _search(seed):
+    return seed, mapgen.search_sequence(seed)
+
+
+@pytest.mark.skipif(not __import__("os").path.exists(REF_JSON), reason="reference assets only exist in the build container")
+def test_block_search_against_the_shipped_30000_map_file():
+    """The reference ships the block sequences of seeds 0..29999 (its golden asset, proven identical to live BIG by
+    test_loading_map_from_json.py).  Every tenth seed (3000 maps) must come out of our block search identically, and the
+    file itself loads through load_map_file."""
+    import json
+    import os
+    from multiprocessing import get_context
+    from pgdrive_b200.env import default_config, load_map_file, parse_map_config
+    with open(REF_JSON) as f:
+        data = json.load(f)
+    seeds = list(range(0, 30000, 10))
+    with get_context("fork").Pool(min(8, os.cpu_count() or 1)) as pool:
+        got = dict(pool.map(_search, seeds, chunksize=16))
+    bad = [s for s in seeds if json.loads(json.dumps(got[s])) != data["map_data"][str(s)]["block_sequence"]]
+    assert not bad, "block sequences differ from the shipped file for seeds %s" % bad[:10]
+    stored = load_map_file(data, parse_map_config(default_config()), range(1000, 1100))
+    assert stored is not None and len(stored) == 30000
