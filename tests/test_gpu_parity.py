@@ -310,3 +310,21 @@ def test_1000envs_config_with_32_slots():
     dones = _rollout(env, ref, 120, act, check_state_every=30, resync_budget=5)
     assert dones > 0
     env.close()
+
+
+def test_config5_size_524288_envs_on_one_gpu():
+    """BASELINE.json configs[4] total size on a single GPU (maximum size): replicas of a seed stay bit-identical."""
+    import torch
+    n = 524288
+    env, _ = _pair(n, list(range(1000, 1100)))
+    env.reset()
+    idx = torch.arange(n, device="cuda") % 100
+    g = torch.Generator(device="cuda")
+    g.manual_seed(3)
+    for t in range(12):
+        a100 = torch.rand((100, 2), generator=g, device="cuda") * 2 - 1
+        a100[:, 1] = a100[:, 1].abs()
+        o, r, d, _ = env.step(a100[idx].contiguous())
+        assert torch.equal(o, o[:100][idx]) and torch.equal(r, r[:100][idx]) and torch.equal(d, d[:100][idx]), t
+    assert float(o.min()) >= 0.0 and float(o.max()) <= 1.0
+    env.close()
