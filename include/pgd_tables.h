@@ -22,7 +22,9 @@ extern "C" {
 
 enum { PGD_LANE_STRAIGHT = 0, PGD_LANE_ARC = 1 };
 enum { PGD_BOX_LANE = 0, PGD_BOX_WHITE = 1, PGD_BOX_YELLOW = 2, PGD_BOX_BROKEN = 3, PGD_BOX_SIDEWALK = 4 };
-enum { PGD_MAX_SLOTS = 32, PGD_MAX_GROUPS = 11, PGD_N_RND25 = 16, PGD_OBS_DIM = 274, PGD_LIDAR_BEAMS = 240 };
+/* PGD_OBS_DIM is the PGDrive-v0 observation (no side / lane-line detector); with detectors see pgd_obs_dim(). */
+enum { PGD_MAX_SLOTS = 32, PGD_MAX_GROUPS = 11, PGD_N_RND25 = 16, PGD_OBS_DIM = 274, PGD_LIDAR_BEAMS = 240,
+       PGD_MAX_DETECTOR_BEAMS = 240 };
 
 typedef struct {          /* 64 B */
   float sx, sy, ex, ey;   /* start / end point of the centre line */
@@ -91,8 +93,18 @@ typedef struct {
   float out_of_road_cost, crash_vehicle_cost;
   int32_t use_lateral, out_of_route_done;
   int32_t auto_reset;       /* 1: an env that reported done is reset at its next step (action ignored) */
+  /* ray fans against lane-line ghosts (vehicle_module/distance_detector.py:137-152; off in PGDrive-v0):
+   * side detector = continuous lines only, lane-line detector = continuous + broken; beam i points at
+   * i * 2pi / n + 90 degrees from the heading */
+  int32_t n_side, n_lane_line;
+  float side_distance, lane_line_distance;
   int32_t pad;
 } PgdConfig;
+
+/* Observation length (obs/state_obs.py:18-23,108-115,125-130): (n_side or 2) + 6 + n_lane_line + 10 + 16 + 240. */
+static inline int32_t pgd_obs_dim(const PgdConfig* c) {
+  return (c->n_side > 0 ? c->n_side : 2) + 6 + c->n_lane_line + 10 + 16 + PGD_LIDAR_BEAMS;
+}
 
 /* per-step info (base_vehicle.py:262-272, pgdrive_env.py:165-207, base_env.py:335-339) */
 enum {

@@ -57,7 +57,8 @@ class Oracle:
         self.cfg = cabi.make_config(num_envs, **cfg)
         self.n = num_envs
         self.h = self.L.orc_create(C.byref(self.tables), C.byref(self.cfg))
-        self.obs = np.zeros((num_envs, cabi.OBS_DIM), np.float32)
+        self.obs_dim = cabi.obs_dim(self.cfg)
+        self.obs = np.zeros((num_envs, self.obs_dim), np.float32)
         self.reward = np.zeros(num_envs, np.float32)
         self.done = np.zeros(num_envs, np.uint8)
         self.info = np.zeros(num_envs, cabi.INFO_DT)
@@ -90,7 +91,7 @@ class Oracle:
 
     def observe(self, env):
         """Observation of the current state of ``env`` (no stepping, no mutation)."""
-        obs = np.zeros(cabi.OBS_DIM, np.float32)
+        obs = np.zeros(self.obs_dim, np.float32)
         info = np.zeros(1, cabi.INFO_DT)
         self.L.orc_observe(self.h, int(env), obs.ctypes.data, info.ctypes.data)
         return obs, info[0]

@@ -139,6 +139,9 @@ static float ray_rect(float ox, float oy, float dx, float dy, const Rect* r) {
   float lo[2] = {px * r->ux + py * r->uy, -px * r->uy + py * r->ux};
   float ld[2] = {dx * r->ux + dy * r->uy, -dx * r->uy + dy * r->ux};
   float half[2] = {r->hl, r->hw};
+  /* Bullet's convex ray cast reports nothing for a shape that contains the ray origin (the ego centre over a line
+   * ghost while it crosses a lane line) */
+  if (fabsf(lo[0]) <= half[0] && fabsf(lo[1]) <= half[1]) return 1.0f;
   float t0 = 0.0f, t1 = 1.0f;
   for (int k = 0; k < 2; ++k) {
     if (fabsf(ld[k]) < 1e-12f) {
@@ -514,6 +517,24 @@ static float heading_diff(const PgdLane* l, const Veh* v) { /* base_vehicle.py:4
   return clipf(c, -1.0f, 1.0f) / 2.0f + 0.5f;
 }
 
+/* One beam of a side / lane-line detector (distance_detector.py:65-94,137-152; cutils.pyx:43-54,103-123): from the
+ * ego centre towards i * 2pi/n + 90 deg + heading, against the line ghosts of the map -- continuous (white / yellow)
+ * always, broken ones only for the lane-line detector.  Brute force over every box of the map. */
+static float detector_beam(const Oracle* o, const PgdMap* m, const Veh* ego, int i, int n, float distance,
+                           int with_broken) {
+  float ang = (float)i * (TWO_PI_F / (float)n) + PI_F / 2 + ego->h;
+  float dx = cosf(ang) * distance, dy = sinf(ang) * distance;
+  float best = 1.0f;
+  for (int b = 0; b < m->n_boxes; ++b) {
+    const PgdBox* box = &o->t.boxes[m->box_off + b];
+    if (!(box->kind == PGD_BOX_WHITE || box->kind == PGD_BOX_YELLOW || (with_broken && box->kind == PGD_BOX_BROKEN)))
+      continue;
+    Rect r = {box->cx, box->cy, box->ux, box->uy, box->hl, box->hw};
+    best = fminf(best, ray_rect(ego->x, ego->y, dx, dy, &r));
+  }
+  return best;
+}
+
 /* After-step bookkeeping + observation + reward + done for the ego.  `fresh` = called from reset. */
 static void post_step(Oracle* o, Env* e, float last_x, float last_y, float last_h, int crash_vehicle, int fresh,
                       float* obs, float* reward, uint8_t* done, PgdInfo* info) {
@@ -566,10 +587,21 @@ static void post_step(Oracle* o, Env* e, float last_x, float last_y, float last_
   if (c->out_of_route_done && (flags & PGD_F_OUT_OF_ROUTE)) out_of_road = 1;
   if (out_of_road) flags |= PGD_F_OUT_OF_ROAD;
 
-  /* ---- observation (obs/state_obs.py:58-170) ---- */
+  /* ---- observation (obs/state_obs.py:58-170) ----
+   * layout: [side detector beams | left, right] + 6 state values + [lane-line detector beams] + 10 navi + 16 + 240 */
   float sp = speed_kmh(ego);
-  obs[0] = clipf(to_left / 18.0f, 0.0f, 1.0f);
-  obs[1] = clipf(to_right / 18.0f, 0.0f, 1.0f);
+  const int n_first = c->n_side > 0 ? c->n_side : 2;
+  float* const obs_row = obs;
+  if (c->n_side > 0) {
+    for (int i = 0; i < c->n_side; ++i) obs[i] = detector_beam(o, m, ego, i, c->n_side, c->side_distance, 0);
+  } else {
+    obs[0] = clipf(to_left / 18.0f, 0.0f, 1.0f);
+    obs[1] = clipf(to_right / 18.0f, 0.0f, 1.0f);
+  }
+  for (int i = 0; i < c->n_lane_line; ++i)
+    obs[n_first + 6 + i] = detector_beam(o, m, ego, i, c->n_lane_line, c->lane_line_distance, 1);
+  float* const navi = obs_row + n_first + 6 + c->n_lane_line;
+  obs = obs_row + n_first - 2; /* obs[2..7] below are the six state values */
   obs[2] = heading_diff(lane_at(o, m, cur_road->first_lane + n_ref - 1), ego);
   obs[3] = clipf((sp + 1.0f) / (MAX_SPEED_KMH + 1.0f), 0.0f, 1.0f);
   obs[4] = clipf((ego->steer / 60.0f + 1.0f) / 2.0f, 0.0f, 1.0f);
@@ -578,8 +610,9 @@ static void post_step(Oracle* o, Env* e, float last_x, float last_y, float last_
   /* yaw rate: arccos(clip(cos(angle between headings), 0, 1)) / 0.1 (state_obs.py:87-94).  arccos is
    * ill-conditioned near 1 in float32, so the identical quantity min(|wrapped heading change|, pi/2) is used. */
   obs[7] = clipf(fminf(fabsf(wrap_to_pi(ego->h - last_h)), PI_F / 2) / 0.1f, 0.0f, 1.0f);
-  navi_info(o, m, ego, cur_road_id, n_ref, obs + 8);
-  navi_info(o, m, ego, route_road(o, ego, ego->ck1), n_ref, obs + 13);
+  navi_info(o, m, ego, cur_road_id, n_ref, navi);
+  navi_info(o, m, ego, route_road(o, ego, ego->ck1), n_ref, navi + 5);
+  obs = navi - 8; /* from here on obs[18..] = neighbours, obs[34..] = lidar, as in the default layout */
   /* 4 nearest vehicles (lidar.py:55-77) */
   {
     int objs[PGD_MAX_SLOTS];
@@ -782,7 +815,7 @@ void orc_step(void* h, int env, const float* action, float* obs, float* reward, 
 void orc_step_range(void* h, int env0, int env1, const float* actions, float* obs, float* reward, uint8_t* done,
                     PgdInfo* info) {
   for (int e = env0; e < env1; ++e)
-    orc_step(h, e, actions + 2 * e, obs + (size_t)PGD_OBS_DIM * e, reward + e, done + e, info + e);
+    orc_step(h, e, actions + 2 * e, obs + (size_t)pgd_obs_dim(&((Oracle*)h)->cfg) * e, reward + e, done + e, info + e);
 }
 
 void orc_get_state(void* h, int env, PgdEnvState* out) {

@@ -185,6 +185,7 @@ __device__ __forceinline__ float ray_rect(float ox, float oy, float dx, float dy
   float px = ox - r.cx, py = oy - r.cy;
   float lo0 = px * r.ux + py * r.uy, lo1 = -px * r.uy + py * r.ux;
   float ld0 = dx * r.ux + dy * r.uy, ld1 = -dx * r.uy + dy * r.ux;
+  if (fabsf(lo0) <= r.hl && fabsf(lo1) <= r.hw) return 1.0f;  // origin inside: Bullet's convex cast reports no hit
   float t0 = 0.0f, t1 = 1.0f;
   if (fabsf(ld0) < 1e-12f) {
     if (fabsf(lo0) > r.hl) return 1.0f;

@@ -158,3 +158,61 @@ def test_lidar_matches_reference_beam_loop():
         hits += int((cloud < 1.0).sum())
     assert hits > 300
     orc.close()
+
+
+def test_static_primitives_match_reference_block_code():
+    """tests/golden/primitives_v0.json.gz: every lane-surface box, line ghost and sidewalk box that the reference's
+    own BaseBlock._add_lane_surface / _add_pgdrive_lanes build (run unmodified, with recording stand-ins for the
+    Bullet classes) for 9 maps.  pgdrive_b200/tables.py must tabulate exactly the same rectangles."""
+    import math
+    from pgdrive_b200 import tables
+    gold = load_golden("primitives_v0.json.gz")
+    kind_of = {"Lane": 0, "White Continuous Line": 1, "Yellow Continuous Line": 2, "Broken Line": 3, "Sidewalk": 4}
+    for s, prims in gold.items():
+        B = tables.build_tables([int(s)]).finish()["boxes"]
+        ref = np.array([[kind_of[p[5]], p[0], p[1], p[3], p[4], abs(math.cos(p[2])), abs(math.sin(p[2]))] for p in prims])
+        mine = np.array([[b["kind"], b["cx"], b["cy"], b["hl"], b["hw"], abs(b["ux"]), abs(b["uy"])] for b in B], float)
+        assert len(ref) == len(mine), s
+        for k in range(5):
+            r, m = ref[ref[:, 0] == k], mine[mine[:, 0] == k]
+            assert len(r) == len(m), (s, k)
+            used = np.zeros(len(m), bool)
+            for row in r:  # one-to-one nearest matching
+                d = np.abs(m[:, 1:] - row[1:]).max(axis=1)
+                d[used] = 1e9
+                j = int(d.argmin())
+                assert d[j] < 1e-4, (s, k, row, m[j])
+                used[j] = True
+
+
+def test_side_and_lane_line_detectors_match_reference_beam_loop():
+    """tests/golden/detectors_v0.json.gz: SideDetector (120 beams, 50 m, continuous lines) and LaneLineDetector
+    (40 beams, 20 m, continuous + broken lines) computed by the reference's beam loop over the line ghosts its own
+    block code built; the oracle's detector beams and their place in the observation vector must agree."""
+    from oracle.oracle import Oracle
+    from pgdrive_b200 import cabi, tables
+    scenes = load_golden("detectors_v0.json.gz")
+    orcs = {}
+    hits = 0
+    for sc in scenes:
+        if sc["seed"] not in orcs:
+            T = tables.build_tables([sc["seed"]]).finish()
+            orcs[sc["seed"]] = Oracle(T, 1, auto_reset=False, n_side=120, side_distance=50.0, n_lane_line=40,
+                                      lane_line_distance=20.0)
+            orcs[sc["seed"]].reset([0], [0])
+        orc = orcs[sc["seed"]]
+        assert orc.obs_dim == 120 + 6 + 40 + 10 + 16 + 240
+        s = np.frombuffer(base64.b64decode(sc["state"]), dtype=cabi.ENV_STATE_DT).copy()
+        orc.set_state(0, s)
+        obs, _ = orc.observe(0)
+        for name, got in (("side", obs[:120]), ("lane_line", obs[126:166])):
+            want = np.array(sc[name])
+            close = np.abs(got - want) < 5e-4
+            for i in np.nonzero(~close)[0]:  # a beam through the 15 cm end of a ghost may differ between f32 and f64
+                nb = [want[(i - 1) % len(want)], want[(i + 1) % len(want)]]
+                assert abs(got[i] - want[i]) < 0.2 and (min(nb) < 1.0), (name, i, got[i], want[i])
+            assert close.mean() > 0.97, (name, close.mean())
+            hits += int((want < 1.0).sum())
+    assert hits > 2000
+    for o in orcs.values():
+        o.close()

@@ -562,6 +562,7 @@ def cmd_lidar(tag, n_scenes=40):
         coordinates (x, -y, z) exactly as cutils_perceive passes them."""
         def __init__(self, boxes):
             self.edges = []
+            self.rects = [(x, y, math.cos(h), math.sin(h), length / 2, width / 2) for x, y, h, length, width in boxes]
             for k, (x, y, h, length, width) in enumerate(boxes):
                 c, s = math.cos(h), math.sin(h)
                 pts = [(x + c * a * length / 2 - s * b * width / 2, y + s * a * length / 2 + c * b * width / 2)
@@ -573,7 +574,12 @@ def cmd_lidar(tag, n_scenes=40):
             p = (start[0], -start[1])
             r = (end[0] - start[0], -(end[1] - start[1]))
             best, node = 1.0, None
+            # Bullet's convex ray cast reports no hit for a shape that contains the ray origin
+            inside = {k for k, (x, y, c, s, hl, hw) in enumerate(self.rects)
+                      if abs((p[0] - x) * c + (p[1] - y) * s) <= hl and abs(-(p[0] - x) * s + (p[1] - y) * c) <= hw}
             for k, a, b in self.edges:
+                if k in inside:
+                    continue
                 sx, sy = b[0] - a[0], b[1] - a[1]
                 den = r[0] * sy - r[1] * sx
                 if den == 0:
@@ -656,3 +662,218 @@ def cmd_digests(seeds, tag):
 
 if __name__ == "__main__" and sys.argv[1] == "digests":
     cmd_digests(list(range(1000, 2000)), "1000_1999")
+
+
+# =================================================================================================
+# side / lane-line detector vectors: the reference's beam loop (cutils.py twin) with the SideDetector /
+# LaneLineDetector conventions (phase offset 90 deg, distance_detector.py:137-152) over an analytic 2-D world made
+# of the line-ghost rectangles that the reference's own block code (component/blocks/base_block.py) builds for the
+# map.  The rectangles are captured from the UNMODIFIED _add_lane_line2bullet / _add_box_body by recording the
+# arguments they pass to the (stubbed) Bullet shape / node calls.
+# =================================================================================================
+def capture_line_boxes(seed, all_kinds=False):
+    """Run the reference's own primitive builders (BaseBlock._add_pgdrive_lanes / _add_lane_surface, unmodified) for
+    every block of the map with recording stand-ins for the Bullet shape / node classes, and return each primitive
+    as (cx, cy, theta, half_length, half_width, name) in PGDrive coordinates."""
+    import math
+    from pgdrive.component.blocks import base_block as bb
+    from pgdrive.constants import BodyName
+    rec = []
+    line_names = (BodyName.White_continuous_line, BodyName.Yellow_continuous_line, BodyName.Broken_line)
+
+    class Shape:
+        def __init__(self, half):
+            self.half = half
+
+    class Node:
+        def __init__(self, name=None, *a, **k):
+            self.name = a[0] if a else name  # BaseRigidBodyNode(lane, BodyName.Lane)
+            self.shape = None
+
+        def addShape(self, shape, *a):
+            self.shape = shape
+
+        def __getattr__(self, k):
+            return lambda *a, **kw: None
+
+    class NP:
+        def __init__(self, node=None):
+            self._node = node
+            self.pos = None
+            self.theta = None
+
+        def node(self):
+            return self._node
+
+        def attachNewNode(self, node):
+            return NP(node if isinstance(node, Node) else Node(node))
+
+        def setPos(self, p):
+            self.pos = p
+
+        def setQuat(self, q):
+            node = self._node
+            self.theta = -2 * math.atan2(q[3], q[0])
+            if isinstance(node, Node) and node.shape is not None:
+                if node.name in line_names:
+                    rec.append((self.pos[0], -self.pos[1], self.theta, node.shape.half[0], node.shape.half[1], node.name))
+                elif node.name == BodyName.Lane and all_kinds:  # BulletBoxShape(length / 2, 0.1, width / 2)
+                    rec.append((self.pos[0], -self.pos[1], self.theta, node.shape.half[0], node.shape.half[2], node.name))
+
+        def setScale(self, sx, sy, sz):
+            if isinstance(self._node, Node) and self._node.name == BodyName.Sidewalk and all_kinds:
+                rec.append((self.pos[0], -self.pos[1], self.theta, sx / 2, sy / 2, self._node.name))
+
+        def __getattr__(self, k):
+            return lambda *a, **kw: None
+
+    names = ("BulletBoxShape", "BulletGhostNode", "BulletRigidBodyNode", "BaseRigidBodyNode", "NodePath", "Vec3",
+             "LQuaternionf", "panda_position")
+    saved = {k: getattr(bb, k) for k in names}
+    bb.BulletBoxShape = lambda v: Shape(v)
+    bb.BulletGhostNode = Node
+    bb.BulletRigidBodyNode = Node
+    bb.BaseRigidBodyNode = Node
+    bb.NodePath = NP
+    bb.Vec3 = lambda *a: tuple(a)
+    bb.LQuaternionf = lambda *a: tuple(a)
+    bb.panda_position = lambda p, z=0.0: (p[0], -p[1], z)
+    try:
+        eng, m = build_map(seed)
+        rec.clear()  # build_map itself ran the patched builders (block search + rebuild); keep one clean pass only
+        for blk in m.blocks:
+            parent = NP(Node("root"))
+            blk.sidewalk_node_path = NP(Node("sidewalks"))
+            blk.lane_node_path = NP(Node("lanes"))
+            blk.lane_vis_node_path = NP(Node("vis"))
+            for _from, to_dict in blk.block_network.graph.items():
+                for _to, lanes in to_dict.items():
+                    if all_kinds:
+                        blk._add_lane_surface(_from, _to, lanes)
+                    for _id, l in enumerate(lanes):
+                        blk._add_pgdrive_lanes(l, _id, l.width_at(0), l.line_color, parent)
+    finally:
+        for k, v in saved.items():
+            setattr(bb, k, v)
+    return rec
+
+
+def cmd_primitives(tag, seeds=(1000, 1003, 1008, 1015, 1021, 1042, 1055, 1077, 1096)):
+    """Every static primitive (lane surfaces, line ghosts, sidewalks) of a few maps as the reference's block code
+    builds them -> tests/golden/primitives_*.json.gz (pins pgdrive_b200/tables.py lane_boxes / surface_boxes)."""
+    out = {}
+    for s in seeds:
+        out[str(s)] = [[float(x) for x in b[:5]] + [str(b[5])] for b in capture_line_boxes(s, all_kinds=True)]
+        print("seed", s, "primitives", len(out[str(s)]))
+    path = os.path.join(GOLD, "primitives_%s.json.gz" % tag)
+    with gzip.open(path, "wt") as f:
+        json.dump(out, f)
+    print("wrote", path, os.path.getsize(path))
+
+
+def cmd_detectors(tag, seeds=(1000, 1003, 1015, 1042), n_poses=24):
+    import base64
+    import math
+    sys.path.insert(0, os.path.dirname(HERE))
+    from oracle.oracle import Oracle
+    from pgdrive_b200 import cabi, tables as ptables
+    from pgdrive.utils.cutils import _get_fake_cutils
+    from pgdrive.constants import BodyName
+    fake = _get_fake_cutils()
+
+    class Hit:
+        def __init__(self, node, frac):
+            self.node, self.frac = node, frac
+
+        def getNode(self):
+            return self.node
+
+        def getHitFraction(self):
+            return self.frac
+
+        def hasHit(self):
+            return self.node is not None
+
+        def getHitPos(self):
+            return (0, 0, 0)
+
+    class World2D:
+        def __init__(self, boxes):
+            self.edges = []
+            self.rects = [(x, y, math.cos(h), math.sin(h), hl, hw) for x, y, h, hl, hw in boxes]
+            for k, (x, y, h, hl, hw) in enumerate(boxes):
+                c, s = math.cos(h), math.sin(h)
+                pts = [(x + c * a * hl - s * b * hw, y + s * a * hl + c * b * hw)
+                       for a, b in ((1, 1), (1, -1), (-1, -1), (-1, 1))]
+                for i in range(4):
+                    self.edges.append((k, pts[i], pts[(i + 1) % 4]))
+
+        def rayTestClosest(self, start, end, mask):
+            p = (start[0], -start[1])
+            r = (end[0] - start[0], -(end[1] - start[1]))
+            best, node = 1.0, None
+            # Bullet's convex ray cast reports no hit for a shape that contains the ray origin
+            inside = {k for k, (x, y, c, s, hl, hw) in enumerate(self.rects)
+                      if abs((p[0] - x) * c + (p[1] - y) * s) <= hl and abs(-(p[0] - x) * s + (p[1] - y) * c) <= hw}
+            for k, a, b in self.edges:
+                if k in inside:
+                    continue
+                sx, sy = b[0] - a[0], b[1] - a[1]
+                den = r[0] * sy - r[1] * sx
+                if den == 0:
+                    continue
+                qx, qy = a[0] - p[0], a[1] - p[1]
+                t = (qx * sy - qy * sx) / den
+                u = (qx * r[1] - qy * r[0]) / den
+                if 0.0 <= t <= 1.0 and 0.0 <= u <= 1.0 and t < best:
+                    best, node = t, k
+            return Hit(node, best)
+
+    out = []
+    for seed in seeds:
+        boxes = capture_line_boxes(seed)
+        cont = [b[:5] for b in boxes if b[5] != BodyName.Broken_line]
+        every = [b[:5] for b in boxes]
+        T = ptables.build_tables([seed]).finish()
+        # the table must hold the same ghosts as the reference built (multiset of rounded rectangles)
+        mine = T["boxes"][T["boxes"]["kind"] > 0]
+        mine = mine[mine["kind"] < 4]
+        assert len(mine) == len(boxes), (seed, len(mine), len(boxes))
+        orc = Oracle(T, 1, auto_reset=False)
+        orc.reset([0], [0])
+        rs = np.random.RandomState(seed)
+        lanes = T["lanes"]
+        for k in range(n_poses):
+            ln = lanes[rs.randint(len(lanes))]
+            s = orc.get_state(0)
+            v = s["veh"][0]
+            t = rs.uniform(0.1, 0.9)
+            if ln["kind"] == 0:
+                x = ln["sx"] + t * (ln["ex"] - ln["sx"]) + rs.uniform(-1, 1)
+                y = ln["sy"] + t * (ln["ey"] - ln["sy"]) + rs.uniform(-1, 1)
+            else:
+                x, y = ln["sx"] + rs.uniform(-2, 2), ln["sy"] + rs.uniform(-2, 2)
+            v[0]["x"], v[0]["y"], v[0]["heading"] = x, y, rs.uniform(-np.pi, np.pi)
+            s["veh"][0] = v
+            ex, ey, eh = float(v[0]["x"]), float(v[0]["y"]), float(v[0]["heading"])
+            rec = dict(seed=seed, state=base64.b64encode(s.tobytes()).decode())
+            for name, n, dist, world in (("side", 120, 50.0, World2D(cont)), ("lane_line", 40, 20.0, World2D(every))):
+                rng_ = np.arange(0, n) * (2 * np.pi / n) + np.deg2rad(90)  # set_start_phase_offset(90)
+                cloud, _, _ = fake.cutils_perceive(np.ones(n), None, None, rng_, dist, eh, ex, ey, n, 0.2, world, set(),
+                                                   False, False, 0, 0, 0)
+                rec[name] = [float(c) for c in cloud]
+            out.append(rec)
+        orc.close()
+        print("seed", seed, "ghosts", len(boxes), "continuous", len(cont))
+    path = os.path.join(GOLD, "detectors_%s.json.gz" % tag)
+    with gzip.open(path, "wt") as f:
+        json.dump(out, f)
+    print("wrote", path, os.path.getsize(path))
+
+
+if __name__ == "__main__" and sys.argv[1] == "detectors":
+    cmd_detectors("v0")
+
+
+if __name__ == "__main__" and sys.argv[1] == "primitives":
+    cmd_primitives("v0")
