@@ -219,8 +219,14 @@ def check_supported(cfg):
         raise NotImplementedError("lidar must be 240 beams x 50 m with 4 neighbours")
     if lid["gaussian_noise"] or lid["dropout_prob"]:
         raise NotImplementedError("lidar noise / dropout are not supported")
-    if vc["side_detector"]["num_lasers"] or vc["lane_line_detector"]["num_lasers"]:
-        raise NotImplementedError("side / lane-line detectors are not supported")
+    for name in ("side_detector", "lane_line_detector"):
+        det = vc[name]
+        if not 0 <= det["num_lasers"] <= 240:
+            raise NotImplementedError("%s supports 0..240 lasers" % name)
+        if det["gaussian_noise"] or det["dropout_prob"]:
+            raise NotImplementedError("%s noise / dropout are not supported" % name)
+        if det["num_lasers"] and det["distance"] <= 0:
+            raise ValueError("%s distance must be positive" % name)
     if vc["increment_steering"] or vc["enable_reverse"] or vc["extra_action_dim"]:
         raise NotImplementedError("increment_steering / enable_reverse / extra_action_dim are not supported")
     if cfg["decision_repeat"] < 1:

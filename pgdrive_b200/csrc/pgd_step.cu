@@ -56,6 +56,7 @@
 #define MIN_CTAS_PER_SM 4
 #endif
 #define DONE_PENDING_RESET 2
+#define PGD_OBS_CAP_DET (2 * PGD_MAX_DETECTOR_BEAMS + 6 + 10 + 16 + PGD_LIDAR_BEAMS)  /* 752 */
 
 struct DevTables {
   const PgdMap* maps;
@@ -222,7 +223,7 @@ __device__ __forceinline__ float pid(float& p_err, float& i_err, float kp, float
 }
 
 // Per-environment shared mirror of what the all-pairs phases need from every slot.
-template <int V>
+template <int V, int OBS_CAP>
 struct EnvShared {
   float x[V], y[V], h[V], v[V];    // pose at the start of the step (IDM) / current (contacts, lidar)
   float ux[V], uy[V];              // heading unit vector
@@ -233,7 +234,7 @@ struct EnvShared {
   float olong[V];                  // longitudinal coordinate of each vehicle on its own lane (start of step)
   int blo[V], bn[V];               // lidar: first beam index and beam count each chassis can intersect
   int croad[V], nroad[V];          // localisation: current / next route road of each moving vehicle
-  float2 obs2[PGD_OBS_DIM / 2];    // the observation row is assembled here and streamed out with 8-byte stores
+  float2 obs2[OBS_CAP / 2];        // the observation row is assembled here and streamed out with 8-byte stores
   int qlane[8];                    // ego queries: lane ids
   float qlon[8], qlat[8];          // ego queries: Frenet results
   float d2[V];                     // squared centre distance to the ego (neighbour ranking)
@@ -249,20 +250,20 @@ struct Sub {  // what one physics sub-step needs, hoisted out of the sub-step lo
 };
 
 // ------------------------------------------------------------------------------------------------------------------
-template <int V>
+template <int V, int OBS_CAP>
 __global__ void __launch_bounds__(CTA_THREADS, MIN_CTAS_PER_SM)
 pgd_step_kernel(DevTables T, DevState S, PgdConfig cfg, int mode, int env_begin, int env_end,
                 const float2* __restrict__ actions,
                 float* __restrict__ obs, float* __restrict__ reward, uint8_t* __restrict__ done,
                 PgdInfo* __restrict__ info) {
   constexpr int ENVS_PER_CTA = CTA_THREADS / V;
-  __shared__ EnvShared<V> sh_all[ENVS_PER_CTA];
+  __shared__ EnvShared<V, OBS_CAP> sh_all[ENVS_PER_CTA];
   const int slot = threadIdx.x % V;
   const int env_in_cta = threadIdx.x / V;
   const int env_raw = env_begin + blockIdx.x * ENVS_PER_CTA + env_in_cta;  // this launch covers [env_begin, env_end)
   const bool env_valid = env_raw < env_end;
   const int env = env_valid ? env_raw : env_end - 1;  // clamp: surplus threads shadow the last env, no stores
-  EnvShared<V>& sh = sh_all[env_in_cta];
+  EnvShared<V, OBS_CAP>& sh = sh_all[env_in_cta];
   const unsigned lane_id = threadIdx.x & 31;
   const unsigned group_mask = (V == 32) ? 0xffffffffu : (0xffffu << (lane_id & 16));
   const int gi = env * V + slot;
@@ -690,7 +691,14 @@ pgd_step_kernel(DevTables T, DevState S, PgdConfig cfg, int mode, int env_begin,
 
   PHASE_SYNC();
   // ---- phase F: observation, reward, done -----------------------------------------------------------------------
-  float* ob = reinterpret_cast<float*>(sh.obs2);  // staged row; copied to obs[env] at the end of phase F
+  // Staged row; copied to obs[env] at the end of phase F.  Layout (obs/state_obs.py): [side beams | left, right],
+  // 6 state values, [lane-line beams], 10 navi, 16 neighbours, 240 lidar.  `ob` is positioned so that the indices of
+  // the detector-less layout (state 2..7, navi 8..17, neighbours 18..33, lidar 34..) address the tail of the row.
+  float* const row = reinterpret_cast<float*>(sh.obs2);
+  const int n_first = cfg.n_side > 0 ? cfg.n_side : 2;
+  const int obs_dim = n_first + 6 + cfg.n_lane_line + 10 + 16 + PGD_LIDAR_BEAMS;
+  float* const st = row + n_first - 2;                   // st[2..7]  = state values
+  float* const ob = row + n_first + cfg.n_lane_line - 2;  // ob[8..]   = navi, neighbours, lidar
   // lidar: beam i = slot + V * k.  Each chassis first publishes the (conservative) arc of beams that can reach it:
   // it lies inside the disc of radius half-diagonal around its centre, so only beams within asin(hd / d) of its
   // bearing and only chassis closer than 50 m + hd matter.  The cull never changes a result (the reference's own
@@ -746,6 +754,44 @@ pgd_step_kernel(DevTables T, DevState S, PgdConfig cfg, int mode, int env_begin,
       }
     }
   }
+  // side / lane-line detectors (distance_detector.py:137-152): ray fans against the line ghosts of the map.  A beam
+  // looks up the bucket of a point every 8 m along itself; buckets list every box within 4 m of them, so each ghost
+  // the beam can touch is found in at least one of them (found twice is harmless: the result is a minimum).
+  if (OBS_CAP > PGD_OBS_DIM && !skip) {
+    const int n_rays = cfg.n_side + cfg.n_lane_line;
+    const int32_t* ent = T.cell_entries + mp.entry_off;
+    for (int rI = slot; rI < n_rays; rI += V) {
+      const bool side = rI < cfg.n_side;
+      const int i = side ? rI : rI - cfg.n_side;
+      const int n = side ? cfg.n_side : cfg.n_lane_line;
+      const float dist = side ? cfg.side_distance : cfg.lane_line_distance;
+      const float ang = (float)i * (TWO_PI_F / (float)n) + PI_F / 2 + eh;
+      float sn, cs;
+      SINCOS(ang, sn, cs);
+      const float dx = cs * dist, dy = sn * dist;
+      float best = 1.0f;
+      for (float sd = 4.0f; sd - 4.0f < dist; sd += 8.0f) {
+        if (best * dist < sd - 4.0f) break;  // already hit something nearer than what the remaining buckets cover
+        const float px = ex_ + cs * sd, py = ey_ + sn * sd;
+        const int cx = (int)floorf((px - mp.x0) * mp.inv_cell), cy = (int)floorf((py - mp.y0) * mp.inv_cell);
+        if (cx < 0 || cy < 0 || cx >= mp.nx || cy >= mp.ny) continue;
+        const int cell = mp.cell_off + cy * mp.nx + cx;
+        const int b0 = __ldg(&T.cell_start[cell]), b1 = __ldg(&T.cell_start[cell + 1]);
+        for (int k = b0; k < b1; ++k) {
+          const int b = __ldg(&ent[k]);
+          const float4 g1 = __ldg(reinterpret_cast<const float4*>(boxes + b) + 1);  // hl, hw, kind, lane
+          const int kind = __float_as_int(g1.z);
+          if (!(kind == PGD_BOX_WHITE || kind == PGD_BOX_YELLOW || (!side && kind == PGD_BOX_BROKEN))) continue;
+          const float4 g0 = __ldg(reinterpret_cast<const float4*>(boxes + b));
+          const Rect r = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y};
+          best = fminf(best, ray_rect(ex_, ey_, dx, dy, r));
+        }
+      }
+      if (side) row[i] = best;
+      else row[n_first + 6 + i] = best;
+    }
+  }
+
   PHASE_SYNC();
   // the 4 nearest vehicles inside the 50 m cylinder (lidar.py:55-77): every chassis ranks itself by centre distance
   // (ties -> lower slot, like a stable selection) and the 4 best write their own features
@@ -847,7 +893,7 @@ pgd_step_kernel(DevTables T, DevState S, PgdConfig cfg, int mode, int env_begin,
       else if (l.dir < 0.0f) { lx = ex_ - l.ax; ly = ey_ - l.ay; }
       else { lx = l.ax - ex_; ly = l.ay - ey_; }
       const float ln = sqrtf(lx * lx + ly * ly);
-      ob[2] = ln > 0.0f ? clipf((eux * lx + euy * ly) / ln, -1.0f, 1.0f) / 2.0f + 0.5f : 0.0f;
+      st[2] = ln > 0.0f ? clipf((eux * lx + euy * ly) / ln, -1.0f, 1.0f) / 2.0f + 0.5f : 0.0f;
     }
   }
   __syncwarp(group_mask);
@@ -908,9 +954,9 @@ pgd_step_kernel(DevTables T, DevState S, PgdConfig cfg, int mode, int env_begin,
       flags |= PGD_F_WAS_RESET;
     }
     if (!skip) {
-      ob[0] = o8[0]; ob[1] = o8[1];
+      if (cfg.n_side <= 0) { row[0] = o8[0]; row[1] = o8[1]; }
 #pragma unroll
-      for (int k = 3; k < 8; ++k) ob[k] = o8[k];
+      for (int k = 3; k < 8; ++k) st[k] = o8[k];
       if (mode == 0) {
         reward[env] = r;
         done[env] = (uint8_t)is_done;
@@ -932,9 +978,14 @@ pgd_step_kernel(DevTables T, DevState S, PgdConfig cfg, int mode, int env_begin,
   // (full 32 B sectors whether the destination is local HBM or a peer-mapped gather buffer on another GPU)
   __syncwarp(group_mask);
   if (!skip) {
-    float2* dst = reinterpret_cast<float2*>(obs + (size_t)env * PGD_OBS_DIM);
+    if ((obs_dim & 1) == 0) {
+      float2* dst = reinterpret_cast<float2*>(obs + (size_t)env * obs_dim);
 #pragma unroll 3
-    for (int k = slot; k < PGD_OBS_DIM / 2; k += V) dst[k] = sh.obs2[k];
+      for (int k = slot; k < obs_dim / 2; k += V) dst[k] = sh.obs2[k];
+    } else {  // odd row length: rows are only 4-byte aligned
+      float* dst = obs + (size_t)env * obs_dim;
+      for (int k = slot; k < obs_dim; k += V) dst[k] = row[k];
+    }
   }
 
   // ---- phase G: store --------------------------------------------------------------------------------------------
@@ -1011,6 +1062,9 @@ extern "C" int pgd_create(const PgdConfig* cfg, int device, PgdHandle** out) {
   if (!cfg || !out) return fail(-1, "pgd_create: null argument");
   if (cfg->num_envs <= 0) return fail(-1, "pgd_create: num_envs must be positive");
   if (cfg->num_slots != 16 && cfg->num_slots != 32) return fail(-1, "pgd_create: num_slots must be 16 or 32");
+  if (cfg->n_side < 0 || cfg->n_side > PGD_MAX_DETECTOR_BEAMS || cfg->n_lane_line < 0 ||
+      cfg->n_lane_line > PGD_MAX_DETECTOR_BEAMS)
+    return fail(-1, "pgd_create: detector beam counts must be in [0, 240]");
   CU(cudaSetDevice(device));
   PgdHandle* h = new PgdHandle();
   memset(h, 0, sizeof(*h));
@@ -1099,12 +1153,15 @@ static int launch_step(PgdHandle* h, int mode, int env_begin, int env_end, const
   const int envs_per_cta = CTA_THREADS / V;
   const int grid = (env_end - env_begin + envs_per_cta - 1) / envs_per_cta;
   if (h->timing && mode == 0) cudaEventRecord(h->ev0, st);
-  if (V == 16)
-    pgd_step_kernel<16><<<grid, CTA_THREADS, 0, st>>>(h->T, h->S, h->cfg, mode, env_begin, env_end,
-                                                      (const float2*)actions, obs, reward, done, info);
-  else
-    pgd_step_kernel<32><<<grid, CTA_THREADS, 0, st>>>(h->T, h->S, h->cfg, mode, env_begin, env_end,
-                                                      (const float2*)actions, obs, reward, done, info);
+  const bool det = h->cfg.n_side > 0 || h->cfg.n_lane_line > 0;  // detectors need the large staged row
+#define PGD_LAUNCH(VV, CAP)                                                                                        \
+  pgd_step_kernel<VV, CAP><<<grid, CTA_THREADS, 0, st>>>(h->T, h->S, h->cfg, mode, env_begin, env_end,            \
+                                                          (const float2*)actions, obs, reward, done, info)
+  if (V == 16 && !det) PGD_LAUNCH(16, PGD_OBS_DIM);
+  else if (V == 32 && !det) PGD_LAUNCH(32, PGD_OBS_DIM);
+  else if (V == 16) PGD_LAUNCH(16, PGD_OBS_CAP_DET);
+  else PGD_LAUNCH(32, PGD_OBS_CAP_DET);
+#undef PGD_LAUNCH
   if (h->timing && mode == 0) cudaEventRecord(h->ev1, st);
   h->launches++;
   CU(cudaGetLastError());
@@ -1151,12 +1208,13 @@ static int ensure_staging(PgdHandle* h) {
   if (h->h_act) return 0;
   const size_t n = (size_t)h->cfg.num_envs;
   CU(cudaMallocHost(&h->h_act, n * 8));
-  CU(cudaMallocHost(&h->h_obs, n * PGD_OBS_DIM * 4));
+  const size_t od = (size_t)pgd_obs_dim(&h->cfg);
+  CU(cudaMallocHost(&h->h_obs, n * od * 4));
   CU(cudaMallocHost(&h->h_rew, n * 4));
   CU(cudaMallocHost(&h->h_done, n));
   CU(cudaMallocHost(&h->h_info, n * sizeof(PgdInfo)));
   CU(cudaMalloc(&h->d_act, n * 8));
-  CU(cudaMalloc(&h->d_obs, n * PGD_OBS_DIM * 4));
+  CU(cudaMalloc(&h->d_obs, n * od * 4));
   CU(cudaMalloc(&h->d_rew, n * 4));
   CU(cudaMalloc(&h->d_done, n));
   CU(cudaMalloc(&h->d_info, n * sizeof(PgdInfo)));
@@ -1180,6 +1238,7 @@ extern "C" int pgd_step_host(PgdHandle* h, const float* actions, float* obs, flo
   int rc = ensure_staging(h);
   if (rc) return rc;
   const size_t n = (size_t)h->cfg.num_envs;
+  const size_t od = (size_t)pgd_obs_dim(&h->cfg);
   cudaStream_t st = h->own_stream;
   // Page-locked caller buffers are DMA targets themselves; pageable ones go through the handle's pinned staging.
   const bool direct = is_pinned(obs) && is_pinned(reward) && is_pinned(done) && (!info || is_pinned(info));
@@ -1203,7 +1262,7 @@ extern "C" int pgd_step_host(PgdHandle* h, const float* actions, float* obs, flo
     rc = launch_step(h, 0, b, e, h->d_act, h->d_obs, h->d_rew, h->d_done, info ? h->d_info : nullptr, cs);
     if (rc) return rc;
     const size_t m = (size_t)(e - b);
-    CU(cudaMemcpyAsync(o_dst + (size_t)b * PGD_OBS_DIM, h->d_obs + (size_t)b * PGD_OBS_DIM, m * PGD_OBS_DIM * 4,
+    CU(cudaMemcpyAsync(o_dst + (size_t)b * od, h->d_obs + (size_t)b * od, m * od * 4,
                        cudaMemcpyDeviceToHost, cs));
     CU(cudaMemcpyAsync(r_dst + b, h->d_rew + b, m * 4, cudaMemcpyDeviceToHost, cs));
     CU(cudaMemcpyAsync(d_dst + b, h->d_done + b, m, cudaMemcpyDeviceToHost, cs));
@@ -1212,7 +1271,7 @@ extern "C" int pgd_step_host(PgdHandle* h, const float* actions, float* obs, flo
   CU(cudaStreamSynchronize(st));
   if (chunks > 1) CU(cudaStreamSynchronize(h->own_stream2));
   if (!direct) {
-    memcpy(obs, h->h_obs, n * PGD_OBS_DIM * 4);
+    memcpy(obs, h->h_obs, n * od * 4);
     memcpy(reward, h->h_rew, n * 4);
     memcpy(done, h->h_done, n);
     if (info) memcpy(info, h->h_info, n * sizeof(PgdInfo));

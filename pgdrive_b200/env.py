@@ -180,8 +180,13 @@ class _Engine:
             num_envs, num_slots, cfg["decision_repeat"], horizon, cfg["physics_world_step_size"],
             cfg["success_reward"], cfg["out_of_road_penalty"], cfg["crash_vehicle_penalty"], cfg["driving_reward"],
             cfg["speed_reward"], cfg["out_of_road_cost"], cfg["crash_vehicle_cost"], cfg["use_lateral"],
-            cfg["out_of_route_done"], auto_reset
+            cfg["out_of_route_done"], auto_reset,
+            n_side=cfg["vehicle_config"]["side_detector"]["num_lasers"],
+            side_distance=cfg["vehicle_config"]["side_detector"]["distance"],
+            n_lane_line=cfg["vehicle_config"]["lane_line_detector"]["num_lasers"],
+            lane_line_distance=cfg["vehicle_config"]["lane_line_detector"]["distance"]
         )
+        self.obs_dim = cabi.obs_dim(self.pcfg)
         self.h = C.c_void_p()
         cabi.check(self.lib, self.lib.pgd_create(C.byref(self.pcfg), device, C.byref(self.h)))
         self.num_envs, self.num_slots = num_envs, num_slots
@@ -236,20 +241,21 @@ class VecPGDriveEnv:
         torch = self.engine.torch
         dev = self.engine.device
         n = self.num_envs
-        self.obs = obs_out if obs_out is not None else torch.empty((n, cabi.OBS_DIM), dtype=torch.float32, device=dev)
+        self.obs_dim = self.engine.obs_dim  # 274 unless side / lane-line detectors are on (state_obs.py:108-130)
+        self.obs = obs_out if obs_out is not None else torch.empty((n, self.obs_dim), dtype=torch.float32, device=dev)
         self.reward = torch.zeros(n, dtype=torch.float32, device=dev)
         self.done = torch.zeros(n, dtype=torch.uint8, device=dev)
         self.info = torch.zeros((n, cabi.INFO_DT.itemsize // 4), dtype=torch.int32, device=dev)
         # host-path results live in page-locked memory so that pgd_step_host can DMA straight into them
         self._pinned = [
-            torch.empty((n, cabi.OBS_DIM), dtype=torch.float32, pin_memory=True),
+            torch.empty((n, self.obs_dim), dtype=torch.float32, pin_memory=True),
             torch.empty(n, dtype=torch.float32, pin_memory=True),
             torch.empty(n, dtype=torch.uint8, pin_memory=True),
             torch.empty((n, cabi.INFO_DT.itemsize // 4), dtype=torch.int32, pin_memory=True),
         ]
         self._h_obs, self._h_reward, self._h_done = [t.numpy() for t in self._pinned[:3]]
         self._h_info = self._pinned[3].numpy().view(cabi.INFO_DT).reshape(n)
-        self.observation_space = Box(-0.0, 1.0, shape=(cabi.OBS_DIM, ), dtype=np.float32)
+        self.observation_space = Box(-0.0, 1.0, shape=(self.obs_dim, ), dtype=np.float32)
         self.action_space = Box(-1.0, 1.0, shape=(2, ), dtype=np.float32)
         self.env_seeds = np.array([self.start_seed + i % self.env_num for i in range(n)], dtype=np.int64)
 
@@ -299,7 +305,7 @@ class VecPGDriveEnv:
             obs, reward, done = out if out is not None else (self.obs, self.reward, self.done)
             if out is not None:
                 n = self.num_envs
-                ok = (tuple(obs.shape) == (n, cabi.OBS_DIM) and obs.dtype == torch.float32 and obs.is_contiguous()
+                ok = (tuple(obs.shape) == (n, self.obs_dim) and obs.dtype == torch.float32 and obs.is_contiguous()
                       and tuple(reward.shape) == (n, ) and reward.dtype == torch.float32 and reward.is_contiguous()
                       and tuple(done.shape) == (n, ) and done.dtype == torch.uint8 and done.is_contiguous()
                       and obs.device == reward.device == done.device == e.device)
@@ -369,7 +375,8 @@ class PGDriveEnv:
         self.map_config = parse_map_config(self.config)
         vc = self.config["vehicle_config"]
         self._spawn = (tuple(vc["spawn_lane_index"]), float(vc["spawn_longitude"]), float(vc["spawn_lateral"]))
-        self.observation_space = Box(-0.0, 1.0, shape=(cabi.OBS_DIM, ), dtype=np.float32)
+        self.obs_dim = (vc["side_detector"]["num_lasers"] or 2) + 6 + vc["lane_line_detector"]["num_lasers"] + 266
+        self.observation_space = Box(-0.0, 1.0, shape=(self.obs_dim, ), dtype=np.float32)
         self.action_space = Box(-1.0, 1.0, shape=(2, ), dtype=np.float32)
         self._parts, self._episode_of_seed = [], {}
         self._stored = None
@@ -400,7 +407,7 @@ class PGDriveEnv:
             self._engine = _Engine(self.config, 1, slots, int(os.environ.get("PGDRIVE_B200_DEVICE", 0)), False)
             torch = self._engine.torch
             dev = self._engine.device
-            self._obs = torch.empty((1, cabi.OBS_DIM), dtype=torch.float32, device=dev)
+            self._obs = torch.empty((1, self.obs_dim), dtype=torch.float32, device=dev)
             self._reward = torch.zeros(1, dtype=torch.float32, device=dev)
             self._done = torch.zeros(1, dtype=torch.uint8, device=dev)
             self._info = torch.zeros((1, cabi.INFO_DT.itemsize // 4), dtype=torch.int32, device=dev)

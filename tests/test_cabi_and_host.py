@@ -171,7 +171,8 @@ def test_vec_env_rejects_unsupported_options():
     from pgdrive_b200 import VecPGDriveEnv
     for cfg in (dict(traffic_mode="respawn"), dict(random_traffic=True), dict(num_agents=2),
                 dict(vehicle_config=dict(lidar=dict(num_lasers=120))),
-                dict(vehicle_config=dict(side_detector=dict(num_lasers=8)))):
+                dict(vehicle_config=dict(side_detector=dict(num_lasers=500))),
+                dict(vehicle_config=dict(lane_line_detector=dict(num_lasers=4, gaussian_noise=0.1)))):
         with pytest.raises(NotImplementedError):
             VecPGDriveEnv(cfg)
     with pytest.raises(KeyError):

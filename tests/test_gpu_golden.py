@@ -75,3 +75,36 @@ def test_lidar_fixture_through_the_cuda_path():
             assert (min(nb) < 1.0) != (max(nb) < 1.0) or abs(got[i] - cloud[i]) < 5e-3, (i, got[i], cloud[i])
         assert close.mean() > 0.995
     env.close()
+
+
+def test_detector_fixture_through_the_cuda_path():
+    """tests/golden/detectors_v0.json.gz (reference beam loop over reference-built line ghosts) vs the kernel."""
+    import torch
+    from pgdrive_b200 import VecPGDriveEnv, cabi, tables
+    scenes = load_golden("detectors_v0.json.gz")
+    envs = {}
+    zero = torch.zeros((1, 2), dtype=torch.float32, device="cuda")
+    for sc in scenes:
+        seed = sc["seed"]
+        if seed not in envs:
+            T = tables.build_tables([seed]).finish()
+            envs[seed] = VecPGDriveEnv(
+                dict(start_seed=seed, environment_num=1, num_envs=1, auto_reset=False,
+                     vehicle_config=dict(side_detector=dict(num_lasers=120, distance=50.0),
+                                         lane_line_detector=dict(num_lasers=40, distance=20.0))), tables_dict=T)
+            envs[seed].reset()
+        env = envs[seed]
+        s = np.frombuffer(base64.b64decode(sc["state"]), dtype=cabi.ENV_STATE_DT).copy()
+        s["veh"]["airborne"] = 5
+        env.set_state(0, s)
+        obs = env.step(zero)[0].cpu().numpy()[0]
+        assert obs.shape == (120 + 6 + 40 + 266, )
+        for name, got in (("side", obs[:120]), ("lane_line", obs[126:166])):
+            want = np.array(sc[name])
+            close = np.abs(got - want) < 5e-4
+            for i in np.nonzero(~close)[0]:
+                nb = [want[(i - 1) % len(want)], want[(i + 1) % len(want)]]
+                assert abs(got[i] - want[i]) < 0.2 and min(nb) < 1.0, (name, i, got[i], want[i])
+            assert close.mean() > 0.97
+    for e in envs.values():
+        e.close()

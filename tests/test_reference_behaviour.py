@@ -156,3 +156,27 @@ def test_lane_following_for_2000_steps():
         assert steps_alive == 2000
     finally:
         env.close()
+
+
+def test_out_of_road_side_detector():
+    """test_functionality/test_out_of_road.py:7-36: drifting off an 11-block straight road, the side detector's
+    nearest reading at the moment of `done` is below vehicle-diagonal / range."""
+    import math
+    for steering in (-0.01, 0.01):
+        for distance in (10, 50, 100):
+            env = _env(dict(map="SSSSSSSSSSS",
+                            vehicle_config=dict(side_detector=dict(num_lasers=120, distance=distance))))
+            try:
+                obs = env.reset()
+                assert obs.shape == (120 + 6 + 266, )
+                tolerance = math.sqrt(1.852**2 + 4.51**2) / distance
+                for _ in range(4000):
+                    o, r, d, i = env.step([steering, 1])
+                    if d:
+                        assert i["out_of_road"] or i["crash_vehicle"]
+                        if i["out_of_road"]:
+                            assert min(o[:120]) < tolerance, (min(o[:120]), tolerance)
+                        break
+                assert d
+            finally:
+                env.close()
