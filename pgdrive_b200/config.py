@@ -202,7 +202,7 @@ def default_config():
 # value and rejected otherwise, so that a config that silently changed behaviour cannot slip through.
 UNSUPPORTED_IF_CHANGED = {
     "num_agents": 1, "is_multi_agent": False, "random_agent_model": False, "IDM_agent": False,
-    "discrete_action": False, "use_render": False, "manual_control": False, "random_lane_width": False,
+    "use_render": False, "manual_control": False, "random_lane_width": False,
     "random_lane_num": False, "use_topdown": False, "offscreen_render": False, "traffic_mode": "trigger",
     "random_traffic": False, "accident_prob": 0., "auto_termination": False, "gaussian_noise": 0.0,
     "dropout_prob": 0.0, "record_episode": False,

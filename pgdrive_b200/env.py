@@ -19,7 +19,7 @@ import numpy as np
 
 from . import cabi, episode, mapgen, tables
 from .config import ENGINE_CONFIG, Config, check_supported, default_config
-from .spaces import Box
+from .spaces import Box, MultiDiscrete
 
 ENVIRONMENTS = {  # /root/reference/pgdrive/register.py:7-40
     "PGDrive-test-v0": dict(start_seed=0, environment_num=200),
@@ -53,6 +53,26 @@ def parse_map_config(cfg):
     mc["type"] = "block_num" if isinstance(easy, int) else "block_sequence"
     mc["config"] = easy
     return mc
+
+
+def make_action_space(cfg):
+    """base_vehicle.py:721-727."""
+    if cfg["discrete_action"]:
+        return MultiDiscrete([cfg["discrete_steering_dim"], cfg["discrete_throttle_dim"]])
+    return Box(-1.0, 1.0, shape=(2, ), dtype=np.float32)
+
+
+def discrete_to_continuous(actions, cfg):
+    """EnvInputPolicy.act + convert_to_continuous_action (policy/env_input_policy.py:17-31), literally: the index is
+    clipped to [-1, 1] BEFORE it is scaled, so every index >= 1 maps to ``unit - 1``.  Works on numpy arrays and
+    torch tensors alike."""
+    su = 2.0 / (cfg["discrete_steering_dim"] - 1)
+    tu = 2.0 / (cfg["discrete_throttle_dim"] - 1)
+    if isinstance(actions, np.ndarray) or not hasattr(actions, "clamp"):
+        a = np.clip(np.asarray(actions, dtype=np.float32), -1.0, 1.0)
+        return np.stack([a[..., 0] * su - 1.0, a[..., 1] * tu - 1.0], axis=-1).astype(np.float32)
+    a = actions.float().clamp(-1.0, 1.0)
+    return (a * a.new_tensor([su, tu]) - 1.0).contiguous()
 
 
 def _seed_tables(args):
@@ -256,7 +276,7 @@ class VecPGDriveEnv:
         self._h_obs, self._h_reward, self._h_done = [t.numpy() for t in self._pinned[:3]]
         self._h_info = self._pinned[3].numpy().view(cabi.INFO_DT).reshape(n)
         self.observation_space = Box(-0.0, 1.0, shape=(self.obs_dim, ), dtype=np.float32)
-        self.action_space = Box(-1.0, 1.0, shape=(2, ), dtype=np.float32)
+        self.action_space = make_action_space(cfg)
         self.env_seeds = np.array([self.start_seed + i % self.env_num for i in range(n)], dtype=np.int64)
 
     # -- reset / step ------------------------------------------------------------------------------
@@ -298,6 +318,8 @@ class VecPGDriveEnv:
         rank's rows of an all-gather buffer."""
         e = self.engine
         torch = e.torch
+        if self.config["discrete_action"]:
+            actions = discrete_to_continuous(actions, self.config)
         if isinstance(actions, torch.Tensor):
             if actions.device != e.device or actions.dtype != torch.float32 or tuple(actions.shape) != (self.num_envs, 2):
                 raise ValueError("actions must be a float32 [num_envs, 2] tensor on %s" % e.device)
@@ -377,7 +399,7 @@ class PGDriveEnv:
         self._spawn = (tuple(vc["spawn_lane_index"]), float(vc["spawn_longitude"]), float(vc["spawn_lateral"]))
         self.obs_dim = (vc["side_detector"]["num_lasers"] or 2) + 6 + vc["lane_line_detector"]["num_lasers"] + 266
         self.observation_space = Box(-0.0, 1.0, shape=(self.obs_dim, ), dtype=np.float32)
-        self.action_space = Box(-1.0, 1.0, shape=(2, ), dtype=np.float32)
+        self.action_space = make_action_space(self.config)
         self._parts, self._episode_of_seed = [], {}
         self._stored = None
         if self.config["load_map_from_json"] and self.config["_load_map_from_json"] is not None:
@@ -452,7 +474,8 @@ class PGDriveEnv:
             raise RuntimeError("call reset() before step()")
         e = self._engine
         self.episode_steps += 1
-        a = np.asarray(action, dtype=np.float32).reshape(2)
+        raw = np.asarray(action, dtype=np.float32).reshape(2)
+        a = discrete_to_continuous(raw, self.config) if self.config["discrete_action"] else raw
         self._act.copy_(e.torch.from_numpy(a).reshape(1, 2))
         cabi.check(
             e.lib,
@@ -469,7 +492,7 @@ class PGDriveEnv:
             acceleration=float(rec["acceleration"]), step_energy=float(rec["step_energy"]),
             episode_energy=float(rec["episode_energy"]), step_reward=float(rec["step_reward"]),
             episode_reward=float(rec["episode_reward"]), episode_length=int(rec["episode_length"]),
-            raw_action=(float(a[0]), float(a[1])), overtake_vehicle_num=0,
+            raw_action=(float(raw[0]), float(raw[1])), overtake_vehicle_num=0,
             on_yellow_continuous_line=bool(flags & cabi.F_ON_YELLOW), on_white_continuous_line=bool(flags & cabi.F_ON_WHITE),
             on_broken_line=bool(flags & cabi.F_ON_BROKEN), crash_sidewalk=bool(flags & cabi.F_CRASH_SIDEWALK),
             on_lane=bool(flags & cabi.F_ON_LANE), out_of_route=bool(flags & cabi.F_OUT_OF_ROUTE)

@@ -30,3 +30,28 @@ class Box:
     def __eq__(self, other):
         return isinstance(other, Box) and self.shape == other.shape and np.allclose(self.low, other.low) and \
             np.allclose(self.high, other.high)
+
+
+class MultiDiscrete:
+    """gym.spaces.MultiDiscrete([n0, n1]) stand-in for ``discrete_action=True`` (base_vehicle.py:721-727)."""
+    def __init__(self, nvec):
+        self.nvec = np.asarray(nvec, dtype=np.int64)
+        self.shape = self.nvec.shape
+        self.dtype = np.dtype(np.int64)
+        self._rs = np.random.RandomState()
+
+    def seed(self, seed=None):
+        self._rs = np.random.RandomState(seed)
+        return [seed]
+
+    def sample(self):
+        return (self._rs.random_sample(self.nvec.shape) * self.nvec).astype(self.dtype)
+
+    def contains(self, x):
+        x = np.asarray(x)
+        return x.shape == self.shape and bool(np.all(x >= 0)) and bool(np.all(x < self.nvec))
+
+    __contains__ = contains
+
+    def __repr__(self):
+        return "MultiDiscrete(%s)" % (self.nvec.tolist(), )

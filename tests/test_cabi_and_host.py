@@ -177,3 +177,16 @@ def test_vec_env_rejects_unsupported_options():
             VecPGDriveEnv(cfg)
     with pytest.raises(KeyError):
         VecPGDriveEnv(dict(no_such_key=True))
+
+
+def test_discrete_actions_follow_the_reference_conversion():
+    """policy/env_input_policy.py:17-31: clip to [-1, 1] first, then index * unit - 1 (so indices >= 1 coincide)."""
+    from pgdrive_b200 import PGDriveEnv
+    from pgdrive_b200.env import discrete_to_continuous
+    env = PGDriveEnv(dict(discrete_action=True))
+    assert repr(env.action_space) == "MultiDiscrete([5, 5])"
+    assert env.action_space.contains(env.action_space.sample())
+    got = discrete_to_continuous(np.array([[0, 0], [1, 4], [3, 2], [4, 1]]), env.config)
+    np.testing.assert_allclose(got, [[-1, -1], [-0.5, -0.5], [-0.5, -0.5], [-0.5, -0.5]])
+    env7 = PGDriveEnv(dict(discrete_action=True, discrete_steering_dim=3, discrete_throttle_dim=9))
+    np.testing.assert_allclose(discrete_to_continuous(np.array([1, 1]), env7.config), [0.0, -0.75])
