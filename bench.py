@@ -7,8 +7,9 @@
 Own arm: every rank steps `--envs` (default 65 536) PGDrive-v0 environments (seeds 1000..1099, traffic density
 0.1, 240-beam lidar, 16 vehicle slots); a "step" is ONE kernel launch advancing all of them by one decision step
 (5 physics sub-steps + observation + reward/done, auto-reset of finished episodes).  Weak scaling: with N ranks
-the job simulates N x 65 536 environments and the observation / reward / done batches are all-gathered (NCCL, in
-place) every step so that rank 0 holds the whole batch.
+the job simulates N x 65 536 environments and every step rank 0 receives the whole observation / reward / done
+batch (--gather: peer = stored by the step kernel straight into rank 0's HBM over NVLink, nccl = in-place
+all-gather overlapped with the next step's kernel, auto = peer at 2 GPUs, nccl beyond).
   value      device-resident: actions pre-generated in HBM, CUDA-event time of K steps, max over ranks
   e2e        same steps through the public VecPGDriveEnv.step(numpy) -> pgd_step_host: pinned H2D of the actions
              and D2H of obs / reward / done / info inside the timed region

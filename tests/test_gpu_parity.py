@@ -36,7 +36,7 @@ def _reset_both(env, ref):
     return obs, ro
 
 
-def _rollout(env, ref, steps, action_fn, check_state_every=0, resync_budget=0):
+def _rollout(env, ref, steps, action_fn, check_state_every=0, resync_budget=0, stats=None):
     """Free-running comparison.  ``resync_budget`` > 0 tolerates that many environments leaving the tolerance band:
     two float32 implementations (CUDA sincosf vs glibc) differ in the last bit, and when a traffic vehicle's IDM
     sits exactly on one of its discrete thresholds (15 m safe gap, 5 m front gap, timer > 50 ...) one of them takes
@@ -45,7 +45,8 @@ def _rollout(env, ref, steps, action_fn, check_state_every=0, resync_budget=0):
     import torch
     n = env.num_envs
     dones = 0
-    grazing = beams = resyncs = 0
+    grazing = beams = 0
+    resyncs = stats["resyncs"] if stats is not None else 0  # cumulative over calls sharing ``stats``
     for t in range(steps):
         a = action_fn(t).astype(np.float32)
         o, r, d, _ = env.step(torch.from_numpy(a).cuda())
@@ -88,6 +89,8 @@ def _rollout(env, ref, steps, action_fn, check_state_every=0, resync_budget=0):
                     np.testing.assert_array_equal(sg[f][:k], sr[f][:k], err_msg="state %s env %d step %d" % (f, e, t))
                 for f in ("x", "y", "heading", "speed"):
                     np.testing.assert_allclose(sg[f][:k], sr[f][:k], rtol=1e-4, atol=2e-3)
+    if stats is not None:
+        stats["resyncs"] = resyncs
     assert grazing <= max(2, beams * 2e-5), "too many ill-conditioned lidar beams: %d of %d" % (grazing, beams)
     return dones
 
@@ -356,4 +359,40 @@ def test_side_and_lane_line_detectors_parity():
     # detector beams end on 15 cm wide ghosts: a beam that just clips a ghost's end is as ill-conditioned as a
     # grazing lidar beam, so a few environments may leave the band (counted and re-synchronised, see _rollout)
     _rollout(env, ref, 150, act, resync_budget=12)
+    env.close()
+
+
+def test_long_soak_with_a_feedback_policy():
+    """1000 steps of a lane-keeping feedback policy (steer towards the checkpoint, hold ~25 km/h): episodes end by
+    arriving, by crashing into traffic and by leaving the road, and every step is compared with the oracle."""
+    import torch
+    seeds = list(range(1000, 1100))
+    n = 200
+    env, ref = _pair(n, seeds)
+    _reset_both(env, ref)
+    rs = np.random.RandomState(9)
+    last = {"obs": ref.obs.copy()}
+    seen = {"arrive": 0, "crash": 0, "out": 0}
+    stats = {"resyncs": 0}  # at most 6 threshold ties in 200 000 env-steps (see _rollout)
+
+    def act(t):
+        o = last["obs"]
+        a = np.zeros((n, 2))
+        a[:, 0] = np.clip(-(o[:, 9] - 0.5) * 6.0 + rs.uniform(-0.05, 0.05, n), -1, 1)
+        a[:, 1] = np.where(o[:, 3] < 0.3, 0.6, 0.0)
+        return a
+
+    for chunk in range(10):
+        def act_and_track(t):
+            a = act(t)
+            return a
+        # _rollout steps both; refresh the policy input from the oracle's observation after every step
+        for t in range(100):
+            _rollout(env, ref, 1, act_and_track, resync_budget=6, stats=stats)
+            last["obs"] = ref.obs.copy()
+            fl = ref.info["flags"]
+            seen["arrive"] += int(((fl & 4) != 0).sum())
+            seen["crash"] += int(((fl & 1) != 0).sum())
+            seen["out"] += int(((fl & 2) != 0).sum())
+    assert seen["arrive"] > 10 and seen["crash"] > 5 and seen["out"] > 50, seen
     env.close()
