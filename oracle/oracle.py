@@ -57,6 +57,8 @@ class Oracle:
         self.cfg = cabi.make_config(num_envs, **cfg)
         self.n = num_envs
         self.h = self.L.orc_create(C.byref(self.tables), C.byref(self.cfg))
+        if not self.h:
+            raise ValueError("an episode needs more vehicle slots / trigger groups than the simulator has")
         self.obs_dim = cabi.obs_dim(self.cfg)
         self.obs = np.zeros((num_envs, self.obs_dim), np.float32)
         self.reward = np.zeros(num_envs, np.float32)

@@ -716,6 +716,10 @@ static void post_step(Oracle* o, Env* e, float last_x, float last_y, float last_
 
 /* ---- public entry points (ctypes) ---------------------------------------------------------------- */
 void* orc_create(const PgdTables* t, const PgdConfig* cfg) {
+  for (int i = 0; i < t->n_episodes; ++i) /* same limits as pgd_load_tables */
+    if (t->episodes[i].n_slots > PGD_MAX_SLOTS || t->episodes[i].n_slots > cfg->num_slots ||
+        t->episodes[i].n_groups > PGD_MAX_GROUPS)
+      return NULL;
   Oracle* o = (Oracle*)calloc(1, sizeof(Oracle));
   o->t = *t;
   o->cfg = *cfg;

@@ -16,7 +16,13 @@ from conftest import load_golden
 
 @pytest.fixture(scope="module")
 def records():
-    return load_golden("step_v0.json.gz")
+    """step_v0: sparse default traffic on 8 maps.  step_dense: 3x the traffic on maps with ramps (lane count drops),
+    only the steps in which some vehicle crept for a forced lane change, braked, re-drew its overtake timer or moved
+    its routing lane -- the branches of idm_policy.py:281-353 that the sparse roll-outs rarely reach."""
+    recs = load_golden("step_v0.json.gz")
+    for r in recs:
+        r.setdefault("density", 0.1)
+    return recs + load_golden("step_dense.json.gz")
 
 
 @pytest.fixture(scope="module")
@@ -24,9 +30,9 @@ def oracles(records):
     from oracle.oracle import Oracle
     from pgdrive_b200 import tables
     out = {}
-    for seed in sorted({r["seed"] for r in records}):
-        T = tables.build_tables([seed]).finish()
-        out[seed] = (Oracle(T, 1, auto_reset=False), T)
+    for seed, density in sorted({(r["seed"], r["density"]) for r in records}):
+        T = tables.build_tables([seed], density=density).finish()
+        out[(seed, density)] = (Oracle(T, 1, auto_reset=False, num_slots=32), T)
     yield out
     for o, _ in out.values():
         o.close()
@@ -34,7 +40,7 @@ def oracles(records):
 
 def _replay(oracles, rec):
     from pgdrive_b200 import cabi
-    orc, T = oracles[rec["seed"]]
+    orc, T = oracles[(rec["seed"], rec["density"])]
     s0 = np.frombuffer(base64.b64decode(rec["s0"]), dtype=cabi.ENV_STATE_DT).copy()
     orc.set_state(0, s0)
     obs, rew, done, info = orc.step(np.array([rec["action"]], np.float32))
@@ -42,19 +48,22 @@ def _replay(oracles, rec):
 
 
 def test_fixture_is_substantial(records):
-    assert len(records) >= 400
-    assert sum(len(r["idm"]) for r in records) >= 1500
+    assert len(records) >= 900
+    assert sum(len(r["idm"]) for r in records) >= 7000
     assert any(r["ck"] != [0, 1] for r in records)
     assert any(max(r["neighbours"]) > 0 for r in records)
 
 
 def test_idm_actions_match_reference(records, oracles):
     worst = 0.0
-    lane_changes = creeps = 0
+    lane_changes = creeps = ties = 0
     for rec in records:
         _, s1, _ = _replay(oracles, rec)
         veh = s1["veh"][0]
         for g in rec["idm"]:
+            if g.get("tie"):  # the reference's own answer flips under a 0.3 mm nudge (exact-threshold tie)
+                ties += 1
+                continue
             v = veh[g["slot"]]
             tag = (rec["seed"], rec["t"], g["slot"])
             assert int(v["rt_lane"]) == g["rt_lane"], tag
@@ -67,6 +76,8 @@ def test_idm_actions_match_reference(records, oracles):
             worst = max(worst, abs(float(v["steer"]) - g["steering"]), abs(float(v["throttle"]) - g["acc"]))
             creeps += g["target_speed"] == 5.0
     assert worst < 5e-2
+    assert creeps >= 60  # forced lane changes with the creep speed are covered
+    assert ties < 0.02 * sum(len(r["idm"]) for r in records)
 
 
 def test_navigation_and_checkpoints_match_reference(records, oracles):

@@ -304,7 +304,7 @@ if __name__ == "__main__":
 # States come from a roll-out of this repo's CPU oracle (they are just inputs); every expected value
 # in the fixture is computed by unmodified reference code running under tools/ref_stub.py.
 # =================================================================================================
-def cmd_step(seeds, tag, steps=260, every=4):
+def cmd_step(seeds, tag, steps=260, every=4, density=0.1, only_interesting=False, max_records=100000):
     import base64
     from collections import deque
     sys.path.insert(0, os.path.dirname(HERE))
@@ -355,11 +355,11 @@ def cmd_step(seeds, tag, steps=260, every=4):
     out = []
     for seed in seeds:
         eng, m = build_map(seed)
-        eng.global_config["traffic_density"] = 0.1
+        eng.global_config["traffic_density"] = density
         pgmap = mapgen.generate_map(seed)
         ts = ptables.TableSet()
         mid = ts.add_map(pgmap)
-        ts.add_episode(pgmap, mid, pepisode.make_episode(pgmap, seed, 0.1))
+        ts.add_episode(pgmap, mid, pepisode.make_episode(pgmap, seed, density))
         T = ts.finish()
         mi = ts.index[0]
         ref_lanes = []
@@ -371,7 +371,10 @@ def cmd_step(seeds, tag, steps=260, every=4):
         node_name = {v: k for k, v in mi.nodes.items()}
         slots = T["slots"]
         n_slots = int(T["episodes"][0]["n_slots"])
-        orc = Oracle(T, 1, auto_reset=False)
+        if n_slots > 32:
+            print("seed", seed, "needs", n_slots, "vehicle slots: skipped")
+            continue
+        orc = Oracle(T, 1, auto_reset=False, num_slots=32)
         orc.reset([0], [0])
         rs = np.random.RandomState(seed)
         policies = {}
@@ -410,7 +413,8 @@ def cmd_step(seeds, tag, steps=260, every=4):
             s1 = orc.get_state(0)
             v1 = s1["veh"][0]
             if t % every == 0 and t > 0:
-                rec = dict(seed=seed, t=t, s0=base64.b64encode(s0.tobytes()).decode(), action=[float(a[0, 0]), float(a[0, 1])])
+                rec = dict(seed=seed, t=t, density=density, s0=base64.b64encode(s0.tobytes()).decode(),
+                           action=[float(a[0, 0]), float(a[0, 1])])
                 # ---- world before the step (IDM inputs) ----
                 world0 = {}
                 for i in range(n_slots):
@@ -452,14 +456,47 @@ def cmd_step(seeds, tag, steps=260, every=4):
                             return v
 
                     pol.np_random = _Stream(slots[i]["rnd25"], int(v0[i]["rnd_n"]))
-                    steering, acc = pol.act()
+                    # A decision that flips when every other vehicle is nudged by 0.3 mm sits on one of IDM's exact
+                    # thresholds (traffic spawns on a 10 m grid and MAX_LONG_DIST is 30 m, SAFE_LANE_CHANGE_DISTANCE
+                    # 15 m): the reference's own outcome then depends on float32 position round-off inside Bullet.
+                    # Such samples are marked as ties and not used as known answers.
+                    import copy as _copy
+                    outcomes = []
+                    for nudge in (0.0, 3e-4, -3e-4):
+                        trial = _copy.copy(pol)
+                        trial.heading_pid, trial.lateral_pid = _copy.copy(pol.heading_pid), _copy.copy(pol.lateral_pid)
+                        trial.np_random = _Stream(slots[i]["rnd25"], int(v0[i]["rnd_n"]))
+                        saved_pos = {}
+                        for j, other in world0.items():
+                            if j != i:
+                                saved_pos[j] = other.position
+                                other.position = other.position + nudge * np.asarray([other.heading[0], other.heading[1]])
+                        st_, acc_ = trial.act()
+                        for j, ppos in saved_pos.items():
+                            world0[j].position = ppos
+                        outcomes.append((float(st_), float(acc_), float(trial.target_speed), int(trial.overtake_timer),
+                                         ref_lanes.index(trial.routing_target_lane), trial))
+                    steering, acc = outcomes[0][0], outcomes[0][1]
+                    pol = outcomes[0][5]
+                    tie = any(abs(o_[0] - steering) > 2e-3 or abs(o_[1] - acc) > 2e-3 or o_[2:5] != outcomes[0][2:5]
+                              for o_ in outcomes[1:])
                     idm.append(dict(
                         slot=i, steering=float(steering), acc=float(acc), target_speed=float(pol.target_speed),
                         timer=int(pol.overtake_timer), rt_lane=ref_lanes.index(pol.routing_target_lane),
                         pid=[float(pol.heading_pid.p_error), float(pol.heading_pid.i_error),
-                             float(pol.lateral_pid.p_error), float(pol.lateral_pid.i_error)]
+                             float(pol.lateral_pid.p_error), float(pol.lateral_pid.i_error)], tie=bool(tie)
                     ))
                 rec["idm"] = idm
+                if only_interesting:
+                    # keep the step only if some vehicle crept, braked, finished a lane change (timer re-drawn) or
+                    # moved its routing lane: the branches a sparse roll-out rarely reaches
+                    keep = False
+                    for g in idm:
+                        v = v0[g["slot"]]
+                        keep |= g["target_speed"] == 5.0 or g["acc"] < 0 or g["timer"] < int(v["timer"]) or \
+                            (int(v["rt_lane"]) >= 0 and g["rt_lane"] != int(v["rt_lane"]))
+                    if not keep:
+                        continue
                 # ---- world after the step (observation / reward inputs) ----
                 world1 = {}
                 for i in range(n_slots):
@@ -512,7 +549,7 @@ def cmd_step(seeds, tag, steps=260, every=4):
                 rec["arrive_dest"] = bool(ego.arrive_destination.fget(ego) if isinstance(
                     ego.arrive_destination, property) else FakeVehicle.arrive_destination.fget(ego))
                 out.append(rec)
-            if done[0]:
+            if done[0] or len(out) >= max_records:
                 break
         orc.close()
         print("seed", seed, "steps", t + 1, "records so far", len(out), "idm samples", sum(len(r["idm"]) for r in out))
@@ -524,6 +561,11 @@ def cmd_step(seeds, tag, steps=260, every=4):
 
 if __name__ == "__main__" and sys.argv[1] == "step":
     cmd_step([1000, 1003, 1008, 1015, 1021, 1042, 1055, 1077], "v0")
+if __name__ == "__main__" and sys.argv[1] == "step_dense":
+    # ramps (lane count drops -> forced lane changes / creeping) and 3x the default traffic, every step sampled,
+    # only the steps that exercise IDM's rarer branches kept
+    cmd_step([1000, 1002, 1006, 1011, 1013, 1016, 1017, 1024, 1028, 1033, 1036, 1039], "dense", steps=400, every=1,
+             density=0.3, only_interesting=True, max_records=100000)
 
 
 # =================================================================================================
