@@ -81,6 +81,25 @@ typedef struct {
   int32_t n_route;
 } PgdTables;
 
+/* Settings of the on-device reset path (pgd_generate_tables): what the reference keeps in map_config
+ * (component/map/base_map.py:16-35: block_num | block_sequence, lane_num, lane_width, exit_length), the traffic
+ * density (manager/traffic_manager.py:263-270) and the ego spawn (base_vehicle.py:299-311). */
+typedef struct {
+  int32_t block_num;       /* number of searched blocks */
+  int32_t lane_num;
+  int32_t n_fixed;         /* > 0: the block types are given (map_config type "block_sequence") */
+  int32_t spawn_lane;      /* lane index on the first road (">", ">>") */
+  double lane_width, exit_length, density, spawn_long, spawn_lat;
+  int8_t fixed_types[32];  /* 0..6 = C S r R X T O (order of BLOCK_TYPE_DISTRIBUTION_V2) */
+} PgdGenConfig;
+
+/* Per-map capacities of the generated tables (map m owns the fixed-stride slice [m * cap, (m + 1) * cap) of every
+ * table; PgdMap / PgdEpisode / PgdSlot carry the offsets as usual).  A map that does not fit is reported, never
+ * truncated. */
+typedef struct {
+  int32_t blocks, lanes, roads, boxes, cells, entries, queue, route, cand;
+} PgdGenCaps;
+
 /* Reward / termination scheme (envs/pgdrive_env.py:93-108) and stepping (envs/base_env.py:33,70). */
 typedef struct {
   int32_t num_envs;

@@ -56,6 +56,25 @@ int pgd_step_host(PgdHandle* h, const float* actions, float* obs, float* reward,
 int pgd_get_state(PgdHandle* h, int32_t env, PgdEnvState* out);
 int pgd_set_state(PgdHandle* h, int32_t env, const PgdEnvState* in);
 
+/* The reset path ON THE DEVICE: component/algorithm/BIG.py:67-151 (block search with retry / back-tracking),
+ * component/blocks/*.py (block builders), component/map/pg_map.py:48-71 (rebuild from the block sequence),
+ * component/blocks/base_block.py:181-463 (static collision primitives), manager/traffic_manager.py:239-290 +
+ * component/vehicle_module/navigation.py:99-153 (traffic slots, vehicle parameters, routes), on the reference's own
+ * random streams (utils/random_utils.py:14-50: sha512-seeded MT19937, numpy legacy draws).  One warp generates one
+ * seed; map i / episode i of the installed tables belong to seeds[i].  seeds, status_out [n] and counts_out [n * 8]
+ * (lanes, roads, boxes, cells + 1, grid entries, slots, route entries, blocks; may be NULL) are HOST pointers; the
+ * tables never leave the device.  Returns -4 (and still fills status_out) when a seed could not be generated, -3
+ * when an episode needs more vehicle slots than the handle has.  Synchronises `stream`. */
+int pgd_generate_tables(PgdHandle* h, const int32_t* seeds, int32_t n, const PgdGenConfig* gen, const PgdGenCaps* caps,
+                        int32_t* status_out, int32_t* counts_out, void* stream);
+
+/* Element counts of the handle's device tables, in the order of PgdTables (maps, lanes, roads, boxes, cell_start,
+ * cell_entries, episodes, slots, route), and a device -> host copy of them into caller-owned buffers of those
+ * sizes (component/map/base_map.py:103-118 save_map is the nearest reference interface; used by tests and to cache
+ * generated maps). */
+int pgd_table_sizes(PgdHandle* h, int64_t sizes[9]);
+int pgd_download_tables(PgdHandle* h, PgdTables* dst);
+
 /* Cross-process peer memory (one process per GPU, NVLink / NVSwitch).  The owner allocates a device buffer and
  * exports a 64-byte handle; every other rank opens it and passes `base + its row offset` as obs_dev / reward_dev /
  * done_dev of pgd_step, so the step kernel stores its results straight into the owner's HBM over NVLink: the gather

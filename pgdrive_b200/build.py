@@ -4,6 +4,7 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "pgd_step.cu")
+SRC_GEN = os.path.join(HERE, "csrc", "pgd_mapgen.cu")
 OUT = os.path.join(HERE, "csrc", "libpgdrive_b200.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared", "-Xcompiler", "-fPIC",
@@ -14,11 +15,12 @@ NVCC_FLAGS = [
 
 
 def build_cuda(force=False, verbose=False):
-    deps = [SRC, os.path.join(HERE, "..", "include", "pgdrive_b200.h"), os.path.join(HERE, "..", "include", "pgd_tables.h")]
+    deps = [SRC, SRC_GEN, os.path.join(HERE, "..", "include", "pgdrive_b200.h"), os.path.join(HERE, "..", "include", "pgd_tables.h")]
+    deps += [os.path.join(HERE, "csrc", f) for f in ("pgd_internal.h", "pgd_mapgen.cuh", "pgd_rng.cuh", "pgd_dd.cuh")]
     if not force and os.path.exists(OUT) and os.path.getmtime(OUT) >= max(os.path.getmtime(d) for d in deps):
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", OUT, SRC]
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", OUT, SRC, SRC_GEN]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if verbose or res.returncode != 0:
         print(res.stdout)

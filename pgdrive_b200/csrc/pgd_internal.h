@@ -1,0 +1,77 @@
+// Internal (not installed) declarations shared by the translation units of libpgdrive_b200.so.
+#ifndef PGD_INTERNAL_H
+#define PGD_INTERNAL_H
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/pgdrive_b200.h"
+
+struct DevTables {
+  const PgdMap* maps;
+  const PgdLane* lanes;
+  const PgdRoad* roads;
+  const PgdBox* boxes;
+  const int32_t* cell_start;
+  const int32_t* cell_entries;
+  const PgdEpisode* episodes;
+  const PgdSlot* slots;
+  const int32_t* route_nodes;
+  const int32_t* route_roads;
+};
+
+// SoA state; index = env * V + slot for the per-slot arrays, env for the per-env ones.
+struct DevState {
+  float4* pose;  // x, y, heading, speed
+  float4* ctrl;  // steer, throttle, heading-PID last error, heading-PID summed error
+  float4* pidl;  // lateral-PID last error, summed error, IDM target speed, yaw rate
+  int4* nav;     // lane, ck0 | ck1 << 16, routing target lane, overtake timer
+  int4* misc;    // rnd draws used, airborne sub-steps left, PGD_V_* flags, -
+  int4* envi;    // episode, next trigger group, done, episode length
+  float4* envf;  // previous steering, previous throttle, episode reward, episode energy
+};
+
+extern thread_local std::string g_pgd_err;
+
+static inline int fail(int code, const std::string& msg) {
+  g_pgd_err = msg;
+  return code;
+}
+
+#define CU(call)                                                                                  \
+  do {                                                                                            \
+    cudaError_t e_ = (call);                                                                      \
+    if (e_ != cudaSuccess) return fail(-2, std::string(#call) + ": " + cudaGetErrorString(e_));   \
+  } while (0)
+
+struct PgdHandle {
+  PgdConfig cfg;
+  int device;
+  DevTables T;
+  void* table_mem[10];
+  int64_t table_count[10];  // elements per table (maps, lanes, roads, boxes, cell_start, cell_entries, episodes, slots, route, route)
+  int n_episodes;
+  DevState S;
+  void* state_mem[7];
+  bool tables_loaded;
+  int64_t launches;
+  // reset scratch
+  int32_t* d_ids;
+  int32_t* d_eps;
+  int scratch_cap;
+  // pinned staging + device buffers for the host-buffer step
+  float *h_act, *h_obs, *h_rew;
+  uint8_t* h_done;
+  PgdInfo* h_info;
+  float *d_act, *d_obs, *d_rew;
+  uint8_t* d_done;
+  PgdInfo* d_info;
+  cudaStream_t own_stream, own_stream2;
+  cudaEvent_t ev_act;
+  // timing
+  int timing;
+  cudaEvent_t ev0, ev1;
+};
+
+#endif

@@ -80,18 +80,8 @@ struct GBlock {
   double lane_width;
 };
 
-struct GenConfig {  // what the reference keeps in map_config + traffic / spawn settings
-  int32_t block_num;       // number of searched blocks (map_config["config"] when type == "block_num")
-  int32_t lane_num;
-  int32_t n_fixed;         // > 0: block types are given (type == "block_sequence"), fixed_types[0..n_fixed)
-  int32_t spawn_lane;      // lane index on the first road (">", ">>")
-  double lane_width, exit_length, density, spawn_long, spawn_lat;
-  int8_t fixed_types[32];
-};
-
-struct GenCaps {
-  int32_t blocks, lanes, roads, boxes, cells, entries, queue, route, cand;
-};
+typedef PgdGenConfig GenConfig;  // include/pgd_tables.h
+typedef PgdGenCaps GenCaps;
 
 struct GBox {
   double cx, cy, ux, uy, hl, hw;

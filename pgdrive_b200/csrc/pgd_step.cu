@@ -24,6 +24,7 @@
 #include <string>
 
 #include "../../include/pgdrive_b200.h"
+#include "pgd_internal.h"
 
 #define PI_F 3.14159265358979323846f
 #define TWO_PI_F 6.28318530717958647692f
@@ -57,30 +58,6 @@
 #endif
 #define DONE_PENDING_RESET 2
 #define PGD_OBS_CAP_DET (2 * PGD_MAX_DETECTOR_BEAMS + 6 + 10 + 16 + PGD_LIDAR_BEAMS)  /* 752 */
-
-struct DevTables {
-  const PgdMap* maps;
-  const PgdLane* lanes;
-  const PgdRoad* roads;
-  const PgdBox* boxes;
-  const int32_t* cell_start;
-  const int32_t* cell_entries;
-  const PgdEpisode* episodes;
-  const PgdSlot* slots;
-  const int32_t* route_nodes;
-  const int32_t* route_roads;
-};
-
-// SoA state; index = env * V + slot for the per-slot arrays, env for the per-env ones.
-struct DevState {
-  float4* pose;  // x, y, heading, speed
-  float4* ctrl;  // steer, throttle, heading-PID last error, heading-PID summed error
-  float4* pidl;  // lateral-PID last error, summed error, IDM target speed, yaw rate
-  int4* nav;     // lane, ck0 | ck1 << 16, routing target lane, overtake timer
-  int4* misc;    // rnd draws used, airborne sub-steps left, PGD_V_* flags, -
-  int4* envi;    // episode, next trigger group, done, episode length
-  float4* envf;  // previous steering, previous throttle, episode reward, episode energy
-};
 
 // ------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float clipf(float a, float lo, float hi) { return fminf(fmaxf(a, lo), hi); }
@@ -1015,48 +992,9 @@ __global__ void pgd_mark_reset_kernel(DevState S, const int32_t* env_ids, const 
 // ===================================================================================================================
 // host side: C-ABI
 // ===================================================================================================================
-static thread_local std::string g_err;
+thread_local std::string g_pgd_err;
 
-static int fail(int code, const std::string& msg) {
-  g_err = msg;
-  return code;
-}
-
-#define CU(call)                                                                                  \
-  do {                                                                                            \
-    cudaError_t e_ = (call);                                                                      \
-    if (e_ != cudaSuccess) return fail(-2, std::string(#call) + ": " + cudaGetErrorString(e_));   \
-  } while (0)
-
-struct PgdHandle {
-  PgdConfig cfg;
-  int device;
-  DevTables T;
-  void* table_mem[10];
-  int n_episodes;
-  DevState S;
-  void* state_mem[7];
-  bool tables_loaded;
-  int64_t launches;
-  // reset scratch
-  int32_t* d_ids;
-  int32_t* d_eps;
-  int scratch_cap;
-  // pinned staging + device buffers for the host-buffer step
-  float *h_act, *h_obs, *h_rew;
-  uint8_t* h_done;
-  PgdInfo* h_info;
-  float *d_act, *d_obs, *d_rew;
-  uint8_t* d_done;
-  PgdInfo* d_info;
-  cudaStream_t own_stream, own_stream2;
-  cudaEvent_t ev_act;
-  // timing
-  int timing;
-  cudaEvent_t ev0, ev1;
-};
-
-extern "C" const char* pgd_last_error(void) { return g_err.c_str(); }
+extern "C" const char* pgd_last_error(void) { return g_pgd_err.c_str(); }
 
 extern "C" int pgd_create(const PgdConfig* cfg, int device, PgdHandle** out) {
   if (!cfg || !out) return fail(-1, "pgd_create: null argument");
@@ -1142,6 +1080,9 @@ extern "C" int pgd_load_tables(PgdHandle* h, const PgdTables* t) {
   h->T.slots = (const PgdSlot*)h->table_mem[7];
   h->T.route_nodes = (const int32_t*)h->table_mem[8];
   h->T.route_roads = (const int32_t*)h->table_mem[9];
+  const int64_t counts[10] = {t->n_maps, t->n_lanes, t->n_roads, t->n_boxes, t->n_cell_start, t->n_cell_entries,
+                              t->n_episodes, t->n_slots, t->n_route, t->n_route};
+  for (int i = 0; i < 10; ++i) h->table_count[i] = counts[i];
   h->n_episodes = t->n_episodes;
   h->tables_loaded = true;
   return 0;

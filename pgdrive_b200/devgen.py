@@ -78,3 +78,63 @@ def caps_for(gen_config):
     c.route = 32 * (3 * b + 10)
     c.cand = 160 * b
     return c
+
+
+def generate(engine, seeds, gen_config, caps=None):
+    """Generate maps + episode templates of ``seeds`` on ``engine``'s device and install them as its tables
+    (pgd_generate_tables).  Returns (status [n], counts [n, 8]); raises when a seed cannot be generated."""
+    import numpy as np
+    from . import cabi
+    caps = caps or caps_for(gen_config)
+    s = np.ascontiguousarray(seeds, dtype=np.int32)
+    status = np.zeros(len(s), np.int32)
+    counts = np.zeros((len(s), 8), np.int32)
+    rc = engine.lib.pgd_generate_tables(engine.h, s.ctypes.data, len(s), C.addressof(gen_config), C.addressof(caps),
+                                        status.ctypes.data, counts.ctypes.data, engine.stream())
+    engine.gen_status, engine.gen_counts, engine.gen_caps = status, counts, caps
+    cabi.check(engine.lib, rc)
+    return status, counts
+
+
+def download(engine):
+    """Device tables -> dict of numpy arrays in the layout of tables.TableSet.finish() (fixed stride per map when
+    they were generated on the device)."""
+    import numpy as np
+    from . import cabi, tables as tb
+    sizes = np.zeros(9, np.int64)
+    cabi.check(engine.lib, engine.lib.pgd_table_sizes(engine.h, sizes.ctypes.data))
+    dts = [tb.MAP_DT, tb.LANE_DT, tb.ROAD_DT, tb.BOX_DT, np.int32, np.int32, tb.EPISODE_DT, tb.SLOT_DT, np.int32]
+    names = ["maps", "lanes", "roads", "boxes", "cell_start", "cell_entries", "episodes", "slots", "route_nodes"]
+    T = {k: np.zeros(int(n), dt) for k, n, dt in zip(names, sizes, dts)}
+    T["route_roads"] = np.zeros(int(sizes[8]), np.int32)
+    t, keep = cabi.pack_tables(T)
+    cabi.check(engine.lib, engine.lib.pgd_download_tables(engine.h, C.byref(t)))
+    T["max_slots"] = int(T["episodes"]["n_slots"].max()) if len(T["episodes"]) else 0
+    return T
+
+
+def compact(T, m):
+    """Map / episode ``m`` of fixed-stride tables as a stand-alone table set with offsets rebased to 0 (the form
+    tables.TableSet.finish() gives for a single seed)."""
+    import numpy as np
+    mp, ep = T["maps"][m:m + 1].copy(), T["episodes"][m:m + 1].copy()
+    r = mp[0]
+    nc = int(r["nx"]) * int(r["ny"]) + 1
+    cs = T["cell_start"][r["cell_off"]:r["cell_off"] + nc]
+    slots = T["slots"][ep[0]["slot_off"]:ep[0]["slot_off"] + ep[0]["n_slots"]].copy()
+    r0 = int(slots["route_off"].min()) if len(slots) else 0
+    nr = int((slots["route_off"] + slots["route_len"]).max()) - r0 if len(slots) else 0
+    out = dict(
+        lanes=T["lanes"][r["lane_off"]:r["lane_off"] + r["n_lanes"]],
+        roads=T["roads"][r["road_off"]:r["road_off"] + r["n_roads"]],
+        boxes=T["boxes"][r["box_off"]:r["box_off"] + r["n_boxes"]],
+        cell_start=cs, cell_entries=T["cell_entries"][r["entry_off"]:r["entry_off"] + int(cs[-1])],
+        route_nodes=T["route_nodes"][r0:r0 + nr], route_roads=T["route_roads"][r0:r0 + nr],
+    )
+    slots["route_off"] -= r0
+    for k in ("lane_off", "road_off", "box_off", "cell_off", "entry_off"):
+        mp[k] = 0
+    ep["map"] = 0
+    ep["slot_off"] = 0
+    out.update(maps=mp, episodes=ep, slots=slots, max_slots=int(ep[0]["n_slots"]))
+    return out

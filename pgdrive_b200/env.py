@@ -17,7 +17,7 @@ import pickle
 
 import numpy as np
 
-from . import cabi, episode, mapgen, tables
+from . import cabi, devgen, episode, mapgen, tables
 from .config import ENGINE_CONFIG, Config, check_supported, default_config
 from .spaces import Box, MultiDiscrete
 
@@ -248,16 +248,35 @@ class VecPGDriveEnv:
         stored = None
         if cfg["load_map_from_json"] and cfg["_load_map_from_json"] is not None:
             stored = load_map_file(cfg["_load_map_from_json"], self.map_config, seeds)
-        self.T = tables_dict if tables_dict is not None else build_seed_tables(
-            seeds, self.map_config, cfg["traffic_density"], self._spawn, stored=stored
-        )
-        self.episode_of_seed = {int(s): i for i, s in enumerate(self.T["episodes"]["seed"])}
-        need = int(self.T["max_slots"])
-        slots = cfg["num_slots"] or (16 if need <= 16 else 32)
-        if need > slots:
-            raise ValueError("the loaded seeds need %d vehicle slots; num_slots=%d" % (need, slots))
-        self.engine = _Engine(cfg, self.num_envs, slots, int(cfg["device"]), bool(cfg["auto_reset"]))
-        self.engine.load(self.T)
+        self._T = None
+        if cfg["device_mapgen"] and tables_dict is None and stored is None:
+            # the whole reset path runs on the GPU (pgd_generate_tables); tables never visit the host
+            gc = devgen.make_gen_config(self.map_config, cfg["traffic_density"], self._spawn)
+            slots = cfg["num_slots"] or 16
+            while True:
+                self.engine = _Engine(cfg, self.num_envs, slots, int(cfg["device"]), bool(cfg["auto_reset"]))
+                try:
+                    devgen.generate(self.engine, seeds, gc)
+                    break
+                except RuntimeError:
+                    need = int(self.engine.gen_counts[:, 5].max())
+                    ok = (self.engine.gen_status == 0).all()
+                    self.engine.close()
+                    if not ok or cfg["num_slots"] or need <= slots or slots == 32:
+                        raise
+                    slots = 32  # some seed needs more than 16 vehicle slots
+            self.episode_of_seed = {int(s): i for i, s in enumerate(seeds)}
+        else:
+            self._T = tables_dict if tables_dict is not None else build_seed_tables(
+                seeds, self.map_config, cfg["traffic_density"], self._spawn, stored=stored
+            )
+            self.episode_of_seed = {int(s): i for i, s in enumerate(self._T["episodes"]["seed"])}
+            need = int(self._T["max_slots"])
+            slots = cfg["num_slots"] or (16 if need <= 16 else 32)
+            if need > slots:
+                raise ValueError("the loaded seeds need %d vehicle slots; num_slots=%d" % (need, slots))
+            self.engine = _Engine(cfg, self.num_envs, slots, int(cfg["device"]), bool(cfg["auto_reset"]))
+            self.engine.load(self._T)
         torch = self.engine.torch
         dev = self.engine.device
         n = self.num_envs
@@ -278,6 +297,13 @@ class VecPGDriveEnv:
         self.observation_space = Box(-0.0, 1.0, shape=(self.obs_dim, ), dtype=np.float32)
         self.action_space = make_action_space(cfg)
         self.env_seeds = np.array([self.start_seed + i % self.env_num for i in range(n)], dtype=np.int64)
+
+    @property
+    def T(self):
+        """Host copy of the tables (downloaded from the device when they were generated there)."""
+        if self._T is None:
+            self._T = devgen.download(self.engine)
+        return self._T
 
     # -- reset / step ------------------------------------------------------------------------------
     def reset(self, seeds=None, env_ids=None):
