@@ -176,10 +176,13 @@ static void localize(const Oracle* o, const PgdMap* m, Veh* v) {
     const PgdBox* box = &o->t.boxes[m->box_off + b];
     if (box->kind != PGD_BOX_LANE || !rect_contains(box, v->x, v->y)) continue;
     const PgdLane* l = lane_at(o, m, box->lane);
-    float lon, lat;
-    lane_local(l, v->x, v->y, &lon, &lat);
-    float lh = lane_heading_at(l, lon);
-    if (!(cosf(lh) * hx + sinf(lh) * hy > 0.0f)) continue;
+    /* cos(lane.heading_at(long)) * hx + sin(...) * hy > 0 (scene_utils.py:158-170) with the lane direction written
+     * without trigonometry: a straight lane's unit vector, an arc's tangent dir * (-dy, dx) / r at the vehicle's
+     * bearing from the centre (heading_at(long) = bearing + dir * pi / 2; r > 0 does not change the sign) */
+    float dot;
+    if (l->kind == PGD_LANE_STRAIGHT) dot = l->ax * hx + l->ay * hy;
+    else dot = l->dir * ((v->x - l->ax) * hy - (v->y - l->ay) * hx);
+    if (!(dot > 0.0f)) continue;
     if (first_any < 0) first_any = box->lane;
     if (first_cur < 0 && l->road == cur_road) first_cur = box->lane;
     if (first_next < 0 && l->road == next_road) first_next = box->lane;

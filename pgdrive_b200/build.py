@@ -3,32 +3,54 @@ import os
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = os.path.join(HERE, "csrc", "pgd_step.cu")
-SRC_GEN = os.path.join(HERE, "csrc", "pgd_mapgen.cu")
-OUT = os.path.join(HERE, "csrc", "libpgdrive_b200.so")
+CSRC = os.path.join(HERE, "csrc")
+INC = os.path.join(HERE, "..", "include")
+OUT = os.path.join(CSRC, "libpgdrive_b200.so")
+COMMON = ["pgd_internal.h", os.path.join(INC, "pgdrive_b200.h"), os.path.join(INC, "pgd_tables.h")]
+# translation unit -> extra dependencies
+UNITS = {
+    "pgd_step.cu": [],
+    "pgd_mapgen.cu": ["pgd_mapgen.cuh", "pgd_rng.cuh", "pgd_dd.cuh"],
+}
 NVCC_FLAGS = [
-    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared", "-Xcompiler", "-fPIC",
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
     # IEEE arithmetic without FMA contraction: the step is checked against a scalar C oracle built with
-    # -ffp-contract=off, and contact / done flags depend on exact comparisons
+    # -ffp-contract=off, contact / done flags depend on exact comparisons, and the map generator must give the
+    # same bits as its host build (explicit fma() calls stay fused on both)
     "-fmad=false", "-Xptxas", "-v"
 ]
 
 
-def build_cuda(force=False, verbose=False):
-    deps = [SRC, SRC_GEN, os.path.join(HERE, "..", "include", "pgdrive_b200.h"), os.path.join(HERE, "..", "include", "pgd_tables.h")]
-    deps += [os.path.join(HERE, "csrc", f) for f in ("pgd_internal.h", "pgd_mapgen.cuh", "pgd_rng.cuh", "pgd_dd.cuh")]
-    if not force and os.path.exists(OUT) and os.path.getmtime(OUT) >= max(os.path.getmtime(d) for d in deps):
-        return OUT
-    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", OUT, SRC, SRC_GEN]
+def _run(cmd, verbose):
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if verbose or res.returncode != 0:
         print(res.stdout)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed: " + " ".join(cmd))
-    with open(os.path.join(HERE, "csrc", "ptxas.log"), "w") as f:
-        f.write(res.stdout)
-    return OUT
+    return res.stdout
+
+
+def build_cuda(force=False, verbose=False, out=OUT, defines=()):
+    """Compile every translation unit to an object (re-used while its sources are unchanged) and link the shared
+    library.  ``defines`` (e.g. ["-DMIN_CTAS_PER_SM=5"]) builds a kernel variant into ``out``."""
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    tag = "".join(c if c.isalnum() else "_" for c in "".join(defines))
+    objs, log, relink = [], [], force or not os.path.exists(out)
+    for unit, extra in UNITS.items():
+        src = os.path.join(CSRC, unit)
+        utag = tag if unit == "pgd_step.cu" else ""  # variants only differ in the step kernel
+        obj = os.path.join(CSRC, unit.replace(".cu", utag + ".o"))
+        deps = [src] + [d if os.path.isabs(d) else os.path.join(CSRC, d) for d in COMMON + extra]
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(d) for d in deps):
+            text = _run([nvcc] + NVCC_FLAGS + (list(defines) if utag else []) + ["-c", "-o", obj, src], verbose)
+            with open(os.path.join(CSRC, unit.replace(".cu", utag + ".ptxas.log")), "w") as f:
+                f.write(text)
+            relink = True
+        relink = relink or os.path.getmtime(obj) > os.path.getmtime(out)
+        objs.append(obj)
+    if relink:
+        _run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out] + objs, verbose)
+    return out
 
 
 if __name__ == "__main__":

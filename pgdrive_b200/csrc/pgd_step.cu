@@ -211,7 +211,6 @@ struct EnvShared {
   float olong[V];                  // longitudinal coordinate of each vehicle on its own lane (start of step)
   int blo[V], bn[V];               // lidar: first beam index and beam count each chassis can intersect
   int croad[V], nroad[V];          // localisation: current / next route road of each moving vehicle
-  float2 obs2[OBS_CAP / 2];        // the observation row is assembled here and streamed out with 8-byte stores
   int qlane[8];                    // ego queries: lane ids
   float qlon[8], qlat[8];          // ego queries: Frenet results
   float d2[V];                     // squared centre distance to the ego (neighbour ranking)
@@ -235,6 +234,9 @@ pgd_step_kernel(DevTables T, DevState S, PgdConfig cfg, int mode, int env_begin,
                 PgdInfo* __restrict__ info) {
   constexpr int ENVS_PER_CTA = CTA_THREADS / V;
   __shared__ EnvShared<V, OBS_CAP> sh_all[ENVS_PER_CTA];
+  // The observation rows of the CTA's environments are assembled back to back (stride = the row length), i.e. in
+  // the layout they have in HBM, and leave with ONE bulk (TMA) shared -> global copy per CTA.
+  __shared__ __align__(16) float obs_rows[ENVS_PER_CTA * OBS_CAP];
   const int slot = threadIdx.x % V;
   const int env_in_cta = threadIdx.x / V;
   const int env_raw = env_begin + blockIdx.x * ENVS_PER_CTA + env_in_cta;  // this launch covers [env_begin, env_end)
@@ -311,13 +313,6 @@ pgd_step_kernel(DevTables T, DevState S, PgdConfig cfg, int mode, int env_begin,
     sh.ux[slot] = c; sh.uy[slot] = s;
     sh.hl[slot] = half_l; sh.hw[slot] = half_w;
     sh.lane[slot] = lane; sh.alive[slot] = alive;
-    if (alive) {
-      const Lane l = load_lane(lanes + lane);
-      sh.sx[slot] = l.sx; sh.sy[slot] = l.sy; sh.ex[slot] = l.ex; sh.ey[slot] = l.ey; sh.llen[slot] = l.length;
-      float lon, lat;
-      lane_local(l, x, y, lon, lat);
-      sh.olong[slot] = lon;
-    }
   }
   __syncwarp(group_mask);
 
@@ -343,6 +338,18 @@ pgd_step_kernel(DevTables T, DevState S, PgdConfig cfg, int mode, int env_begin,
       }
     }
 
+    // what the IDM neighbour search reads from every vehicle -- the geometry of the lane it is on and its
+    // longitudinal coordinate there -- is only needed when some traffic vehicle of this environment is awake
+    if (__ballot_sync(group_mask, alive && active && slot != 0) & group_mask) {
+      if (alive) {
+        const Lane l = load_lane(lanes + lane);
+        sh.sx[slot] = l.sx; sh.sy[slot] = l.sy; sh.ex[slot] = l.ex; sh.ey[slot] = l.ey; sh.llen[slot] = l.length;
+        float lon, lat;
+        lane_local(l, x, y, lon, lat);
+        sh.olong[slot] = lon;
+      }
+      __syncwarp(group_mask);
+    }
   }
   PHASE_SYNC();
   if (stepping) {
@@ -612,15 +619,23 @@ pgd_step_kernel(DevTables T, DevState S, PgdConfig cfg, int mode, int env_begin,
           if (kind == PGD_BOX_LANE) {
             const float dx = vx - g0.x, dy = vy - g0.y;
             if (!(fabsf(dx * g0.z + dy * g0.w) <= g1.x && fabsf(-dx * g0.w + dy * g0.z) <= g1.y)) continue;
-            const Lane l = load_lane(lanes + __float_as_int(g1.w));
-            float lon, lat;
-            lane_local(l, vx, vy, lon, lat);
-            float ls, lc;
-            SINCOS(lane_heading_at(l, lon), ls, lc);
-            if (!(lc * vc + ls * vs > 0.0f)) continue;
+            // keep lanes whose direction at the vehicle makes an acute angle with its heading (scene_utils.py:158-170).
+            // The lane direction needs no trigonometry: a straight lane's is its unit vector, an arc's is the tangent
+            // dir * (-dy, dx) / r at the vehicle's bearing from the centre (r > 0 does not change the sign).
+            const float4* lq = reinterpret_cast<const float4*>(lanes + __float_as_int(g1.w));
+            const float4 lb = __ldg(lq + 1);                                  // ax, ay, length, width
+            const int4 ld = __ldg(reinterpret_cast<const int4*>(lq + 3));     // road, idx, kind, pad
+            float dot;
+            if (ld.z == PGD_LANE_STRAIGHT) {
+              dot = lb.x * vc + lb.y * vs;
+            } else {
+              const float ldir = __ldg(reinterpret_cast<const float*>(lq + 2) + 2);
+              dot = ldir * ((vx - lb.x) * vs - (vy - lb.y) * vc);
+            }
+            if (!(dot > 0.0f)) continue;
             b_any = min(b_any, b);
-            if (l.road == cur_road) b_cur = min(b_cur, b);
-            if (l.road == next_road) b_next = min(b_next, b);
+            if (ld.x == cur_road) b_cur = min(b_cur, b);
+            if (ld.x == next_road) b_next = min(b_next, b);
           } else if (t == 0) {
             const Rect r = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y};
             if (!rect_overlap(er, r)) continue;
@@ -671,9 +686,9 @@ pgd_step_kernel(DevTables T, DevState S, PgdConfig cfg, int mode, int env_begin,
   // Staged row; copied to obs[env] at the end of phase F.  Layout (obs/state_obs.py): [side beams | left, right],
   // 6 state values, [lane-line beams], 10 navi, 16 neighbours, 240 lidar.  `ob` is positioned so that the indices of
   // the detector-less layout (state 2..7, navi 8..17, neighbours 18..33, lidar 34..) address the tail of the row.
-  float* const row = reinterpret_cast<float*>(sh.obs2);
   const int n_first = cfg.n_side > 0 ? cfg.n_side : 2;
   const int obs_dim = n_first + 6 + cfg.n_lane_line + 10 + 16 + PGD_LIDAR_BEAMS;
+  float* const row = obs_rows + env_in_cta * obs_dim;
   float* const st = row + n_first - 2;                   // st[2..7]  = state values
   float* const ob = row + n_first + cfg.n_lane_line - 2;  // ob[8..]   = navi, neighbours, lidar
   // lidar: beam i = slot + V * k.  Each chassis first publishes the (conservative) arc of beams that can reach it:
@@ -951,14 +966,28 @@ pgd_step_kernel(DevTables T, DevState S, PgdConfig cfg, int mode, int env_begin,
     }
   }
 
-  // stream the staged observation row out: 137 x 8 B per environment, consecutive threads -> consecutive addresses
-  // (full 32 B sectors whether the destination is local HBM or a peer-mapped gather buffer on another GPU)
-  __syncwarp(group_mask);
-  if (!skip) {
+  // Write the staged rows out.  Full CTA (every environment valid and stepped, 16-byte aligned destination): one
+  // elected thread issues a single cp.async.bulk of ENVS_PER_CTA rows (8 768 B at V = 16) -- the destination may be
+  // local HBM or a peer-mapped gather buffer on another GPU.  Otherwise each group streams its own row with
+  // coalesced 8-byte stores.
+  const size_t cta_row0 = (size_t)(env_begin + blockIdx.x * ENVS_PER_CTA) * obs_dim;
+  const unsigned cta_bytes = (unsigned)(ENVS_PER_CTA * obs_dim * sizeof(float));
+  const bool bulk_possible = (cta_bytes % 16u) == 0 && ((reinterpret_cast<uintptr_t>(obs + cta_row0)) & 15u) == 0;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the bulk copy
+  const bool bulk = __syncthreads_and(env_valid && !skip && bulk_possible);
+  if (bulk) {
+    if (threadIdx.x == 0) {
+      const unsigned src = (unsigned)__cvta_generic_to_shared(obs_rows);
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                   :: "l"(obs + cta_row0), "r"(src), "r"(cta_bytes) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  } else if (!skip) {
     if ((obs_dim & 1) == 0) {
       float2* dst = reinterpret_cast<float2*>(obs + (size_t)env * obs_dim);
+      const float2* src2 = reinterpret_cast<const float2*>(row);
 #pragma unroll 3
-      for (int k = slot; k < obs_dim / 2; k += V) dst[k] = sh.obs2[k];
+      for (int k = slot; k < obs_dim / 2; k += V) dst[k] = src2[k];
     } else {  // odd row length: rows are only 4-byte aligned
       float* dst = obs + (size_t)env * obs_dim;
       for (int k = slot; k < obs_dim; k += V) dst[k] = row[k];
@@ -974,6 +1003,7 @@ pgd_step_kernel(DevTables T, DevState S, PgdConfig cfg, int mode, int env_begin,
     S.nav[gi] = make_int4(lane, ck0 | (ck1 << 16), rt_lane, timer);
     S.misc[gi] = make_int4(rnd_n, airborne, vflags, 0);
   }
+  if (bulk && threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 // marks environments for a forced reset on the given episode templates
