@@ -353,6 +353,35 @@ def run_own(args):
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get("bytes_per_launch")
 
+    # ---- the reset path: maps + episode templates of the workload's seeds generated ON the device (one warp per
+    # seed; pgd_generate_tables) beside the host Python path (bounded sample of seeds, one process)
+    reset_path = None
+    if world == 1:
+        try:
+            from pgdrive_b200 import devgen
+            from pgdrive_b200.env import _seed_tables, default_config, parse_map_config
+            mc = parse_map_config(default_config())
+            gc = devgen.make_gen_config(mc, 0.1)
+            first, count = WORKLOADS[args.workload][0], WORKLOADS[args.workload][1]
+            seeds = list(range(first, first + count))
+            devgen.generate(env.engine, seeds[:4], gc)  # warm-up: module load, local-memory allocation
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            devgen.generate(env.engine, seeds, gc)
+            torch.cuda.synchronize()
+            dev_s = time.perf_counter() - t0
+            k = min(len(seeds), 20)
+            t0 = time.perf_counter()
+            for sd in seeds[:k]:
+                _seed_tables((sd, mc, 0.1, ((">", ">>", 0), 5.0, 0.0)))
+            host_rate = k / (time.perf_counter() - t0)
+            reset_path = dict(seeds=len(seeds), device_maps_per_s=len(seeds) / dev_s, device_ms=dev_s * 1e3,
+                              host_python_maps_per_s=host_rate, host_sample="%d seeds, 1 process" % k)
+            env.engine.load(T)  # back to the reference-pinned host tables for the legs below
+            env.reset()
+        except Exception as e:  # the headline must not depend on this leg
+            reset_path = dict(error=str(e)[:200])
+
     cpu = None
     if world == 1 and not args.no_cpu:
         threads = host_threads()
@@ -381,6 +410,7 @@ def run_own(args):
         roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
                       kernel="pgd_step_kernel<%d>" % n_slots, kernel_ms=kernel_ms, bytes_per_env_step=b_step, peak_source=peak_src),
         cpu_baseline=cpu,
+        reset_path=reset_path,
         e2e=dict(value=total_envs * e2e_steps / (e2e_ms * 1e-3), unit="env-steps/s",
                  h2d_bytes_per_step=n * 8, d2h_bytes_per_step=n * (4 * OBS_DIM + 4 + 1 + INFO_BYTES),
                  steps=e2e_steps, api="VecPGDriveEnv.step(numpy) -> pgd_step_host", checksum=checksum),
