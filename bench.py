@@ -9,7 +9,8 @@ Own arm: every rank steps `--envs` (default 65 536) PGDrive-v0 environments (see
 (5 physics sub-steps + observation + reward/done, auto-reset of finished episodes).  Weak scaling: with N ranks
 the job simulates N x 65 536 environments and every step rank 0 receives the whole observation / reward / done
 batch (--gather: peer = stored by the step kernel straight into rank 0's HBM over NVLink, nccl = in-place
-all-gather overlapped with the next step's kernel, auto = peer at 2 GPUs, nccl beyond).
+all-gather overlapped with the next step's kernel, auto = peer, falling back to nccl when peer mapping is not
+permitted).
   value      device-resident: actions pre-generated in HBM, CUDA-event time of K steps, max over ranks
   e2e        same steps through the public VecPGDriveEnv.step(numpy) -> pgd_step_host: pinned H2D of the actions
              and D2H of obs / reward / done / info inside the timed region
@@ -211,7 +212,7 @@ def run_own(args):
     if world > 1:
         gather_mode = args.gather
         if gather_mode == "auto":
-            gather_mode = "peer" if world == 2 else "nccl"
+            gather_mode = "peer"  # bulk (TMA) row stores into rank 0 beat the NCCL all-gather at 2 and at 8 GPUs
         if gather_mode == "peer":
             from pgdrive_b200.sharding import PeerGather
             ok = torch.ones(1, dtype=torch.int32, device=dev)

@@ -1130,8 +1130,12 @@ static int launch_step(PgdHandle* h, int mode, int env_begin, int env_end, const
                                                           (const float2*)actions, obs, reward, done, info)
   if (V == 16 && !det) PGD_LAUNCH(16, PGD_OBS_DIM);
   else if (V == 32 && !det) PGD_LAUNCH(32, PGD_OBS_DIM);
+#if CTA_THREADS <= 128
   else if (V == 16) PGD_LAUNCH(16, PGD_OBS_CAP_DET);
   else PGD_LAUNCH(32, PGD_OBS_CAP_DET);
+#else  // experiment builds with larger CTAs: the detector rows do not fit static shared memory
+  else return fail(-3, "this build has no side / lane-line detector kernels");
+#endif
 #undef PGD_LAUNCH
   if (h->timing && mode == 0) cudaEventRecord(h->ev1, st);
   h->launches++;
