@@ -95,22 +95,32 @@ PGD_HD inline void dd_sincos(double x, dd* s_out, dd* c_out) {
   r = quick_two_sum(r.hi, r.lo);
   r = dd_sub(r, two_prod(kf, PGD_PIO2_2));
   r = dd_sub(r, two_prod(kf, PGD_PIO2_3));
-  // Taylor series on |r| <= pi/4 (+ a little)
-  dd r2 = dd_mul(r, r);
-  dd term = r;  // sine terms: r^(2k+1)/(2k+1)!
-  dd s = r;
-  for (int k = 1; k <= 14; ++k) {
-    term = dd_div_d(dd_mul(term, r2), (double)((2 * k) * (2 * k + 1)));
-    term = dd_neg(term);
-    s = dd_add(s, term);
+  // Taylor series on |r| <= pi/4 (+ a little), Horner form in r^2 with the signed inverse factorials as
+  // double-double constants: 14 terms leave < 2^-106
+  const double SC[14][2] = {
+      {-0.16666666666666666, -9.25185853854297e-18},   {0.008333333333333333, 1.1564823173178714e-19},
+      {-0.0001984126984126984, -1.7209558293420705e-22}, {2.7557319223985893e-06, -1.858393274046472e-22},
+      {-2.505210838544172e-08, 1.448814070935912e-24},  {1.6059043836821613e-10, 1.2585294588752098e-26},
+      {-7.647163731819816e-13, -7.03872877733453e-30},  {2.8114572543455206e-15, 1.6508842730861433e-31},
+      {-8.22063524662433e-18, -2.2141894119604265e-34}, {1.9572941063391263e-20, -1.3643503830087908e-36},
+      {-3.868170170630684e-23, 8.843177655482344e-40},  {6.446950284384474e-26, -1.9330404233703465e-42},
+      {-9.183689863795546e-29, -1.4303150396787322e-45}, {1.1309962886447716e-31, 1.0498015412959506e-47}};
+  const double CC[14][2] = {
+      {-0.5, 0.0},                                      {0.041666666666666664, 2.3129646346357427e-18},
+      {-0.001388888888888889, 5.300543954373577e-20},   {2.48015873015873e-05, 2.1511947866775882e-23},
+      {-2.755731922398589e-07, -2.3767714622250297e-23}, {2.08767569878681e-09, -1.20734505911326e-25},
+      {-1.1470745597729725e-11, -2.0655512752830745e-28}, {4.779477332387385e-14, 4.399205485834081e-31},
+      {-1.5619206968586225e-16, -1.1910679660273754e-32}, {4.110317623312165e-19, 1.4412973378659527e-36},
+      {-8.896791392450574e-22, 7.911402614872376e-38},  {1.6117375710961184e-24, -3.6846573564509766e-41},
+      {-2.4795962632247976e-27, 1.2953730964765229e-43}, {3.279889237069838e-30, 1.5117542744029879e-46}};
+  const dd r2 = dd_mul(r, r);
+  dd ps = dd{SC[13][0], SC[13][1]}, pc = dd{CC[13][0], CC[13][1]};
+  for (int k = 12; k >= 0; --k) {
+    ps = dd_add(dd_mul(ps, r2), dd{SC[k][0], SC[k][1]});
+    pc = dd_add(dd_mul(pc, r2), dd{CC[k][0], CC[k][1]});
   }
-  dd c = dd{1.0, 0.0};
-  term = dd{1.0, 0.0};
-  for (int k = 1; k <= 14; ++k) {
-    term = dd_div_d(dd_mul(term, r2), (double)((2 * k - 1) * (2 * k)));
-    term = dd_neg(term);
-    c = dd_add(c, term);
-  }
+  const dd s = dd_add(r, dd_mul(dd_mul(ps, r2), r));   // r + r^3 * (...)
+  const dd c = dd_add_d(dd_mul(pc, r2), 1.0);          // 1 + r^2 * (...)
   long long q = (long long)kf;
   switch (q & 3) {
     case 0: *s_out = s; *c_out = c; break;

@@ -112,23 +112,19 @@ PGD_HD inline void mt_init_by_array(MT* s, const uint32_t* key, int len) {
   s->pos = 624;
 }
 
+/* One output.  The twist is done one word at a time, in place and in order, which yields the same sequence as the
+ * textbook block regeneration (word k only needs the OLD words k + 1 and k + 397, both still untouched when k is
+ * produced; past 227 it needs NEW words that are already there) -- most of the reference's streams are seeded, asked
+ * for one or two numbers and dropped. */
 PGD_HD inline uint32_t mt_next(MT* s) {
-  if (s->pos >= 624) {
-    uint32_t* mt = s->mt;
-    int kk;
-    for (kk = 0; kk < 624 - 397; ++kk) {
-      uint32_t y = (mt[kk] & 0x80000000U) | (mt[kk + 1] & 0x7fffffffU);
-      mt[kk] = mt[kk + 397] ^ (y >> 1) ^ ((y & 1U) ? 0x9908b0dfU : 0U);
-    }
-    for (; kk < 623; ++kk) {
-      uint32_t y = (mt[kk] & 0x80000000U) | (mt[kk + 1] & 0x7fffffffU);
-      mt[kk] = mt[kk + (397 - 624)] ^ (y >> 1) ^ ((y & 1U) ? 0x9908b0dfU : 0U);
-    }
-    uint32_t y = (mt[623] & 0x80000000U) | (mt[0] & 0x7fffffffU);
-    mt[623] = mt[396] ^ (y >> 1) ^ ((y & 1U) ? 0x9908b0dfU : 0U);
-    s->pos = 0;
-  }
-  uint32_t y = s->mt[s->pos++];
+  if (s->pos >= 624) s->pos = 0;  // a new block of 624 starts
+  const int k = s->pos++;
+  uint32_t* mt = s->mt;
+  const int k1 = (k == 623) ? 0 : k + 1;
+  const int km = (k < 227) ? k + 397 : k - 227;
+  uint32_t y = (mt[k] & 0x80000000U) | (mt[k1] & 0x7fffffffU);
+  y = mt[km] ^ (y >> 1) ^ ((y & 1U) ? 0x9908b0dfU : 0U);
+  mt[k] = y;
   y ^= (y >> 11);
   y ^= (y << 7) & 0x9d2c5680U;
   y ^= (y << 15) & 0xefc60000U;

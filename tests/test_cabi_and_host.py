@@ -45,6 +45,23 @@ def test_struct_sizes_match_header():
     assert got == want
 
 
+def test_generator_struct_sizes_match_header():
+    from pgdrive_b200 import devgen
+    src = r"""
+    #include <stdio.h>
+    #include <stddef.h>
+    #include "include/pgdrive_b200.h"
+    int main(void){ printf("%zu %zu %zu %zu\n", sizeof(PgdGenConfig), sizeof(PgdGenCaps),
+      offsetof(PgdGenConfig, lane_width), offsetof(PgdGenConfig, fixed_types)); return 0; }
+    """
+    exe = os.path.join(ROOT, "oracle", "_build", "gen_sizes")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    subprocess.run(["gcc", "-x", "c", "-", "-I", ROOT, "-o", exe], input=src.encode(), check=True, cwd=ROOT)
+    got = [int(x) for x in subprocess.check_output([exe]).split()]
+    assert got == [ctypes.sizeof(devgen.GenConfig), ctypes.sizeof(devgen.GenCaps), devgen.GenConfig.lane_width.offset,
+                   devgen.GenConfig.fixed_types.offset]
+
+
 def test_config_rejects_unknown_keys_like_the_reference():
     from pgdrive_b200 import PGDriveEnv
     from pgdrive_b200.config import default_config
