@@ -203,8 +203,7 @@ def default_config():
 # value and rejected otherwise, so that a config that silently changed behaviour cannot slip through.
 UNSUPPORTED_IF_CHANGED = {
     "num_agents": 1, "is_multi_agent": False, "random_agent_model": False, "IDM_agent": False,
-    "use_render": False, "manual_control": False, "random_lane_width": False,
-    "random_lane_num": False, "use_topdown": False, "offscreen_render": False, "traffic_mode": "trigger",
+    "use_render": False, "manual_control": False, "use_topdown": False, "offscreen_render": False, "traffic_mode": "trigger",
     "random_traffic": False, "accident_prob": 0., "auto_termination": False, "gaussian_noise": 0.0,
     "dropout_prob": 0.0, "record_episode": False,
 }
@@ -214,6 +213,9 @@ def check_supported(cfg):
     for k, v in UNSUPPORTED_IF_CHANGED.items():
         if cfg[k] != v:
             raise NotImplementedError("config[%r]=%r is not supported by the batched simulator (only %r)" % (k, cfg[k], v))
+    if (cfg["random_lane_width"] or cfg["random_lane_num"]) and cfg["load_map_from_json"]:
+        # manager/map_manager.py:158-166
+        raise AssertionError("You are supposed to turn off the load_map_from_json")
     vc = cfg["vehicle_config"]
     lid = vc["lidar"]
     if (lid["num_lasers"], lid["distance"], lid["num_others"]) != (240, 50, 4):

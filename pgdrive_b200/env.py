@@ -75,6 +75,22 @@ def discrete_to_continuous(actions, cfg):
     return (a * a.new_tensor([su, tu]) - 1.0).contiguous()
 
 
+def seed_map_config(mc, seed, random_lane_width=False, random_lane_num=False):
+    """MapManager.add_random_to_map (manager/map_manager.py:157-169) on the stream MapManager.seed(current_seed) sets
+    up (engine/base_engine.py:300-304): lane width = rand() * (4.5 - 3.0) + 3.0, then lane number =
+    randint(MIN_LANE_NUM=2, MAX_LANE_NUM=3) -- literally, i.e. always 2 (component/map/pg_map.py:13-16)."""
+    if not (random_lane_width or random_lane_num):
+        return mc
+    from . import rng
+    rs = rng.seeded(int(seed))
+    out = dict(mc)
+    if random_lane_width:
+        out["lane_width"] = float(rs.rand() * (4.5 - 3.0) + 3.0)
+    if random_lane_num:
+        out["lane_num"] = int(rs.randint(2, 3))
+    return out
+
+
 def _seed_tables(args):
     seed, mc, density, spawn = args[:4]
     stored = args[4] if len(args) > 4 else None
@@ -153,12 +169,12 @@ def dump_maps(seeds, map_config):
     return dict(map_config=dict(map_config), map_data=out)
 
 
-def build_seed_tables(seeds, map_config, density, spawn, workers=None, stored=None):
+def build_seed_tables(seeds, map_config, density, spawn, workers=None, stored=None, random_lane=(False, False)):
     """Tables for a list of seeds, built in worker processes when there are many, with an optional
     on-disk cache ($PGDRIVE_B200_CACHE) because map search costs ~50 ms per seed.  ``stored`` = {seed: block
     sequence} restored from a map file."""
     seeds = [int(s) for s in seeds]
-    jobs = [(s, map_config, density, spawn, (stored or {}).get(s)) for s in seeds]
+    jobs = [(s, seed_map_config(map_config, s, *random_lane), density, spawn, (stored or {}).get(s)) for s in seeds]
     cache_dir = os.environ.get("PGDRIVE_B200_CACHE")
     path = None
     if cache_dir:
@@ -249,6 +265,9 @@ class VecPGDriveEnv:
         if cfg["load_map_from_json"] and cfg["_load_map_from_json"] is not None:
             stored = load_map_file(cfg["_load_map_from_json"], self.map_config, seeds)
         self._T = None
+        random_lane = (bool(cfg["random_lane_width"]), bool(cfg["random_lane_num"]))
+        if cfg["device_mapgen"] and any(random_lane):
+            raise NotImplementedError("device_mapgen generates every seed with one lane configuration")
         if cfg["device_mapgen"] and tables_dict is None and stored is None:
             # the whole reset path runs on the GPU (pgd_generate_tables); tables never visit the host
             gc = devgen.make_gen_config(self.map_config, cfg["traffic_density"], self._spawn)
@@ -268,7 +287,7 @@ class VecPGDriveEnv:
             self.episode_of_seed = {int(s): i for i, s in enumerate(seeds)}
         else:
             self._T = tables_dict if tables_dict is not None else build_seed_tables(
-                seeds, self.map_config, cfg["traffic_density"], self._spawn, stored=stored
+                seeds, self.map_config, cfg["traffic_density"], self._spawn, stored=stored, random_lane=random_lane
             )
             self.episode_of_seed = {int(s): i for i, s in enumerate(self._T["episodes"]["seed"])}
             need = int(self._T["max_slots"])
@@ -441,8 +460,8 @@ class PGDriveEnv:
     def _ensure_seed(self, seed):
         if seed in self._episode_of_seed:
             return
-        part = _seed_tables((seed, self.map_config, self.config["traffic_density"], self._spawn,
-                             (self._stored or {}).get(seed)))
+        mc = seed_map_config(self.map_config, seed, self.config["random_lane_width"], self.config["random_lane_num"])
+        part = _seed_tables((seed, mc, self.config["traffic_density"], self._spawn, (self._stored or {}).get(seed)))
         self._parts.append(part)
         self._episode_of_seed[seed] = len(self._parts) - 1
         T = merge_tables(self._parts)

@@ -173,3 +173,49 @@ def test_block_search_against_the_shipped_30000_map_file():
     assert not bad, "block sequences differ from the shipped file for seeds %s" % bad[:10]
     stored = load_map_file(data, parse_map_config(default_config()), range(1000, 1100))
     assert stored is not None and len(stored) == 30000
+
+
+def test_random_lane_width_and_number_match_reference():
+    """random_lane_width / random_lane_num (manager/map_manager.py:157-169): the per-seed lane configuration and the
+    map generated with it, against the reference's own add_random_to_map + live block search
+    (tests/golden/maps_random_lane.json.gz, tools/make_golden.py random_lane)."""
+    from conftest import load_golden
+    from pgdrive_b200.env import seed_map_config
+    base = dict(type="block_num", config=3, lane_width=3.5, lane_num=3, exit_length=50)
+    gold = load_golden("maps_random_lane.json.gz")
+    assert len(gold) >= 12
+    for s, rec in gold.items():
+        seed = int(s)
+        for name, flags in (("both", (True, True)), ("width", (True, False)), ("num", (False, True))):
+            mc = seed_map_config(base, seed, *flags)
+            assert mc["lane_width"] == rec[name]["lane_width"] and mc["lane_num"] == rec[name]["lane_num"], (s, name)
+        assert seed_map_config(base, seed) is base
+        mc = seed_map_config(base, seed, True, True)
+        m = mapgen.generate_map(seed, block_num=3, lane_num=mc["lane_num"], lane_width=mc["lane_width"])
+        assert [b["id"] for b in m.block_sequence] == [b["id"] for b in rec["block_sequence"]], s
+        mine = _lanes(m)
+        assert len(mine) == len(rec["lanes"]), s
+        for (f, t, i, ln), g in zip(mine, rec["lanes"]):
+            assert (f, t, i, ln.kind) == (g["frm"], g["to"], g["idx"], g["kind"]), s
+            assert [str(x) for x in ln.line_types] == g["line_types"], (s, f, t, i)
+            a = [ln.sx, ln.sy, ln.ex, ln.ey, ln.length, ln.width]
+            b = g["start"] + g["end"] + [g["length"], g["width"]]
+            if ln.kind == "C":
+                a += [ln.cx, ln.cy, ln.radius, ln.ph0, ln.ph1, ln.dir]
+                b += g["center"] + [g["radius"], g["start_phase"], g["end_phase"], g["direction"]]
+            assert [float(x) for x in a] == [float(x) for x in b], (s, f, t, i)
+        # the simulator drives on the search-time map with these options: sockets and spawn roads must agree too
+        for b, g in zip(m.blocks, rec["blocks"]):
+            socks = [dict(index=x.index, pos=list(x.pos), neg=list(x.neg)) for x in b.sockets.values()]
+            assert socks == g["sockets"], (s, b.name)
+            assert [list(r) for r in b.respawn] == g["respawn_roads"], (s, b.name)
+
+
+def test_random_lane_options_need_live_map_generation():
+    from pgdrive_b200.config import check_supported, default_config
+    cfg = default_config()
+    cfg.update(dict(random_lane_width=True))
+    with pytest.raises(AssertionError):
+        check_supported(cfg)
+    cfg.update(dict(load_map_from_json=False))
+    check_supported(cfg)

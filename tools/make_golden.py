@@ -919,3 +919,64 @@ if __name__ == "__main__" and sys.argv[1] == "detectors":
 
 if __name__ == "__main__" and sys.argv[1] == "primitives":
     cmd_primitives("v0")
+
+
+# ---------------------------------------------------------------------------------------------
+def cmd_random_lane(seeds, tag):
+    """random_lane_width / random_lane_num (manager/map_manager.py:157-169): the reference's own add_random_to_map on
+    a stream seeded like MapManager.seed(current_seed) (engine/base_engine.py:300-304, base_class/randomizable.py:16-18),
+    then the LIVE block search with that lane configuration (load_map_from_json must be off with these options, so
+    the simulator drives on the search-time map, pg_map.py:34-46)."""
+    from pgdrive.manager.map_manager import MapManager
+
+    class _Eng:
+        def __init__(self, flags):
+            self.global_config = flags
+
+    class _Self:
+        pass
+
+    out = {}
+    for s in seeds:
+        rec = {}
+        for name, flags in (("both", dict(random_lane_width=True, random_lane_num=True)),
+                            ("width", dict(random_lane_width=True, random_lane_num=False)),
+                            ("num", dict(random_lane_width=False, random_lane_num=True))):
+            me = _Self()
+            me.engine = _Eng(dict(flags, load_map_from_json=False))
+            me.np_random = get_np_random(s)
+            cfg = dict(MAP_CONFIG)
+            cfg["seed"] = s
+            cfg = MapManager.add_random_to_map(me, cfg)
+            rec[name] = dict(lane_width=float(cfg["lane_width"]), lane_num=int(cfg["lane_num"]))
+            if name != "both":
+                continue
+            make_engine(s)
+            m = PGMap(map_config=dict(cfg), random_seed=None)
+            lanes = []
+            for frm, td in m.road_network.graph.items():
+                for to, ls in td.items():
+                    for i, l in enumerate(ls):
+                        lanes.append(lane_record(frm, to, i, l))
+            blocks = []
+            for b in m.blocks:
+                blocks.append(dict(
+                    id=b.ID, name=b.name,
+                    sockets=[dict(index=k.index, pos=[k.positive_road.start_node, k.positive_road.end_node],
+                                  neg=[k.negative_road.start_node, k.negative_road.end_node])
+                             for k in b.get_socket_list()],
+                    respawn_roads=[[r.start_node, r.end_node] for r in b.get_respawn_roads()],
+                    spawn_lanes=[[find_index(m, l) for l in ls] for ls in b.get_intermediate_spawn_lanes()]
+                    if b.block_index != 0 else [],
+                ))
+            rec["lanes"], rec["blocks"] = lanes, blocks
+            rec["block_sequence"] = json.loads(json.dumps(m.save_map()["block_sequence"]))
+        out[str(s)] = rec
+    path = os.path.join(GOLD, "maps_%s.json.gz" % tag)
+    with gzip.open(path, "wt") as f:
+        json.dump(out, f)
+    print("wrote", path, os.path.getsize(path))
+
+
+if __name__ == "__main__" and sys.argv[1] == "random_lane":
+    cmd_random_lane(list(range(1000, 1012)) + [5, 77, 2500], "random_lane")
