@@ -204,7 +204,7 @@ def default_config():
 UNSUPPORTED_IF_CHANGED = {
     "num_agents": 1, "is_multi_agent": False, "random_agent_model": False, "IDM_agent": False,
     "use_render": False, "manual_control": False, "use_topdown": False, "offscreen_render": False, "traffic_mode": "trigger",
-    "random_traffic": False, "accident_prob": 0., "auto_termination": False, "gaussian_noise": 0.0,
+    "random_traffic": False, "accident_prob": 0., "gaussian_noise": 0.0,
     "dropout_prob": 0.0, "record_episode": False,
 }
 

@@ -55,6 +55,24 @@ def parse_map_config(cfg):
     return mc
 
 
+def effective_horizon(cfg, map_config):
+    """Step limit handed to the kernel: ``horizon`` (base_env.py:190-192) and, with ``auto_termination``, the
+    reference's 250 steps per block including the first one (base_env.py:318-326); both end the episode with
+    ``max_step`` set, so the smaller one decides.  Every map of an environment has the same number of blocks."""
+    limits = []
+    if cfg["horizon"]:
+        limits.append(int(cfg["horizon"]))
+    if cfg["auto_termination"]:
+        if map_config["type"] == "block_num":
+            n_blocks = int(map_config["config"]) + 1
+        elif map_config["type"] == "block_sequence":
+            n_blocks = len(str(map_config["config"])) + 1
+        else:
+            raise ValueError("Map can not be created by {}".format(map_config["type"]))
+        limits.append(250 * n_blocks)
+    return min(limits) if limits else 0
+
+
 def make_action_space(cfg):
     """base_vehicle.py:721-727."""
     if cfg["discrete_action"]:
@@ -204,14 +222,14 @@ def build_seed_tables(seeds, map_config, density, spawn, workers=None, stored=No
 
 class _Engine:
     """One C-ABI handle + its loaded tables."""
-    def __init__(self, cfg, num_envs, num_slots, device, auto_reset):
+    def __init__(self, cfg, num_envs, num_slots, device, auto_reset, horizon=None):
         import torch
         if not torch.cuda.is_available():
             raise RuntimeError("pgdrive_b200 needs a CUDA device (there is no CPU fallback)")
         self.torch = torch
         self.lib = cabi.load_library()
         self.device = torch.device("cuda", device)
-        horizon = cfg["horizon"] or 0
+        horizon = (cfg["horizon"] or 0) if horizon is None else horizon
         self.pcfg = cabi.make_config(
             num_envs, num_slots, cfg["decision_repeat"], horizon, cfg["physics_world_step_size"],
             cfg["success_reward"], cfg["out_of_road_penalty"], cfg["crash_vehicle_penalty"], cfg["driving_reward"],
@@ -273,7 +291,8 @@ class VecPGDriveEnv:
             gc = devgen.make_gen_config(self.map_config, cfg["traffic_density"], self._spawn)
             slots = cfg["num_slots"] or 16
             while True:
-                self.engine = _Engine(cfg, self.num_envs, slots, int(cfg["device"]), bool(cfg["auto_reset"]))
+                self.engine = _Engine(cfg, self.num_envs, slots, int(cfg["device"]), bool(cfg["auto_reset"]),
+                                      effective_horizon(cfg, self.map_config))
                 try:
                     devgen.generate(self.engine, seeds, gc)
                     break
@@ -294,7 +313,8 @@ class VecPGDriveEnv:
             slots = cfg["num_slots"] or (16 if need <= 16 else 32)
             if need > slots:
                 raise ValueError("the loaded seeds need %d vehicle slots; num_slots=%d" % (need, slots))
-            self.engine = _Engine(cfg, self.num_envs, slots, int(cfg["device"]), bool(cfg["auto_reset"]))
+            self.engine = _Engine(cfg, self.num_envs, slots, int(cfg["device"]), bool(cfg["auto_reset"]),
+                                      effective_horizon(cfg, self.map_config))
             self.engine.load(self._T)
         torch = self.engine.torch
         dev = self.engine.device
@@ -471,7 +491,8 @@ class PGDriveEnv:
             self._engine.close()
             self._engine = None
         if self._engine is None:
-            self._engine = _Engine(self.config, 1, slots, int(os.environ.get("PGDRIVE_B200_DEVICE", 0)), False)
+            self._engine = _Engine(self.config, 1, slots, int(os.environ.get("PGDRIVE_B200_DEVICE", 0)), False,
+                                   effective_horizon(self.config, self.map_config))
             torch = self._engine.torch
             dev = self._engine.device
             self._obs = torch.empty((1, self.obs_dim), dtype=torch.float32, device=dev)

@@ -207,3 +207,21 @@ def test_discrete_actions_follow_the_reference_conversion():
     np.testing.assert_allclose(got, [[-1, -1], [-0.5, -0.5], [-0.5, -0.5], [-0.5, -0.5]])
     env7 = PGDriveEnv(dict(discrete_action=True, discrete_steering_dim=3, discrete_throttle_dim=9))
     np.testing.assert_allclose(discrete_to_continuous(np.array([1, 1]), env7.config), [0.0, -0.75])
+
+
+def test_effective_horizon_combines_horizon_and_auto_termination():
+    """base_env.py:190-192 (horizon) and :318-326 (auto_termination: 250 steps per block, first block included)."""
+    from pgdrive_b200.config import check_supported, default_config
+    from pgdrive_b200.env import effective_horizon, parse_map_config
+    cfg = default_config()
+    mc = parse_map_config(cfg)
+    assert effective_horizon(cfg, mc) == 0
+    cfg.update(dict(auto_termination=True))
+    check_supported(cfg)
+    assert effective_horizon(cfg, mc) == 1000  # map = 3 blocks + the first block
+    cfg.update(dict(horizon=300))
+    assert effective_horizon(cfg, mc) == 300
+    cfg.update(dict(horizon=5000, map="SCrRX"))
+    assert effective_horizon(cfg, parse_map_config(cfg)) == 1500
+    cfg.update(dict(auto_termination=False))
+    assert effective_horizon(cfg, parse_map_config(cfg)) == 5000
