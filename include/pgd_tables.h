@@ -117,7 +117,9 @@ typedef struct {
    * i * 2pi / n + 90 degrees from the heading */
   int32_t n_side, n_lane_line;
   float side_distance, lane_line_distance;
-  int32_t pad;
+  /* 0 (default): cooperative kernel, 16 / 32 threads per environment, state [env][slot];
+   * 1 (experimental): one thread per environment, state [slot][env] (pgd_step_v2.cu) */
+  int32_t layout;
 } PgdConfig;
 
 /* Observation length (obs/state_obs.py:18-23,108-115,125-130): (n_side or 2) + 6 + n_lane_line + 10 + 16 + 240. */

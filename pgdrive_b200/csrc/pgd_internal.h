@@ -74,4 +74,7 @@ struct PgdHandle {
   cudaEvent_t ev0, ev1;
 };
 
+// pgd_step_v2.cu: one thread per environment (PgdConfig.layout == 1)
+int pgd_launch_step_v2(PgdHandle* h, int mode, int env_begin, int env_end, const float* actions, float* obs,
+                       float* reward, uint8_t* done, PgdInfo* info, cudaStream_t st);
 #endif

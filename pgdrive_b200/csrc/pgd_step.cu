@@ -1030,6 +1030,7 @@ extern "C" int pgd_create(const PgdConfig* cfg, int device, PgdHandle** out) {
   if (!cfg || !out) return fail(-1, "pgd_create: null argument");
   if (cfg->num_envs <= 0) return fail(-1, "pgd_create: num_envs must be positive");
   if (cfg->num_slots != 16 && cfg->num_slots != 32) return fail(-1, "pgd_create: num_slots must be 16 or 32");
+  if (cfg->layout != 0 && cfg->layout != 1) return fail(-1, "pgd_create: layout must be 0 or 1");
   if (cfg->n_side < 0 || cfg->n_side > PGD_MAX_DETECTOR_BEAMS || cfg->n_lane_line < 0 ||
       cfg->n_lane_line > PGD_MAX_DETECTOR_BEAMS)
     return fail(-1, "pgd_create: detector beam counts must be in [0, 240]");
@@ -1120,6 +1121,7 @@ extern "C" int pgd_load_tables(PgdHandle* h, const PgdTables* t) {
 
 static int launch_step(PgdHandle* h, int mode, int env_begin, int env_end, const float* actions, float* obs,
                        float* reward, uint8_t* done, PgdInfo* info, cudaStream_t st) {
+  if (h->cfg.layout == 1) return pgd_launch_step_v2(h, mode, env_begin, env_end, actions, obs, reward, done, info, st);
   const int V = h->cfg.num_slots;
   const int envs_per_cta = CTA_THREADS / V;
   const int grid = (env_end - env_begin + envs_per_cta - 1) / envs_per_cta;
@@ -1257,6 +1259,7 @@ extern "C" int pgd_step_host(PgdHandle* h, const float* actions, float* obs, flo
 extern "C" int pgd_get_state(PgdHandle* h, int32_t env, PgdEnvState* out) {
   if (!h || !out) return fail(-1, "pgd_get_state: null argument");
   if (env < 0 || env >= h->cfg.num_envs) return fail(-1, "pgd_get_state: env out of range");
+  if (h->cfg.layout != 0) return fail(-3, "pgd_get_state: not available with the one-thread-per-environment layout");
   CU(cudaSetDevice(h->device));
   CU(cudaDeviceSynchronize());
   const int V = h->cfg.num_slots;
@@ -1286,6 +1289,7 @@ extern "C" int pgd_get_state(PgdHandle* h, int32_t env, PgdEnvState* out) {
 extern "C" int pgd_set_state(PgdHandle* h, int32_t env, const PgdEnvState* in) {
   if (!h || !in) return fail(-1, "pgd_set_state: null argument");
   if (env < 0 || env >= h->cfg.num_envs) return fail(-1, "pgd_set_state: env out of range");
+  if (h->cfg.layout != 0) return fail(-3, "pgd_set_state: not available with the one-thread-per-environment layout");
   if (in->episode < 0 || in->episode >= h->n_episodes) return fail(-1, "pgd_set_state: episode out of range");
   CU(cudaSetDevice(h->device));
   CU(cudaDeviceSynchronize());

@@ -238,7 +238,8 @@ class _Engine:
             n_side=cfg["vehicle_config"]["side_detector"]["num_lasers"],
             side_distance=cfg["vehicle_config"]["side_detector"]["distance"],
             n_lane_line=cfg["vehicle_config"]["lane_line_detector"]["num_lasers"],
-            lane_line_distance=cfg["vehicle_config"]["lane_line_detector"]["distance"]
+            lane_line_distance=cfg["vehicle_config"]["lane_line_detector"]["distance"],
+            layout=1 if cfg.get("one_thread_per_env", False) else 0
         )
         self.obs_dim = cabi.obs_dim(self.pcfg)
         self.h = C.c_void_p()

@@ -1,0 +1,103 @@
+"""The one-thread-per-environment step (pgdrive_b200/csrc/pgd_step_v2.cuh), HOST build, against the independent CPU
+oracle (oracle/pgd_oracle.c).  Both are float32 on glibc and the step function keeps the cooperative kernel's
+expressions, so the bar here is bit-identical observations, rewards, done flags and info records over free-running
+rollouts -- stricter than the GPU tests' 1e-3, and runnable without a GPU."""
+import numpy as np
+import pytest
+
+V0 = dict(type="block_num", config=3, lane_num=3, lane_width=3.5, exit_length=50)
+SPAWN = ((">", ">>", 0), 5.0, 0.0)
+
+
+def _tables(seeds, density=0.1):
+    from pgdrive_b200 import env as E
+    return E.merge_tables([E._seed_tables((s, V0, density, SPAWN)) for s in seeds])
+
+
+def _pair(T, n, **cfg):
+    from oracle.oracle import Oracle
+    from oracle.step_v2_host import HostStepV2
+    slots = 16 if T["max_slots"] <= 16 else 32
+    return Oracle(T, n, num_slots=slots, **cfg), HostStepV2(T, n, num_slots=slots, **cfg)
+
+
+def _actions(rs, n, mode):
+    a = rs.uniform(-1, 1, (n, 2)).astype(np.float32)
+    if mode == "forward":
+        a[:, 1] = np.abs(a[:, 1])
+        a[:, 0] *= 0.1
+    elif mode == "lane":
+        a[:, 0] = 0.0
+        a[:, 1] = 0.6
+    return a
+
+
+def _same(x, y):
+    o1, r1, d1, i1 = x
+    o2, r2, d2, i2 = y
+    return (np.array_equal(o1, o2) and np.array_equal(r1, r2) and np.array_equal(d1, d2)
+            and i1.tobytes() == i2.tobytes())
+
+
+@pytest.mark.parametrize("mode,n_seeds,n,steps,density", [
+    ("uniform", 30, 120, 150, 0.1),
+    ("forward", 30, 120, 300, 0.1),
+    ("lane", 50, 150, 300, 0.1),
+    ("lane", 12, 48, 300, 0.2),   # 32 vehicle slots
+])
+def test_free_running_rollouts_are_bit_identical(mode, n_seeds, n, steps, density):
+    T = _tables(range(1000, 1000 + n_seeds), density)
+    a, b = _pair(T, n, auto_reset=True)
+    eps = [i % n_seeds for i in range(n)]
+    assert np.array_equal(a.reset(range(n), eps), b.reset(range(n), eps))
+    rs = np.random.RandomState(3)
+    dones = 0
+    for t in range(steps):
+        act = _actions(rs, n, mode)
+        ra, rb = a.step(act), b.step(act)
+        assert _same(ra, rb), (mode, t)
+        dones += int(ra[2].sum())
+    assert dones > 0 or mode == "uniform"  # episodes ended and restarted inside the rollout
+    a.close()
+    b.close()
+
+
+def test_horizon_sticky_done_and_partial_reset():
+    T = _tables([1000, 1001, 1002])
+    a, b = _pair(T, 6, auto_reset=False, horizon=7)
+    eps = [0, 1, 2, 0, 1, 2]
+    a.reset(range(6), eps)
+    b.reset(range(6), eps)
+    rs = np.random.RandomState(0)
+    for t in range(12):
+        act = _actions(rs, 6, "forward")
+        if t == 3:
+            act[2] = np.nan  # NaN action -> -1 like the compiled cutils_clip
+        ra, rb = a.step(act), b.step(act)
+        assert _same(ra, rb), t
+        if t >= 6:
+            assert ra[2].all() and rb[2].all()  # max_step reached and done stays set without auto-reset
+    ia = a.reset([1, 4], [2, 0]).copy()
+    ib = b.reset([1, 4], [2, 0]).copy()
+    assert np.array_equal(ia[[1, 4]], ib[[1, 4]])
+    ra, rb = a.step(np.zeros((6, 2), np.float32)), b.step(np.zeros((6, 2), np.float32))
+    assert np.array_equal(ra[2], rb[2]) and np.array_equal(ra[0][[1, 4]], rb[0][[1, 4]])
+    assert not ra[2][1] and not ra[2][4] and ra[2][0]
+    a.close()
+    b.close()
+
+
+def test_reward_scheme_options():
+    T = _tables(range(1000, 1010))
+    cfg = dict(auto_reset=True, use_lateral=True, out_of_route_done=True, success_reward=20.0, driving_reward=2.0,
+               speed_reward=0.3, out_of_road_penalty=7.0, crash_vehicle_penalty=3.0, decision_repeat=3)
+    a, b = _pair(T, 40, **cfg)
+    eps = [i % 10 for i in range(40)]
+    a.reset(range(40), eps)
+    b.reset(range(40), eps)
+    rs = np.random.RandomState(5)
+    for t in range(200):
+        act = _actions(rs, 40, "forward")
+        assert _same(a.step(act), b.step(act)), t
+    a.close()
+    b.close()
