@@ -36,19 +36,25 @@ def build_cuda(force=False, verbose=False, out=OUT, defines=()):
     library.  ``defines`` (e.g. ["-DMIN_CTAS_PER_SM=5"]) builds a kernel variant into ``out``."""
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     tag = "".join(c if c.isalnum() else "_" for c in "".join(defines))
-    objs, log, relink = [], [], force or not os.path.exists(out)
+    objs, jobs, relink = [], [], force or not os.path.exists(out)
     for unit, extra in UNITS.items():
         src = os.path.join(CSRC, unit)
         utag = tag if unit == "pgd_step.cu" else ""  # variants only differ in the step kernel
         obj = os.path.join(CSRC, unit.replace(".cu", utag + ".o"))
         deps = [src] + [d if os.path.isabs(d) else os.path.join(CSRC, d) for d in COMMON + extra]
         if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(d) for d in deps):
-            text = _run([nvcc] + NVCC_FLAGS + (list(defines) if utag else []) + ["-c", "-o", obj, src], verbose)
-            with open(os.path.join(CSRC, unit.replace(".cu", utag + ".ptxas.log")), "w") as f:
-                f.write(text)
-            relink = True
-        relink = relink or os.path.getmtime(obj) > os.path.getmtime(out)
+            cmd = [nvcc] + NVCC_FLAGS + (list(defines) if utag else []) + ["-c", "-o", obj, src]
+            jobs.append((cmd, os.path.join(CSRC, unit.replace(".cu", utag + ".ptxas.log"))))
         objs.append(obj)
+    if jobs:  # the translation units compile side by side
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(len(jobs)) as pool:
+            texts = list(pool.map(lambda j: _run(j[0], verbose), jobs))
+        for (cmd, log_path), text in zip(jobs, texts):
+            with open(log_path, "w") as f:
+                f.write(text)
+        relink = True
+    relink = relink or any(os.path.getmtime(o) > os.path.getmtime(out) for o in objs)
     if relink:
         _run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out] + objs, verbose)
     return out
