@@ -15,8 +15,9 @@
 using namespace pgdv2;
 
 #define V2_CTA_THREADS 64
+#define V2_OBS_CAP_DET (2 * PGD_MAX_DETECTOR_BEAMS + 6 + 10 + 16 + PGD_LIDAR_BEAMS) /* 752 */
 
-template <int V>
+template <int V, int OBS_CAP>
 __global__ void __launch_bounds__(V2_CTA_THREADS) pgd_step_v2_kernel(Tables T, State S, PgdConfig cfg, int mode,
                                                                      int env_begin, int env_end,
                                                                      const float* __restrict__ actions,
@@ -29,7 +30,8 @@ __global__ void __launch_bounds__(V2_CTA_THREADS) pgd_step_v2_kernel(Tables T, S
   const int env = env_begin + blockIdx.x * V2_CTA_THREADS + threadIdx.x;
   const int warp_env0 = env - lane;
   const bool valid = env < env_end;
-  float row[PGD_OBS_DIM];
+  float row[OBS_CAP];
+  const int obs_dim = (cfg.n_side > 0 ? cfg.n_side : 2) + 6 + cfg.n_lane_line + 10 + 16 + PGD_LIDAR_BEAMS;
   bool wrote = false;
   if (valid) {
     const I4 envi = S.envi[env];
@@ -50,22 +52,20 @@ __global__ void __launch_bounds__(V2_CTA_THREADS) pgd_step_v2_kernel(Tables T, S
   // transposed write-out of the observation rows of the warp's 32 environments
   const unsigned wmask = __ballot_sync(0xffffffffu, wrote);
   if (wmask == 0) return;
-  for (int c = 0; c < PGD_OBS_DIM; c += 32) {
-    const int nc = PGD_OBS_DIM - c < 32 ? PGD_OBS_DIM - c : 32;
+  for (int c = 0; c < obs_dim; c += 32) {
+    const int nc = obs_dim - c < 32 ? obs_dim - c : 32;
     if (wrote)
       for (int k = 0; k < nc; ++k) tile[warp][lane][k] = row[c + k];
     __syncwarp();
     if (lane < nc)
       for (int r = 0; r < 32; ++r)
-        if ((wmask >> r) & 1u) obs[(size_t)(warp_env0 + r) * PGD_OBS_DIM + c + lane] = tile[warp][r][lane];
+        if ((wmask >> r) & 1u) obs[(size_t)(warp_env0 + r) * obs_dim + c + lane] = tile[warp][r][lane];
     __syncwarp();
   }
 }
 
 int pgd_launch_step_v2(PgdHandle* h, int mode, int env_begin, int env_end, const float* actions, float* obs,
                        float* reward, uint8_t* done, PgdInfo* info, cudaStream_t st) {
-  if (h->cfg.n_side > 0 || h->cfg.n_lane_line > 0)
-    return fail(-3, "the one-thread-per-environment layout has no side / lane-line detectors yet");
   if (h->cfg.decision_repeat > V2_MAX_SUBSTEPS)
     return fail(-3, "the one-thread-per-environment layout supports decision_repeat <= 16");
   Tables T;
@@ -77,12 +77,15 @@ int pgd_launch_step_v2(PgdHandle* h, int mode, int env_begin, int env_end, const
   S.misc = (I4*)h->S.misc; S.envi = (I4*)h->S.envi; S.envf = (F4*)h->S.envf;
   const int grid = (env_end - env_begin + V2_CTA_THREADS - 1) / V2_CTA_THREADS;
   if (h->timing && mode == 0) cudaEventRecord(h->ev0, st);
-  if (h->cfg.num_slots == 16)
-    pgd_step_v2_kernel<16><<<grid, V2_CTA_THREADS, 0, st>>>(T, S, h->cfg, mode, env_begin, env_end, actions, obs,
-                                                            reward, done, info);
-  else
-    pgd_step_v2_kernel<32><<<grid, V2_CTA_THREADS, 0, st>>>(T, S, h->cfg, mode, env_begin, env_end, actions, obs,
-                                                            reward, done, info);
+  const bool det = h->cfg.n_side > 0 || h->cfg.n_lane_line > 0;  // detectors need the long row
+#define V2_LAUNCH(VV, CAP)                                                                                   \
+  pgd_step_v2_kernel<VV, CAP><<<grid, V2_CTA_THREADS, 0, st>>>(T, S, h->cfg, mode, env_begin, env_end, actions, \
+                                                               obs, reward, done, info)
+  if (h->cfg.num_slots == 16 && !det) V2_LAUNCH(16, PGD_OBS_DIM);
+  else if (h->cfg.num_slots == 32 && !det) V2_LAUNCH(32, PGD_OBS_DIM);
+  else if (h->cfg.num_slots == 16) V2_LAUNCH(16, V2_OBS_CAP_DET);
+  else V2_LAUNCH(32, V2_OBS_CAP_DET);
+#undef V2_LAUNCH
   if (h->timing && mode == 0) cudaEventRecord(h->ev1, st);
   h->launches++;
   CU(cudaGetLastError());

@@ -480,6 +480,29 @@ V2_HD void step_env(const Tables& T, const State& S, const PgdConfig& cfg, int m
       for (int s = 0; s < n_slots; ++s) {
         Veh& q = veh[s];
         if (!(q.vflags & PGD_V_ALIVE)) continue;
+        const float reach = veh[0].hl + veh[0].hw + q.hl + q.hw;
+        // A vehicle at rest with no yaw rate and no engine force (parked traffic, a braking ego) is a fixed point of
+        // the sub-step: speed = max(0 - dv, 0) = 0, yaw stays 0, the pose does not move.  With v = 0 it cannot be
+        // over the speed limit, so "no engine force" is just throttle <= 0 and the force model is not needed at all;
+        // only its drop counter runs and its (fixed) chassis is tested against the ego's pose of every sub-step.
+        if (q.v == 0.0f && q.yaw == 0.0f && !(q.throttle > 0.0f)) {
+          q.airborne = q.airborne > ns ? q.airborne - ns : 0;
+          if (s == 0) {
+            for (int k = 0; k < ns; ++k) {
+              ego_traj[k].x = q.x; ego_traj[k].y = q.y; ego_traj[k].z = q.hc; ego_traj[k].w = q.hs;
+            }
+          } else {
+            for (int k = 0; k < ns; ++k) {
+              const float ddx = q.x - ego_traj[k].x, ddy = q.y - ego_traj[k].y;
+              if (ddx * ddx + ddy * ddy <= reach * reach) {
+                Rect me = {q.x, q.y, q.hc, q.hs, q.hl, q.hw};
+                Rect eg = {ego_traj[k].x, ego_traj[k].y, ego_traj[k].z, ego_traj[k].w, veh[0].hl, veh[0].hw};
+                if (rect_overlap(eg, me)) crash = 1;
+              }
+            }
+          }
+          continue;
+        }
         const PgdSlot& t = tpl[s];
         Sub sub;
         sub.mu_g = t.friction * V2_GRAVITY;
@@ -497,7 +520,6 @@ V2_HD void step_env(const Tables& T, const State& S, const PgdConfig& cfg, int m
         const float tb = t.lr / (t.lf + t.lr) * tanf(delta);
         sub.sb = tb / sqrtf(1.0f + tb * tb);
         const bool at_rest = q.v == 0.0f && q.yaw == 0.0f && !(sub.accel > 0.0f);
-        const float reach = veh[0].hl + veh[0].hw + q.hl + q.hw;
         for (int k = 0; k < ns; ++k) {
           if (q.airborne > 0) q.airborne--;
           else if (!at_rest) substep(q, sub, cfg.dt);
@@ -590,9 +612,15 @@ V2_HD void step_env(const Tables& T, const State& S, const PgdConfig& cfg, int m
     const Veh& ego = veh[0];
     const PgdSlot& t0 = tpl[0];
     const int32_t* rroads = T.route_roads + t0.route_off;
+    // row layout (obs/state_obs.py): [side beams | left, right], 6 state values, [lane-line beams], 10 navi,
+    // 16 neighbours, 240 lidar; st / ob are positioned so that the indices of the detector-less layout
+    // (state 2..7, navi 8..17, neighbours 18..33, lidar 34..) address the right part of the row
+    const int n_first = cfg.n_side > 0 ? cfg.n_side : 2;
+    float* const st = obs + n_first - 2;
+    float* const ob = obs + n_first + cfg.n_lane_line - 2;
     // lidar: 1.0 everywhere, then every chassis lowers the beams of the arc that can reach it (exact cull, see
     // pgd_step.cu phase F)
-    for (int i = 0; i < PGD_LIDAR_BEAMS; ++i) obs[34 + i] = 1.0f;
+    for (int i = 0; i < PGD_LIDAR_BEAMS; ++i) ob[34 + i] = 1.0f;
     for (int s = 1; s < n_slots; ++s) {
       const Veh& q = veh[s];
       if (!(q.vflags & PGD_V_ALIVE)) continue;
@@ -623,7 +651,40 @@ V2_HD void step_env(const Tables& T, const State& S, const PgdConfig& cfg, int m
         float sn, cs;
         V2_SINCOS(ang, sn, cs);
         const float hit = ray_rect(ego.x, ego.y, cs * V2_LIDAR_RANGE, sn * V2_LIDAR_RANGE, r);
-        obs[34 + i] = fminf(obs[34 + i], hit);
+        ob[34 + i] = fminf(ob[34 + i], hit);
+      }
+    }
+    // side / lane-line detectors (distance_detector.py:137-152): ray fans against the line ghosts of the map; a beam
+    // looks up the bucket of a point every 8 m along itself (buckets list every box within 4 m of them)
+    if (cfg.n_side > 0 || cfg.n_lane_line > 0) {
+      const int n_rays = cfg.n_side + cfg.n_lane_line;
+      const int32_t* ent = T.cell_entries + mp.entry_off;
+      for (int rI = 0; rI < n_rays; ++rI) {
+        const bool side = rI < cfg.n_side;
+        const int i = side ? rI : rI - cfg.n_side;
+        const int n = side ? cfg.n_side : cfg.n_lane_line;
+        const float dist = side ? cfg.side_distance : cfg.lane_line_distance;
+        const float ang = (float)i * (V2_TWO_PI / (float)n) + V2_PI / 2 + ego.h;
+        float sn, cs;
+        V2_SINCOS(ang, sn, cs);
+        const float dx = cs * dist, dy = sn * dist;
+        float best = 1.0f;
+        for (float sd = 4.0f; sd - 4.0f < dist; sd += 8.0f) {
+          if (best * dist < sd - 4.0f) break;
+          const float px = ego.x + cs * sd, py = ego.y + sn * sd;
+          const int cx = (int)floorf((px - mp.x0) * mp.inv_cell), cy = (int)floorf((py - mp.y0) * mp.inv_cell);
+          if (cx < 0 || cy < 0 || cx >= mp.nx || cy >= mp.ny) continue;
+          const int cell = mp.cell_off + cy * mp.nx + cx;
+          const int b0 = V2_LDG(&T.cell_start[cell]), b1 = V2_LDG(&T.cell_start[cell + 1]);
+          for (int k = b0; k < b1; ++k) {
+            const PgdBox g = boxes[V2_LDG(&ent[k])];
+            if (!(g.kind == PGD_BOX_WHITE || g.kind == PGD_BOX_YELLOW || (!side && g.kind == PGD_BOX_BROKEN))) continue;
+            const Rect r = {g.cx, g.cy, g.ux, g.uy, g.hl, g.hw};
+            best = fminf(best, ray_rect(ego.x, ego.y, dx, dy, r));
+          }
+        }
+        if (side) obs[i] = best;
+        else obs[n_first + 6 + i] = best;
       }
     }
     // the 4 nearest vehicles inside the 50 m cylinder (ties -> lower slot)
@@ -641,7 +702,7 @@ V2_HD void step_env(const Tables& T, const State& S, const PgdConfig& cfg, int m
         int best = -1;
         for (int s = 1; s < n_slots; ++s)
           if (d2s[s] < INFINITY && (best < 0 || d2s[s] < d2s[best])) best = s;
-        float* o4 = obs + 18 + 4 * rank;
+        float* o4 = ob + 18 + 4 * rank;
         if (best < 0) {
           o4[0] = o4[1] = o4[2] = o4[3] = 0.0f;
           continue;
@@ -692,7 +753,7 @@ V2_HD void step_env(const Tables& T, const State& S, const PgdConfig& cfg, int m
         dir = l.dir;
         angle = l.length / l.radius;
       }
-      float* q = obs + 8 + 5 * c;
+      float* q = ob + 8 + 5 * c;
       q[0] = clipf((ph / 50.0f + 1.0f) / 2.0f, 0.0f, 1.0f);
       q[1] = clipf((ps / 50.0f + 1.0f) / 2.0f, 0.0f, 1.0f);
       q[2] = clipf(bend, 0.0f, 1.0f);
@@ -706,7 +767,7 @@ V2_HD void step_env(const Tables& T, const State& S, const PgdConfig& cfg, int m
       else if (l.dir < 0.0f) { lx = ego.x - l.ax; ly = ego.y - l.ay; }
       else { lx = l.ax - ego.x; ly = l.ay - ego.y; }
       const float ln = sqrtf(lx * lx + ly * ly);
-      obs[2] = ln > 0.0f ? clipf((ego.hc * lx + ego.hs * ly) / ln, -1.0f, 1.0f) / 2.0f + 0.5f : 0.0f;
+      st[2] = ln > 0.0f ? clipf((ego.hc * lx + ego.hs * ly) / ln, -1.0f, 1.0f) / 2.0f + 0.5f : 0.0f;
     }
     const bool on_lane = (ego.vflags & PGD_V_ON_LANE) != 0;
     if (on_lane) flags |= PGD_F_ON_LANE;
@@ -725,13 +786,15 @@ V2_HD void step_env(const Tables& T, const State& S, const PgdConfig& cfg, int m
     if (out_of_road) flags |= PGD_F_OUT_OF_ROAD;
 
     const float sp = clipf(ego.v * 3.6f, 0.0f, 100000.0f);
-    obs[0] = clipf(to_left / 18.0f, 0.0f, 1.0f);
-    obs[1] = clipf(to_right / 18.0f, 0.0f, 1.0f);
-    obs[3] = clipf((sp + 1.0f) / (V2_MAX_SPEED_KMH + 1.0f), 0.0f, 1.0f);
-    obs[4] = clipf((ego.steer / 60.0f + 1.0f) / 2.0f, 0.0f, 1.0f);
-    obs[5] = clipf((envf.x + 1.0f) / 2.0f, 0.0f, 1.0f);
-    obs[6] = clipf((envf.y + 1.0f) / 2.0f, 0.0f, 1.0f);
-    obs[7] = clipf(fminf(fabsf(wrap_to_pi(ego.h - last_h)), V2_PI / 2) / 0.1f, 0.0f, 1.0f);
+    if (cfg.n_side <= 0) {
+      obs[0] = clipf(to_left / 18.0f, 0.0f, 1.0f);
+      obs[1] = clipf(to_right / 18.0f, 0.0f, 1.0f);
+    }
+    st[3] = clipf((sp + 1.0f) / (V2_MAX_SPEED_KMH + 1.0f), 0.0f, 1.0f);
+    st[4] = clipf((ego.steer / 60.0f + 1.0f) / 2.0f, 0.0f, 1.0f);
+    st[5] = clipf((envf.x + 1.0f) / 2.0f, 0.0f, 1.0f);
+    st[6] = clipf((envf.y + 1.0f) / 2.0f, 0.0f, 1.0f);
+    st[7] = clipf(fminf(fabsf(wrap_to_pi(ego.h - last_h)), V2_PI / 2) / 0.1f, 0.0f, 1.0f);
     float r = 0.0f, step_reward = 0.0f, cost = 0.0f, step_energy = 0.0f;
     int is_done = 0;
     if (!fresh) {

@@ -101,3 +101,19 @@ def test_reward_scheme_options():
         assert _same(a.step(act), b.step(act)), t
     a.close()
     b.close()
+
+
+@pytest.mark.parametrize("ns,ds,nl,dl", [(12, 50.0, 8, 20.0), (0, 50.0, 16, 30.0), (120, 40.0, 0, 20.0)])
+def test_side_and_lane_line_detectors(ns, ds, nl, dl):
+    T = _tables(range(1000, 1016))
+    cfg = dict(auto_reset=True, n_side=ns, side_distance=ds, n_lane_line=nl, lane_line_distance=dl)
+    a, b = _pair(T, 48, **cfg)
+    eps = [i % 16 for i in range(48)]
+    assert np.array_equal(a.reset(range(48), eps), b.reset(range(48), eps))
+    assert a.obs.shape[1] == (ns or 2) + 6 + nl + 266
+    rs = np.random.RandomState(8)
+    for t in range(160):
+        act = _actions(rs, 48, "forward")
+        assert _same(a.step(act), b.step(act)), t
+    a.close()
+    b.close()
