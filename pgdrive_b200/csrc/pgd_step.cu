@@ -1256,20 +1256,34 @@ extern "C" int pgd_step_host(PgdHandle* h, const float* actions, float* obs, flo
   return 0;
 }
 
+// the V per-slot records of one environment: contiguous in the default layout ([env][slot]), strided by num_envs in
+// the one-thread-per-environment layout ([slot][env])
+static cudaError_t copy_slots(PgdHandle* h, void* dev_base, int env, void* host, bool to_host) {
+  const int V = h->cfg.num_slots;
+  if (h->cfg.layout == 0) {
+    char* d = (char*)dev_base + (size_t)env * V * 16;
+    return to_host ? cudaMemcpy(host, d, (size_t)V * 16, cudaMemcpyDeviceToHost)
+                   : cudaMemcpy(d, host, (size_t)V * 16, cudaMemcpyHostToDevice);
+  }
+  char* d = (char*)dev_base + (size_t)env * 16;
+  const size_t pitch = (size_t)h->cfg.num_envs * 16;
+  return to_host ? cudaMemcpy2D(host, 16, d, pitch, 16, V, cudaMemcpyDeviceToHost)
+                 : cudaMemcpy2D(d, pitch, host, 16, 16, V, cudaMemcpyHostToDevice);
+}
+
 extern "C" int pgd_get_state(PgdHandle* h, int32_t env, PgdEnvState* out) {
   if (!h || !out) return fail(-1, "pgd_get_state: null argument");
   if (env < 0 || env >= h->cfg.num_envs) return fail(-1, "pgd_get_state: env out of range");
-  if (h->cfg.layout != 0) return fail(-3, "pgd_get_state: not available with the one-thread-per-environment layout");
   CU(cudaSetDevice(h->device));
   CU(cudaDeviceSynchronize());
   const int V = h->cfg.num_slots;
   float4 pose[PGD_MAX_SLOTS], ctrl[PGD_MAX_SLOTS], pidl[PGD_MAX_SLOTS], envf;
   int4 nav[PGD_MAX_SLOTS], misc[PGD_MAX_SLOTS], envi;
-  CU(cudaMemcpy(pose, h->S.pose + (size_t)env * V, V * 16, cudaMemcpyDeviceToHost));
-  CU(cudaMemcpy(ctrl, h->S.ctrl + (size_t)env * V, V * 16, cudaMemcpyDeviceToHost));
-  CU(cudaMemcpy(pidl, h->S.pidl + (size_t)env * V, V * 16, cudaMemcpyDeviceToHost));
-  CU(cudaMemcpy(nav, h->S.nav + (size_t)env * V, V * 16, cudaMemcpyDeviceToHost));
-  CU(cudaMemcpy(misc, h->S.misc + (size_t)env * V, V * 16, cudaMemcpyDeviceToHost));
+  CU(copy_slots(h, h->S.pose, env, pose, true));
+  CU(copy_slots(h, h->S.ctrl, env, ctrl, true));
+  CU(copy_slots(h, h->S.pidl, env, pidl, true));
+  CU(copy_slots(h, h->S.nav, env, nav, true));
+  CU(copy_slots(h, h->S.misc, env, misc, true));
   CU(cudaMemcpy(&envi, h->S.envi + env, 16, cudaMemcpyDeviceToHost));
   CU(cudaMemcpy(&envf, h->S.envf + env, 16, cudaMemcpyDeviceToHost));
   memset(out, 0, sizeof(*out));
@@ -1289,7 +1303,6 @@ extern "C" int pgd_get_state(PgdHandle* h, int32_t env, PgdEnvState* out) {
 extern "C" int pgd_set_state(PgdHandle* h, int32_t env, const PgdEnvState* in) {
   if (!h || !in) return fail(-1, "pgd_set_state: null argument");
   if (env < 0 || env >= h->cfg.num_envs) return fail(-1, "pgd_set_state: env out of range");
-  if (h->cfg.layout != 0) return fail(-3, "pgd_set_state: not available with the one-thread-per-environment layout");
   if (in->episode < 0 || in->episode >= h->n_episodes) return fail(-1, "pgd_set_state: episode out of range");
   CU(cudaSetDevice(h->device));
   CU(cudaDeviceSynchronize());
@@ -1306,11 +1319,11 @@ extern "C" int pgd_set_state(PgdHandle* h, int32_t env, const PgdEnvState* in) {
     nav[i] = make_int4(s->lane, s->ck0 | (s->ck1 << 16), s->rt_lane, s->timer);
     misc[i] = make_int4(s->rnd_n, s->airborne, s->flags, 0);
   }
-  CU(cudaMemcpy(h->S.pose + (size_t)env * V, pose, V * 16, cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(h->S.ctrl + (size_t)env * V, ctrl, V * 16, cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(h->S.pidl + (size_t)env * V, pidl, V * 16, cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(h->S.nav + (size_t)env * V, nav, V * 16, cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(h->S.misc + (size_t)env * V, misc, V * 16, cudaMemcpyHostToDevice));
+  CU(copy_slots(h, h->S.pose, env, pose, false));
+  CU(copy_slots(h, h->S.ctrl, env, ctrl, false));
+  CU(copy_slots(h, h->S.pidl, env, pidl, false));
+  CU(copy_slots(h, h->S.nav, env, nav, false));
+  CU(copy_slots(h, h->S.misc, env, misc, false));
   CU(cudaMemcpy(h->S.envi + env, &envi, 16, cudaMemcpyHostToDevice));
   CU(cudaMemcpy(h->S.envf + env, &envf, 16, cudaMemcpyHostToDevice));
   return 0;
