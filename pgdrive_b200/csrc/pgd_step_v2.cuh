@@ -58,6 +58,7 @@ namespace pgdv2 {
 #define V2_IDM_MAX_SPEED 100.0f
 #define V2_YAW_TAU 0.1f
 #define V2_DONE_PENDING_RESET 2
+#define V2_HDG_VALID (1 << 30) /* thread-local bit of Veh.vflags: (hc, hs) computed; never stored */
 #define V2_MAX_SUBSTEPS 16  /* decision_repeat supported by this layout (default 5) */
 
 struct F4 { float x, y, z, w; };
@@ -225,6 +226,13 @@ V2_HD void substep(Veh& q, const Sub& sub, float dt) {
   q.v = speed;
 }
 
+V2_HD void ensure_heading(Veh& q) {  // heading unit vector of a parked vehicle, on first use
+  if (!(q.vflags & V2_HDG_VALID)) {
+    V2_SINCOS(q.h, q.hs, q.hc);
+    q.vflags |= V2_HDG_VALID;
+  }
+}
+
 /* One environment, one decision step (mode 0) or the reset pass (mode 1: only environments marked pending are
  * touched).  V = vehicle slots.  obs points at this environment's row. */
 template <int V>
@@ -250,6 +258,9 @@ V2_HD void step_env(const Tables& T, const State& S, const PgdConfig& cfg, int m
 
   // ---- phase A: load ------------------------------------------------------------------------------------------
   Veh veh[V];
+  uint32_t was_parked = 0;  // slots that entered this step as parked traffic
+  uint32_t untouched = 0;   // slots whose stored state stays as it is
+  uint32_t drop_ran = 0;    // parked slots whose drop counter changed
   for (int s = 0; s < n_slots; ++s) {
     Veh& q = veh[s];
     const PgdSlot& t = tpl[s];
@@ -262,17 +273,33 @@ V2_HD void step_env(const Tables& T, const State& S, const PgdConfig& cfg, int m
       q.vflags = PGD_V_ALIVE | PGD_V_ON_LANE | (s == 0 ? PGD_V_ACTIVE : 0);
     } else {
       const size_t gi = (size_t)s * num_envs + env;
-      const F4 p = S.pose[gi], c = S.ctrl[gi], l = S.pidl[gi];
-      const I4 n = S.nav[gi], m = S.misc[gi];
-      q.x = p.x; q.y = p.y; q.h = p.z; q.v = p.w;
-      q.steer = c.x; q.throttle = c.y; q.hp = c.z; q.hi = c.w;
-      q.lp = l.x; q.li = l.y; q.tspeed = l.z; q.yaw = l.w;
-      q.lane = n.x; q.ck0 = n.y & 0xffff; q.ck1 = n.y >> 16; q.rt_lane = n.z; q.timer = n.w;
+      const I4 m = S.misc[gi];
       q.rnd_n = m.x; q.airborne = m.y; q.vflags = m.z;
+      if (!(m.z & PGD_V_ALIVE)) {
+        untouched |= 1u << s;  // removed earlier: nothing reads it, nothing is stored
+      } else if (m.z & PGD_V_ACTIVE) {
+        const F4 p = S.pose[gi], c = S.ctrl[gi], l = S.pidl[gi];
+        const I4 n = S.nav[gi];
+        q.x = p.x; q.y = p.y; q.h = p.z; q.v = p.w;
+        q.steer = c.x; q.throttle = c.y; q.hp = c.z; q.hi = c.w;
+        q.lp = l.x; q.li = l.y; q.tspeed = l.z; q.yaw = l.w;
+        q.lane = n.x; q.ck0 = n.y & 0xffff; q.ck1 = n.y >> 16; q.rt_lane = n.z; q.timer = n.w;
+      } else {
+        // Traffic that has not been woken yet has never been touched by IDM, physics (it is at rest) or
+        // localisation: everything but its drop counter still has the value the reset gave it, so it is taken from
+        // the episode template (L2-resident, shared by all environments on the seed) instead of from the state.
+        q.x = t.x; q.y = t.y; q.h = t.heading; q.v = 0.0f; q.yaw = 0.0f;
+        q.steer = q.throttle = q.hp = q.hi = q.lp = q.li = 0.0f;
+        q.tspeed = V2_IDM_NORMAL_SPEED;
+        q.lane = t.lane; q.ck0 = 0; q.ck1 = t.route_len > 2 ? 1 : 0; q.rt_lane = -1;
+        q.timer = t.overtake_timer;
+      }
     }
-    V2_SINCOS(q.h, q.hs, q.hc);
     q.hl = t.length * 0.5f;
     q.hw = t.width * 0.5f;
+    // heading unit vector: now for vehicles that move, on first use for parked ones (most are never looked at)
+    if ((q.vflags & (PGD_V_ALIVE | PGD_V_ACTIVE)) == (PGD_V_ALIVE | PGD_V_ACTIVE)) ensure_heading(q);
+    if (!(q.vflags & PGD_V_ACTIVE)) was_parked |= 1u << s;
   }
   if (fresh) {
     envi.y = 0; envi.z = 0; envi.w = 0;
@@ -294,7 +321,10 @@ V2_HD void step_env(const Tables& T, const State& S, const PgdConfig& cfg, int m
       const int ego_road = V2_LDG(&lanes[veh[0].lane].road);
       if (ego_road == V2_LDG(&ep->trigger_road[envi.y])) {
         for (int s = 1; s < n_slots; ++s)
-          if (tpl[s].group == envi.y) veh[s].vflags |= PGD_V_ACTIVE;
+          if (tpl[s].group == envi.y) {
+            veh[s].vflags |= PGD_V_ACTIVE;
+            ensure_heading(veh[s]);
+          }
         envi.y += 1;
       }
     }
@@ -306,6 +336,7 @@ V2_HD void step_env(const Tables& T, const State& S, const PgdConfig& cfg, int m
       float olong[V], lsx[V], lsy[V], lex[V], ley[V], llen[V];
       for (int s = 0; s < n_slots; ++s) {
         if (!(veh[s].vflags & PGD_V_ALIVE)) continue;
+        ensure_heading(veh[s]);
         const PgdLane l = lanes[veh[s].lane];
         lsx[s] = l.sx; lsy[s] = l.sy; lex[s] = l.ex; ley[s] = l.ey; llen[s] = l.length;
         float lon, lat;
@@ -486,6 +517,7 @@ V2_HD void step_env(const Tables& T, const State& S, const PgdConfig& cfg, int m
         // over the speed limit, so "no engine force" is just throttle <= 0 and the force model is not needed at all;
         // only its drop counter runs and its (fixed) chassis is tested against the ego's pose of every sub-step.
         if (q.v == 0.0f && q.yaw == 0.0f && !(q.throttle > 0.0f)) {
+          if (q.airborne > 0) drop_ran |= 1u << s;
           q.airborne = q.airborne > ns ? q.airborne - ns : 0;
           if (s == 0) {
             for (int k = 0; k < ns; ++k) {
@@ -495,6 +527,7 @@ V2_HD void step_env(const Tables& T, const State& S, const PgdConfig& cfg, int m
             for (int k = 0; k < ns; ++k) {
               const float ddx = q.x - ego_traj[k].x, ddy = q.y - ego_traj[k].y;
               if (ddx * ddx + ddy * ddy <= reach * reach) {
+                ensure_heading(q);
                 Rect me = {q.x, q.y, q.hc, q.hs, q.hl, q.hw};
                 Rect eg = {ego_traj[k].x, ego_traj[k].y, ego_traj[k].z, ego_traj[k].w, veh[0].hl, veh[0].hw};
                 if (rect_overlap(eg, me)) crash = 1;
@@ -609,7 +642,7 @@ V2_HD void step_env(const Tables& T, const State& S, const PgdConfig& cfg, int m
 
   // ---- phase F: observation, reward, done -----------------------------------------------------------------------
   {
-    const Veh& ego = veh[0];
+    const Veh ego = veh[0];
     const PgdSlot& t0 = tpl[0];
     const int32_t* rroads = T.route_roads + t0.route_off;
     // row layout (obs/state_obs.py): [side beams | left, right], 6 state values, [lane-line beams], 10 navi,
@@ -622,13 +655,14 @@ V2_HD void step_env(const Tables& T, const State& S, const PgdConfig& cfg, int m
     // pgd_step.cu phase F)
     for (int i = 0; i < PGD_LIDAR_BEAMS; ++i) ob[34 + i] = 1.0f;
     for (int s = 1; s < n_slots; ++s) {
-      const Veh& q = veh[s];
+      Veh& q = veh[s];
       if (!(q.vflags & PGD_V_ALIVE)) continue;
       const float dx = q.x - ego.x, dy = q.y - ego.y;
       const float d2 = dx * dx + dy * dy;
       const float hd = sqrtf(q.hl * q.hl + q.hw * q.hw);
       const float reach = V2_LIDAR_RANGE + hd;
       if (!(d2 < reach * reach)) continue;
+      ensure_heading(q);
       const float d = sqrtf(d2);
       int blo = 0, bn = PGD_LIDAR_BEAMS;
       if (d > hd * 1.001f) {
@@ -708,7 +742,8 @@ V2_HD void step_env(const Tables& T, const State& S, const PgdConfig& cfg, int m
           continue;
         }
         d2s[best] = INFINITY;
-        const Veh& q = veh[best];
+        Veh& q = veh[best];
+        ensure_heading(q);
         float pf, ps, vf, vs;
         project(ego.hc, ego.hs, q.x - ego.x, q.y - ego.y, pf, ps);
         const float ws = clipf(q.v * 3.6f, 0.0f, 100000.0f);
@@ -836,12 +871,22 @@ V2_HD void step_env(const Tables& T, const State& S, const PgdConfig& cfg, int m
   }
 
   // ---- phase G: store --------------------------------------------------------------------------------------------
+  // Only what can have changed is written back: parked traffic has at most run its drop counter, vehicles removed in
+  // an earlier step are not touched at all.  A freshly started episode writes every slot once.
   for (int s = 0; s < V; ++s) {
     const size_t gi = (size_t)s * num_envs + env;
     if (s < n_slots) {
       const Veh& q = veh[s];
+      if ((untouched >> s) & 1u) continue;
+      const int vflags = q.vflags & ~V2_HDG_VALID;
+      const I4 m = {q.rnd_n, q.airborne, vflags, 0};
+      const bool still_parked = ((was_parked >> s) & 1u) && !(vflags & PGD_V_ACTIVE);
+      if (still_parked && !fresh) {
+        if ((drop_ran >> s) & 1u) S.misc[gi] = m;
+        continue;
+      }
       F4 p = {q.x, q.y, q.h, q.v}, c = {q.steer, q.throttle, q.hp, q.hi}, l = {q.lp, q.li, q.tspeed, q.yaw};
-      I4 n = {q.lane, q.ck0 | (q.ck1 << 16), q.rt_lane, q.timer}, m = {q.rnd_n, q.airborne, q.vflags, 0};
+      I4 n = {q.lane, q.ck0 | (q.ck1 << 16), q.rt_lane, q.timer};
       S.pose[gi] = p; S.ctrl[gi] = c; S.pidl[gi] = l; S.nav[gi] = n; S.misc[gi] = m;
     } else if (fresh) {  // unused slots of a freshly started episode: clear the flags once
       I4 m = {0, 0, 0, 0};
