@@ -16,6 +16,24 @@ struct HostV2 {
   PgdConfig cfg;
 };
 
+template <int V>
+static void run_v(HostV2* h, int mode, const float* actions, float* obs, float* reward, uint8_t* done, PgdInfo* info) {
+  const int n = h->cfg.num_envs, od = pgd_obs_dim(&h->cfg), head = od - PGD_LIDAR_BEAMS;
+  for (int e = 0; e < n; ++e) {
+    if (mode == 1 && h->S.envi[e].z != V2_DONE_PENDING_RESET) continue;
+    LidarCtx<V> lc;
+    float* row = obs + (size_t)e * od;
+    step_env<V>(h->T, h->S, h->cfg, mode, e, n, actions ? actions + 2 * e : nullptr, row, lc,
+                reward ? reward + e : nullptr, done ? done + e : nullptr, info ? info + e : nullptr);
+    for (int i = 0; i < PGD_LIDAR_BEAMS; ++i) row[head + i] = lidar_beam<V>(lc, i);
+  }
+}
+
+static void run(HostV2* h, int mode, const float* actions, float* obs, float* reward, uint8_t* done, PgdInfo* info) {
+  if (h->cfg.num_slots == 16) run_v<16>(h, mode, actions, obs, reward, done, info);
+  else run_v<32>(h, mode, actions, obs, reward, done, info);
+}
+
 extern "C" {
 
 void* v2h_create(const PgdTables* t, const PgdConfig* cfg) {
@@ -35,19 +53,6 @@ void v2h_destroy(void* p) {
   HostV2* h = (HostV2*)p;
   free(h->S.pose); free(h->S.ctrl); free(h->S.pidl); free(h->S.nav); free(h->S.misc); free(h->S.envi); free(h->S.envf);
   free(h);
-}
-
-static void run(HostV2* h, int mode, const float* actions, float* obs, float* reward, uint8_t* done, PgdInfo* info) {
-  const int n = h->cfg.num_envs, od = pgd_obs_dim(&h->cfg);
-  for (int e = 0; e < n; ++e) {
-    const float* a = actions ? actions + 2 * e : nullptr;
-    if (h->cfg.num_slots == 16)
-      step_env<16>(h->T, h->S, h->cfg, mode, e, n, a, obs + (size_t)e * od, reward ? reward + e : nullptr,
-                   done ? done + e : nullptr, info ? info + e : nullptr);
-    else
-      step_env<32>(h->T, h->S, h->cfg, mode, e, n, a, obs + (size_t)e * od, reward ? reward + e : nullptr,
-                   done ? done + e : nullptr, info ? info + e : nullptr);
-  }
 }
 
 /* pgd_reset: environments env_ids[i] restart on episode_ids[i]; their observation rows are rewritten */

@@ -5,7 +5,8 @@
 // loads and stores of a slot are 32 consecutive 16-byte vectors; the thread's vehicles and its observation row live
 // in thread-local arrays (lane-interleaved local memory, served by L1).  The rows are written out through a
 // shared-memory transpose: 32 environments x 32 floats per tile, so that every global store instruction covers
-// 32 consecutive floats of one row.
+// 32 consecutive floats of one row; the 240 lidar beams are evaluated right there (lidar_beam) and never stored
+// in local memory.
 //
 // STATUS: the step function is checked bit for bit against the CPU oracle in its host build
 // (tests/test_step_v2.py); the sm_100a build has not run on a GPU yet (tests/test_gpu_step_v2.py is opt-in).
@@ -15,9 +16,10 @@
 using namespace pgdv2;
 
 #define V2_CTA_THREADS 64
-#define V2_OBS_CAP_DET (2 * PGD_MAX_DETECTOR_BEAMS + 6 + 10 + 16 + PGD_LIDAR_BEAMS) /* 752 */
+#define V2_HEAD (PGD_OBS_DIM - PGD_LIDAR_BEAMS)                         /* 34: state, navi, neighbours */
+#define V2_HEAD_DET (2 * PGD_MAX_DETECTOR_BEAMS + 6 + 10 + 16)          /* 512: with both detector fans */
 
-template <int V, int OBS_CAP>
+template <int V, int HEAD_CAP>
 __global__ void __launch_bounds__(V2_CTA_THREADS) pgd_step_v2_kernel(Tables T, State S, PgdConfig cfg, int mode,
                                                                      int env_begin, int env_end,
                                                                      const float* __restrict__ actions,
@@ -30,7 +32,9 @@ __global__ void __launch_bounds__(V2_CTA_THREADS) pgd_step_v2_kernel(Tables T, S
   const int env = env_begin + blockIdx.x * V2_CTA_THREADS + threadIdx.x;
   const int warp_env0 = env - lane;
   const bool valid = env < env_end;
-  float row[OBS_CAP];
+  float row[HEAD_CAP];  // the row up to the lidar beams
+  LidarCtx<V> lc;
+  lc.n = 0;
   const int obs_dim = (cfg.n_side > 0 ? cfg.n_side : 2) + 6 + cfg.n_lane_line + 10 + 16 + PGD_LIDAR_BEAMS;
   bool wrote = false;
   if (valid) {
@@ -39,7 +43,7 @@ __global__ void __launch_bounds__(V2_CTA_THREADS) pgd_step_v2_kernel(Tables T, S
     float r = 0.0f;
     uint8_t d = 0;
     PgdInfo inf;
-    step_env<V>(T, S, cfg, mode, env, cfg.num_envs, actions ? actions + 2 * (size_t)env : nullptr, row, &r, &d,
+    step_env<V>(T, S, cfg, mode, env, cfg.num_envs, actions ? actions + 2 * (size_t)env : nullptr, row, lc, &r, &d,
                 info ? &inf : nullptr);
     if (wrote) {
       if (mode == 0) {
@@ -52,10 +56,11 @@ __global__ void __launch_bounds__(V2_CTA_THREADS) pgd_step_v2_kernel(Tables T, S
   // transposed write-out of the observation rows of the warp's 32 environments
   const unsigned wmask = __ballot_sync(0xffffffffu, wrote);
   if (wmask == 0) return;
+  const int head = obs_dim - PGD_LIDAR_BEAMS;
   for (int c = 0; c < obs_dim; c += 32) {
     const int nc = obs_dim - c < 32 ? obs_dim - c : 32;
     if (wrote)
-      for (int k = 0; k < nc; ++k) tile[warp][lane][k] = row[c + k];
+      for (int k = 0; k < nc; ++k) tile[warp][lane][k] = (c + k < head) ? row[c + k] : lidar_beam<V>(lc, c + k - head);
     __syncwarp();
     if (lane < nc)
       for (int r = 0; r < 32; ++r)
@@ -81,10 +86,10 @@ int pgd_launch_step_v2(PgdHandle* h, int mode, int env_begin, int env_end, const
 #define V2_LAUNCH(VV, CAP)                                                                                   \
   pgd_step_v2_kernel<VV, CAP><<<grid, V2_CTA_THREADS, 0, st>>>(T, S, h->cfg, mode, env_begin, env_end, actions, \
                                                                obs, reward, done, info)
-  if (h->cfg.num_slots == 16 && !det) V2_LAUNCH(16, PGD_OBS_DIM);
-  else if (h->cfg.num_slots == 32 && !det) V2_LAUNCH(32, PGD_OBS_DIM);
-  else if (h->cfg.num_slots == 16) V2_LAUNCH(16, V2_OBS_CAP_DET);
-  else V2_LAUNCH(32, V2_OBS_CAP_DET);
+  if (h->cfg.num_slots == 16 && !det) V2_LAUNCH(16, V2_HEAD);
+  else if (h->cfg.num_slots == 32 && !det) V2_LAUNCH(32, V2_HEAD);
+  else if (h->cfg.num_slots == 16) V2_LAUNCH(16, V2_HEAD_DET);
+  else V2_LAUNCH(32, V2_HEAD_DET);
 #undef V2_LAUNCH
   if (h->timing && mode == 0) cudaEventRecord(h->ev1, st);
   h->launches++;

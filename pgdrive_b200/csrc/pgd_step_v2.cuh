@@ -226,6 +226,40 @@ V2_HD void substep(Veh& q, const Sub& sub, float dt) {
   q.v = speed;
 }
 
+/* What the 240 lidar beams of one environment depend on: the ego's pose and, per chassis in range, its rectangle and
+ * the (conservative, exact) arc of beams that can reach it.  The beams themselves are evaluated when the observation
+ * row is written out, so they never sit in thread-local memory. */
+template <int V>
+struct LidarCtx {
+  float ex, ey, eh;
+  int n;
+  float cx[V], cy[V], ux[V], uy[V], hl[V], hw[V];
+  int blo[V], bn[V];
+};
+
+template <int V>
+V2_HD float lidar_beam(const LidarCtx<V>& lc, int i) {
+  float best = 1.0f;
+  bool have_dir = false;
+  float dx = 0.0f, dy = 0.0f;
+  for (int j = 0; j < lc.n; ++j) {
+    int rel = i - lc.blo[j];
+    if (rel < 0) rel += PGD_LIDAR_BEAMS;
+    if (rel > lc.bn[j]) continue;
+    if (!have_dir) {
+      const float ang = (float)i * (V2_TWO_PI / (float)PGD_LIDAR_BEAMS) + lc.eh;
+      float sn, cs;
+      V2_SINCOS(ang, sn, cs);
+      dx = cs * V2_LIDAR_RANGE;
+      dy = sn * V2_LIDAR_RANGE;
+      have_dir = true;
+    }
+    const Rect r = {lc.cx[j], lc.cy[j], lc.ux[j], lc.uy[j], lc.hl[j], lc.hw[j]};
+    best = fminf(best, ray_rect(lc.ex, lc.ey, dx, dy, r));
+  }
+  return best;
+}
+
 V2_HD void ensure_heading(Veh& q) {  // heading unit vector of a parked vehicle, on first use
   if (!(q.vflags & V2_HDG_VALID)) {
     V2_SINCOS(q.h, q.hs, q.hc);
@@ -234,10 +268,11 @@ V2_HD void ensure_heading(Veh& q) {  // heading unit vector of a parked vehicle,
 }
 
 /* One environment, one decision step (mode 0) or the reset pass (mode 1: only environments marked pending are
- * touched).  V = vehicle slots.  obs points at this environment's row. */
+ * touched).  V = vehicle slots.  obs receives the row up to the lidar beams (34 floats without detectors); the
+ * beams are described by lc and evaluated by lidar_beam(). */
 template <int V>
 V2_HD void step_env(const Tables& T, const State& S, const PgdConfig& cfg, int mode, int env, int num_envs,
-                    const float* action, float* obs, float* reward, uint8_t* done, PgdInfo* info) {
+                    const float* action, float* obs, LidarCtx<V>& lc, float* reward, uint8_t* done, PgdInfo* info) {
   I4 envi = S.envi[env];
   F4 envf = S.envf[env];
   const bool pending = envi.z == V2_DONE_PENDING_RESET;
@@ -651,9 +686,10 @@ V2_HD void step_env(const Tables& T, const State& S, const PgdConfig& cfg, int m
     const int n_first = cfg.n_side > 0 ? cfg.n_side : 2;
     float* const st = obs + n_first - 2;
     float* const ob = obs + n_first + cfg.n_lane_line - 2;
-    // lidar: 1.0 everywhere, then every chassis lowers the beams of the arc that can reach it (exact cull, see
-    // pgd_step.cu phase F)
-    for (int i = 0; i < PGD_LIDAR_BEAMS; ++i) ob[34 + i] = 1.0f;
+    // lidar: every chassis in range publishes its rectangle and the arc of beams that can reach it (exact cull, see
+    // pgd_step.cu phase F); beam values are computed by lidar_beam() at write-out
+    lc.ex = ego.x; lc.ey = ego.y; lc.eh = ego.h;
+    lc.n = 0;
     for (int s = 1; s < n_slots; ++s) {
       Veh& q = veh[s];
       if (!(q.vflags & PGD_V_ALIVE)) continue;
@@ -676,17 +712,9 @@ V2_HD void step_env(const Tables& T, const State& S, const PgdConfig& cfg, int m
           if (blo < 0) blo += PGD_LIDAR_BEAMS;
         }
       }
-      const Rect r = {q.x, q.y, q.hc, q.hs, q.hl, q.hw};
-      const int count = bn >= PGD_LIDAR_BEAMS ? PGD_LIDAR_BEAMS : bn + 1;  // relative beam indices 0..bn
-      for (int rel = 0; rel < count; ++rel) {
-        int i = blo + rel;
-        if (i >= PGD_LIDAR_BEAMS) i -= PGD_LIDAR_BEAMS;
-        const float ang = (float)i * (V2_TWO_PI / (float)PGD_LIDAR_BEAMS) + ego.h;
-        float sn, cs;
-        V2_SINCOS(ang, sn, cs);
-        const float hit = ray_rect(ego.x, ego.y, cs * V2_LIDAR_RANGE, sn * V2_LIDAR_RANGE, r);
-        ob[34 + i] = fminf(ob[34 + i], hit);
-      }
+      const int j = lc.n++;
+      lc.cx[j] = q.x; lc.cy[j] = q.y; lc.ux[j] = q.hc; lc.uy[j] = q.hs; lc.hl[j] = q.hl; lc.hw[j] = q.hw;
+      lc.blo[j] = blo; lc.bn[j] = bn;
     }
     // side / lane-line detectors (distance_detector.py:137-152): ray fans against the line ghosts of the map; a beam
     // looks up the bucket of a point every 8 m along itself (buckets list every box within 4 m of them)
