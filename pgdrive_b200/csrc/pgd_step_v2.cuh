@@ -543,10 +543,19 @@ V2_HD void step_env(const Tables& T, const State& S, const PgdConfig& cfg, int m
     F4 ego_traj[V2_MAX_SUBSTEPS];
     {
       const int ns = cfg.decision_repeat < V2_MAX_SUBSTEPS ? cfg.decision_repeat : V2_MAX_SUBSTEPS;
+      float ego_travel = -1.0f;  // not known until the ego (slot 0, always alive) has been integrated
       for (int s = 0; s < n_slots; ++s) {
         Veh& q = veh[s];
         if (!(q.vflags & PGD_V_ALIVE)) continue;
         const float reach = veh[0].hl + veh[0].hw + q.hl + q.hw;
+        if (s > 0 && ego_travel < 0.0f) {  // first vehicle after the ego: how far did the ego get from its start pose?
+          float m2 = 0.0f;
+          for (int k = 0; k < ns; ++k) {
+            const float ex = ego_traj[k].x - last_x, ey = ego_traj[k].y - last_y;
+            m2 = fmaxf(m2, ex * ex + ey * ey);
+          }
+          ego_travel = sqrtf(m2) * 1.001f + 1e-3f;
+        }
         // A vehicle at rest with no yaw rate and no engine force (parked traffic, a braking ego) is a fixed point of
         // the sub-step: speed = max(0 - dv, 0) = 0, yaw stays 0, the pose does not move.  With v = 0 it cannot be
         // over the speed limit, so "no engine force" is just throttle <= 0 and the force model is not needed at all;
@@ -559,6 +568,11 @@ V2_HD void step_env(const Tables& T, const State& S, const PgdConfig& cfg, int m
               ego_traj[k].x = q.x; ego_traj[k].y = q.y; ego_traj[k].z = q.hc; ego_traj[k].w = q.hs;
             }
           } else {
+            // the ego stays within ego_travel of where it started the step: a parked chassis further away than
+            // reach + ego_travel cannot be touched in any sub-step (triangle inequality; the margin covers rounding)
+            const float ddx0 = q.x - last_x, ddy0 = q.y - last_y;
+            const float far = reach + ego_travel;
+            if (ddx0 * ddx0 + ddy0 * ddy0 > far * far) continue;
             for (int k = 0; k < ns; ++k) {
               const float ddx = q.x - ego_traj[k].x, ddy = q.y - ego_traj[k].y;
               if (ddx * ddx + ddy * ddy <= reach * reach) {
