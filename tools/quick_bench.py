@@ -6,7 +6,9 @@ import bench
 from pgdrive_b200 import VecPGDriveEnv
 n = int(os.environ.get("ENVS", 65536)); K = int(os.environ.get("STEPS", 200)); W = 40
 T = bench.build_tables()
-env = VecPGDriveEnv(dict(start_seed=1000, environment_num=100, num_envs=n, traffic_density=0.1, num_slots=16), tables_dict=T)
+layout = os.environ.get("LAYOUT", "0") == "1"  # LAYOUT=1: one thread per environment (pgd_step_v2.cu)
+env = VecPGDriveEnv(dict(start_seed=1000, environment_num=100, num_envs=n, traffic_density=0.1, num_slots=16,
+                         one_thread_per_env=layout), tables_dict=T)
 env.reset()
 mode = os.environ.get("ACTIONS", "uniform")
 g = torch.Generator(device="cuda"); g.manual_seed(1)
@@ -20,4 +22,4 @@ e0.record()
 for t in range(K): env.step(a[W + t])
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / K
-print("%s actions=%s: %.4f ms/step, %.1f M env-steps/s" % (os.environ.get("PGDRIVE_B200_LIB", "default"), mode, ms, n / ms / 1e3))
+print("%s layout=%d actions=%s: %.4f ms/step, %.1f M env-steps/s" % (os.environ.get("PGDRIVE_B200_LIB", "default"), int(layout), mode, ms, n / ms / 1e3))
