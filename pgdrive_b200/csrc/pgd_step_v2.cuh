@@ -61,8 +61,8 @@ namespace pgdv2 {
 #define V2_HDG_VALID (1 << 30) /* thread-local bit of Veh.vflags: (hc, hs) computed; never stored */
 #define V2_MAX_SUBSTEPS 16  /* decision_repeat supported by this layout (default 5) */
 
-struct F4 { float x, y, z, w; };
-struct I4 { int x, y, z, w; };
+struct alignas(16) F4 { float x, y, z, w; };  // one 16-byte load / store
+struct alignas(16) I4 { int x, y, z, w; };
 
 struct Tables {  // device (or host) pointers to the tables of include/pgd_tables.h
   const PgdMap* maps;
