@@ -96,6 +96,23 @@ V2_HD T_ ldg(const T_* p) {  // read-only table data
 #endif
 }
 
+/* A whole table record (PgdLane 64 B, PgdBox / PgdRoad 32 B, PgdMap 64 B: multiples of 16, 16-byte aligned) with
+ * 16-byte read-only loads on the device. */
+template <class T_>
+V2_HD T_ load_rec(const T_* p) {
+#ifdef __CUDA_ARCH__
+  static_assert(sizeof(T_) % 16 == 0, "table records are multiples of 16 bytes");
+  T_ out;
+  const uint4* src = reinterpret_cast<const uint4*>(p);
+  uint4* dst = reinterpret_cast<uint4*>(&out);
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(T_) / 16); ++i) dst[i] = __ldg(src + i);
+  return out;
+#else
+  return *p;
+#endif
+}
+
 V2_HD float clipf(float a, float lo, float hi) { return fminf(fmaxf(a, lo), hi); }
 
 V2_HD float wrap_to_pi(float x) {
@@ -283,7 +300,7 @@ V2_HD void step_env(const Tables& T, const State& S, const PgdConfig& cfg, int m
   const bool stepping = !fresh;
 
   const PgdEpisode* ep = T.episodes + envi.x;
-  const PgdMap mp = T.maps[V2_LDG(&ep->map)];
+  const PgdMap mp = load_rec(T.maps + V2_LDG(&ep->map));
   const int n_slots = V2_LDG(&ep->n_slots);
   const int n_groups = V2_LDG(&ep->n_groups);
   const PgdLane* lanes = T.lanes + mp.lane_off;
@@ -372,7 +389,7 @@ V2_HD void step_env(const Tables& T, const State& S, const PgdConfig& cfg, int m
       for (int s = 0; s < n_slots; ++s) {
         if (!(veh[s].vflags & PGD_V_ALIVE)) continue;
         ensure_heading(veh[s]);
-        const PgdLane l = lanes[veh[s].lane];
+        const PgdLane l = load_rec(lanes + (veh[s].lane));
         lsx[s] = l.sx; lsy[s] = l.sy; lex[s] = l.ex; ley[s] = l.ey; llen[s] = l.length;
         float lon, lat;
         lane_local(l, veh[s].x, veh[s].y, lon, lat);
@@ -384,7 +401,7 @@ V2_HD void step_env(const Tables& T, const State& S, const PgdConfig& cfg, int m
         const PgdSlot& t = tpl[s];
         const int32_t* rroads = T.route_roads + t.route_off;
         const int cur_road_id = V2_LDG(&rroads[q.ck0]);
-        const PgdRoad cur_road = roads[cur_road_id];
+        const PgdRoad cur_road = load_rec(roads + (cur_road_id));
         bool ok;
         if (q.rt_lane < 0) {
           q.rt_lane = q.lane;
@@ -408,10 +425,10 @@ V2_HD void step_env(const Tables& T, const State& S, const PgdConfig& cfg, int m
         } else {
           ok = true;
         }
-        const PgdLane rl = lanes[q.rt_lane];
+        const PgdLane rl = load_rec(lanes + (q.rt_lane));
         int cand[3] = {-1, q.rt_lane, -1};
         if (ok) {
-          const PgdRoad rr = roads[rl.road];
+          const PgdRoad rr = load_rec(roads + (rl.road));
           if (rl.idx > 0) cand[0] = rr.first_lane + rl.idx - 1;
           if (rl.idx + 1 < rr.n_lanes) cand[2] = rr.first_lane + rl.idx + 1;
         }
@@ -421,7 +438,7 @@ V2_HD void step_env(const Tables& T, const State& S, const PgdConfig& cfg, int m
           front[i] = back[i] = -1;
           fdist[i] = bdist[i] = V2_IDM_MAX_LONG;
           if (cand[i] < 0) continue;
-          const PgdLane l = (i == 1) ? rl : lanes[cand[i]];
+          const PgdLane l = (i == 1) ? rl : load_rec(lanes + cand[i]);
           float cur_long, lat;
           lane_local(l, q.x, q.y, cur_long, lat);
           const float left_long = l.length - cur_long;
@@ -451,7 +468,7 @@ V2_HD void step_env(const Tables& T, const State& S, const PgdConfig& cfg, int m
           bool decided = false;
           const int idx = rl.idx;
           if (q.ck0 != q.ck1) {
-            const PgdRoad nxt = roads[V2_LDG(&rroads[q.ck1])];
+            const PgdRoad nxt = load_rec(roads + (V2_LDG(&rroads[q.ck1])));
             const int diff = n_cur - nxt.n_lanes;
             if (diff > 0) {
               const PgdLane* c0 = lanes + cur_road.first_lane;
@@ -511,7 +528,7 @@ V2_HD void step_env(const Tables& T, const State& S, const PgdConfig& cfg, int m
           }
         }
         {  // steering_control
-          const PgdLane tl = (steer_lane == q.rt_lane) ? rl : lanes[steer_lane];
+          const PgdLane tl = (steer_lane == q.rt_lane) ? rl : load_rec(lanes + steer_lane);
           float lon, lat;
           lane_local(tl, q.x, q.y, lon, lat);
           const float lane_heading = lane_heading_at(tl, lon + 1.0f);
@@ -639,9 +656,20 @@ V2_HD void step_env(const Tables& T, const State& S, const PgdConfig& cfg, int m
       if (cx >= 0 && cy >= 0 && cx < mp.nx && cy < mp.ny) {
         const int cell = mp.cell_off + cy * mp.nx + cx;
         const int b0 = V2_LDG(&T.cell_start[cell]), b1 = V2_LDG(&T.cell_start[cell + 1]);
-        for (int k = b0; k < b1; ++k) {
-          const int b = V2_LDG(&ent[k]);
-          const PgdBox g = boxes[b];
+        // entries are fetched four at a time (indices, then records) so that their latencies overlap
+        for (int k0 = b0; k0 < b1; k0 += 4) {
+          int bb[4];
+          PgdBox gg[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) bb[j] = (k0 + j < b1) ? V2_LDG(&ent[k0 + j]) : -1;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (bb[j] >= 0) gg[j] = load_rec(boxes + bb[j]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+          if (bb[j] < 0) continue;
+          const int b = bb[j];
+          const PgdBox& g = gg[j];
           if (g.kind == PGD_BOX_LANE) {
             const float dx = q.x - g.cx, dy = q.y - g.cy;
             if (!(fabsf(dx * g.ux + dy * g.uy) <= g.hl && fabsf(-dx * g.uy + dy * g.ux) <= g.hw)) continue;
@@ -664,13 +692,14 @@ V2_HD void step_env(const Tables& T, const State& S, const PgdConfig& cfg, int m
                    : g.kind == PGD_BOX_YELLOW ? PGD_F_ON_YELLOW
                    : g.kind == PGD_BOX_BROKEN ? PGD_F_ON_BROKEN : PGD_F_CRASH_SIDEWALK;
           }
+          }
         }
       }
       const int nb = b_cur != INT_MAX ? b_cur : (b_next != INT_MAX ? b_next : b_any);
       const bool on_lane = nb != INT_MAX;
       if (on_lane) q.lane = V2_LDG(&boxes[nb].lane);
       if (q.ck0 != q.ck1) {  // _update_target_checkpoints
-        const PgdLane l = lanes[q.lane];
+        const PgdLane l = load_rec(lanes + (q.lane));
         float lon, lat;
         lane_local(l, q.x, q.y, lon, lat);
         const int start = V2_LDG(&roads[l.road].start_node);
@@ -753,7 +782,7 @@ V2_HD void step_env(const Tables& T, const State& S, const PgdConfig& cfg, int m
           const int cell = mp.cell_off + cy * mp.nx + cx;
           const int b0 = V2_LDG(&T.cell_start[cell]), b1 = V2_LDG(&T.cell_start[cell + 1]);
           for (int k = b0; k < b1; ++k) {
-            const PgdBox g = boxes[V2_LDG(&ent[k])];
+            const PgdBox g = load_rec(boxes + V2_LDG(&ent[k]));
             if (!(g.kind == PGD_BOX_WHITE || g.kind == PGD_BOX_YELLOW || (!side && g.kind == PGD_BOX_BROKEN))) continue;
             const Rect r = {g.cx, g.cy, g.ux, g.uy, g.hl, g.hw};
             best = fminf(best, ray_rect(ego.x, ego.y, dx, dy, r));
@@ -798,24 +827,24 @@ V2_HD void step_env(const Tables& T, const State& S, const PgdConfig& cfg, int m
     }
     // ego bookkeeping
     const int cur_road_id = V2_LDG(&rroads[ego.ck0]);
-    const PgdRoad cur_road = roads[cur_road_id];
-    const PgdRoad fr = roads[V2_LDG(&rroads[t0.route_len - 2])];
+    const PgdRoad cur_road = load_rec(roads + (cur_road_id));
+    const PgdRoad fr = load_rec(roads + (V2_LDG(&rroads[t0.route_len - 2])));
     const int el_road = V2_LDG(&lanes[ego.lane].road);
     const bool use_ego_lane = el_road == cur_road_id;
     const int reward_lane = use_ego_lane ? ego.lane : cur_road.first_lane;
     const int n_ref = cur_road.n_lanes;
     const int sign_i = use_ego_lane ? 0 : (V2_LDG(&roads[el_road].negative) ? -1 : 1);
     float qlon0, qlat0, qlon1, qlat1, long_last, lat_last, long_now, lat_now;
-    lane_local(lanes[cur_road.first_lane], ego.x, ego.y, qlon0, qlat0);
-    const PgdLane final_lane = lanes[fr.first_lane + fr.n_lanes - 1];
+    lane_local(load_rec(lanes + cur_road.first_lane), ego.x, ego.y, qlon0, qlat0);
+    const PgdLane final_lane = load_rec(lanes + (fr.first_lane + fr.n_lanes - 1));
     lane_local(final_lane, ego.x, ego.y, qlon1, qlat1);
     {
-      const PgdLane rl = lanes[reward_lane];
+      const PgdLane rl = load_rec(lanes + (reward_lane));
       lane_local(rl, last_x, last_y, long_last, lat_last);
       lane_local(rl, ego.x, ego.y, long_now, lat_now);
     }
     for (int c = 0; c < 2; ++c) {  // navigation.py:213-260
-      const PgdLane l = lanes[c == 0 ? cur_road.first_lane : V2_LDG(&roads[V2_LDG(&rroads[ego.ck1])].first_lane)];
+      const PgdLane l = load_rec(lanes + (c == 0 ? cur_road.first_lane : V2_LDG(&roads[V2_LDG(&rroads[ego.ck1])].first_lane)));
       const float later_middle = ((float)n_ref / 2.0f - 0.5f) * mp.lane_width;
       float px, py;
       lane_position(l, l.length, later_middle, px, py);
@@ -838,7 +867,7 @@ V2_HD void step_env(const Tables& T, const State& S, const PgdConfig& cfg, int m
       q[4] = clipf((angle * (180.0f / V2_PI) / 135.0f + 1.0f) / 2.0f, 0.0f, 1.0f);
     }
     {  // heading_diff (base_vehicle.py:433-458)
-      const PgdLane l = lanes[cur_road.first_lane + cur_road.n_lanes - 1];
+      const PgdLane l = load_rec(lanes + (cur_road.first_lane + cur_road.n_lanes - 1));
       float lx, ly;
       if (l.kind == PGD_LANE_STRAIGHT) { lx = -l.ay; ly = l.ax; }
       else if (l.dir < 0.0f) { lx = ego.x - l.ax; ly = ego.y - l.ay; }
