@@ -313,6 +313,15 @@ V2_HD void step_env(const Tables& T, const State& S, const PgdConfig& cfg, int m
   uint32_t was_parked = 0;  // slots that entered this step as parked traffic
   uint32_t untouched = 0;   // slots whose stored state stays as it is
   uint32_t drop_ran = 0;    // parked slots whose drop counter changed
+  if (!fresh) {  // the flag words of all slots first: 16 independent 16-byte loads in flight
+#pragma unroll
+    for (int s = 0; s < V; ++s) {
+      if (s < n_slots) {
+        const I4 m = S.misc[(size_t)s * num_envs + env];
+        veh[s].rnd_n = m.x; veh[s].airborne = m.y; veh[s].vflags = m.z;
+      }
+    }
+  }
   for (int s = 0; s < n_slots; ++s) {
     Veh& q = veh[s];
     const PgdSlot& t = tpl[s];
@@ -325,11 +334,9 @@ V2_HD void step_env(const Tables& T, const State& S, const PgdConfig& cfg, int m
       q.vflags = PGD_V_ALIVE | PGD_V_ON_LANE | (s == 0 ? PGD_V_ACTIVE : 0);
     } else {
       const size_t gi = (size_t)s * num_envs + env;
-      const I4 m = S.misc[gi];
-      q.rnd_n = m.x; q.airborne = m.y; q.vflags = m.z;
-      if (!(m.z & PGD_V_ALIVE)) {
+      if (!(q.vflags & PGD_V_ALIVE)) {
         untouched |= 1u << s;  // removed earlier: nothing reads it, nothing is stored
-      } else if (m.z & PGD_V_ACTIVE) {
+      } else if (q.vflags & PGD_V_ACTIVE) {
         const F4 p = S.pose[gi], c = S.ctrl[gi], l = S.pidl[gi];
         const I4 n = S.nav[gi];
         q.x = p.x; q.y = p.y; q.h = p.z; q.v = p.w;
