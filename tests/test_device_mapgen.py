@@ -287,3 +287,26 @@ def test_device_generation_errors_are_reported():
     with pytest.raises(RuntimeError, match="box table full"):
         devgen.generate(eng, [1000], devgen.make_gen_config(V0, 0.1, SPAWN), caps)
     eng.close()
+
+
+def test_host_build_property_random_map_configs():
+    """Randomly drawn map configurations (1-4 lanes, 1-6 blocks, lane width, exit length, density, seed): the
+    generator's host build equals the reference-pinned Python reset path bit for bit (or reports the same overflow)."""
+    from hypothesis import given, settings, strategies as st
+    from pgdrive_b200 import devgen
+
+    @settings(max_examples=30, deadline=None, derandomize=True)
+    @given(st.integers(1, 4), st.integers(1, 6), st.sampled_from([3.0, 3.25, 3.5, 4.0, 4.5]),
+           st.sampled_from([40, 50, 70]), st.sampled_from([0.0, 0.05, 0.1, 0.15]), st.integers(0, 20000))
+    def check(lane_num, blocks, width, exit_length, density, seed):
+        mc = dict(type="block_num", config=blocks, lane_num=lane_num, lane_width=width, exit_length=exit_length)
+        gc = devgen.make_gen_config(mc, density, SPAWN)
+        rc, got, _ = _host().generate(seed, gc, devgen.caps_for(gc))
+        want = _python_tables(seed, mc, density, SPAWN)
+        if int(want["max_slots"]) > 32:
+            assert rc == 9
+            return
+        assert rc == 0, devgen.GEN_ERRORS.get(rc)
+        assert _same(want, got), (lane_num, blocks, width, exit_length, density, seed)
+
+    check()
