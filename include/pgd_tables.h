@@ -91,6 +91,9 @@ typedef struct {
   int32_t spawn_lane;      /* lane index on the first road (">", ">>") */
   double lane_width, exit_length, density, spawn_long, spawn_lat;
   int8_t fixed_types[32];  /* 0..6 = C S r R X T O (order of BLOCK_TYPE_DISTRIBUTION_V2) */
+  /* manager/map_manager.py:157-169: per-seed lane width = rand() * 1.5 + 3.0 and lane number = randint(2, 3) from
+   * the map manager's stream of the seed, replacing lane_width / lane_num above */
+  int32_t random_lane_width, random_lane_num;
 } PgdGenConfig;
 
 /* Per-map capacities of the generated tables (map m owns the fixed-stride slice [m * cap, (m + 1) * cap) of every

@@ -1408,12 +1408,19 @@ PGD_HD inline int generate_one(uint64_t seed, const GenConfig& cfg, const GenCap
                                GenOut& out) {
   Gen g;
   g.cfg = cfg;
+  if (cfg.random_lane_width || cfg.random_lane_num) {
+    // MapManager.add_random_to_map (manager/map_manager.py:157-169) on the stream MapManager.seed(seed) sets up
+    MT* rs = &scratch.mt[0];
+    mt_seeded(rs, seed);
+    if (cfg.random_lane_width) g.cfg.lane_width = mt_double(rs) * (4.5 - 3.0) + 3.0;
+    if (cfg.random_lane_num) g.cfg.lane_num = 2 + (int)mt_randint(rs, 1);  // randint(2, 3): always 2, no draw
+  }
   g.caps = caps;
   g.s = scratch;
   g.n_lanes = g.n_roads = g.n_blocks = 0;
   g.status = GEN_OK;
   for (int i = 0; i < 8; ++i) out.counts[i] = 0;
-  if (cfg.lane_num < 1 || cfg.lane_num > MAX_ROAD_LANES - 2 || caps.blocks < 2) {
+  if (g.cfg.lane_num < 1 || g.cfg.lane_num > MAX_ROAD_LANES - 2 || caps.blocks < 2) {
     return GEN_ERR_CONFIG;
   }
   search_blocks(g, seed);
@@ -1579,7 +1586,7 @@ PGD_HD inline int generate_one(uint64_t seed, const GenConfig& cfg, const GenCap
   pm.cell_off = out.cell_off; pm.entry_off = out.entry_off;
   pm.nx = nx; pm.ny = ny;
   pm.x0 = (float)x0; pm.y0 = (float)y0; pm.inv_cell = (float)(1.0 / CELL);
-  pm.lane_width = (float)cfg.lane_width; pm.lane_num = cfg.lane_num; pm.pad = 0;
+  pm.lane_width = (float)g.cfg.lane_width; pm.lane_num = g.cfg.lane_num; pm.pad = 0;
   out.counts[0] = n_lanes; out.counts[1] = n_roads; out.counts[2] = n_boxes; out.counts[3] = n_cells + 1;
   out.counts[7] = g.n_blocks;
 

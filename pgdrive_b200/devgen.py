@@ -28,7 +28,8 @@ class GenConfig(C.Structure):
     _fields_ = [
         ("block_num", C.c_int32), ("lane_num", C.c_int32), ("n_fixed", C.c_int32), ("spawn_lane", C.c_int32),
         ("lane_width", C.c_double), ("exit_length", C.c_double), ("density", C.c_double), ("spawn_long", C.c_double),
-        ("spawn_lat", C.c_double), ("fixed_types", C.c_int8 * 32)
+        ("spawn_lat", C.c_double), ("fixed_types", C.c_int8 * 32), ("random_lane_width", C.c_int32),
+        ("random_lane_num", C.c_int32)
     ]
 
 
@@ -37,7 +38,7 @@ class GenCaps(C.Structure):
                                          "cand")]
 
 
-def make_gen_config(map_config, density, spawn=((">", ">>", 0), 5.0, 0.0)):
+def make_gen_config(map_config, density, spawn=((">", ">>", 0), 5.0, 0.0), random_lane=(False, False)):
     """``map_config``: the reference's map_config dict (type block_num | block_sequence)."""
     lane, lon, lat = spawn
     if tuple(lane[:2]) != (">", ">>"):
@@ -48,6 +49,7 @@ def make_gen_config(map_config, density, spawn=((">", ">>", 0), 5.0, 0.0)):
     gc.exit_length = float(map_config["exit_length"])
     gc.density = float(density)
     gc.spawn_lane, gc.spawn_long, gc.spawn_lat = int(lane[2]), float(lon), float(lat)
+    gc.random_lane_width, gc.random_lane_num = int(bool(random_lane[0])), int(bool(random_lane[1]))
     if map_config["type"] == "block_num":
         gc.block_num, gc.n_fixed = int(map_config["config"]), 0
     elif map_config["type"] == "block_sequence":

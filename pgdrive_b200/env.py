@@ -285,11 +285,9 @@ class VecPGDriveEnv:
             stored = load_map_file(cfg["_load_map_from_json"], self.map_config, seeds)
         self._T = None
         random_lane = (bool(cfg["random_lane_width"]), bool(cfg["random_lane_num"]))
-        if cfg["device_mapgen"] and any(random_lane):
-            raise NotImplementedError("device_mapgen generates every seed with one lane configuration")
         if cfg["device_mapgen"] and tables_dict is None and stored is None:
             # the whole reset path runs on the GPU (pgd_generate_tables); tables never visit the host
-            gc = devgen.make_gen_config(self.map_config, cfg["traffic_density"], self._spawn)
+            gc = devgen.make_gen_config(self.map_config, cfg["traffic_density"], self._spawn, random_lane)
             slots = cfg["num_slots"] or 16
             while True:
                 self.engine = _Engine(cfg, self.num_envs, slots, int(cfg["device"]), bool(cfg["auto_reset"]),

@@ -310,3 +310,19 @@ def test_host_build_property_random_map_configs():
         assert _same(want, got), (lane_num, blocks, width, exit_length, density, seed)
 
     check()
+
+
+def test_host_build_random_lane_width_and_number():
+    """random_lane_width / random_lane_num decided per seed inside the generator (manager/map_manager.py:157-169)."""
+    from pgdrive_b200 import devgen
+    from pgdrive_b200.env import seed_map_config
+    for flags in ((True, True), (True, False), (False, True)):
+        gc = devgen.make_gen_config(V0, 0.1, SPAWN, random_lane=flags)
+        caps = devgen.caps_for(gc)
+        for s in list(range(1000, 1010)) + [5, 77, 2500]:
+            rc, got, _ = _host().generate(s, gc, caps)
+            assert rc == 0
+            want = _python_tables(s, seed_map_config(V0, s, *flags))
+            assert _same(want, got), (flags, s)
+            if flags[1]:
+                assert int(got["maps"]["lane_num"][0]) == 2
