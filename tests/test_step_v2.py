@@ -117,3 +117,30 @@ def test_side_and_lane_line_detectors(ns, ds, nl, dl):
         assert _same(a.step(act), b.step(act)), t
     a.close()
     b.close()
+
+
+def test_soak_with_a_feedback_policy_arrivals_crashes_and_exits():
+    """A lane-keeping feedback policy (steer towards the checkpoint, hold ~25 km/h) for 700 steps: episodes end by
+    arriving, by crashing into traffic and by leaving the road; every step is bit-identical to the oracle."""
+    n_seeds, n = 100, 200
+    T = _tables(range(1000, 1000 + n_seeds))
+    a, b = _pair(T, n, auto_reset=True)
+    eps = [i % n_seeds for i in range(n)]
+    assert np.array_equal(a.reset(range(n), eps), b.reset(range(n), eps))
+    rs = np.random.RandomState(9)
+    obs = a.obs.copy()
+    seen = dict(arrive=0, crash=0, out=0)
+    for t in range(700):
+        act = np.zeros((n, 2), np.float32)
+        act[:, 0] = np.clip(-(obs[:, 9] - 0.5) * 6.0 + rs.uniform(-0.05, 0.05, n), -1, 1)
+        act[:, 1] = np.where(obs[:, 3] < 0.3, 0.6, 0.0)
+        ra, rb = a.step(act, threads=4), b.step(act)
+        assert _same(ra, rb), t
+        obs = ra[0].copy()
+        fl = ra[3]["flags"]
+        seen["arrive"] += int(((fl & 4) != 0).sum())
+        seen["crash"] += int(((fl & 1) != 0).sum())
+        seen["out"] += int(((fl & 2) != 0).sum())
+    assert seen["arrive"] > 5 and seen["crash"] > 3 and seen["out"] > 30, seen
+    a.close()
+    b.close()
