@@ -445,6 +445,74 @@ class VecPGDriveEnv:
             pass
 
 
+class EgoView:
+    """Read-only stand-in for ``env.vehicle`` (component/vehicle/base_vehicle.py:390-425,683-698): the ego's pose and
+    flags read back from the simulator.  ``state`` / ``flags`` are callables so that every access is current."""
+    LENGTH, WIDTH, HEIGHT, MASS = 4.51, 1.852, 1.19, 1100.0  # DefaultVehicle (vehicle_type.py:7-20)
+    MAX_LENGTH, MAX_WIDTH = 5.8, 2.3
+
+    def __init__(self, state, flags, lane_name, destination, spawn_road):
+        self._state, self._flags, self._lane_name = state, flags, lane_name
+        self._destination, self._spawn_road = destination, spawn_road
+
+    def _veh(self):
+        return self._state()["veh"][0][0]
+
+    @property
+    def position(self):
+        v = self._veh()
+        return np.array([float(v["x"]), float(v["y"])])
+
+    @property
+    def heading_theta(self):
+        return float(self._veh()["heading"])
+
+    @property
+    def heading(self):
+        h = self.heading_theta
+        return np.array([np.cos(h), np.sin(h)])
+
+    @property
+    def speed(self):
+        """km/h, clipped at 0 like base_vehicle.py:400-408."""
+        return float(np.clip(self._veh()["speed"] * 3.6, 0.0, 100000.0))
+
+    @property
+    def velocity(self):
+        return self.heading * self.speed
+
+    @property
+    def steering(self):
+        return float(self._veh()["steer"])
+
+    @property
+    def throttle_brake(self):
+        return float(self._veh()["throttle"])
+
+    @property
+    def lane_index(self):
+        return self._lane_name(int(self._veh()["lane"]))
+
+    @property
+    def on_lane(self):
+        return bool(self._veh()["flags"] & cabi.V_ON_LANE)
+
+    crash_vehicle = property(lambda self: bool(self._flags() & cabi.F_CRASH_VEHICLE))
+    crash_sidewalk = property(lambda self: bool(self._flags() & cabi.F_CRASH_SIDEWALK))
+    out_of_route = property(lambda self: bool(self._flags() & cabi.F_OUT_OF_ROUTE))
+    on_yellow_continuous_line = property(lambda self: bool(self._flags() & cabi.F_ON_YELLOW))
+    on_white_continuous_line = property(lambda self: bool(self._flags() & cabi.F_ON_WHITE))
+    on_broken_line = property(lambda self: bool(self._flags() & cabi.F_ON_BROKEN))
+    arrive_destination = property(lambda self: bool(self._flags() & cabi.F_ARRIVE_DEST))
+
+    def get_state(self):
+        return {
+            "heading": self.heading_theta, "position": self.position.tolist(),
+            "done": self.crash_vehicle or self.out_of_route or self.crash_sidewalk or not self.on_lane,
+            "speed": self.speed, "spawn_road": self._spawn_road, "destination": self._destination(),
+        }
+
+
 class PGDriveEnv:
     """Single-environment drop-in (a ``num_envs=1`` view of the batched engine).  Maps are built lazily,
     one seed at a time, like the reference's map manager (manager/map_manager.py:98-155)."""
@@ -465,6 +533,7 @@ class PGDriveEnv:
         self.observation_space = Box(-0.0, 1.0, shape=(self.obs_dim, ), dtype=np.float32)
         self.action_space = make_action_space(self.config)
         self._parts, self._episode_of_seed = [], {}
+        self._maps = {}
         self._stored = None
         if self.config["load_map_from_json"] and self.config["_load_map_from_json"] is not None:
             self._stored = load_map_file(self.config["_load_map_from_json"], self.map_config,
@@ -500,6 +569,43 @@ class PGDriveEnv:
             self._info = torch.zeros((1, cabi.INFO_DT.itemsize // 4), dtype=torch.int32, device=dev)
             self._act = torch.zeros((1, 2), dtype=torch.float32, device=dev)
         self._engine.load(T)
+
+    # -- read-only views of the reference's object graph (envs/base_env.py:371-462) ----------------------------------
+    def _map_of(self, seed):
+        if seed not in self._maps:
+            mc = seed_map_config(self.map_config, seed, self.config["random_lane_width"], self.config["random_lane_num"])
+            kw = dict(lane_num=mc["lane_num"], lane_width=mc["lane_width"], exit_length=mc["exit_length"])
+            stored = (self._stored or {}).get(seed)
+            if stored is not None:
+                self._maps[seed] = mapgen.build_from_sequence(seed, stored, **kw)
+            elif mc["type"] == "block_num":
+                self._maps[seed] = mapgen.generate_map(seed, block_num=mc["config"], **kw)
+            else:
+                self._maps[seed] = mapgen.generate_map(seed, sequence=mc["config"], **kw)
+        return self._maps[seed]
+
+    @property
+    def current_map(self):
+        """The map of the current seed as the host generator's object (blocks, road network, block sequence)."""
+        return None if self._seed is None else self._map_of(self._seed)
+
+    @property
+    def maps(self):
+        """{seed: map or None}: which maps of [start_seed, start_seed + environment_num) have been visited."""
+        return {s: (self._map_of(s) if s in self._episode_of_seed else None)
+                for s in range(self.start_seed, self.start_seed + self.env_num)}
+
+    @property
+    def vehicle(self):
+        assert self._engine is not None, "Please initialize the environment first!"
+        flat = [(f, t, i) for (f, t), lanes in self.current_map.net.roads() for i in range(len(lanes))]
+        route = episode.route_for(self.current_map, tuple(self._spawn[0]), self._seed)
+        return EgoView(self.get_state, lambda: int(self._info.cpu().numpy().view(cabi.INFO_DT).reshape(-1)[0]["flags"]),
+                       lambda k: flat[k], lambda: (route[-2], route[-1]), tuple(self._spawn[0][:-1]))
+
+    @property
+    def vehicles(self):
+        return {self.DEFAULT_AGENT: self.vehicle}
 
     def dump_all_maps(self):
         """envs/pgdrive_env.py:260-288: every map of [start_seed, start_seed + environment_num) as block sequences."""

@@ -574,6 +574,18 @@ class PGMapData:
         self.lane_num = lane_num
         self.lane_width = lane_width
 
+    @property
+    def num_blocks(self):
+        return len(self.blocks)
+
+    @property
+    def road_network(self):
+        return self.net
+
+    def save_map(self):
+        """BaseMap.save_map (component/map/base_map.py:103-118)."""
+        return dict(block_sequence=[dict(b) for b in self.block_sequence])
+
 
 def search_sequence(seed, block_num=3, lane_num=3, lane_width=3.5, exit_length=50, sequence=None):
     """The BIG search: append random blocks, retry a block up to MAX_TRIAL times when it overlaps the

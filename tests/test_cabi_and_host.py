@@ -225,3 +225,24 @@ def test_effective_horizon_combines_horizon_and_auto_termination():
     assert effective_horizon(cfg, parse_map_config(cfg)) == 1500
     cfg.update(dict(auto_termination=False))
     assert effective_horizon(cfg, parse_map_config(cfg)) == 5000
+
+
+def test_ego_view_and_map_views_mirror_the_reference_properties():
+    """env.vehicle / env.current_map stand-ins (envs/base_env.py:371-462, base_vehicle.py:390-425,683-698), driven by
+    a synthetic state record (no GPU)."""
+    from pgdrive_b200 import cabi, mapgen
+    from pgdrive_b200.env import EgoView
+    st = np.zeros(1, cabi.ENV_STATE_DT)
+    st["veh"][0][0]["x"], st["veh"][0][0]["y"] = 12.5, -3.0
+    st["veh"][0][0]["heading"], st["veh"][0][0]["speed"] = 0.5, 10.0
+    st["veh"][0][0]["lane"], st["veh"][0][0]["flags"] = 4, cabi.V_ALIVE | cabi.V_ACTIVE | cabi.V_ON_LANE
+    m = mapgen.generate_map(1000)
+    flat = [(f, t, i) for (f, t), lanes in m.net.roads() for i in range(len(lanes))]
+    v = EgoView(lambda: st, lambda: cabi.F_ON_LANE | cabi.F_ON_BROKEN, lambda k: flat[k], lambda: ("a", "b"), (">", ">>"))
+    assert v.position.tolist() == [12.5, -3.0] and abs(v.speed - 36.0) < 1e-5 and v.heading_theta == 0.5
+    assert np.allclose(v.velocity, 36.0 * np.array([np.cos(0.5), np.sin(0.5)]))
+    assert v.lane_index == flat[4] and v.on_lane and v.on_broken_line and not v.crash_vehicle
+    s = v.get_state()
+    assert s["done"] is False and s["destination"] == ("a", "b") and s["spawn_road"] == (">", ">>")
+    assert m.num_blocks == 4 and m.road_network is m.net
+    assert [b["id"] for b in m.save_map()["block_sequence"]] == [b.id for b in m.blocks]
