@@ -449,7 +449,7 @@ class EgoView:
     """Read-only stand-in for ``env.vehicle`` (component/vehicle/base_vehicle.py:390-425,683-698): the ego's pose and
     flags read back from the simulator.  ``state`` / ``flags`` are callables so that every access is current."""
     LENGTH, WIDTH, HEIGHT, MASS = 4.51, 1.852, 1.19, 1100.0  # DefaultVehicle (vehicle_type.py:7-20)
-    MAX_LENGTH, MAX_WIDTH = 5.8, 2.3
+    MAX_LENGTH, MAX_WIDTH, MAX_STEERING = 10, 2.5, 60  # base_vehicle.py:83-85
 
     def __init__(self, state, flags, lane_name, destination, spawn_road):
         self._state, self._flags, self._lane_name = state, flags, lane_name
