@@ -1,9 +1,10 @@
 """Run the host builds of the generator, the v2 step and the oracle under ASan + UBSan."""
 import ctypes, os, sys
-sys.path.insert(0, "/root/repo")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
 import numpy as np
 from oracle import mapgen_host as mh, oracle as orc, step_v2_host as v2
-SAN = "/root/repo/oracle/_san"
+SAN = os.path.join(ROOT, "oracle", "_san")
 mh.LIB = os.path.join(SAN, "libpgd_mapgen_host.so"); mh.build = lambda force=False: mh.LIB
 orc.LIB = os.path.join(SAN, "libpgd_oracle.so"); orc.build = lambda force=False: orc.LIB
 v2.LIB = os.path.join(SAN, "libpgd_step_v2_host.so")
