@@ -23,6 +23,7 @@
 #include <limits.h>
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "../../include/pgd_tables.h"
 
@@ -310,6 +311,10 @@ V2_HD void step_env(const Tables& T, const State& S, const PgdConfig& cfg, int m
 
   // ---- phase A: load ------------------------------------------------------------------------------------------
   Veh veh[V];
+#ifdef V2_POISON  // host debugging: thread-local arrays start as garbage on the device; results must not depend on it
+  memset(veh, 0xff, sizeof(veh));
+  memset(&lc, 0xff, sizeof(lc));
+#endif
   uint32_t was_parked = 0;  // slots that entered this step as parked traffic
   uint32_t untouched = 0;   // slots whose stored state stays as it is
   uint32_t drop_ran = 0;    // parked slots whose drop counter changed
