@@ -59,10 +59,13 @@ __global__ void __launch_bounds__(V2_CTA_THREADS) pgd_step_v2_kernel(Tables T, S
   const int head = obs_dim - PGD_LIDAR_BEAMS;
   for (int c = 0; c < obs_dim; c += 32) {
     const int nc = obs_dim - c < 32 ? obs_dim - c : 32;
-    if (wrote)
+    if (wrote) {
+#pragma unroll 1
       for (int k = 0; k < nc; ++k) tile[warp][lane][k] = (c + k < head) ? row[c + k] : lidar_beam<V>(lc, c + k - head);
+    }
     __syncwarp();
     if (lane < nc)
+#pragma unroll 4
       for (int r = 0; r < 32; ++r)
         if ((wmask >> r) & 1u) obs[(size_t)(warp_env0 + r) * obs_dim + c + lane] = tile[warp][r][lane];
     __syncwarp();

@@ -29,18 +29,15 @@
 
 #ifdef __CUDACC__
 #define V2_HD __host__ __device__ __forceinline__
+// one out-of-line copy on the device: the accurate sincosf / atan2f / fmodf expand to hundreds of instructions each,
+// and inlined at every call site they made the kernel 10 k instructions (the cooperative kernel learnt the same
+// lesson, profiles/README.md r01d -> r01g)
+#define V2_HD_OUTLINE __host__ __device__ __noinline__
 #else
 #define V2_HD inline
+#define V2_HD_OUTLINE inline
 #endif
-#ifdef __CUDA_ARCH__
-#define V2_SINCOS(a, s, c) sincosf((a), &(s), &(c))
-#else
-#define V2_SINCOS(a, s, c) \
-  do {                     \
-    (s) = sinf(a);         \
-    (c) = cosf(a);         \
-  } while (0)
-#endif
+#define V2_SINCOS(a, s, c) pgdv2::sincos_hd((a), &(s), &(c))
 #define V2_LDG(p) pgdv2::ldg(p)
 
 namespace pgdv2 {
@@ -88,6 +85,15 @@ struct State {  // slot-major: per-slot arrays are indexed slot * num_envs + env
   F4* envf;   // previous steering, previous throttle, episode reward, episode energy
 };
 
+V2_HD_OUTLINE void sincos_hd(float a, float* s, float* c) {
+#ifdef __CUDA_ARCH__
+  sincosf(a, s, c);
+#else
+  *s = sinf(a);
+  *c = cosf(a);
+#endif
+}
+
 template <class T_>
 V2_HD T_ ldg(const T_* p) {  // read-only table data
 #ifdef __CUDA_ARCH__
@@ -116,10 +122,20 @@ V2_HD T_ load_rec(const T_* p) {
 
 V2_HD float clipf(float a, float lo, float hi) { return fminf(fmaxf(a, lo), hi); }
 
-V2_HD float wrap_to_pi(float x) {
+V2_HD_OUTLINE float wrap_to_pi(float x) {
   float m = fmodf(x + V2_PI, V2_TWO_PI);
   if (m < 0.0f) m += V2_TWO_PI;
   return m - V2_PI;
+}
+
+V2_HD_OUTLINE void arc_local(float cx, float cy, float ph0, float dir, float radius, float x, float y, float* lon,
+                             float* lat) {
+  float dx = x - cx, dy = y - cy;
+  float phi = atan2f(dy, dx);
+  phi = ph0 + wrap_to_pi(phi - ph0);
+  float r = sqrtf(dx * dx + dy * dy);
+  *lon = dir * (phi - ph0) * radius;
+  *lat = dir * (radius - r);
 }
 
 V2_HD void lane_local(const PgdLane& l, float x, float y, float& lon, float& lat) {
@@ -128,12 +144,7 @@ V2_HD void lane_local(const PgdLane& l, float x, float y, float& lon, float& lat
     lon = dx * l.ax + dy * l.ay;
     lat = dx * -l.ay + dy * l.ax;
   } else {
-    float dx = x - l.ax, dy = y - l.ay;
-    float phi = atan2f(dy, dx);
-    phi = l.ph0 + wrap_to_pi(phi - l.ph0);
-    float r = sqrtf(dx * dx + dy * dy);
-    lon = l.dir * (phi - l.ph0) * l.radius;
-    lat = l.dir * (l.radius - r);
+    arc_local(l.ax, l.ay, l.ph0, l.dir, l.radius, x, y, &lon, &lat);
   }
 }
 
@@ -164,7 +175,7 @@ V2_HD bool precedes(float ex, float ey, float sx, float sy) {
 
 struct Rect { float cx, cy, ux, uy, hl, hw; };
 
-V2_HD bool rect_overlap(const Rect& a, const Rect& b) {
+V2_HD_OUTLINE bool rect_overlap(const Rect& a, const Rect& b) {
   float dx = b.cx - a.cx, dy = b.cy - a.cy;
   float c = fabsf(a.ux * b.ux + a.uy * b.uy);
   float s = fabsf(a.ux * b.uy - a.uy * b.ux);
@@ -202,7 +213,7 @@ V2_HD float ray_rect(float ox, float oy, float dx, float dy, const Rect& r) {
   return t0;
 }
 
-V2_HD void project(float hx, float hy, float vx, float vy, float& fwd, float& side) {
+V2_HD_OUTLINE void project(float hx, float hy, float vx, float vy, float& fwd, float& side) {
   const float n = 1.0f + 1e-6f;
   fwd = (vx * hx + vy * hy) / n;
   side = (vx * -hy + vy * hx) / n;
@@ -225,7 +236,7 @@ struct Sub {
   float accel, brake_dv, sb, mu_g, lr;
 };
 
-V2_HD void substep(Veh& q, const Sub& sub, float dt) {
+V2_HD_OUTLINE void substep(Veh& q, const Sub& sub, float dt) {
   float speed = q.v;
   if (sub.accel > 0.0f) speed += sub.accel * dt;
   else speed = fmaxf(speed - sub.brake_dv, 0.0f);
@@ -256,7 +267,7 @@ struct LidarCtx {
 };
 
 template <int V>
-V2_HD float lidar_beam(const LidarCtx<V>& lc, int i) {
+V2_HD_OUTLINE float lidar_beam(const LidarCtx<V>& lc, int i) {
   float best = 1.0f;
   bool have_dir = false;
   float dx = 0.0f, dy = 0.0f;
@@ -278,7 +289,7 @@ V2_HD float lidar_beam(const LidarCtx<V>& lc, int i) {
   return best;
 }
 
-V2_HD void ensure_heading(Veh& q) {  // heading unit vector of a parked vehicle, on first use
+V2_HD_OUTLINE void ensure_heading(Veh& q) {  // heading unit vector of a parked vehicle, on first use
   if (!(q.vflags & V2_HDG_VALID)) {
     V2_SINCOS(q.h, q.hs, q.hc);
     q.vflags |= V2_HDG_VALID;
@@ -327,6 +338,7 @@ V2_HD void step_env(const Tables& T, const State& S, const PgdConfig& cfg, int m
       }
     }
   }
+  #pragma unroll 1
   for (int s = 0; s < n_slots; ++s) {
     Veh& q = veh[s];
     const PgdSlot& t = tpl[s];
@@ -384,6 +396,7 @@ V2_HD void step_env(const Tables& T, const State& S, const PgdConfig& cfg, int m
     if (envi.y < n_groups) {
       const int ego_road = V2_LDG(&lanes[veh[0].lane].road);
       if (ego_road == V2_LDG(&ep->trigger_road[envi.y])) {
+        #pragma unroll 1
         for (int s = 1; s < n_slots; ++s)
           if (tpl[s].group == envi.y) {
             veh[s].vflags |= PGD_V_ACTIVE;
@@ -394,10 +407,12 @@ V2_HD void step_env(const Tables& T, const State& S, const PgdConfig& cfg, int m
     }
     // ---- phase C: IDM ------------------------------------------------------------------------------------------
     bool any_awake = false;
+    #pragma unroll 1
     for (int s = 1; s < n_slots; ++s)
       any_awake = any_awake || ((veh[s].vflags & (PGD_V_ALIVE | PGD_V_ACTIVE)) == (PGD_V_ALIVE | PGD_V_ACTIVE));
     if (any_awake) {
       float olong[V], lsx[V], lsy[V], lex[V], ley[V], llen[V];
+      #pragma unroll 1
       for (int s = 0; s < n_slots; ++s) {
         if (!(veh[s].vflags & PGD_V_ALIVE)) continue;
         ensure_heading(veh[s]);
@@ -407,6 +422,7 @@ V2_HD void step_env(const Tables& T, const State& S, const PgdConfig& cfg, int m
         lane_local(l, veh[s].x, veh[s].y, lon, lat);
         olong[s] = lon;
       }
+      #pragma unroll 1
       for (int s = 1; s < n_slots; ++s) {
         Veh& q = veh[s];
         if ((q.vflags & (PGD_V_ALIVE | PGD_V_ACTIVE)) != (PGD_V_ALIVE | PGD_V_ACTIVE)) continue;
@@ -421,6 +437,7 @@ V2_HD void step_env(const Tables& T, const State& S, const PgdConfig& cfg, int m
         } else if (V2_LDG(&lanes[q.rt_lane].road) != cur_road_id) {
           ok = false;
           const float rex = V2_LDG(&lanes[q.rt_lane].ex), rey = V2_LDG(&lanes[q.rt_lane].ey);
+          #pragma unroll 1
           for (int k = 0; k < cur_road.n_lanes; ++k) {
             const PgdLane* c = lanes + cur_road.first_lane + k;
             if (precedes(rex, rey, V2_LDG(&c->sx), V2_LDG(&c->sy))) {
@@ -455,6 +472,7 @@ V2_HD void step_env(const Tables& T, const State& S, const PgdConfig& cfg, int m
           lane_local(l, q.x, q.y, cur_long, lat);
           const float left_long = l.length - cur_long;
           bool found_front = false, found_back = false;
+          #pragma unroll 1
           for (int j = 0; j < n_slots; ++j) {
             if (j == s || !(veh[j].vflags & PGD_V_ALIVE)) continue;
             const float ddx = veh[j].x - q.x, ddy = veh[j].y - q.y;
@@ -573,12 +591,14 @@ V2_HD void step_env(const Tables& T, const State& S, const PgdConfig& cfg, int m
     {
       const int ns = cfg.decision_repeat < V2_MAX_SUBSTEPS ? cfg.decision_repeat : V2_MAX_SUBSTEPS;
       float ego_travel = -1.0f;  // not known until the ego (slot 0, always alive) has been integrated
+      #pragma unroll 1
       for (int s = 0; s < n_slots; ++s) {
         Veh& q = veh[s];
         if (!(q.vflags & PGD_V_ALIVE)) continue;
         const float reach = veh[0].hl + veh[0].hw + q.hl + q.hw;
         if (s > 0 && ego_travel < 0.0f) {  // first vehicle after the ego: how far did the ego get from its start pose?
           float m2 = 0.0f;
+          #pragma unroll 1
           for (int k = 0; k < ns; ++k) {
             const float ex = ego_traj[k].x - last_x, ey = ego_traj[k].y - last_y;
             m2 = fmaxf(m2, ex * ex + ey * ey);
@@ -593,6 +613,7 @@ V2_HD void step_env(const Tables& T, const State& S, const PgdConfig& cfg, int m
           if (q.airborne > 0) drop_ran |= 1u << s;
           q.airborne = q.airborne > ns ? q.airborne - ns : 0;
           if (s == 0) {
+            #pragma unroll 1
             for (int k = 0; k < ns; ++k) {
               ego_traj[k].x = q.x; ego_traj[k].y = q.y; ego_traj[k].z = q.hc; ego_traj[k].w = q.hs;
             }
@@ -602,6 +623,7 @@ V2_HD void step_env(const Tables& T, const State& S, const PgdConfig& cfg, int m
             const float ddx0 = q.x - last_x, ddy0 = q.y - last_y;
             const float far = reach + ego_travel;
             if (ddx0 * ddx0 + ddy0 * ddy0 > far * far) continue;
+            #pragma unroll 1
             for (int k = 0; k < ns; ++k) {
               const float ddx = q.x - ego_traj[k].x, ddy = q.y - ego_traj[k].y;
               if (ddx * ddx + ddy * ddy <= reach * reach) {
@@ -631,6 +653,7 @@ V2_HD void step_env(const Tables& T, const State& S, const PgdConfig& cfg, int m
         const float tb = t.lr / (t.lf + t.lr) * tanf(delta);
         sub.sb = tb / sqrtf(1.0f + tb * tb);
         const bool at_rest = q.v == 0.0f && q.yaw == 0.0f && !(sub.accel > 0.0f);
+        #pragma unroll 1
         for (int k = 0; k < ns; ++k) {
           if (q.airborne > 0) q.airborne--;
           else if (!at_rest) substep(q, sub, cfg.dt);
@@ -655,6 +678,7 @@ V2_HD void step_env(const Tables& T, const State& S, const PgdConfig& cfg, int m
     const Veh& ego = veh[0];
     const Rect er = {ego.x, ego.y, ego.hc, ego.hs, ego.hl, ego.hw};
     const int32_t* ent = T.cell_entries + mp.entry_off;
+    #pragma unroll 1
     for (int s = 0; s < n_slots; ++s) {
       Veh& q = veh[s];
       if ((q.vflags & (PGD_V_ALIVE | PGD_V_ACTIVE)) != (PGD_V_ALIVE | PGD_V_ACTIVE)) continue;
@@ -716,6 +740,7 @@ V2_HD void step_env(const Tables& T, const State& S, const PgdConfig& cfg, int m
         lane_local(l, q.x, q.y, lon, lat);
         const int start = V2_LDG(&roads[l.road].start_node);
         if (lon < 5.0f) {
+          #pragma unroll 1
           for (int j = q.ck1; j < t.route_len - 1; ++j) {
             if (V2_LDG(&rnodes[j]) == start) {
               q.ck0 = j;
@@ -745,6 +770,7 @@ V2_HD void step_env(const Tables& T, const State& S, const PgdConfig& cfg, int m
     // pgd_step.cu phase F); beam values are computed by lidar_beam() at write-out
     lc.ex = ego.x; lc.ey = ego.y; lc.eh = ego.h;
     lc.n = 0;
+    #pragma unroll 1
     for (int s = 1; s < n_slots; ++s) {
       Veh& q = veh[s];
       if (!(q.vflags & PGD_V_ALIVE)) continue;
@@ -776,6 +802,7 @@ V2_HD void step_env(const Tables& T, const State& S, const PgdConfig& cfg, int m
     if (cfg.n_side > 0 || cfg.n_lane_line > 0) {
       const int n_rays = cfg.n_side + cfg.n_lane_line;
       const int32_t* ent = T.cell_entries + mp.entry_off;
+      #pragma unroll 1
       for (int rI = 0; rI < n_rays; ++rI) {
         const bool side = rI < cfg.n_side;
         const int i = side ? rI : rI - cfg.n_side;
@@ -793,6 +820,7 @@ V2_HD void step_env(const Tables& T, const State& S, const PgdConfig& cfg, int m
           if (cx < 0 || cy < 0 || cx >= mp.nx || cy >= mp.ny) continue;
           const int cell = mp.cell_off + cy * mp.nx + cx;
           const int b0 = V2_LDG(&T.cell_start[cell]), b1 = V2_LDG(&T.cell_start[cell + 1]);
+          #pragma unroll 1
           for (int k = b0; k < b1; ++k) {
             const PgdBox g = load_rec(boxes + V2_LDG(&ent[k]));
             if (!(g.kind == PGD_BOX_WHITE || g.kind == PGD_BOX_YELLOW || (!side && g.kind == PGD_BOX_BROKEN))) continue;
@@ -807,6 +835,7 @@ V2_HD void step_env(const Tables& T, const State& S, const PgdConfig& cfg, int m
     // the 4 nearest vehicles inside the 50 m cylinder (ties -> lower slot)
     {
       float d2s[V];
+      #pragma unroll 1
       for (int s = 1; s < n_slots; ++s) {
         d2s[s] = INFINITY;
         if (!(veh[s].vflags & PGD_V_ALIVE)) continue;
@@ -815,8 +844,10 @@ V2_HD void step_env(const Tables& T, const State& S, const PgdConfig& cfg, int m
         if (d2 < V2_LIDAR_RANGE * V2_LIDAR_RANGE) d2s[s] = d2;
       }
       const float esp = clipf(ego.v * 3.6f, 0.0f, 100000.0f);
+      #pragma unroll 1
       for (int rank = 0; rank < 4; ++rank) {
         int best = -1;
+        #pragma unroll 1
         for (int s = 1; s < n_slots; ++s)
           if (d2s[s] < INFINITY && (best < 0 || d2s[s] < d2s[best])) best = s;
         float* o4 = ob + 18 + 4 * rank;
@@ -855,6 +886,7 @@ V2_HD void step_env(const Tables& T, const State& S, const PgdConfig& cfg, int m
       lane_local(rl, last_x, last_y, long_last, lat_last);
       lane_local(rl, ego.x, ego.y, long_now, lat_now);
     }
+    #pragma unroll 1
     for (int c = 0; c < 2; ++c) {  // navigation.py:213-260
       const PgdLane l = load_rec(lanes + (c == 0 ? cur_road.first_lane : V2_LDG(&roads[V2_LDG(&rroads[ego.ck1])].first_lane)));
       const float later_middle = ((float)n_ref / 2.0f - 0.5f) * mp.lane_width;
@@ -956,6 +988,7 @@ V2_HD void step_env(const Tables& T, const State& S, const PgdConfig& cfg, int m
   // ---- phase G: store --------------------------------------------------------------------------------------------
   // Only what can have changed is written back: parked traffic has at most run its drop counter, vehicles removed in
   // an earlier step are not touched at all.  A freshly started episode writes every slot once.
+  #pragma unroll 1
   for (int s = 0; s < V; ++s) {
     const size_t gi = (size_t)s * num_envs + env;
     if (s < n_slots) {
