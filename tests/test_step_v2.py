@@ -144,3 +144,30 @@ def test_soak_with_a_feedback_policy_arrivals_crashes_and_exits():
     assert seen["arrive"] > 5 and seen["crash"] > 3 and seen["out"] > 30, seen
     a.close()
     b.close()
+
+
+def test_property_random_step_configurations():
+    """Randomly drawn step configurations (sub-steps per decision, step size, reward scheme, detectors, horizon,
+    auto-reset, policy): still bit-identical to the oracle."""
+    from hypothesis import given, settings, strategies as st
+    T = _tables(range(1000, 1012))
+
+    @settings(max_examples=14, deadline=None, derandomize=True)
+    @given(st.integers(1, 8), st.sampled_from([0.01, 0.02, 0.04]), st.booleans(), st.booleans(), st.booleans(),
+           st.sampled_from([0, 0, 6, 24]), st.sampled_from([0, 0, 5]), st.sampled_from([0, 40]),
+           st.sampled_from(["forward", "lane", "uniform"]), st.integers(0, 10**6))
+    def check(repeat, dt, use_lateral, route_done, auto_reset, n_side, n_lane_line, horizon, mode, seed):
+        cfg = dict(decision_repeat=repeat, dt=dt, use_lateral=use_lateral, out_of_route_done=route_done,
+                   auto_reset=auto_reset, n_side=n_side, n_lane_line=n_lane_line, horizon=horizon,
+                   side_distance=45.0, lane_line_distance=25.0)
+        a, b = _pair(T, 24, **cfg)
+        eps = [i % 12 for i in range(24)]
+        assert np.array_equal(a.reset(range(24), eps), b.reset(range(24), eps))
+        rs = np.random.RandomState(seed)
+        for t in range(70):
+            act = _actions(rs, 24, mode)
+            assert _same(a.step(act), b.step(act)), (cfg, mode, t)
+        a.close()
+        b.close()
+
+    check()
