@@ -1442,8 +1442,9 @@ PGD_HD inline int generate_one(uint64_t seed, const GenConfig& cfg, const GenCap
   if (g.status != GEN_OK) return g.status;
 
   // ---- numbering: roads in the map's iteration order, decoration last
-  // `order` lives at the end of the BFS queue buffer's second half? no: keep it on the stack (roads <= caps.roads)
-  int* order = g.s.cand + 3 * g.caps.cand;  // caller reserves caps.roads extra ints behind the candidate list
+  // three work arrays live behind the candidate list (the caller reserves 4 * caps.roads ints there): the emission
+  // order of the roads, the first flat lane id of every pool road, and the node codes in order of first appearance
+  int* order = g.s.cand + 3 * g.caps.cand;
   int n_order = 0;
   for (int bi = 0; bi < g.n_blocks; ++bi) {
     const GBlock& b = g.s.blocks[bi];
@@ -1459,7 +1460,6 @@ PGD_HD inline int generate_one(uint64_t seed, const GenConfig& cfg, const GenCap
   const int n_roads = n_order + (deco_lanes > 0 ? 1 : 0);
   if (n_roads > g.caps.roads) return GEN_ERR_ROADS;
   // flat lane ids: first lane of every pool road (-1 when not emitted); node ids by first appearance
-  // reuse the GRoad.bbox_valid? no -- small arrays in the queue buffer's tail are not safe; use a second scratch:
   int32_t* first_lane = order + g.caps.roads;       // [caps.roads] indexed by pool road
   int32_t* node_codes = first_lane + g.caps.roads;  // [2 * caps.roads] node id -> code
   int n_nodes = 0, n_lanes = 0;
