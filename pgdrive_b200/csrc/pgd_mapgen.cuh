@@ -94,7 +94,7 @@ struct GenScratch {  // per map, caller-provided
   GBlock* blocks;
   GBox* boxes;
   int32_t* queue;  // BFS entries: node, parent
-  int32_t* cand;   // spawn candidates: road, lane, k
+  int32_t* cand;   // spawn candidates (road, lane, k) x caps.cand, then 4 * caps.roads ints of work arrays
   MT* mt;          // 3 generators
 };
 
