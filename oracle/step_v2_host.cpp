@@ -66,6 +66,29 @@ void v2h_reset(void* p, const int32_t* env_ids, const int32_t* episode_ids, int 
   run(h, 1, nullptr, obs, nullptr, nullptr, info);
 }
 
+/* pgd_get_state for the slot-major layout (exchange format of include/pgd_tables.h) */
+void v2h_get_state(void* p, int env, PgdEnvState* out) {
+  HostV2* h = (HostV2*)p;
+  const int n = h->cfg.num_envs, V = h->cfg.num_slots;
+  memset(out, 0, sizeof(*out));
+  const I4 ei = h->S.envi[env];
+  const F4 ef = h->S.envf[env];
+  out->episode = ei.x; out->next_group = ei.y; out->done = ei.z; out->ep_len = ei.w;
+  out->prev_steer = ef.x; out->prev_throttle = ef.y; out->ep_reward = ef.z; out->energy = ef.w;
+  const int n_slots = h->T.episodes[ei.x].n_slots;
+  for (int i = 0; i < n_slots && i < V; ++i) {
+    const size_t gi = (size_t)i * n + env;
+    const F4 po = h->S.pose[gi], c = h->S.ctrl[gi], l = h->S.pidl[gi];
+    const I4 nv = h->S.nav[gi], m = h->S.misc[gi];
+    PgdVehState* s = &out->veh[i];
+    s->x = po.x; s->y = po.y; s->heading = po.z; s->speed = po.w;
+    s->steer = c.x; s->throttle = c.y; s->pid_hp = c.z; s->pid_hi = c.w;
+    s->pid_lp = l.x; s->pid_li = l.y; s->target_speed = l.z; s->yaw_rate = l.w;
+    s->lane = nv.x; s->ck0 = nv.y & 0xffff; s->ck1 = nv.y >> 16; s->rt_lane = nv.z; s->timer = nv.w;
+    s->rnd_n = m.x; s->airborne = m.y; s->flags = m.z;
+  }
+}
+
 void v2h_step(void* p, const float* actions, float* obs, float* reward, uint8_t* done, PgdInfo* info) {
   run((HostV2*)p, 0, actions, obs, reward, done, info);
 }

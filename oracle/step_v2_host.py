@@ -25,6 +25,7 @@ def lib():
         L.v2h_destroy.argtypes = [vp]
         L.v2h_reset.argtypes = [vp, vp, vp, C.c_int32, vp, vp]
         L.v2h_step.argtypes = [vp, vp, vp, vp, vp, vp]
+        L.v2h_get_state.argtypes = [vp, C.c_int32, vp]
         _lib = L
     return _lib
 
@@ -59,3 +60,8 @@ class HostStepV2:
         self.L.v2h_step(self.h, a.ctypes.data, self.obs.ctypes.data, self.reward.ctypes.data, self.done.ctypes.data,
                         self.info.ctypes.data)
         return self.obs, self.reward, self.done, self.info
+
+    def get_state(self, env):
+        s = np.zeros(1, cabi.ENV_STATE_DT)
+        self.L.v2h_get_state(self.h, int(env), s.ctypes.data)
+        return s

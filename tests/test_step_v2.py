@@ -171,3 +171,36 @@ def test_property_random_step_configurations():
         b.close()
 
     check()
+
+
+def test_stored_state_equals_the_oracles_state():
+    """What the layout writes back lazily (parked traffic: only the drop counter; removed vehicles: nothing) is, field
+    for field, the state the oracle holds -- checked every 20 steps of a rollout in which traffic wakes up and dies."""
+    T = _tables(range(1000, 1030))
+    n = 90
+    a, b = _pair(T, n, auto_reset=True)
+    eps = [i % 30 for i in range(n)]
+    a.reset(range(n), eps)
+    b.reset(range(n), eps)
+    rs = np.random.RandomState(4)
+    removed = 0
+    obs = a.obs.copy()
+    for t in range(600):
+        act = np.zeros((n, 2), np.float32)  # lane-keeping feedback: long episodes, traffic wakes up and arrives
+        act[:, 0] = np.clip(-(obs[:, 9] - 0.5) * 6.0 + rs.uniform(-0.05, 0.05, n), -1, 1)
+        act[:, 1] = np.where(obs[:, 3] < 0.3, 0.6, 0.0)
+        ra = a.step(act, threads=4)
+        assert _same(ra, b.step(act)), t
+        obs = ra[0].copy()
+        if t % 25 == 0 or t == 599:
+            for e in range(n):
+                sa, sb = a.get_state(e), b.get_state(e)
+                k = int(T["episodes"][eps[e]]["n_slots"])
+                for f in ("episode", "next_group", "done", "ep_len", "prev_steer", "prev_throttle", "ep_reward", "energy"):
+                    assert sa[f][0] == sb[f][0], (t, e, f)
+                va, vb = sa["veh"][0][:k], sb["veh"][0][:k]
+                assert va.tobytes() == vb.tobytes(), (t, e, [f for f in va.dtype.names if not np.array_equal(va[f], vb[f])])
+                removed += int(((va["flags"] & 1) == 0).sum())
+    assert removed > 0  # some traffic left its road and was removed during the rollout
+    a.close()
+    b.close()
