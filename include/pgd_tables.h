@@ -123,11 +123,16 @@ typedef struct {
   /* 0 (default): cooperative kernel, 16 / 32 threads per environment, state [env][slot];
    * 1 (experimental): one thread per environment, state [slot][env] (pgd_step_v2.cu) */
   int32_t layout;
+  /* envs/base_env.py:29, obs/state_obs.py:18-23,103-105: the ego is one of the five vehicle types (chosen per seed by
+   * the host) and the observation gains LENGTH / 10 and WIDTH / 2.5 after the lane-line beams */
+  int32_t random_agent_model;
 } PgdConfig;
 
-/* Observation length (obs/state_obs.py:18-23,108-115,125-130): (n_side or 2) + 6 + n_lane_line + 10 + 16 + 240. */
+/* Observation length (obs/state_obs.py:18-23,108-115,125-130): (n_side or 2) + 6 + n_lane_line [+ 2 vehicle
+ * dimensions] + 10 + 16 + 240. */
 static inline int32_t pgd_obs_dim(const PgdConfig* c) {
-  return (c->n_side > 0 ? c->n_side : 2) + 6 + c->n_lane_line + 10 + 16 + PGD_LIDAR_BEAMS;
+  return (c->n_side > 0 ? c->n_side : 2) + 6 + c->n_lane_line + (c->random_agent_model ? 2 : 0) + 10 + 16 +
+         PGD_LIDAR_BEAMS;
 }
 
 /* per-step info (base_vehicle.py:262-272, pgdrive_env.py:165-207, base_env.py:335-339) */

@@ -603,7 +603,12 @@ static void post_step(Oracle* o, Env* e, float last_x, float last_y, float last_
   }
   for (int i = 0; i < c->n_lane_line; ++i)
     obs[n_first + 6 + i] = detector_beam(o, m, ego, i, c->n_lane_line, c->lane_line_distance, 1);
-  float* const navi = obs_row + n_first + 6 + c->n_lane_line;
+  const int n_extra = c->random_agent_model ? 2 : 0;
+  if (n_extra) { /* obs/state_obs.py:103-105: LENGTH / MAX_LENGTH, WIDTH / MAX_WIDTH (base_vehicle.py:83-84) */
+    obs_row[n_first + 6 + c->n_lane_line] = clipf(ego->s->length / 10.0f, 0.0f, 1.0f);
+    obs_row[n_first + 6 + c->n_lane_line + 1] = clipf(ego->s->width / 2.5f, 0.0f, 1.0f);
+  }
+  float* const navi = obs_row + n_first + 6 + c->n_lane_line + n_extra;
   obs = obs_row + n_first - 2; /* obs[2..7] below are the six state values */
   obs[2] = heading_diff(lane_at(o, m, cur_road->first_lane + n_ref - 1), ego);
   obs[3] = clipf((sp + 1.0f) / (MAX_SPEED_KMH + 1.0f), 0.0f, 1.0f);

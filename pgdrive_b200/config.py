@@ -203,7 +203,7 @@ def default_config():
 # Options of the reference that this simulator does not implement.  They are accepted at their default
 # value and rejected otherwise, so that a config that silently changed behaviour cannot slip through.
 UNSUPPORTED_IF_CHANGED = {
-    "num_agents": 1, "is_multi_agent": False, "random_agent_model": False, "IDM_agent": False,
+    "num_agents": 1, "is_multi_agent": False, "IDM_agent": False,
     "use_render": False, "manual_control": False, "use_topdown": False, "offscreen_render": False, "traffic_mode": "trigger",
     "random_traffic": False, "accident_prob": 0., "gaussian_noise": 0.0,
     "dropout_prob": 0.0, "record_episode": False,

@@ -1031,6 +1031,8 @@ extern "C" int pgd_create(const PgdConfig* cfg, int device, PgdHandle** out) {
   if (cfg->num_envs <= 0) return fail(-1, "pgd_create: num_envs must be positive");
   if (cfg->num_slots != 16 && cfg->num_slots != 32) return fail(-1, "pgd_create: num_slots must be 16 or 32");
   if (cfg->layout != 0 && cfg->layout != 1) return fail(-1, "pgd_create: layout must be 0 or 1");
+  if (cfg->random_agent_model && cfg->layout != 1)
+    return fail(-3, "pgd_create: random_agent_model needs the one-thread-per-environment layout (layout = 1)");
   if (cfg->n_side < 0 || cfg->n_side > PGD_MAX_DETECTOR_BEAMS || cfg->n_lane_line < 0 ||
       cfg->n_lane_line > PGD_MAX_DETECTOR_BEAMS)
     return fail(-1, "pgd_create: detector beam counts must be in [0, 240]");

@@ -16,8 +16,8 @@
 using namespace pgdv2;
 
 #define V2_CTA_THREADS 64
-#define V2_HEAD (PGD_OBS_DIM - PGD_LIDAR_BEAMS)                         /* 34: state, navi, neighbours */
-#define V2_HEAD_DET (2 * PGD_MAX_DETECTOR_BEAMS + 6 + 10 + 16)          /* 512: with both detector fans */
+#define V2_HEAD (PGD_OBS_DIM - PGD_LIDAR_BEAMS + 2)                     /* 36: state, [vehicle size], navi, neighbours */
+#define V2_HEAD_DET (2 * PGD_MAX_DETECTOR_BEAMS + 6 + 2 + 10 + 16)      /* 514: with both detector fans */
 
 template <int V, int HEAD_CAP>
 __global__ void __launch_bounds__(V2_CTA_THREADS) pgd_step_v2_kernel(Tables T, State S, PgdConfig cfg, int mode,
@@ -35,7 +35,8 @@ __global__ void __launch_bounds__(V2_CTA_THREADS) pgd_step_v2_kernel(Tables T, S
   float row[HEAD_CAP];  // the row up to the lidar beams
   LidarCtx<V> lc;
   lc.n = 0;
-  const int obs_dim = (cfg.n_side > 0 ? cfg.n_side : 2) + 6 + cfg.n_lane_line + 10 + 16 + PGD_LIDAR_BEAMS;
+  const int obs_dim = (cfg.n_side > 0 ? cfg.n_side : 2) + 6 + cfg.n_lane_line + (cfg.random_agent_model ? 2 : 0) + 10 +
+                      16 + PGD_LIDAR_BEAMS;
   bool wrote = false;
   if (valid) {
     const I4 envi = S.envi[env];

@@ -765,7 +765,12 @@ V2_HD void step_env(const Tables& T, const State& S, const PgdConfig& cfg, int m
     // (state 2..7, navi 8..17, neighbours 18..33, lidar 34..) address the right part of the row
     const int n_first = cfg.n_side > 0 ? cfg.n_side : 2;
     float* const st = obs + n_first - 2;
-    float* const ob = obs + n_first + cfg.n_lane_line - 2;
+    const int n_extra = cfg.random_agent_model ? 2 : 0;
+    float* const ob = obs + n_first + cfg.n_lane_line + n_extra - 2;
+    if (n_extra) {  // obs/state_obs.py:103-105: LENGTH / MAX_LENGTH, WIDTH / MAX_WIDTH (base_vehicle.py:83-84)
+      obs[n_first + 6 + cfg.n_lane_line] = clipf(t0.length / 10.0f, 0.0f, 1.0f);
+      obs[n_first + 6 + cfg.n_lane_line + 1] = clipf(t0.width / 2.5f, 0.0f, 1.0f);
+    }
     // lidar: every chassis in range publishes its rectangle and the arc of beams that can reach it (exact cull, see
     // pgd_step.cu phase F); beam values are computed by lidar_beam() at write-out
     lc.ex = ego.x; lc.ey = ego.y; lc.eh = ego.h;

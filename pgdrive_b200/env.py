@@ -112,6 +112,7 @@ def seed_map_config(mc, seed, random_lane_width=False, random_lane_num=False):
 def _seed_tables(args):
     seed, mc, density, spawn = args[:4]
     stored = args[4] if len(args) > 4 else None
+    random_agent = bool(args[5]) if len(args) > 5 else False
     kw = dict(lane_num=mc["lane_num"], lane_width=mc["lane_width"], exit_length=mc["exit_length"])
     if stored is not None:  # restored from a map file: no block search (pg_map.py:48-71)
         pgmap = mapgen.build_from_sequence(seed, stored, **kw)
@@ -124,7 +125,8 @@ def _seed_tables(args):
     ts = tables.TableSet()
     mid = ts.add_map(pgmap)
     lane, lon, lat = spawn
-    ts.add_episode(pgmap, mid, episode.make_episode(pgmap, seed, density, tuple(lane)), tuple(lane), lon, lat)
+    ts.add_episode(pgmap, mid, episode.make_episode(pgmap, seed, density, tuple(lane), random_agent), tuple(lane), lon,
+                   lat)
     return ts.finish()
 
 
@@ -187,12 +189,14 @@ def dump_maps(seeds, map_config):
     return dict(map_config=dict(map_config), map_data=out)
 
 
-def build_seed_tables(seeds, map_config, density, spawn, workers=None, stored=None, random_lane=(False, False)):
+def build_seed_tables(seeds, map_config, density, spawn, workers=None, stored=None, random_lane=(False, False),
+                      random_agent_model=False):
     """Tables for a list of seeds, built in worker processes when there are many, with an optional
     on-disk cache ($PGDRIVE_B200_CACHE) because map search costs ~50 ms per seed.  ``stored`` = {seed: block
     sequence} restored from a map file."""
     seeds = [int(s) for s in seeds]
-    jobs = [(s, seed_map_config(map_config, s, *random_lane), density, spawn, (stored or {}).get(s)) for s in seeds]
+    jobs = [(s, seed_map_config(map_config, s, *random_lane), density, spawn, (stored or {}).get(s),
+             bool(random_agent_model)) for s in seeds]
     cache_dir = os.environ.get("PGDRIVE_B200_CACHE")
     path = None
     if cache_dir:
@@ -239,7 +243,8 @@ class _Engine:
             side_distance=cfg["vehicle_config"]["side_detector"]["distance"],
             n_lane_line=cfg["vehicle_config"]["lane_line_detector"]["num_lasers"],
             lane_line_distance=cfg["vehicle_config"]["lane_line_detector"]["distance"],
-            layout=1 if cfg.get("one_thread_per_env", False) else 0
+            layout=1 if cfg.get("one_thread_per_env", False) else 0,
+            random_agent_model=bool(cfg["random_agent_model"])
         )
         self.obs_dim = cabi.obs_dim(self.pcfg)
         self.h = C.c_void_p()
@@ -285,6 +290,11 @@ class VecPGDriveEnv:
             stored = load_map_file(cfg["_load_map_from_json"], self.map_config, seeds)
         self._T = None
         random_lane = (bool(cfg["random_lane_width"]), bool(cfg["random_lane_num"]))
+        if cfg["random_agent_model"] and not cfg["one_thread_per_env"]:
+            raise NotImplementedError("random_agent_model is only in the one-thread-per-environment layout "
+                                      "(one_thread_per_env=True) so far")
+        if cfg["random_agent_model"] and cfg["device_mapgen"]:
+            raise NotImplementedError("device_mapgen spawns the default ego vehicle")
         if cfg["device_mapgen"] and tables_dict is None and stored is None:
             # the whole reset path runs on the GPU (pgd_generate_tables); tables never visit the host
             gc = devgen.make_gen_config(self.map_config, cfg["traffic_density"], self._spawn, random_lane)
@@ -305,7 +315,8 @@ class VecPGDriveEnv:
             self.episode_of_seed = {int(s): i for i, s in enumerate(seeds)}
         else:
             self._T = tables_dict if tables_dict is not None else build_seed_tables(
-                seeds, self.map_config, cfg["traffic_density"], self._spawn, stored=stored, random_lane=random_lane
+                seeds, self.map_config, cfg["traffic_density"], self._spawn, stored=stored, random_lane=random_lane,
+                random_agent_model=cfg["random_agent_model"]
             )
             self.episode_of_seed = {int(s): i for i, s in enumerate(self._T["episodes"]["seed"])}
             need = int(self._T["max_slots"])
@@ -525,6 +536,8 @@ class PGDriveEnv:
     def __init__(self, config=None):
         self.config = self.default_config().update(config or {}, allow_add_new_key=False)
         check_supported(self.config)
+        if self.config["random_agent_model"]:
+            raise NotImplementedError("random_agent_model: use VecPGDriveEnv(one_thread_per_env=True)")
         self.start_seed, self.env_num = int(self.config["start_seed"]), int(self.config["environment_num"])
         self.map_config = parse_map_config(self.config)
         vc = self.config["vehicle_config"]

@@ -74,17 +74,23 @@ class EpisodeTemplate:
         self.seed = seed
         self.density = density
         self.ego_seed = None
+        self.ego_type = "default"
         self.ego_params = None
         self.ego_checkpoints = None
         self.block_vehicles = []  # [(trigger_road, [VehicleSlot])], LAST element triggers first
 
 
-def make_episode(pgmap, seed, density=0.1, spawn_lane=(">", ">>", 0)):
+def make_episode(pgmap, seed, density=0.1, spawn_lane=(">", ">>", 0), random_agent_model=False):
     engine_rs = rng.seeded(seed)
     traffic_rs = rng.seeded(seed)
     ep = EpisodeTemplate(seed, density)
+    # random_agent_model (manager/agent_manager.py:63-71, component/vehicle/vehicle_type.py:84-86): the agent manager's
+    # own stream of the seed picks one of the five types with equal probability
+    ep.ego_type = "default"
+    if random_agent_model:
+        ep.ego_type = TYPE_KEYS[int(rng.seeded(seed).choice(len(TYPE_KEYS), p=[1 / len(TYPE_KEYS)] * len(TYPE_KEYS)))]
     ep.ego_seed = rng.draw_seed(engine_rs)
-    ep.ego_params = sample_vehicle("default", ep.ego_seed)
+    ep.ego_params = sample_vehicle(ep.ego_type, ep.ego_seed)
     ep.ego_checkpoints = route_for(pgmap, spawn_lane, seed)
     if abs(density) < 1e-2:
         return ep

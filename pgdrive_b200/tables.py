@@ -280,8 +280,8 @@ class TableSet:
     def add_episode(self, pgmap, map_id, ep, spawn_lane=(">", ">>", 0), spawn_long=5.0, spawn_lat=0.0):
         mi = self.index[map_id]
         slot_off = len(self.slots)
-        self._slot(pgmap, mi, "default", ep.ego_params, spawn_lane, spawn_long, spawn_lat, -1, 0, None,
-                   ep.ego_checkpoints)
+        self._slot(pgmap, mi, getattr(ep, "ego_type", "default"), ep.ego_params, spawn_lane, spawn_long, spawn_lat, -1, 0,
+                   None, ep.ego_checkpoints)
         groups = list(reversed(ep.block_vehicles))  # trigger order: block 1 first
         if len(groups) > MAX_GROUPS:
             raise ValueError("more than %d traffic trigger groups" % MAX_GROUPS)

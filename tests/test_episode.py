@@ -28,3 +28,33 @@ def test_ego_params_known_answer():
     assert ep.ego_params["max_engine_force"] == 783.99267578125
     assert ep.ego_params["max_brake_force"] == 113.99264526367188
     assert ep.block_vehicles == []
+
+
+def test_random_agent_model_type_and_parameters_match_reference():
+    """random_agent_model (manager/agent_manager.py:63-71): ego vehicle type drawn per seed and its sampled
+    parameters, against the reference's own random_vehicle_type / parameter sampling
+    (tests/golden/reset_random_agent.json.gz, tools/make_golden.py random_agent)."""
+    from conftest import load_golden
+    from pgdrive_b200 import episode, mapgen
+    gold = load_golden("reset_random_agent.json.gz")
+    seen = set()
+    for s, rec in gold.items():
+        seed = int(s)
+        m = mapgen.generate_map(seed) if seed in (1000, 1001, 5) else None
+        if m is not None:
+            ep = episode.make_episode(m, seed, 0.0, random_agent_model=True)
+            assert ep.ego_type == rec["type"], s
+            for k, v in rec["params"].items():
+                assert float(ep.ego_params[k]) == v, (s, k)
+            assert episode.make_episode(m, seed, 0.0).ego_type == "default"
+        else:  # the draw alone (no map needed)
+            from pgdrive_b200 import rng
+            t = episode.TYPE_KEYS[int(rng.seeded(seed).choice(5, p=[1 / 5] * 5))]
+            assert t == rec["type"], s
+            p = episode.sample_vehicle(t, rng.draw_seed(rng.seeded(seed)))
+            for k, v in rec["params"].items():
+                assert float(p[k]) == v, (s, k)
+        body = episode.VEHICLE_BODY[rec["type"]]
+        assert (body[0], body[1]) == (rec["length"], rec["width"]) and rec["max_length"] == 10 and rec["max_width"] == 2.5
+        seen.add(rec["type"])
+    assert len(seen) >= 4

@@ -204,3 +204,30 @@ def test_stored_state_equals_the_oracles_state():
     assert removed > 0  # some traffic left its road and was removed during the rollout
     a.close()
     b.close()
+
+
+def test_random_agent_model_observation_and_dynamics():
+    """random_agent_model: the ego is one of five vehicle types per seed and the observation gains its length / 10 and
+    width / 2.5 after the (optional) lane-line beams (obs/state_obs.py:18-23,103-105)."""
+    from pgdrive_b200 import env as E
+    from pgdrive_b200.episode import VEHICLE_BODY, TYPE_KEYS
+    seeds = list(range(1000, 1020))
+    T = E.merge_tables([E._seed_tables((s, V0, 0.1, SPAWN, None, True)) for s in seeds])
+    types = [TYPE_KEYS[int(T["slots"][int(e["slot_off"])]["type"])] for e in T["episodes"]]
+    assert len(set(types)) >= 3
+    for cfg in (dict(), dict(n_side=6, n_lane_line=4, side_distance=50.0, lane_line_distance=20.0)):
+        a, b = _pair(T, 40, auto_reset=True, random_agent_model=True, **cfg)
+        eps = [i % 20 for i in range(40)]
+        oa, ob = a.reset(range(40), eps), b.reset(range(40), eps)
+        assert np.array_equal(oa, ob)
+        n_first, nl = cfg.get("n_side", 0) or 2, cfg.get("n_lane_line", 0)
+        assert oa.shape[1] == n_first + 6 + nl + 2 + 266
+        for i in range(40):
+            body = VEHICLE_BODY[types[eps[i]]]
+            assert abs(oa[i, n_first + 6 + nl] - body[0] / 10) < 1e-6 and abs(oa[i, n_first + 6 + nl + 1] - body[1] / 2.5) < 1e-6
+        rs = np.random.RandomState(6)
+        for t in range(200):
+            act = _actions(rs, 40, "forward")
+            assert _same(a.step(act), b.step(act)), t
+        a.close()
+        b.close()

@@ -980,3 +980,26 @@ def cmd_random_lane(seeds, tag):
 
 if __name__ == "__main__" and sys.argv[1] == "random_lane":
     cmd_random_lane(list(range(1000, 1012)) + [5, 77, 2500], "random_lane")
+
+
+def cmd_random_agent(seeds, tag):
+    """random_agent_model: the ego's vehicle type per seed, from the reference's own random_vehicle_type on the stream
+    AgentManager.seed(current_seed) sets up (manager/agent_manager.py:63-71, vehicle_type.py:84-86), and the type's
+    dimensions / sampled parameters."""
+    from pgdrive.component.vehicle.vehicle_type import random_vehicle_type, vehicle_type
+    names = {v: k for k, v in vehicle_type.items()}
+    out = {}
+    for s in seeds:
+        cls = random_vehicle_type(get_np_random(s))
+        ego_seed = int(get_np_random(s).randint(0, 65536))  # BaseEngine.spawn_object -> generate_seed (first draw)
+        out[str(s)] = dict(type=names[cls], length=float(cls.LENGTH), width=float(cls.WIDTH),
+                           max_length=float(cls.MAX_LENGTH), max_width=float(cls.MAX_WIDTH),
+                           params=sample_vehicle_params(cls, ego_seed))
+    path = os.path.join(GOLD, "reset_%s.json.gz" % tag)
+    with gzip.open(path, "wt") as f:
+        json.dump(out, f)
+    print("wrote", path, os.path.getsize(path))
+
+
+if __name__ == "__main__" and sys.argv[1] == "random_agent":
+    cmd_random_agent(list(range(1000, 1040)) + [0, 5, 77, 2500], "random_agent")
