@@ -14,10 +14,8 @@ LIB = os.path.join(HERE, "_build", "libpgd_oracle.so")
 
 
 def build(force=False):
-    src = os.path.join(HERE, "pgd_oracle.c")
-    hdr = os.path.join(os.path.dirname(HERE), "include", "pgd_tables.h")
-    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
-        subprocess.check_call(["make", "-C", HERE, "-B"], stdout=subprocess.DEVNULL)
+    """make decides what is stale (sources and the shared headers are its prerequisites)."""
+    subprocess.check_call(["make", "-C", HERE] + (["-B"] if force else []), stdout=subprocess.DEVNULL)
     return LIB
 
 

@@ -23,6 +23,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include "../include/pgd_math.h" /* shared float32 sin / cos / atan2 / exp: same bits as the CUDA build */
 #include "../include/pgd_tables.h"
 
 #define PI_F 3.14159265358979323846f
@@ -63,11 +64,10 @@ typedef struct {
 
 static float clipf(float a, float lo, float hi) { return fminf(fmaxf(a, lo), hi); } /* cutils.pyx:153 */
 
-static float wrap_to_pi(float x) { /* utils/math_utils.py:32-33 (python modulo) */
-  float m = fmodf(x + PI_F, TWO_PI_F);
-  if (m < 0.0f) m += TWO_PI_F;
-  return m - PI_F;
-}
+static float wrap_to_pi(float x) { return pgd_wrap_to_pi(x); } /* utils/math_utils.py:32-33 */
+
+static float cosf_(float a) { float s, c; pgd_sincosf(a, &s, &c); return c; }
+static float sinf_(float a) { float s, c; pgd_sincosf(a, &s, &c); return s; }
 
 /* ---- lanes: straight_lane.py:53-67, circular_lane.py:46-67 ------------------------------------ */
 static void lane_local(const PgdLane* l, float x, float y, float* lon, float* lat) {
@@ -77,7 +77,7 @@ static void lane_local(const PgdLane* l, float x, float y, float* lon, float* la
     *lat = dx * -l->ay + dy * l->ax;
   } else {
     float dx = x - l->ax, dy = y - l->ay;
-    float phi = atan2f(dy, dx);
+    float phi = pgd_atan2f(dy, dx);
     phi = l->ph0 + wrap_to_pi(phi - l->ph0);
     float r = sqrtf(dx * dx + dy * dy);
     *lon = l->dir * (phi - l->ph0) * l->radius;
@@ -92,8 +92,8 @@ static void lane_position(const PgdLane* l, float lon, float lat, float* x, floa
   } else {
     float phi = l->dir * lon / l->radius + l->ph0;
     float r = l->radius - lat * l->dir;
-    *x = l->ax + r * cosf(phi);
-    *y = l->ay + r * sinf(phi);
+    *x = l->ax + r * cosf_(phi);
+    *y = l->ay + r * sinf_(phi);
   }
 }
 
@@ -112,7 +112,7 @@ static int lane_precedes(const PgdLane* a, const PgdLane* b) { /* abs_lane.py:11
 typedef struct { float cx, cy, ux, uy, hl, hw; } Rect;
 
 static Rect veh_rect(const Veh* v) {
-  Rect r = {v->x, v->y, cosf(v->h), sinf(v->h), v->s->length * 0.5f, v->s->width * 0.5f};
+  Rect r = {v->x, v->y, cosf_(v->h), sinf_(v->h), v->s->length * 0.5f, v->s->width * 0.5f};
   return r;
 }
 
@@ -168,7 +168,7 @@ static int route_node(const Oracle* o, const Veh* v, int k) { return o->t.route_
 
 /* ---- localisation: scene_utils.py:138-185 + navigation.py:155-211,262-282,328-344 -------------- */
 static void localize(const Oracle* o, const PgdMap* m, Veh* v) {
-  float hx = cosf(v->h), hy = sinf(v->h);
+  float hx = cosf_(v->h), hy = sinf_(v->h);
   int cur_road = route_road(o, v, v->ck0);
   int next_road = (v->ck0 == v->ck1) ? -1 : route_road(o, v, v->ck1);
   int first_any = -1, first_cur = -1, first_next = -1;
@@ -413,12 +413,12 @@ static void idm_act(const Oracle* o, const PgdMap* m, Env* e, int self, float* s
   steering += pid(&v->lp, &v->li, 0.3f, 0.002f, 0.05f, -lat);
   /* acceleration (:254-271), speeds in km/h as in the reference */
   float sp = speed_kmh(v);
-  float acc = 1.0f - powf(fmaxf(sp, 0.0f) / v->target_speed, 10.0f);
+  float acc = 1.0f - pgd_pow10f(fmaxf(sp, 0.0f) / v->target_speed);
   if (front_obj >= 0) {
     const Veh* f = &e->v[front_obj];
-    float hx = cosf(v->h), hy = sinf(v->h);
+    float hx = cosf_(v->h), hy = sinf_(v->h);
     float fs = speed_kmh(f);
-    float dvx = sp * hx - fs * cosf(f->h), dvy = sp * hy - fs * sinf(f->h);
+    float dvx = sp * hx - fs * cosf_(f->h), dvy = sp * hy - fs * sinf_(f->h);
     float dv = dvx * hx + dvy * hy;
     float d_star = 10.0f + sp * 1.5f + sp * dv / (2.0f * sqrtf(5.0f));
     float d = front_dist;
@@ -448,7 +448,7 @@ static void physics_substep(Veh* v, float dt, int overspeed) {
     speed = fmaxf(speed - dv, 0.0f);
   }
   float delta = clipf(-v->steer * s->max_steer, -1.4f, 1.4f); /* +steering = left = heading decreases */
-  float tb = s->lr / (s->lf + s->lr) * tanf(delta);
+  float tb = s->lr / (s->lf + s->lr) * pgd_tanf(delta);
   float sb0 = tb / sqrtf(1.0f + tb * tb);
   /* yaw rate relaxes towards the kinematic-bicycle value (tyre relaxation + yaw inertia, tau = 0.1 s) ... */
   float yaw = v->w + (speed * sb0 / s->lr - v->w) * (dt / YAW_TAU);
@@ -456,7 +456,7 @@ static void physics_substep(Veh* v, float dt, int overspeed) {
   if (speed * fabsf(yaw) > mu_g) yaw = copysignf(mu_g / speed, yaw);
   float sb = speed > 1e-3f ? clipf(yaw * s->lr / speed, -1.0f, 1.0f) : 0.0f;
   float cb = sqrtf(fmaxf(1.0f - sb * sb, 0.0f));
-  float ch = cosf(v->h), sh = sinf(v->h);
+  float ch = cosf_(v->h), sh = sinf_(v->h);
   v->x += speed * (ch * cb - sh * sb) * dt;
   v->y += speed * (sh * cb + ch * sb) * dt;
   float h = v->h + yaw * dt;
@@ -488,7 +488,7 @@ static void navi_info(const Oracle* o, const PgdMap* m, const Veh* v, int road_i
     dy = dy / dn * 50.0f;
   }
   float ph, ps;
-  project(cosf(v->h), sinf(v->h), dx, dy, &ph, &ps);
+  project(cosf_(v->h), sinf_(v->h), dx, dy, &ph, &ps);
   float bend = 0.0f, dir = 0.0f, angle = 0.0f;
   if (ref->kind == PGD_LANE_ARC) {
     bend = ref->radius / (60.0f + (float)n_ref * m->lane_width);
@@ -516,7 +516,7 @@ static float heading_diff(const PgdLane* l, const Veh* v) { /* base_vehicle.py:4
   }
   float ln = sqrtf(lx * lx + ly * ly);
   if (!(ln > 0.0f)) return 0.0f;
-  float c = (cosf(v->h) * lx + sinf(v->h) * ly) / ln;
+  float c = (cosf_(v->h) * lx + sinf_(v->h) * ly) / ln;
   return clipf(c, -1.0f, 1.0f) / 2.0f + 0.5f;
 }
 
@@ -526,7 +526,7 @@ static float heading_diff(const PgdLane* l, const Veh* v) { /* base_vehicle.py:4
 static float detector_beam(const Oracle* o, const PgdMap* m, const Veh* ego, int i, int n, float distance,
                            int with_broken) {
   float ang = (float)i * (TWO_PI_F / (float)n) + PI_F / 2 + ego->h;
-  float dx = cosf(ang) * distance, dy = sinf(ang) * distance;
+  float dx = cosf_(ang) * distance, dy = sinf_(ang) * distance;
   float best = 1.0f;
   for (int b = 0; b < m->n_boxes; ++b) {
     const PgdBox* box = &o->t.boxes[m->box_off + b];
@@ -630,7 +630,7 @@ static void post_step(Oracle* o, Env* e, float last_x, float last_y, float last_
       float dx = e->v[objs[k]].x - ego->x, dy = e->v[objs[k]].y - ego->y;
       d2[k] = dx * dx + dy * dy;
     }
-    float hx = cosf(ego->h), hy = sinf(ego->h);
+    float hx = cosf_(ego->h), hy = sinf_(ego->h);
     for (int slot = 0; slot < 4; ++slot) {
       int best = -1;
       for (int k = 0; k < n; ++k)
@@ -645,7 +645,7 @@ static void post_step(Oracle* o, Env* e, float last_x, float last_y, float last_
       float pf, ps, vf, vs;
       project(hx, hy, w->x - ego->x, w->y - ego->y, &pf, &ps);
       float ws = speed_kmh(w);
-      project(hx, hy, ws * cosf(w->h) - sp * hx, ws * sinf(w->h) - sp * hy, &vf, &vs);
+      project(hx, hy, ws * cosf_(w->h) - sp * hx, ws * sinf_(w->h) - sp * hy, &vf, &vs);
       q[0] = clipf((pf / LIDAR_RANGE + 1.0f) / 2.0f, 0.0f, 1.0f);
       q[1] = clipf((ps / LIDAR_RANGE + 1.0f) / 2.0f, 0.0f, 1.0f);
       q[2] = clipf((vf / MAX_SPEED_KMH + 1.0f) / 2.0f, 0.0f, 1.0f);
@@ -655,7 +655,7 @@ static void post_step(Oracle* o, Env* e, float last_x, float last_y, float last_
   /* 240-beam lidar against every other chassis (cutils.pyx:60-142) */
   for (int i = 0; i < PGD_LIDAR_BEAMS; ++i) {
     float ang = (float)i * (TWO_PI_F / (float)PGD_LIDAR_BEAMS) + ego->h;
-    float dx = cosf(ang) * LIDAR_RANGE, dy = sinf(ang) * LIDAR_RANGE;
+    float dx = cosf_(ang) * LIDAR_RANGE, dy = sinf_(ang) * LIDAR_RANGE;
     float best = 1.0f;
     for (int j = 1; j < e->n_slots; ++j) {
       if (!e->v[j].alive) continue;
@@ -693,7 +693,7 @@ static void post_step(Oracle* o, Env* e, float last_x, float last_y, float last_
     else if (crash_vehicle) cost = c->crash_vehicle_cost;
     is_done = (flags & PGD_F_ARRIVE_DEST) || out_of_road || crash_vehicle;
     float ddx = last_x - ego->x, ddy = last_y - ego->y; /* base_vehicle.py:278-290 */
-    step_energy = 3.25f * expf(0.01f * sp) * (sqrtf(ddx * ddx + ddy * ddy) / 1000.0f) / 100.0f * 1000.0f;
+    step_energy = 3.25f * pgd_expf(0.01f * sp) * (sqrtf(ddx * ddx + ddy * ddy) / 1000.0f) / 100.0f * 1000.0f;
     e->energy += step_energy;
     e->ep_reward += r;
     e->ep_len += 1;
@@ -892,6 +892,6 @@ void orc_lane_local(const PgdLane* l, float x, float y, float* out) { lane_local
 void orc_lane_position(const PgdLane* l, float lon, float lat, float* out) { lane_position(l, lon, lat, out, out + 1); }
 float orc_lane_heading_at(const PgdLane* l, float lon) { return lane_heading_at(l, lon); }
 float orc_ray_rect(float ox, float oy, float dx, float dy, float cx, float cy, float h, float len, float wid) {
-  Rect r = {cx, cy, cosf(h), sinf(h), len * 0.5f, wid * 0.5f};
+  Rect r = {cx, cy, cosf_(h), sinf_(h), len * 0.5f, wid * 0.5f};
   return ray_rect(ox, oy, dx, dy, &r);
 }

@@ -6,7 +6,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INC = os.path.join(HERE, "..", "include")
 OUT = os.path.join(CSRC, "libpgdrive_b200.so")
-COMMON = ["pgd_internal.h", os.path.join(INC, "pgdrive_b200.h"), os.path.join(INC, "pgd_tables.h")]
+COMMON = ["pgd_internal.h", os.path.join(INC, "pgdrive_b200.h"), os.path.join(INC, "pgd_tables.h"),
+          os.path.join(INC, "pgd_math.h")]
 # translation unit -> extra dependencies
 UNITS = {
     "pgd_step.cu": [],

@@ -23,6 +23,7 @@
 
 #include <string>
 
+#include "../../include/pgd_math.h"
 #include "../../include/pgdrive_b200.h"
 #include "pgd_internal.h"
 
@@ -64,7 +65,7 @@ __device__ __forceinline__ float clipf(float a, float lo, float hi) { return fmi
 
 __device__ __noinline__ float2 sincos2(float a) {  // (sin, cos); single out-of-line copy of the accurate sincosf
   float s, c;
-  sincosf(a, &s, &c);
+  pgd_sincosf(a, &s, &c);
   return make_float2(s, c);
 }
 #define SINCOS(angle, s_out, c_out)          \
@@ -77,9 +78,7 @@ __device__ __noinline__ float2 sincos2(float a) {  // (sin, cos); single out-of-
 // Out-of-line on purpose: fmodf / atan2f / sincosf expand to hundreds of instructions each and were inlined at a
 // dozen call sites; the kernel then missed the instruction cache for 64 % of its issue slots (profiles/r01d).
 __device__ __noinline__ float wrap_to_pi(float x) {
-  float m = fmodf(x + PI_F, TWO_PI_F);
-  if (m < 0.0f) m += TWO_PI_F;
-  return m - PI_F;
+  return pgd_wrap_to_pi(x);
 }
 
 struct Lane {  // registers copy of a PgdLane (4 x 16 B loads)
@@ -101,7 +100,7 @@ __device__ __forceinline__ Lane load_lane(const PgdLane* p) {
 
 __device__ __noinline__ float2 arc_local(float cx, float cy, float ph0, float dir, float radius, float x, float y) {
   float dx = x - cx, dy = y - cy;
-  float phi = atan2f(dy, dx);
+  float phi = pgd_atan2f(dy, dx);
   phi = ph0 + wrap_to_pi(phi - ph0);
   float r = sqrtf(dx * dx + dy * dy);
   return make_float2(dir * (phi - ph0) * radius, dir * (radius - r));
@@ -500,7 +499,7 @@ pgd_step_kernel(DevTables T, DevState S, PgdConfig cfg, int mode, int env_begin,
       // acceleration
       {
         const float sp = clipf(v * 3.6f, 0.0f, 100000.0f);
-        float acc = 1.0f - powf(fmaxf(sp, 0.0f) / target_speed, 10.0f);
+        float acc = 1.0f - pgd_pow10f(fmaxf(sp, 0.0f) / target_speed);
         if (front_obj >= 0) {
           const float hx = sh.ux[slot], hy = sh.uy[slot];
           const float fs = clipf(sh.v[front_obj] * 3.6f, 0.0f, 100000.0f);
@@ -534,7 +533,7 @@ pgd_step_kernel(DevTables T, DevState S, PgdConfig cfg, int mode, int env_begin,
         sub.brake_dv = fminf(4.0f * imp / t1.y, sub.mu_g * cfg.dt);
       }
       const float delta = clipf(-steer * t2.z, -1.4f, 1.4f);
-      const float tb = t1.w / (t1.z + t1.w) * tanf(delta);
+      const float tb = t1.w / (t1.z + t1.w) * pgd_tanf(delta);
       sub.sb = tb / sqrtf(1.0f + tb * tb);
     }
     // A vehicle at rest with no yaw rate and no engine force (parked traffic, a braking ego) is a fixed point of the
@@ -707,8 +706,8 @@ pgd_step_kernel(DevTables T, DevState S, PgdConfig cfg, int mode, int env_begin,
         bn = PGD_LIDAR_BEAMS;
         if (d > hd * 1.001f) {
           const float per_rad = (float)PGD_LIDAR_BEAMS / TWO_PI_F;
-          const float c = (atan2f(dy, dx) - eh) * per_rad;
-          const float w = asinf(fminf(hd / d, 1.0f)) * per_rad;
+          const float c = (pgd_atan2f(dy, dx) - eh) * per_rad;
+          const float w = pgd_asinf(fminf(hd / d, 1.0f)) * per_rad;
           const int n = (int)ceilf(2.0f * w) + 3;
           if (n < PGD_LIDAR_BEAMS) {
             bn = n;
@@ -935,7 +934,7 @@ pgd_step_kernel(DevTables T, DevState S, PgdConfig cfg, int mode, int env_begin,
       else if (crash) cost = cfg.crash_vehicle_cost;
       is_done = ((flags & PGD_F_ARRIVE_DEST) || out_of_road || crash) ? 1 : 0;
       const float ddx = last_x - x, ddy = last_y - y;
-      step_energy = 3.25f * expf(0.01f * sp) * (sqrtf(ddx * ddx + ddy * ddy) / 1000.0f) / 100.0f * 1000.0f;
+      step_energy = 3.25f * pgd_expf(0.01f * sp) * (sqrtf(ddx * ddx + ddy * ddy) / 1000.0f) / 100.0f * 1000.0f;
       envf.w += step_energy;
       envf.z += r;
       envi.w += 1;

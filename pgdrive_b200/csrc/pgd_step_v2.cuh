@@ -25,6 +25,7 @@
 #include <stdint.h>
 #include <string.h>
 
+#include "../../include/pgd_math.h"
 #include "../../include/pgd_tables.h"
 
 #ifdef __CUDACC__
@@ -86,12 +87,7 @@ struct State {  // slot-major: per-slot arrays are indexed slot * num_envs + env
 };
 
 V2_HD_OUTLINE void sincos_hd(float a, float* s, float* c) {
-#ifdef __CUDA_ARCH__
-  sincosf(a, s, c);
-#else
-  *s = sinf(a);
-  *c = cosf(a);
-#endif
+  pgd_sincosf(a, s, c);
 }
 
 template <class T_>
@@ -123,15 +119,13 @@ V2_HD T_ load_rec(const T_* p) {
 V2_HD float clipf(float a, float lo, float hi) { return fminf(fmaxf(a, lo), hi); }
 
 V2_HD_OUTLINE float wrap_to_pi(float x) {
-  float m = fmodf(x + V2_PI, V2_TWO_PI);
-  if (m < 0.0f) m += V2_TWO_PI;
-  return m - V2_PI;
+  return pgd_wrap_to_pi(x);
 }
 
 V2_HD_OUTLINE void arc_local(float cx, float cy, float ph0, float dir, float radius, float x, float y, float* lon,
                              float* lat) {
   float dx = x - cx, dy = y - cy;
-  float phi = atan2f(dy, dx);
+  float phi = pgd_atan2f(dy, dx);
   phi = ph0 + wrap_to_pi(phi - ph0);
   float r = sqrtf(dx * dx + dy * dy);
   *lon = dir * (phi - ph0) * radius;
@@ -568,7 +562,7 @@ V2_HD void step_env(const Tables& T, const State& S, const PgdConfig& cfg, int m
         }
         {  // acceleration
           const float sp = clipf(q.v * 3.6f, 0.0f, 100000.0f);
-          float acc = 1.0f - powf(fmaxf(sp, 0.0f) / q.tspeed, 10.0f);
+          float acc = 1.0f - pgd_pow10f(fmaxf(sp, 0.0f) / q.tspeed);
           if (front_obj >= 0) {
             const float hx = q.hc, hy = q.hs;
             const float fs = clipf(veh[front_obj].v * 3.6f, 0.0f, 100000.0f);
@@ -650,7 +644,7 @@ V2_HD void step_env(const Tables& T, const State& S, const PgdConfig& cfg, int m
           sub.brake_dv = fminf(4.0f * imp / t.mass, sub.mu_g * cfg.dt);
         }
         const float delta = clipf(-q.steer * t.max_steer, -1.4f, 1.4f);
-        const float tb = t.lr / (t.lf + t.lr) * tanf(delta);
+        const float tb = t.lr / (t.lf + t.lr) * pgd_tanf(delta);
         sub.sb = tb / sqrtf(1.0f + tb * tb);
         const bool at_rest = q.v == 0.0f && q.yaw == 0.0f && !(sub.accel > 0.0f);
         #pragma unroll 1
@@ -789,8 +783,8 @@ V2_HD void step_env(const Tables& T, const State& S, const PgdConfig& cfg, int m
       int blo = 0, bn = PGD_LIDAR_BEAMS;
       if (d > hd * 1.001f) {
         const float per_rad = (float)PGD_LIDAR_BEAMS / V2_TWO_PI;
-        const float c = (atan2f(dy, dx) - ego.h) * per_rad;
-        const float w = asinf(fminf(hd / d, 1.0f)) * per_rad;
+        const float c = (pgd_atan2f(dy, dx) - ego.h) * per_rad;
+        const float w = pgd_asinf(fminf(hd / d, 1.0f)) * per_rad;
         const int n = (int)ceilf(2.0f * w) + 3;
         if (n < PGD_LIDAR_BEAMS) {
           bn = n;
@@ -966,7 +960,7 @@ V2_HD void step_env(const Tables& T, const State& S, const PgdConfig& cfg, int m
       else if (crash) cost = cfg.crash_vehicle_cost;
       is_done = ((flags & PGD_F_ARRIVE_DEST) || out_of_road || crash) ? 1 : 0;
       const float ddx = last_x - ego.x, ddy = last_y - ego.y;
-      step_energy = 3.25f * expf(0.01f * sp) * (sqrtf(ddx * ddx + ddy * ddy) / 1000.0f) / 100.0f * 1000.0f;
+      step_energy = 3.25f * pgd_expf(0.01f * sp) * (sqrtf(ddx * ddx + ddy * ddy) / 1000.0f) / 100.0f * 1000.0f;
       envf.w += step_energy;
       envf.z += r;
       envi.w += 1;
