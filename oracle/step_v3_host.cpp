@@ -1,0 +1,117 @@
+/* TEST INFRASTRUCTURE ONLY.  Host (g++) build of the role-per-warp step (pgdrive_b200/csrc/pgd_step_v3.cuh is
+ * written for host + device): every CTA of 32 environments is emulated by running the phases in order over all
+ * (role, lane) pairs -- the loops stand for the CTA barriers -- so that the step's logic, including its
+ * shared-memory exchanges, is checked against the independent CPU oracle (oracle/pgd_oracle.c) without a GPU.
+ * The product never loads this library. */
+#include <stdlib.h>
+#include <string.h>
+
+#include "../pgdrive_b200/csrc/pgd_step_v3.cuh"
+
+using namespace pgdv3;
+
+#define HOST_OBS_CAP (2 * PGD_MAX_DETECTOR_BEAMS + 6 + 2 + 10 + 16 + PGD_LIDAR_BEAMS)
+
+struct HostV3 {
+  Tables T;
+  State S;
+  PgdConfig cfg;
+  int roles;
+};
+
+template <int V>
+static void run_v(HostV3* h, int mode, const float* actions, float* obs, float* reward, uint8_t* done, PgdInfo* info) {
+  typedef Smem<V, HOST_OBS_CAP> SM;
+  static SM* sm = nullptr;
+  if (!sm) sm = (SM*)aligned_alloc(128, (sizeof(SM) + 127) / 128 * 128);
+  static Thr th[V3_MAX_ROLES][V3_LANES];
+  const int n = h->cfg.num_envs, od = obs_dim_of(h->cfg), R = h->roles;
+  for (int env0 = 0; env0 < n; env0 += V3_LANES) {
+    memset(sm, 0xff, sizeof(SM));  // shared memory starts as garbage on the device
+    bool any = false;
+    for (int r = 0; r < R; ++r)
+      for (int l = 0; l < V3_LANES; ++l) {
+        thread_init(th[r][l], h->T, h->S, h->cfg, mode, l, r, env0 + l, n);
+        any = any || th[r][l].valid;
+      }
+    if (!any) continue;
+#define ALL(call) for (int r = 0; r < R; ++r) for (int l = 0; l < V3_LANES; ++l) { Thr& t = th[r][l]; (void)t; call; }
+    ALL(phase_a(*sm, t, h->S, h->cfg, R, actions));
+    ALL(phase_b(*sm, t, R));
+    ALL(phase_c(*sm, t, h->T, h->S, h->cfg, R));
+    for (int i = 0; i < V3_LANES * od; ++i) sm->u.obs[i] = 1.0f;
+    ALL(phase_d(*sm, t, h->T, h->S, h->cfg, R));
+    ALL(phase_f(*sm, t, h->T, h->S, h->cfg, mode, R, od, reward, done, info));
+    ALL(phase_l(*sm, r, l, R, od));
+#undef ALL
+    for (int l = 0; l < V3_LANES; ++l)
+      if (sm->wrote[l]) memcpy(obs + (size_t)(env0 + l) * od, sm->u.obs + (size_t)l * od, (size_t)od * 4);
+  }
+}
+
+static void run(HostV3* h, int mode, const float* actions, float* obs, float* reward, uint8_t* done, PgdInfo* info) {
+  if (h->cfg.num_slots == 16) run_v<16>(h, mode, actions, obs, reward, done, info);
+  else if (h->cfg.num_slots == 24) run_v<24>(h, mode, actions, obs, reward, done, info);
+  else run_v<32>(h, mode, actions, obs, reward, done, info);
+}
+
+extern "C" {
+
+void* v3h_create(const PgdTables* t, const PgdConfig* cfg, int roles) {
+  HostV3* h = (HostV3*)calloc(1, sizeof(HostV3));
+  h->cfg = *cfg;
+  h->roles = roles;
+  h->T.maps = t->maps; h->T.lanes = t->lanes; h->T.roads = t->roads; h->T.boxes = t->boxes;
+  h->T.cell_start = t->cell_start; h->T.cell_entries = t->cell_entries; h->T.episodes = t->episodes;
+  h->T.slots = t->slots; h->T.route_nodes = t->route_nodes; h->T.route_roads = t->route_roads;
+  const size_t nv = (size_t)cfg->num_envs * cfg->num_slots, n = (size_t)cfg->num_envs;
+  h->S.pose = (F4*)calloc(nv, 16); h->S.ctrl = (F4*)calloc(nv, 16); h->S.pidl = (F4*)calloc(nv, 16);
+  h->S.nav = (I4*)calloc(nv, 16); h->S.misc = (I4*)calloc(nv, 16);
+  h->S.envi = (I4*)calloc(n, 16); h->S.envf = (F4*)calloc(n, 16);
+  return h;
+}
+
+void v3h_destroy(void* p) {
+  HostV3* h = (HostV3*)p;
+  free(h->S.pose); free(h->S.ctrl); free(h->S.pidl); free(h->S.nav); free(h->S.misc); free(h->S.envi); free(h->S.envf);
+  free(h);
+}
+
+/* pgd_reset: environments env_ids[i] restart on episode_ids[i]; their observation rows are rewritten */
+void v3h_reset(void* p, const int32_t* env_ids, const int32_t* episode_ids, int n, float* obs, PgdInfo* info) {
+  HostV3* h = (HostV3*)p;
+  for (int i = 0; i < n; ++i) {
+    int e = env_ids ? env_ids[i] : i;
+    h->S.envi[e].x = episode_ids[i];
+    h->S.envi[e].z = V3_DONE_PENDING_RESET;
+  }
+  run(h, 1, nullptr, obs, nullptr, nullptr, info);
+}
+
+/* pgd_get_state for the slot-major layout (exchange format of include/pgd_tables.h) */
+void v3h_get_state(void* p, int env, PgdEnvState* out) {
+  HostV3* h = (HostV3*)p;
+  const int n = h->cfg.num_envs, V = h->cfg.num_slots;
+  memset(out, 0, sizeof(*out));
+  const I4 ei = h->S.envi[env];
+  const F4 ef = h->S.envf[env];
+  out->episode = ei.x; out->next_group = ei.y; out->done = ei.z; out->ep_len = ei.w;
+  out->prev_steer = ef.x; out->prev_throttle = ef.y; out->ep_reward = ef.z; out->energy = ef.w;
+  const int n_slots = h->T.episodes[ei.x].n_slots;
+  for (int i = 0; i < n_slots && i < V; ++i) {
+    const size_t gi = (size_t)i * n + env;
+    const F4 po = h->S.pose[gi], c = h->S.ctrl[gi], l = h->S.pidl[gi];
+    const I4 nv = h->S.nav[gi], m = h->S.misc[gi];
+    PgdVehState* s = &out->veh[i];
+    s->x = po.x; s->y = po.y; s->heading = po.z; s->speed = po.w;
+    s->steer = c.x; s->throttle = c.y; s->pid_hp = c.z; s->pid_hi = c.w;
+    s->pid_lp = l.x; s->pid_li = l.y; s->target_speed = l.z; s->yaw_rate = l.w;
+    s->lane = nv.x; s->ck0 = nv.y & 0xffff; s->ck1 = nv.y >> 16; s->rt_lane = nv.z; s->timer = nv.w;
+    s->rnd_n = m.x; s->airborne = m.y; s->flags = m.z;
+  }
+}
+
+void v3h_step(void* p, const float* actions, float* obs, float* reward, uint8_t* done, PgdInfo* info) {
+  run((HostV3*)p, 0, actions, obs, reward, done, info);
+}
+}

@@ -13,6 +13,7 @@ UNITS = {
     "pgd_step.cu": [],
     "pgd_mapgen.cu": ["pgd_mapgen.cuh", "pgd_rng.cuh", "pgd_dd.cuh"],
     "pgd_step_v2.cu": ["pgd_step_v2.cuh"],
+    "pgd_step_v3.cu": ["pgd_step_v3.cuh"],
 }
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",

@@ -189,7 +189,8 @@ ENGINE_CONFIG = dict(
     num_slots=None,      # vehicle slots per env (16 / 32); None = smallest that fits the loaded seeds
     device=0,            # CUDA device ordinal
     auto_reset=True,     # VecPGDriveEnv only: a finished env restarts at its next step (action ignored)
-    one_thread_per_env=False,  # experimental second layout of the step (pgd_step_v2.cu); not validated on a GPU yet
+    one_thread_per_env=False,  # second layout of the step (pgd_step_v2.cu)
+    layout=None,         # step kernel: 0 cooperative, 1 one thread per env, 2 role per warp; None = the default
     device_mapgen=False,  # VecPGDriveEnv only: run the reset path (map search, tables, episode templates) on the GPU
 )
 

@@ -77,4 +77,7 @@ struct PgdHandle {
 // pgd_step_v2.cu: one thread per environment (PgdConfig.layout == 1)
 int pgd_launch_step_v2(PgdHandle* h, int mode, int env_begin, int env_end, const float* actions, float* obs,
                        float* reward, uint8_t* done, PgdInfo* info, cudaStream_t st);
+// pgd_step_v3.cu: role per warp, environment per lane (PgdConfig.layout == 2)
+int pgd_launch_step_v3(PgdHandle* h, int mode, int env_begin, int env_end, const float* actions, float* obs,
+                       float* reward, uint8_t* done, PgdInfo* info, cudaStream_t st);
 #endif

@@ -1028,10 +1028,11 @@ extern "C" const char* pgd_last_error(void) { return g_pgd_err.c_str(); }
 extern "C" int pgd_create(const PgdConfig* cfg, int device, PgdHandle** out) {
   if (!cfg || !out) return fail(-1, "pgd_create: null argument");
   if (cfg->num_envs <= 0) return fail(-1, "pgd_create: num_envs must be positive");
-  if (cfg->num_slots != 16 && cfg->num_slots != 32) return fail(-1, "pgd_create: num_slots must be 16 or 32");
-  if (cfg->layout != 0 && cfg->layout != 1) return fail(-1, "pgd_create: layout must be 0 or 1");
-  if (cfg->random_agent_model && cfg->layout != 1)
-    return fail(-3, "pgd_create: random_agent_model needs the one-thread-per-environment layout (layout = 1)");
+  if (cfg->layout < 0 || cfg->layout > 2) return fail(-1, "pgd_create: layout must be 0, 1 or 2");
+  if (cfg->num_slots != 16 && cfg->num_slots != 32 && !(cfg->num_slots == 24 && cfg->layout == 2))
+    return fail(-1, "pgd_create: num_slots must be 16, 24 (layout 2) or 32");
+  if (cfg->random_agent_model && cfg->layout == 0)
+    return fail(-3, "pgd_create: random_agent_model is not in the cooperative layout (layout = 0)");
   if (cfg->n_side < 0 || cfg->n_side > PGD_MAX_DETECTOR_BEAMS || cfg->n_lane_line < 0 ||
       cfg->n_lane_line > PGD_MAX_DETECTOR_BEAMS)
     return fail(-1, "pgd_create: detector beam counts must be in [0, 240]");
@@ -1123,6 +1124,7 @@ extern "C" int pgd_load_tables(PgdHandle* h, const PgdTables* t) {
 static int launch_step(PgdHandle* h, int mode, int env_begin, int env_end, const float* actions, float* obs,
                        float* reward, uint8_t* done, PgdInfo* info, cudaStream_t st) {
   if (h->cfg.layout == 1) return pgd_launch_step_v2(h, mode, env_begin, env_end, actions, obs, reward, done, info, st);
+  if (h->cfg.layout == 2) return pgd_launch_step_v3(h, mode, env_begin, env_end, actions, obs, reward, done, info, st);
   const int V = h->cfg.num_slots;
   const int envs_per_cta = CTA_THREADS / V;
   const int grid = (env_end - env_begin + envs_per_cta - 1) / envs_per_cta;
@@ -1233,7 +1235,7 @@ extern "C" int pgd_step_host(PgdHandle* h, const float* actions, float* obs, flo
     CU(cudaEventRecord(h->ev_act, st));
     CU(cudaStreamWaitEvent(h->own_stream2, h->ev_act, 0));
   }
-  const int per = (int)((n / chunks + 7) / 8 * 8);
+  const int per = (int)((n / chunks + 31) / 32 * 32);
   for (int c = 0; c < chunks; ++c) {
     const int b = c * per, e = (c == chunks - 1) ? (int)n : (c + 1) * per;
     cudaStream_t cs = (c & 1) ? h->own_stream2 : st;

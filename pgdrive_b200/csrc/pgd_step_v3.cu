@@ -1,0 +1,115 @@
+// Role per warp / environment per lane: kernel wrapper around pgd_step_v3.cuh (PgdConfig.layout = 2).
+//
+// A CTA = R warps x 32 lanes advances 32 environments (see the header of pgd_step_v3.cuh for the phases).  The 32
+// observation rows are assembled in shared memory in their HBM layout and leave with ONE bulk (TMA) copy per CTA
+// (cp.async.bulk.global.shared::cta, 35 KB at 274 floats per row); the destination may be a peer-mapped buffer on
+// another GPU.  CTAs that are not full (partial reset, tail) fall back to coalesced per-row stores.
+#include "pgd_internal.h"
+#include "pgd_step_v3.cuh"
+
+using namespace pgdv3;
+
+#ifndef V3_ROLES
+#define V3_ROLES 4
+#endif
+#define V3_OBS_DET (2 * PGD_MAX_DETECTOR_BEAMS + 6 + 2 + 10 + 16 + PGD_LIDAR_BEAMS) /* 754: both detector fans */
+#define V3_OBS_PLAIN (PGD_OBS_DIM + 2)                                               /* 276: + vehicle size */
+
+template <int V, int OBS_CAP>
+__global__ void __launch_bounds__(V3_ROLES * 32) pgd_step_v3_kernel(Tables T, State S, PgdConfig cfg, int mode,
+                                                                    int env_begin, int env_end,
+                                                                    const float* __restrict__ actions,
+                                                                    float* __restrict__ obs,
+                                                                    float* __restrict__ reward,
+                                                                    uint8_t* __restrict__ done,
+                                                                    PgdInfo* __restrict__ info) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Smem<V, OBS_CAP>& sm = *reinterpret_cast<Smem<V, OBS_CAP>*>(smem_raw);
+  const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
+  const int env0 = env_begin + blockIdx.x * V3_LANES;
+  const int obs_dim = obs_dim_of(cfg);
+  Thr th;
+  thread_init(th, T, S, cfg, mode, lane, role, env0 + lane, env_end);
+  if (!__syncthreads_or(th.valid)) return;  // reset pass: no environment of this CTA is marked
+  phase_a(sm, th, S, cfg, V3_ROLES, actions);
+  __syncthreads();
+  phase_b(sm, th, V3_ROLES);
+  __syncthreads();
+  phase_c(sm, th, T, S, cfg, V3_ROLES);
+  __syncthreads();
+  {  // pre-fill the rows with 1.0 = "no hit" (the IDM look-up data that shared this storage is dead now)
+    float4* o4 = reinterpret_cast<float4*>(sm.u.obs);
+    const int n4 = V3_LANES * obs_dim / 4;  // 32 rows: a multiple of 4 floats for every row length
+    for (int i = threadIdx.x; i < n4; i += V3_ROLES * 32) o4[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+  }
+  phase_d(sm, th, T, S, cfg, V3_ROLES);
+  __syncthreads();
+  phase_f(sm, th, T, S, cfg, mode, V3_ROLES, obs_dim, reward, done, info);
+  __syncthreads();
+  phase_l(sm, role, lane, V3_ROLES, obs_dim);
+  // ---- write-out -----------------------------------------------------------------------------------------------------
+  const int all = __syncthreads_and(sm.wrote[lane]);
+  float* dst = obs + (size_t)env0 * obs_dim;
+  if (all && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+    if (threadIdx.x == 0) {
+      const uint32_t bytes = (uint32_t)(V3_LANES * obs_dim * sizeof(float));
+      const uint32_t src = (uint32_t)__cvta_generic_to_shared(sm.u.obs);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes)
+                   : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+  } else {
+    for (int e = role; e < V3_LANES; e += V3_ROLES) {
+      if (!sm.wrote[e]) continue;
+      const float* src = sm.u.obs + (size_t)e * obs_dim;
+      float* d = dst + (size_t)e * obs_dim;
+      for (int c = lane; c < obs_dim; c += 32) d[c] = src[c];
+    }
+  }
+}
+
+template <int V, int OBS_CAP>
+static int launch_one(PgdHandle* h, const Tables& T, const State& S, int mode, int env_begin, int env_end,
+                      const float* actions, float* obs, float* reward, uint8_t* done, PgdInfo* info, cudaStream_t st) {
+  static bool configured = false;  // per instantiation
+  const size_t smem = sizeof(Smem<V, OBS_CAP>);
+  if (!configured) {
+    CU(cudaFuncSetAttribute(pgd_step_v3_kernel<V, OBS_CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  const int grid = (env_end - env_begin + V3_LANES - 1) / V3_LANES;
+  pgd_step_v3_kernel<V, OBS_CAP><<<grid, V3_ROLES * 32, smem, st>>>(T, S, h->cfg, mode, env_begin, env_end, actions,
+                                                                   obs, reward, done, info);
+  return 0;
+}
+
+int pgd_launch_step_v3(PgdHandle* h, int mode, int env_begin, int env_end, const float* actions, float* obs,
+                       float* reward, uint8_t* done, PgdInfo* info, cudaStream_t st) {
+  if (h->cfg.decision_repeat > V3_MAX_SUBSTEPS) return fail(-3, "decision_repeat > 8 is not supported");
+  Tables T;
+  T.maps = h->T.maps; T.lanes = h->T.lanes; T.roads = h->T.roads; T.boxes = h->T.boxes;
+  T.cell_start = h->T.cell_start; T.cell_entries = h->T.cell_entries; T.episodes = h->T.episodes;
+  T.slots = h->T.slots; T.route_nodes = h->T.route_nodes; T.route_roads = h->T.route_roads;
+  State S;
+  S.pose = (F4*)h->S.pose; S.ctrl = (F4*)h->S.ctrl; S.pidl = (F4*)h->S.pidl; S.nav = (I4*)h->S.nav;
+  S.misc = (I4*)h->S.misc; S.envi = (I4*)h->S.envi; S.envf = (F4*)h->S.envf;
+  if (h->timing && mode == 0) cudaEventRecord(h->ev0, st);
+  const bool det = h->cfg.n_side > 0 || h->cfg.n_lane_line > 0;  // detectors need the long rows
+  const int V = h->cfg.num_slots;
+  int rc;
+#define V3_LAUNCH(VV, CAP) rc = launch_one<VV, CAP>(h, T, S, mode, env_begin, env_end, actions, obs, reward, done, info, st)
+  if (V == 16 && !det) V3_LAUNCH(16, V3_OBS_PLAIN);
+  else if (V == 24 && !det) V3_LAUNCH(24, V3_OBS_PLAIN);
+  else if (V == 32 && !det) V3_LAUNCH(32, V3_OBS_PLAIN);
+  else if (V == 16) V3_LAUNCH(16, V3_OBS_DET);
+  else if (V == 24) V3_LAUNCH(24, V3_OBS_DET);
+  else V3_LAUNCH(32, V3_OBS_DET);
+#undef V3_LAUNCH
+  if (rc) return rc;
+  if (h->timing && mode == 0) cudaEventRecord(h->ev1, st);
+  h->launches++;
+  CU(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,1197 @@
+/* Environment step, ROLE PER WARP / ENVIRONMENT PER LANE.
+ *
+ * A CTA advances 32 environments with R warps.  Lane l of every warp works on environment l of the CTA; the warp
+ * index is the ROLE: warp 0 carries the 32 egos, warps 1..R-1 carry the traffic slots (slot s belongs to role
+ * 1 + (s - 1) % (R - 1)).  An instruction of warp 0 therefore advances 32 egos (the round-1 kernel advanced 2 per
+ * instruction, its one-thread-per-environment variant 32 but with 2 048 warps on the whole GPU), and a traffic warp
+ * only spends instructions on vehicles that are awake.  What the vehicles of an environment need from each other --
+ * poses for IDM's neighbour search, the ego's trajectory through the sub-steps for the chassis contacts, final poses
+ * for lidar and the neighbour features -- goes through shared memory, structure-of-arrays with the environment as
+ * the fastest index (conflict-free), between CTA barriers:
+ *
+ *   A  publish start-of-step public state of every slot; ego action; traffic trigger        (all roles)
+ *   B  lanes with awake traffic: every vehicle's coordinate on its own lane (IDM look-up data)
+ *   C  role 0: ego sub-steps -> trajectory;  traffic roles: IDM / PID of their awake vehicles
+ *   D  role 0: ego localisation + line / sidewalk contacts;  traffic: sub-steps, chassis contact against the ego
+ *      trajectory, localisation, removal; final poses published; observation rows pre-filled with 1.0
+ *   F  role-parallel ego bookkeeping: reward / done / state (0), navigation info (1), 4 nearest vehicles (2),
+ *      lidar windows (3); detector ray fans over all roles
+ *   L  lidar as a scatter: every (visible chassis, beam of its window) pair is one work item; lanes = beams
+ *   W  the 32 rows leave the CTA with ONE bulk (TMA) shared -> global copy (pgd_step_v3.cu)
+ *
+ * State in HBM is slot-major ([slot][env]) so that a warp's loads / stores of a slot are 32 consecutive 16-byte
+ * vectors.  Parked traffic is never loaded beyond its flag word (its pose is the episode template's).
+ *
+ * The arithmetic is the oracle's, expression for expression.  The file compiles for the host too
+ * (oracle/step_v3_host.cpp runs the phases in order over all (role, lane) pairs), so the whole step is checked bit
+ * for bit against the independent CPU oracle without a GPU (tests/test_step_host.py).
+ *
+ * Reference call stack (paths under /root/reference/pgdrive): envs/base_env.py:184-224,303-344 (step),
+ * policy/idm_policy.py:83-353 (IDM), engine/base_engine.py:206-232 (sub-steps), vehicle_module/navigation.py:155-344,
+ * utils/scene_utils.py:138-185 (localisation), component/vehicle/base_vehicle.py:615-644 (line / sidewalk contacts),
+ * cutils.pyx:60-142 + vehicle_module/lidar.py:55-77 (lidar, neighbours), obs/state_obs.py:58-170 (observation),
+ * envs/pgdrive_env.py:162-258 (reward / cost / done).
+ */
+#ifndef PGD_STEP_V3_CUH
+#define PGD_STEP_V3_CUH
+#include <limits.h>
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "../../include/pgd_math.h"
+#include "../../include/pgd_tables.h"
+
+#ifdef __CUDACC__
+#define V3_HD __host__ __device__ __forceinline__
+#define V3_HD_OUTLINE __host__ __device__ __noinline__
+#else
+#define V3_HD inline
+#define V3_HD_OUTLINE inline
+#endif
+
+namespace pgdv3 {
+
+#define V3_PI 3.14159265358979323846f
+#define V3_TWO_PI 6.28318530717958647692f
+#define V3_GRAVITY 9.81f
+#define V3_LIDAR_RANGE 50.0f
+#define V3_MAX_SPEED_KMH 80.0f
+#define V3_IDM_MAX_LONG 30.0f
+#define V3_IDM_NORMAL_SPEED 30.0f
+#define V3_IDM_CREEP_SPEED 5.0f
+#define V3_IDM_SAFE_DIST 15.0f
+#define V3_IDM_LANE_CHANGE_FREQ 50
+#define V3_IDM_SPEED_INCREASE 10.0f
+#define V3_IDM_MAX_SPEED 100.0f
+#define V3_YAW_TAU 0.1f
+#define V3_DONE_PENDING_RESET 2
+#define V3_MAX_SUBSTEPS 8 /* decision_repeat supported (default 5) */
+#define V3_LANES 32       /* environments per CTA = lanes of a warp */
+#define V3_MAX_ROLES 8
+
+struct alignas(16) F4 { float x, y, z, w; };
+struct alignas(16) I4 { int x, y, z, w; };
+
+struct Tables {  // device (or host) pointers to the tables of include/pgd_tables.h
+  const PgdMap* maps;
+  const PgdLane* lanes;
+  const PgdRoad* roads;
+  const PgdBox* boxes;
+  const int32_t* cell_start;
+  const int32_t* cell_entries;
+  const PgdEpisode* episodes;
+  const PgdSlot* slots;
+  const int32_t* route_nodes;
+  const int32_t* route_roads;
+};
+
+struct State {  // slot-major: per-slot arrays are indexed slot * num_envs + env, per-env arrays by env
+  F4* pose;   // x, y, heading, speed
+  F4* ctrl;   // steer, throttle, heading-PID last error, heading-PID summed error
+  F4* pidl;   // lateral-PID last error, summed error, IDM target speed, yaw rate
+  I4* nav;    // lane, ck0 | ck1 << 16, routing target lane, overtake timer
+  I4* misc;   // rnd draws used, airborne sub-steps left, PGD_V_* flags, -
+  I4* envi;   // episode, next trigger group, done, episode length
+  F4* envf;   // previous steering, previous throttle, episode reward, episode energy
+};
+
+template <class T_>
+V3_HD T_ ldg(const T_* p) {
+#ifdef __CUDA_ARCH__
+  return __ldg(p);
+#else
+  return *p;
+#endif
+}
+
+/* A whole table record (PgdLane 64 B, PgdBox / PgdRoad 32 B, PgdMap 64 B) with 16-byte read-only loads. */
+template <class T_>
+V3_HD T_ load_rec(const T_* p) {
+#ifdef __CUDA_ARCH__
+  static_assert(sizeof(T_) % 16 == 0, "table records are multiples of 16 bytes");
+  T_ out;
+  const uint4* src = reinterpret_cast<const uint4*>(p);
+  uint4* dst = reinterpret_cast<uint4*>(&out);
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(T_) / 16); ++i) dst[i] = __ldg(src + i);
+  return out;
+#else
+  return *p;
+#endif
+}
+
+V3_HD float clipf(float a, float lo, float hi) { return fminf(fmaxf(a, lo), hi); }
+
+V3_HD_OUTLINE void sincos_hd(float a, float* s, float* c) { pgd_sincosf(a, s, c); }
+#define V3_SINCOS(a, s, c) pgdv3::sincos_hd((a), &(s), &(c))
+
+V3_HD_OUTLINE void arc_local(float cx, float cy, float ph0, float dir, float radius, float x, float y, float* lon,
+                             float* lat) {
+  float dx = x - cx, dy = y - cy;
+  float phi = pgd_atan2f(dy, dx);
+  phi = ph0 + pgd_wrap_to_pi(phi - ph0);
+  float r = sqrtf(dx * dx + dy * dy);
+  *lon = dir * (phi - ph0) * radius;
+  *lat = dir * (radius - r);
+}
+
+V3_HD void lane_local(const PgdLane& l, float x, float y, float& lon, float& lat) {
+  if (l.kind == PGD_LANE_STRAIGHT) {
+    float dx = x - l.sx, dy = y - l.sy;
+    lon = dx * l.ax + dy * l.ay;
+    lat = dx * -l.ay + dy * l.ax;
+  } else {
+    arc_local(l.ax, l.ay, l.ph0, l.dir, l.radius, x, y, &lon, &lat);
+  }
+}
+
+V3_HD void lane_position(const PgdLane& l, float lon, float lat, float& x, float& y) {
+  if (l.kind == PGD_LANE_STRAIGHT) {
+    x = l.sx + lon * l.ax + lat * -l.ay;
+    y = l.sy + lon * l.ay + lat * l.ax;
+  } else {
+    float phi = l.dir * lon / l.radius + l.ph0;
+    float r = l.radius - lat * l.dir;
+    float s, c;
+    V3_SINCOS(phi, s, c);
+    x = l.ax + r * c;
+    y = l.ay + r * s;
+  }
+}
+
+V3_HD float lane_heading_at(const PgdLane& l, float lon) {
+  if (l.kind == PGD_LANE_STRAIGHT) return l.heading;
+  float phi = l.dir * lon / l.radius + l.ph0;
+  return phi + V3_PI / 2 * l.dir;
+}
+
+V3_HD bool precedes(float ex, float ey, float sx, float sy) {  // abs_lane.py:114-119 (norm < 0.1)
+  float dx = ex - sx, dy = ey - sy;
+  return dx * dx + dy * dy < 1e-2f;
+}
+
+struct Rect { float cx, cy, ux, uy, hl, hw; };
+
+V3_HD_OUTLINE bool rect_overlap(const Rect& a, const Rect& b) {
+  float dx = b.cx - a.cx, dy = b.cy - a.cy;
+  float c = fabsf(a.ux * b.ux + a.uy * b.uy);
+  float s = fabsf(a.ux * b.uy - a.uy * b.ux);
+  if (fabsf(dx * a.ux + dy * a.uy) > a.hl + b.hl * c + b.hw * s) return false;
+  if (fabsf(-dx * a.uy + dy * a.ux) > a.hw + b.hl * s + b.hw * c) return false;
+  if (fabsf(dx * b.ux + dy * b.uy) > b.hl + a.hl * c + a.hw * s) return false;
+  if (fabsf(-dx * b.uy + dy * b.ux) > b.hw + a.hl * s + a.hw * c) return false;
+  return true;
+}
+
+V3_HD float ray_rect(float ox, float oy, float dx, float dy, const Rect& r) {
+  float px = ox - r.cx, py = oy - r.cy;
+  float lo0 = px * r.ux + py * r.uy, lo1 = -px * r.uy + py * r.ux;
+  float ld0 = dx * r.ux + dy * r.uy, ld1 = -dx * r.uy + dy * r.ux;
+  if (fabsf(lo0) <= r.hl && fabsf(lo1) <= r.hw) return 1.0f;  // origin inside: Bullet's convex cast reports no hit
+  float t0 = 0.0f, t1 = 1.0f;
+  if (fabsf(ld0) < 1e-12f) {
+    if (fabsf(lo0) > r.hl) return 1.0f;
+  } else {
+    float inv = 1.0f / ld0;
+    float ta = (-r.hl - lo0) * inv, tb = (r.hl - lo0) * inv;
+    t0 = fmaxf(t0, fminf(ta, tb));
+    t1 = fminf(t1, fmaxf(ta, tb));
+    if (t0 > t1) return 1.0f;
+  }
+  if (fabsf(ld1) < 1e-12f) {
+    if (fabsf(lo1) > r.hw) return 1.0f;
+  } else {
+    float inv = 1.0f / ld1;
+    float ta = (-r.hw - lo1) * inv, tb = (r.hw - lo1) * inv;
+    t0 = fmaxf(t0, fminf(ta, tb));
+    t1 = fminf(t1, fmaxf(ta, tb));
+    if (t0 > t1) return 1.0f;
+  }
+  return t0;
+}
+
+V3_HD void project(float hx, float hy, float vx, float vy, float& fwd, float& side) {  // base_vehicle.py:460-475
+  const float n = 1.0f + 1e-6f;
+  fwd = (vx * hx + vy * hy) / n;
+  side = (vx * -hy + vy * hx) / n;
+}
+
+V3_HD float pid(float& p_err, float& i_err, float kp, float ki, float kd, float err) {  // PID_controller.py
+  i_err += err;
+  float d = err - p_err;
+  p_err = err;
+  return -kp * p_err - ki * i_err - kd * d;
+}
+
+V3_HD float kmh(float v) { return clipf(v * 3.6f, 0.0f, 100000.0f); }  // base_vehicle.py:395-401
+
+struct Veh {  // one vehicle, in registers while its owner works on it
+  float x, y, h, v, yaw, steer, throttle, hp, hi, lp, li, tspeed;
+  float hc, hs, hl, hw;
+  int lane, ck0, ck1, rt_lane, timer, rnd_n, airborne, vflags;
+};
+
+struct Sub {  // what one physics sub-step needs, hoisted out of the sub-step loop
+  float accel, brake_dv, sb, mu_g, lr;
+};
+
+V3_HD_OUTLINE void substep(Veh& q, const Sub& sub, float dt) {  // planar stand-in for BulletVehicle
+  float speed = q.v;
+  if (sub.accel > 0.0f) speed += sub.accel * dt;
+  else speed = fmaxf(speed - sub.brake_dv, 0.0f);
+  float yaw = q.yaw + (speed * sub.sb / sub.lr - q.yaw) * (dt / V3_YAW_TAU);
+  if (speed * fabsf(yaw) > sub.mu_g) yaw = copysignf(sub.mu_g / speed, yaw);
+  const float sb = speed > 1e-3f ? clipf(yaw * sub.lr / speed, -1.0f, 1.0f) : 0.0f;
+  const float cb = sqrtf(fmaxf(1.0f - sb * sb, 0.0f));
+  q.x += speed * (q.hc * cb - q.hs * sb) * dt;
+  q.y += speed * (q.hs * cb + q.hc * sb) * dt;
+  float nh = q.h + yaw * dt;
+  if (nh > V3_PI) nh -= V3_TWO_PI;
+  if (nh < -V3_PI) nh += V3_TWO_PI;
+  q.yaw = yaw;
+  if (nh != q.h) V3_SINCOS(nh, q.hs, q.hc);
+  q.h = nh;
+  q.v = speed;
+}
+
+V3_HD Sub make_sub(const Veh& q, const PgdSlot& t, float dt) {  // base_vehicle.py:343-376
+  Sub sub;
+  sub.mu_g = t.friction * V3_GRAVITY;
+  sub.lr = t.lr;
+  const bool overspeed = kmh(q.v) > V3_MAX_SPEED_KMH;
+  if (q.throttle > 0.0f && !overspeed) {
+    sub.accel = fminf(4.0f * t.max_engine * q.throttle / t.mass, sub.mu_g);
+    sub.brake_dv = 0.0f;
+  } else {
+    sub.accel = 0.0f;
+    const float imp = q.throttle >= 0.0f ? 2.0f : -q.throttle * t.max_brake;
+    sub.brake_dv = fminf(4.0f * imp / t.mass, sub.mu_g * dt);
+  }
+  const float delta = clipf(-q.steer * t.max_steer, -1.4f, 1.4f);
+  const float tb = t.lr / (t.lf + t.lr) * pgd_tanf(delta);
+  sub.sb = tb / sqrtf(1.0f + tb * tb);
+  return sub;
+}
+
+// ---- shared memory ------------------------------------------------------------------------------------------------
+template <int V>
+struct Pub {  // public per-slot state, [slot][lane]
+  float x[V][V3_LANES], y[V][V3_LANES], hc[V][V3_LANES], hs[V][V3_LANES], v[V][V3_LANES];
+  float hl[V][V3_LANES], hw[V][V3_LANES];
+  int lane[V][V3_LANES], fl[V][V3_LANES];
+};
+
+template <int V>
+struct IdmPub {  // IDM look-up data of every vehicle (phase B -> C); shares its storage with the observation rows
+  float olong[V][V3_LANES], lsx[V][V3_LANES], lsy[V][V3_LANES], lex[V][V3_LANES], ley[V][V3_LANES],
+      llen[V][V3_LANES];
+};
+
+template <int V, int OBS_CAP>
+struct Smem {
+  union alignas(128) {
+    float obs[V3_LANES * OBS_CAP];  // the CTA's rows back to back, stride = the row length (HBM layout)
+    IdmPub<V> idm;
+  } u;
+  Pub<V> p;
+  F4 traj[V3_MAX_SUBSTEPS][V3_LANES];  // ego pose (x, y, cos, sin) after every sub-step
+  float last_x[V3_LANES], last_y[V3_LANES], ego_travel[V3_LANES], ego_h[V3_LANES];
+  int ego_ck[V3_LANES];
+  int awake[V3_MAX_ROLES][V3_LANES], crash[V3_MAX_ROLES][V3_LANES];  // one word per role: no atomics, no clearing
+  int n_vis[V3_LANES];
+  int vis[V][V3_LANES];  // visible chassis: slot | first beam << 8 | beam count << 16
+  int wrote[V3_LANES];
+};
+
+struct Thr {  // what a thread keeps across the phases
+  int lane, role, env, num_envs;
+  bool valid, fresh, stepping;
+  I4 envi;
+  F4 envf;
+  PgdMap mp;
+  const PgdEpisode* ep;
+  const PgdLane* lanes;
+  const PgdRoad* roads;
+  const PgdBox* boxes;
+  const PgdSlot* tpl;
+  int n_slots, n_groups, trig;
+  Veh ego;         // role 0
+  uint32_t flags;  // role 0: PGD_F_* of the ego
+};
+
+V3_HD int owner_first(int role, int n_roles) { return role; }                // first traffic slot of a traffic role
+V3_HD int owner_stride(int n_roles) { return n_roles - 1; }
+
+V3_HD void veh_from_template(Veh& q, const PgdSlot& t, int s) {
+  q.x = t.x; q.y = t.y; q.h = t.heading; q.v = 0.0f; q.yaw = 0.0f;
+  q.steer = q.throttle = q.hp = q.hi = q.lp = q.li = 0.0f;
+  q.tspeed = V3_IDM_NORMAL_SPEED;
+  q.lane = t.lane; q.ck0 = 0; q.ck1 = t.route_len > 2 ? 1 : 0; q.rt_lane = -1;
+  q.timer = t.overtake_timer; q.rnd_n = 0; q.airborne = t.drop_substeps;
+  q.vflags = PGD_V_ALIVE | PGD_V_ON_LANE | (s == 0 ? PGD_V_ACTIVE : 0);
+}
+
+V3_HD void veh_load(Veh& q, const State& S, size_t gi) {
+  const F4 p = S.pose[gi], c = S.ctrl[gi], l = S.pidl[gi];
+  const I4 n = S.nav[gi], m = S.misc[gi];
+  q.x = p.x; q.y = p.y; q.h = p.z; q.v = p.w;
+  q.steer = c.x; q.throttle = c.y; q.hp = c.z; q.hi = c.w;
+  q.lp = l.x; q.li = l.y; q.tspeed = l.z; q.yaw = l.w;
+  q.lane = n.x; q.ck0 = n.y & 0xffff; q.ck1 = n.y >> 16; q.rt_lane = n.z; q.timer = n.w;
+  q.rnd_n = m.x; q.airborne = m.y; q.vflags = m.z;
+}
+
+V3_HD void veh_store(const Veh& q, const State& S, size_t gi) {
+  const F4 p = {q.x, q.y, q.h, q.v}, c = {q.steer, q.throttle, q.hp, q.hi}, l = {q.lp, q.li, q.tspeed, q.yaw};
+  const I4 n = {q.lane, q.ck0 | (q.ck1 << 16), q.rt_lane, q.timer}, m = {q.rnd_n, q.airborne, q.vflags, 0};
+  S.pose[gi] = p; S.ctrl[gi] = c; S.pidl[gi] = l; S.nav[gi] = n; S.misc[gi] = m;
+}
+
+// ---- thread set-up ---------------------------------------------------------------------------------------------------
+V3_HD void thread_init(Thr& th, const Tables& T, const State& S, const PgdConfig& cfg, int mode, int lane, int role,
+                       int env, int env_end) {
+  th.lane = lane; th.role = role; th.env = env; th.num_envs = cfg.num_envs;
+  th.valid = env < env_end;
+  th.fresh = th.stepping = false;
+  th.trig = -1;
+  th.flags = 0;
+  if (!th.valid) return;
+  th.envi = S.envi[env];
+  th.envf = S.envf[env];
+  const bool pending = th.envi.z == V3_DONE_PENDING_RESET;
+  if (mode == 1) {
+    th.fresh = pending;
+    if (!pending) { th.valid = false; return; }  // the reset pass only touches environments marked for it
+  } else {
+    th.fresh = pending || (cfg.auto_reset && th.envi.z == 1);
+  }
+  th.stepping = !th.fresh;
+  th.ep = T.episodes + th.envi.x;
+  th.mp = load_rec(T.maps + ldg(&th.ep->map));
+  th.n_slots = ldg(&th.ep->n_slots);
+  th.n_groups = ldg(&th.ep->n_groups);
+  th.lanes = T.lanes + th.mp.lane_off;
+  th.roads = T.roads + th.mp.road_off;
+  th.boxes = T.boxes + th.mp.box_off;
+  th.tpl = T.slots + ldg(&th.ep->slot_off);
+  if (th.fresh) {
+    th.envi.y = 0; th.envi.z = 0; th.envi.w = 0;
+    th.envf.x = th.envf.y = th.envf.z = th.envf.w = 0.0f;
+  }
+}
+
+// ---- phase A: publish start-of-step state; ego action; traffic trigger ------------------------------------------
+template <int V, int OBS_CAP>
+V3_HD void phase_a(Smem<V, OBS_CAP>& sm, Thr& th, const State& S, const PgdConfig& cfg, int n_roles,
+                   const float* actions) {
+  const int ln = th.lane;
+  if (th.role == 0) sm.wrote[ln] = th.valid ? 1 : 0;
+  sm.awake[th.role][ln] = 0;
+  sm.crash[th.role][ln] = 0;
+  if (!th.valid) return;
+  Pub<V>& P = sm.p;
+  // TrafficManager.before_step (traffic_manager.py:71-89): the next group wakes when the ego is on its trigger road.
+  // Every role evaluates the (cheap) test itself instead of waiting for role 0.
+  if (th.stepping && th.envi.y < th.n_groups) {
+    const int ego_lane = S.nav[th.env].x;  // slot 0
+    if (ldg(&th.lanes[ego_lane].road) == ldg(&th.ep->trigger_road[th.envi.y])) th.trig = th.envi.y;
+  }
+  if (th.role == 0) {
+    Veh& q = th.ego;
+    const PgdSlot& t = th.tpl[0];
+    if (th.fresh) veh_from_template(q, t, 0);
+    else veh_load(q, S, (size_t)th.env);
+    q.hl = t.length * 0.5f;
+    q.hw = t.width * 0.5f;
+    V3_SINCOS(q.h, q.hs, q.hc);
+    sm.last_x[ln] = q.x; sm.last_y[ln] = q.y;
+    P.x[0][ln] = q.x; P.y[0][ln] = q.y; P.hc[0][ln] = q.hc; P.hs[0][ln] = q.hs; P.v[0][ln] = q.v;
+    P.hl[0][ln] = q.hl; P.hw[0][ln] = q.hw; P.lane[0][ln] = q.lane; P.fl[0][ln] = q.vflags;
+    if (th.stepping) {  // EnvInputPolicy.act (env_input_policy.py:17-26): clip; fminf / fmaxf turn NaN into -1
+      th.envf.x = q.steer;  // last_current_action[0] after the push (base_vehicle.py:248)
+      th.envf.y = q.throttle;
+      q.steer = clipf(actions[2 * (size_t)th.env], -1.0f, 1.0f);
+      q.throttle = clipf(actions[2 * (size_t)th.env + 1], -1.0f, 1.0f);
+      if (th.trig >= 0) th.envi.y += 1;
+    }
+    return;
+  }
+  int any_awake = 0;
+#pragma unroll 1
+  for (int s = owner_first(th.role, n_roles); s < V; s += owner_stride(n_roles)) {
+    const size_t gi = (size_t)s * th.num_envs + th.env;
+    if (s >= th.n_slots) {
+      if (th.fresh) {  // unused slots of a freshly started episode: clear the flags once
+        const I4 m = {0, 0, 0, 0};
+        S.misc[gi] = m;
+      }
+      continue;
+    }
+    const PgdSlot& t = th.tpl[s];
+    float x, y, h, v = 0.0f;
+    int lane, fl;
+    if (th.fresh) {
+      Veh q;
+      veh_from_template(q, t, s);
+      veh_store(q, S, gi);
+      x = q.x; y = q.y; h = q.h; lane = q.lane; fl = q.vflags;
+    } else {
+      fl = S.misc[gi].z;
+      if (!(fl & PGD_V_ALIVE)) {
+        P.fl[s][ln] = 0;
+        continue;
+      }
+      if (fl & PGD_V_ACTIVE) {
+        const F4 p = S.pose[gi];
+        x = p.x; y = p.y; h = p.z; v = p.w;
+        lane = S.nav[gi].x;
+      } else {
+        // Traffic that has not been woken yet has never been touched by IDM, physics (it is at rest) or localisation:
+        // its pose is the episode template's (L2-resident, shared by all environments on the seed).
+        x = t.x; y = t.y; h = t.heading; lane = t.lane;
+        if (t.group == th.trig) fl |= PGD_V_ACTIVE;
+      }
+    }
+    float sn, cs;
+    V3_SINCOS(h, sn, cs);
+    P.x[s][ln] = x; P.y[s][ln] = y; P.hc[s][ln] = cs; P.hs[s][ln] = sn; P.v[s][ln] = v;
+    P.hl[s][ln] = t.length * 0.5f; P.hw[s][ln] = t.width * 0.5f; P.lane[s][ln] = lane; P.fl[s][ln] = fl;
+    if ((fl & (PGD_V_ALIVE | PGD_V_ACTIVE)) == (PGD_V_ALIVE | PGD_V_ACTIVE)) any_awake = 1;
+  }
+  sm.awake[th.role][ln] = any_awake;
+}
+
+template <int V, int OBS_CAP>
+V3_HD bool env_awake(const Smem<V, OBS_CAP>& sm, int ln, int n_roles) {
+  int a = 0;
+  for (int r = 1; r < n_roles; ++r) a |= sm.awake[r][ln];
+  return a != 0;
+}
+
+// ---- phase B: IDM look-up data (only environments with awake traffic) --------------------------------------------
+template <int V, int OBS_CAP>
+V3_HD void phase_b(Smem<V, OBS_CAP>& sm, Thr& th, int n_roles) {
+  if (!th.valid || !th.stepping) return;
+  const int ln = th.lane;
+  if (!env_awake(sm, ln, n_roles)) return;
+  const Pub<V>& P = sm.p;
+  IdmPub<V>& I = sm.u.idm;
+  const int s0 = th.role == 0 ? 0 : owner_first(th.role, n_roles);
+  const int ds = th.role == 0 ? V : owner_stride(n_roles);
+#pragma unroll 1
+  for (int s = s0; s < th.n_slots; s += ds) {
+    if (!(P.fl[s][ln] & PGD_V_ALIVE)) continue;
+    const PgdLane l = load_rec(th.lanes + P.lane[s][ln]);
+    I.lsx[s][ln] = l.sx; I.lsy[s][ln] = l.sy; I.lex[s][ln] = l.ex; I.ley[s][ln] = l.ey; I.llen[s][ln] = l.length;
+    float lon, lat;
+    lane_local(l, P.x[s][ln], P.y[s][ln], lon, lat);
+    I.olong[s][ln] = lon;
+  }
+}
+
+// ---- IDM / PID action of one awake traffic vehicle (idm_policy.py:190-353) --------------------------------------
+template <int V, int OBS_CAP>
+V3_HD void idm_act(const Smem<V, OBS_CAP>& sm, const Thr& th, const Tables& T, Veh& q, int s) {
+  const int ln = th.lane;
+  const Pub<V>& P = sm.p;
+  const IdmPub<V>& I = sm.u.idm;
+  const PgdSlot& t = th.tpl[s];
+  const PgdLane* lanes = th.lanes;
+  const PgdRoad* roads = th.roads;
+  const int n_slots = th.n_slots;
+  const int32_t* rroads = T.route_roads + t.route_off;
+  const int cur_road_id = ldg(&rroads[q.ck0]);
+  const PgdRoad cur_road = load_rec(roads + cur_road_id);
+  bool ok;  // move_to_next_road (:222-242)
+  if (q.rt_lane < 0) {
+    q.rt_lane = q.lane;
+    ok = ldg(&lanes[q.rt_lane].road) == cur_road_id;
+  } else if (ldg(&lanes[q.rt_lane].road) != cur_road_id) {
+    ok = false;
+    const float rex = ldg(&lanes[q.rt_lane].ex), rey = ldg(&lanes[q.rt_lane].ey);
+#pragma unroll 1
+    for (int k = 0; k < cur_road.n_lanes; ++k) {
+      const PgdLane* c = lanes + cur_road.first_lane + k;
+      if (precedes(rex, rey, ldg(&c->sx), ldg(&c->sy))) {
+        q.rt_lane = cur_road.first_lane + k;
+        ok = true;
+        break;
+      }
+    }
+  } else if (ldg(&lanes[q.lane].road) == cur_road_id && q.rt_lane != q.lane) {
+    q.rt_lane = q.lane;
+    q.timer = t.rnd25[q.rnd_n % PGD_N_RND25];
+    q.rnd_n++;
+    ok = true;
+  } else {
+    ok = true;
+  }
+  const PgdLane rl = load_rec(lanes + q.rt_lane);
+  int cand[3] = {-1, q.rt_lane, -1};
+  if (ok) {
+    const PgdRoad rr = load_rec(roads + rl.road);
+    if (rl.idx > 0) cand[0] = rr.first_lane + rl.idx - 1;
+    if (rl.idx + 1 < rr.n_lanes) cand[2] = rr.first_lane + rl.idx + 1;
+  }
+  int front[3], back[3];
+  float fdist[3], bdist[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {  // FrontBackObjects.get_find_front_back_objs (:83-133)
+    front[i] = back[i] = -1;
+    fdist[i] = bdist[i] = V3_IDM_MAX_LONG;
+    if (cand[i] < 0) continue;
+    const PgdLane l = (i == 1) ? rl : load_rec(lanes + cand[i]);
+    float cur_long, lat;
+    lane_local(l, q.x, q.y, cur_long, lat);
+    const float left_long = l.length - cur_long;
+    bool found_front = false, found_back = false;
+#pragma unroll 1
+    for (int j = 0; j < n_slots; ++j) {
+      if (j == s || !(P.fl[j][ln] & PGD_V_ALIVE)) continue;
+      const float ddx = P.x[j][ln] - q.x, ddy = P.y[j][ln] - q.y;
+      if (!(ddx * ddx + ddy * ddy < V3_LIDAR_RANGE * V3_LIDAR_RANGE)) continue;
+      if (P.lane[j][ln] == cand[i]) {
+        const float lg = I.olong[j][ln] - cur_long;
+        if (fdist[i] > lg && lg > 0.0f) { fdist[i] = lg; front[i] = j; found_front = true; }
+        if (lg < 0.0f && fabsf(lg) < bdist[i]) { bdist[i] = fabsf(lg); back[i] = j; found_back = true; }
+      } else if (!found_front && precedes(l.ex, l.ey, I.lsx[j][ln], I.lsy[j][ln])) {
+        const float lg = I.olong[j][ln] + left_long;
+        if (fdist[i] > lg && lg > 0.0f) { fdist[i] = lg; front[i] = j; }
+      } else if (!found_back && precedes(I.lex[j][ln], I.ley[j][ln], l.sx, l.sy)) {
+        const float lg = I.llen[j][ln] - I.olong[j][ln] + cur_long;
+        if (bdist[i] > lg) { bdist[i] = lg; back[i] = j; }
+      }
+    }
+  }
+  int front_obj = front[1], steer_lane = q.rt_lane;
+  float front_dist = fdist[1];
+  if (ok) {  // lane_change_policy (:281-353)
+    const int n_cur = cur_road.n_lanes;
+    int lo = 0, hi_idx = n_cur - 1;
+    bool decided = false;
+    const int idx = rl.idx;
+    if (q.ck0 != q.ck1) {
+      const PgdRoad nxt = load_rec(roads + ldg(&rroads[q.ck1]));
+      const int diff = n_cur - nxt.n_lanes;
+      if (diff > 0) {
+        const PgdLane* c0 = lanes + cur_road.first_lane;
+        const PgdLane* n0 = lanes + nxt.first_lane;
+        if (precedes(ldg(&c0->ex), ldg(&c0->ey), ldg(&n0->sx), ldg(&n0->sy))) {
+          lo = 0; hi_idx = nxt.n_lanes - 1;
+        } else {
+          lo = diff; hi_idx = n_cur - 1;
+        }
+        if (idx < lo || idx > hi_idx) {
+          decided = true;
+          const int side = idx > hi_idx ? 0 : 2;
+          if (bdist[side] < V3_IDM_SAFE_DIST || fdist[side] < 5.0f) {
+            q.tspeed = V3_IDM_CREEP_SPEED;
+          } else {
+            q.tspeed = V3_IDM_NORMAL_SPEED;
+            front_obj = front[side];
+            front_dist = fdist[side];
+            steer_lane = cur_road.first_lane + idx + (side == 0 ? -1 : 1);
+          }
+        }
+      }
+    }
+    if (!decided) {
+      const float my_speed = kmh(q.v);
+      if (fabsf(my_speed - V3_IDM_NORMAL_SPEED) > 3.0f && front[1] >= 0 &&
+          fabsf(kmh(P.v[front[1]][ln]) - V3_IDM_NORMAL_SPEED) > 3.0f && q.timer > V3_IDM_LANE_CHANGE_FREQ) {
+        float side_speed[3] = {0.f, 0.f, 0.f};
+        bool side_ok[3] = {false, false, false};
+#pragma unroll
+        for (int sd = 0; sd < 3; sd += 2) {
+          if (front[sd] >= 0) {
+            side_speed[sd] = kmh(P.v[front[sd]][ln]);
+            side_ok[sd] = true;
+          } else if (cand[sd] >= 0 && fdist[sd] > V3_IDM_SAFE_DIST && bdist[sd] > V3_IDM_SAFE_DIST) {
+            side_speed[sd] = V3_IDM_MAX_SPEED;
+            side_ok[sd] = true;
+          }
+        }
+        const float front_speed = kmh(P.v[front[1]][ln]);
+        if (side_ok[0] && side_speed[0] - front_speed > V3_IDM_SPEED_INCREASE && idx - 1 >= lo && idx - 1 <= hi_idx) {
+          decided = true;
+          front_obj = front[0]; front_dist = fdist[0];
+          steer_lane = cur_road.first_lane + idx - 1;
+        } else if (side_ok[2] && side_speed[2] - front_speed > V3_IDM_SPEED_INCREASE && idx + 1 >= lo &&
+                   idx + 1 <= hi_idx) {
+          decided = true;
+          front_obj = front[2]; front_dist = fdist[2];
+          steer_lane = cur_road.first_lane + idx + 1;
+        }
+      }
+    }
+    if (!decided) {
+      q.tspeed = V3_IDM_NORMAL_SPEED;
+      q.timer += 1;
+    }
+  }
+  {  // steering_control (:244-252)
+    const PgdLane tl = (steer_lane == q.rt_lane) ? rl : load_rec(lanes + steer_lane);
+    float lon, lat;
+    lane_local(tl, q.x, q.y, lon, lat);
+    const float lane_heading = lane_heading_at(tl, lon + 1.0f);
+    float st = pid(q.hp, q.hi, 1.7f, 0.01f, 3.5f, pgd_wrap_to_pi(lane_heading - q.h));
+    st += pid(q.lp, q.li, 0.3f, 0.002f, 0.05f, -lat);
+    q.steer = st;
+  }
+  {  // acceleration (:254-271), speeds in km/h as in the reference
+    const float sp = kmh(q.v);
+    float acc = 1.0f - pgd_pow10f(fmaxf(sp, 0.0f) / q.tspeed);
+    if (front_obj >= 0) {
+      const float hx = q.hc, hy = q.hs;
+      const float fs = kmh(P.v[front_obj][ln]);
+      const float dvx = sp * hx - fs * P.hc[front_obj][ln], dvy = sp * hy - fs * P.hs[front_obj][ln];
+      const float dv = dvx * hx + dvy * hy;
+      const float d_star = 10.0f + sp * 1.5f + sp * dv / (2.0f * sqrtf(5.0f));
+      float d = front_dist;
+      if (!(fabsf(d) > 1e-2f)) d = d > 0.0f ? 1e-2f : -1e-2f;  // not_zero
+      const float ratio = d_star / d;
+      acc -= ratio * ratio;
+    }
+    q.throttle = acc;
+  }
+}
+
+// ---- phase C: ego sub-steps (role 0)  |  IDM of the awake traffic (traffic roles) ----------------------------------
+template <int V, int OBS_CAP>
+V3_HD void phase_c(Smem<V, OBS_CAP>& sm, Thr& th, const Tables& T, const State& S, const PgdConfig& cfg, int n_roles) {
+  if (!th.valid || !th.stepping) return;
+  const int ln = th.lane;
+  const int ns = cfg.decision_repeat < V3_MAX_SUBSTEPS ? cfg.decision_repeat : V3_MAX_SUBSTEPS;
+  if (th.role == 0) {  // 5 x doPhysics(0.02) of the ego (base_engine.py:206-232), remembering every pose
+    Veh& q = th.ego;
+    // A vehicle at rest with no yaw rate and no engine force is a fixed point of the sub-step (speed = max(0 - dv, 0)
+    // = 0, the pose does not move); only its drop counter runs.
+    const bool parked = q.v == 0.0f && q.yaw == 0.0f && !(q.throttle > 0.0f);
+    Sub sub;
+    if (!parked) sub = make_sub(q, th.tpl[0], cfg.dt);
+    float m2 = 0.0f;
+#pragma unroll 1
+    for (int k = 0; k < ns; ++k) {
+      if (q.airborne > 0) q.airborne--;  // placed 1 m above the road: no wheel contact while it drops
+      else if (!parked) substep(q, sub, cfg.dt);
+      const F4 p = {q.x, q.y, q.hc, q.hs};
+      sm.traj[k][ln] = p;
+      const float ex = q.x - sm.last_x[ln], ey = q.y - sm.last_y[ln];
+      m2 = fmaxf(m2, ex * ex + ey * ey);
+    }
+    sm.ego_travel[ln] = sqrtf(m2) * 1.001f + 1e-3f;  // how far the ego gets from its start pose within the step
+    return;
+  }
+  if (!sm.awake[th.role][ln]) return;
+  const Pub<V>& P = sm.p;
+#pragma unroll 1
+  for (int s = owner_first(th.role, n_roles); s < th.n_slots; s += owner_stride(n_roles)) {
+    const int fl = P.fl[s][ln];
+    if ((fl & (PGD_V_ALIVE | PGD_V_ACTIVE)) != (PGD_V_ALIVE | PGD_V_ACTIVE)) continue;
+    const size_t gi = (size_t)s * th.num_envs + th.env;
+    Veh q;
+    veh_load(q, S, gi);
+    q.vflags = fl;  // a vehicle woken in this step carries ACTIVE only in shared memory so far
+    q.hc = P.hc[s][ln]; q.hs = P.hs[s][ln];
+    idm_act(sm, th, T, q, s);
+    // hand-over to phase D through the vehicle's own state record (same thread)
+    const F4 c = {q.steer, q.throttle, q.hp, q.hi}, l = {q.lp, q.li, q.tspeed, q.yaw};
+    const I4 n = {q.lane, q.ck0 | (q.ck1 << 16), q.rt_lane, q.timer}, m = {q.rnd_n, q.airborne, q.vflags, 0};
+    S.ctrl[gi] = c; S.pidl[gi] = l; S.nav[gi] = n; S.misc[gi] = m;
+  }
+}
+
+// ---- localisation of one vehicle through the bucket grid (navigation.py:155-344, scene_utils.py:138-185); for the ego
+// the same scan also tests the chassis against line ghosts and sidewalks (base_vehicle.py:615-644) ----------------------
+template <bool EGO>
+V3_HD void localise(const Thr& th, const Tables& T, Veh& q, int s, uint32_t& flags) {
+  const PgdMap& mp = th.mp;
+  const PgdSlot& t = th.tpl[s];
+  const int32_t* rroads = T.route_roads + t.route_off;
+  const int32_t* rnodes = T.route_nodes + t.route_off;
+  const int32_t* ent = T.cell_entries + mp.entry_off;
+  const int cur_road = ldg(&rroads[q.ck0]);
+  const int next_road = q.ck0 != q.ck1 ? ldg(&rroads[q.ck1]) : -1;
+  const Rect er = {q.x, q.y, q.hc, q.hs, q.hl, q.hw};
+  int b_any = INT_MAX, b_cur = INT_MAX, b_next = INT_MAX;
+  const int cx = (int)floorf((q.x - mp.x0) * mp.inv_cell), cy = (int)floorf((q.y - mp.y0) * mp.inv_cell);
+  if (cx >= 0 && cy >= 0 && cx < mp.nx && cy < mp.ny) {
+    const int cell = mp.cell_off + cy * mp.nx + cx;
+    const int b0 = ldg(&T.cell_start[cell]), b1 = ldg(&T.cell_start[cell + 1]);
+    // entries are fetched four at a time (indices, then records) so that their latencies overlap
+    for (int k0 = b0; k0 < b1; k0 += 4) {
+      int bb[4];
+      PgdBox gg[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bb[j] = (k0 + j < b1) ? ldg(&ent[k0 + j]) : -1;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (bb[j] >= 0) gg[j] = load_rec(th.boxes + bb[j]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (bb[j] < 0) continue;
+        const int b = bb[j];
+        const PgdBox& g = gg[j];
+        if (g.kind == PGD_BOX_LANE) {
+          const float dx = q.x - g.cx, dy = q.y - g.cy;
+          if (!(fabsf(dx * g.ux + dy * g.uy) <= g.hl && fabsf(-dx * g.uy + dy * g.ux) <= g.hw)) continue;
+          const PgdLane* l = th.lanes + g.lane;
+          float dot;  // lane direction . heading > 0, written without trigonometry
+          if (ldg(&l->kind) == PGD_LANE_STRAIGHT) {
+            dot = ldg(&l->ax) * q.hc + ldg(&l->ay) * q.hs;
+          } else {
+            dot = ldg(&l->dir) * ((q.x - ldg(&l->ax)) * q.hs - (q.y - ldg(&l->ay)) * q.hc);
+          }
+          if (!(dot > 0.0f)) continue;
+          const int lroad = ldg(&l->road);
+          if (b < b_any) b_any = b;
+          if (lroad == cur_road && b < b_cur) b_cur = b;
+          if (lroad == next_road && b < b_next) b_next = b;
+        } else if (EGO) {
+          const Rect r = {g.cx, g.cy, g.ux, g.uy, g.hl, g.hw};
+          if (!rect_overlap(er, r)) continue;
+          flags |= g.kind == PGD_BOX_WHITE ? PGD_F_ON_WHITE
+                 : g.kind == PGD_BOX_YELLOW ? PGD_F_ON_YELLOW
+                 : g.kind == PGD_BOX_BROKEN ? PGD_F_ON_BROKEN : PGD_F_CRASH_SIDEWALK;
+        }
+      }
+    }
+  }
+  const int nb = b_cur != INT_MAX ? b_cur : (b_next != INT_MAX ? b_next : b_any);
+  const bool on_lane = nb != INT_MAX;
+  if (on_lane) q.lane = ldg(&th.boxes[nb].lane);
+  if (q.ck0 != q.ck1) {  // _update_target_checkpoints
+    const PgdLane l = load_rec(th.lanes + q.lane);
+    float lon, lat;
+    lane_local(l, q.x, q.y, lon, lat);
+    const int start = ldg(&th.roads[l.road].start_node);
+    if (lon < 5.0f) {
+#pragma unroll 1
+      for (int j = q.ck1; j < t.route_len - 1; ++j) {
+        if (ldg(&rnodes[j]) == start) {
+          q.ck0 = j;
+          q.ck1 = (j + 1 == t.route_len - 1) ? j : j + 1;
+          break;
+        }
+      }
+    }
+  }
+  q.vflags = on_lane ? (q.vflags | PGD_V_ON_LANE) : (q.vflags & ~PGD_V_ON_LANE);
+  if (!EGO && !on_lane) q.vflags &= ~PGD_V_ALIVE;  // traffic_manager.py:91-109
+}
+
+// ---- phase D: traffic sub-steps + chassis contact + after_step  |  ego after_step -------------------------------
+template <int V, int OBS_CAP>
+V3_HD void phase_d(Smem<V, OBS_CAP>& sm, Thr& th, const Tables& T, const State& S, const PgdConfig& cfg, int n_roles) {
+  if (!th.valid) return;
+  const int ln = th.lane;
+  Pub<V>& P = sm.p;
+  if (th.role == 0) {
+    Veh& q = th.ego;
+    localise<true>(th, T, q, 0, th.flags);
+    P.x[0][ln] = q.x; P.y[0][ln] = q.y; P.hc[0][ln] = q.hc; P.hs[0][ln] = q.hs; P.v[0][ln] = q.v;
+    P.lane[0][ln] = q.lane; P.fl[0][ln] = q.vflags;
+    sm.ego_h[ln] = q.h;
+    sm.ego_ck[ln] = q.ck0 | (q.ck1 << 16);
+    return;
+  }
+  if (!th.stepping) return;
+  const int ns = cfg.decision_repeat < V3_MAX_SUBSTEPS ? cfg.decision_repeat : V3_MAX_SUBSTEPS;
+  const float ehl = P.hl[0][ln], ehw = P.hw[0][ln];
+  int crash = 0;
+#pragma unroll 1
+  for (int s = owner_first(th.role, n_roles); s < th.n_slots; s += owner_stride(n_roles)) {
+    const int fl = P.fl[s][ln];
+    if (!(fl & PGD_V_ALIVE)) continue;
+    const size_t gi = (size_t)s * th.num_envs + th.env;
+    const float hl = P.hl[s][ln], hw = P.hw[s][ln];
+    const float reach = ehl + ehw + hl + hw;
+    if (!(fl & PGD_V_ACTIVE)) {
+      // parked: only its drop counter runs and its (fixed) chassis is tested against the ego's pose of every sub-step
+      const I4 m = S.misc[gi];
+      if (m.y > 0) {
+        const I4 m2 = {m.x, m.y > ns ? m.y - ns : 0, m.z, 0};
+        S.misc[gi] = m2;
+      }
+      const float px = P.x[s][ln], py = P.y[s][ln];
+      const float ddx0 = px - sm.last_x[ln], ddy0 = py - sm.last_y[ln];
+      const float far = reach + sm.ego_travel[ln];
+      if (ddx0 * ddx0 + ddy0 * ddy0 > far * far) continue;  // triangle inequality; the margin covers rounding
+#pragma unroll 1
+      for (int k = 0; k < ns; ++k) {
+        const F4 e = sm.traj[k][ln];
+        const float ddx = px - e.x, ddy = py - e.y;
+        if (ddx * ddx + ddy * ddy <= reach * reach) {
+          const Rect me = {px, py, P.hc[s][ln], P.hs[s][ln], hl, hw};
+          const Rect eg = {e.x, e.y, e.z, e.w, ehl, ehw};
+          if (rect_overlap(eg, me)) crash = 1;
+        }
+      }
+      continue;
+    }
+    Veh q;
+    veh_load(q, S, gi);
+    q.hc = P.hc[s][ln]; q.hs = P.hs[s][ln]; q.hl = hl; q.hw = hw;
+    const bool at_rest = q.v == 0.0f && q.yaw == 0.0f && !(q.throttle > 0.0f);
+    Sub sub;
+    if (!at_rest) sub = make_sub(q, th.tpl[s], cfg.dt);
+#pragma unroll 1
+    for (int k = 0; k < ns; ++k) {
+      if (q.airborne > 0) q.airborne--;
+      else if (!at_rest) substep(q, sub, cfg.dt);
+      const F4 e = sm.traj[k][ln];
+      const float ddx = q.x - e.x, ddy = q.y - e.y;
+      if (ddx * ddx + ddy * ddy <= reach * reach) {
+        const Rect me = {q.x, q.y, q.hc, q.hs, q.hl, q.hw};
+        const Rect eg = {e.x, e.y, e.z, e.w, ehl, ehw};
+        if (rect_overlap(eg, me)) crash = 1;
+      }
+    }
+    uint32_t unused = 0;
+    localise<false>(th, T, q, s, unused);
+    veh_store(q, S, gi);
+    P.x[s][ln] = q.x; P.y[s][ln] = q.y; P.hc[s][ln] = q.hc; P.hs[s][ln] = q.hs; P.v[s][ln] = q.v;
+    P.lane[s][ln] = q.lane; P.fl[s][ln] = q.vflags;
+  }
+  sm.crash[th.role][ln] = crash;
+}
+
+// ---- phase F: ego bookkeeping, one task per role ---------------------------------------------------------------------
+V3_HD int obs_dim_of(const PgdConfig& cfg) {
+  return (cfg.n_side > 0 ? cfg.n_side : 2) + 6 + cfg.n_lane_line + (cfg.random_agent_model ? 2 : 0) + 10 + 16 +
+         PGD_LIDAR_BEAMS;
+}
+
+/* task 0 (role 0): route distances, arrival, reward / cost / done, state observation, info, ego state store */
+template <int V, int OBS_CAP>
+V3_HD void task_reward(Smem<V, OBS_CAP>& sm, Thr& th, const Tables& T, const State& S, const PgdConfig& cfg, int mode,
+                       int n_roles, float* obs, float* reward, uint8_t* done, PgdInfo* info) {
+  const int ln = th.lane;
+  const Veh& ego = th.ego;
+  const PgdMap& mp = th.mp;
+  const PgdSlot& t0 = th.tpl[0];
+  const int32_t* rroads = T.route_roads + t0.route_off;
+  const int n_first = cfg.n_side > 0 ? cfg.n_side : 2;
+  float* const st = obs + n_first - 2;
+  const int n_extra = cfg.random_agent_model ? 2 : 0;
+  if (n_extra) {  // obs/state_obs.py:103-105: LENGTH / MAX_LENGTH, WIDTH / MAX_WIDTH (base_vehicle.py:83-84)
+    obs[n_first + 6 + cfg.n_lane_line] = clipf(t0.length / 10.0f, 0.0f, 1.0f);
+    obs[n_first + 6 + cfg.n_lane_line + 1] = clipf(t0.width / 2.5f, 0.0f, 1.0f);
+  }
+  uint32_t flags = th.flags;
+  int crash = 0;
+  for (int r = 1; r < n_roles; ++r) crash |= sm.crash[r][ln];
+  const float last_x = sm.last_x[ln], last_y = sm.last_y[ln];
+  const int cur_road_id = ldg(&rroads[ego.ck0]);
+  const PgdRoad cur_road = load_rec(th.roads + cur_road_id);
+  const PgdRoad fr = load_rec(th.roads + ldg(&rroads[t0.route_len - 2]));
+  const int el_road = ldg(&th.lanes[ego.lane].road);
+  const bool use_ego_lane = el_road == cur_road_id;
+  const int reward_lane = use_ego_lane ? ego.lane : cur_road.first_lane;
+  const int n_ref = cur_road.n_lanes;
+  const int sign_i = use_ego_lane ? 0 : (ldg(&th.roads[el_road].negative) ? -1 : 1);
+  float qlon0, qlat0, qlon1, qlat1, long_last = 0.0f, lat_last, long_now = 0.0f, lat_now = 0.0f;
+  lane_local(load_rec(th.lanes + cur_road.first_lane), ego.x, ego.y, qlon0, qlat0);
+  const PgdLane final_lane = load_rec(th.lanes + (fr.first_lane + fr.n_lanes - 1));
+  lane_local(final_lane, ego.x, ego.y, qlon1, qlat1);
+  if (!th.fresh) {
+    const PgdLane rl = load_rec(th.lanes + reward_lane);
+    lane_local(rl, last_x, last_y, long_last, lat_last);
+    lane_local(rl, ego.x, ego.y, long_now, lat_now);
+  }
+  const bool on_lane = (ego.vflags & PGD_V_ON_LANE) != 0;
+  if (on_lane) flags |= PGD_F_ON_LANE;
+  if (crash) flags |= PGD_F_CRASH_VEHICLE;
+  const float to_left = qlat0 + mp.lane_width / 2.0f;  // base_vehicle.py:383-388
+  const float to_right = mp.lane_width * (float)n_ref - to_left;
+  if (to_left < 0.0f || to_right < 0.0f) flags |= PGD_F_OUT_OF_ROUTE;
+  {  // arrive_destination (base_vehicle.py:738-745)
+    const float flen = final_lane.length;
+    if (flen - 5.0f < qlon1 && qlon1 < flen + 5.0f && mp.lane_width / 2.0f >= qlat1 &&
+        qlat1 >= (0.5f - (float)n_ref) * mp.lane_width)
+      flags |= PGD_F_ARRIVE_DEST;
+  }
+  bool out_of_road = (flags & (PGD_F_ON_YELLOW | PGD_F_ON_WHITE | PGD_F_CRASH_SIDEWALK)) || !on_lane;
+  if (cfg.out_of_route_done && (flags & PGD_F_OUT_OF_ROUTE)) out_of_road = true;
+  if (out_of_road) flags |= PGD_F_OUT_OF_ROAD;
+
+  const float sp = kmh(ego.v);
+  if (cfg.n_side <= 0) {
+    obs[0] = clipf(to_left / 18.0f, 0.0f, 1.0f);
+    obs[1] = clipf(to_right / 18.0f, 0.0f, 1.0f);
+  }
+  st[3] = clipf((sp + 1.0f) / (V3_MAX_SPEED_KMH + 1.0f), 0.0f, 1.0f);
+  st[4] = clipf((ego.steer / 60.0f + 1.0f) / 2.0f, 0.0f, 1.0f);
+  st[5] = clipf((th.envf.x + 1.0f) / 2.0f, 0.0f, 1.0f);
+  st[6] = clipf((th.envf.y + 1.0f) / 2.0f, 0.0f, 1.0f);
+  // yaw rate: arccos(clip(cos(angle between headings), 0, 1)) / 0.1 (state_obs.py:87-94) = min(|wrapped heading
+  // change|, pi/2) / 0.1 without the ill-conditioned arccos
+  const float last_h = th.fresh ? ego.h : S.pose[th.env].z;  // the stored heading is still the start-of-step one
+  st[7] = clipf(fminf(fabsf(pgd_wrap_to_pi(ego.h - last_h)), V3_PI / 2) / 0.1f, 0.0f, 1.0f);
+  float r = 0.0f, step_reward = 0.0f, cost = 0.0f, step_energy = 0.0f;
+  int is_done = 0;
+  if (!th.fresh) {  // envs/pgdrive_env.py:162-258
+    const float sign = sign_i == 0 ? 1.0f : (float)sign_i;
+    float lateral_factor = 1.0f;
+    if (cfg.use_lateral) lateral_factor = clipf(1.0f - 2.0f * fabsf(lat_now) / mp.lane_width, 0.0f, 1.0f);
+    r += cfg.driving_reward * (long_now - long_last) * lateral_factor * sign;
+    r += cfg.speed_reward * (sp / V3_MAX_SPEED_KMH) * sign;
+    step_reward = r;
+    if (flags & PGD_F_ARRIVE_DEST) r = cfg.success_reward;
+    else if (out_of_road) r = -cfg.out_of_road_penalty;
+    else if (crash) r = -cfg.crash_vehicle_penalty;
+    if (out_of_road) cost = cfg.out_of_road_cost;
+    else if (crash) cost = cfg.crash_vehicle_cost;
+    is_done = ((flags & PGD_F_ARRIVE_DEST) || out_of_road || crash) ? 1 : 0;
+    const float ddx = last_x - ego.x, ddy = last_y - ego.y;  // base_vehicle.py:278-290
+    step_energy = 3.25f * pgd_expf(0.01f * sp) * (sqrtf(ddx * ddx + ddy * ddy) / 1000.0f) / 100.0f * 1000.0f;
+    th.envf.w += step_energy;
+    th.envf.z += r;
+    th.envi.w += 1;
+    if (cfg.horizon > 0 && th.envi.w >= cfg.horizon) { is_done = 1; flags |= PGD_F_MAX_STEP; }
+    if (th.envi.z == 1) is_done = 1;  // done is sticky (base_env.py:315-316)
+    th.envi.z = is_done;
+  } else {
+    flags |= PGD_F_WAS_RESET;
+  }
+  if (mode == 0) {
+    reward[th.env] = r;
+    done[th.env] = (uint8_t)is_done;
+  }
+  if (info) {
+    PgdInfo inf;
+    inf.velocity = sp; inf.steering = ego.steer; inf.acceleration = ego.throttle;
+    inf.step_energy = step_energy; inf.episode_energy = th.envf.w;
+    inf.step_reward = step_reward; inf.episode_reward = th.envf.z; inf.cost = cost;
+    inf.episode_length = th.envi.w; inf.flags = flags;
+    info[th.env] = inf;
+  }
+  S.envi[th.env] = th.envi;
+  S.envf[th.env] = th.envf;
+  veh_store(ego, S, (size_t)th.env);
+}
+
+/* task 1: navigation info of the two checkpoints (navigation.py:213-260) + heading_diff (base_vehicle.py:433-458) */
+template <int V, int OBS_CAP>
+V3_HD void task_navi(const Smem<V, OBS_CAP>& sm, const Thr& th, const Tables& T, const PgdConfig& cfg, float* obs) {
+  const int ln = th.lane;
+  const Pub<V>& P = sm.p;
+  const PgdMap& mp = th.mp;
+  const float ex = P.x[0][ln], ey = P.y[0][ln], ehc = P.hc[0][ln], ehs = P.hs[0][ln];
+  const int ck0 = sm.ego_ck[ln] & 0xffff, ck1 = sm.ego_ck[ln] >> 16;
+  const int32_t* rroads = T.route_roads + th.tpl[0].route_off;
+  const int n_first = cfg.n_side > 0 ? cfg.n_side : 2;
+  float* const st = obs + n_first - 2;
+  float* const ob = obs + n_first + cfg.n_lane_line + (cfg.random_agent_model ? 2 : 0) - 2;
+  const PgdRoad cur_road = load_rec(th.roads + ldg(&rroads[ck0]));
+  const int n_ref = cur_road.n_lanes;
+#pragma unroll 1
+  for (int c = 0; c < 2; ++c) {
+    const PgdLane l = load_rec(th.lanes + (c == 0 ? cur_road.first_lane : ldg(&th.roads[ldg(&rroads[ck1])].first_lane)));
+    const float later_middle = ((float)n_ref / 2.0f - 0.5f) * mp.lane_width;
+    float px, py;
+    lane_position(l, l.length, later_middle, px, py);
+    float dx = px - ex, dy = py - ey;
+    const float dn = sqrtf(dx * dx + dy * dy);
+    if (dn > 50.0f) { dx = dx / dn * 50.0f; dy = dy / dn * 50.0f; }
+    float ph, ps;
+    project(ehc, ehs, dx, dy, ph, ps);
+    float bend = 0.0f, dir = 0.0f, angle = 0.0f;
+    if (l.kind == PGD_LANE_ARC) {
+      bend = l.radius / (60.0f + (float)n_ref * mp.lane_width);
+      dir = l.dir;
+      angle = l.length / l.radius;
+    }
+    float* q = ob + 8 + 5 * c;
+    q[0] = clipf((ph / 50.0f + 1.0f) / 2.0f, 0.0f, 1.0f);
+    q[1] = clipf((ps / 50.0f + 1.0f) / 2.0f, 0.0f, 1.0f);
+    q[2] = clipf(bend, 0.0f, 1.0f);
+    q[3] = clipf((dir + 1.0f) / 2.0f, 0.0f, 1.0f);
+    q[4] = clipf((angle * (180.0f / V3_PI) / 135.0f + 1.0f) / 2.0f, 0.0f, 1.0f);
+  }
+  {  // heading_diff against the right-most reference lane
+    const PgdLane l = load_rec(th.lanes + (cur_road.first_lane + cur_road.n_lanes - 1));
+    float lx, ly;
+    if (l.kind == PGD_LANE_STRAIGHT) { lx = -l.ay; ly = l.ax; }
+    else if (l.dir < 0.0f) { lx = ex - l.ax; ly = ey - l.ay; }
+    else { lx = l.ax - ex; ly = l.ay - ey; }
+    const float lnm = sqrtf(lx * lx + ly * ly);
+    st[2] = lnm > 0.0f ? clipf((ehc * lx + ehs * ly) / lnm, -1.0f, 1.0f) / 2.0f + 0.5f : 0.0f;
+  }
+}
+
+/* task 2: the 4 nearest vehicles inside the 50 m cylinder (lidar.py:55-77; ties -> lower slot) */
+template <int V, int OBS_CAP>
+V3_HD void task_neighbours(const Smem<V, OBS_CAP>& sm, const Thr& th, const PgdConfig& cfg, float* obs) {
+  const int ln = th.lane;
+  const Pub<V>& P = sm.p;
+  const float ex = P.x[0][ln], ey = P.y[0][ln], ehc = P.hc[0][ln], ehs = P.hs[0][ln];
+  const float esp = kmh(P.v[0][ln]);
+  const int n_first = cfg.n_side > 0 ? cfg.n_side : 2;
+  float* const ob = obs + n_first + cfg.n_lane_line + (cfg.random_agent_model ? 2 : 0) - 2;
+  uint32_t taken = 0;
+#pragma unroll 1
+  for (int rank = 0; rank < 4; ++rank) {
+    int best = -1;
+    float best_d2 = INFINITY;
+#pragma unroll 1
+    for (int s = 1; s < th.n_slots; ++s) {
+      if (!(P.fl[s][ln] & PGD_V_ALIVE) || ((taken >> s) & 1u)) continue;
+      const float dx = P.x[s][ln] - ex, dy = P.y[s][ln] - ey;
+      const float d2 = dx * dx + dy * dy;
+      if (d2 < V3_LIDAR_RANGE * V3_LIDAR_RANGE && (best < 0 || d2 < best_d2)) { best = s; best_d2 = d2; }
+    }
+    float* o4 = ob + 18 + 4 * rank;
+    if (best < 0) {
+      o4[0] = o4[1] = o4[2] = o4[3] = 0.0f;
+      continue;
+    }
+    taken |= 1u << best;
+    float pf, ps, vf, vs;
+    project(ehc, ehs, P.x[best][ln] - ex, P.y[best][ln] - ey, pf, ps);
+    const float ws = kmh(P.v[best][ln]);
+    project(ehc, ehs, ws * P.hc[best][ln] - esp * ehc, ws * P.hs[best][ln] - esp * ehs, vf, vs);
+    o4[0] = clipf((pf / V3_LIDAR_RANGE + 1.0f) / 2.0f, 0.0f, 1.0f);
+    o4[1] = clipf((ps / V3_LIDAR_RANGE + 1.0f) / 2.0f, 0.0f, 1.0f);
+    o4[2] = clipf((vf / V3_MAX_SPEED_KMH + 1.0f) / 2.0f, 0.0f, 1.0f);
+    o4[3] = clipf((vs / V3_MAX_SPEED_KMH + 1.0f) / 2.0f, 0.0f, 1.0f);
+  }
+}
+
+/* task 3: which chassis the lidar can reach, and the (conservative) arc of beams that can hit each */
+template <int V, int OBS_CAP>
+V3_HD void task_lidar_windows(Smem<V, OBS_CAP>& sm, const Thr& th) {
+  const int ln = th.lane;
+  const Pub<V>& P = sm.p;
+  const float ex = P.x[0][ln], ey = P.y[0][ln], eh = sm.ego_h[ln];
+  int n = 0;
+#pragma unroll 1
+  for (int s = 1; s < th.n_slots; ++s) {
+    if (!(P.fl[s][ln] & PGD_V_ALIVE)) continue;
+    const float dx = P.x[s][ln] - ex, dy = P.y[s][ln] - ey;
+    const float d2 = dx * dx + dy * dy;
+    const float hl = P.hl[s][ln], hw = P.hw[s][ln];
+    const float hd = sqrtf(hl * hl + hw * hw);
+    const float reach = V3_LIDAR_RANGE + hd;
+    if (!(d2 < reach * reach)) continue;
+    const float d = sqrtf(d2);
+    int blo = 0, bn = PGD_LIDAR_BEAMS - 1;
+    if (d > hd * 1.001f) {
+      const float per_rad = (float)PGD_LIDAR_BEAMS / V3_TWO_PI;
+      const float c = (pgd_atan2f(dy, dx) - eh) * per_rad;
+      const float w = pgd_asinf(fminf(hd / d, 1.0f)) * per_rad;
+      const int nn = (int)ceilf(2.0f * w) + 3;
+      if (nn < PGD_LIDAR_BEAMS) {
+        bn = nn;
+        blo = ((int)floorf(c - w) - 1) % PGD_LIDAR_BEAMS;
+        if (blo < 0) blo += PGD_LIDAR_BEAMS;
+      }
+    }
+    sm.vis[n++][ln] = s | (blo << 8) | (bn << 16);
+  }
+  sm.n_vis[ln] = n;
+}
+
+/* side / lane-line detectors (distance_detector.py:137-152): ray fans against the line ghosts of the map; a beam
+ * looks up the bucket of a point every 8 m along itself (buckets list every box within 4 m of them).  The rays of an
+ * environment are spread over the roles. */
+template <int V, int OBS_CAP>
+V3_HD void task_detectors(const Smem<V, OBS_CAP>& sm, const Thr& th, const Tables& T, const PgdConfig& cfg, int n_roles,
+                          float* obs) {
+  const int ln = th.lane;
+  const Pub<V>& P = sm.p;
+  const PgdMap& mp = th.mp;
+  const float ex = P.x[0][ln], ey = P.y[0][ln], eh = sm.ego_h[ln];
+  const int n_first = cfg.n_side > 0 ? cfg.n_side : 2;
+  const int n_rays = cfg.n_side + cfg.n_lane_line;
+  const int32_t* ent = T.cell_entries + mp.entry_off;
+#pragma unroll 1
+  for (int rI = th.role; rI < n_rays; rI += n_roles) {
+    const bool side = rI < cfg.n_side;
+    const int i = side ? rI : rI - cfg.n_side;
+    const int n = side ? cfg.n_side : cfg.n_lane_line;
+    const float dist = side ? cfg.side_distance : cfg.lane_line_distance;
+    const float ang = (float)i * (V3_TWO_PI / (float)n) + V3_PI / 2 + eh;
+    float sn, cs;
+    V3_SINCOS(ang, sn, cs);
+    const float dx = cs * dist, dy = sn * dist;
+    float best = 1.0f;
+    for (float sd = 4.0f; sd - 4.0f < dist; sd += 8.0f) {
+      if (best * dist < sd - 4.0f) break;
+      const float px = ex + cs * sd, py = ey + sn * sd;
+      const int cx = (int)floorf((px - mp.x0) * mp.inv_cell), cy = (int)floorf((py - mp.y0) * mp.inv_cell);
+      if (cx < 0 || cy < 0 || cx >= mp.nx || cy >= mp.ny) continue;
+      const int cell = mp.cell_off + cy * mp.nx + cx;
+      const int b0 = ldg(&T.cell_start[cell]), b1 = ldg(&T.cell_start[cell + 1]);
+#pragma unroll 1
+      for (int k = b0; k < b1; ++k) {
+        const PgdBox g = load_rec(th.boxes + ldg(&ent[k]));
+        if (!(g.kind == PGD_BOX_WHITE || g.kind == PGD_BOX_YELLOW || (!side && g.kind == PGD_BOX_BROKEN))) continue;
+        const Rect r = {g.cx, g.cy, g.ux, g.uy, g.hl, g.hw};
+        best = fminf(best, ray_rect(ex, ey, dx, dy, r));
+      }
+    }
+    if (side) obs[i] = best;
+    else obs[n_first + 6 + i] = best;
+  }
+}
+
+template <int V, int OBS_CAP>
+V3_HD void phase_f(Smem<V, OBS_CAP>& sm, Thr& th, const Tables& T, const State& S, const PgdConfig& cfg, int mode,
+                   int n_roles, int obs_dim, float* reward, uint8_t* done, PgdInfo* info) {
+  if (!th.valid) return;
+  float* obs = sm.u.obs + (size_t)th.lane * obs_dim;
+#pragma unroll 1
+  for (int task = th.role; task < 4; task += n_roles) {
+    if (task == 0) task_reward(sm, th, T, S, cfg, mode, n_roles, obs, reward, done, info);
+    else if (task == 1) task_navi(sm, th, T, cfg, obs);
+    else if (task == 2) task_neighbours(sm, th, cfg, obs);
+    else task_lidar_windows(sm, th);
+  }
+  if (cfg.n_side > 0 || cfg.n_lane_line > 0) task_detectors(sm, th, T, cfg, n_roles, obs);
+}
+
+// ---- phase L: lidar as a scatter (cutils.pyx:60-142 restated per chassis instead of per beam) ---------------------
+/* Thread (role, lane) of the CTA: the warp `role` takes environments role, role + R, ...; its lanes are the beams
+ * of the window of each visible chassis.  The row was pre-filled with 1.0 (no hit); hits are min-ed in. */
+V3_HD void lidar_min(float* cell, float t) {
+#ifdef __CUDA_ARCH__
+  atomicMin(reinterpret_cast<int*>(cell), __float_as_int(t));  // non-negative floats order like their bit patterns
+#else
+  if (t < *cell) *cell = t;
+#endif
+}
+
+template <int V, int OBS_CAP>
+V3_HD void phase_l(Smem<V, OBS_CAP>& sm, int role, int lane, int n_roles, int obs_dim) {
+  const Pub<V>& P = sm.p;
+  const int head = obs_dim - PGD_LIDAR_BEAMS;
+#pragma unroll 1
+  for (int e = role; e < V3_LANES; e += n_roles) {
+    if (!sm.wrote[e]) continue;
+    const int nv = sm.n_vis[e];
+    if (nv == 0) continue;
+    const float ex = P.x[0][e], ey = P.y[0][e], eh = sm.ego_h[e];
+    float* row = sm.u.obs + (size_t)e * obs_dim + head;
+#pragma unroll 1
+    for (int k = 0; k < nv; ++k) {
+      const int w = sm.vis[k][e];
+      const int s = w & 0xff, blo = (w >> 8) & 0xff, bn = w >> 16;
+      const Rect r = {P.x[s][e], P.y[s][e], P.hc[s][e], P.hs[s][e], P.hl[s][e], P.hw[s][e]};
+#pragma unroll 1
+      for (int rel = lane; rel <= bn; rel += V3_LANES) {
+        int i = blo + rel;
+        if (i >= PGD_LIDAR_BEAMS) i -= PGD_LIDAR_BEAMS;
+        const float ang = (float)i * (V3_TWO_PI / (float)PGD_LIDAR_BEAMS) + eh;
+        float sn, cs;
+        V3_SINCOS(ang, sn, cs);
+        const float t = ray_rect(ex, ey, cs * V3_LIDAR_RANGE, sn * V3_LIDAR_RANGE, r);
+        if (t < 1.0f) lidar_min(row + i, t);
+      }
+    }
+  }
+}
+
+}  // namespace pgdv3
+#endif

@@ -224,6 +224,12 @@ def build_seed_tables(seeds, map_config, density, spawn, workers=None, stored=No
     return T
 
 
+def engine_layout(cfg):
+    if cfg.get("layout", None) is not None:
+        return int(cfg["layout"])
+    return 1 if cfg.get("one_thread_per_env", False) else 0
+
+
 class _Engine:
     """One C-ABI handle + its loaded tables."""
     def __init__(self, cfg, num_envs, num_slots, device, auto_reset, horizon=None):
@@ -243,7 +249,7 @@ class _Engine:
             side_distance=cfg["vehicle_config"]["side_detector"]["distance"],
             n_lane_line=cfg["vehicle_config"]["lane_line_detector"]["num_lasers"],
             lane_line_distance=cfg["vehicle_config"]["lane_line_detector"]["distance"],
-            layout=1 if cfg.get("one_thread_per_env", False) else 0,
+            layout=engine_layout(cfg),
             random_agent_model=bool(cfg["random_agent_model"])
         )
         self.obs_dim = cabi.obs_dim(self.pcfg)
@@ -290,7 +296,7 @@ class VecPGDriveEnv:
             stored = load_map_file(cfg["_load_map_from_json"], self.map_config, seeds)
         self._T = None
         random_lane = (bool(cfg["random_lane_width"]), bool(cfg["random_lane_num"]))
-        if cfg["random_agent_model"] and not cfg["one_thread_per_env"]:
+        if cfg["random_agent_model"] and engine_layout(cfg) == 0:
             raise NotImplementedError("random_agent_model is only in the one-thread-per-environment layout "
                                       "(one_thread_per_env=True) so far")
         if cfg["random_agent_model"] and cfg["device_mapgen"]:

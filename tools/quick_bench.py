@@ -6,9 +6,9 @@ import bench
 from pgdrive_b200 import VecPGDriveEnv
 n = int(os.environ.get("ENVS", 65536)); K = int(os.environ.get("STEPS", 200)); W = 40
 T = bench.build_tables()
-layout = os.environ.get("LAYOUT", "0") == "1"  # LAYOUT=1: one thread per environment (pgd_step_v2.cu)
+layout = int(os.environ.get("LAYOUT", "0"))  # 0 cooperative, 1 one thread per env, 2 role per warp
 env = VecPGDriveEnv(dict(start_seed=1000, environment_num=100, num_envs=n, traffic_density=0.1, num_slots=16,
-                         one_thread_per_env=layout), tables_dict=T)
+                         layout=layout), tables_dict=T)
 env.reset()
 mode = os.environ.get("ACTIONS", "uniform")
 g = torch.Generator(device="cuda"); g.manual_seed(1)
