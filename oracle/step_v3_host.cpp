@@ -10,8 +10,6 @@
 
 using namespace pgdv3;
 
-#define HOST_OBS_CAP (2 * PGD_MAX_DETECTOR_BEAMS + 6 + 2 + 10 + 16 + PGD_LIDAR_BEAMS)
-
 struct HostV3 {
   Tables T;
   State S;
@@ -19,15 +17,19 @@ struct HostV3 {
   int roles;
 };
 
-template <int V>
-static void run_v(HostV3* h, int mode, const float* actions, float* obs, float* reward, uint8_t* done, PgdInfo* info) {
-  typedef Smem<V, HOST_OBS_CAP> SM;
-  static SM* sm = nullptr;
-  if (!sm) sm = (SM*)aligned_alloc(128, (sizeof(SM) + 127) / 128 * 128);
-  static Thr th[V3_MAX_ROLES][V3_LANES];
-  const int n = h->cfg.num_envs, od = obs_dim_of(h->cfg), R = h->roles;
+template <int V, int R>
+static void run_vr(HostV3* h, int mode, const float* actions, float* obs, float* reward, uint8_t* done, PgdInfo* info) {
+  typedef Smem<V, R> SM;
+  const int n = h->cfg.num_envs, od = obs_dim_of(h->cfg);
+  const size_t bytes = smem_bytes<V, R>(od, h->cfg.decision_repeat);
+  unsigned char* raw = (unsigned char*)aligned_alloc(128, (bytes + 127) / 128 * 128);
+  SM& sm = *reinterpret_cast<SM*>(raw);
+  float* rows = reinterpret_cast<float*>(raw + smem_obs_offset<V, R>());
+  TrajPtr traj = reinterpret_cast<TrajPtr>(raw + smem_tv_offset<V, R>(od));
+  VisPtr vis = reinterpret_cast<VisPtr>(raw + smem_tv_offset<V, R>(od));
+  static Thr<V, R> th[R][V3_LANES];
   for (int env0 = 0; env0 < n; env0 += V3_LANES) {
-    memset(sm, 0xff, sizeof(SM));  // shared memory starts as garbage on the device
+    memset(raw, 0xff, bytes);  // shared memory starts as garbage on the device
     bool any = false;
     for (int r = 0; r < R; ++r)
       for (int l = 0; l < V3_LANES; ++l) {
@@ -35,17 +37,29 @@ static void run_v(HostV3* h, int mode, const float* actions, float* obs, float* 
         any = any || th[r][l].valid;
       }
     if (!any) continue;
-#define ALL(call) for (int r = 0; r < R; ++r) for (int l = 0; l < V3_LANES; ++l) { Thr& t = th[r][l]; (void)t; call; }
-    ALL(phase_a(*sm, t, h->S, h->cfg, R, actions));
-    ALL(phase_b(*sm, t, R));
-    ALL(phase_c(*sm, t, h->T, h->S, h->cfg, R));
-    for (int i = 0; i < V3_LANES * od; ++i) sm->u.obs[i] = 1.0f;
-    ALL(phase_d(*sm, t, h->T, h->S, h->cfg, R));
-    ALL(phase_f(*sm, t, h->T, h->S, h->cfg, mode, R, od, reward, done, info));
-    ALL(phase_l(*sm, r, l, R, od));
+#define ALL(call) for (int r = 0; r < R; ++r) for (int l = 0; l < V3_LANES; ++l) { Thr<V, R>& t = th[r][l]; (void)t; call; }
+    ALL(phase_a(sm, t, h->S, h->cfg, actions));
+    ALL(phase_b(sm, t, rows));
+    ALL(phase_c(sm, t, h->T, h->S, h->cfg, rows, traj));
+    for (int i = 0; i < V3_LANES * od; ++i) rows[i] = 1.0f;
+    ALL(phase_d(sm, t, h->T, h->S, h->cfg, traj));
+    ALL(phase_f(sm, t, h->T, h->S, h->cfg, mode, od, rows, vis, reward, done, info));
+    ALL(phase_l(sm, h->T, h->S, r, l, n, env0, od, rows, vis));
 #undef ALL
     for (int l = 0; l < V3_LANES; ++l)
-      if (sm->wrote[l]) memcpy(obs + (size_t)(env0 + l) * od, sm->u.obs + (size_t)l * od, (size_t)od * 4);
+      if (sm.wrote[l]) memcpy(obs + (size_t)(env0 + l) * od, rows + (size_t)l * od, (size_t)od * 4);
+  }
+  free(raw);
+}
+
+template <int V>
+static void run_v(HostV3* h, int mode, const float* actions, float* obs, float* reward, uint8_t* done, PgdInfo* info) {
+  switch (h->roles) {
+    case 2: run_vr<V, 2>(h, mode, actions, obs, reward, done, info); break;
+    case 3: run_vr<V, 3>(h, mode, actions, obs, reward, done, info); break;
+    case 4: run_vr<V, 4>(h, mode, actions, obs, reward, done, info); break;
+    case 6: run_vr<V, 6>(h, mode, actions, obs, reward, done, info); break;
+    default: run_vr<V, 8>(h, mode, actions, obs, reward, done, info); break;
   }
 }
 

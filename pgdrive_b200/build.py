@@ -41,7 +41,8 @@ def build_cuda(force=False, verbose=False, out=OUT, defines=()):
     objs, jobs, relink = [], [], force or not os.path.exists(out)
     for unit, extra in UNITS.items():
         src = os.path.join(CSRC, unit)
-        utag = tag if unit == "pgd_step.cu" else ""  # variants only differ in the step kernel
+        variant_unit = "pgd_step_v3.cu" if any("V3_" in d for d in defines) else "pgd_step.cu"
+        utag = tag if unit == variant_unit else ""  # variants only differ in one step kernel
         obj = os.path.join(CSRC, unit.replace(".cu", utag + ".o"))
         deps = [src] + [d if os.path.isabs(d) else os.path.join(CSRC, d) for d in COMMON + extra]
         if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(d) for d in deps):

@@ -12,76 +12,119 @@ using namespace pgdv3;
 #ifndef V3_ROLES
 #define V3_ROLES 4
 #endif
-#define V3_OBS_DET (2 * PGD_MAX_DETECTOR_BEAMS + 6 + 2 + 10 + 16 + PGD_LIDAR_BEAMS) /* 754: both detector fans */
-#define V3_OBS_PLAIN (PGD_OBS_DIM + 2)                                               /* 276: + vehicle size */
+#ifndef V3_MIN_CTAS
+#define V3_MIN_CTAS 4
+#endif
 
-template <int V, int OBS_CAP>
-__global__ void __launch_bounds__(V3_ROLES * 32) pgd_step_v3_kernel(Tables T, State S, PgdConfig cfg, int mode,
-                                                                    int env_begin, int env_end,
-                                                                    const float* __restrict__ actions,
-                                                                    float* __restrict__ obs,
-                                                                    float* __restrict__ reward,
-                                                                    uint8_t* __restrict__ done,
-                                                                    PgdInfo* __restrict__ info) {
+#ifdef V3_PHASE_CLOCKS  // diagnostic build: cycles between the CTA barriers, summed over CTAs (thread 0 of each)
+__device__ unsigned long long g_v3_clk[16];
+#define V3_CLK(i)                                                              \
+  do {                                                                         \
+    if (threadIdx.x == 0) {                                                    \
+      const long long now_ = clock64();                                        \
+      atomicAdd(&g_v3_clk[i], (unsigned long long)(now_ - clk_));              \
+      clk_ = now_;                                                             \
+    }                                                                          \
+  } while (0)
+extern "C" int pgd_debug_phase_clocks(unsigned long long* out, int reset) {
+  cudaMemcpyFromSymbol(out, g_v3_clk, sizeof(g_v3_clk));
+  if (reset) {
+    unsigned long long z[16] = {0};
+    cudaMemcpyToSymbol(g_v3_clk, z, sizeof(z));
+  }
+  return 0;
+}
+#else
+#define V3_CLK(i)
+#endif
+
+template <int V, int R>
+__global__ void __launch_bounds__(R * 32, V3_MIN_CTAS) pgd_step_v3_kernel(Tables T, State S, PgdConfig cfg, int mode,
+                                                                         int env_begin, int env_end,
+                                                                         const float* __restrict__ actions,
+                                                                         float* __restrict__ obs,
+                                                                         float* __restrict__ reward,
+                                                                         uint8_t* __restrict__ done,
+                                                                         PgdInfo* __restrict__ info) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  Smem<V, OBS_CAP>& sm = *reinterpret_cast<Smem<V, OBS_CAP>*>(smem_raw);
+  Smem<V, R>& sm = *reinterpret_cast<Smem<V, R>*>(smem_raw);
+  float* rows = reinterpret_cast<float*>(smem_raw + smem_obs_offset<V, R>());
+  const int obs_dim = obs_dim_of(cfg);
+  unsigned char* tv = smem_raw + smem_tv_offset<V, R>(obs_dim);
+  TrajPtr traj = reinterpret_cast<TrajPtr>(tv);
+  VisPtr vis = reinterpret_cast<VisPtr>(tv);
   const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
   const int env0 = env_begin + blockIdx.x * V3_LANES;
-  const int obs_dim = obs_dim_of(cfg);
-  Thr th;
+#ifdef V3_PHASE_CLOCKS
+  long long clk_ = clock64();
+#endif
+  Thr<V, R> th;
   thread_init(th, T, S, cfg, mode, lane, role, env0 + lane, env_end);
   if (!__syncthreads_or(th.valid)) return;  // reset pass: no environment of this CTA is marked
-  phase_a(sm, th, S, cfg, V3_ROLES, actions);
+  V3_CLK(0);
+  phase_a(sm, th, S, cfg, actions);
+  V3_CLK(1);
   __syncthreads();
-  phase_b(sm, th, V3_ROLES);
+  V3_CLK(2);
+  phase_b(sm, th, rows);
   __syncthreads();
-  phase_c(sm, th, T, S, cfg, V3_ROLES);
+  V3_CLK(3);
+  phase_c(sm, th, T, S, cfg, rows, traj);
+  V3_CLK(4);
   __syncthreads();
+  V3_CLK(5);
   {  // pre-fill the rows with 1.0 = "no hit" (the IDM look-up data that shared this storage is dead now)
-    float4* o4 = reinterpret_cast<float4*>(sm.u.obs);
+    float4* o4 = reinterpret_cast<float4*>(rows);
     const int n4 = V3_LANES * obs_dim / 4;  // 32 rows: a multiple of 4 floats for every row length
-    for (int i = threadIdx.x; i < n4; i += V3_ROLES * 32) o4[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+    for (int i = threadIdx.x; i < n4; i += R * 32) o4[i] = make_float4(1.f, 1.f, 1.f, 1.f);
   }
-  phase_d(sm, th, T, S, cfg, V3_ROLES);
+  V3_CLK(6);
+  phase_d(sm, th, T, S, cfg, traj);
+  V3_CLK(7);
   __syncthreads();
-  phase_f(sm, th, T, S, cfg, mode, V3_ROLES, obs_dim, reward, done, info);
+  V3_CLK(8);
+  phase_f(sm, th, T, S, cfg, mode, obs_dim, rows, vis, reward, done, info);
+  V3_CLK(9);
   __syncthreads();
-  phase_l(sm, role, lane, V3_ROLES, obs_dim);
+  V3_CLK(10);
+  phase_l(sm, T, S, role, lane, cfg.num_envs, env0, obs_dim, rows, vis);
+  V3_CLK(11);
   // ---- write-out -----------------------------------------------------------------------------------------------------
   const int all = __syncthreads_and(sm.wrote[lane]);
   float* dst = obs + (size_t)env0 * obs_dim;
   if (all && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
     if (threadIdx.x == 0) {
       const uint32_t bytes = (uint32_t)(V3_LANES * obs_dim * sizeof(float));
-      const uint32_t src = (uint32_t)__cvta_generic_to_shared(sm.u.obs);
+      const uint32_t src = (uint32_t)__cvta_generic_to_shared(rows);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes)
                    : "memory");
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
+    V3_CLK(12);
   } else {
-    for (int e = role; e < V3_LANES; e += V3_ROLES) {
+    for (int e = role; e < V3_LANES; e += R) {
       if (!sm.wrote[e]) continue;
-      const float* src = sm.u.obs + (size_t)e * obs_dim;
+      const float* src = rows + (size_t)e * obs_dim;
       float* d = dst + (size_t)e * obs_dim;
       for (int c = lane; c < obs_dim; c += 32) d[c] = src[c];
     }
   }
 }
 
-template <int V, int OBS_CAP>
+template <int V, int R>
 static int launch_one(PgdHandle* h, const Tables& T, const State& S, int mode, int env_begin, int env_end,
                       const float* actions, float* obs, float* reward, uint8_t* done, PgdInfo* info, cudaStream_t st) {
-  static bool configured = false;  // per instantiation
-  const size_t smem = sizeof(Smem<V, OBS_CAP>);
-  if (!configured) {
-    CU(cudaFuncSetAttribute(pgd_step_v3_kernel<V, OBS_CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
+  static int configured = 0;  // per instantiation: largest dynamic shared-memory size opted into so far
+  const int smem = (int)smem_bytes<V, R>(obs_dim_of(h->cfg), h->cfg.decision_repeat);
+  if (smem > configured) {
+    CU(cudaFuncSetAttribute(pgd_step_v3_kernel<V, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = smem;
   }
   const int grid = (env_end - env_begin + V3_LANES - 1) / V3_LANES;
-  pgd_step_v3_kernel<V, OBS_CAP><<<grid, V3_ROLES * 32, smem, st>>>(T, S, h->cfg, mode, env_begin, env_end, actions,
-                                                                   obs, reward, done, info);
+  pgd_step_v3_kernel<V, R><<<grid, R * 32, smem, st>>>(T, S, h->cfg, mode, env_begin, env_end, actions, obs, reward,
+                                                       done, info);
   return 0;
 }
 
@@ -96,16 +139,12 @@ int pgd_launch_step_v3(PgdHandle* h, int mode, int env_begin, int env_end, const
   S.pose = (F4*)h->S.pose; S.ctrl = (F4*)h->S.ctrl; S.pidl = (F4*)h->S.pidl; S.nav = (I4*)h->S.nav;
   S.misc = (I4*)h->S.misc; S.envi = (I4*)h->S.envi; S.envf = (F4*)h->S.envf;
   if (h->timing && mode == 0) cudaEventRecord(h->ev0, st);
-  const bool det = h->cfg.n_side > 0 || h->cfg.n_lane_line > 0;  // detectors need the long rows
   const int V = h->cfg.num_slots;
   int rc;
-#define V3_LAUNCH(VV, CAP) rc = launch_one<VV, CAP>(h, T, S, mode, env_begin, env_end, actions, obs, reward, done, info, st)
-  if (V == 16 && !det) V3_LAUNCH(16, V3_OBS_PLAIN);
-  else if (V == 24 && !det) V3_LAUNCH(24, V3_OBS_PLAIN);
-  else if (V == 32 && !det) V3_LAUNCH(32, V3_OBS_PLAIN);
-  else if (V == 16) V3_LAUNCH(16, V3_OBS_DET);
-  else if (V == 24) V3_LAUNCH(24, V3_OBS_DET);
-  else V3_LAUNCH(32, V3_OBS_DET);
+#define V3_LAUNCH(VV) rc = launch_one<VV, V3_ROLES>(h, T, S, mode, env_begin, env_end, actions, obs, reward, done, info, st)
+  if (V == 16) V3_LAUNCH(16);
+  else if (V == 24) V3_LAUNCH(24);
+  else V3_LAUNCH(32);
 #undef V3_LAUNCH
   if (rc) return rc;
   if (h->timing && mode == 0) cudaEventRecord(h->ev1, st);

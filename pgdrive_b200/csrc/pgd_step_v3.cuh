@@ -276,11 +276,12 @@ V3_HD Sub make_sub(const Veh& q, const PgdSlot& t, float dt) {  // base_vehicle.
 
 // ---- shared memory ------------------------------------------------------------------------------------------------
 template <int V>
-struct Pub {  // public per-slot state, [slot][lane]
+struct Pub {  // public per-slot state, [slot][lane]; lf = lane << 8 | PGD_V_* flags
   float x[V][V3_LANES], y[V][V3_LANES], hc[V][V3_LANES], hs[V][V3_LANES], v[V][V3_LANES];
-  float hl[V][V3_LANES], hw[V][V3_LANES];
-  int lane[V][V3_LANES], fl[V][V3_LANES];
+  int lf[V][V3_LANES];
 };
+V3_HD int lf_pack(int lane, int fl) { return (lane << 8) | (fl & 0xff); }
+V3_HD int lf_lane(int lf) { return lf >> 8; }
 
 template <int V>
 struct IdmPub {  // IDM look-up data of every vehicle (phase B -> C); shares its storage with the observation rows
@@ -288,23 +289,38 @@ struct IdmPub {  // IDM look-up data of every vehicle (phase B -> C); shares its
       llen[V][V3_LANES];
 };
 
-template <int V, int OBS_CAP>
+/* Dynamic shared memory: [Smem, fixed part][rows: 32 x obs_dim floats in HBM layout; phases B, C: IdmPub][tv: phases
+ * C, D the ego's pose (x, y, cos, sin) after every sub-step, F4 [ns][32]; phases F, L the visible chassis, int [V][32]:
+ * slot | first beam << 8 | beam count << 16]. */
+typedef F4 (*TrajPtr)[V3_LANES];
+typedef int (*VisPtr)[V3_LANES];
+template <int V, int R>
 struct Smem {
-  union alignas(128) {
-    float obs[V3_LANES * OBS_CAP];  // the CTA's rows back to back, stride = the row length (HBM layout)
-    IdmPub<V> idm;
-  } u;
   Pub<V> p;
-  F4 traj[V3_MAX_SUBSTEPS][V3_LANES];  // ego pose (x, y, cos, sin) after every sub-step
-  float last_x[V3_LANES], last_y[V3_LANES], ego_travel[V3_LANES], ego_h[V3_LANES];
-  int ego_ck[V3_LANES];
-  int awake[V3_MAX_ROLES][V3_LANES], crash[V3_MAX_ROLES][V3_LANES];  // one word per role: no atomics, no clearing
-  int n_vis[V3_LANES];
-  int vis[V][V3_LANES];  // visible chassis: slot | first beam << 8 | beam count << 16
-  int wrote[V3_LANES];
+  F4 efin[V3_LANES];                     // ego pose after the sub-steps (template pose when the episode restarts)
+  int scan[R][4][V3_LANES];              // ego bucket scan, one share per role: b_any, b_cur, b_next, PGD_F_* flags
+  int amask[R][V3_LANES], pmask[R][V3_LANES], crash[R][V3_LANES];  // one word per role: no atomics, no clearing
+  float last_x[V3_LANES], last_y[V3_LANES], ego_travel[V3_LANES], ego_h[V3_LANES], ego_v[V3_LANES],
+      ego_hl[V3_LANES], ego_hw[V3_LANES];
+  int ego_ck[V3_LANES], n_vis[V3_LANES], wrote[V3_LANES];
 };
 
+template <int V, int R>
+V3_HD constexpr size_t smem_obs_offset() { return (sizeof(Smem<V, R>) + 127) / 128 * 128; }
+template <int V, int R>
+V3_HD size_t smem_tv_offset(int obs_dim) {
+  const size_t rows = (size_t)V3_LANES * obs_dim * sizeof(float);
+  return smem_obs_offset<V, R>() + ((rows > sizeof(IdmPub<V>) ? rows : sizeof(IdmPub<V>)) + 127) / 128 * 128;
+}
+template <int V, int R>
+V3_HD size_t smem_bytes(int obs_dim, int substeps) {
+  const size_t traj = (size_t)substeps * V3_LANES * sizeof(F4), vis = (size_t)V * V3_LANES * sizeof(int);
+  return smem_tv_offset<V, R>(obs_dim) + (traj > vis ? traj : vis);
+}
+
+template <int V, int R>
 struct Thr {  // what a thread keeps across the phases
+  static constexpr int MAXOWN = (V - 1 + R - 2) / (R - 1);  // slots a traffic role publishes
   int lane, role, env, num_envs;
   bool valid, fresh, stepping;
   I4 envi;
@@ -318,10 +334,24 @@ struct Thr {  // what a thread keeps across the phases
   int n_slots, n_groups, trig;
   Veh ego;         // role 0
   uint32_t flags;  // role 0: PGD_F_* of the ego
+  // loads that depend on nothing but the environment index, issued before the table look-ups they overlap with
+  F4 pre_pose, pre_ctrl, pre_pidl;  // role 0: the ego's record
+  I4 pre_nav, pre_misc;             // role 0 (all roles: pre_nav.x = the ego's lane, for the trigger test)
+  int pre_fl[MAXOWN], pre_air[MAXOWN];  // traffic roles: flags / drop counters of the slots they publish
 };
 
-V3_HD int owner_first(int role, int n_roles) { return role; }                // first traffic slot of a traffic role
-V3_HD int owner_stride(int n_roles) { return n_roles - 1; }
+V3_HD int imin(int a, int b) { return a < b ? a : b; }
+V3_HD int ctz32(uint32_t m) {
+#ifdef __CUDA_ARCH__
+  return __ffs((int)m) - 1;
+#else
+  return __builtin_ctz(m);
+#endif
+}
+V3_HD uint32_t drop_low(uint32_t m, int n) {  // clear the n lowest set bits
+  for (int i = 0; i < n && m; ++i) m &= m - 1;
+  return m;
+}
 
 V3_HD void veh_from_template(Veh& q, const PgdSlot& t, int s) {
   q.x = t.x; q.y = t.y; q.h = t.heading; q.v = 0.0f; q.yaw = 0.0f;
@@ -332,14 +362,18 @@ V3_HD void veh_from_template(Veh& q, const PgdSlot& t, int s) {
   q.vflags = PGD_V_ALIVE | PGD_V_ON_LANE | (s == 0 ? PGD_V_ACTIVE : 0);
 }
 
-V3_HD void veh_load(Veh& q, const State& S, size_t gi) {
-  const F4 p = S.pose[gi], c = S.ctrl[gi], l = S.pidl[gi];
-  const I4 n = S.nav[gi], m = S.misc[gi];
+V3_HD void veh_unpack(Veh& q, const F4& p, const F4& c, const F4& l, const I4& n, const I4& m) {
   q.x = p.x; q.y = p.y; q.h = p.z; q.v = p.w;
   q.steer = c.x; q.throttle = c.y; q.hp = c.z; q.hi = c.w;
   q.lp = l.x; q.li = l.y; q.tspeed = l.z; q.yaw = l.w;
   q.lane = n.x; q.ck0 = n.y & 0xffff; q.ck1 = n.y >> 16; q.rt_lane = n.z; q.timer = n.w;
   q.rnd_n = m.x; q.airborne = m.y; q.vflags = m.z;
+}
+
+V3_HD void veh_load(Veh& q, const State& S, size_t gi) {
+  const F4 p = S.pose[gi], c = S.ctrl[gi], l = S.pidl[gi];
+  const I4 n = S.nav[gi], m = S.misc[gi];
+  veh_unpack(q, p, c, l, n, m);
 }
 
 V3_HD void veh_store(const Veh& q, const State& S, size_t gi) {
@@ -348,9 +382,15 @@ V3_HD void veh_store(const Veh& q, const State& S, size_t gi) {
   S.pose[gi] = p; S.ctrl[gi] = c; S.pidl[gi] = l; S.nav[gi] = n; S.misc[gi] = m;
 }
 
+template <int V, int R>
+V3_HD IdmPub<V>& idm_of(float* obs) { return *reinterpret_cast<IdmPub<V>*>(obs); }
+template <int V, int R>
+V3_HD const IdmPub<V>& idm_of(const float* obs) { return *reinterpret_cast<const IdmPub<V>*>(obs); }
+
 // ---- thread set-up ---------------------------------------------------------------------------------------------------
-V3_HD void thread_init(Thr& th, const Tables& T, const State& S, const PgdConfig& cfg, int mode, int lane, int role,
-                       int env, int env_end) {
+template <int V, int R>
+V3_HD void thread_init(Thr<V, R>& th, const Tables& T, const State& S, const PgdConfig& cfg, int mode, int lane,
+                       int role, int env, int env_end) {
   th.lane = lane; th.role = role; th.env = env; th.num_envs = cfg.num_envs;
   th.valid = env < env_end;
   th.fresh = th.stepping = false;
@@ -358,7 +398,22 @@ V3_HD void thread_init(Thr& th, const Tables& T, const State& S, const PgdConfig
   th.flags = 0;
   if (!th.valid) return;
   th.envi = S.envi[env];
-  th.envf = S.envf[env];
+  // everything below that only needs the environment index is requested now, so that it is in flight while the
+  // episode -> map -> template look-ups (dependent loads) run
+  th.pre_nav = S.nav[env];  // slot 0
+  if (role == 0) {
+    th.envf = S.envf[env];
+    th.pre_pose = S.pose[env]; th.pre_ctrl = S.ctrl[env]; th.pre_pidl = S.pidl[env]; th.pre_misc = S.misc[env];
+  } else {
+#pragma unroll
+    for (int k = 0; k < Thr<V, R>::MAXOWN; ++k) {
+      const int s = role + k * (R - 1);
+      I4 m = {0, 0, 0, 0};
+      if (s < V) m = S.misc[(size_t)s * cfg.num_envs + env];
+      th.pre_fl[k] = m.z;
+      th.pre_air[k] = m.y;
+    }
+  }
   const bool pending = th.envi.z == V3_DONE_PENDING_RESET;
   if (mode == 1) {
     th.fresh = pending;
@@ -382,32 +437,33 @@ V3_HD void thread_init(Thr& th, const Tables& T, const State& S, const PgdConfig
 }
 
 // ---- phase A: publish start-of-step state; ego action; traffic trigger ------------------------------------------
-template <int V, int OBS_CAP>
-V3_HD void phase_a(Smem<V, OBS_CAP>& sm, Thr& th, const State& S, const PgdConfig& cfg, int n_roles,
-                   const float* actions) {
+template <int V, int R>
+V3_HD void phase_a(Smem<V, R>& sm, Thr<V, R>& th, const State& S, const PgdConfig& cfg, const float* actions) {
   const int ln = th.lane;
   if (th.role == 0) sm.wrote[ln] = th.valid ? 1 : 0;
-  sm.awake[th.role][ln] = 0;
+  sm.amask[th.role][ln] = 0;
+  sm.pmask[th.role][ln] = 0;
   sm.crash[th.role][ln] = 0;
   if (!th.valid) return;
   Pub<V>& P = sm.p;
   // TrafficManager.before_step (traffic_manager.py:71-89): the next group wakes when the ego is on its trigger road.
   // Every role evaluates the (cheap) test itself instead of waiting for role 0.
   if (th.stepping && th.envi.y < th.n_groups) {
-    const int ego_lane = S.nav[th.env].x;  // slot 0
-    if (ldg(&th.lanes[ego_lane].road) == ldg(&th.ep->trigger_road[th.envi.y])) th.trig = th.envi.y;
+    if (ldg(&th.lanes[th.pre_nav.x].road) == ldg(&th.ep->trigger_road[th.envi.y])) th.trig = th.envi.y;
   }
   if (th.role == 0) {
     Veh& q = th.ego;
     const PgdSlot& t = th.tpl[0];
     if (th.fresh) veh_from_template(q, t, 0);
-    else veh_load(q, S, (size_t)th.env);
+    else veh_unpack(q, th.pre_pose, th.pre_ctrl, th.pre_pidl, th.pre_nav, th.pre_misc);
     q.hl = t.length * 0.5f;
     q.hw = t.width * 0.5f;
     V3_SINCOS(q.h, q.hs, q.hc);
     sm.last_x[ln] = q.x; sm.last_y[ln] = q.y;
+    sm.ego_hl[ln] = q.hl; sm.ego_hw[ln] = q.hw;
+    sm.ego_ck[ln] = q.ck0 | (q.ck1 << 16);
     P.x[0][ln] = q.x; P.y[0][ln] = q.y; P.hc[0][ln] = q.hc; P.hs[0][ln] = q.hs; P.v[0][ln] = q.v;
-    P.hl[0][ln] = q.hl; P.hw[0][ln] = q.hw; P.lane[0][ln] = q.lane; P.fl[0][ln] = q.vflags;
+    P.lf[0][ln] = lf_pack(q.lane, q.vflags);
     if (th.stepping) {  // EnvInputPolicy.act (env_input_policy.py:17-26): clip; fminf / fmaxf turn NaN into -1
       th.envf.x = q.steer;  // last_current_action[0] after the push (base_vehicle.py:248)
       th.envf.y = q.throttle;
@@ -417,9 +473,11 @@ V3_HD void phase_a(Smem<V, OBS_CAP>& sm, Thr& th, const State& S, const PgdConfi
     }
     return;
   }
-  int any_awake = 0;
-#pragma unroll 1
-  for (int s = owner_first(th.role, n_roles); s < V; s += owner_stride(n_roles)) {
+  uint32_t amask = 0, pmask = 0;
+#pragma unroll
+  for (int k = 0; k < Thr<V, R>::MAXOWN; ++k) {
+    const int s = th.role + k * (R - 1);
+    if (s >= V) break;
     const size_t gi = (size_t)s * th.num_envs + th.env;
     if (s >= th.n_slots) {
       if (th.fresh) {  // unused slots of a freshly started episode: clear the flags once
@@ -437,9 +495,9 @@ V3_HD void phase_a(Smem<V, OBS_CAP>& sm, Thr& th, const State& S, const PgdConfi
       veh_store(q, S, gi);
       x = q.x; y = q.y; h = q.h; lane = q.lane; fl = q.vflags;
     } else {
-      fl = S.misc[gi].z;
+      fl = th.pre_fl[k];
       if (!(fl & PGD_V_ALIVE)) {
-        P.fl[s][ln] = 0;
+        P.lf[s][ln] = 0;
         continue;
       }
       if (fl & PGD_V_ACTIVE) {
@@ -456,33 +514,43 @@ V3_HD void phase_a(Smem<V, OBS_CAP>& sm, Thr& th, const State& S, const PgdConfi
     float sn, cs;
     V3_SINCOS(h, sn, cs);
     P.x[s][ln] = x; P.y[s][ln] = y; P.hc[s][ln] = cs; P.hs[s][ln] = sn; P.v[s][ln] = v;
-    P.hl[s][ln] = t.length * 0.5f; P.hw[s][ln] = t.width * 0.5f; P.lane[s][ln] = lane; P.fl[s][ln] = fl;
-    if ((fl & (PGD_V_ALIVE | PGD_V_ACTIVE)) == (PGD_V_ALIVE | PGD_V_ACTIVE)) any_awake = 1;
+    P.lf[s][ln] = lf_pack(lane, fl);
+    if (fl & PGD_V_ACTIVE) amask |= 1u << s;
+    else pmask |= 1u << s;
   }
-  sm.awake[th.role][ln] = any_awake;
+  sm.amask[th.role][ln] = (int)amask;
+  sm.pmask[th.role][ln] = (int)pmask;
 }
 
-template <int V, int OBS_CAP>
-V3_HD bool env_awake(const Smem<V, OBS_CAP>& sm, int ln, int n_roles) {
-  int a = 0;
-  for (int r = 1; r < n_roles; ++r) a |= sm.awake[r][ln];
-  return a != 0;
+template <int V, int R>
+V3_HD uint32_t env_amask(const Smem<V, R>& sm, int ln) {  // alive + awake traffic slots of the environment
+  uint32_t a = 0;
+#pragma unroll
+  for (int r = 1; r < R; ++r) a |= (uint32_t)sm.amask[r][ln];
+  return a;
+}
+template <int V, int R>
+V3_HD uint32_t env_pmask(const Smem<V, R>& sm, int ln) {  // alive + parked traffic slots
+  uint32_t a = 0;
+#pragma unroll
+  for (int r = 1; r < R; ++r) a |= (uint32_t)sm.pmask[r][ln];
+  return a;
 }
 
 // ---- phase B: IDM look-up data (only environments with awake traffic) --------------------------------------------
-template <int V, int OBS_CAP>
-V3_HD void phase_b(Smem<V, OBS_CAP>& sm, Thr& th, int n_roles) {
+template <int V, int R>
+V3_HD void phase_b(Smem<V, R>& sm, Thr<V, R>& th, float* obs) {
   if (!th.valid || !th.stepping) return;
   const int ln = th.lane;
-  if (!env_awake(sm, ln, n_roles)) return;
+  if (!env_amask(sm, ln)) return;
   const Pub<V>& P = sm.p;
-  IdmPub<V>& I = sm.u.idm;
-  const int s0 = th.role == 0 ? 0 : owner_first(th.role, n_roles);
-  const int ds = th.role == 0 ? V : owner_stride(n_roles);
+  IdmPub<V>& I = idm_of<V, R>(obs);
+  // every alive vehicle (the ego and parked traffic included: they are obstacles), spread evenly over all roles
+  const uint32_t alive = env_amask(sm, ln) | env_pmask(sm, ln) | 1u;
 #pragma unroll 1
-  for (int s = s0; s < th.n_slots; s += ds) {
-    if (!(P.fl[s][ln] & PGD_V_ALIVE)) continue;
-    const PgdLane l = load_rec(th.lanes + P.lane[s][ln]);
+  for (uint32_t m = drop_low(alive, th.role); m; m = drop_low(m, R)) {
+    const int s = ctz32(m);
+    const PgdLane l = load_rec(th.lanes + lf_lane(P.lf[s][ln]));
     I.lsx[s][ln] = l.sx; I.lsy[s][ln] = l.sy; I.lex[s][ln] = l.ex; I.ley[s][ln] = l.ey; I.llen[s][ln] = l.length;
     float lon, lat;
     lane_local(l, P.x[s][ln], P.y[s][ln], lon, lat);
@@ -491,15 +559,15 @@ V3_HD void phase_b(Smem<V, OBS_CAP>& sm, Thr& th, int n_roles) {
 }
 
 // ---- IDM / PID action of one awake traffic vehicle (idm_policy.py:190-353) --------------------------------------
-template <int V, int OBS_CAP>
-V3_HD void idm_act(const Smem<V, OBS_CAP>& sm, const Thr& th, const Tables& T, Veh& q, int s) {
+template <int V, int R>
+V3_HD void idm_act(const Smem<V, R>& sm, const Thr<V, R>& th, const Tables& T, const float* obs, uint32_t alive,
+                   Veh& q, int s) {
   const int ln = th.lane;
   const Pub<V>& P = sm.p;
-  const IdmPub<V>& I = sm.u.idm;
+  const IdmPub<V>& I = idm_of<V, R>(obs);
   const PgdSlot& t = th.tpl[s];
   const PgdLane* lanes = th.lanes;
   const PgdRoad* roads = th.roads;
-  const int n_slots = th.n_slots;
   const int32_t* rroads = T.route_roads + t.route_off;
   const int cur_road_id = ldg(&rroads[q.ck0]);
   const PgdRoad cur_road = load_rec(roads + cur_road_id);
@@ -536,6 +604,7 @@ V3_HD void idm_act(const Smem<V, OBS_CAP>& sm, const Thr& th, const Tables& T, V
   }
   int front[3], back[3];
   float fdist[3], bdist[3];
+  const uint32_t others = alive & ~(1u << s);
 #pragma unroll
   for (int i = 0; i < 3; ++i) {  // FrontBackObjects.get_find_front_back_objs (:83-133)
     front[i] = back[i] = -1;
@@ -547,11 +616,11 @@ V3_HD void idm_act(const Smem<V, OBS_CAP>& sm, const Thr& th, const Tables& T, V
     const float left_long = l.length - cur_long;
     bool found_front = false, found_back = false;
 #pragma unroll 1
-    for (int j = 0; j < n_slots; ++j) {
-      if (j == s || !(P.fl[j][ln] & PGD_V_ALIVE)) continue;
+    for (uint32_t m = others; m; m &= m - 1) {  // ascending slot order, like the oracle's object list
+      const int j = ctz32(m);
       const float ddx = P.x[j][ln] - q.x, ddy = P.y[j][ln] - q.y;
       if (!(ddx * ddx + ddy * ddy < V3_LIDAR_RANGE * V3_LIDAR_RANGE)) continue;
-      if (P.lane[j][ln] == cand[i]) {
+      if (lf_lane(P.lf[j][ln]) == cand[i]) {
         const float lg = I.olong[j][ln] - cur_long;
         if (fdist[i] > lg && lg > 0.0f) { fdist[i] = lg; front[i] = j; found_front = true; }
         if (lg < 0.0f && fabsf(lg) < bdist[i]) { bdist[i] = fabsf(lg); back[i] = j; found_back = true; }
@@ -658,189 +727,251 @@ V3_HD void idm_act(const Smem<V, OBS_CAP>& sm, const Thr& th, const Tables& T, V
 }
 
 // ---- phase C: ego sub-steps (role 0)  |  IDM of the awake traffic (traffic roles) ----------------------------------
-template <int V, int OBS_CAP>
-V3_HD void phase_c(Smem<V, OBS_CAP>& sm, Thr& th, const Tables& T, const State& S, const PgdConfig& cfg, int n_roles) {
-  if (!th.valid || !th.stepping) return;
+/* Awake vehicles are dealt to the traffic roles by their RANK among the environment's awake vehicles (role r takes
+ * the (r-1)-th, (r-1+R-1)-th ... set bit of the mask), not by slot number: every traffic thread of an environment
+ * gets the same share, so a warp's lanes run the same number of iterations. */
+template <int V, int R>
+V3_HD void phase_c(Smem<V, R>& sm, Thr<V, R>& th, const Tables& T, const State& S, const PgdConfig& cfg,
+                   const float* obs, TrajPtr traj) {
+  if (!th.valid) return;
   const int ln = th.lane;
   const int ns = cfg.decision_repeat < V3_MAX_SUBSTEPS ? cfg.decision_repeat : V3_MAX_SUBSTEPS;
-  if (th.role == 0) {  // 5 x doPhysics(0.02) of the ego (base_engine.py:206-232), remembering every pose
+  if (th.role == 0) {
     Veh& q = th.ego;
-    // A vehicle at rest with no yaw rate and no engine force is a fixed point of the sub-step (speed = max(0 - dv, 0)
-    // = 0, the pose does not move); only its drop counter runs.
-    const bool parked = q.v == 0.0f && q.yaw == 0.0f && !(q.throttle > 0.0f);
-    Sub sub;
-    if (!parked) sub = make_sub(q, th.tpl[0], cfg.dt);
-    float m2 = 0.0f;
+    if (th.stepping) {  // 5 x doPhysics(0.02) of the ego (base_engine.py:206-232), remembering every pose
+      // A vehicle at rest with no yaw rate and no engine force is a fixed point of the sub-step (speed = max(0 - dv, 0)
+      // = 0, the pose does not move); only its drop counter runs.
+      const bool parked = q.v == 0.0f && q.yaw == 0.0f && !(q.throttle > 0.0f);
+      Sub sub;
+      if (!parked) sub = make_sub(q, th.tpl[0], cfg.dt);
+      float m2 = 0.0f;
 #pragma unroll 1
-    for (int k = 0; k < ns; ++k) {
-      if (q.airborne > 0) q.airborne--;  // placed 1 m above the road: no wheel contact while it drops
-      else if (!parked) substep(q, sub, cfg.dt);
-      const F4 p = {q.x, q.y, q.hc, q.hs};
-      sm.traj[k][ln] = p;
-      const float ex = q.x - sm.last_x[ln], ey = q.y - sm.last_y[ln];
-      m2 = fmaxf(m2, ex * ex + ey * ey);
+      for (int k = 0; k < ns; ++k) {
+        if (q.airborne > 0) q.airborne--;  // placed 1 m above the road: no wheel contact while it drops
+        else if (!parked) substep(q, sub, cfg.dt);
+        const F4 p = {q.x, q.y, q.hc, q.hs};
+        traj[k][ln] = p;
+        const float ex = q.x - sm.last_x[ln], ey = q.y - sm.last_y[ln];
+        m2 = fmaxf(m2, ex * ex + ey * ey);
+      }
+      sm.ego_travel[ln] = sqrtf(m2) * 1.001f + 1e-3f;  // how far the ego gets from its start pose within the step
     }
-    sm.ego_travel[ln] = sqrtf(m2) * 1.001f + 1e-3f;  // how far the ego gets from its start pose within the step
+    const F4 fin = {q.x, q.y, q.hc, q.hs};
+    sm.efin[ln] = fin;
+    sm.ego_h[ln] = q.h;
+    sm.ego_v[ln] = q.v;
     return;
   }
-  if (!sm.awake[th.role][ln]) return;
+  if (!th.stepping) return;
+  const uint32_t amask = env_amask(sm, ln);
+  if (!amask) return;
   const Pub<V>& P = sm.p;
+  const uint32_t alive = amask | env_pmask(sm, ln) | 1u;
 #pragma unroll 1
-  for (int s = owner_first(th.role, n_roles); s < th.n_slots; s += owner_stride(n_roles)) {
-    const int fl = P.fl[s][ln];
-    if ((fl & (PGD_V_ALIVE | PGD_V_ACTIVE)) != (PGD_V_ALIVE | PGD_V_ACTIVE)) continue;
+  for (uint32_t m = drop_low(amask, th.role - 1); m; m = drop_low(m, R - 1)) {
+    const int s = ctz32(m);
     const size_t gi = (size_t)s * th.num_envs + th.env;
     Veh q;
     veh_load(q, S, gi);
-    q.vflags = fl;  // a vehicle woken in this step carries ACTIVE only in shared memory so far
+    q.vflags = P.lf[s][ln] & 0xff;  // a vehicle woken in this step carries ACTIVE only in shared memory so far
     q.hc = P.hc[s][ln]; q.hs = P.hs[s][ln];
-    idm_act(sm, th, T, q, s);
-    // hand-over to phase D through the vehicle's own state record (same thread)
+    idm_act(sm, th, T, obs, alive, q, s);
+    // hand-over to phase D through the vehicle's own state record (the same thread picks it up)
     const F4 c = {q.steer, q.throttle, q.hp, q.hi}, l = {q.lp, q.li, q.tspeed, q.yaw};
-    const I4 n = {q.lane, q.ck0 | (q.ck1 << 16), q.rt_lane, q.timer}, m = {q.rnd_n, q.airborne, q.vflags, 0};
-    S.ctrl[gi] = c; S.pidl[gi] = l; S.nav[gi] = n; S.misc[gi] = m;
+    const I4 n = {q.lane, q.ck0 | (q.ck1 << 16), q.rt_lane, q.timer}, mm = {q.rnd_n, q.airborne, q.vflags, 0};
+    S.ctrl[gi] = c; S.pidl[gi] = l; S.nav[gi] = n; S.misc[gi] = mm;
   }
 }
 
-// ---- localisation of one vehicle through the bucket grid (navigation.py:155-344, scene_utils.py:138-185); for the ego
-// the same scan also tests the chassis against line ghosts and sidewalks (base_vehicle.py:615-644) ----------------------
+// ---- localisation through the bucket grid (navigation.py:155-344, scene_utils.py:138-185) ------------------------
+struct ScanOut { int b_any, b_cur, b_next; uint32_t flags; };
+
+/* Entries [first, ...) of the bucket of (x, y), `stride` groups of 4 apart: lane-surface boxes that contain the point
+ * and run along the heading; with EGO also the chassis against line ghosts and sidewalks (base_vehicle.py:615-644). */
 template <bool EGO>
-V3_HD void localise(const Thr& th, const Tables& T, Veh& q, int s, uint32_t& flags) {
-  const PgdMap& mp = th.mp;
-  const PgdSlot& t = th.tpl[s];
-  const int32_t* rroads = T.route_roads + t.route_off;
-  const int32_t* rnodes = T.route_nodes + t.route_off;
+V3_HD void bucket_scan(const PgdMap& mp, const PgdLane* lanes, const PgdBox* boxes, const Tables& T, float x, float y,
+                       float hc, float hs, float hl, float hw, int cur_road, int next_road, int first, int stride,
+                       ScanOut& out) {
+  out.b_any = out.b_cur = out.b_next = INT_MAX;
+  out.flags = 0;
   const int32_t* ent = T.cell_entries + mp.entry_off;
-  const int cur_road = ldg(&rroads[q.ck0]);
-  const int next_road = q.ck0 != q.ck1 ? ldg(&rroads[q.ck1]) : -1;
-  const Rect er = {q.x, q.y, q.hc, q.hs, q.hl, q.hw};
-  int b_any = INT_MAX, b_cur = INT_MAX, b_next = INT_MAX;
-  const int cx = (int)floorf((q.x - mp.x0) * mp.inv_cell), cy = (int)floorf((q.y - mp.y0) * mp.inv_cell);
-  if (cx >= 0 && cy >= 0 && cx < mp.nx && cy < mp.ny) {
-    const int cell = mp.cell_off + cy * mp.nx + cx;
-    const int b0 = ldg(&T.cell_start[cell]), b1 = ldg(&T.cell_start[cell + 1]);
-    // entries are fetched four at a time (indices, then records) so that their latencies overlap
-    for (int k0 = b0; k0 < b1; k0 += 4) {
-      int bb[4];
-      PgdBox gg[4];
+  const Rect er = {x, y, hc, hs, hl, hw};
+  const int cx = (int)floorf((x - mp.x0) * mp.inv_cell), cy = (int)floorf((y - mp.y0) * mp.inv_cell);
+  if (!(cx >= 0 && cy >= 0 && cx < mp.nx && cy < mp.ny)) return;
+  const int cell = mp.cell_off + cy * mp.nx + cx;
+  const int b0 = ldg(&T.cell_start[cell]), b1 = ldg(&T.cell_start[cell + 1]);
+  // entries are fetched four at a time (indices, then records) so that their latencies overlap
+  for (int k0 = b0 + 4 * first; k0 < b1; k0 += 4 * stride) {
+    int bb[4];
+    PgdBox gg[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) bb[j] = (k0 + j < b1) ? ldg(&ent[k0 + j]) : -1;
+    for (int j = 0; j < 4; ++j) bb[j] = (k0 + j < b1) ? ldg(&ent[k0 + j]) : -1;
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (bb[j] >= 0) gg[j] = load_rec(th.boxes + bb[j]);
+    for (int j = 0; j < 4; ++j)
+      if (bb[j] >= 0) gg[j] = load_rec(boxes + bb[j]);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (bb[j] < 0) continue;
-        const int b = bb[j];
-        const PgdBox& g = gg[j];
-        if (g.kind == PGD_BOX_LANE) {
-          const float dx = q.x - g.cx, dy = q.y - g.cy;
-          if (!(fabsf(dx * g.ux + dy * g.uy) <= g.hl && fabsf(-dx * g.uy + dy * g.ux) <= g.hw)) continue;
-          const PgdLane* l = th.lanes + g.lane;
-          float dot;  // lane direction . heading > 0, written without trigonometry
-          if (ldg(&l->kind) == PGD_LANE_STRAIGHT) {
-            dot = ldg(&l->ax) * q.hc + ldg(&l->ay) * q.hs;
-          } else {
-            dot = ldg(&l->dir) * ((q.x - ldg(&l->ax)) * q.hs - (q.y - ldg(&l->ay)) * q.hc);
-          }
-          if (!(dot > 0.0f)) continue;
-          const int lroad = ldg(&l->road);
-          if (b < b_any) b_any = b;
-          if (lroad == cur_road && b < b_cur) b_cur = b;
-          if (lroad == next_road && b < b_next) b_next = b;
-        } else if (EGO) {
-          const Rect r = {g.cx, g.cy, g.ux, g.uy, g.hl, g.hw};
-          if (!rect_overlap(er, r)) continue;
-          flags |= g.kind == PGD_BOX_WHITE ? PGD_F_ON_WHITE
-                 : g.kind == PGD_BOX_YELLOW ? PGD_F_ON_YELLOW
-                 : g.kind == PGD_BOX_BROKEN ? PGD_F_ON_BROKEN : PGD_F_CRASH_SIDEWALK;
+    for (int j = 0; j < 4; ++j) {
+      if (bb[j] < 0) continue;
+      const int b = bb[j];
+      const PgdBox& g = gg[j];
+      if (g.kind == PGD_BOX_LANE) {
+        const float dx = x - g.cx, dy = y - g.cy;
+        if (!(fabsf(dx * g.ux + dy * g.uy) <= g.hl && fabsf(-dx * g.uy + dy * g.ux) <= g.hw)) continue;
+        const PgdLane* l = lanes + g.lane;
+        float dot;  // lane direction . heading > 0, written without trigonometry
+        if (ldg(&l->kind) == PGD_LANE_STRAIGHT) {
+          dot = ldg(&l->ax) * hc + ldg(&l->ay) * hs;
+        } else {
+          dot = ldg(&l->dir) * ((x - ldg(&l->ax)) * hs - (y - ldg(&l->ay)) * hc);
         }
+        if (!(dot > 0.0f)) continue;
+        const int lroad = ldg(&l->road);
+        if (b < out.b_any) out.b_any = b;
+        if (lroad == cur_road && b < out.b_cur) out.b_cur = b;
+        if (lroad == next_road && b < out.b_next) out.b_next = b;
+      } else if (EGO) {
+        const Rect r = {g.cx, g.cy, g.ux, g.uy, g.hl, g.hw};
+        if (!rect_overlap(er, r)) continue;
+        out.flags |= g.kind == PGD_BOX_WHITE ? PGD_F_ON_WHITE
+                   : g.kind == PGD_BOX_YELLOW ? PGD_F_ON_YELLOW
+                   : g.kind == PGD_BOX_BROKEN ? PGD_F_ON_BROKEN : PGD_F_CRASH_SIDEWALK;
       }
     }
   }
-  const int nb = b_cur != INT_MAX ? b_cur : (b_next != INT_MAX ? b_next : b_any);
-  const bool on_lane = nb != INT_MAX;
-  if (on_lane) q.lane = ldg(&th.boxes[nb].lane);
-  if (q.ck0 != q.ck1) {  // _update_target_checkpoints
-    const PgdLane l = load_rec(th.lanes + q.lane);
+}
+
+/* What follows the scan: lane choice (current road, then next road, then any; lowest box id), checkpoint update
+ * (_update_target_checkpoints), on-lane flag. */
+template <int V, int R>
+V3_HD void after_scan(const Thr<V, R>& th, const Tables& T, const PgdSlot& t, const ScanOut& sc, float x, float y,
+                      int& lane, int& ck0, int& ck1, bool& on_lane) {
+  const int32_t* rnodes = T.route_nodes + t.route_off;
+  const int nb = sc.b_cur != INT_MAX ? sc.b_cur : (sc.b_next != INT_MAX ? sc.b_next : sc.b_any);
+  on_lane = nb != INT_MAX;
+  if (on_lane) lane = ldg(&th.boxes[nb].lane);
+  if (ck0 != ck1) {
+    const PgdLane l = load_rec(th.lanes + lane);
     float lon, lat;
-    lane_local(l, q.x, q.y, lon, lat);
+    lane_local(l, x, y, lon, lat);
     const int start = ldg(&th.roads[l.road].start_node);
     if (lon < 5.0f) {
 #pragma unroll 1
-      for (int j = q.ck1; j < t.route_len - 1; ++j) {
+      for (int j = ck1; j < t.route_len - 1; ++j) {
         if (ldg(&rnodes[j]) == start) {
-          q.ck0 = j;
-          q.ck1 = (j + 1 == t.route_len - 1) ? j : j + 1;
+          ck0 = j;
+          ck1 = (j + 1 == t.route_len - 1) ? j : j + 1;
           break;
         }
       }
     }
   }
-  q.vflags = on_lane ? (q.vflags | PGD_V_ON_LANE) : (q.vflags & ~PGD_V_ON_LANE);
-  if (!EGO && !on_lane) q.vflags &= ~PGD_V_ALIVE;  // traffic_manager.py:91-109
 }
 
-// ---- phase D: traffic sub-steps + chassis contact + after_step  |  ego after_step -------------------------------
-template <int V, int OBS_CAP>
-V3_HD void phase_d(Smem<V, OBS_CAP>& sm, Thr& th, const Tables& T, const State& S, const PgdConfig& cfg, int n_roles) {
+template <int V, int R>
+V3_HD void localise_traffic(const Thr<V, R>& th, const Tables& T, Veh& q, int s) {
+  const PgdSlot& t = th.tpl[s];
+  const int32_t* rroads = T.route_roads + t.route_off;
+  const int cur_road = ldg(&rroads[q.ck0]);
+  const int next_road = q.ck0 != q.ck1 ? ldg(&rroads[q.ck1]) : -1;
+  ScanOut sc;
+  bucket_scan<false>(th.mp, th.lanes, th.boxes, T, q.x, q.y, q.hc, q.hs, q.hl, q.hw, cur_road, next_road, 0, 1, sc);
+  bool on_lane;
+  after_scan(th, T, t, sc, q.x, q.y, q.lane, q.ck0, q.ck1, on_lane);
+  q.vflags = on_lane ? (q.vflags | PGD_V_ON_LANE) : (q.vflags & ~(PGD_V_ON_LANE | PGD_V_ALIVE));  // traffic_manager.py:91-109
+}
+
+/* The ego's share of phase F that every reader of its lane / checkpoints needs: combine the roles' scan shares. */
+template <int V, int R>
+V3_HD void ego_after_scan(const Smem<V, R>& sm, const Thr<V, R>& th, const Tables& T, int& lane, int& ck0, int& ck1,
+                          bool& on_lane, uint32_t& flags) {
+  const int ln = th.lane;
+  ScanOut sc = {INT_MAX, INT_MAX, INT_MAX, 0u};
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    sc.b_any = imin(sc.b_any, sm.scan[r][0][ln]);
+    sc.b_cur = imin(sc.b_cur, sm.scan[r][1][ln]);
+    sc.b_next = imin(sc.b_next, sm.scan[r][2][ln]);
+    sc.flags |= (uint32_t)sm.scan[r][3][ln];
+  }
+  flags = sc.flags;
+  lane = lf_lane(sm.p.lf[0][ln]);  // the start-of-step lane stays when no lane box is under the vehicle
+  ck0 = sm.ego_ck[ln] & 0xffff;
+  ck1 = sm.ego_ck[ln] >> 16;
+  const F4 e = sm.efin[ln];
+  after_scan(th, T, th.tpl[0], sc, e.x, e.y, lane, ck0, ck1, on_lane);
+}
+
+// ---- phase D: every role: its share of the ego's bucket scan;  traffic roles: sub-steps, chassis contact against
+// the ego's trajectory, after_step of their vehicles -----------------------------------------------------------------
+template <int V, int R>
+V3_HD void phase_d(Smem<V, R>& sm, Thr<V, R>& th, const Tables& T, const State& S, const PgdConfig& cfg,
+                   TrajPtr traj) {
   if (!th.valid) return;
   const int ln = th.lane;
   Pub<V>& P = sm.p;
-  if (th.role == 0) {
-    Veh& q = th.ego;
-    localise<true>(th, T, q, 0, th.flags);
-    P.x[0][ln] = q.x; P.y[0][ln] = q.y; P.hc[0][ln] = q.hc; P.hs[0][ln] = q.hs; P.v[0][ln] = q.v;
-    P.lane[0][ln] = q.lane; P.fl[0][ln] = q.vflags;
-    sm.ego_h[ln] = q.h;
-    sm.ego_ck[ln] = q.ck0 | (q.ck1 << 16);
-    return;
+  const float ehl = sm.ego_hl[ln], ehw = sm.ego_hw[ln];
+  {  // ego after_step, first half (navigation.py:155-211, base_vehicle.py:615-644), spread over the roles
+    const F4 e = sm.efin[ln];
+    const int ck0 = sm.ego_ck[ln] & 0xffff, ck1 = sm.ego_ck[ln] >> 16;
+    const int32_t* rroads = T.route_roads + th.tpl[0].route_off;
+    const int cur_road = ldg(&rroads[ck0]);
+    const int next_road = ck0 != ck1 ? ldg(&rroads[ck1]) : -1;
+    ScanOut sc;
+    bucket_scan<true>(th.mp, th.lanes, th.boxes, T, e.x, e.y, e.z, e.w, ehl, ehw, cur_road, next_road, th.role, R, sc);
+    sm.scan[th.role][0][ln] = sc.b_any; sm.scan[th.role][1][ln] = sc.b_cur; sm.scan[th.role][2][ln] = sc.b_next;
+    sm.scan[th.role][3][ln] = (int)sc.flags;
   }
-  if (!th.stepping) return;
+  if (th.role == 0 || !th.stepping) return;
   const int ns = cfg.decision_repeat < V3_MAX_SUBSTEPS ? cfg.decision_repeat : V3_MAX_SUBSTEPS;
-  const float ehl = P.hl[0][ln], ehw = P.hw[0][ln];
   int crash = 0;
-#pragma unroll 1
-  for (int s = owner_first(th.role, n_roles); s < th.n_slots; s += owner_stride(n_roles)) {
-    const int fl = P.fl[s][ln];
-    if (!(fl & PGD_V_ALIVE)) continue;
+  const uint32_t amask = env_amask(sm, ln), pmask = env_pmask(sm, ln);
+  // parked traffic (the slots this role published in phase A, whose drop counters it already holds): only the drop
+  // counter runs and the (fixed) chassis is tested against the ego's pose of every sub-step
+#pragma unroll
+  for (int k = 0; k < Thr<V, R>::MAXOWN; ++k) {
+    const int s = th.role + k * (R - 1);
+    if (s >= th.n_slots) break;
+    if (!((pmask >> s) & 1u)) continue;
     const size_t gi = (size_t)s * th.num_envs + th.env;
-    const float hl = P.hl[s][ln], hw = P.hw[s][ln];
-    const float reach = ehl + ehw + hl + hw;
-    if (!(fl & PGD_V_ACTIVE)) {
-      // parked: only its drop counter runs and its (fixed) chassis is tested against the ego's pose of every sub-step
-      const I4 m = S.misc[gi];
-      if (m.y > 0) {
-        const I4 m2 = {m.x, m.y > ns ? m.y - ns : 0, m.z, 0};
-        S.misc[gi] = m2;
-      }
-      const float px = P.x[s][ln], py = P.y[s][ln];
-      const float ddx0 = px - sm.last_x[ln], ddy0 = py - sm.last_y[ln];
-      const float far = reach + sm.ego_travel[ln];
-      if (ddx0 * ddx0 + ddy0 * ddy0 > far * far) continue;  // triangle inequality; the margin covers rounding
-#pragma unroll 1
-      for (int k = 0; k < ns; ++k) {
-        const F4 e = sm.traj[k][ln];
-        const float ddx = px - e.x, ddy = py - e.y;
-        if (ddx * ddx + ddy * ddy <= reach * reach) {
-          const Rect me = {px, py, P.hc[s][ln], P.hs[s][ln], hl, hw};
-          const Rect eg = {e.x, e.y, e.z, e.w, ehl, ehw};
-          if (rect_overlap(eg, me)) crash = 1;
-        }
-      }
-      continue;
+    const PgdSlot& t = th.tpl[s];
+    if (th.pre_air[k] > 0) {
+      const I4 m2 = {0, th.pre_air[k] > ns ? th.pre_air[k] - ns : 0, th.pre_fl[k], 0};  // parked: no IDM draw yet
+      S.misc[gi] = m2;
     }
+    const float px = P.x[s][ln], py = P.y[s][ln];
+    const float ddx0 = px - sm.last_x[ln], ddy0 = py - sm.last_y[ln];
+    const float far = ehl + ehw + 8.0f + sm.ego_travel[ln];  // no chassis has an 8 m half-diagonal
+    if (ddx0 * ddx0 + ddy0 * ddy0 > far * far) continue;  // triangle inequality; the margin covers rounding
+    const float hl = t.length * 0.5f, hw = t.width * 0.5f;
+    const float reach = ehl + ehw + hl + hw;
+#pragma unroll 1
+    for (int kk = 0; kk < ns; ++kk) {
+      const F4 e = traj[kk][ln];
+      const float ddx = px - e.x, ddy = py - e.y;
+      if (ddx * ddx + ddy * ddy <= reach * reach) {
+        const Rect me = {px, py, P.hc[s][ln], P.hs[s][ln], hl, hw};
+        const Rect eg = {e.x, e.y, e.z, e.w, ehl, ehw};
+        if (rect_overlap(eg, me)) crash = 1;
+      }
+    }
+  }
+#pragma unroll 1
+  for (uint32_t m = drop_low(amask, th.role - 1); m; m = drop_low(m, R - 1)) {
+    const int s = ctz32(m);
+    const size_t gi = (size_t)s * th.num_envs + th.env;
+    const PgdSlot& t = th.tpl[s];
     Veh q;
     veh_load(q, S, gi);
-    q.hc = P.hc[s][ln]; q.hs = P.hs[s][ln]; q.hl = hl; q.hw = hw;
+    q.hc = P.hc[s][ln]; q.hs = P.hs[s][ln]; q.hl = t.length * 0.5f; q.hw = t.width * 0.5f;
+    const float reach = ehl + ehw + q.hl + q.hw;
     const bool at_rest = q.v == 0.0f && q.yaw == 0.0f && !(q.throttle > 0.0f);
     Sub sub;
-    if (!at_rest) sub = make_sub(q, th.tpl[s], cfg.dt);
+    if (!at_rest) sub = make_sub(q, t, cfg.dt);
 #pragma unroll 1
     for (int k = 0; k < ns; ++k) {
       if (q.airborne > 0) q.airborne--;
       else if (!at_rest) substep(q, sub, cfg.dt);
-      const F4 e = sm.traj[k][ln];
+      const F4 e = traj[k][ln];
       const float ddx = q.x - e.x, ddy = q.y - e.y;
       if (ddx * ddx + ddy * ddy <= reach * reach) {
         const Rect me = {q.x, q.y, q.hc, q.hs, q.hl, q.hw};
@@ -848,11 +979,10 @@ V3_HD void phase_d(Smem<V, OBS_CAP>& sm, Thr& th, const Tables& T, const State& 
         if (rect_overlap(eg, me)) crash = 1;
       }
     }
-    uint32_t unused = 0;
-    localise<false>(th, T, q, s, unused);
+    localise_traffic(th, T, q, s);
     veh_store(q, S, gi);
     P.x[s][ln] = q.x; P.y[s][ln] = q.y; P.hc[s][ln] = q.hc; P.hs[s][ln] = q.hs; P.v[s][ln] = q.v;
-    P.lane[s][ln] = q.lane; P.fl[s][ln] = q.vflags;
+    P.lf[s][ln] = lf_pack(q.lane, q.vflags);
   }
   sm.crash[th.role][ln] = crash;
 }
@@ -863,15 +993,21 @@ V3_HD int obs_dim_of(const PgdConfig& cfg) {
          PGD_LIDAR_BEAMS;
 }
 
-/* task 0 (role 0): route distances, arrival, reward / cost / done, state observation, info, ego state store */
-template <int V, int OBS_CAP>
-V3_HD void task_reward(Smem<V, OBS_CAP>& sm, Thr& th, const Tables& T, const State& S, const PgdConfig& cfg, int mode,
-                       int n_roles, float* obs, float* reward, uint8_t* done, PgdInfo* info) {
+/* task 0 (role 0): lane + checkpoints, route distances, arrival, reward / cost / done, state observation, info, ego
+ * state store */
+template <int V, int R>
+V3_HD void task_reward(Smem<V, R>& sm, Thr<V, R>& th, const Tables& T, const State& S, const PgdConfig& cfg, int mode,
+                       float* obs, float* reward, uint8_t* done, PgdInfo* info) {
   const int ln = th.lane;
-  const Veh& ego = th.ego;
+  Veh& ego = th.ego;
   const PgdMap& mp = th.mp;
   const PgdSlot& t0 = th.tpl[0];
   const int32_t* rroads = T.route_roads + t0.route_off;
+  const float last_h = th.fresh ? ego.h : th.pre_pose.z;
+  uint32_t flags;
+  bool on_lane;
+  ego_after_scan(sm, th, T, ego.lane, ego.ck0, ego.ck1, on_lane, flags);
+  ego.vflags = on_lane ? (ego.vflags | PGD_V_ON_LANE) : (ego.vflags & ~PGD_V_ON_LANE);
   const int n_first = cfg.n_side > 0 ? cfg.n_side : 2;
   float* const st = obs + n_first - 2;
   const int n_extra = cfg.random_agent_model ? 2 : 0;
@@ -879,9 +1015,9 @@ V3_HD void task_reward(Smem<V, OBS_CAP>& sm, Thr& th, const Tables& T, const Sta
     obs[n_first + 6 + cfg.n_lane_line] = clipf(t0.length / 10.0f, 0.0f, 1.0f);
     obs[n_first + 6 + cfg.n_lane_line + 1] = clipf(t0.width / 2.5f, 0.0f, 1.0f);
   }
-  uint32_t flags = th.flags;
   int crash = 0;
-  for (int r = 1; r < n_roles; ++r) crash |= sm.crash[r][ln];
+#pragma unroll
+  for (int r = 1; r < R; ++r) crash |= sm.crash[r][ln];
   const float last_x = sm.last_x[ln], last_y = sm.last_y[ln];
   const int cur_road_id = ldg(&rroads[ego.ck0]);
   const PgdRoad cur_road = load_rec(th.roads + cur_road_id);
@@ -900,7 +1036,6 @@ V3_HD void task_reward(Smem<V, OBS_CAP>& sm, Thr& th, const Tables& T, const Sta
     lane_local(rl, last_x, last_y, long_last, lat_last);
     lane_local(rl, ego.x, ego.y, long_now, lat_now);
   }
-  const bool on_lane = (ego.vflags & PGD_V_ON_LANE) != 0;
   if (on_lane) flags |= PGD_F_ON_LANE;
   if (crash) flags |= PGD_F_CRASH_VEHICLE;
   const float to_left = qlat0 + mp.lane_width / 2.0f;  // base_vehicle.py:383-388
@@ -927,7 +1062,6 @@ V3_HD void task_reward(Smem<V, OBS_CAP>& sm, Thr& th, const Tables& T, const Sta
   st[6] = clipf((th.envf.y + 1.0f) / 2.0f, 0.0f, 1.0f);
   // yaw rate: arccos(clip(cos(angle between headings), 0, 1)) / 0.1 (state_obs.py:87-94) = min(|wrapped heading
   // change|, pi/2) / 0.1 without the ill-conditioned arccos
-  const float last_h = th.fresh ? ego.h : S.pose[th.env].z;  // the stored heading is still the start-of-step one
   st[7] = clipf(fminf(fabsf(pgd_wrap_to_pi(ego.h - last_h)), V3_PI / 2) / 0.1f, 0.0f, 1.0f);
   float r = 0.0f, step_reward = 0.0f, cost = 0.0f, step_energy = 0.0f;
   int is_done = 0;
@@ -973,13 +1107,16 @@ V3_HD void task_reward(Smem<V, OBS_CAP>& sm, Thr& th, const Tables& T, const Sta
 }
 
 /* task 1: navigation info of the two checkpoints (navigation.py:213-260) + heading_diff (base_vehicle.py:433-458) */
-template <int V, int OBS_CAP>
-V3_HD void task_navi(const Smem<V, OBS_CAP>& sm, const Thr& th, const Tables& T, const PgdConfig& cfg, float* obs) {
+template <int V, int R>
+V3_HD void task_navi(const Smem<V, R>& sm, const Thr<V, R>& th, const Tables& T, const PgdConfig& cfg, float* obs) {
   const int ln = th.lane;
-  const Pub<V>& P = sm.p;
   const PgdMap& mp = th.mp;
-  const float ex = P.x[0][ln], ey = P.y[0][ln], ehc = P.hc[0][ln], ehs = P.hs[0][ln];
-  const int ck0 = sm.ego_ck[ln] & 0xffff, ck1 = sm.ego_ck[ln] >> 16;
+  const F4 e = sm.efin[ln];
+  const float ex = e.x, ey = e.y, ehc = e.z, ehs = e.w;
+  int lane, ck0, ck1;
+  bool on_lane;
+  uint32_t fl_unused;
+  ego_after_scan(sm, th, T, lane, ck0, ck1, on_lane, fl_unused);
   const int32_t* rroads = T.route_roads + th.tpl[0].route_off;
   const int n_first = cfg.n_side > 0 ? cfg.n_side : 2;
   float* const st = obs + n_first - 2;
@@ -1022,32 +1159,39 @@ V3_HD void task_navi(const Smem<V, OBS_CAP>& sm, const Thr& th, const Tables& T,
 }
 
 /* task 2: the 4 nearest vehicles inside the 50 m cylinder (lidar.py:55-77; ties -> lower slot) */
-template <int V, int OBS_CAP>
-V3_HD void task_neighbours(const Smem<V, OBS_CAP>& sm, const Thr& th, const PgdConfig& cfg, float* obs) {
+template <int V, int R>
+V3_HD void task_neighbours(const Smem<V, R>& sm, const Thr<V, R>& th, const PgdConfig& cfg, float* obs) {
   const int ln = th.lane;
   const Pub<V>& P = sm.p;
-  const float ex = P.x[0][ln], ey = P.y[0][ln], ehc = P.hc[0][ln], ehs = P.hs[0][ln];
-  const float esp = kmh(P.v[0][ln]);
+  const F4 e = sm.efin[ln];
+  const float ex = e.x, ey = e.y, ehc = e.z, ehs = e.w;
+  const float esp = kmh(sm.ego_v[ln]);
   const int n_first = cfg.n_side > 0 ? cfg.n_side : 2;
   float* const ob = obs + n_first + cfg.n_lane_line + (cfg.random_agent_model ? 2 : 0) - 2;
-  uint32_t taken = 0;
+  uint32_t cand = 0;  // alive vehicles inside the cylinder
+#pragma unroll 1
+  for (int s = 1; s < th.n_slots; ++s) {
+    if (!(P.lf[s][ln] & PGD_V_ALIVE)) continue;
+    const float dx = P.x[s][ln] - ex, dy = P.y[s][ln] - ey;
+    if (dx * dx + dy * dy < V3_LIDAR_RANGE * V3_LIDAR_RANGE) cand |= 1u << s;
+  }
 #pragma unroll 1
   for (int rank = 0; rank < 4; ++rank) {
     int best = -1;
     float best_d2 = INFINITY;
 #pragma unroll 1
-    for (int s = 1; s < th.n_slots; ++s) {
-      if (!(P.fl[s][ln] & PGD_V_ALIVE) || ((taken >> s) & 1u)) continue;
+    for (uint32_t m = cand; m; m &= m - 1) {
+      const int s = ctz32(m);
       const float dx = P.x[s][ln] - ex, dy = P.y[s][ln] - ey;
       const float d2 = dx * dx + dy * dy;
-      if (d2 < V3_LIDAR_RANGE * V3_LIDAR_RANGE && (best < 0 || d2 < best_d2)) { best = s; best_d2 = d2; }
+      if (best < 0 || d2 < best_d2) { best = s; best_d2 = d2; }
     }
     float* o4 = ob + 18 + 4 * rank;
     if (best < 0) {
       o4[0] = o4[1] = o4[2] = o4[3] = 0.0f;
       continue;
     }
-    taken |= 1u << best;
+    cand &= ~(1u << best);
     float pf, ps, vf, vs;
     project(ehc, ehs, P.x[best][ln] - ex, P.y[best][ln] - ey, pf, ps);
     const float ws = kmh(P.v[best][ln]);
@@ -1060,18 +1204,21 @@ V3_HD void task_neighbours(const Smem<V, OBS_CAP>& sm, const Thr& th, const PgdC
 }
 
 /* task 3: which chassis the lidar can reach, and the (conservative) arc of beams that can hit each */
-template <int V, int OBS_CAP>
-V3_HD void task_lidar_windows(Smem<V, OBS_CAP>& sm, const Thr& th) {
+template <int V, int R>
+V3_HD void task_lidar_windows(Smem<V, R>& sm, const Thr<V, R>& th, VisPtr vis) {
   const int ln = th.lane;
   const Pub<V>& P = sm.p;
-  const float ex = P.x[0][ln], ey = P.y[0][ln], eh = sm.ego_h[ln];
+  const F4 e = sm.efin[ln];
+  const float ex = e.x, ey = e.y, eh = sm.ego_h[ln];
   int n = 0;
 #pragma unroll 1
   for (int s = 1; s < th.n_slots; ++s) {
-    if (!(P.fl[s][ln] & PGD_V_ALIVE)) continue;
+    if (!(P.lf[s][ln] & PGD_V_ALIVE)) continue;
     const float dx = P.x[s][ln] - ex, dy = P.y[s][ln] - ey;
     const float d2 = dx * dx + dy * dy;
-    const float hl = P.hl[s][ln], hw = P.hw[s][ln];
+    if (!(d2 < (V3_LIDAR_RANGE + 8.0f) * (V3_LIDAR_RANGE + 8.0f))) continue;  // no chassis has an 8 m half-diagonal
+    const PgdSlot& t = th.tpl[s];
+    const float hl = t.length * 0.5f, hw = t.width * 0.5f;
     const float hd = sqrtf(hl * hl + hw * hw);
     const float reach = V3_LIDAR_RANGE + hd;
     if (!(d2 < reach * reach)) continue;
@@ -1088,7 +1235,7 @@ V3_HD void task_lidar_windows(Smem<V, OBS_CAP>& sm, const Thr& th) {
         if (blo < 0) blo += PGD_LIDAR_BEAMS;
       }
     }
-    sm.vis[n++][ln] = s | (blo << 8) | (bn << 16);
+    vis[n++][ln] = s | (blo << 8) | (bn << 16);
   }
   sm.n_vis[ln] = n;
 }
@@ -1096,18 +1243,18 @@ V3_HD void task_lidar_windows(Smem<V, OBS_CAP>& sm, const Thr& th) {
 /* side / lane-line detectors (distance_detector.py:137-152): ray fans against the line ghosts of the map; a beam
  * looks up the bucket of a point every 8 m along itself (buckets list every box within 4 m of them).  The rays of an
  * environment are spread over the roles. */
-template <int V, int OBS_CAP>
-V3_HD void task_detectors(const Smem<V, OBS_CAP>& sm, const Thr& th, const Tables& T, const PgdConfig& cfg, int n_roles,
+template <int V, int R>
+V3_HD void task_detectors(const Smem<V, R>& sm, const Thr<V, R>& th, const Tables& T, const PgdConfig& cfg,
                           float* obs) {
   const int ln = th.lane;
-  const Pub<V>& P = sm.p;
   const PgdMap& mp = th.mp;
-  const float ex = P.x[0][ln], ey = P.y[0][ln], eh = sm.ego_h[ln];
+  const F4 e = sm.efin[ln];
+  const float ex = e.x, ey = e.y, eh = sm.ego_h[ln];
   const int n_first = cfg.n_side > 0 ? cfg.n_side : 2;
   const int n_rays = cfg.n_side + cfg.n_lane_line;
   const int32_t* ent = T.cell_entries + mp.entry_off;
 #pragma unroll 1
-  for (int rI = th.role; rI < n_rays; rI += n_roles) {
+  for (int rI = th.role; rI < n_rays; rI += R) {
     const bool side = rI < cfg.n_side;
     const int i = side ? rI : rI - cfg.n_side;
     const int n = side ? cfg.n_side : cfg.n_lane_line;
@@ -1137,19 +1284,19 @@ V3_HD void task_detectors(const Smem<V, OBS_CAP>& sm, const Thr& th, const Table
   }
 }
 
-template <int V, int OBS_CAP>
-V3_HD void phase_f(Smem<V, OBS_CAP>& sm, Thr& th, const Tables& T, const State& S, const PgdConfig& cfg, int mode,
-                   int n_roles, int obs_dim, float* reward, uint8_t* done, PgdInfo* info) {
+template <int V, int R>
+V3_HD void phase_f(Smem<V, R>& sm, Thr<V, R>& th, const Tables& T, const State& S, const PgdConfig& cfg, int mode,
+                   int obs_dim, float* obs_rows, VisPtr vis, float* reward, uint8_t* done, PgdInfo* info) {
   if (!th.valid) return;
-  float* obs = sm.u.obs + (size_t)th.lane * obs_dim;
+  float* obs = obs_rows + (size_t)th.lane * obs_dim;
 #pragma unroll 1
-  for (int task = th.role; task < 4; task += n_roles) {
-    if (task == 0) task_reward(sm, th, T, S, cfg, mode, n_roles, obs, reward, done, info);
+  for (int task = th.role; task < 4; task += R) {
+    if (task == 0) task_reward(sm, th, T, S, cfg, mode, obs, reward, done, info);
     else if (task == 1) task_navi(sm, th, T, cfg, obs);
     else if (task == 2) task_neighbours(sm, th, cfg, obs);
-    else task_lidar_windows(sm, th);
+    else task_lidar_windows(sm, th, vis);
   }
-  if (cfg.n_side > 0 || cfg.n_lane_line > 0) task_detectors(sm, th, T, cfg, n_roles, obs);
+  if (cfg.n_side > 0 || cfg.n_lane_line > 0) task_detectors(sm, th, T, cfg, obs);
 }
 
 // ---- phase L: lidar as a scatter (cutils.pyx:60-142 restated per chassis instead of per beam) ---------------------
@@ -1163,22 +1310,26 @@ V3_HD void lidar_min(float* cell, float t) {
 #endif
 }
 
-template <int V, int OBS_CAP>
-V3_HD void phase_l(Smem<V, OBS_CAP>& sm, int role, int lane, int n_roles, int obs_dim) {
+template <int V, int R>
+V3_HD void phase_l(const Smem<V, R>& sm, const Tables& T, const State& S, int role, int lane, int num_envs, int env0,
+                   int obs_dim, float* obs_rows, VisPtr vis) {
   const Pub<V>& P = sm.p;
   const int head = obs_dim - PGD_LIDAR_BEAMS;
 #pragma unroll 1
-  for (int e = role; e < V3_LANES; e += n_roles) {
+  for (int e = role; e < V3_LANES; e += R) {
     if (!sm.wrote[e]) continue;
     const int nv = sm.n_vis[e];
     if (nv == 0) continue;
-    const float ex = P.x[0][e], ey = P.y[0][e], eh = sm.ego_h[e];
-    float* row = sm.u.obs + (size_t)e * obs_dim + head;
+    const F4 eg = sm.efin[e];
+    const float ex = eg.x, ey = eg.y, eh = sm.ego_h[e];
+    float* row = obs_rows + (size_t)e * obs_dim + head;
+    const PgdSlot* tpl = T.slots + ldg(&T.episodes[S.envi[env0 + e].x].slot_off);
 #pragma unroll 1
     for (int k = 0; k < nv; ++k) {
-      const int w = sm.vis[k][e];
+      const int w = vis[k][e];
       const int s = w & 0xff, blo = (w >> 8) & 0xff, bn = w >> 16;
-      const Rect r = {P.x[s][e], P.y[s][e], P.hc[s][e], P.hs[s][e], P.hl[s][e], P.hw[s][e]};
+      const Rect r = {P.x[s][e], P.y[s][e], P.hc[s][e], P.hs[s][e], ldg(&tpl[s].length) * 0.5f,
+                      ldg(&tpl[s].width) * 0.5f};
 #pragma unroll 1
       for (int rel = lane; rel <= bn; rel += V3_LANES) {
         int i = blo + rel;

@@ -10,13 +10,12 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-VARIANTS = {
-    "ctas5": ["-DMIN_CTAS_PER_SM=5"],
-    "ctas6": ["-DMIN_CTAS_PER_SM=6"],
-    "c64": ["-DCTA_THREADS=64", "-DMIN_CTAS_PER_SM=8"],
-    "c64nb": ["-DCTA_THREADS=64", "-DMIN_CTAS_PER_SM=8", "-DPHASE_BARRIERS=0"],
-    "c32": ["-DCTA_THREADS=32", "-DMIN_CTAS_PER_SM=16", "-DPHASE_BARRIERS=0"],
-    "c256": ["-DCTA_THREADS=256", "-DMIN_CTAS_PER_SM=2"],
+VARIANTS = {  # role-per-warp kernel (pgd_step_v3.cu): warps per CTA x resident CTAs the register budget is set for
+    "clk": ["-DV3_ROLES=4", "-DV3_MIN_CTAS=4", "-DV3_PHASE_CLOCKS"],
+    "r4c3": ["-DV3_ROLES=4", "-DV3_MIN_CTAS=3"],
+    "r5c4": ["-DV3_ROLES=5", "-DV3_MIN_CTAS=4"],
+    "r6c3": ["-DV3_ROLES=6", "-DV3_MIN_CTAS=3"],
+    "r8c3": ["-DV3_ROLES=8", "-DV3_MIN_CTAS=3"],
 }
 
 
@@ -33,7 +32,7 @@ def main():
         if lib and not os.path.exists(lib):
             continue
         for actions in ("uniform", "forward"):
-            env = dict(os.environ, PGDRIVE_B200_LIB=lib, ACTIONS=actions)
+            env = dict(os.environ, PGDRIVE_B200_LIB=lib, ACTIONS=actions, LAYOUT=os.environ.get("LAYOUT", "2"))
             out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "quick_bench.py")], env=env,
                                  stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True).stdout.strip().split("\n")
             print(name, out[-1], flush=True)

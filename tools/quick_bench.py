@@ -23,3 +23,13 @@ for t in range(K): env.step(a[W + t])
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / K
 print("%s layout=%d actions=%s: %.4f ms/step, %.1f M env-steps/s" % (os.environ.get("PGDRIVE_B200_LIB", "default"), int(layout), mode, ms, n / ms / 1e3))
+
+if hasattr(env.engine.lib, "pgd_debug_phase_clocks"):  # diagnostic build (-DV3_PHASE_CLOCKS): cycles per phase, thread 0
+    import ctypes
+    buf = (ctypes.c_ulonglong * 16)()
+    env.engine.lib.pgd_debug_phase_clocks(buf, 1)
+    names = ["init", "A", "wait A", "B + wait", "C", "wait C", "fill", "D", "wait D", "F", "wait F", "L", "store"]
+    ctas = (n + 31) // 32 * (W + K + 1)
+    tot = sum(buf[:13])
+    print("phase clocks (cycles per CTA, thread 0):", ", ".join("%s %.0f" % (nm, buf[i] / ctas) for i, nm in enumerate(names)),
+          "| total %.0f" % (tot / ctas))
