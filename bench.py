@@ -121,8 +121,8 @@ def cpu_oracle_rate(T, n_envs, steps, warmup, threads, episode_ids, seed=0):
 WORKLOADS = {
     # name: (first seed, number of seeds, vehicle slots, description)
     "v0": (1000, 100, 16, WORKLOAD),
-    "1000envs": (1000, 1000, 32, "65536 envs PGDrive-1000envs-v0 (seeds 1000-1999, 1000 distinct maps), "
-                                 "traffic_density=0.1, 240-beam lidar, 32 vehicle slots"),
+    "1000envs": (1000, 1000, 24, "65536 envs PGDrive-1000envs-v0 (seeds 1000-1999, 1000 distinct maps), "
+                                 "traffic_density=0.1, 240-beam lidar, 24 vehicle slots"),
 }
 
 
@@ -201,7 +201,7 @@ def run_own(args):
     side = torch.cuda.Stream(device=dev, priority=-1) if world > 1 else None
     env = VecPGDriveEnv(
         dict(start_seed=first_seed, environment_num=n_seeds, num_envs=n, traffic_density=0.1, device=local_rank,
-             num_slots=n_slots, one_thread_per_env=(args.layout == "per_env")),
+             num_slots=n_slots),
         tables_dict=T, obs_out=bufs[0].local(bufs[0].obs)
     )
     # N > 1, default: the gather to rank 0 is fused into the step kernel (results stored straight into rank 0's HBM
@@ -409,7 +409,7 @@ def run_own(args):
             driving_policy_env_steps_per_s_per_gpu=fwd_rate,
         ),
         roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
-                      kernel=("pgd_step_v2_kernel<%d>" if args.layout == "per_env" else "pgd_step_kernel<%d>") % n_slots, kernel_ms=kernel_ms, bytes_per_env_step=b_step, peak_source=peak_src),
+                      kernel="pgd_step_kernel<%d>" % n_slots, kernel_ms=kernel_ms, bytes_per_env_step=b_step, peak_source=peak_src),
         cpu_baseline=cpu,
         reset_path=reset_path,
         e2e=dict(value=total_envs * e2e_steps / (e2e_ms * 1e-3), unit="env-steps/s",
@@ -431,9 +431,6 @@ def main():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--envs", type=int, default=65536, help="environments per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--layout", default="cooperative", choices=["cooperative", "per_env"],
-                    help="step kernel: cooperative (16 threads per environment, default) or per_env (one thread per "
-                         "environment, experimental; DESIGN.md section 10)")
     ap.add_argument("--gather", default="auto", choices=["auto", "peer", "nccl"],
                     help="N > 1: how rank 0 gets the whole batch (auto = peer: rows stored by the step kernel straight "
                          "into rank 0's HBM with one bulk copy per CTA, 694 M env-steps/s at 8 GPUs against 533 M for "

@@ -106,7 +106,7 @@ typedef struct {
 /* Reward / termination scheme (envs/pgdrive_env.py:93-108) and stepping (envs/base_env.py:33,70). */
 typedef struct {
   int32_t num_envs;
-  int32_t num_slots;        /* vehicle slots per env: 16 or 32 */
+  int32_t num_slots;        /* vehicle slots per env: 16, 24 or 32 */
   int32_t decision_repeat;  /* physics sub-steps per env step (5) */
   int32_t horizon;          /* 0 = none */
   float dt;                 /* physics_world_step_size (0.02) */
@@ -120,9 +120,6 @@ typedef struct {
    * i * 2pi / n + 90 degrees from the heading */
   int32_t n_side, n_lane_line;
   float side_distance, lane_line_distance;
-  /* 0 (default): cooperative kernel, 16 / 32 threads per environment, state [env][slot];
-   * 1 (experimental): one thread per environment, state [slot][env] (pgd_step_v2.cu) */
-  int32_t layout;
   /* envs/base_env.py:29, obs/state_obs.py:18-23,103-105: the ego is one of the five vehicle types (chosen per seed by
    * the host) and the observation gains LENGTH / 10 and WIDTH / 2.5 after the lane-line beams */
   int32_t random_agent_model;

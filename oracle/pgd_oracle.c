@@ -449,9 +449,9 @@ static void physics_substep(Veh* v, float dt, int overspeed) {
   }
   float delta = clipf(-v->steer * s->max_steer, -1.4f, 1.4f); /* +steering = left = heading decreases */
   float tb = s->lr / (s->lf + s->lr) * pgd_tanf(delta);
-  float sb0 = tb / sqrtf(1.0f + tb * tb);
+  float k_yaw = tb / sqrtf(1.0f + tb * tb) / s->lr; /* kinematic yaw rate per unit speed: sin(slip angle) / lr */
   /* yaw rate relaxes towards the kinematic-bicycle value (tyre relaxation + yaw inertia, tau = 0.1 s) ... */
-  float yaw = v->w + (speed * sb0 / s->lr - v->w) * (dt / YAW_TAU);
+  float yaw = v->w + (speed * k_yaw - v->w) * (dt / YAW_TAU);
   /* ... and the tyres cannot give more than mu*g of lateral acceleration */
   if (speed * fabsf(yaw) > mu_g) yaw = copysignf(mu_g / speed, yaw);
   float sb = speed > 1e-3f ? clipf(yaw * s->lr / speed, -1.0f, 1.0f) : 0.0f;

@@ -1,4 +1,4 @@
-/* TEST INFRASTRUCTURE ONLY.  Host (g++) build of the role-per-warp step (pgdrive_b200/csrc/pgd_step_v3.cuh is
+/* TEST INFRASTRUCTURE ONLY.  Host (g++) build of the role-per-warp step (pgdrive_b200/csrc/pgd_step.cuh is
  * written for host + device): every CTA of 32 environments is emulated by running the phases in order over all
  * (role, lane) pairs -- the loops stand for the CTA barriers -- so that the step's logic, including its
  * shared-memory exchanges, is checked against the independent CPU oracle (oracle/pgd_oracle.c) without a GPU.
@@ -6,11 +6,11 @@
 #include <stdlib.h>
 #include <string.h>
 
-#include "../pgdrive_b200/csrc/pgd_step_v3.cuh"
+#include "../pgdrive_b200/csrc/pgd_step.cuh"
 
-using namespace pgdv3;
+using namespace pgdstep;
 
-struct HostV3 {
+struct HostStep {
   Tables T;
   State S;
   PgdConfig cfg;
@@ -18,7 +18,7 @@ struct HostV3 {
 };
 
 template <int V, int R>
-static void run_vr(HostV3* h, int mode, const float* actions, float* obs, float* reward, uint8_t* done, PgdInfo* info) {
+static void run_vr(HostStep* h, int mode, const float* actions, float* obs, float* reward, uint8_t* done, PgdInfo* info) {
   typedef Smem<V, R> SM;
   const int n = h->cfg.num_envs, od = obs_dim_of(h->cfg);
   const size_t bytes = smem_bytes<V, R>(od, h->cfg.decision_repeat);
@@ -27,33 +27,33 @@ static void run_vr(HostV3* h, int mode, const float* actions, float* obs, float*
   float* rows = reinterpret_cast<float*>(raw + smem_obs_offset<V, R>());
   TrajPtr traj = reinterpret_cast<TrajPtr>(raw + smem_tv_offset<V, R>(od));
   VisPtr vis = reinterpret_cast<VisPtr>(raw + smem_tv_offset<V, R>(od));
-  static Thr<V, R> th[R][V3_LANES];
-  for (int env0 = 0; env0 < n; env0 += V3_LANES) {
+  static Thr<V, R> th[R][PGS_LANES];
+  for (int env0 = 0; env0 < n; env0 += PGS_LANES) {
     memset(raw, 0xff, bytes);  // shared memory starts as garbage on the device
     bool any = false;
     for (int r = 0; r < R; ++r)
-      for (int l = 0; l < V3_LANES; ++l) {
+      for (int l = 0; l < PGS_LANES; ++l) {
         thread_init(th[r][l], h->T, h->S, h->cfg, mode, l, r, env0 + l, n);
         any = any || th[r][l].valid;
       }
     if (!any) continue;
-#define ALL(call) for (int r = 0; r < R; ++r) for (int l = 0; l < V3_LANES; ++l) { Thr<V, R>& t = th[r][l]; (void)t; call; }
+#define ALL(call) for (int r = 0; r < R; ++r) for (int l = 0; l < PGS_LANES; ++l) { Thr<V, R>& t = th[r][l]; (void)t; call; }
     ALL(phase_a(sm, t, h->S, h->cfg, actions));
     ALL(phase_b(sm, t, rows));
     ALL(phase_c(sm, t, h->T, h->S, h->cfg, rows, traj));
-    for (int i = 0; i < V3_LANES * od; ++i) rows[i] = 1.0f;
+    for (int i = 0; i < PGS_LANES * od; ++i) rows[i] = 1.0f;
     ALL(phase_d(sm, t, h->T, h->S, h->cfg, traj));
     ALL(phase_f(sm, t, h->T, h->S, h->cfg, mode, od, rows, vis, reward, done, info));
     ALL(phase_l(sm, h->T, h->S, r, l, n, env0, od, rows, vis));
 #undef ALL
-    for (int l = 0; l < V3_LANES; ++l)
+    for (int l = 0; l < PGS_LANES; ++l)
       if (sm.wrote[l]) memcpy(obs + (size_t)(env0 + l) * od, rows + (size_t)l * od, (size_t)od * 4);
   }
   free(raw);
 }
 
 template <int V>
-static void run_v(HostV3* h, int mode, const float* actions, float* obs, float* reward, uint8_t* done, PgdInfo* info) {
+static void run_v(HostStep* h, int mode, const float* actions, float* obs, float* reward, uint8_t* done, PgdInfo* info) {
   switch (h->roles) {
     case 2: run_vr<V, 2>(h, mode, actions, obs, reward, done, info); break;
     case 3: run_vr<V, 3>(h, mode, actions, obs, reward, done, info); break;
@@ -63,7 +63,7 @@ static void run_v(HostV3* h, int mode, const float* actions, float* obs, float* 
   }
 }
 
-static void run(HostV3* h, int mode, const float* actions, float* obs, float* reward, uint8_t* done, PgdInfo* info) {
+static void run(HostStep* h, int mode, const float* actions, float* obs, float* reward, uint8_t* done, PgdInfo* info) {
   if (h->cfg.num_slots == 16) run_v<16>(h, mode, actions, obs, reward, done, info);
   else if (h->cfg.num_slots == 24) run_v<24>(h, mode, actions, obs, reward, done, info);
   else run_v<32>(h, mode, actions, obs, reward, done, info);
@@ -71,8 +71,8 @@ static void run(HostV3* h, int mode, const float* actions, float* obs, float* re
 
 extern "C" {
 
-void* v3h_create(const PgdTables* t, const PgdConfig* cfg, int roles) {
-  HostV3* h = (HostV3*)calloc(1, sizeof(HostV3));
+void* sth_create(const PgdTables* t, const PgdConfig* cfg, int roles) {
+  HostStep* h = (HostStep*)calloc(1, sizeof(HostStep));
   h->cfg = *cfg;
   h->roles = roles;
   h->T.maps = t->maps; h->T.lanes = t->lanes; h->T.roads = t->roads; h->T.boxes = t->boxes;
@@ -85,26 +85,26 @@ void* v3h_create(const PgdTables* t, const PgdConfig* cfg, int roles) {
   return h;
 }
 
-void v3h_destroy(void* p) {
-  HostV3* h = (HostV3*)p;
+void sth_destroy(void* p) {
+  HostStep* h = (HostStep*)p;
   free(h->S.pose); free(h->S.ctrl); free(h->S.pidl); free(h->S.nav); free(h->S.misc); free(h->S.envi); free(h->S.envf);
   free(h);
 }
 
 /* pgd_reset: environments env_ids[i] restart on episode_ids[i]; their observation rows are rewritten */
-void v3h_reset(void* p, const int32_t* env_ids, const int32_t* episode_ids, int n, float* obs, PgdInfo* info) {
-  HostV3* h = (HostV3*)p;
+void sth_reset(void* p, const int32_t* env_ids, const int32_t* episode_ids, int n, float* obs, PgdInfo* info) {
+  HostStep* h = (HostStep*)p;
   for (int i = 0; i < n; ++i) {
     int e = env_ids ? env_ids[i] : i;
     h->S.envi[e].x = episode_ids[i];
-    h->S.envi[e].z = V3_DONE_PENDING_RESET;
+    h->S.envi[e].z = PGS_DONE_PENDING_RESET;
   }
   run(h, 1, nullptr, obs, nullptr, nullptr, info);
 }
 
 /* pgd_get_state for the slot-major layout (exchange format of include/pgd_tables.h) */
-void v3h_get_state(void* p, int env, PgdEnvState* out) {
-  HostV3* h = (HostV3*)p;
+void sth_get_state(void* p, int env, PgdEnvState* out) {
+  HostStep* h = (HostStep*)p;
   const int n = h->cfg.num_envs, V = h->cfg.num_slots;
   memset(out, 0, sizeof(*out));
   const I4 ei = h->S.envi[env];
@@ -125,7 +125,7 @@ void v3h_get_state(void* p, int env, PgdEnvState* out) {
   }
 }
 
-void v3h_step(void* p, const float* actions, float* obs, float* reward, uint8_t* done, PgdInfo* info) {
-  run((HostV3*)p, 0, actions, obs, reward, done, info);
+void sth_step(void* p, const float* actions, float* obs, float* reward, uint8_t* done, PgdInfo* info) {
+  run((HostStep*)p, 0, actions, obs, reward, done, info);
 }
 }

@@ -10,10 +10,9 @@ COMMON = ["pgd_internal.h", os.path.join(INC, "pgdrive_b200.h"), os.path.join(IN
           os.path.join(INC, "pgd_math.h")]
 # translation unit -> extra dependencies
 UNITS = {
-    "pgd_step.cu": [],
+    "pgd_abi.cu": [],
+    "pgd_step_kernel.cu": ["pgd_step.cuh"],
     "pgd_mapgen.cu": ["pgd_mapgen.cuh", "pgd_rng.cuh", "pgd_dd.cuh"],
-    "pgd_step_v2.cu": ["pgd_step_v2.cuh"],
-    "pgd_step_v3.cu": ["pgd_step_v3.cuh"],
 }
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
@@ -41,8 +40,7 @@ def build_cuda(force=False, verbose=False, out=OUT, defines=()):
     objs, jobs, relink = [], [], force or not os.path.exists(out)
     for unit, extra in UNITS.items():
         src = os.path.join(CSRC, unit)
-        variant_unit = "pgd_step_v3.cu" if any("V3_" in d for d in defines) else "pgd_step.cu"
-        utag = tag if unit == variant_unit else ""  # variants only differ in one step kernel
+        utag = tag if unit == "pgd_step_kernel.cu" else ""  # variants only differ in the step kernel
         obj = os.path.join(CSRC, unit.replace(".cu", utag + ".o"))
         deps = [src] + [d if os.path.isabs(d) else os.path.join(CSRC, d) for d in COMMON + extra]
         if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(d) for d in deps):

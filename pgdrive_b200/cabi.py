@@ -54,7 +54,7 @@ class PgdConfig(C.Structure):
         ("crash_vehicle_penalty", C.c_float), ("driving_reward", C.c_float), ("speed_reward", C.c_float),
         ("out_of_road_cost", C.c_float), ("crash_vehicle_cost", C.c_float), ("use_lateral", C.c_int32),
         ("out_of_route_done", C.c_int32), ("auto_reset", C.c_int32), ("n_side", C.c_int32),
-        ("n_lane_line", C.c_int32), ("side_distance", C.c_float), ("lane_line_distance", C.c_float), ("layout", C.c_int32),
+        ("n_lane_line", C.c_int32), ("side_distance", C.c_float), ("lane_line_distance", C.c_float),
         ("random_agent_model", C.c_int32)
     ]
 
@@ -62,14 +62,14 @@ class PgdConfig(C.Structure):
 def make_config(num_envs, num_slots=16, decision_repeat=5, horizon=0, dt=0.02, success_reward=10.0,
                 out_of_road_penalty=5.0, crash_vehicle_penalty=5.0, driving_reward=1.0, speed_reward=0.1,
                 out_of_road_cost=1.0, crash_vehicle_cost=1.0, use_lateral=False, out_of_route_done=False,
-                auto_reset=True, n_side=0, side_distance=50.0, n_lane_line=0, lane_line_distance=20.0, layout=0,
+                auto_reset=True, n_side=0, side_distance=50.0, n_lane_line=0, lane_line_distance=20.0,
                 random_agent_model=False):
     if not (0 <= n_side <= MAX_DETECTOR_BEAMS and 0 <= n_lane_line <= MAX_DETECTOR_BEAMS):
         raise ValueError("side / lane-line detectors support 0..%d lasers" % MAX_DETECTOR_BEAMS)
     return PgdConfig(num_envs, num_slots, decision_repeat, int(horizon or 0), dt, success_reward, out_of_road_penalty,
                      crash_vehicle_penalty, driving_reward, speed_reward, out_of_road_cost, crash_vehicle_cost,
                      int(use_lateral), int(out_of_route_done), int(auto_reset), int(n_side), int(n_lane_line),
-                     float(side_distance), float(lane_line_distance), int(layout), int(bool(random_agent_model)))
+                     float(side_distance), float(lane_line_distance), int(bool(random_agent_model)))
 
 
 def obs_dim(cfg):

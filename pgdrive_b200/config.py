@@ -186,11 +186,9 @@ PGDRIVE_DEFAULT_CONFIG = dict(
 # knobs of the batched engine itself (not in the reference)
 ENGINE_CONFIG = dict(
     num_envs=1,          # environments stepped per launch
-    num_slots=None,      # vehicle slots per env (16 / 32); None = smallest that fits the loaded seeds
+    num_slots=None,      # vehicle slots per env (16 / 24 / 32); None = smallest that fits the loaded seeds
     device=0,            # CUDA device ordinal
     auto_reset=True,     # VecPGDriveEnv only: a finished env restarts at its next step (action ignored)
-    one_thread_per_env=False,  # second layout of the step (pgd_step_v2.cu)
-    layout=None,         # step kernel: 0 cooperative, 1 one thread per env, 2 role per warp; None = the default
     device_mapgen=False,  # VecPGDriveEnv only: run the reset path (map search, tables, episode templates) on the GPU
 )
 

@@ -21,7 +21,7 @@ struct DevTables {
   const int32_t* route_roads;
 };
 
-// SoA state; index = env * V + slot for the per-slot arrays, env for the per-env ones.
+// SoA state, slot-major: index = slot * num_envs + env for the per-slot arrays, env for the per-env ones.
 struct DevState {
   float4* pose;  // x, y, heading, speed
   float4* ctrl;  // steer, throttle, heading-PID last error, heading-PID summed error
@@ -74,10 +74,7 @@ struct PgdHandle {
   cudaEvent_t ev0, ev1;
 };
 
-// pgd_step_v2.cu: one thread per environment (PgdConfig.layout == 1)
-int pgd_launch_step_v2(PgdHandle* h, int mode, int env_begin, int env_end, const float* actions, float* obs,
-                       float* reward, uint8_t* done, PgdInfo* info, cudaStream_t st);
-// pgd_step_v3.cu: role per warp, environment per lane (PgdConfig.layout == 2)
-int pgd_launch_step_v3(PgdHandle* h, int mode, int env_begin, int env_end, const float* actions, float* obs,
-                       float* reward, uint8_t* done, PgdInfo* info, cudaStream_t st);
+// pgd_step_kernel.cu: the fused environment step (mode 0) / the reset pass (mode 1) over environments [env_begin, env_end)
+int pgd_launch_step(PgdHandle* h, int mode, int env_begin, int env_end, const float* actions, float* obs,
+                    float* reward, uint8_t* done, PgdInfo* info, cudaStream_t st);
 #endif

@@ -17,13 +17,13 @@
  *   F  role-parallel ego bookkeeping: reward / done / state (0), navigation info (1), 4 nearest vehicles (2),
  *      lidar windows (3); detector ray fans over all roles
  *   L  lidar as a scatter: every (visible chassis, beam of its window) pair is one work item; lanes = beams
- *   W  the 32 rows leave the CTA with ONE bulk (TMA) shared -> global copy (pgd_step_v3.cu)
+ *   W  the 32 rows leave the CTA with ONE bulk (TMA) shared -> global copy (pgd_step_kernel.cu)
  *
  * State in HBM is slot-major ([slot][env]) so that a warp's loads / stores of a slot are 32 consecutive 16-byte
  * vectors.  Parked traffic is never loaded beyond its flag word (its pose is the episode template's).
  *
  * The arithmetic is the oracle's, expression for expression.  The file compiles for the host too
- * (oracle/step_v3_host.cpp runs the phases in order over all (role, lane) pairs), so the whole step is checked bit
+ * (oracle/step_host.cpp runs the phases in order over all (role, lane) pairs), so the whole step is checked bit
  * for bit against the independent CPU oracle without a GPU (tests/test_step_host.py).
  *
  * Reference call stack (paths under /root/reference/pgdrive): envs/base_env.py:184-224,303-344 (step),
@@ -32,8 +32,8 @@
  * cutils.pyx:60-142 + vehicle_module/lidar.py:55-77 (lidar, neighbours), obs/state_obs.py:58-170 (observation),
  * envs/pgdrive_env.py:162-258 (reward / cost / done).
  */
-#ifndef PGD_STEP_V3_CUH
-#define PGD_STEP_V3_CUH
+#ifndef PGD_STEP_CUH
+#define PGD_STEP_CUH
 #include <limits.h>
 #include <math.h>
 #include <stdint.h>
@@ -43,32 +43,32 @@
 #include "../../include/pgd_tables.h"
 
 #ifdef __CUDACC__
-#define V3_HD __host__ __device__ __forceinline__
-#define V3_HD_OUTLINE __host__ __device__ __noinline__
+#define PGS_HD __host__ __device__ __forceinline__
+#define PGS_HD_OUTLINE __host__ __device__ __noinline__
 #else
-#define V3_HD inline
-#define V3_HD_OUTLINE inline
+#define PGS_HD inline
+#define PGS_HD_OUTLINE inline
 #endif
 
-namespace pgdv3 {
+namespace pgdstep {
 
-#define V3_PI 3.14159265358979323846f
-#define V3_TWO_PI 6.28318530717958647692f
-#define V3_GRAVITY 9.81f
-#define V3_LIDAR_RANGE 50.0f
-#define V3_MAX_SPEED_KMH 80.0f
-#define V3_IDM_MAX_LONG 30.0f
-#define V3_IDM_NORMAL_SPEED 30.0f
-#define V3_IDM_CREEP_SPEED 5.0f
-#define V3_IDM_SAFE_DIST 15.0f
-#define V3_IDM_LANE_CHANGE_FREQ 50
-#define V3_IDM_SPEED_INCREASE 10.0f
-#define V3_IDM_MAX_SPEED 100.0f
-#define V3_YAW_TAU 0.1f
-#define V3_DONE_PENDING_RESET 2
-#define V3_MAX_SUBSTEPS 8 /* decision_repeat supported (default 5) */
-#define V3_LANES 32       /* environments per CTA = lanes of a warp */
-#define V3_MAX_ROLES 8
+#define PGS_PI 3.14159265358979323846f
+#define PGS_TWO_PI 6.28318530717958647692f
+#define PGS_GRAVITY 9.81f
+#define PGS_LIDAR_RANGE 50.0f
+#define PGS_MAX_SPEED_KMH 80.0f
+#define PGS_IDM_MAX_LONG 30.0f
+#define PGS_IDM_NORMAL_SPEED 30.0f
+#define PGS_IDM_CREEP_SPEED 5.0f
+#define PGS_IDM_SAFE_DIST 15.0f
+#define PGS_IDM_LANE_CHANGE_FREQ 50
+#define PGS_IDM_SPEED_INCREASE 10.0f
+#define PGS_IDM_MAX_SPEED 100.0f
+#define PGS_YAW_TAU 0.1f
+#define PGS_DONE_PENDING_RESET 2
+#define PGS_MAX_SUBSTEPS 8 /* decision_repeat supported (default 5) */
+#define PGS_LANES 32       /* environments per CTA = lanes of a warp */
+#define PGS_MAX_ROLES 8
 
 struct alignas(16) F4 { float x, y, z, w; };
 struct alignas(16) I4 { int x, y, z, w; };
@@ -96,8 +96,25 @@ struct State {  // slot-major: per-slot arrays are indexed slot * num_envs + env
   F4* envf;   // previous steering, previous throttle, episode reward, episode energy
 };
 
+#if defined(__CUDA_ARCH__) && defined(PGS_TABLE_EVICT_LAST)
+// read-only table data with an L2 evict_last policy: the tables (7 MB for 100 maps) are re-read by every CTA of every
+// step while 100+ MB of state and observation rows stream through the L2 in between
+__device__ __forceinline__ uint64_t table_policy() {
+  uint64_t pol;
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint4 ldg16_keep(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p), "l"(table_policy()));
+  return v;
+}
+#endif
+
 template <class T_>
-V3_HD T_ ldg(const T_* p) {
+PGS_HD T_ ldg(const T_* p) {
 #ifdef __CUDA_ARCH__
   return __ldg(p);
 #else
@@ -107,46 +124,65 @@ V3_HD T_ ldg(const T_* p) {
 
 /* A whole table record (PgdLane 64 B, PgdBox / PgdRoad 32 B, PgdMap 64 B) with 16-byte read-only loads. */
 template <class T_>
-V3_HD T_ load_rec(const T_* p) {
+PGS_HD T_ load_rec(const T_* p) {
 #ifdef __CUDA_ARCH__
   static_assert(sizeof(T_) % 16 == 0, "table records are multiples of 16 bytes");
   T_ out;
   const uint4* src = reinterpret_cast<const uint4*>(p);
   uint4* dst = reinterpret_cast<uint4*>(&out);
 #pragma unroll
+#ifdef PGS_TABLE_EVICT_LAST
+  for (int i = 0; i < (int)(sizeof(T_) / 16); ++i) dst[i] = ldg16_keep(src + i);
+#else
   for (int i = 0; i < (int)(sizeof(T_) / 16); ++i) dst[i] = __ldg(src + i);
+#endif
   return out;
 #else
   return *p;
 #endif
 }
 
-V3_HD float clipf(float a, float lo, float hi) { return fminf(fmaxf(a, lo), hi); }
+PGS_HD float clipf(float a, float lo, float hi) { return fminf(fmaxf(a, lo), hi); }
 
-V3_HD_OUTLINE void sincos_hd(float a, float* s, float* c) { pgd_sincosf(a, s, c); }
-#define V3_SINCOS(a, s, c) pgdv3::sincos_hd((a), &(s), &(c))
+// out of line (one copy; ~45 instructions), results by value so that nothing goes through local memory
+struct SinCos { float s, c; };
+PGS_HD_OUTLINE SinCos sincos_hd(float a) {
+  SinCos r;
+  pgd_sincosf(a, &r.s, &r.c);
+  return r;
+}
+#define PGS_SINCOS(a, s_out, c_out)                 \
+  do {                                              \
+    const pgdstep::SinCos sc_ = pgdstep::sincos_hd(a); \
+    (s_out) = sc_.s;                                \
+    (c_out) = sc_.c;                                \
+  } while (0)
 
-V3_HD_OUTLINE void arc_local(float cx, float cy, float ph0, float dir, float radius, float x, float y, float* lon,
-                             float* lat) {
+struct LonLat { float lon, lat; };
+PGS_HD_OUTLINE LonLat arc_local(float cx, float cy, float ph0, float dir, float radius, float x, float y) {
   float dx = x - cx, dy = y - cy;
   float phi = pgd_atan2f(dy, dx);
   phi = ph0 + pgd_wrap_to_pi(phi - ph0);
   float r = sqrtf(dx * dx + dy * dy);
-  *lon = dir * (phi - ph0) * radius;
-  *lat = dir * (radius - r);
+  LonLat o;
+  o.lon = dir * (phi - ph0) * radius;
+  o.lat = dir * (radius - r);
+  return o;
 }
 
-V3_HD void lane_local(const PgdLane& l, float x, float y, float& lon, float& lat) {
+PGS_HD void lane_local(const PgdLane& l, float x, float y, float& lon, float& lat) {
   if (l.kind == PGD_LANE_STRAIGHT) {
     float dx = x - l.sx, dy = y - l.sy;
     lon = dx * l.ax + dy * l.ay;
     lat = dx * -l.ay + dy * l.ax;
   } else {
-    arc_local(l.ax, l.ay, l.ph0, l.dir, l.radius, x, y, &lon, &lat);
+    const LonLat o = arc_local(l.ax, l.ay, l.ph0, l.dir, l.radius, x, y);
+    lon = o.lon;
+    lat = o.lat;
   }
 }
 
-V3_HD void lane_position(const PgdLane& l, float lon, float lat, float& x, float& y) {
+PGS_HD void lane_position(const PgdLane& l, float lon, float lat, float& x, float& y) {
   if (l.kind == PGD_LANE_STRAIGHT) {
     x = l.sx + lon * l.ax + lat * -l.ay;
     y = l.sy + lon * l.ay + lat * l.ax;
@@ -154,26 +190,26 @@ V3_HD void lane_position(const PgdLane& l, float lon, float lat, float& x, float
     float phi = l.dir * lon / l.radius + l.ph0;
     float r = l.radius - lat * l.dir;
     float s, c;
-    V3_SINCOS(phi, s, c);
+    PGS_SINCOS(phi, s, c);
     x = l.ax + r * c;
     y = l.ay + r * s;
   }
 }
 
-V3_HD float lane_heading_at(const PgdLane& l, float lon) {
+PGS_HD float lane_heading_at(const PgdLane& l, float lon) {
   if (l.kind == PGD_LANE_STRAIGHT) return l.heading;
   float phi = l.dir * lon / l.radius + l.ph0;
-  return phi + V3_PI / 2 * l.dir;
+  return phi + PGS_PI / 2 * l.dir;
 }
 
-V3_HD bool precedes(float ex, float ey, float sx, float sy) {  // abs_lane.py:114-119 (norm < 0.1)
+PGS_HD bool precedes(float ex, float ey, float sx, float sy) {  // abs_lane.py:114-119 (norm < 0.1)
   float dx = ex - sx, dy = ey - sy;
   return dx * dx + dy * dy < 1e-2f;
 }
 
 struct Rect { float cx, cy, ux, uy, hl, hw; };
 
-V3_HD_OUTLINE bool rect_overlap(const Rect& a, const Rect& b) {
+PGS_HD bool rect_overlap(const Rect& a, const Rect& b) {
   float dx = b.cx - a.cx, dy = b.cy - a.cy;
   float c = fabsf(a.ux * b.ux + a.uy * b.uy);
   float s = fabsf(a.ux * b.uy - a.uy * b.ux);
@@ -184,7 +220,7 @@ V3_HD_OUTLINE bool rect_overlap(const Rect& a, const Rect& b) {
   return true;
 }
 
-V3_HD float ray_rect(float ox, float oy, float dx, float dy, const Rect& r) {
+PGS_HD float ray_rect(float ox, float oy, float dx, float dy, const Rect& r) {
   float px = ox - r.cx, py = oy - r.cy;
   float lo0 = px * r.ux + py * r.uy, lo1 = -px * r.uy + py * r.ux;
   float ld0 = dx * r.ux + dy * r.uy, ld1 = -dx * r.uy + dy * r.ux;
@@ -211,20 +247,20 @@ V3_HD float ray_rect(float ox, float oy, float dx, float dy, const Rect& r) {
   return t0;
 }
 
-V3_HD void project(float hx, float hy, float vx, float vy, float& fwd, float& side) {  // base_vehicle.py:460-475
+PGS_HD void project(float hx, float hy, float vx, float vy, float& fwd, float& side) {  // base_vehicle.py:460-475
   const float n = 1.0f + 1e-6f;
   fwd = (vx * hx + vy * hy) / n;
   side = (vx * -hy + vy * hx) / n;
 }
 
-V3_HD float pid(float& p_err, float& i_err, float kp, float ki, float kd, float err) {  // PID_controller.py
+PGS_HD float pid(float& p_err, float& i_err, float kp, float ki, float kd, float err) {  // PID_controller.py
   i_err += err;
   float d = err - p_err;
   p_err = err;
   return -kp * p_err - ki * i_err - kd * d;
 }
 
-V3_HD float kmh(float v) { return clipf(v * 3.6f, 0.0f, 100000.0f); }  // base_vehicle.py:395-401
+PGS_HD float kmh(float v) { return clipf(v * 3.6f, 0.0f, 100000.0f); }  // base_vehicle.py:395-401
 
 struct Veh {  // one vehicle, in registers while its owner works on it
   float x, y, h, v, yaw, steer, throttle, hp, hi, lp, li, tspeed;
@@ -233,88 +269,95 @@ struct Veh {  // one vehicle, in registers while its owner works on it
 };
 
 struct Sub {  // what one physics sub-step needs, hoisted out of the sub-step loop
-  float accel, brake_dv, sb, mu_g, lr;
+  float accel;     // > 0: engine acceleration [m/s^2]; else brake
+  float brake_dv;  // speed removed per sub-step when braking
+  float k_yaw;     // kinematic yaw rate per unit speed: sin(slip angle) / lr
+  float k_relax;   // dt / tau of the yaw-rate relaxation
+  float mu_g, lr;
 };
 
-V3_HD_OUTLINE void substep(Veh& q, const Sub& sub, float dt) {  // planar stand-in for BulletVehicle
+PGS_HD void substep(Veh& q, const Sub& sub, float dt) {  // planar stand-in for BulletVehicle
   float speed = q.v;
   if (sub.accel > 0.0f) speed += sub.accel * dt;
   else speed = fmaxf(speed - sub.brake_dv, 0.0f);
-  float yaw = q.yaw + (speed * sub.sb / sub.lr - q.yaw) * (dt / V3_YAW_TAU);
+  // yaw rate relaxes towards the kinematic-bicycle value (tyre relaxation + yaw inertia, tau = 0.1 s) ...
+  float yaw = q.yaw + (speed * sub.k_yaw - q.yaw) * sub.k_relax;
+  // ... and the tyres cannot give more than mu * g of lateral acceleration
   if (speed * fabsf(yaw) > sub.mu_g) yaw = copysignf(sub.mu_g / speed, yaw);
   const float sb = speed > 1e-3f ? clipf(yaw * sub.lr / speed, -1.0f, 1.0f) : 0.0f;
   const float cb = sqrtf(fmaxf(1.0f - sb * sb, 0.0f));
   q.x += speed * (q.hc * cb - q.hs * sb) * dt;
   q.y += speed * (q.hs * cb + q.hc * sb) * dt;
   float nh = q.h + yaw * dt;
-  if (nh > V3_PI) nh -= V3_TWO_PI;
-  if (nh < -V3_PI) nh += V3_TWO_PI;
+  if (nh > PGS_PI) nh -= PGS_TWO_PI;
+  if (nh < -PGS_PI) nh += PGS_TWO_PI;
   q.yaw = yaw;
-  if (nh != q.h) V3_SINCOS(nh, q.hs, q.hc);
+  if (nh != q.h) PGS_SINCOS(nh, q.hs, q.hc);
   q.h = nh;
   q.v = speed;
 }
 
-V3_HD Sub make_sub(const Veh& q, const PgdSlot& t, float dt) {  // base_vehicle.py:343-376
+PGS_HD Sub make_sub(const Veh& q, const PgdSlot& t, float dt) {  // base_vehicle.py:343-376
   Sub sub;
-  sub.mu_g = t.friction * V3_GRAVITY;
+  sub.mu_g = t.friction * PGS_GRAVITY;
   sub.lr = t.lr;
-  const bool overspeed = kmh(q.v) > V3_MAX_SPEED_KMH;
-  if (q.throttle > 0.0f && !overspeed) {
+  sub.k_relax = dt / PGS_YAW_TAU;
+  const bool overspeed = kmh(q.v) > PGS_MAX_SPEED_KMH;
+  if (q.throttle > 0.0f && !overspeed) {  // engine force on 4 wheels; Bullet ignores the brake when it is non-zero
     sub.accel = fminf(4.0f * t.max_engine * q.throttle / t.mass, sub.mu_g);
     sub.brake_dv = 0.0f;
-  } else {
+  } else {  // per-wheel brake impulse: 2.0 idle, |throttle| * max_brake_force when braking
     sub.accel = 0.0f;
     const float imp = q.throttle >= 0.0f ? 2.0f : -q.throttle * t.max_brake;
     sub.brake_dv = fminf(4.0f * imp / t.mass, sub.mu_g * dt);
   }
-  const float delta = clipf(-q.steer * t.max_steer, -1.4f, 1.4f);
+  const float delta = clipf(-q.steer * t.max_steer, -1.4f, 1.4f);  // +steering = left = heading decreases
   const float tb = t.lr / (t.lf + t.lr) * pgd_tanf(delta);
-  sub.sb = tb / sqrtf(1.0f + tb * tb);
+  sub.k_yaw = tb / sqrtf(1.0f + tb * tb) / t.lr;
   return sub;
 }
 
 // ---- shared memory ------------------------------------------------------------------------------------------------
 template <int V>
 struct Pub {  // public per-slot state, [slot][lane]; lf = lane << 8 | PGD_V_* flags
-  float x[V][V3_LANES], y[V][V3_LANES], hc[V][V3_LANES], hs[V][V3_LANES], v[V][V3_LANES];
-  int lf[V][V3_LANES];
+  float x[V][PGS_LANES], y[V][PGS_LANES], hc[V][PGS_LANES], hs[V][PGS_LANES], v[V][PGS_LANES];
+  int lf[V][PGS_LANES];
 };
-V3_HD int lf_pack(int lane, int fl) { return (lane << 8) | (fl & 0xff); }
-V3_HD int lf_lane(int lf) { return lf >> 8; }
+PGS_HD int lf_pack(int lane, int fl) { return (lane << 8) | (fl & 0xff); }
+PGS_HD int lf_lane(int lf) { return lf >> 8; }
 
 template <int V>
 struct IdmPub {  // IDM look-up data of every vehicle (phase B -> C); shares its storage with the observation rows
-  float olong[V][V3_LANES], lsx[V][V3_LANES], lsy[V][V3_LANES], lex[V][V3_LANES], ley[V][V3_LANES],
-      llen[V][V3_LANES];
+  float olong[V][PGS_LANES], lsx[V][PGS_LANES], lsy[V][PGS_LANES], lex[V][PGS_LANES], ley[V][PGS_LANES],
+      llen[V][PGS_LANES];
 };
 
 /* Dynamic shared memory: [Smem, fixed part][rows: 32 x obs_dim floats in HBM layout; phases B, C: IdmPub][tv: phases
  * C, D the ego's pose (x, y, cos, sin) after every sub-step, F4 [ns][32]; phases F, L the visible chassis, int [V][32]:
  * slot | first beam << 8 | beam count << 16]. */
-typedef F4 (*TrajPtr)[V3_LANES];
-typedef int (*VisPtr)[V3_LANES];
+typedef F4 (*TrajPtr)[PGS_LANES];
+typedef int (*VisPtr)[PGS_LANES];
 template <int V, int R>
 struct Smem {
   Pub<V> p;
-  F4 efin[V3_LANES];                     // ego pose after the sub-steps (template pose when the episode restarts)
-  int scan[R][4][V3_LANES];              // ego bucket scan, one share per role: b_any, b_cur, b_next, PGD_F_* flags
-  int amask[R][V3_LANES], pmask[R][V3_LANES], crash[R][V3_LANES];  // one word per role: no atomics, no clearing
-  float last_x[V3_LANES], last_y[V3_LANES], ego_travel[V3_LANES], ego_h[V3_LANES], ego_v[V3_LANES],
-      ego_hl[V3_LANES], ego_hw[V3_LANES];
-  int ego_ck[V3_LANES], n_vis[V3_LANES], wrote[V3_LANES];
+  F4 efin[PGS_LANES];                     // ego pose after the sub-steps (template pose when the episode restarts)
+  int scan[R][4][PGS_LANES];              // ego bucket scan, one share per role: b_any, b_cur, b_next, PGD_F_* flags
+  int amask[R][PGS_LANES], pmask[R][PGS_LANES], crash[R][PGS_LANES];  // one word per role: no atomics, no clearing
+  float last_x[PGS_LANES], last_y[PGS_LANES], ego_travel[PGS_LANES], ego_h[PGS_LANES], ego_v[PGS_LANES],
+      ego_hl[PGS_LANES], ego_hw[PGS_LANES];
+  int ego_ck[PGS_LANES], n_vis[PGS_LANES], wrote[PGS_LANES];
 };
 
 template <int V, int R>
-V3_HD constexpr size_t smem_obs_offset() { return (sizeof(Smem<V, R>) + 127) / 128 * 128; }
+PGS_HD constexpr size_t smem_obs_offset() { return (sizeof(Smem<V, R>) + 127) / 128 * 128; }
 template <int V, int R>
-V3_HD size_t smem_tv_offset(int obs_dim) {
-  const size_t rows = (size_t)V3_LANES * obs_dim * sizeof(float);
+PGS_HD size_t smem_tv_offset(int obs_dim) {
+  const size_t rows = (size_t)PGS_LANES * obs_dim * sizeof(float);
   return smem_obs_offset<V, R>() + ((rows > sizeof(IdmPub<V>) ? rows : sizeof(IdmPub<V>)) + 127) / 128 * 128;
 }
 template <int V, int R>
-V3_HD size_t smem_bytes(int obs_dim, int substeps) {
-  const size_t traj = (size_t)substeps * V3_LANES * sizeof(F4), vis = (size_t)V * V3_LANES * sizeof(int);
+PGS_HD size_t smem_bytes(int obs_dim, int substeps) {
+  const size_t traj = (size_t)substeps * PGS_LANES * sizeof(F4), vis = (size_t)V * PGS_LANES * sizeof(int);
   return smem_tv_offset<V, R>(obs_dim) + (traj > vis ? traj : vis);
 }
 
@@ -340,29 +383,29 @@ struct Thr {  // what a thread keeps across the phases
   int pre_fl[MAXOWN], pre_air[MAXOWN];  // traffic roles: flags / drop counters of the slots they publish
 };
 
-V3_HD int imin(int a, int b) { return a < b ? a : b; }
-V3_HD int ctz32(uint32_t m) {
+PGS_HD int imin(int a, int b) { return a < b ? a : b; }
+PGS_HD int ctz32(uint32_t m) {
 #ifdef __CUDA_ARCH__
   return __ffs((int)m) - 1;
 #else
   return __builtin_ctz(m);
 #endif
 }
-V3_HD uint32_t drop_low(uint32_t m, int n) {  // clear the n lowest set bits
+PGS_HD uint32_t drop_low(uint32_t m, int n) {  // clear the n lowest set bits
   for (int i = 0; i < n && m; ++i) m &= m - 1;
   return m;
 }
 
-V3_HD void veh_from_template(Veh& q, const PgdSlot& t, int s) {
+PGS_HD void veh_from_template(Veh& q, const PgdSlot& t, int s) {
   q.x = t.x; q.y = t.y; q.h = t.heading; q.v = 0.0f; q.yaw = 0.0f;
   q.steer = q.throttle = q.hp = q.hi = q.lp = q.li = 0.0f;
-  q.tspeed = V3_IDM_NORMAL_SPEED;
+  q.tspeed = PGS_IDM_NORMAL_SPEED;
   q.lane = t.lane; q.ck0 = 0; q.ck1 = t.route_len > 2 ? 1 : 0; q.rt_lane = -1;
   q.timer = t.overtake_timer; q.rnd_n = 0; q.airborne = t.drop_substeps;
   q.vflags = PGD_V_ALIVE | PGD_V_ON_LANE | (s == 0 ? PGD_V_ACTIVE : 0);
 }
 
-V3_HD void veh_unpack(Veh& q, const F4& p, const F4& c, const F4& l, const I4& n, const I4& m) {
+PGS_HD void veh_unpack(Veh& q, const F4& p, const F4& c, const F4& l, const I4& n, const I4& m) {
   q.x = p.x; q.y = p.y; q.h = p.z; q.v = p.w;
   q.steer = c.x; q.throttle = c.y; q.hp = c.z; q.hi = c.w;
   q.lp = l.x; q.li = l.y; q.tspeed = l.z; q.yaw = l.w;
@@ -370,26 +413,26 @@ V3_HD void veh_unpack(Veh& q, const F4& p, const F4& c, const F4& l, const I4& n
   q.rnd_n = m.x; q.airborne = m.y; q.vflags = m.z;
 }
 
-V3_HD void veh_load(Veh& q, const State& S, size_t gi) {
+PGS_HD void veh_load(Veh& q, const State& S, size_t gi) {
   const F4 p = S.pose[gi], c = S.ctrl[gi], l = S.pidl[gi];
   const I4 n = S.nav[gi], m = S.misc[gi];
   veh_unpack(q, p, c, l, n, m);
 }
 
-V3_HD void veh_store(const Veh& q, const State& S, size_t gi) {
+PGS_HD void veh_store(const Veh& q, const State& S, size_t gi) {
   const F4 p = {q.x, q.y, q.h, q.v}, c = {q.steer, q.throttle, q.hp, q.hi}, l = {q.lp, q.li, q.tspeed, q.yaw};
   const I4 n = {q.lane, q.ck0 | (q.ck1 << 16), q.rt_lane, q.timer}, m = {q.rnd_n, q.airborne, q.vflags, 0};
   S.pose[gi] = p; S.ctrl[gi] = c; S.pidl[gi] = l; S.nav[gi] = n; S.misc[gi] = m;
 }
 
 template <int V, int R>
-V3_HD IdmPub<V>& idm_of(float* obs) { return *reinterpret_cast<IdmPub<V>*>(obs); }
+PGS_HD IdmPub<V>& idm_of(float* obs) { return *reinterpret_cast<IdmPub<V>*>(obs); }
 template <int V, int R>
-V3_HD const IdmPub<V>& idm_of(const float* obs) { return *reinterpret_cast<const IdmPub<V>*>(obs); }
+PGS_HD const IdmPub<V>& idm_of(const float* obs) { return *reinterpret_cast<const IdmPub<V>*>(obs); }
 
 // ---- thread set-up ---------------------------------------------------------------------------------------------------
 template <int V, int R>
-V3_HD void thread_init(Thr<V, R>& th, const Tables& T, const State& S, const PgdConfig& cfg, int mode, int lane,
+PGS_HD void thread_init(Thr<V, R>& th, const Tables& T, const State& S, const PgdConfig& cfg, int mode, int lane,
                        int role, int env, int env_end) {
   th.lane = lane; th.role = role; th.env = env; th.num_envs = cfg.num_envs;
   th.valid = env < env_end;
@@ -414,7 +457,7 @@ V3_HD void thread_init(Thr<V, R>& th, const Tables& T, const State& S, const Pgd
       th.pre_air[k] = m.y;
     }
   }
-  const bool pending = th.envi.z == V3_DONE_PENDING_RESET;
+  const bool pending = th.envi.z == PGS_DONE_PENDING_RESET;
   if (mode == 1) {
     th.fresh = pending;
     if (!pending) { th.valid = false; return; }  // the reset pass only touches environments marked for it
@@ -438,7 +481,7 @@ V3_HD void thread_init(Thr<V, R>& th, const Tables& T, const State& S, const Pgd
 
 // ---- phase A: publish start-of-step state; ego action; traffic trigger ------------------------------------------
 template <int V, int R>
-V3_HD void phase_a(Smem<V, R>& sm, Thr<V, R>& th, const State& S, const PgdConfig& cfg, const float* actions) {
+PGS_HD void phase_a(Smem<V, R>& sm, Thr<V, R>& th, const State& S, const PgdConfig& cfg, const float* actions) {
   const int ln = th.lane;
   if (th.role == 0) sm.wrote[ln] = th.valid ? 1 : 0;
   sm.amask[th.role][ln] = 0;
@@ -458,7 +501,7 @@ V3_HD void phase_a(Smem<V, R>& sm, Thr<V, R>& th, const State& S, const PgdConfi
     else veh_unpack(q, th.pre_pose, th.pre_ctrl, th.pre_pidl, th.pre_nav, th.pre_misc);
     q.hl = t.length * 0.5f;
     q.hw = t.width * 0.5f;
-    V3_SINCOS(q.h, q.hs, q.hc);
+    PGS_SINCOS(q.h, q.hs, q.hc);
     sm.last_x[ln] = q.x; sm.last_y[ln] = q.y;
     sm.ego_hl[ln] = q.hl; sm.ego_hw[ln] = q.hw;
     sm.ego_ck[ln] = q.ck0 | (q.ck1 << 16);
@@ -512,7 +555,7 @@ V3_HD void phase_a(Smem<V, R>& sm, Thr<V, R>& th, const State& S, const PgdConfi
       }
     }
     float sn, cs;
-    V3_SINCOS(h, sn, cs);
+    PGS_SINCOS(h, sn, cs);
     P.x[s][ln] = x; P.y[s][ln] = y; P.hc[s][ln] = cs; P.hs[s][ln] = sn; P.v[s][ln] = v;
     P.lf[s][ln] = lf_pack(lane, fl);
     if (fl & PGD_V_ACTIVE) amask |= 1u << s;
@@ -523,14 +566,14 @@ V3_HD void phase_a(Smem<V, R>& sm, Thr<V, R>& th, const State& S, const PgdConfi
 }
 
 template <int V, int R>
-V3_HD uint32_t env_amask(const Smem<V, R>& sm, int ln) {  // alive + awake traffic slots of the environment
+PGS_HD uint32_t env_amask(const Smem<V, R>& sm, int ln) {  // alive + awake traffic slots of the environment
   uint32_t a = 0;
 #pragma unroll
   for (int r = 1; r < R; ++r) a |= (uint32_t)sm.amask[r][ln];
   return a;
 }
 template <int V, int R>
-V3_HD uint32_t env_pmask(const Smem<V, R>& sm, int ln) {  // alive + parked traffic slots
+PGS_HD uint32_t env_pmask(const Smem<V, R>& sm, int ln) {  // alive + parked traffic slots
   uint32_t a = 0;
 #pragma unroll
   for (int r = 1; r < R; ++r) a |= (uint32_t)sm.pmask[r][ln];
@@ -539,7 +582,7 @@ V3_HD uint32_t env_pmask(const Smem<V, R>& sm, int ln) {  // alive + parked traf
 
 // ---- phase B: IDM look-up data (only environments with awake traffic) --------------------------------------------
 template <int V, int R>
-V3_HD void phase_b(Smem<V, R>& sm, Thr<V, R>& th, float* obs) {
+PGS_HD void phase_b(Smem<V, R>& sm, Thr<V, R>& th, float* obs) {
   if (!th.valid || !th.stepping) return;
   const int ln = th.lane;
   if (!env_amask(sm, ln)) return;
@@ -560,7 +603,7 @@ V3_HD void phase_b(Smem<V, R>& sm, Thr<V, R>& th, float* obs) {
 
 // ---- IDM / PID action of one awake traffic vehicle (idm_policy.py:190-353) --------------------------------------
 template <int V, int R>
-V3_HD void idm_act(const Smem<V, R>& sm, const Thr<V, R>& th, const Tables& T, const float* obs, uint32_t alive,
+PGS_HD void idm_act(const Smem<V, R>& sm, const Thr<V, R>& th, const Tables& T, const float* obs, uint32_t alive,
                    Veh& q, int s) {
   const int ln = th.lane;
   const Pub<V>& P = sm.p;
@@ -608,7 +651,7 @@ V3_HD void idm_act(const Smem<V, R>& sm, const Thr<V, R>& th, const Tables& T, c
 #pragma unroll
   for (int i = 0; i < 3; ++i) {  // FrontBackObjects.get_find_front_back_objs (:83-133)
     front[i] = back[i] = -1;
-    fdist[i] = bdist[i] = V3_IDM_MAX_LONG;
+    fdist[i] = bdist[i] = PGS_IDM_MAX_LONG;
     if (cand[i] < 0) continue;
     const PgdLane l = (i == 1) ? rl : load_rec(lanes + cand[i]);
     float cur_long, lat;
@@ -619,7 +662,7 @@ V3_HD void idm_act(const Smem<V, R>& sm, const Thr<V, R>& th, const Tables& T, c
     for (uint32_t m = others; m; m &= m - 1) {  // ascending slot order, like the oracle's object list
       const int j = ctz32(m);
       const float ddx = P.x[j][ln] - q.x, ddy = P.y[j][ln] - q.y;
-      if (!(ddx * ddx + ddy * ddy < V3_LIDAR_RANGE * V3_LIDAR_RANGE)) continue;
+      if (!(ddx * ddx + ddy * ddy < PGS_LIDAR_RANGE * PGS_LIDAR_RANGE)) continue;
       if (lf_lane(P.lf[j][ln]) == cand[i]) {
         const float lg = I.olong[j][ln] - cur_long;
         if (fdist[i] > lg && lg > 0.0f) { fdist[i] = lg; front[i] = j; found_front = true; }
@@ -654,10 +697,10 @@ V3_HD void idm_act(const Smem<V, R>& sm, const Thr<V, R>& th, const Tables& T, c
         if (idx < lo || idx > hi_idx) {
           decided = true;
           const int side = idx > hi_idx ? 0 : 2;
-          if (bdist[side] < V3_IDM_SAFE_DIST || fdist[side] < 5.0f) {
-            q.tspeed = V3_IDM_CREEP_SPEED;
+          if (bdist[side] < PGS_IDM_SAFE_DIST || fdist[side] < 5.0f) {
+            q.tspeed = PGS_IDM_CREEP_SPEED;
           } else {
-            q.tspeed = V3_IDM_NORMAL_SPEED;
+            q.tspeed = PGS_IDM_NORMAL_SPEED;
             front_obj = front[side];
             front_dist = fdist[side];
             steer_lane = cur_road.first_lane + idx + (side == 0 ? -1 : 1);
@@ -667,8 +710,8 @@ V3_HD void idm_act(const Smem<V, R>& sm, const Thr<V, R>& th, const Tables& T, c
     }
     if (!decided) {
       const float my_speed = kmh(q.v);
-      if (fabsf(my_speed - V3_IDM_NORMAL_SPEED) > 3.0f && front[1] >= 0 &&
-          fabsf(kmh(P.v[front[1]][ln]) - V3_IDM_NORMAL_SPEED) > 3.0f && q.timer > V3_IDM_LANE_CHANGE_FREQ) {
+      if (fabsf(my_speed - PGS_IDM_NORMAL_SPEED) > 3.0f && front[1] >= 0 &&
+          fabsf(kmh(P.v[front[1]][ln]) - PGS_IDM_NORMAL_SPEED) > 3.0f && q.timer > PGS_IDM_LANE_CHANGE_FREQ) {
         float side_speed[3] = {0.f, 0.f, 0.f};
         bool side_ok[3] = {false, false, false};
 #pragma unroll
@@ -676,17 +719,17 @@ V3_HD void idm_act(const Smem<V, R>& sm, const Thr<V, R>& th, const Tables& T, c
           if (front[sd] >= 0) {
             side_speed[sd] = kmh(P.v[front[sd]][ln]);
             side_ok[sd] = true;
-          } else if (cand[sd] >= 0 && fdist[sd] > V3_IDM_SAFE_DIST && bdist[sd] > V3_IDM_SAFE_DIST) {
-            side_speed[sd] = V3_IDM_MAX_SPEED;
+          } else if (cand[sd] >= 0 && fdist[sd] > PGS_IDM_SAFE_DIST && bdist[sd] > PGS_IDM_SAFE_DIST) {
+            side_speed[sd] = PGS_IDM_MAX_SPEED;
             side_ok[sd] = true;
           }
         }
         const float front_speed = kmh(P.v[front[1]][ln]);
-        if (side_ok[0] && side_speed[0] - front_speed > V3_IDM_SPEED_INCREASE && idx - 1 >= lo && idx - 1 <= hi_idx) {
+        if (side_ok[0] && side_speed[0] - front_speed > PGS_IDM_SPEED_INCREASE && idx - 1 >= lo && idx - 1 <= hi_idx) {
           decided = true;
           front_obj = front[0]; front_dist = fdist[0];
           steer_lane = cur_road.first_lane + idx - 1;
-        } else if (side_ok[2] && side_speed[2] - front_speed > V3_IDM_SPEED_INCREASE && idx + 1 >= lo &&
+        } else if (side_ok[2] && side_speed[2] - front_speed > PGS_IDM_SPEED_INCREASE && idx + 1 >= lo &&
                    idx + 1 <= hi_idx) {
           decided = true;
           front_obj = front[2]; front_dist = fdist[2];
@@ -695,7 +738,7 @@ V3_HD void idm_act(const Smem<V, R>& sm, const Thr<V, R>& th, const Tables& T, c
       }
     }
     if (!decided) {
-      q.tspeed = V3_IDM_NORMAL_SPEED;
+      q.tspeed = PGS_IDM_NORMAL_SPEED;
       q.timer += 1;
     }
   }
@@ -731,11 +774,11 @@ V3_HD void idm_act(const Smem<V, R>& sm, const Thr<V, R>& th, const Tables& T, c
  * the (r-1)-th, (r-1+R-1)-th ... set bit of the mask), not by slot number: every traffic thread of an environment
  * gets the same share, so a warp's lanes run the same number of iterations. */
 template <int V, int R>
-V3_HD void phase_c(Smem<V, R>& sm, Thr<V, R>& th, const Tables& T, const State& S, const PgdConfig& cfg,
+PGS_HD void phase_c(Smem<V, R>& sm, Thr<V, R>& th, const Tables& T, const State& S, const PgdConfig& cfg,
                    const float* obs, TrajPtr traj) {
   if (!th.valid) return;
   const int ln = th.lane;
-  const int ns = cfg.decision_repeat < V3_MAX_SUBSTEPS ? cfg.decision_repeat : V3_MAX_SUBSTEPS;
+  const int ns = cfg.decision_repeat < PGS_MAX_SUBSTEPS ? cfg.decision_repeat : PGS_MAX_SUBSTEPS;
   if (th.role == 0) {
     Veh& q = th.ego;
     if (th.stepping) {  // 5 x doPhysics(0.02) of the ego (base_engine.py:206-232), remembering every pose
@@ -789,7 +832,7 @@ struct ScanOut { int b_any, b_cur, b_next; uint32_t flags; };
 /* Entries [first, ...) of the bucket of (x, y), `stride` groups of 4 apart: lane-surface boxes that contain the point
  * and run along the heading; with EGO also the chassis against line ghosts and sidewalks (base_vehicle.py:615-644). */
 template <bool EGO>
-V3_HD void bucket_scan(const PgdMap& mp, const PgdLane* lanes, const PgdBox* boxes, const Tables& T, float x, float y,
+PGS_HD void bucket_scan(const PgdMap& mp, const PgdLane* lanes, const PgdBox* boxes, const Tables& T, float x, float y,
                        float hc, float hs, float hl, float hw, int cur_road, int next_road, int first, int stride,
                        ScanOut& out) {
   out.b_any = out.b_cur = out.b_next = INT_MAX;
@@ -843,7 +886,7 @@ V3_HD void bucket_scan(const PgdMap& mp, const PgdLane* lanes, const PgdBox* box
 /* What follows the scan: lane choice (current road, then next road, then any; lowest box id), checkpoint update
  * (_update_target_checkpoints), on-lane flag. */
 template <int V, int R>
-V3_HD void after_scan(const Thr<V, R>& th, const Tables& T, const PgdSlot& t, const ScanOut& sc, float x, float y,
+PGS_HD void after_scan(const Thr<V, R>& th, const Tables& T, const PgdSlot& t, const ScanOut& sc, float x, float y,
                       int& lane, int& ck0, int& ck1, bool& on_lane) {
   const int32_t* rnodes = T.route_nodes + t.route_off;
   const int nb = sc.b_cur != INT_MAX ? sc.b_cur : (sc.b_next != INT_MAX ? sc.b_next : sc.b_any);
@@ -868,7 +911,7 @@ V3_HD void after_scan(const Thr<V, R>& th, const Tables& T, const PgdSlot& t, co
 }
 
 template <int V, int R>
-V3_HD void localise_traffic(const Thr<V, R>& th, const Tables& T, Veh& q, int s) {
+PGS_HD void localise_traffic(const Thr<V, R>& th, const Tables& T, Veh& q, int s) {
   const PgdSlot& t = th.tpl[s];
   const int32_t* rroads = T.route_roads + t.route_off;
   const int cur_road = ldg(&rroads[q.ck0]);
@@ -882,7 +925,7 @@ V3_HD void localise_traffic(const Thr<V, R>& th, const Tables& T, Veh& q, int s)
 
 /* The ego's share of phase F that every reader of its lane / checkpoints needs: combine the roles' scan shares. */
 template <int V, int R>
-V3_HD void ego_after_scan(const Smem<V, R>& sm, const Thr<V, R>& th, const Tables& T, int& lane, int& ck0, int& ck1,
+PGS_HD void ego_after_scan(const Smem<V, R>& sm, const Thr<V, R>& th, const Tables& T, int& lane, int& ck0, int& ck1,
                           bool& on_lane, uint32_t& flags) {
   const int ln = th.lane;
   ScanOut sc = {INT_MAX, INT_MAX, INT_MAX, 0u};
@@ -904,7 +947,7 @@ V3_HD void ego_after_scan(const Smem<V, R>& sm, const Thr<V, R>& th, const Table
 // ---- phase D: every role: its share of the ego's bucket scan;  traffic roles: sub-steps, chassis contact against
 // the ego's trajectory, after_step of their vehicles -----------------------------------------------------------------
 template <int V, int R>
-V3_HD void phase_d(Smem<V, R>& sm, Thr<V, R>& th, const Tables& T, const State& S, const PgdConfig& cfg,
+PGS_HD void phase_d(Smem<V, R>& sm, Thr<V, R>& th, const Tables& T, const State& S, const PgdConfig& cfg,
                    TrajPtr traj) {
   if (!th.valid) return;
   const int ln = th.lane;
@@ -922,7 +965,7 @@ V3_HD void phase_d(Smem<V, R>& sm, Thr<V, R>& th, const Tables& T, const State& 
     sm.scan[th.role][3][ln] = (int)sc.flags;
   }
   if (th.role == 0 || !th.stepping) return;
-  const int ns = cfg.decision_repeat < V3_MAX_SUBSTEPS ? cfg.decision_repeat : V3_MAX_SUBSTEPS;
+  const int ns = cfg.decision_repeat < PGS_MAX_SUBSTEPS ? cfg.decision_repeat : PGS_MAX_SUBSTEPS;
   int crash = 0;
   const uint32_t amask = env_amask(sm, ln), pmask = env_pmask(sm, ln);
   // parked traffic (the slots this role published in phase A, whose drop counters it already holds): only the drop
@@ -988,7 +1031,7 @@ V3_HD void phase_d(Smem<V, R>& sm, Thr<V, R>& th, const Tables& T, const State& 
 }
 
 // ---- phase F: ego bookkeeping, one task per role ---------------------------------------------------------------------
-V3_HD int obs_dim_of(const PgdConfig& cfg) {
+PGS_HD int obs_dim_of(const PgdConfig& cfg) {
   return (cfg.n_side > 0 ? cfg.n_side : 2) + 6 + cfg.n_lane_line + (cfg.random_agent_model ? 2 : 0) + 10 + 16 +
          PGD_LIDAR_BEAMS;
 }
@@ -996,7 +1039,7 @@ V3_HD int obs_dim_of(const PgdConfig& cfg) {
 /* task 0 (role 0): lane + checkpoints, route distances, arrival, reward / cost / done, state observation, info, ego
  * state store */
 template <int V, int R>
-V3_HD void task_reward(Smem<V, R>& sm, Thr<V, R>& th, const Tables& T, const State& S, const PgdConfig& cfg, int mode,
+PGS_HD void task_reward(Smem<V, R>& sm, Thr<V, R>& th, const Tables& T, const State& S, const PgdConfig& cfg, int mode,
                        float* obs, float* reward, uint8_t* done, PgdInfo* info) {
   const int ln = th.lane;
   Veh& ego = th.ego;
@@ -1056,13 +1099,13 @@ V3_HD void task_reward(Smem<V, R>& sm, Thr<V, R>& th, const Tables& T, const Sta
     obs[0] = clipf(to_left / 18.0f, 0.0f, 1.0f);
     obs[1] = clipf(to_right / 18.0f, 0.0f, 1.0f);
   }
-  st[3] = clipf((sp + 1.0f) / (V3_MAX_SPEED_KMH + 1.0f), 0.0f, 1.0f);
+  st[3] = clipf((sp + 1.0f) / (PGS_MAX_SPEED_KMH + 1.0f), 0.0f, 1.0f);
   st[4] = clipf((ego.steer / 60.0f + 1.0f) / 2.0f, 0.0f, 1.0f);
   st[5] = clipf((th.envf.x + 1.0f) / 2.0f, 0.0f, 1.0f);
   st[6] = clipf((th.envf.y + 1.0f) / 2.0f, 0.0f, 1.0f);
   // yaw rate: arccos(clip(cos(angle between headings), 0, 1)) / 0.1 (state_obs.py:87-94) = min(|wrapped heading
   // change|, pi/2) / 0.1 without the ill-conditioned arccos
-  st[7] = clipf(fminf(fabsf(pgd_wrap_to_pi(ego.h - last_h)), V3_PI / 2) / 0.1f, 0.0f, 1.0f);
+  st[7] = clipf(fminf(fabsf(pgd_wrap_to_pi(ego.h - last_h)), PGS_PI / 2) / 0.1f, 0.0f, 1.0f);
   float r = 0.0f, step_reward = 0.0f, cost = 0.0f, step_energy = 0.0f;
   int is_done = 0;
   if (!th.fresh) {  // envs/pgdrive_env.py:162-258
@@ -1070,7 +1113,7 @@ V3_HD void task_reward(Smem<V, R>& sm, Thr<V, R>& th, const Tables& T, const Sta
     float lateral_factor = 1.0f;
     if (cfg.use_lateral) lateral_factor = clipf(1.0f - 2.0f * fabsf(lat_now) / mp.lane_width, 0.0f, 1.0f);
     r += cfg.driving_reward * (long_now - long_last) * lateral_factor * sign;
-    r += cfg.speed_reward * (sp / V3_MAX_SPEED_KMH) * sign;
+    r += cfg.speed_reward * (sp / PGS_MAX_SPEED_KMH) * sign;
     step_reward = r;
     if (flags & PGD_F_ARRIVE_DEST) r = cfg.success_reward;
     else if (out_of_road) r = -cfg.out_of_road_penalty;
@@ -1108,7 +1151,7 @@ V3_HD void task_reward(Smem<V, R>& sm, Thr<V, R>& th, const Tables& T, const Sta
 
 /* task 1: navigation info of the two checkpoints (navigation.py:213-260) + heading_diff (base_vehicle.py:433-458) */
 template <int V, int R>
-V3_HD void task_navi(const Smem<V, R>& sm, const Thr<V, R>& th, const Tables& T, const PgdConfig& cfg, float* obs) {
+PGS_HD void task_navi(const Smem<V, R>& sm, const Thr<V, R>& th, const Tables& T, const PgdConfig& cfg, float* obs) {
   const int ln = th.lane;
   const PgdMap& mp = th.mp;
   const F4 e = sm.efin[ln];
@@ -1145,7 +1188,7 @@ V3_HD void task_navi(const Smem<V, R>& sm, const Thr<V, R>& th, const Tables& T,
     q[1] = clipf((ps / 50.0f + 1.0f) / 2.0f, 0.0f, 1.0f);
     q[2] = clipf(bend, 0.0f, 1.0f);
     q[3] = clipf((dir + 1.0f) / 2.0f, 0.0f, 1.0f);
-    q[4] = clipf((angle * (180.0f / V3_PI) / 135.0f + 1.0f) / 2.0f, 0.0f, 1.0f);
+    q[4] = clipf((angle * (180.0f / PGS_PI) / 135.0f + 1.0f) / 2.0f, 0.0f, 1.0f);
   }
   {  // heading_diff against the right-most reference lane
     const PgdLane l = load_rec(th.lanes + (cur_road.first_lane + cur_road.n_lanes - 1));
@@ -1160,7 +1203,7 @@ V3_HD void task_navi(const Smem<V, R>& sm, const Thr<V, R>& th, const Tables& T,
 
 /* task 2: the 4 nearest vehicles inside the 50 m cylinder (lidar.py:55-77; ties -> lower slot) */
 template <int V, int R>
-V3_HD void task_neighbours(const Smem<V, R>& sm, const Thr<V, R>& th, const PgdConfig& cfg, float* obs) {
+PGS_HD void task_neighbours(const Smem<V, R>& sm, const Thr<V, R>& th, const PgdConfig& cfg, float* obs) {
   const int ln = th.lane;
   const Pub<V>& P = sm.p;
   const F4 e = sm.efin[ln];
@@ -1173,7 +1216,7 @@ V3_HD void task_neighbours(const Smem<V, R>& sm, const Thr<V, R>& th, const PgdC
   for (int s = 1; s < th.n_slots; ++s) {
     if (!(P.lf[s][ln] & PGD_V_ALIVE)) continue;
     const float dx = P.x[s][ln] - ex, dy = P.y[s][ln] - ey;
-    if (dx * dx + dy * dy < V3_LIDAR_RANGE * V3_LIDAR_RANGE) cand |= 1u << s;
+    if (dx * dx + dy * dy < PGS_LIDAR_RANGE * PGS_LIDAR_RANGE) cand |= 1u << s;
   }
 #pragma unroll 1
   for (int rank = 0; rank < 4; ++rank) {
@@ -1196,16 +1239,16 @@ V3_HD void task_neighbours(const Smem<V, R>& sm, const Thr<V, R>& th, const PgdC
     project(ehc, ehs, P.x[best][ln] - ex, P.y[best][ln] - ey, pf, ps);
     const float ws = kmh(P.v[best][ln]);
     project(ehc, ehs, ws * P.hc[best][ln] - esp * ehc, ws * P.hs[best][ln] - esp * ehs, vf, vs);
-    o4[0] = clipf((pf / V3_LIDAR_RANGE + 1.0f) / 2.0f, 0.0f, 1.0f);
-    o4[1] = clipf((ps / V3_LIDAR_RANGE + 1.0f) / 2.0f, 0.0f, 1.0f);
-    o4[2] = clipf((vf / V3_MAX_SPEED_KMH + 1.0f) / 2.0f, 0.0f, 1.0f);
-    o4[3] = clipf((vs / V3_MAX_SPEED_KMH + 1.0f) / 2.0f, 0.0f, 1.0f);
+    o4[0] = clipf((pf / PGS_LIDAR_RANGE + 1.0f) / 2.0f, 0.0f, 1.0f);
+    o4[1] = clipf((ps / PGS_LIDAR_RANGE + 1.0f) / 2.0f, 0.0f, 1.0f);
+    o4[2] = clipf((vf / PGS_MAX_SPEED_KMH + 1.0f) / 2.0f, 0.0f, 1.0f);
+    o4[3] = clipf((vs / PGS_MAX_SPEED_KMH + 1.0f) / 2.0f, 0.0f, 1.0f);
   }
 }
 
 /* task 3: which chassis the lidar can reach, and the (conservative) arc of beams that can hit each */
 template <int V, int R>
-V3_HD void task_lidar_windows(Smem<V, R>& sm, const Thr<V, R>& th, VisPtr vis) {
+PGS_HD void task_lidar_windows(Smem<V, R>& sm, const Thr<V, R>& th, VisPtr vis) {
   const int ln = th.lane;
   const Pub<V>& P = sm.p;
   const F4 e = sm.efin[ln];
@@ -1216,16 +1259,16 @@ V3_HD void task_lidar_windows(Smem<V, R>& sm, const Thr<V, R>& th, VisPtr vis) {
     if (!(P.lf[s][ln] & PGD_V_ALIVE)) continue;
     const float dx = P.x[s][ln] - ex, dy = P.y[s][ln] - ey;
     const float d2 = dx * dx + dy * dy;
-    if (!(d2 < (V3_LIDAR_RANGE + 8.0f) * (V3_LIDAR_RANGE + 8.0f))) continue;  // no chassis has an 8 m half-diagonal
+    if (!(d2 < (PGS_LIDAR_RANGE + 8.0f) * (PGS_LIDAR_RANGE + 8.0f))) continue;  // no chassis has an 8 m half-diagonal
     const PgdSlot& t = th.tpl[s];
     const float hl = t.length * 0.5f, hw = t.width * 0.5f;
     const float hd = sqrtf(hl * hl + hw * hw);
-    const float reach = V3_LIDAR_RANGE + hd;
+    const float reach = PGS_LIDAR_RANGE + hd;
     if (!(d2 < reach * reach)) continue;
     const float d = sqrtf(d2);
     int blo = 0, bn = PGD_LIDAR_BEAMS - 1;
     if (d > hd * 1.001f) {
-      const float per_rad = (float)PGD_LIDAR_BEAMS / V3_TWO_PI;
+      const float per_rad = (float)PGD_LIDAR_BEAMS / PGS_TWO_PI;
       const float c = (pgd_atan2f(dy, dx) - eh) * per_rad;
       const float w = pgd_asinf(fminf(hd / d, 1.0f)) * per_rad;
       const int nn = (int)ceilf(2.0f * w) + 3;
@@ -1244,7 +1287,7 @@ V3_HD void task_lidar_windows(Smem<V, R>& sm, const Thr<V, R>& th, VisPtr vis) {
  * looks up the bucket of a point every 8 m along itself (buckets list every box within 4 m of them).  The rays of an
  * environment are spread over the roles. */
 template <int V, int R>
-V3_HD void task_detectors(const Smem<V, R>& sm, const Thr<V, R>& th, const Tables& T, const PgdConfig& cfg,
+PGS_HD void task_detectors(const Smem<V, R>& sm, const Thr<V, R>& th, const Tables& T, const PgdConfig& cfg,
                           float* obs) {
   const int ln = th.lane;
   const PgdMap& mp = th.mp;
@@ -1259,9 +1302,9 @@ V3_HD void task_detectors(const Smem<V, R>& sm, const Thr<V, R>& th, const Table
     const int i = side ? rI : rI - cfg.n_side;
     const int n = side ? cfg.n_side : cfg.n_lane_line;
     const float dist = side ? cfg.side_distance : cfg.lane_line_distance;
-    const float ang = (float)i * (V3_TWO_PI / (float)n) + V3_PI / 2 + eh;
+    const float ang = (float)i * (PGS_TWO_PI / (float)n) + PGS_PI / 2 + eh;
     float sn, cs;
-    V3_SINCOS(ang, sn, cs);
+    PGS_SINCOS(ang, sn, cs);
     const float dx = cs * dist, dy = sn * dist;
     float best = 1.0f;
     for (float sd = 4.0f; sd - 4.0f < dist; sd += 8.0f) {
@@ -1285,7 +1328,7 @@ V3_HD void task_detectors(const Smem<V, R>& sm, const Thr<V, R>& th, const Table
 }
 
 template <int V, int R>
-V3_HD void phase_f(Smem<V, R>& sm, Thr<V, R>& th, const Tables& T, const State& S, const PgdConfig& cfg, int mode,
+PGS_HD void phase_f(Smem<V, R>& sm, Thr<V, R>& th, const Tables& T, const State& S, const PgdConfig& cfg, int mode,
                    int obs_dim, float* obs_rows, VisPtr vis, float* reward, uint8_t* done, PgdInfo* info) {
   if (!th.valid) return;
   float* obs = obs_rows + (size_t)th.lane * obs_dim;
@@ -1302,7 +1345,7 @@ V3_HD void phase_f(Smem<V, R>& sm, Thr<V, R>& th, const Tables& T, const State& 
 // ---- phase L: lidar as a scatter (cutils.pyx:60-142 restated per chassis instead of per beam) ---------------------
 /* Thread (role, lane) of the CTA: the warp `role` takes environments role, role + R, ...; its lanes are the beams
  * of the window of each visible chassis.  The row was pre-filled with 1.0 (no hit); hits are min-ed in. */
-V3_HD void lidar_min(float* cell, float t) {
+PGS_HD void lidar_min(float* cell, float t) {
 #ifdef __CUDA_ARCH__
   atomicMin(reinterpret_cast<int*>(cell), __float_as_int(t));  // non-negative floats order like their bit patterns
 #else
@@ -1311,12 +1354,12 @@ V3_HD void lidar_min(float* cell, float t) {
 }
 
 template <int V, int R>
-V3_HD void phase_l(const Smem<V, R>& sm, const Tables& T, const State& S, int role, int lane, int num_envs, int env0,
+PGS_HD void phase_l(const Smem<V, R>& sm, const Tables& T, const State& S, int role, int lane, int num_envs, int env0,
                    int obs_dim, float* obs_rows, VisPtr vis) {
   const Pub<V>& P = sm.p;
   const int head = obs_dim - PGD_LIDAR_BEAMS;
 #pragma unroll 1
-  for (int e = role; e < V3_LANES; e += R) {
+  for (int e = role; e < PGS_LANES; e += R) {
     if (!sm.wrote[e]) continue;
     const int nv = sm.n_vis[e];
     if (nv == 0) continue;
@@ -1331,18 +1374,18 @@ V3_HD void phase_l(const Smem<V, R>& sm, const Tables& T, const State& S, int ro
       const Rect r = {P.x[s][e], P.y[s][e], P.hc[s][e], P.hs[s][e], ldg(&tpl[s].length) * 0.5f,
                       ldg(&tpl[s].width) * 0.5f};
 #pragma unroll 1
-      for (int rel = lane; rel <= bn; rel += V3_LANES) {
+      for (int rel = lane; rel <= bn; rel += PGS_LANES) {
         int i = blo + rel;
         if (i >= PGD_LIDAR_BEAMS) i -= PGD_LIDAR_BEAMS;
-        const float ang = (float)i * (V3_TWO_PI / (float)PGD_LIDAR_BEAMS) + eh;
+        const float ang = (float)i * (PGS_TWO_PI / (float)PGD_LIDAR_BEAMS) + eh;
         float sn, cs;
-        V3_SINCOS(ang, sn, cs);
-        const float t = ray_rect(ex, ey, cs * V3_LIDAR_RANGE, sn * V3_LIDAR_RANGE, r);
+        PGS_SINCOS(ang, sn, cs);
+        const float t = ray_rect(ex, ey, cs * PGS_LIDAR_RANGE, sn * PGS_LIDAR_RANGE, r);
         if (t < 1.0f) lidar_min(row + i, t);
       }
     }
   }
 }
 
-}  // namespace pgdv3
+}  // namespace pgdstep
 #endif

@@ -1,45 +1,48 @@
-// Role per warp / environment per lane: kernel wrapper around pgd_step_v3.cuh (PgdConfig.layout = 2).
+// Role per warp / environment per lane: kernel wrapper around pgd_step.cuh .
 //
-// A CTA = R warps x 32 lanes advances 32 environments (see the header of pgd_step_v3.cuh for the phases).  The 32
+// A CTA = R warps x 32 lanes advances 32 environments (see the header of pgd_step.cuh for the phases).  The 32
 // observation rows are assembled in shared memory in their HBM layout and leave with ONE bulk (TMA) copy per CTA
 // (cp.async.bulk.global.shared::cta, 35 KB at 274 floats per row); the destination may be a peer-mapped buffer on
 // another GPU.  CTAs that are not full (partial reset, tail) fall back to coalesced per-row stores.
 #include "pgd_internal.h"
-#include "pgd_step_v3.cuh"
+#include "pgd_step.cuh"
 
-using namespace pgdv3;
+using namespace pgdstep;
 
-#ifndef V3_ROLES
-#define V3_ROLES 4
+#ifndef PGS_ROLES
+#define PGS_ROLES 4
 #endif
-#ifndef V3_MIN_CTAS
-#define V3_MIN_CTAS 4
+#ifndef PGS_MIN_CTAS
+#define PGS_MIN_CTAS 4
+#endif
+#ifndef PGS_OBS_EVICT_FIRST
+#define PGS_OBS_EVICT_FIRST 1
 #endif
 
-#ifdef V3_PHASE_CLOCKS  // diagnostic build: cycles between the CTA barriers, summed over CTAs (thread 0 of each)
-__device__ unsigned long long g_v3_clk[16];
-#define V3_CLK(i)                                                              \
+#ifdef PGS_PHASE_CLOCKS  // diagnostic build: cycles between the CTA barriers, summed over CTAs (thread 0 of each)
+__device__ unsigned long long g_pgs_clk[16];
+#define PGS_CLK(i)                                                              \
   do {                                                                         \
     if (threadIdx.x == 0) {                                                    \
       const long long now_ = clock64();                                        \
-      atomicAdd(&g_v3_clk[i], (unsigned long long)(now_ - clk_));              \
+      atomicAdd(&g_pgs_clk[i], (unsigned long long)(now_ - clk_));              \
       clk_ = now_;                                                             \
     }                                                                          \
   } while (0)
 extern "C" int pgd_debug_phase_clocks(unsigned long long* out, int reset) {
-  cudaMemcpyFromSymbol(out, g_v3_clk, sizeof(g_v3_clk));
+  cudaMemcpyFromSymbol(out, g_pgs_clk, sizeof(g_pgs_clk));
   if (reset) {
     unsigned long long z[16] = {0};
-    cudaMemcpyToSymbol(g_v3_clk, z, sizeof(z));
+    cudaMemcpyToSymbol(g_pgs_clk, z, sizeof(z));
   }
   return 0;
 }
 #else
-#define V3_CLK(i)
+#define PGS_CLK(i)
 #endif
 
 template <int V, int R>
-__global__ void __launch_bounds__(R * 32, V3_MIN_CTAS) pgd_step_v3_kernel(Tables T, State S, PgdConfig cfg, int mode,
+__global__ void __launch_bounds__(R * 32, PGS_MIN_CTAS) pgd_step_kernel(Tables T, State S, PgdConfig cfg, int mode,
                                                                          int env_begin, int env_end,
                                                                          const float* __restrict__ actions,
                                                                          float* __restrict__ obs,
@@ -54,61 +57,71 @@ __global__ void __launch_bounds__(R * 32, V3_MIN_CTAS) pgd_step_v3_kernel(Tables
   TrajPtr traj = reinterpret_cast<TrajPtr>(tv);
   VisPtr vis = reinterpret_cast<VisPtr>(tv);
   const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
-  const int env0 = env_begin + blockIdx.x * V3_LANES;
-#ifdef V3_PHASE_CLOCKS
+  const int env0 = env_begin + blockIdx.x * PGS_LANES;
+#ifdef PGS_PHASE_CLOCKS
   long long clk_ = clock64();
 #endif
   Thr<V, R> th;
   thread_init(th, T, S, cfg, mode, lane, role, env0 + lane, env_end);
   if (!__syncthreads_or(th.valid)) return;  // reset pass: no environment of this CTA is marked
-  V3_CLK(0);
+  PGS_CLK(0);
   phase_a(sm, th, S, cfg, actions);
-  V3_CLK(1);
+  PGS_CLK(1);
   __syncthreads();
-  V3_CLK(2);
+  PGS_CLK(2);
   phase_b(sm, th, rows);
   __syncthreads();
-  V3_CLK(3);
+  PGS_CLK(3);
   phase_c(sm, th, T, S, cfg, rows, traj);
-  V3_CLK(4);
+  PGS_CLK(4);
   __syncthreads();
-  V3_CLK(5);
+  PGS_CLK(5);
   {  // pre-fill the rows with 1.0 = "no hit" (the IDM look-up data that shared this storage is dead now)
     float4* o4 = reinterpret_cast<float4*>(rows);
-    const int n4 = V3_LANES * obs_dim / 4;  // 32 rows: a multiple of 4 floats for every row length
+    const int n4 = PGS_LANES * obs_dim / 4;  // 32 rows: a multiple of 4 floats for every row length
     for (int i = threadIdx.x; i < n4; i += R * 32) o4[i] = make_float4(1.f, 1.f, 1.f, 1.f);
   }
-  V3_CLK(6);
+  PGS_CLK(6);
   phase_d(sm, th, T, S, cfg, traj);
-  V3_CLK(7);
+  PGS_CLK(7);
   __syncthreads();
-  V3_CLK(8);
+  PGS_CLK(8);
   phase_f(sm, th, T, S, cfg, mode, obs_dim, rows, vis, reward, done, info);
-  V3_CLK(9);
+  PGS_CLK(9);
   __syncthreads();
-  V3_CLK(10);
+  PGS_CLK(10);
   phase_l(sm, T, S, role, lane, cfg.num_envs, env0, obs_dim, rows, vis);
-  V3_CLK(11);
+  PGS_CLK(11);
   // ---- write-out -----------------------------------------------------------------------------------------------------
   const int all = __syncthreads_and(sm.wrote[lane]);
   float* dst = obs + (size_t)env0 * obs_dim;
   if (all && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
     if (threadIdx.x == 0) {
-      const uint32_t bytes = (uint32_t)(V3_LANES * obs_dim * sizeof(float));
+      const uint32_t bytes = (uint32_t)(PGS_LANES * obs_dim * sizeof(float));
       const uint32_t src = (uint32_t)__cvta_generic_to_shared(rows);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#if PGS_OBS_EVICT_FIRST
+      // the rows are written once and read by somebody else (the policy, the gather): do not let 72 MB of them per
+      // step push the tables and the 26 MB of state that the next step re-reads out of the 126 MB L2
+      uint64_t pol;
+      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst), "r"(src),
+                   "r"(bytes), "l"(pol)
+                   : "memory");
+#else
       asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes)
                    : "memory");
+#endif
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
-    V3_CLK(12);
+    PGS_CLK(12);
   } else {
-    for (int e = role; e < V3_LANES; e += R) {
+    for (int e = role; e < PGS_LANES; e += R) {
       if (!sm.wrote[e]) continue;
       const float* src = rows + (size_t)e * obs_dim;
       float* d = dst + (size_t)e * obs_dim;
-      for (int c = lane; c < obs_dim; c += 32) d[c] = src[c];
+      for (int c = lane; c < obs_dim; c += 32) __stcs(d + c, src[c]);
     }
   }
 }
@@ -119,18 +132,17 @@ static int launch_one(PgdHandle* h, const Tables& T, const State& S, int mode, i
   static int configured = 0;  // per instantiation: largest dynamic shared-memory size opted into so far
   const int smem = (int)smem_bytes<V, R>(obs_dim_of(h->cfg), h->cfg.decision_repeat);
   if (smem > configured) {
-    CU(cudaFuncSetAttribute(pgd_step_v3_kernel<V, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CU(cudaFuncSetAttribute(pgd_step_kernel<V, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = smem;
   }
-  const int grid = (env_end - env_begin + V3_LANES - 1) / V3_LANES;
-  pgd_step_v3_kernel<V, R><<<grid, R * 32, smem, st>>>(T, S, h->cfg, mode, env_begin, env_end, actions, obs, reward,
+  const int grid = (env_end - env_begin + PGS_LANES - 1) / PGS_LANES;
+  pgd_step_kernel<V, R><<<grid, R * 32, smem, st>>>(T, S, h->cfg, mode, env_begin, env_end, actions, obs, reward,
                                                        done, info);
   return 0;
 }
 
-int pgd_launch_step_v3(PgdHandle* h, int mode, int env_begin, int env_end, const float* actions, float* obs,
+int pgd_launch_step(PgdHandle* h, int mode, int env_begin, int env_end, const float* actions, float* obs,
                        float* reward, uint8_t* done, PgdInfo* info, cudaStream_t st) {
-  if (h->cfg.decision_repeat > V3_MAX_SUBSTEPS) return fail(-3, "decision_repeat > 8 is not supported");
   Tables T;
   T.maps = h->T.maps; T.lanes = h->T.lanes; T.roads = h->T.roads; T.boxes = h->T.boxes;
   T.cell_start = h->T.cell_start; T.cell_entries = h->T.cell_entries; T.episodes = h->T.episodes;
@@ -141,11 +153,11 @@ int pgd_launch_step_v3(PgdHandle* h, int mode, int env_begin, int env_end, const
   if (h->timing && mode == 0) cudaEventRecord(h->ev0, st);
   const int V = h->cfg.num_slots;
   int rc;
-#define V3_LAUNCH(VV) rc = launch_one<VV, V3_ROLES>(h, T, S, mode, env_begin, env_end, actions, obs, reward, done, info, st)
-  if (V == 16) V3_LAUNCH(16);
-  else if (V == 24) V3_LAUNCH(24);
-  else V3_LAUNCH(32);
-#undef V3_LAUNCH
+#define PGS_LAUNCH(VV) rc = launch_one<VV, PGS_ROLES>(h, T, S, mode, env_begin, env_end, actions, obs, reward, done, info, st)
+  if (V == 16) PGS_LAUNCH(16);
+  else if (V == 24) PGS_LAUNCH(24);
+  else PGS_LAUNCH(32);
+#undef PGS_LAUNCH
   if (rc) return rc;
   if (h->timing && mode == 0) cudaEventRecord(h->ev1, st);
   h->launches++;

@@ -224,10 +224,12 @@ def build_seed_tables(seeds, map_config, density, spawn, workers=None, stored=No
     return T
 
 
-def engine_layout(cfg):
-    if cfg.get("layout", None) is not None:
-        return int(cfg["layout"])
-    return 1 if cfg.get("one_thread_per_env", False) else 0
+def pick_slots(need):
+    """Smallest vehicle-slot count the kernel is instantiated for (16 / 24 / 32) that holds ``need`` vehicles."""
+    for v in (16, 24, 32):
+        if need <= v:
+            return v
+    raise ValueError("an episode needs %d vehicle slots; at most 32 are supported" % need)
 
 
 class _Engine:
@@ -249,7 +251,6 @@ class _Engine:
             side_distance=cfg["vehicle_config"]["side_detector"]["distance"],
             n_lane_line=cfg["vehicle_config"]["lane_line_detector"]["num_lasers"],
             lane_line_distance=cfg["vehicle_config"]["lane_line_detector"]["distance"],
-            layout=engine_layout(cfg),
             random_agent_model=bool(cfg["random_agent_model"])
         )
         self.obs_dim = cabi.obs_dim(self.pcfg)
@@ -296,9 +297,6 @@ class VecPGDriveEnv:
             stored = load_map_file(cfg["_load_map_from_json"], self.map_config, seeds)
         self._T = None
         random_lane = (bool(cfg["random_lane_width"]), bool(cfg["random_lane_num"]))
-        if cfg["random_agent_model"] and engine_layout(cfg) == 0:
-            raise NotImplementedError("random_agent_model is only in the one-thread-per-environment layout "
-                                      "(one_thread_per_env=True) so far")
         if cfg["random_agent_model"] and cfg["device_mapgen"]:
             raise NotImplementedError("device_mapgen spawns the default ego vehicle")
         if cfg["device_mapgen"] and tables_dict is None and stored is None:
@@ -326,7 +324,7 @@ class VecPGDriveEnv:
             )
             self.episode_of_seed = {int(s): i for i, s in enumerate(self._T["episodes"]["seed"])}
             need = int(self._T["max_slots"])
-            slots = cfg["num_slots"] or (16 if need <= 16 else 32)
+            slots = cfg["num_slots"] or pick_slots(need)
             if need > slots:
                 raise ValueError("the loaded seeds need %d vehicle slots; num_slots=%d" % (need, slots))
             self.engine = _Engine(cfg, self.num_envs, slots, int(cfg["device"]), bool(cfg["auto_reset"]),
@@ -542,13 +540,12 @@ class PGDriveEnv:
     def __init__(self, config=None):
         self.config = self.default_config().update(config or {}, allow_add_new_key=False)
         check_supported(self.config)
-        if self.config["random_agent_model"]:
-            raise NotImplementedError("random_agent_model: use VecPGDriveEnv(one_thread_per_env=True)")
         self.start_seed, self.env_num = int(self.config["start_seed"]), int(self.config["environment_num"])
         self.map_config = parse_map_config(self.config)
         vc = self.config["vehicle_config"]
         self._spawn = (tuple(vc["spawn_lane_index"]), float(vc["spawn_longitude"]), float(vc["spawn_lateral"]))
-        self.obs_dim = (vc["side_detector"]["num_lasers"] or 2) + 6 + vc["lane_line_detector"]["num_lasers"] + 266
+        self.obs_dim = ((vc["side_detector"]["num_lasers"] or 2) + 6 + vc["lane_line_detector"]["num_lasers"] + 266 +
+                        (2 if self.config["random_agent_model"] else 0))
         self.observation_space = Box(-0.0, 1.0, shape=(self.obs_dim, ), dtype=np.float32)
         self.action_space = make_action_space(self.config)
         self._parts, self._episode_of_seed = [], {}
@@ -568,12 +565,13 @@ class PGDriveEnv:
         if seed in self._episode_of_seed:
             return
         mc = seed_map_config(self.map_config, seed, self.config["random_lane_width"], self.config["random_lane_num"])
-        part = _seed_tables((seed, mc, self.config["traffic_density"], self._spawn, (self._stored or {}).get(seed)))
+        part = _seed_tables((seed, mc, self.config["traffic_density"], self._spawn, (self._stored or {}).get(seed),
+                             bool(self.config["random_agent_model"])))
         self._parts.append(part)
         self._episode_of_seed[seed] = len(self._parts) - 1
         T = merge_tables(self._parts)
         need = int(T["max_slots"])
-        slots = 16 if need <= 16 else 32
+        slots = pick_slots(need)
         if self._engine is not None and self._engine.num_slots < slots:
             self._engine.close()
             self._engine = None

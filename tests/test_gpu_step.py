@@ -1,5 +1,5 @@
-"""The role-per-warp step on the GPU (PgdConfig.layout = 2, pgd_step_v3.cu) against the CPU oracle, bit for bit, and
-against the other layouts, through the C-ABI."""
+"""More GPU parity rollouts of the step kernel against the CPU oracle, bit for bit, through the C-ABI: 32 and 24 vehicle
+slots, horizon, partial CTAs, and the full-size timing smoke."""
 import os
 
 import numpy as np
@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 def _rollouts(n, seeds, steps, policy, density=0.1, **cfg):
     import torch
     from test_gpu_parity import _pair, _reset_both, _rollout
-    env, ref = _pair(n, seeds, density=density, layout=2, **cfg)
+    env, ref = _pair(n, seeds, density=density, **cfg)
     obs, ro = _reset_both(env, ref)
     assert np.array_equal(obs, ro)
     rs = np.random.RandomState(2)
@@ -31,50 +31,29 @@ def _rollouts(n, seeds, steps, policy, density=0.1, **cfg):
     return dones
 
 
-def test_v3_random_and_forward_policies_match_oracle():
+def test_step_random_and_forward_policies_match_oracle():
     seeds = list(range(1000, 1100))
     _rollouts(400, seeds, 100, "uniform")
     assert _rollouts(400, seeds, 250, "forward") > 0
 
 
-def test_v3_lane_following_meets_traffic():
+def test_step_lane_following_meets_traffic():
     assert _rollouts(300, list(range(1000, 1100)), 350, "lane") > 0
 
 
-def test_v3_32_slots_and_horizon():
+def test_step_32_and_24_slots_and_horizon():
     _rollouts(96, list(range(1000, 1012)), 200, "lane", density=0.2)
+    _rollouts(70, list(range(1000, 1012)), 120, "lane", density=0.1, num_slots=24)  # 70 envs: a partly empty CTA
     _rollouts(64, [1000, 1001], 40, "forward", horizon=9, auto_reset=False)
 
 
-def test_v3_equals_cooperative_kernel():
-    """Same tables, same actions: both layouts of the step give the same observations / rewards / dones."""
-    import torch
-    from pgdrive_b200 import VecPGDriveEnv
-    n = 512
-    common = dict(start_seed=1000, environment_num=100, num_envs=n, traffic_density=0.1)
-    a = VecPGDriveEnv(dict(common))
-    b = VecPGDriveEnv(dict(common, layout=2), tables_dict=a.T)
-    assert np.array_equal(a.reset().cpu().numpy(), b.reset().cpu().numpy())
-    rs = np.random.RandomState(4)
-    for t in range(200):
-        act = rs.uniform(-1, 1, (n, 2)).astype(np.float32)
-        act[:, 1] = np.abs(act[:, 1])
-        at = torch.from_numpy(act).cuda()
-        ra = [x.cpu().numpy().copy() for x in a.step(at)[:3]]
-        rb = [x.cpu().numpy().copy() for x in b.step(at)[:3]]
-        assert np.array_equal(ra[2], rb[2]), t
-        assert np.array_equal(ra[0], rb[0]) and np.array_equal(ra[1], rb[1]), t
-    a.close()
-    b.close()
-
-
-def test_v3_full_size_throughput_smoke():
+def test_step_full_size_throughput_smoke():
     """65 536 environments: runs, replicas of a seed stay identical, and the time per step is printed."""
     import torch
     from pgdrive_b200 import VecPGDriveEnv
     n = 65536
     env = VecPGDriveEnv(dict(start_seed=1000, environment_num=100, num_envs=n, traffic_density=0.1,
-                             layout=2))
+                             ))
     env.reset()
     g = torch.Generator(device="cuda")
     g.manual_seed(1)

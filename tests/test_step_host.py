@@ -1,12 +1,13 @@
-"""The one-thread-per-environment step (pgdrive_b200/csrc/pgd_step_v2.cuh), HOST build, against the independent CPU
-oracle (oracle/pgd_oracle.c).  Both are float32 on glibc and the step function keeps the cooperative kernel's
-expressions, so the bar here is bit-identical observations, rewards, done flags and info records over free-running
-rollouts -- stricter than the GPU tests' 1e-3, and runnable without a GPU."""
+"""The role-per-warp step (pgdrive_b200/csrc/pgd_step.cuh), HOST build, against the independent CPU oracle
+(oracle/pgd_oracle.c).  The host build runs the kernel's phases in order over all (role, lane) pairs of a 32-environment
+CTA -- shared-memory exchanges included -- and shares include/pgd_math.h with the oracle, so the bar is bit-identical
+observations, rewards, done flags and info records over free-running rollouts, runnable without a GPU."""
 import numpy as np
 import pytest
 
 V0 = dict(type="block_num", config=3, lane_num=3, lane_width=3.5, exit_length=50)
 SPAWN = ((">", ">>", 0), 5.0, 0.0)
+ROLES = [4]  # warps per CTA emulated by the host build (test_role_counts varies it)
 
 
 def _tables(seeds, density=0.1):
@@ -16,9 +17,9 @@ def _tables(seeds, density=0.1):
 
 def _pair(T, n, **cfg):
     from oracle.oracle import Oracle
-    from oracle.step_v2_host import HostStepV2
+    from oracle.step_host import HostStep
     slots = 16 if T["max_slots"] <= 16 else 32
-    return Oracle(T, n, num_slots=slots, **cfg), HostStepV2(T, n, num_slots=slots, **cfg)
+    return Oracle(T, n, num_slots=slots, **cfg), HostStep(T, n, roles=ROLES[0], num_slots=slots, **cfg)
 
 
 def _actions(rs, n, mode):
@@ -231,3 +232,23 @@ def test_random_agent_model_observation_and_dynamics():
             assert _same(a.step(act), b.step(act)), t
         a.close()
         b.close()
+
+
+@pytest.mark.parametrize("roles", [2, 3, 8])
+def test_role_counts(roles):
+    """The slot -> role assignment and the task split depend on the number of warps per CTA; the result must not."""
+    ROLES[0] = roles
+    try:
+        T = _tables(range(1000, 1020))
+        n = 70  # not a multiple of 32: the last CTA is partly empty
+        a, b = _pair(T, n, auto_reset=True)
+        eps = [i % 20 for i in range(n)]
+        assert np.array_equal(a.reset(range(n), eps), b.reset(range(n), eps))
+        rs = np.random.RandomState(12)
+        for t in range(250):
+            act = _actions(rs, n, "lane" if t % 2 else "forward")
+            assert _same(a.step(act), b.step(act)), t
+        a.close()
+        b.close()
+    finally:
+        ROLES[0] = 4

@@ -10,12 +10,13 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-VARIANTS = {  # role-per-warp kernel (pgd_step_v3.cu): warps per CTA x resident CTAs the register budget is set for
-    "clk": ["-DV3_ROLES=4", "-DV3_MIN_CTAS=4", "-DV3_PHASE_CLOCKS"],
-    "r4c3": ["-DV3_ROLES=4", "-DV3_MIN_CTAS=3"],
-    "r5c4": ["-DV3_ROLES=5", "-DV3_MIN_CTAS=4"],
-    "r6c3": ["-DV3_ROLES=6", "-DV3_MIN_CTAS=3"],
-    "r8c3": ["-DV3_ROLES=8", "-DV3_MIN_CTAS=3"],
+VARIANTS = {  # step kernel (pgd_step_kernel.cu): warps per CTA, resident CTAs the register budget is set for, L2 hints
+    "clk": ["-DPGS_ROLES=4", "-DPGS_MIN_CTAS=4", "-DPGS_PHASE_CLOCKS"],
+    "noev": ["-DPGS_OBS_EVICT_FIRST=0"],
+    "keep": ["-DPGS_TABLE_EVICT_LAST"],
+    "r4c3": ["-DPGS_ROLES=4", "-DPGS_MIN_CTAS=3"],
+    "r8c3": ["-DPGS_ROLES=8", "-DPGS_MIN_CTAS=3"],
+    "r8c3keep": ["-DPGS_ROLES=8", "-DPGS_MIN_CTAS=3", "-DPGS_TABLE_EVICT_LAST"],
 }
 
 
@@ -32,7 +33,7 @@ def main():
         if lib and not os.path.exists(lib):
             continue
         for actions in ("uniform", "forward"):
-            env = dict(os.environ, PGDRIVE_B200_LIB=lib, ACTIONS=actions, LAYOUT=os.environ.get("LAYOUT", "2"))
+            env = dict(os.environ, PGDRIVE_B200_LIB=lib, ACTIONS=actions)
             out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "quick_bench.py")], env=env,
                                  stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True).stdout.strip().split("\n")
             print(name, out[-1], flush=True)

@@ -6,9 +6,7 @@ import bench
 from pgdrive_b200 import VecPGDriveEnv
 n = int(os.environ.get("ENVS", 65536)); K = int(os.environ.get("STEPS", 200)); W = 40
 T = bench.build_tables()
-layout = int(os.environ.get("LAYOUT", "0"))  # 0 cooperative, 1 one thread per env, 2 role per warp
-env = VecPGDriveEnv(dict(start_seed=1000, environment_num=100, num_envs=n, traffic_density=0.1, num_slots=16,
-                         layout=layout), tables_dict=T)
+env = VecPGDriveEnv(dict(start_seed=1000, environment_num=100, num_envs=n, traffic_density=0.1, num_slots=16), tables_dict=T)
 env.reset()
 mode = os.environ.get("ACTIONS", "uniform")
 g = torch.Generator(device="cuda"); g.manual_seed(1)
@@ -22,7 +20,7 @@ e0.record()
 for t in range(K): env.step(a[W + t])
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / K
-print("%s layout=%d actions=%s: %.4f ms/step, %.1f M env-steps/s" % (os.environ.get("PGDRIVE_B200_LIB", "default"), int(layout), mode, ms, n / ms / 1e3))
+print("%s actions=%s: %.4f ms/step, %.1f M env-steps/s" % (os.path.basename(os.environ.get("PGDRIVE_B200_LIB", "") or "default"), mode, ms, n / ms / 1e3))
 
 if hasattr(env.engine.lib, "pgd_debug_phase_clocks"):  # diagnostic build (-DV3_PHASE_CLOCKS): cycles per phase, thread 0
     import ctypes

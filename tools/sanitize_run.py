@@ -1,13 +1,13 @@
-"""Run the host builds of the generator, the v2 step and the oracle under ASan + UBSan."""
+"""Run the host builds of the generator, the step and the oracle under ASan + UBSan."""
 import ctypes, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np
-from oracle import mapgen_host as mh, oracle as orc, step_v2_host as v2
+from oracle import mapgen_host as mh, oracle as orc, step_host as v2
 SAN = os.path.join(ROOT, "oracle", "_san")
 mh.LIB = os.path.join(SAN, "libpgd_mapgen_host.so"); mh.build = lambda force=False: mh.LIB
 orc.LIB = os.path.join(SAN, "libpgd_oracle.so"); orc.build = lambda force=False: orc.LIB
-v2.LIB = os.path.join(SAN, "libpgd_step_v2_host.so")
+v2.LIB = os.path.join(SAN, "libpgd_step_host.so")
 import subprocess
 v2.subprocess = type("S", (), {"check_call": staticmethod(lambda *a, **k: 0), "DEVNULL": None})
 from pgdrive_b200 import devgen, env as E
@@ -27,10 +27,10 @@ for field, val in [("lanes", 30), ("roads", 10), ("boxes", 200), ("cells", 100),
     for s in range(1000, 1010):
         rc, T, seq = mh.generate(s, gc, caps); n += 1
 print("generator runs under sanitizers:", n)
-# v2 step + oracle rollouts
+# step + oracle rollouts
 seeds = list(range(1000, 1030))
 T = E.merge_tables([E._seed_tables((s, V0, 0.1, SP)) for s in seeds])
-a = orc.Oracle(T, 90, auto_reset=True, num_slots=16); b = v2.HostStepV2(T, 90, auto_reset=True, num_slots=16)
+a = orc.Oracle(T, 90, auto_reset=True, num_slots=16); b = v2.HostStep(T, 90, auto_reset=True, num_slots=16)
 eps = [i % 30 for i in range(90)]
 a.reset(range(90), eps); b.reset(range(90), eps)
 rs = np.random.RandomState(0)
@@ -39,7 +39,7 @@ for t in range(250):
     r1 = a.step(act); r2 = b.step(act)
     assert np.array_equal(r1[0], r2[0])
 cfg = dict(auto_reset=True, n_side=12, side_distance=50.0, n_lane_line=8, lane_line_distance=20.0)
-a = orc.Oracle(T, 30, num_slots=16, **cfg); b = v2.HostStepV2(T, 30, num_slots=16, **cfg)
+a = orc.Oracle(T, 30, num_slots=16, **cfg); b = v2.HostStep(T, 30, num_slots=16, **cfg)
 a.reset(range(30), range(30)); b.reset(range(30), range(30))
 for t in range(100):
     act = rs.uniform(-1, 1, (30, 2)).astype(np.float32); act[:, 1] = np.abs(act[:, 1])
