@@ -1,21 +1,27 @@
 #!/usr/bin/env python
 """Benchmark of the hot path: env-steps/s of the fused step kernel (BASELINE.json's metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--envs E]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--envs E] [--workload v0|1000envs]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 Own arm: every rank steps `--envs` (default 65 536) PGDrive-v0 environments (seeds 1000..1099, traffic density
 0.1, 240-beam lidar, 16 vehicle slots); a "step" is ONE kernel launch advancing all of them by one decision step
-(5 physics sub-steps + observation + reward/done, auto-reset of finished episodes).  Weak scaling: with N ranks
+(5 physics sub-steps + observation + reward/done, auto-reset of finished episodes).  Every timed region starts
+after an untimed pre-roll of 128 steps of the same policy, so the number does not depend on where in the episode
+distribution the timer starts (fresh resets are the cheapest state of the simulator).  Weak scaling: with N ranks
 the job simulates N x 65 536 environments and every step rank 0 receives the whole observation / reward / done
-batch (--gather: peer = stored by the step kernel straight into rank 0's HBM over NVLink, nccl = in-place
-all-gather overlapped with the next step's kernel, auto = peer, falling back to nccl when peer mapping is not
-permitted).
-  value      device-resident: actions pre-generated in HBM, CUDA-event time of K steps, max over ranks
-  e2e        same steps through the public VecPGDriveEnv.step(numpy) -> pgd_step_host: pinned H2D of the actions
-             and D2H of obs / reward / done / info inside the timed region
-  roofline   algorithmic bytes per env-step (DESIGN.md "Bytes") x envs / average kernel time vs measured HBM peak
-  cpu_baseline  the CPU oracle (oracle/pgd_oracle.c, a scalar port of the same step) on all host cores, bounded sample
+batch (--gather, DESIGN.md "Multi-GPU") and READS it (a checksum kernel stands for the policy network).
+  value        device-resident, random policy of BASELINE.md: actions pre-generated in HBM, CUDA-event time of K
+               steps, max over ranks
+  driving      the same kernel under a policy that drives (traffic awake, lidar hits, frequent resets), with its
+               own roofline block
+  e2e          same steps through the public host-buffer API: N = 1 VecPGDriveEnv.step(numpy) -> pgd_step_host
+               (pinned H2D of the actions, D2H of obs / reward / done / info inside the timed region); N > 1 the
+               actions of the WHOLE batch start on rank 0's host and the gathered results end there
+  roofline     algorithmic bytes per env-step (DESIGN.md "Bytes") x envs / average kernel time vs measured HBM peak;
+               `issue` = the secondary bound: warp instructions per launch (ncu, profiles/) against the SMs' issue rate
+  cpu_baseline the CPU oracle (oracle/pgd_oracle.c, a scalar port of the same step) on all host cores, bounded sample
+  sim_only     N > 1: the same K steps without the gather (does the kernel itself scale?)
 
 Reference arm (--impl reference): the reference's own step runs on Panda3D/Bullet, which is neither vendored nor
 installable offline, so this arm times the CPU oracle port on all host cores on the same config and metric.
@@ -33,9 +39,17 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-WORKLOAD = "65536 envs PGDrive-v0 (seeds 1000-1099), traffic_density=0.1, 240-beam lidar, 16 vehicle slots"
 OBS_DIM = 274
 INFO_BYTES = 40
+PREROLL = 128  # untimed steps before every timed region (the episode-length distribution reaches its steady state)
+SMS, ISSUE_PER_SM_CLK = 148, 4  # B200: 148 SMs x 4 warp schedulers, one warp instruction per scheduler per clock
+
+WORKLOADS = {
+    # name: (first seed, number of seeds, vehicle slots, description)
+    "v0": (1000, 100, 16, "%d envs PGDrive-v0 (seeds 1000-1099), traffic_density=0.1, 240-beam lidar, 16 vehicle slots"),
+    "1000envs": (1000, 1000, 24, "%d envs PGDrive-1000envs-v0 (seeds 1000-1999, 1000 distinct maps), "
+                                 "traffic_density=0.1, 240-beam lidar, 24 vehicle slots"),
+}
 
 
 def algorithmic_bytes_per_env_step(num_slots):
@@ -101,10 +115,10 @@ def host_threads():
     return len(os.sched_getaffinity(0))
 
 
-def cpu_oracle_rate(T, n_envs, steps, warmup, threads, episode_ids, seed=0):
+def cpu_oracle_rate(T, n_envs, steps, warmup, threads, episode_ids, num_slots, seed=0):
     """env-steps/s of the CPU oracle on `threads` host threads (uniform [-1,1]^2 actions, auto-reset)."""
     from oracle.oracle import Oracle
-    ref = Oracle(T, n_envs, auto_reset=True)
+    ref = Oracle(T, n_envs, auto_reset=True, num_slots=num_slots)
     ref.reset(range(n_envs), episode_ids)
     rs = np.random.RandomState(seed)
     acts = rs.uniform(-1, 1, (warmup + steps, n_envs, 2)).astype(np.float32)
@@ -116,14 +130,6 @@ def cpu_oracle_rate(T, n_envs, steps, warmup, threads, episode_ids, seed=0):
     dt = time.perf_counter() - t0
     ref.close()
     return n_envs * steps / dt, dt
-
-
-WORKLOADS = {
-    # name: (first seed, number of seeds, vehicle slots, description)
-    "v0": (1000, 100, 16, WORKLOAD),
-    "1000envs": (1000, 1000, 24, "65536 envs PGDrive-1000envs-v0 (seeds 1000-1999, 1000 distinct maps), "
-                                 "traffic_density=0.1, 240-beam lidar, 24 vehicle slots"),
-}
 
 
 def build_tables(workload="v0"):
@@ -141,24 +147,41 @@ def run_reference(args):
     orc.build()
     T = build_tables(args.workload)
     threads = host_threads()
-    n_seeds = WORKLOADS[args.workload][1]
+    _, n_seeds, n_slots, desc = WORKLOADS[args.workload]
     # calibrate, then size the per-step sample so that warmup + steps finish in about 100 s
-    rate0, _ = cpu_oracle_rate(T, 1024, 4, 1, threads, [i % n_seeds for i in range(1024)])
+    rate0, _ = cpu_oracle_rate(T, 1024, 4, 1, threads, [i % n_seeds for i in range(1024)], n_slots)
     n = int(min(args.envs, max(256, rate0 * 100.0 / (args.steps + args.warmup))))
     n = max(100, n // 100 * 100)
-    rate, dt = cpu_oracle_rate(T, n, args.steps, args.warmup, threads, [i % n_seeds for i in range(n)])
+    rate, dt = cpu_oracle_rate(T, n, args.steps, args.warmup, threads, [i % n_seeds for i in range(n)], n_slots)
     sample = "%d of %d envs per step x %d steps, %d host threads" % (n, args.envs, args.steps, threads)
     line = dict(
         impl="reference", metric="env-steps/s", value=rate, unit="env-steps/s", n_gpus=args.gpus, steps=args.steps,
         warmup=args.warmup, ms_per_step=dt / args.steps * 1e3, higher_is_better=True, scaling="weak",
         vs_baseline=None, dtype="f32", data="synthetic",
-        config=dict(workload=WORKLOADS[args.workload][3], envs_per_gpu=args.envs, actions="uniform[-1,1]^2, RandomState(0)",
+        config=dict(workload=desc % args.envs, envs_per_gpu=args.envs, actions="uniform[-1,1]^2, RandomState(0)",
                     note="reference step needs Panda3D/Bullet (not installable offline): CPU oracle port timed instead"),
         cpu_baseline=dict(value=rate, unit="env-steps/s", cores=threads, kind="port", sample=sample),
         e2e=dict(value=rate, unit="env-steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
     )
     print(json.dumps(line))
     return 0
+
+
+def issue_bound(kernel_ms, sm_mhz, policy, workload):
+    """Secondary (honest) bound, SURVEY 8(d): the kernel is latency / issue bound, not HBM bound.  Warp instructions
+    per launch come from the committed ncu capture of this workload (profiles/issue_slots.json); the rate they are
+    issued at is live: kernel time from this run, SM clock from nvidia-smi during it."""
+    path = os.path.join(ROOT, "profiles", "issue_slots.json")
+    if not os.path.exists(path) or not sm_mhz or not kernel_ms:
+        return None
+    rec = json.load(open(path)).get(workload, {}).get(policy)
+    if not rec:
+        return None
+    peak = SMS * ISSUE_PER_SM_CLK * sm_mhz * 1e6  # warp instructions / s
+    achieved = rec["warp_instructions_per_launch"] / (kernel_ms * 1e-3)
+    return dict(bound="issue", achieved=achieved / 1e9, peak=peak / 1e9, unit="G warp-inst/s", frac=achieved / peak,
+                warp_instructions_per_launch=rec["warp_instructions_per_launch"],
+                threads_per_instruction=rec.get("threads_per_instruction"), source=rec.get("source"))
 
 
 def run_own(args):
@@ -174,12 +197,12 @@ def run_own(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if "BENCH_NCCL_DEBUG" in os.environ:
-            os.environ["NCCL_DEBUG"] = os.environ["BENCH_NCCL_DEBUG"]
-        else:
-            os.environ.pop("NCCL_DEBUG", None)  # NCCL prints its version banner to stdout; keep stdout to the JSON line
+        # NCCL's INFO log (version banner, rings, "comm ... nranks N") goes to stderr so that stdout stays the one
+        # JSON line; it is not switched off
+        if os.environ.get("NCCL_DEBUG"):
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         # the collective runs on a high-priority stream: its few CTAs are scheduled as soon as a step-kernel CTA
-        # retires instead of queueing behind the whole (register-file-filling) step kernel
+        # retires instead of queueing behind the whole step kernel
         opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
         dist.init_process_group("nccl", device_id=dev, pg_options=opts)
 
@@ -188,15 +211,12 @@ def run_own(args):
         __graft_entry__.build()
     if world > 1:
         dist.barrier()
-    from pgdrive_b200 import VecPGDriveEnv, cabi
+    from pgdrive_b200 import VecPGDriveEnv
+    from pgdrive_b200.sharding import GatherBuffers, PeerGather
     n, K, W = args.envs, args.steps, args.warmup
-    first_seed, n_seeds, n_slots, workload_name = WORKLOADS[args.workload]
+    first_seed, n_seeds, n_slots, desc = WORKLOADS[args.workload]
     T = build_tables(args.workload)
-    # weak scaling: rank r owns environments [r*n, (r+1)*n) of the global batch; the kernel writes its observations
-    # straight into this rank's slice of the gather buffer (in-place all-gather, no packing kernel)
-    from pgdrive_b200.sharding import GatherBuffers
-    # two gather buffers: while the all-gather of step t runs on a side stream, the kernel of step t+1 already writes
-    # this rank's rows of the other buffer (results reach rank 0 one kernel later; nothing waits on the collective)
+    # weak scaling: rank r owns environments [r*n, (r+1)*n) of the global batch
     bufs = [GatherBuffers(torch, n, world, rank, dev, obs_dim=OBS_DIM) for _ in range(2 if world > 1 else 1)]
     side = torch.cuda.Stream(device=dev, priority=-1) if world > 1 else None
     env = VecPGDriveEnv(
@@ -204,60 +224,83 @@ def run_own(args):
              num_slots=n_slots),
         tables_dict=T, obs_out=bufs[0].local(bufs[0].obs)
     )
-    # N > 1, default: the gather to rank 0 is fused into the step kernel (results stored straight into rank 0's HBM
-    # through CUDA-IPC peer mappings over NVLink; pgdrive_b200.sharding.PeerGather).  --gather nccl selects the plain
-    # in-place NCCL all-gather instead; it is also the fall-back when peer mapping is not permitted on the box.
     peer = None
     gather_mode = "none"
     if world > 1:
         gather_mode = args.gather
         if gather_mode == "auto":
-            gather_mode = "peer"  # bulk (TMA) row stores into rank 0 beat the NCCL all-gather at 2 and at 8 GPUs
-        if gather_mode == "peer":
-            from pgdrive_b200.sharding import PeerGather
+            gather_mode = "peer"
+        if gather_mode in ("peer", "copy"):
             ok = torch.ones(1, dtype=torch.int32, device=dev)
             try:
-                peer = PeerGather(env, torch, dist, n, world, rank)
+                peer = PeerGather(env, torch, dist, n, world, rank, mode=gather_mode)
             except Exception as exc:  # noqa: BLE001
                 sys.stderr.write("rank %d: peer gather unavailable (%s)\n" % (rank, exc))
                 ok.zero_()
             dist.all_reduce(ok, op=dist.ReduceOp.MIN)
             if int(ok.item()) == 0:
                 peer, gather_mode = None, "nccl (peer mapping unavailable)"
-    env.reset()
+
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)  # Philox counter-based stream, one per rank
-    actions = torch.rand((W + K, n, 2), generator=gen, device=dev, dtype=torch.float32) * 2 - 1
+    n_act = max(W + K, PREROLL)
+    actions = torch.rand((n_act, n, 2), generator=gen, device=dev, dtype=torch.float32) * 2 - 1
+    fwd = actions.clone()  # a policy that drives: never brakes, small steering noise
+    fwd[..., 1] = fwd[..., 1].abs()
+    fwd[..., 0] *= 0.1
 
-    free = [None, None]  # event after which a buffer's previous all-gather has finished
+    done_ev = [None, None]      # per gather buffer: event after which it may be written again
     counter = [0]
+    consumed = torch.zeros(3, dtype=torch.float64, device=dev)   # rank 0: what the consumer read from the gathered batch
+    local_sum = torch.zeros(3, dtype=torch.float64, device=dev)  # every rank: the same sums over its own rows
 
-    def step_and_gather(a):
+    def checksum_into(acc, obs, reward, done):
+        acc[0] += obs.sum(dtype=torch.float64)
+        acc[1] += reward.sum(dtype=torch.float64)
+        acc[2] += done.sum(dtype=torch.float64)
+
+    def step_and_gather(a, check=False):
+        """One step of this rank + the gather of everybody's results to rank 0 (+ rank 0 reading the batch)."""
         if world == 1:
             env.step(a)
             return
         i = counter[0] % 2
         counter[0] += 1
         cur = torch.cuda.current_stream(dev)
+        if done_ev[1 - i] is not None:
+            # buffer i was last written two steps ago.  Waiting for the PREVIOUS step's barrier is what makes rewriting
+            # it safe: rank 0 enqueued its read of buffer i before it joined that barrier (sharding.PeerGather)
+            cur.wait_event(done_ev[1 - i])
         if peer is not None:
-            env.step_into(a, *peer.pointers(i))
+            direct = peer.mode == "peer" or rank == 0  # rank 0's own rows are local memory either way
+            env.step_into(a, *(peer.pointers(i) if direct else peer.local_pointers(i)))
+            if check:
+                checksum_into(local_sum, *peer.local_views(i, remote=direct))
             ready = torch.cuda.Event()
             ready.record(cur)
             side.wait_event(ready)
             with torch.cuda.stream(side):
+                if not direct:
+                    peer.push(i)  # copy engine: local rows -> rank 0's buffer over NVLink
                 peer.completion_barrier()
+                if rank == 0 and check:
+                    checksum_into(consumed, *peer.tensors(i))  # the consumer reads the whole gathered batch
+                done_ev[i] = torch.cuda.Event()
+                done_ev[i].record(side)
             return
         b = bufs[i]
-        if free[i] is not None:
-            cur.wait_event(free[i])
         env.step(a, out=(b.local(b.obs), b.local(b.reward), b.local(b.done)))
+        if check:
+            checksum_into(local_sum, b.local(b.obs), b.local(b.reward), b.local(b.done))
         ready = torch.cuda.Event()
         ready.record(cur)
         side.wait_event(ready)
         with torch.cuda.stream(side):
             b.all_gather(dist)
-            free[i] = torch.cuda.Event()
-            free[i].record(side)
+            if rank == 0 and check:
+                checksum_into(consumed, b.obs, b.reward, b.done)
+            done_ev[i] = torch.cuda.Event()
+            done_ev[i].record(side)
 
     def drain():
         if side is not None:
@@ -268,6 +311,25 @@ def run_own(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed(acts, k, fn):
+        """K steps bracketed by barrier + synchronize; returns (total ms, mean per-step ms between events)."""
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(k)]
+        barrier()
+        ev0.record()
+        for t in range(k):
+            k_ev[t][0].record()
+            fn(acts[t])
+            k_ev[t][1].record()
+        drain()
+        ev1.record()
+        barrier()
+        return ev0.elapsed_time(ev1), float(np.mean([a.elapsed_time(b) for a, b in k_ev]))
+
+    # ---- headline: BASELINE.md's random policy, gather included -------------------------------------------------------
+    env.reset()
+    for t in range(PREROLL):  # untimed pre-roll: not tied to --steps / --warmup
+        env.step(actions[t])
     for t in range(W):
         step_and_gather(actions[t])
     drain()
@@ -277,64 +339,86 @@ def run_own(args):
         clocks.start()
         time.sleep(0.3)
     launches0 = env.launch_count
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    barrier()
-    ev0.record()
-    for t in range(K):
-        k_ev[t][0].record()
-        step_and_gather(actions[W + t])
-        k_ev[t][1].record()
-    drain()
-    ev1.record()
-    barrier()
-    ms = ev0.elapsed_time(ev1)
-    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in k_ev]))
+    ms, kernel_ms = timed(actions[W:W + K], K, lambda a: step_and_gather(a, check=(world > 1)))
     launches = env.launch_count - launches0
     clk = clocks.stop() if rank == 0 else None
-    if world == 1 or (peer is not None and rank != 0):
-        last_done = env.done
-    elif peer is not None:
-        last_done = peer.tensors(0)[2][:n]
-    else:
-        last_done = bufs[0].local(bufs[0].done)
-    done_rate = float(last_done.float().mean().item())
+    done_rate = float(env.done.float().mean().item()) if world == 1 else None
 
-    # ---- the same kernel under a policy that actually drives (traffic awake, lidar hits, frequent resets): reported
-    # beside the headline because uniform-random throttle brakes half the time and the ego barely leaves its spawn
-    fwd = actions[:min(K, 128)].clone()
-    fwd[..., 1] = fwd[..., 1].abs()
-    fwd[..., 0] *= 0.1
-    env.reset()
-    for t in range(fwd.shape[0]):
-        env.step(fwd[t])
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    f0.record()
-    for t in range(fwd.shape[0]):
-        env.step(fwd[t])
-    f1.record()
-    torch.cuda.synchronize()
-    fwd_rate = n * fwd.shape[0] / (f0.elapsed_time(f1) * 1e-3)
-    env.reset()
+    # ---- N > 1: the same steps without the gather (does the kernel itself scale?) -----------------------------------
+    sim_ms = None
+    if world > 1:
+        sim_ms, _ = timed(actions[W:W + K], K, lambda a: env.step(a))
 
-    # ---- end to end through the public host-buffer API (pinned H2D actions, D2H results every step) ----
-    h_actions = actions[W:W + K].cpu().numpy()
+    # ---- the same kernel under a policy that drives (own pre-roll, own roofline) -----------------------------------------
+    env.reset()
+    for t in range(PREROLL):
+        env.step(fwd[t])
+    fwd_k = min(K, fwd.shape[0])
+    fwd_ms, fwd_kernel_ms = timed(fwd[:fwd_k], fwd_k, lambda a: env.step(a))
+    fwd_done_rate = float(env.done.float().mean().item())
+
+    # ---- end to end through the public host-buffer API ------------------------------------------------------------------
+    env.reset()
+    for t in range(PREROLL):
+        env.step(actions[t])
     e2e_steps = min(K, 64)
+    h_actions = actions[W:W + e2e_steps].cpu().numpy()
     for t in range(min(W, 4)):
-        env.step(h_actions[t])
+        env.step(h_actions[t % e2e_steps])
     barrier()
     t0 = time.perf_counter()
     for t in range(e2e_steps):
         o, r, d, i = env.step(h_actions[t])
     torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+    per_rank_e2e_s = time.perf_counter() - t0
     checksum = float(o[:, :8].sum())
+    e2e_s, e2e_api = per_rank_e2e_s, "VecPGDriveEnv.step(numpy) -> pgd_step_host"
+    e2e_h2d, e2e_d2h = n * 8, n * (4 * OBS_DIM + 4 + 1 + INFO_BYTES)
+    if world > 1 and peer is not None:
+        # north_star's path: the actions of the WHOLE batch start in rank 0's host memory, the gathered observation /
+        # reward / done batch ends there.  H2D on rank 0, broadcast over NVLink, step + gather, one D2H on rank 0.
+        rows = world * n
+        all_act_dev = torch.empty((rows, 2), dtype=torch.float32, device=dev)
+        if rank == 0:
+            h_all = torch.empty((rows, 2), dtype=torch.float32, pin_memory=True)
+            h_all.uniform_(-1, 1)
+            h_obs = torch.empty((rows, OBS_DIM), dtype=torch.float32, pin_memory=True)
+            h_rew = torch.empty(rows, dtype=torch.float32, pin_memory=True)
+            h_done = torch.empty(rows, dtype=torch.uint8, pin_memory=True)
 
-    times = torch.tensor([ms, e2e_s * 1e3, kernel_ms], dtype=torch.float64, device=dev)
+        def host_step():
+            if rank == 0:
+                all_act_dev.copy_(h_all, non_blocking=True)
+            dist.broadcast(all_act_dev, src=0)
+            step_and_gather(all_act_dev[rank * n:(rank + 1) * n])
+            drain()
+            if rank == 0:
+                go, gr, gd = peer.tensors(counter[0] - 1)
+                h_obs.copy_(go, non_blocking=True)
+                h_rew.copy_(gr, non_blocking=True)
+                h_done.copy_(gd, non_blocking=True)
+            torch.cuda.synchronize()
+
+        e2e_steps_n = min(e2e_steps, 16)
+        host_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps_n):
+            host_step()
+        barrier()
+        e2e_s = (time.perf_counter() - t0) * e2e_steps / e2e_steps_n  # normalised to e2e_steps below
+        e2e_api = ("rank 0 host actions [N*n, 2] -> H2D -> NCCL broadcast -> step + gather to rank 0 -> D2H of the "
+                   "gathered obs / reward / done to rank 0's host")
+        e2e_h2d, e2e_d2h = rows * 8, rows * (4 * OBS_DIM + 4 + 1)
+
+    times = torch.tensor([ms, e2e_s * 1e3, kernel_ms, fwd_ms, fwd_kernel_ms, per_rank_e2e_s * 1e3, sim_ms or 0.0],
+                         dtype=torch.float64, device=dev)
+    sums = None
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms, e2e_ms, kernel_ms = [float(x) for x in times.tolist()]
+        sums = [torch.zeros_like(local_sum) for _ in range(world)]
+        dist.all_gather(sums, local_sum)
+    ms, e2e_ms, kernel_ms, fwd_ms, fwd_kernel_ms, per_rank_e2e_ms, sim_ms = [float(x) for x in times.tolist()]
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -348,14 +432,28 @@ def run_own(args):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    achieved = b_step * n / (kernel_ms * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get("bytes_per_launch")
 
-    # ---- the reset path: maps + episode templates of the workload's seeds generated ON the device (one warp per
-    # seed; pgd_generate_tables) beside the host Python path (bounded sample of seeds, one process)
+    def roofline(k_ms, policy):
+        achieved = b_step * n / (k_ms * 1e-3) / 1e9
+        return dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
+                    traffic=traffic if (policy == "random" and args.workload == "v0" and n == 65536) else None,
+                    kernel="pgd_step_kernel<%d, 4>" % n_slots, kernel_ms=k_ms, bytes_per_env_step=b_step,
+                    peak_source=peak_src, issue=issue_bound(k_ms, (clk or {}).get("sm_mhz"), policy, args.workload))
+
+    gather_check = None
+    if world > 1:
+        want = torch.stack(sums).sum(0).cpu().numpy()
+        got = consumed.cpu().numpy()
+        gather_check = dict(
+            consumer="rank 0 sums obs / reward / done of the gathered batch after every step's gather",
+            consumed=[float(x) for x in got], sum_of_rank_local=[float(x) for x in want],
+            ok=bool(np.allclose(got, want, rtol=1e-9, atol=1e-6)))
+
+    # ---- the reset path: maps + episode templates of the workload's seeds generated ON the device -------------------
     reset_path = None
     if world == 1:
         try:
@@ -363,8 +461,7 @@ def run_own(args):
             from pgdrive_b200.env import _seed_tables, default_config, parse_map_config
             mc = parse_map_config(default_config())
             gc = devgen.make_gen_config(mc, 0.1)
-            first, count = WORKLOADS[args.workload][0], WORKLOADS[args.workload][1]
-            seeds = list(range(first, first + count))
+            seeds = list(range(first_seed, first_seed + n_seeds))
             devgen.generate(env.engine, seeds[:4], gc)  # warm-up: module load, local-memory allocation
             torch.cuda.synchronize()
             t0 = time.perf_counter()
@@ -378,7 +475,7 @@ def run_own(args):
             host_rate = k / (time.perf_counter() - t0)
             reset_path = dict(seeds=len(seeds), device_maps_per_s=len(seeds) / dev_s, device_ms=dev_s * 1e3,
                               host_python_maps_per_s=host_rate, host_sample="%d seeds, 1 process" % k)
-            env.engine.load(T)  # back to the reference-pinned host tables for the legs below
+            env.engine.load(T)
             env.reset()
         except Exception as e:  # the headline must not depend on this leg
             reset_path = dict(error=str(e)[:200])
@@ -387,36 +484,48 @@ def run_own(args):
     if world == 1 and not args.no_cpu:
         threads = host_threads()
         cn, cs = 32768, 128  # ~4.2M env-steps: 10-30 s of CPU work on a 16-thread host
-        rate, dt = cpu_oracle_rate(T, cn, cs, 2, threads, [i % n_seeds for i in range(cn)])
+        rate, dt = cpu_oracle_rate(T, cn, cs, 2, threads, [i % n_seeds for i in range(cn)], n_slots)
         cpu = dict(value=rate, unit="env-steps/s", cores=threads, kind="port",
                    sample="%d of %d envs x %d steps (%.1f s), CPU oracle on %d host threads" % (cn, n, cs, dt, threads))
 
+    collective = {
+        "none": "none",
+        "peer": "gather to rank 0 fused into the step kernel: the 32 rows of a CTA leave with one bulk (TMA) store "
+                "straight into rank 0's HBM through CUDA-IPC peer mappings over NVLink; a 4-byte all-reduce per step on "
+                "a side stream is the completion barrier; a buffer is rewritten only after rank 0 has read it",
+        "copy": "kernel writes this rank's rows locally, the copy engine pushes them into rank 0's buffer (CUDA-IPC peer "
+                "mapping) on a side stream while the next step's kernel runs; 4-byte all-reduce as completion barrier",
+    }.get(gather_mode, "in-place NCCL all-gather of obs/reward/done every step, double-buffered on a high-priority "
+                       "side stream so that it overlaps the next step's kernel [%s]" % gather_mode)
     line = dict(
         metric="env-steps/s", value=value, unit="env-steps/s", n_gpus=world, steps=K, warmup=W,
-        ms_per_step=ms / K, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+        ms_per_step=ms / K, higher_is_better=True, scaling="weak", vs_baseline=None,
+        dtype="f32", data="synthetic",
         config=dict(
-            workload=workload_name, envs_per_gpu=n, total_envs=total_envs, parallelism="env-sharded x%d" % world,
-            actions="uniform[-1,1]^2, Philox, pre-generated in HBM",
+            workload=desc % n, envs_per_gpu=n, total_envs=total_envs, parallelism="env-sharded x%d" % world,
+            actions="uniform[-1,1]^2, Philox, pre-generated in HBM", preroll_steps=PREROLL,
+            arithmetic="float32 throughout; the reference's Python side computes in float64, Bullet in float32",
             l2="no flush: state + observations touched per step = %.0f MB > 126 MB L2" % (
                 (2 * (80 * n_slots + 32) + 4 * OBS_DIM) * n / 1e6),
-            collective={"none": "none",
-                        "peer": "gather to rank 0 fused into the step kernel: obs/reward/done stored into rank 0's HBM "
-                                "through CUDA-IPC peer mappings over NVLink; one 4-byte all-reduce per step as the "
-                                "completion barrier (side stream)"}.get(
-                gather_mode, "in-place NCCL all-gather of obs/reward/done every step, double-buffered on a high-"
-                             "priority side stream so that it overlaps the next step's kernel [%s]" % gather_mode),
-            done_rate_last_step=done_rate,
-            driving_policy_env_steps_per_s_per_gpu=fwd_rate,
+            collective=collective, done_rate_last_step=done_rate,
         ),
-        roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
-                      kernel="pgd_step_kernel<%d>" % n_slots, kernel_ms=kernel_ms, bytes_per_env_step=b_step, peak_source=peak_src),
+        roofline=roofline(kernel_ms, "random"),
+        driving=dict(value=n * fwd_k / (fwd_ms * 1e-3), unit="env-steps/s per GPU", steps=fwd_k,
+                     policy="throttle |u|, steering 0.1 u: traffic awake, lidar hits, frequent resets",
+                     done_rate_last_step=fwd_done_rate, roofline=roofline(fwd_kernel_ms, "driving")),
         cpu_baseline=cpu,
         reset_path=reset_path,
         e2e=dict(value=total_envs * e2e_steps / (e2e_ms * 1e-3), unit="env-steps/s",
-                 h2d_bytes_per_step=n * 8, d2h_bytes_per_step=n * (4 * OBS_DIM + 4 + 1 + INFO_BYTES),
-                 steps=e2e_steps, api="VecPGDriveEnv.step(numpy) -> pgd_step_host", checksum=checksum),
+                 h2d_bytes_per_step=e2e_h2d, d2h_bytes_per_step=e2e_d2h, steps=e2e_steps, api=e2e_api,
+                 checksum=checksum,
+                 per_rank=dict(value=total_envs * e2e_steps / (per_rank_e2e_ms * 1e-3),
+                               api="every rank: VecPGDriveEnv.step(numpy) -> pgd_step_host on its own shard")),
         gpu_launches=int(launches), clocks=clk,
     )
+    if world > 1:
+        line["sim_only"] = dict(value=total_envs * K / (sim_ms * 1e-3), unit="env-steps/s", ms_per_step=sim_ms / K,
+                                note="the same K steps without the gather")
+        line["gather_check"] = gather_check
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -429,12 +538,12 @@ def main():
     ap.add_argument("--steps", type=int, default=256)
     ap.add_argument("--warmup", type=int, default=32)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
-    ap.add_argument("--envs", type=int, default=65536, help="environments per GPU")
+    ap.add_argument("--envs", type=int, default=65536, help="environments per GPU (4096 = BASELINE.json configs[1])")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--gather", default="auto", choices=["auto", "peer", "nccl"],
+    ap.add_argument("--gather", default="auto", choices=["auto", "peer", "copy", "nccl"],
                     help="N > 1: how rank 0 gets the whole batch (auto = peer: rows stored by the step kernel straight "
-                         "into rank 0's HBM with one bulk copy per CTA, 694 M env-steps/s at 8 GPUs against 533 M for "
-                         "the NCCL all-gather; nccl is the fall-back when peer mapping is not permitted)")
+                         "into rank 0's HBM; copy: local rows pushed by the copy engine on a side stream; nccl: in-place "
+                         "all-gather, also the fall-back when peer mapping is not permitted)")
     ap.add_argument("--workload", default="v0", choices=sorted(WORKLOADS), help="v0 = BASELINE.json configs[2] (the metric's "
                     "configuration); 1000envs = configs[3]")
     args = ap.parse_args()

@@ -22,6 +22,10 @@ extern "C" {
 
 enum { PGD_LANE_STRAIGHT = 0, PGD_LANE_ARC = 1 };
 enum { PGD_BOX_LANE = 0, PGD_BOX_WHITE = 1, PGD_BOX_YELLOW = 2, PGD_BOX_BROKEN = 3, PGD_BOX_SIDEWALK = 4 };
+/* Bucket-grid entries (cell_entries) are box ids; inside a cell the lane-surface boxes come first (ascending id), then
+ * everything else (ascending id) with this bit set, so that a scan for lanes stops at the first flagged entry and a
+ * scan for line ghosts skips the others without touching the box records. */
+enum { PGD_ENTRY_NOT_LANE = 1 << 30, PGD_ENTRY_ID_MASK = (1 << 30) - 1 };
 /* PGD_OBS_DIM is the PGDrive-v0 observation (no side / lane-line detector); with detectors see pgd_obs_dim(). */
 enum { PGD_MAX_SLOTS = 32, PGD_MAX_GROUPS = 11, PGD_N_RND25 = 16, PGD_OBS_DIM = 274, PGD_LIDAR_BEAMS = 240,
        PGD_MAX_DETECTOR_BEAMS = 240 };

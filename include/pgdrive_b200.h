@@ -8,9 +8,10 @@
  *
  * Conventions: every function returns 0 on success or a negative error code; pgd_last_error() gives
  * the message of the calling thread's last failure.  One host thread per handle; handles are
- * independent (one per GPU).  All device work is enqueued on the caller's CUDA stream (cudaStream_t
- * passed as void*, NULL = default stream) and the *_dev calls do not synchronise.  Pointers are
- * borrowed for the duration of the call only.  No torch types appear here.
+ * independent (one per GPU).  The *_dev calls enqueue their work on the caller's CUDA stream (cudaStream_t
+ * passed as void*, NULL = default stream) and do not synchronise; pgd_step_host runs on streams the handle
+ * owns, ordered after everything the *_dev calls enqueued before it, and returns when its results are valid.
+ * Pointers are borrowed for the duration of the call only.  No torch types appear here.
  */
 #ifndef PGDRIVE_B200_H
 #define PGDRIVE_B200_H

@@ -112,7 +112,9 @@ static int lane_precedes(const PgdLane* a, const PgdLane* b) { /* abs_lane.py:11
 typedef struct { float cx, cy, ux, uy, hl, hw; } Rect;
 
 static Rect veh_rect(const Veh* v) {
-  Rect r = {v->x, v->y, cosf_(v->h), sinf_(v->h), v->s->length * 0.5f, v->s->width * 0.5f};
+  float sn, cs;
+  pgd_sincosf(v->h, &sn, &cs);
+  Rect r = {v->x, v->y, cs, sn, v->s->length * 0.5f, v->s->width * 0.5f};
   return r;
 }
 
@@ -653,16 +655,20 @@ static void post_step(Oracle* o, Env* e, float last_x, float last_y, float last_
     }
   }
   /* 240-beam lidar against every other chassis (cutils.pyx:60-142) */
-  for (int i = 0; i < PGD_LIDAR_BEAMS; ++i) {
-    float ang = (float)i * (TWO_PI_F / (float)PGD_LIDAR_BEAMS) + ego->h;
-    float dx = cosf_(ang) * LIDAR_RANGE, dy = sinf_(ang) * LIDAR_RANGE;
-    float best = 1.0f;
-    for (int j = 1; j < e->n_slots; ++j) {
-      if (!e->v[j].alive) continue;
-      Rect r = veh_rect(&e->v[j]);
-      best = fminf(best, ray_rect(ego->x, ego->y, dx, dy, &r));
+  {
+    Rect rects[PGD_MAX_SLOTS];
+    int n_rects = 0;
+    for (int j = 1; j < e->n_slots; ++j)
+      if (e->v[j].alive) rects[n_rects++] = veh_rect(&e->v[j]);
+    for (int i = 0; i < PGD_LIDAR_BEAMS; ++i) {
+      float ang = (float)i * (TWO_PI_F / (float)PGD_LIDAR_BEAMS) + ego->h;
+      float sn, cs;
+      pgd_sincosf(ang, &sn, &cs);
+      float dx = cs * LIDAR_RANGE, dy = sn * LIDAR_RANGE;
+      float best = 1.0f;
+      for (int j = 0; j < n_rects; ++j) best = fminf(best, ray_rect(ego->x, ego->y, dx, dy, &rects[j]));
+      obs[34 + i] = best;
     }
-    obs[34 + i] = best;
   }
 
   /* ---- reward / cost / done (envs/pgdrive_env.py:162-258) ---- */

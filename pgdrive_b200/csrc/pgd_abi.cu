@@ -14,6 +14,7 @@
 #include "pgd_internal.h"
 
 #define DONE_PENDING_RESET 2
+#define PGD_INTERNAL_V_POSE_SET 8  // PGS_V_POSE_SET of pgd_step.cuh
 
 // marks environments for a forced reset on the given episode templates
 __global__ void pgd_mark_reset_kernel(DevState S, const int32_t* env_ids, const int32_t* episode_ids, int n,
@@ -63,6 +64,7 @@ extern "C" int pgd_create(const PgdConfig* cfg, int device, PgdHandle** out) {
   CU(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&h->own_stream2, cudaStreamNonBlocking));
   CU(cudaEventCreateWithFlags(&h->ev_act, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&h->ev_last, cudaEventDisableTiming));
   CU(cudaEventCreate(&h->ev0));
   CU(cudaEventCreate(&h->ev1));
   *out = h;
@@ -82,6 +84,7 @@ extern "C" int pgd_destroy(PgdHandle* h) {
   cudaStreamDestroy(h->own_stream);
   cudaStreamDestroy(h->own_stream2);
   cudaEventDestroy(h->ev_act);
+  cudaEventDestroy(h->ev_last);
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
   delete h;
   return 0;
@@ -132,6 +135,14 @@ static int launch_step(PgdHandle* h, int mode, int env_begin, int env_end, const
   return pgd_launch_step(h, mode, env_begin, env_end, actions, obs, reward, done, info, st);
 }
 
+// pgd_step_host runs on the handle's own (non-blocking) streams; pgd_reset / pgd_step run on the caller's.  Both touch
+// the same simulator state, so the host-buffer step waits for whatever was enqueued last on the caller's stream.
+static int note_caller_stream(PgdHandle* h, cudaStream_t st) {
+  CU(cudaEventRecord(h->ev_last, st));
+  h->have_last = true;
+  return 0;
+}
+
 extern "C" int pgd_reset(PgdHandle* h, const int32_t* env_ids, const int32_t* episode_ids, int32_t n, float* obs_dev,
                          PgdInfo* info_dev, void* stream) {
   if (!h || !episode_ids || !obs_dev) return fail(-1, "pgd_reset: null argument");
@@ -156,7 +167,9 @@ extern "C" int pgd_reset(PgdHandle* h, const int32_t* env_ids, const int32_t* ep
                                                          h->cfg.num_envs);
   h->launches++;
   CU(cudaGetLastError());
-  return launch_step(h, 1, 0, h->cfg.num_envs, nullptr, obs_dev, nullptr, nullptr, info_dev, st);
+  const int rc = launch_step(h, 1, 0, h->cfg.num_envs, nullptr, obs_dev, nullptr, nullptr, info_dev, st);
+  if (rc) return rc;
+  return note_caller_stream(h, st);
 }
 
 extern "C" int pgd_step(PgdHandle* h, const float* actions_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev,
@@ -164,8 +177,10 @@ extern "C" int pgd_step(PgdHandle* h, const float* actions_dev, float* obs_dev, 
   if (!h || !actions_dev || !obs_dev || !reward_dev || !done_dev) return fail(-1, "pgd_step: null argument");
   if (!h->tables_loaded) return fail(-3, "pgd_step: no tables loaded");
   CU(cudaSetDevice(h->device));
-  return launch_step(h, 0, 0, h->cfg.num_envs, actions_dev, obs_dev, reward_dev, done_dev, info_dev,
-                     (cudaStream_t)stream);
+  const int rc = launch_step(h, 0, 0, h->cfg.num_envs, actions_dev, obs_dev, reward_dev, done_dev, info_dev,
+                             (cudaStream_t)stream);
+  if (rc) return rc;
+  return note_caller_stream(h, (cudaStream_t)stream);
 }
 
 static int ensure_staging(PgdHandle* h) {
@@ -210,6 +225,7 @@ extern "C" int pgd_step_host(PgdHandle* h, const float* actions, float* obs, flo
   float* r_dst = direct ? reward : h->h_rew;
   uint8_t* d_dst = direct ? done : h->h_done;
   PgdInfo* i_dst = direct ? info : h->h_info;
+  if (h->have_last) CU(cudaStreamWaitEvent(st, h->ev_last, 0));  // order after the caller-stream reset / step
   memcpy(h->h_act, actions, n * 8);
   CU(cudaMemcpyAsync(h->d_act, h->h_act, n * 8, cudaMemcpyHostToDevice, st));
   // The step is cut into chunks of environments on two streams so that the device-to-host copy of one chunk (the
@@ -276,7 +292,7 @@ extern "C" int pgd_get_state(PgdHandle* h, int32_t env, PgdEnvState* out) {
     s->steer = ctrl[i].x; s->throttle = ctrl[i].y; s->pid_hp = ctrl[i].z; s->pid_hi = ctrl[i].w;
     s->pid_lp = pidl[i].x; s->pid_li = pidl[i].y; s->target_speed = pidl[i].z; s->yaw_rate = pidl[i].w;
     s->lane = nav[i].x; s->ck0 = nav[i].y & 0xffff; s->ck1 = nav[i].y >> 16; s->rt_lane = nav[i].z;
-    s->timer = nav[i].w; s->rnd_n = misc[i].x; s->airborne = misc[i].y; s->flags = misc[i].z;
+    s->timer = nav[i].w; s->rnd_n = misc[i].x; s->airborne = misc[i].y; s->flags = misc[i].z & ~PGD_INTERNAL_V_POSE_SET;
   }
   return 0;
 }
@@ -298,7 +314,9 @@ extern "C" int pgd_set_state(PgdHandle* h, int32_t env, const PgdEnvState* in) {
     ctrl[i] = make_float4(s->steer, s->throttle, s->pid_hp, s->pid_hi);
     pidl[i] = make_float4(s->pid_lp, s->pid_li, s->target_speed, s->yaw_rate);
     nav[i] = make_int4(s->lane, s->ck0 | (s->ck1 << 16), s->rt_lane, s->timer);
-    misc[i] = make_int4(s->rnd_n, s->airborne, s->flags, 0);
+    // a parked vehicle normally takes its pose from the episode template; this one was placed by the caller
+    const bool parked = (s->flags & PGD_V_ALIVE) && !(s->flags & PGD_V_ACTIVE);
+    misc[i] = make_int4(s->rnd_n, s->airborne, s->flags | (parked ? PGD_INTERNAL_V_POSE_SET : 0), 0);
   }
   CU(copy_slots(h, h->S.pose, env, pose, false));
   CU(copy_slots(h, h->S.ctrl, env, ctrl, false));

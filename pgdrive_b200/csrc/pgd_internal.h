@@ -69,6 +69,8 @@ struct PgdHandle {
   PgdInfo* d_info;
   cudaStream_t own_stream, own_stream2;
   cudaEvent_t ev_act;
+  cudaEvent_t ev_last;  // recorded after every enqueue on the caller's stream; the host-buffer step waits for it
+  bool have_last;
   // timing
   int timing;
   cudaEvent_t ev0, ev1;

@@ -1547,9 +1547,12 @@ PGD_HD inline int generate_one(uint64_t seed, const GenConfig& cfg, const GenCap
   const int n_cells = nx * ny;
   if (n_cells + 1 > g.caps.cells) return GEN_ERR_CELLS;
   for (int c = 0; c <= n_cells; ++c) out.cell_start[c] = 0;
-  for (int pass = 0; pass < 2; ++pass) {
+  // pass 0 counts; passes 1 and 2 fill: lane-surface boxes first, then the rest with PGD_ENTRY_NOT_LANE set
+  for (int pass = 0; pass < 3; ++pass) {
     for (int i = 0; i < n_boxes; ++i) {
       const GBox& b = g.s.boxes[i];
+      if (pass == 1 && b.kind != PGD_BOX_LANE) continue;
+      if (pass == 2 && b.kind == PGD_BOX_LANE) continue;
       double ex = fabs(b.ux) * b.hl + fabs(b.uy) * b.hw + MARGIN;
       double ey = fabs(b.uy) * b.hl + fabs(b.ux) * b.hw + MARGIN;
       int ix0 = (int)floor((b.cx - ex - x0) / CELL), ix1 = (int)floor((b.cx + ex - x0) / CELL);
@@ -1558,9 +1561,10 @@ PGD_HD inline int generate_one(uint64_t seed, const GenConfig& cfg, const GenCap
         for (int ix = ix0; ix <= ix1; ++ix) {
           int c = iy * nx + ix;
           if (pass == 0) out.cell_start[c + 1]++;
-          else out.cell_entries[out.cell_start[c]++] = i;
+          else out.cell_entries[out.cell_start[c]++] = pass == 1 ? i : (i | PGD_ENTRY_NOT_LANE);
         }
     }
+    if (pass == 1) continue;
     if (pass == 0) {
       int total = 0;
       for (int c = 0; c < n_cells; ++c) {

@@ -69,6 +69,9 @@ namespace pgdstep {
 #define PGS_MAX_SUBSTEPS 8 /* decision_repeat supported (default 5) */
 #define PGS_LANES 32       /* environments per CTA = lanes of a warp */
 #define PGS_MAX_ROLES 8
+/* internal bit of the per-slot flag word: pgd_set_state wrote this parked vehicle's pose, read it from the state
+ * instead of the episode template (masked out of pgd_get_state) */
+#define PGS_V_POSE_SET 8
 
 struct alignas(16) F4 { float x, y, z, w; };
 struct alignas(16) I4 { int x, y, z, w; };
@@ -550,7 +553,13 @@ PGS_HD void phase_a(Smem<V, R>& sm, Thr<V, R>& th, const State& S, const PgdConf
       } else {
         // Traffic that has not been woken yet has never been touched by IDM, physics (it is at rest) or localisation:
         // its pose is the episode template's (L2-resident, shared by all environments on the seed).
-        x = t.x; y = t.y; h = t.heading; lane = t.lane;
+        if (fl & PGS_V_POSE_SET) {  // placed by pgd_set_state
+          const F4 p = S.pose[gi];
+          x = p.x; y = p.y; h = p.z;
+          lane = S.nav[gi].x;
+        } else {
+          x = t.x; y = t.y; h = t.heading; lane = t.lane;
+        }
         if (t.group == th.trig) fl |= PGD_V_ACTIVE;
       }
     }
@@ -843,19 +852,23 @@ PGS_HD void bucket_scan(const PgdMap& mp, const PgdLane* lanes, const PgdBox* bo
   if (!(cx >= 0 && cy >= 0 && cx < mp.nx && cy < mp.ny)) return;
   const int cell = mp.cell_off + cy * mp.nx + cx;
   const int b0 = ldg(&T.cell_start[cell]), b1 = ldg(&T.cell_start[cell + 1]);
-  // entries are fetched four at a time (indices, then records) so that their latencies overlap
+  // entries are fetched four at a time (indices, then records) so that their latencies overlap; inside a cell the
+  // lane-surface boxes come first, everything else carries PGD_ENTRY_NOT_LANE: traffic stops there
   for (int k0 = b0 + 4 * first; k0 < b1; k0 += 4 * stride) {
     int bb[4];
     PgdBox gg[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) bb[j] = (k0 + j < b1) ? ldg(&ent[k0 + j]) : -1;
+    for (int j = 0; j < 4; ++j) {
+      bb[j] = (k0 + j < b1) ? ldg(&ent[k0 + j]) : -1;
+      if (!EGO && bb[j] >= PGD_ENTRY_NOT_LANE) bb[j] = -1;
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j)
-      if (bb[j] >= 0) gg[j] = load_rec(boxes + bb[j]);
+      if (bb[j] >= 0) gg[j] = load_rec(boxes + (bb[j] & PGD_ENTRY_ID_MASK));
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       if (bb[j] < 0) continue;
-      const int b = bb[j];
+      const int b = bb[j] & PGD_ENTRY_ID_MASK;
       const PgdBox& g = gg[j];
       if (g.kind == PGD_BOX_LANE) {
         const float dx = x - g.cx, dy = y - g.cy;
@@ -880,6 +893,7 @@ PGS_HD void bucket_scan(const PgdMap& mp, const PgdLane* lanes, const PgdBox* bo
                    : g.kind == PGD_BOX_BROKEN ? PGD_F_ON_BROKEN : PGD_F_CRASH_SIDEWALK;
       }
     }
+    if (!EGO && bb[3] < 0) break;  // ran into the flagged part (or the end) of the cell
   }
 }
 
@@ -1316,7 +1330,9 @@ PGS_HD void task_detectors(const Smem<V, R>& sm, const Thr<V, R>& th, const Tabl
       const int b0 = ldg(&T.cell_start[cell]), b1 = ldg(&T.cell_start[cell + 1]);
 #pragma unroll 1
       for (int k = b0; k < b1; ++k) {
-        const PgdBox g = load_rec(th.boxes + ldg(&ent[k]));
+        const int en = ldg(&ent[k]);
+        if (en < PGD_ENTRY_NOT_LANE) continue;  // lane-surface boxes are no ray targets
+        const PgdBox g = load_rec(th.boxes + (en & PGD_ENTRY_ID_MASK));
         if (!(g.kind == PGD_BOX_WHITE || g.kind == PGD_BOX_YELLOW || (!side && g.kind == PGD_BOX_BROKEN))) continue;
         const Rect r = {g.cx, g.cy, g.ux, g.uy, g.hl, g.hw};
         best = fminf(best, ray_rect(ex, ey, dx, dy, r));

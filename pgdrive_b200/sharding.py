@@ -48,14 +48,24 @@ class _DevArray:
 
 
 class PeerGather:
-    """Gather to rank 0 fused into the step kernel: rank 0 owns ``depth`` whole-batch buffers, every other rank maps
-    them through CUDA IPC and hands the step kernel pointers to ITS rows, so observations / rewards / dones are
-    written over NVLink as they are produced.  No collective carries payload; a per-step ``completion_barrier``
-    (a 4-byte all-reduce) tells rank 0 that every rank's kernel for that buffer has finished."""
-    def __init__(self, env, torch, dist, n_local, world_size, rank, obs_dim=274, depth=2):
+    """Gather to rank 0 over CUDA-IPC peer mappings: rank 0 owns ``depth`` whole-batch buffers, every other rank maps
+    them.  Two ways to fill them:
+
+    ``mode="peer"``  fused into the step kernel: a rank hands the kernel pointers to ITS rows of rank 0's buffer, so
+                     observations / rewards / dones are written over NVLink as they are produced (one bulk store per
+                     32 environments); no collective carries payload.
+    ``mode="copy"``  the kernel writes local rows; ``push(i)`` copies them into rank 0's buffer with the copy engine
+                     (enqueue it on a side stream: it overlaps the next step's kernel and the SMs are free meanwhile).
+
+    In both, ``completion_barrier`` (a 4-byte all-reduce) tells rank 0 that every rank's rows of that buffer have
+    landed, and -- because rank 0 enqueues its reads of buffer i before it joins the barrier of step i + 1 -- a rank
+    that waits for barrier i + 1 before writing buffer i again (step i + 2) never overwrites unread rows."""
+    def __init__(self, env, torch, dist, n_local, world_size, rank, obs_dim=274, depth=2, mode="peer"):
         import ctypes as C
         from . import cabi
-        self.env, self.torch, self.dist = env, torch, dist
+        if mode not in ("peer", "copy"):
+            raise ValueError("mode must be 'peer' or 'copy'")
+        self.env, self.torch, self.dist, self.mode = env, torch, dist, mode
         self.n, self.world, self.rank, self.depth, self.obs_dim = n_local, world_size, rank, depth, obs_dim
         rows = world_size * n_local
         self.obs_bytes, self.rew_bytes = rows * obs_dim * 4, rows * 4
@@ -74,12 +84,44 @@ class PeerGather:
             cabi.check(e.lib, e.lib.pgd_peer_open(e.h, blob[0], C.byref(base)))
         self.base = base.value
         self._flag = torch.zeros(1, dtype=torch.int32, device=e.device)
+        self._local = None
+        if mode == "copy" and rank != 0:
+            dev = e.device
+            self._local = [(torch.empty((n_local, obs_dim), dtype=torch.float32, device=dev),
+                            torch.empty(n_local, dtype=torch.float32, device=dev),
+                            torch.empty(n_local, dtype=torch.uint8, device=dev)) for _ in range(depth)]
 
-    def pointers(self, i):
-        """(obs, reward, done) device pointers of THIS rank's rows in buffer ``i``."""
+    def _offsets(self, i):
         b = self.base + (i % self.depth) * self.stride
         return (b + self.rank * self.n * self.obs_dim * 4, b + self.obs_bytes + self.rank * self.n * 4,
                 b + self.obs_bytes + self.rew_bytes + self.rank * self.n)
+
+    def pointers(self, i):
+        """(obs, reward, done) device pointers of THIS rank's rows in rank 0's buffer ``i``."""
+        return self._offsets(i)
+
+    def local_pointers(self, i):
+        """mode "copy", rank > 0: pointers of the local staging rows the kernel writes before ``push``."""
+        return tuple(t.data_ptr() for t in self._local[i % self.depth])
+
+    def _wrap(self, ptr, shape, typestr):
+        return self.torch.as_tensor(_DevArray(ptr, shape, typestr), device=self.env.engine.device)
+
+    def remote_views(self, i):
+        """THIS rank's rows of rank 0's buffer ``i`` as tensors (peer-mapped memory on ranks > 0)."""
+        o, r, d = self._offsets(i)
+        return (self._wrap(o, (self.n, self.obs_dim), "<f4"), self._wrap(r, (self.n, ), "<f4"),
+                self._wrap(d, (self.n, ), "|u1"))
+
+    def local_views(self, i, remote=False):
+        """The rows this rank's kernel wrote for buffer ``i`` (local staging, or its rows of rank 0's buffer)."""
+        return self.remote_views(i) if remote or self._local is None else self._local[i % self.depth]
+
+    def push(self, i):
+        """mode "copy", rank > 0: enqueue (current stream) the device-to-device copies of the local rows into rank 0's
+        buffer ``i`` -- contiguous, so the driver hands them to the copy engine."""
+        for dst, src in zip(self.remote_views(i), self._local[i % self.depth]):
+            dst.copy_(src, non_blocking=True)
 
     def completion_barrier(self):
         """Enqueue (on the current stream) a barrier after which rank 0 may read the buffer written last."""
@@ -89,13 +131,10 @@ class PeerGather:
     def tensors(self, i):
         """Rank 0 only: the whole-batch (obs, reward, done) tensors of buffer ``i``."""
         assert self.rank == 0
-        t = self.torch
         rows = self.world * self.n
         b = self.base + (i % self.depth) * self.stride
-        obs = t.as_tensor(_DevArray(b, (rows, self.obs_dim), "<f4"), device=self.env.engine.device)
-        rew = t.as_tensor(_DevArray(b + self.obs_bytes, (rows, ), "<f4"), device=self.env.engine.device)
-        done = t.as_tensor(_DevArray(b + self.obs_bytes + self.rew_bytes, (rows, ), "|u1"), device=self.env.engine.device)
-        return obs, rew, done
+        return (self._wrap(b, (rows, self.obs_dim), "<f4"), self._wrap(b + self.obs_bytes, (rows, ), "<f4"),
+                self._wrap(b + self.obs_bytes + self.rew_bytes, (rows, ), "|u1"))
 
     def close(self):
         import ctypes as C

@@ -64,6 +64,7 @@ SIDEWALK_WIDTH = 3.0
 SIDEWALK_GAP = 0.6
 CELL = 8.0  # bucket size [m]
 GRID_MARGIN = 4.0  # >= half diagonal of the largest chassis (5.8 x 2.3 -> 3.12 m)
+ENTRY_NOT_LANE = 1 << 30  # PGD_ENTRY_NOT_LANE (include/pgd_tables.h)
 
 GRAVITY = 9.81
 
@@ -243,9 +244,9 @@ class TableSet:
                     cells[iy * nx + ix].append(b)
         cell_off, entry_off = len(self.cell_start), len(self.cell_entries)
         pos = 0
-        for c in cells:
+        for c in cells:  # lane-surface boxes first, the rest flagged (PGD_ENTRY_NOT_LANE, include/pgd_tables.h)
             self.cell_start.append(pos)
-            self.cell_entries += c
+            self.cell_entries += [b for b in c if boxes[b][6] == 0] + [b | ENTRY_NOT_LANE for b in c if boxes[b][6] != 0]
             pos += len(c)
         self.cell_start.append(pos)
         self.maps.append((lane_off, len(mi.lanes), road_off, len(mi.road_list), box_off, len(boxes), cell_off,

@@ -201,6 +201,27 @@ def test_host_buffer_step_equals_device_step(n):
     env_b.close()
 
 
+def test_reset_then_host_buffer_step_are_ordered():
+    """pgd_step_host runs on the handle's own streams; it must wait for the reset kernels that the caller's stream
+    still has in flight (a large batch makes the reset pass long enough to overlap if it did not)."""
+    from oracle.oracle import Oracle
+    n = 32768
+    env, _ = _pair(n, list(range(1000, 1100)))
+    ref = Oracle(env.T, 200, auto_reset=True)
+    rs = np.random.RandomState(7)
+    for rep in range(3):
+        env.reset()  # asynchronous on torch's current stream
+        a = rs.uniform(-1, 1, (n, 2)).astype(np.float32)
+        o, r, d, info = env.step(a)  # host buffers: the handle's own streams
+        ref.reset(range(200), [i % 100 for i in range(200)])
+        ro, rr, rd, rinfo = ref.step(a[:200])
+        assert np.array_equal(o[:200], ro) and np.array_equal(r[:200], rr) and np.array_equal(d[:200], rd)
+        assert not (info["flags"] & 1024).any()  # no environment treated the step as a second reset
+        idx = np.arange(n) % 100
+        assert np.array_equal(o[100:200], o[:100]) and np.array_equal(o[idx[:4096] + 100], o[idx[:4096]])
+    env.close()
+
+
 def test_horizon_and_partial_reset():
     import torch
     env, ref = _pair(8, [1000, 1001], horizon=5, auto_reset=False)
@@ -268,12 +289,12 @@ def test_full_size_65536_envs_replicas_and_oracle():
     env.close()
 
 
-def test_1000envs_config_with_32_slots():
-    """BASELINE.json configs[3]: PGDrive-1000envs-v0, 1000 distinct maps, up to 17 vehicles -> 32 slots."""
+def test_1000envs_config_with_24_slots():
+    """BASELINE.json configs[3]: PGDrive-1000envs-v0, 1000 distinct maps, up to 17 vehicles -> 24 slots."""
     seeds = list(range(1000, 2000))
     n = 2000
     env, ref = _pair(n, seeds)
-    assert env.engine.num_slots == 32
+    assert env.engine.num_slots == 24
     o, ro = _reset_both(env, ref)
     assert np.array_equal(o, ro)
     rs = np.random.RandomState(4)

@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import bench
 from pgdrive_b200 import VecPGDriveEnv
-n = int(os.environ.get("ENVS", 65536)); K = int(os.environ.get("STEPS", 200)); W = 40
+n = int(os.environ.get("ENVS", 65536)); K = int(os.environ.get("STEPS", 200)); W = int(os.environ.get('WARM', 130))
 T = bench.build_tables()
 env = VecPGDriveEnv(dict(start_seed=1000, environment_num=100, num_envs=n, traffic_density=0.1, num_slots=16), tables_dict=T)
 env.reset()
