@@ -211,14 +211,14 @@ def test_reset_then_host_buffer_step_are_ordered():
     rs = np.random.RandomState(7)
     for rep in range(3):
         env.reset()  # asynchronous on torch's current stream
-        a = rs.uniform(-1, 1, (n, 2)).astype(np.float32)
+        idx = np.arange(n) % 100  # replicas of a seed get the same action
+        a = rs.uniform(-1, 1, (100, 2)).astype(np.float32)[idx]
         o, r, d, info = env.step(a)  # host buffers: the handle's own streams
         ref.reset(range(200), [i % 100 for i in range(200)])
         ro, rr, rd, rinfo = ref.step(a[:200])
         assert np.array_equal(o[:200], ro) and np.array_equal(r[:200], rr) and np.array_equal(d[:200], rd)
         assert not (info["flags"] & 1024).any()  # no environment treated the step as a second reset
-        idx = np.arange(n) % 100
-        assert np.array_equal(o[100:200], o[:100]) and np.array_equal(o[idx[:4096] + 100], o[idx[:4096]])
+        assert np.array_equal(o, o[:100][idx])
     env.close()
 
 
