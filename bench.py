@@ -7,8 +7,9 @@
 Own arm: every rank steps `--envs` (default 65 536) PGDrive-v0 environments (seeds 1000..1099, traffic density
 0.1, 240-beam lidar, 16 vehicle slots); a "step" is ONE kernel launch advancing all of them by one decision step
 (5 physics sub-steps + observation + reward/done, auto-reset of finished episodes).  Every timed region starts
-after an untimed pre-roll of 128 steps of the same policy, so the number does not depend on where in the episode
-distribution the timer starts (fresh resets are the cheapest state of the simulator).  Weak scaling: with N ranks
+after an untimed pre-roll of the same policy (2 048 steps for the random policy, whose episodes last ~1 000 steps;
+256 for the driving policy), so the number does not depend on where in the episode distribution the timer starts
+(fresh resets are the cheapest state of the simulator: 0.10 ms per step against 0.29 ms in the steady state).  Weak scaling: with N ranks
 the job simulates N x 65 536 environments and every step rank 0 receives the whole observation / reward / done
 batch (--gather, DESIGN.md "Multi-GPU") and READS it (a checksum kernel stands for the policy network).
   value        device-resident, random policy of BASELINE.md: actions pre-generated in HBM, CUDA-event time of K
@@ -41,7 +42,10 @@ import numpy as np  # noqa: E402
 
 OBS_DIM = 274
 INFO_BYTES = 40
-PREROLL = 128  # untimed steps before every timed region (the episode-length distribution reaches its steady state)
+PREROLL = 2048  # untimed random-policy steps before the timed region: the cost of a step climbs from 0.10 ms right
+# after a reset to a 0.33 ms peak near step 400 and settles by step ~2000 (mean episode ~1000 steps,
+# profiles/r02i_cost_curve_*.log); the driving policy (mean episode ~50 steps) is steady after 256
+PREROLL_DRIVING = 256
 SMS, ISSUE_PER_SM_CLK = 148, 4  # B200: 148 SMs x 4 warp schedulers, one warp instruction per scheduler per clock
 
 WORKLOADS = {
@@ -243,7 +247,7 @@ def run_own(args):
 
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)  # Philox counter-based stream, one per rank
-    n_act = max(W + K, PREROLL)
+    n_act = max(W + K, 256)
     actions = torch.rand((n_act, n, 2), generator=gen, device=dev, dtype=torch.float32) * 2 - 1
     fwd = actions.clone()  # a policy that drives: never brakes, small steering noise
     fwd[..., 1] = fwd[..., 1].abs()
@@ -329,7 +333,7 @@ def run_own(args):
     # ---- headline: BASELINE.md's random policy, gather included -------------------------------------------------------
     env.reset()
     for t in range(PREROLL):  # untimed pre-roll: not tied to --steps / --warmup
-        env.step(actions[t])
+        env.step(actions[t % n_act])
     for t in range(W):
         step_and_gather(actions[t])
     drain()
@@ -351,8 +355,8 @@ def run_own(args):
 
     # ---- the same kernel under a policy that drives (own pre-roll, own roofline) -----------------------------------------
     env.reset()
-    for t in range(PREROLL):
-        env.step(fwd[t])
+    for t in range(PREROLL_DRIVING):
+        env.step(fwd[t % n_act])
     fwd_k = min(K, fwd.shape[0])
     fwd_ms, fwd_kernel_ms = timed(fwd[:fwd_k], fwd_k, lambda a: env.step(a))
     fwd_done_rate = float(env.done.float().mean().item())
@@ -360,7 +364,7 @@ def run_own(args):
     # ---- end to end through the public host-buffer API ------------------------------------------------------------------
     env.reset()
     for t in range(PREROLL):
-        env.step(actions[t])
+        env.step(actions[t % n_act])
     e2e_steps = min(K, 64)
     h_actions = actions[W:W + e2e_steps].cpu().numpy()
     for t in range(min(W, 4)):
@@ -504,6 +508,7 @@ def run_own(args):
         config=dict(
             workload=desc % n, envs_per_gpu=n, total_envs=total_envs, parallelism="env-sharded x%d" % world,
             actions="uniform[-1,1]^2, Philox, pre-generated in HBM", preroll_steps=PREROLL,
+            preroll_steps_driving=PREROLL_DRIVING,
             arithmetic="float32 throughout; the reference's Python side computes in float64, Bullet in float32",
             l2="no flush: state + observations touched per step = %.0f MB > 126 MB L2" % (
                 (2 * (80 * n_slots + 32) + 4 * OBS_DIM) * n / 1e6),

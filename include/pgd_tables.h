@@ -26,6 +26,11 @@ enum { PGD_BOX_LANE = 0, PGD_BOX_WHITE = 1, PGD_BOX_YELLOW = 2, PGD_BOX_BROKEN =
  * everything else (ascending id) with this bit set, so that a scan for lanes stops at the first flagged entry and a
  * scan for line ghosts skips the others without touching the box records. */
 enum { PGD_ENTRY_NOT_LANE = 1 << 30, PGD_ENTRY_ID_MASK = (1 << 30) - 1 };
+/* Bucket grid geometry: square cells of PGD_GRID_CELL metres; a box is listed in every cell that its bounding rectangle
+ * grown by PGD_GRID_MARGIN touches (>= the half diagonal of the largest chassis, 5.8 x 2.3 m -> 3.12 m, so the cell
+ * under a chassis centre lists everything the chassis can overlap; a detector ray samples a point every 2 margins). */
+#define PGD_GRID_CELL 4.0
+#define PGD_GRID_MARGIN 3.2
 /* PGD_OBS_DIM is the PGDrive-v0 observation (no side / lane-line detector); with detectors see pgd_obs_dim(). */
 enum { PGD_MAX_SLOTS = 32, PGD_MAX_GROUPS = 11, PGD_N_RND25 = 16, PGD_OBS_DIM = 274, PGD_LIDAR_BEAMS = 240,
        PGD_MAX_DETECTOR_BEAMS = 240 };
@@ -56,6 +61,10 @@ typedef struct {          /* 64 B */
   float lane_width;       /* map_config lane_width */
   int32_t lane_num, pad;
 } PgdMap;
+
+/* PgdSlot.group: >= 0 trigger group (woken when the ego reaches the group's road), -1 the ego, PGD_GROUP_AWAKE a
+ * traffic vehicle that drives from the first step (traffic_mode "respawn", manager/traffic_manager.py:63-66,224-237) */
+enum { PGD_GROUP_AWAKE = -2 };
 
 typedef struct {          /* 96 B */
   float x, y, heading;    /* spawn pose */

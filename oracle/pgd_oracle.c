@@ -767,7 +767,7 @@ static void load_template(Oracle* o, Env* e, int episode) {
     v->airborne = s->drop_substeps;
     v->target_speed = IDM_NORMAL_SPEED;
     v->alive = 1;
-    v->active = i == 0;
+    v->active = i == 0 || s->group == PGD_GROUP_AWAKE; /* respawn mode: traffic drives from the first step */
     v->on_lane = 1;
   }
 }

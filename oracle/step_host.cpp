@@ -37,12 +37,15 @@ static void run_vr(HostStep* h, int mode, const float* actions, float* obs, floa
         any = any || th[r][l].valid;
       }
     if (!any) continue;
+    for (int r = 0; r < R; ++r) for (int l = 0; l < PGS_LANES; ++l) phase_0(sm, th[r][l]);
 #define ALL(call) for (int r = 0; r < R; ++r) for (int l = 0; l < PGS_LANES; ++l) { Thr<V, R>& t = th[r][l]; (void)t; call; }
     ALL(phase_a(sm, t, h->S, h->cfg, actions));
     ALL(phase_b(sm, t, rows));
     ALL(phase_c(sm, t, h->T, h->S, h->cfg, rows, traj));
+    ALL(phase_c_traffic(sm, t, h->T, h->S, rows));
     for (int i = 0; i < PGS_LANES * od; ++i) rows[i] = 1.0f;
     ALL(phase_d(sm, t, h->T, h->S, h->cfg, traj));
+    ALL(phase_d_traffic(sm, t, h->T, h->S, h->cfg, traj));
     ALL(phase_f(sm, t, h->T, h->S, h->cfg, mode, od, rows, vis, reward, done, info));
     ALL(phase_l(sm, h->T, h->S, r, l, n, env0, od, rows, vis));
 #undef ALL

@@ -203,7 +203,7 @@ def default_config():
 # value and rejected otherwise, so that a config that silently changed behaviour cannot slip through.
 UNSUPPORTED_IF_CHANGED = {
     "num_agents": 1, "is_multi_agent": False, "IDM_agent": False,
-    "use_render": False, "manual_control": False, "use_topdown": False, "offscreen_render": False, "traffic_mode": "trigger",
+    "use_render": False, "manual_control": False, "use_topdown": False, "offscreen_render": False,
     "random_traffic": False, "accident_prob": 0., "gaussian_noise": 0.0,
     "dropout_prob": 0.0, "record_episode": False,
 }
@@ -213,6 +213,8 @@ def check_supported(cfg):
     for k, v in UNSUPPORTED_IF_CHANGED.items():
         if cfg[k] != v:
             raise NotImplementedError("config[%r]=%r is not supported by the batched simulator (only %r)" % (k, cfg[k], v))
+    if cfg["traffic_mode"] not in ("trigger", "hybrid", "respawn"):
+        raise ValueError("No such mode named {}".format(cfg["traffic_mode"]))  # traffic_manager.py:69
     if (cfg["random_lane_width"] or cfg["random_lane_num"]) and cfg["load_map_from_json"]:
         # manager/map_manager.py:158-166
         raise AssertionError("You are supposed to turn off the load_map_from_json")

@@ -1527,8 +1527,8 @@ PGD_HD inline int generate_one(uint64_t seed, const GenConfig& cfg, const GenCap
     }
   }
   if (g.status != GEN_OK) return g.status;
-  // ---- bucket grid (tables.py add_map): 8 m cells over the boxes grown by 4 m
-  const double CELL = 8.0, MARGIN = 4.0;
+  // ---- bucket grid (tables.py add_map): PGD_GRID_CELL cells over the boxes grown by PGD_GRID_MARGIN
+  const double CELL = PGD_GRID_CELL, MARGIN = PGD_GRID_MARGIN;
   double minx = 1e300, maxx = -1e300, miny = 1e300, maxy = -1e300;
   for (int i = 0; i < n_boxes; ++i) {
     const GBox& b = g.s.boxes[i];

@@ -343,12 +343,15 @@ typedef int (*VisPtr)[PGS_LANES];
 template <int V, int R>
 struct Smem {
   Pub<V> p;
-  F4 efin[PGS_LANES];                     // ego pose after the sub-steps (template pose when the episode restarts)
-  int scan[R][4][PGS_LANES];              // ego bucket scan, one share per role: b_any, b_cur, b_next, PGD_F_* flags
-  int amask[R][PGS_LANES], pmask[R][PGS_LANES], crash[R][PGS_LANES];  // one word per role: no atomics, no clearing
+  F4 efin[PGS_LANES];                    // ego pose after the sub-steps (template pose when the episode restarts)
+  int scan[4][PGS_LANES];                // ego bucket scan, combined over the roles: b_any, b_cur, b_next (min), flags (or)
+  int amask[PGS_LANES], pmask[PGS_LANES], crash[PGS_LANES];  // awake / parked traffic slots, chassis contact (or-ed in)
   float last_x[PGS_LANES], last_y[PGS_LANES], ego_travel[PGS_LANES], ego_h[PGS_LANES], ego_v[PGS_LANES],
       ego_hl[PGS_LANES], ego_hw[PGS_LANES];
   int ego_ck[PGS_LANES], n_vis[PGS_LANES], wrote[PGS_LANES];
+  int ctx_map[PGS_LANES], ctx_slot_off[PGS_LANES];  // map id / first template slot of each environment (for work items)
+  int n_work;
+  int work[(V - 1) * PGS_LANES];         // awake traffic of the whole CTA: lane | slot << 8, dealt to all traffic threads
 };
 
 template <int V, int R>
@@ -387,6 +390,20 @@ struct Thr {  // what a thread keeps across the phases
 };
 
 PGS_HD int imin(int a, int b) { return a < b ? a : b; }
+PGS_HD void smem_or(int* p, int v) {  // shared-memory word combined by several roles
+#ifdef __CUDA_ARCH__
+  if (v) atomicOr(p, v);
+#else
+  *p |= v;
+#endif
+}
+PGS_HD void smem_min(int* p, int v) {
+#ifdef __CUDA_ARCH__
+  atomicMin(p, v);
+#else
+  if (v < *p) *p = v;
+#endif
+}
 PGS_HD int ctz32(uint32_t m) {
 #ifdef __CUDA_ARCH__
   return __ffs((int)m) - 1;
@@ -405,7 +422,7 @@ PGS_HD void veh_from_template(Veh& q, const PgdSlot& t, int s) {
   q.tspeed = PGS_IDM_NORMAL_SPEED;
   q.lane = t.lane; q.ck0 = 0; q.ck1 = t.route_len > 2 ? 1 : 0; q.rt_lane = -1;
   q.timer = t.overtake_timer; q.rnd_n = 0; q.airborne = t.drop_substeps;
-  q.vflags = PGD_V_ALIVE | PGD_V_ON_LANE | (s == 0 ? PGD_V_ACTIVE : 0);
+  q.vflags = PGD_V_ALIVE | PGD_V_ON_LANE | ((s == 0 || t.group == PGD_GROUP_AWAKE) ? PGD_V_ACTIVE : 0);
 }
 
 PGS_HD void veh_unpack(Veh& q, const F4& p, const F4& c, const F4& l, const I4& n, const I4& m) {
@@ -482,14 +499,26 @@ PGS_HD void thread_init(Thr<V, R>& th, const Tables& T, const State& S, const Pg
   }
 }
 
+// ---- before phase A (same barrier interval as thread_init): clear the words that several roles combine into -------
+template <int V, int R>
+PGS_HD void phase_0(Smem<V, R>& sm, const Thr<V, R>& th) {
+  if (th.role != 0) return;
+  const int ln = th.lane;
+  sm.wrote[ln] = th.valid ? 1 : 0;
+  sm.amask[ln] = sm.pmask[ln] = sm.crash[ln] = 0;
+  sm.scan[0][ln] = sm.scan[1][ln] = sm.scan[2][ln] = INT_MAX;
+  sm.scan[3][ln] = 0;
+  sm.n_vis[ln] = 0;
+  if (th.valid) {
+    sm.ctx_map[ln] = ldg(&th.ep->map);
+    sm.ctx_slot_off[ln] = ldg(&th.ep->slot_off);
+  }
+}
+
 // ---- phase A: publish start-of-step state; ego action; traffic trigger ------------------------------------------
 template <int V, int R>
 PGS_HD void phase_a(Smem<V, R>& sm, Thr<V, R>& th, const State& S, const PgdConfig& cfg, const float* actions) {
   const int ln = th.lane;
-  if (th.role == 0) sm.wrote[ln] = th.valid ? 1 : 0;
-  sm.amask[th.role][ln] = 0;
-  sm.pmask[th.role][ln] = 0;
-  sm.crash[th.role][ln] = 0;
   if (!th.valid) return;
   Pub<V>& P = sm.p;
   // TrafficManager.before_step (traffic_manager.py:71-89): the next group wakes when the ego is on its trigger road.
@@ -567,31 +596,63 @@ PGS_HD void phase_a(Smem<V, R>& sm, Thr<V, R>& th, const State& S, const PgdConf
     PGS_SINCOS(h, sn, cs);
     P.x[s][ln] = x; P.y[s][ln] = y; P.hc[s][ln] = cs; P.hs[s][ln] = sn; P.v[s][ln] = v;
     P.lf[s][ln] = lf_pack(lane, fl);
-    if (fl & PGD_V_ACTIVE) amask |= 1u << s;
+    // an episode that restarts in this call does not act: its awake traffic (traffic_mode "respawn") is no work item
+    if ((fl & PGD_V_ACTIVE) && th.stepping) amask |= 1u << s;
     else pmask |= 1u << s;
   }
-  sm.amask[th.role][ln] = (int)amask;
-  sm.pmask[th.role][ln] = (int)pmask;
+  smem_or(&sm.amask[ln], (int)amask);
+  smem_or(&sm.pmask[ln], (int)pmask);
 }
 
 template <int V, int R>
-PGS_HD uint32_t env_amask(const Smem<V, R>& sm, int ln) {  // alive + awake traffic slots of the environment
-  uint32_t a = 0;
-#pragma unroll
-  for (int r = 1; r < R; ++r) a |= (uint32_t)sm.amask[r][ln];
-  return a;
-}
+PGS_HD uint32_t env_amask(const Smem<V, R>& sm, int ln) { return (uint32_t)sm.amask[ln]; }  // alive + awake traffic
 template <int V, int R>
-PGS_HD uint32_t env_pmask(const Smem<V, R>& sm, int ln) {  // alive + parked traffic slots
-  uint32_t a = 0;
+PGS_HD uint32_t env_pmask(const Smem<V, R>& sm, int ln) { return (uint32_t)sm.pmask[ln]; }  // alive + parked traffic
+
+/* The awake traffic of the CTA's 32 environments as ONE list (lane | slot << 8, by environment, then slot), so that
+ * phases C and D deal vehicles to ALL traffic threads of the CTA instead of to the threads of their own environment:
+ * a warp's lanes then run the same number of vehicles whatever the spread between environments.  Built by one warp
+ * (an exclusive scan of the per-environment counts); `lane` = this thread's lane in that warp. */
+template <int V, int R>
+PGS_HD void build_work_list(Smem<V, R>& sm, int lane) {
+#ifdef __CUDA_ARCH__
+  const uint32_t m = (uint32_t)sm.amask[lane];
+  const int c = __popc(m);
+  int incl = c;
 #pragma unroll
-  for (int r = 1; r < R; ++r) a |= (uint32_t)sm.pmask[r][ln];
-  return a;
+  for (int d = 1; d < 32; d <<= 1) {
+    const int up = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += up;
+  }
+  int at = incl - c;
+  for (uint32_t mm = m; mm; mm &= mm - 1) sm.work[at++] = lane | (ctz32(mm) << 8);
+  if (lane == 31) sm.n_work = incl;
+#else
+  if (lane != 0) return;  // the host build runs the "warp" as one loop
+  int at = 0;
+  for (int e = 0; e < PGS_LANES; ++e)
+    for (uint32_t mm = (uint32_t)sm.amask[e]; mm; mm &= mm - 1) sm.work[at++] = e | (ctz32(mm) << 8);
+  sm.n_work = at;
+#endif
+}
+
+/* The context of ANOTHER environment of the CTA (a work item), from what role 0 published for it. */
+template <int V, int R>
+PGS_HD void item_context(const Smem<V, R>& sm, const Thr<V, R>& th, const Tables& T, int e, Thr<V, R>& it) {
+  it.lane = e;
+  it.env = th.env - th.lane + e;
+  it.num_envs = th.num_envs;
+  it.mp = load_rec(T.maps + sm.ctx_map[e]);
+  it.lanes = T.lanes + it.mp.lane_off;
+  it.roads = T.roads + it.mp.road_off;
+  it.boxes = T.boxes + it.mp.box_off;
+  it.tpl = T.slots + sm.ctx_slot_off[e];
 }
 
 // ---- phase B: IDM look-up data (only environments with awake traffic) --------------------------------------------
 template <int V, int R>
 PGS_HD void phase_b(Smem<V, R>& sm, Thr<V, R>& th, float* obs) {
+  if (th.role == 1) build_work_list(sm, th.lane);  // every lane of the warp takes part (invalid lanes count 0)
   if (!th.valid || !th.stepping) return;
   const int ln = th.lane;
   if (!env_amask(sm, ln)) return;
@@ -814,20 +875,28 @@ PGS_HD void phase_c(Smem<V, R>& sm, Thr<V, R>& th, const Tables& T, const State&
     sm.ego_v[ln] = q.v;
     return;
   }
-  if (!th.stepping) return;
-  const uint32_t amask = env_amask(sm, ln);
-  if (!amask) return;
+  (void)ns;
+}
+
+/* Traffic half of phase C: IDM / PID of the CTA's awake vehicles, dealt to all traffic threads (any thread may get a
+ * vehicle of any of the 32 environments).  Runs for every traffic thread, also those whose own lane is idle. */
+template <int V, int R>
+PGS_HD void phase_c_traffic(Smem<V, R>& sm, const Thr<V, R>& th, const Tables& T, const State& S, const float* obs) {
+  if (th.role == 0) return;
   const Pub<V>& P = sm.p;
-  const uint32_t alive = amask | env_pmask(sm, ln) | 1u;
+  const int n_work = sm.n_work;
 #pragma unroll 1
-  for (uint32_t m = drop_low(amask, th.role - 1); m; m = drop_low(m, R - 1)) {
-    const int s = ctz32(m);
-    const size_t gi = (size_t)s * th.num_envs + th.env;
+  for (int i = (th.role - 1) * PGS_LANES + th.lane; i < n_work; i += (R - 1) * PGS_LANES) {
+    const int e = sm.work[i] & 0xff, s = sm.work[i] >> 8;
+    Thr<V, R> it;
+    item_context(sm, th, T, e, it);
+    const uint32_t alive = env_amask(sm, e) | env_pmask(sm, e) | 1u;
+    const size_t gi = (size_t)s * it.num_envs + it.env;
     Veh q;
     veh_load(q, S, gi);
-    q.vflags = P.lf[s][ln] & 0xff;  // a vehicle woken in this step carries ACTIVE only in shared memory so far
-    q.hc = P.hc[s][ln]; q.hs = P.hs[s][ln];
-    idm_act(sm, th, T, obs, alive, q, s);
+    q.vflags = P.lf[s][e] & 0xff;  // a vehicle woken in this step carries ACTIVE only in shared memory so far
+    q.hc = P.hc[s][e]; q.hs = P.hs[s][e];
+    idm_act(sm, it, T, obs, alive, q, s);
     // hand-over to phase D through the vehicle's own state record (the same thread picks it up)
     const F4 c = {q.steer, q.throttle, q.hp, q.hi}, l = {q.lp, q.li, q.tspeed, q.yaw};
     const I4 n = {q.lane, q.ck0 | (q.ck1 << 16), q.rt_lane, q.timer}, mm = {q.rnd_n, q.airborne, q.vflags, 0};
@@ -942,14 +1011,7 @@ template <int V, int R>
 PGS_HD void ego_after_scan(const Smem<V, R>& sm, const Thr<V, R>& th, const Tables& T, int& lane, int& ck0, int& ck1,
                           bool& on_lane, uint32_t& flags) {
   const int ln = th.lane;
-  ScanOut sc = {INT_MAX, INT_MAX, INT_MAX, 0u};
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    sc.b_any = imin(sc.b_any, sm.scan[r][0][ln]);
-    sc.b_cur = imin(sc.b_cur, sm.scan[r][1][ln]);
-    sc.b_next = imin(sc.b_next, sm.scan[r][2][ln]);
-    sc.flags |= (uint32_t)sm.scan[r][3][ln];
-  }
+  const ScanOut sc = {sm.scan[0][ln], sm.scan[1][ln], sm.scan[2][ln], (uint32_t)sm.scan[3][ln]};
   flags = sc.flags;
   lane = lf_lane(sm.p.lf[0][ln]);  // the start-of-step lane stays when no lane box is under the vehicle
   ck0 = sm.ego_ck[ln] & 0xffff;
@@ -975,13 +1037,15 @@ PGS_HD void phase_d(Smem<V, R>& sm, Thr<V, R>& th, const Tables& T, const State&
     const int next_road = ck0 != ck1 ? ldg(&rroads[ck1]) : -1;
     ScanOut sc;
     bucket_scan<true>(th.mp, th.lanes, th.boxes, T, e.x, e.y, e.z, e.w, ehl, ehw, cur_road, next_road, th.role, R, sc);
-    sm.scan[th.role][0][ln] = sc.b_any; sm.scan[th.role][1][ln] = sc.b_cur; sm.scan[th.role][2][ln] = sc.b_next;
-    sm.scan[th.role][3][ln] = (int)sc.flags;
+    if (sc.b_any != INT_MAX) smem_min(&sm.scan[0][ln], sc.b_any);
+    if (sc.b_cur != INT_MAX) smem_min(&sm.scan[1][ln], sc.b_cur);
+    if (sc.b_next != INT_MAX) smem_min(&sm.scan[2][ln], sc.b_next);
+    smem_or(&sm.scan[3][ln], (int)sc.flags);
   }
   if (th.role == 0 || !th.stepping) return;
   const int ns = cfg.decision_repeat < PGS_MAX_SUBSTEPS ? cfg.decision_repeat : PGS_MAX_SUBSTEPS;
   int crash = 0;
-  const uint32_t amask = env_amask(sm, ln), pmask = env_pmask(sm, ln);
+  const uint32_t pmask = env_pmask(sm, ln);
   // parked traffic (the slots this role published in phase A, whose drop counters it already holds): only the drop
   // counter runs and the (fixed) chassis is tested against the ego's pose of every sub-step
 #pragma unroll
@@ -1012,36 +1076,52 @@ PGS_HD void phase_d(Smem<V, R>& sm, Thr<V, R>& th, const Tables& T, const State&
       }
     }
   }
+  smem_or(&sm.crash[ln], crash);
+}
+
+/* Traffic half of phase D: sub-steps, chassis contact against the ego's trajectory and after_step of the CTA's awake
+ * vehicles, dealt to all traffic threads like phase C (the same thread gets the same vehicle). */
+template <int V, int R>
+PGS_HD void phase_d_traffic(Smem<V, R>& sm, const Thr<V, R>& th, const Tables& T, const State& S, const PgdConfig& cfg,
+                           TrajPtr traj) {
+  if (th.role == 0) return;
+  Pub<V>& P = sm.p;
+  const int ns = cfg.decision_repeat < PGS_MAX_SUBSTEPS ? cfg.decision_repeat : PGS_MAX_SUBSTEPS;
+  const int n_work = sm.n_work;
 #pragma unroll 1
-  for (uint32_t m = drop_low(amask, th.role - 1); m; m = drop_low(m, R - 1)) {
-    const int s = ctz32(m);
-    const size_t gi = (size_t)s * th.num_envs + th.env;
-    const PgdSlot& t = th.tpl[s];
+  for (int i = (th.role - 1) * PGS_LANES + th.lane; i < n_work; i += (R - 1) * PGS_LANES) {
+    const int e = sm.work[i] & 0xff, s = sm.work[i] >> 8;
+    Thr<V, R> it;
+    item_context(sm, th, T, e, it);
+    const float ehl = sm.ego_hl[e], ehw = sm.ego_hw[e];
+    const size_t gi = (size_t)s * it.num_envs + it.env;
+    const PgdSlot& t = it.tpl[s];
     Veh q;
     veh_load(q, S, gi);
-    q.hc = P.hc[s][ln]; q.hs = P.hs[s][ln]; q.hl = t.length * 0.5f; q.hw = t.width * 0.5f;
+    q.hc = P.hc[s][e]; q.hs = P.hs[s][e]; q.hl = t.length * 0.5f; q.hw = t.width * 0.5f;
     const float reach = ehl + ehw + q.hl + q.hw;
     const bool at_rest = q.v == 0.0f && q.yaw == 0.0f && !(q.throttle > 0.0f);
     Sub sub;
     if (!at_rest) sub = make_sub(q, t, cfg.dt);
+    int crash = 0;
 #pragma unroll 1
     for (int k = 0; k < ns; ++k) {
       if (q.airborne > 0) q.airborne--;
       else if (!at_rest) substep(q, sub, cfg.dt);
-      const F4 e = traj[k][ln];
-      const float ddx = q.x - e.x, ddy = q.y - e.y;
+      const F4 eg4 = traj[k][e];
+      const float ddx = q.x - eg4.x, ddy = q.y - eg4.y;
       if (ddx * ddx + ddy * ddy <= reach * reach) {
         const Rect me = {q.x, q.y, q.hc, q.hs, q.hl, q.hw};
-        const Rect eg = {e.x, e.y, e.z, e.w, ehl, ehw};
+        const Rect eg = {eg4.x, eg4.y, eg4.z, eg4.w, ehl, ehw};
         if (rect_overlap(eg, me)) crash = 1;
       }
     }
-    localise_traffic(th, T, q, s);
+    localise_traffic(it, T, q, s);
     veh_store(q, S, gi);
-    P.x[s][ln] = q.x; P.y[s][ln] = q.y; P.hc[s][ln] = q.hc; P.hs[s][ln] = q.hs; P.v[s][ln] = q.v;
-    P.lf[s][ln] = lf_pack(q.lane, q.vflags);
+    P.x[s][e] = q.x; P.y[s][e] = q.y; P.hc[s][e] = q.hc; P.hs[s][e] = q.hs; P.v[s][e] = q.v;
+    P.lf[s][e] = lf_pack(q.lane, q.vflags);
+    smem_or(&sm.crash[e], crash);
   }
-  sm.crash[th.role][ln] = crash;
 }
 
 // ---- phase F: ego bookkeeping, one task per role ---------------------------------------------------------------------
@@ -1072,9 +1152,7 @@ PGS_HD void task_reward(Smem<V, R>& sm, Thr<V, R>& th, const Tables& T, const St
     obs[n_first + 6 + cfg.n_lane_line] = clipf(t0.length / 10.0f, 0.0f, 1.0f);
     obs[n_first + 6 + cfg.n_lane_line + 1] = clipf(t0.width / 2.5f, 0.0f, 1.0f);
   }
-  int crash = 0;
-#pragma unroll
-  for (int r = 1; r < R; ++r) crash |= sm.crash[r][ln];
+  const int crash = sm.crash[ln];
   const float last_x = sm.last_x[ln], last_y = sm.last_y[ln];
   const int cur_road_id = ldg(&rroads[ego.ck0]);
   const PgdRoad cur_road = load_rec(th.roads + cur_road_id);
@@ -1298,7 +1376,7 @@ PGS_HD void task_lidar_windows(Smem<V, R>& sm, const Thr<V, R>& th, VisPtr vis) 
 }
 
 /* side / lane-line detectors (distance_detector.py:137-152): ray fans against the line ghosts of the map; a beam
- * looks up the bucket of a point every 8 m along itself (buckets list every box within 4 m of them).  The rays of an
+ * looks up the bucket of a point every 2 PGD_GRID_MARGIN along itself (buckets list every box within one margin).  The rays of an
  * environment are spread over the roles. */
 template <int V, int R>
 PGS_HD void task_detectors(const Smem<V, R>& sm, const Thr<V, R>& th, const Tables& T, const PgdConfig& cfg,
@@ -1321,8 +1399,9 @@ PGS_HD void task_detectors(const Smem<V, R>& sm, const Thr<V, R>& th, const Tabl
     PGS_SINCOS(ang, sn, cs);
     const float dx = cs * dist, dy = sn * dist;
     float best = 1.0f;
-    for (float sd = 4.0f; sd - 4.0f < dist; sd += 8.0f) {
-      if (best * dist < sd - 4.0f) break;
+    const float gm = (float)PGD_GRID_MARGIN;
+    for (float sd = gm; sd - gm < dist; sd += 2.0f * gm) {
+      if (best * dist < sd - gm) break;
       const float px = ex + cs * sd, py = ey + sn * sd;
       const int cx = (int)floorf((px - mp.x0) * mp.inv_cell), cy = (int)floorf((py - mp.y0) * mp.inv_cell);
       if (cx < 0 || cy < 0 || cx >= mp.nx || cy >= mp.ny) continue;

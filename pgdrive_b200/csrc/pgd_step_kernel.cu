@@ -63,6 +63,7 @@ __global__ void __launch_bounds__(R * 32, PGS_MIN_CTAS) pgd_step_kernel(Tables T
 #endif
   Thr<V, R> th;
   thread_init(th, T, S, cfg, mode, lane, role, env0 + lane, env_end);
+  phase_0(sm, th);
   if (!__syncthreads_or(th.valid)) return;  // reset pass: no environment of this CTA is marked
   PGS_CLK(0);
   phase_a(sm, th, S, cfg, actions);
@@ -73,6 +74,7 @@ __global__ void __launch_bounds__(R * 32, PGS_MIN_CTAS) pgd_step_kernel(Tables T
   __syncthreads();
   PGS_CLK(3);
   phase_c(sm, th, T, S, cfg, rows, traj);
+  phase_c_traffic(sm, th, T, S, rows);
   PGS_CLK(4);
   __syncthreads();
   PGS_CLK(5);
@@ -83,6 +85,7 @@ __global__ void __launch_bounds__(R * 32, PGS_MIN_CTAS) pgd_step_kernel(Tables T
   }
   PGS_CLK(6);
   phase_d(sm, th, T, S, cfg, traj);
+  phase_d_traffic(sm, th, T, S, cfg, traj);
   PGS_CLK(7);
   __syncthreads();
   PGS_CLK(8);

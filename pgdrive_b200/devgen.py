@@ -74,8 +74,8 @@ def caps_for(gen_config):
     c.lanes = 88 * b
     c.roads = 32 * b
     c.boxes = 900 * b
-    c.cells = 1200 * b + 1
-    c.entries = 7000 * b
+    c.cells = 4800 * b + 1
+    c.entries = 12000 * b
     c.queue = 4096
     c.route = 32 * (3 * b + 10)
     c.cand = 160 * b

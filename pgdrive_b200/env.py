@@ -113,6 +113,7 @@ def _seed_tables(args):
     seed, mc, density, spawn = args[:4]
     stored = args[4] if len(args) > 4 else None
     random_agent = bool(args[5]) if len(args) > 5 else False
+    traffic_mode = args[6] if len(args) > 6 else "trigger"
     kw = dict(lane_num=mc["lane_num"], lane_width=mc["lane_width"], exit_length=mc["exit_length"])
     if stored is not None:  # restored from a map file: no block search (pg_map.py:48-71)
         pgmap = mapgen.build_from_sequence(seed, stored, **kw)
@@ -125,7 +126,8 @@ def _seed_tables(args):
     ts = tables.TableSet()
     mid = ts.add_map(pgmap)
     lane, lon, lat = spawn
-    ts.add_episode(pgmap, mid, episode.make_episode(pgmap, seed, density, tuple(lane), random_agent), tuple(lane), lon,
+    ts.add_episode(pgmap, mid, episode.make_episode(pgmap, seed, density, tuple(lane), random_agent, traffic_mode), tuple(lane),
+                   lon,
                    lat)
     return ts.finish()
 
@@ -190,13 +192,13 @@ def dump_maps(seeds, map_config):
 
 
 def build_seed_tables(seeds, map_config, density, spawn, workers=None, stored=None, random_lane=(False, False),
-                      random_agent_model=False):
+                      random_agent_model=False, traffic_mode="trigger"):
     """Tables for a list of seeds, built in worker processes when there are many, with an optional
     on-disk cache ($PGDRIVE_B200_CACHE) because map search costs ~50 ms per seed.  ``stored`` = {seed: block
     sequence} restored from a map file."""
     seeds = [int(s) for s in seeds]
     jobs = [(s, seed_map_config(map_config, s, *random_lane), density, spawn, (stored or {}).get(s),
-             bool(random_agent_model)) for s in seeds]
+             bool(random_agent_model), traffic_mode) for s in seeds]
     cache_dir = os.environ.get("PGDRIVE_B200_CACHE")
     path = None
     if cache_dir:
@@ -299,6 +301,8 @@ class VecPGDriveEnv:
         random_lane = (bool(cfg["random_lane_width"]), bool(cfg["random_lane_num"]))
         if cfg["random_agent_model"] and cfg["device_mapgen"]:
             raise NotImplementedError("device_mapgen spawns the default ego vehicle")
+        if cfg["traffic_mode"] == "respawn" and cfg["device_mapgen"]:
+            raise NotImplementedError("device_mapgen builds trigger-mode traffic")
         if cfg["device_mapgen"] and tables_dict is None and stored is None:
             # the whole reset path runs on the GPU (pgd_generate_tables); tables never visit the host
             gc = devgen.make_gen_config(self.map_config, cfg["traffic_density"], self._spawn, random_lane)
@@ -320,7 +324,7 @@ class VecPGDriveEnv:
         else:
             self._T = tables_dict if tables_dict is not None else build_seed_tables(
                 seeds, self.map_config, cfg["traffic_density"], self._spawn, stored=stored, random_lane=random_lane,
-                random_agent_model=cfg["random_agent_model"]
+                random_agent_model=cfg["random_agent_model"], traffic_mode=cfg["traffic_mode"]
             )
             self.episode_of_seed = {int(s): i for i, s in enumerate(self._T["episodes"]["seed"])}
             need = int(self._T["max_slots"])
@@ -566,7 +570,7 @@ class PGDriveEnv:
             return
         mc = seed_map_config(self.map_config, seed, self.config["random_lane_width"], self.config["random_lane_num"])
         part = _seed_tables((seed, mc, self.config["traffic_density"], self._spawn, (self._stored or {}).get(seed),
-                             bool(self.config["random_agent_model"])))
+                             bool(self.config["random_agent_model"]), self.config["traffic_mode"]))
         self._parts.append(part)
         self._episode_of_seed[seed] = len(self._parts) - 1
         T = merge_tables(self._parts)

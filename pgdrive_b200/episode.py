@@ -80,7 +80,28 @@ class EpisodeTemplate:
         self.block_vehicles = []  # [(trigger_road, [VehicleSlot])], LAST element triggers first
 
 
-def make_episode(pgmap, seed, density=0.1, spawn_lane=(">", ">>", 0), random_agent_model=False):
+def respawn_lanes(pgmap):
+    """TrafficManager._get_available_respawn_lanes (traffic_manager.py:292-309): a road listed by two blocks drops out."""
+    roads = []
+    for block in pgmap.blocks:
+        for road in block.respawn:
+            if road in roads:
+                roads.remove(road)
+            else:
+                roads.append(road)
+    lanes = []
+    for road in roads:
+        lanes += [(road, i, ln) for i, ln in enumerate(pgmap.net.lanes(road))]
+    return lanes
+
+
+def make_episode(pgmap, seed, density=0.1, spawn_lane=(">", ">>", 0), random_agent_model=False, traffic_mode="trigger"):
+    """``traffic_mode`` (traffic_manager.py:21-27): "trigger" and "hybrid" create every block's vehicles once and wake
+    them when the ego reaches the block (in this version of the reference the two are the same code path, :63-69,
+    :76-85); "respawn" fills every respawn lane with one vehicle per 10 m -- the density only switches traffic on --
+    and all of them drive from the first step (:224-237; the re-spawn itself is commented out at :100-105)."""
+    if traffic_mode not in ("trigger", "hybrid", "respawn"):
+        raise ValueError("No such mode named {}".format(traffic_mode))
     engine_rs = rng.seeded(seed)
     traffic_rs = rng.seeded(seed)
     ep = EpisodeTemplate(seed, density)
@@ -98,6 +119,26 @@ def make_episode(pgmap, seed, density=0.1, spawn_lane=(">", ">>", 0), random_age
     for (frm, to), lanes in pgmap.net.roads():
         for i, ln in enumerate(lanes):
             lane_index[id(ln)] = (frm, to, i)
+
+    def new_slot(lane, lon):
+        v = VehicleSlot()
+        v.type = TYPE_KEYS[int(traffic_rs.choice(len(TYPE_KEYS), p=TYPE_PROB))]
+        v.lane, v.long = lane, float(lon)
+        v.seed = rng.draw_seed(engine_rs)
+        v.params = sample_vehicle(v.type, v.seed)
+        v.checkpoints = route_for(pgmap, lane, seed)
+        v.idm_seed = rng.draw_seed(traffic_rs)
+        v.overtake_timer = int(rng.seeded(v.idm_seed).randint(0, 50))
+        return v
+
+    if traffic_mode == "respawn":  # _create_respawn_vehicles -> _create_vehicles_on_lane (traffic_manager.py:188-237)
+        slots = []
+        for road, i, ln in respawn_lanes(pgmap):
+            longs = [k * VEHICLE_GAP for k in range(int(ln.length / VEHICLE_GAP))]
+            traffic_rs.shuffle(longs)
+            slots += [new_slot((road[0], road[1], i), lon) for lon in longs]
+        ep.block_vehicles.append((None, slots))  # no trigger road: awake from the first step
+        return ep
     for block in pgmap.blocks[1:]:
         spawn = block.spawn_lanes()
         cand = []
@@ -108,17 +149,7 @@ def make_episode(pgmap, seed, density=0.1, spawn_lane=(">", ">>", 0), random_age
         total_length = sum(ln.length for lanes in spawn for ln in lanes)
         total = int(math.floor(int(math.floor(total_length / VEHICLE_GAP)) * density))
         traffic_rs.shuffle(cand)
-        slots = []
-        for lane, lon in cand[:min(total, len(cand))]:
-            v = VehicleSlot()
-            v.type = TYPE_KEYS[int(traffic_rs.choice(len(TYPE_KEYS), p=TYPE_PROB))]
-            v.lane, v.long = lane, float(lon)
-            v.seed = rng.draw_seed(engine_rs)
-            v.params = sample_vehicle(v.type, v.seed)
-            v.checkpoints = route_for(pgmap, lane, seed)
-            v.idm_seed = rng.draw_seed(traffic_rs)
-            v.overtake_timer = int(rng.seeded(v.idm_seed).randint(0, 50))
-            slots.append(v)
+        slots = [new_slot(lane, lon) for lane, lon in cand[:min(total, len(cand))]]
         ep.block_vehicles.append((block.pre_socket.pos, slots))
     ep.block_vehicles.reverse()
     return ep

@@ -62,9 +62,10 @@ STRIPE = 1.5
 SIDEWALK_SEG = 3.0
 SIDEWALK_WIDTH = 3.0
 SIDEWALK_GAP = 0.6
-CELL = 8.0  # bucket size [m]
-GRID_MARGIN = 4.0  # >= half diagonal of the largest chassis (5.8 x 2.3 -> 3.12 m)
+CELL = 4.0  # bucket size [m] (PGD_GRID_CELL, include/pgd_tables.h)
+GRID_MARGIN = 3.2  # PGD_GRID_MARGIN: >= half diagonal of the largest chassis (5.8 x 2.3 -> 3.12 m)
 ENTRY_NOT_LANE = 1 << 30  # PGD_ENTRY_NOT_LANE (include/pgd_tables.h)
+GROUP_AWAKE = -2  # PGD_GROUP_AWAKE: PgdSlot.group of a vehicle that drives from the first step (traffic_mode respawn)
 
 GRAVITY = 9.81
 
@@ -284,9 +285,15 @@ class TableSet:
         self._slot(pgmap, mi, getattr(ep, "ego_type", "default"), ep.ego_params, spawn_lane, spawn_long, spawn_lat, -1, 0,
                    None, ep.ego_checkpoints)
         groups = list(reversed(ep.block_vehicles))  # trigger order: block 1 first
+        awake = [vs for road, vs in groups if road is None]  # traffic_mode "respawn": no trigger, awake from step 0
+        groups = [(road, vs) for road, vs in groups if road is not None]
         if len(groups) > MAX_GROUPS:
             raise ValueError("more than %d traffic trigger groups" % MAX_GROUPS)
         trig = [-1] * MAX_GROUPS
+        for vehicles in awake:
+            for v in vehicles:
+                self._slot(pgmap, mi, v.type, v.params, v.lane, v.long, 0.0, GROUP_AWAKE, v.overtake_timer, v.idm_seed,
+                           v.checkpoints)
         for g, (road, vehicles) in enumerate(groups):
             trig[g] = mi.roads[tuple(road)]
             for v in vehicles:

@@ -58,3 +58,30 @@ def test_random_agent_model_type_and_parameters_match_reference():
         assert (body[0], body[1]) == (rec["length"], rec["width"]) and rec["max_length"] == 10 and rec["max_width"] == 2.5
         seen.add(rec["type"])
     assert len(seen) >= 4
+
+
+def test_respawn_traffic_mode_matches_reference():
+    """traffic_mode="respawn" (traffic_manager.py:63-66,188-237,292-309): which lanes are filled, the shuffled order of
+    the 10 m slots on each, vehicle types / seeds / parameters / IDM seeds / routes -- against the reference's own
+    _create_respawn_vehicles (tests/golden/reset_respawn.json.gz, tools/make_golden.py reset_respawn).  "hybrid" is the
+    trigger code path in this version of the reference."""
+    from conftest import load_golden
+    gold = load_golden("reset_respawn.json.gz")
+    counts = []
+    for s, d in gold.items():
+        m = mapgen.generate_map(int(s))
+        ep = episode.make_episode(m, int(s), d["density"], traffic_mode="respawn")
+        assert ep.ego_seed == d["ego_seed"] and ep.ego_params == d["ego_params"], s
+        assert len(ep.block_vehicles) == 1 and ep.block_vehicles[0][0] is None
+        slots, want = ep.block_vehicles[0][1], d["block_vehicles"][0]["vehicles"]
+        assert len(slots) == len(want), s
+        for v, gv in zip(slots, want):
+            assert (v.type, list(v.lane), v.long, v.seed) == (gv["type"], gv["lane"], gv["long"], gv["seed"]), s
+            assert (v.idm_seed, v.overtake_timer) == (gv["idm_seed"], gv["overtake_timer"]), s
+            assert v.params == gv["params"] and v.checkpoints == gv["checkpoints"], s
+        counts.append(len(slots))
+        hy = episode.make_episode(m, int(s), d["density"], traffic_mode="hybrid")
+        tr = episode.make_episode(m, int(s), d["density"], traffic_mode="trigger")
+        assert [(r, [(v.lane, v.long, v.seed) for v in vs]) for r, vs in hy.block_vehicles] == \
+               [(r, [(v.lane, v.long, v.seed) for v in vs]) for r, vs in tr.block_vehicles]
+    assert min(counts) >= 12 and max(counts) > 31  # some maps need more than the 32 vehicle slots the kernel has

@@ -252,3 +252,27 @@ def test_role_counts(roles):
         b.close()
     finally:
         ROLES[0] = 4
+
+
+def test_respawn_traffic_mode_all_traffic_awake_from_the_first_step():
+    """traffic_mode="respawn": every respawn lane carries a vehicle per 10 m and all of them run IDM from step 0
+    (PgdSlot.group = PGD_GROUP_AWAKE).  Seeds whose maps need at most 32 vehicle slots."""
+    from pgdrive_b200 import env as E
+    seeds = [1002, 1003, 1004, 1006, 1010, 1012, 1017, 1018, 1022, 1028]
+    T = E.merge_tables([E._seed_tables((s, V0, 0.1, SPAWN, None, False, "respawn")) for s in seeds])
+    assert 16 < T["max_slots"] <= 32 and (T["slots"]["group"] == -2).sum() == len(T["slots"]) - len(seeds)
+    n = 40
+    a, b = _pair(T, n, auto_reset=True)
+    eps = [i % len(seeds) for i in range(n)]
+    assert np.array_equal(a.reset(range(n), eps), b.reset(range(n), eps))
+    rs = np.random.RandomState(21)
+    moved = 0
+    for t in range(220):
+        act = _actions(rs, n, "lane" if t < 150 else "forward")
+        ra, rb = a.step(act, threads=4), b.step(act)
+        assert _same(ra, rb), t
+        if t == 10:  # traffic is already driving (bumper to bumper: one vehicle per 10 m), no trigger needed
+            moved = sum(int((b.get_state(e)["veh"][0]["speed"][1:] > 0.5).sum()) for e in range(10))
+    assert moved >= 10
+    a.close()
+    b.close()

@@ -189,7 +189,7 @@ def sample_vehicle_params(vclass, seed):
     return {k: float(v) for k, v in obj.get_config().items()}
 
 
-def dump_reset(seed, density=0.1):
+def dump_reset(seed, density=0.1, mode="trigger"):
     from pgdrive.component.vehicle_module.navigation import Navigation
     from pgdrive.component.vehicle.vehicle_type import vehicle_type, DefaultVehicle
     from pgdrive.manager.traffic_manager import TrafficManager
@@ -220,7 +220,7 @@ def dump_reset(seed, density=0.1):
     tm.spawned_objects = {}
     tm._traffic_vehicles = []
     tm.block_triggered_vehicles = []
-    tm.mode = "trigger"
+    tm.mode = mode
     tm.random_traffic = False
     tm.density = density
     vehicles = []
@@ -251,10 +251,17 @@ def dump_reset(seed, density=0.1):
     eng.object_manager = type("OM", (), dict(accident_lanes=[]))()
     type(eng).map_manager = property(lambda self: type("MM", (), dict(current_map=m))())
     if abs(density) >= 1e-2:
-        tm._create_vehicles_once(m, density)
+        if mode == "respawn":  # traffic_manager.py:63-66: every respawn lane is filled, all vehicles act from step 0
+            tm.respawn_lanes = tm._get_available_respawn_lanes(m)
+            tm._create_respawn_vehicles(m, density)
+        else:
+            tm._create_vehicles_once(m, density)
     name_of = {v: k for k, v in vehicle_type.items()}
     out_blocks = []
-    for bv in tm.block_triggered_vehicles:  # already reversed: last element triggers first
+    groups = list(tm.block_triggered_vehicles)  # already reversed: last element triggers first
+    if mode == "respawn":
+        groups = [type("BV", (), dict(trigger_road=None, vehicles=list(tm._traffic_vehicles)))()]
+    for bv in groups:
         vs = []
         for v in bv.vehicles:
             nv = Navigation(eng)
@@ -271,15 +278,16 @@ def dump_reset(seed, density=0.1):
                     checkpoints=list(nv.checkpoints),
                 )
             )
-        out_blocks.append(dict(trigger_road=[bv.trigger_road.start_node, bv.trigger_road.end_node], vehicles=vs))
+        out_blocks.append(dict(trigger_road=None if bv.trigger_road is None else
+                               [bv.trigger_road.start_node, bv.trigger_road.end_node], vehicles=vs))
     rec["block_vehicles"] = out_blocks
     return rec
 
 
-def cmd_reset(seeds, tag, density=0.1):
+def cmd_reset(seeds, tag, density=0.1, mode="trigger"):
     out = {}
     for s in seeds:
-        out[str(s)] = dump_reset(s, density)
+        out[str(s)] = dump_reset(s, density, mode)
     path = os.path.join(GOLD, "reset_%s.json.gz" % tag)
     with gzip.open(path, "wt") as f:
         json.dump(out, f)
@@ -294,6 +302,8 @@ if __name__ == "__main__":
     elif what == "reset":
         cmd_reset(list(range(1000, 1100)), "v0_1000_1099")
         cmd_reset([0, 1, 2, 99, 1500, 1999, 2999, 12345, 29999], "misc")
+    elif what == "reset_respawn":  # traffic_mode="respawn" (traffic_manager.py:21-27,63-66,224-237)
+        cmd_reset(list(range(1000, 1030)) + [0, 1, 2, 99], "respawn", mode="respawn")
     elif what == "probe":
         print(json.dumps(dump_reset(int(sys.argv[2])), indent=1)[:6000])
 

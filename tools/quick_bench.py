@@ -4,20 +4,21 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import bench
 from pgdrive_b200 import VecPGDriveEnv
-n = int(os.environ.get("ENVS", 65536)); K = int(os.environ.get("STEPS", 200)); W = int(os.environ.get('WARM', 130))
+n = int(os.environ.get("ENVS", 65536)); K = int(os.environ.get("STEPS", 200)); W = int(os.environ.get('WARM', 2048))  # steady state of the episode distribution (profiles/r02i_cost_curve_*.log)
 T = bench.build_tables()
 env = VecPGDriveEnv(dict(start_seed=1000, environment_num=100, num_envs=n, traffic_density=0.1, num_slots=16), tables_dict=T)
 env.reset()
 mode = os.environ.get("ACTIONS", "uniform")
 g = torch.Generator(device="cuda"); g.manual_seed(1)
-a = torch.rand((W + K, n, 2), generator=g, device="cuda") * 2 - 1
+NA = 256
+a = torch.rand((NA, n, 2), generator=g, device="cuda") * 2 - 1
 if mode == "forward":
     a[..., 1] = a[..., 1].abs(); a[..., 0] *= 0.1
-for t in range(W): env.step(a[t])
+for t in range(W): env.step(a[t % NA])
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
-for t in range(K): env.step(a[W + t])
+for t in range(K): env.step(a[(W + t) % NA])
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / K
 print("%s actions=%s: %.4f ms/step, %.1f M env-steps/s" % (os.path.basename(os.environ.get("PGDRIVE_B200_LIB", "") or "default"), mode, ms, n / ms / 1e3))
