@@ -98,6 +98,66 @@ PGD_MATH_FN float pgd_expf(float x) {
   return e * scale;
 }
 
+/* ln(x) for normal x > 0 (Box-Muller of the lidar noise): exponent split by bit operations, mantissa in [sqrt(1/2),
+ * sqrt(2)), the classic degree-9 polynomial. */
+PGD_MATH_FN float pgd_logf(float x) {
+  int32_t bits;
+  memcpy(&bits, &x, 4);
+  int32_t e = ((bits >> 23) & 0xff) - 126;                 /* x = m * 2^e, m in [0.5, 1) */
+  bits = (bits & 0x007fffff) | 0x3f000000;
+  float m;
+  memcpy(&m, &bits, 4);
+  if (m < 0.707106781186547524f) {
+    e -= 1;
+    m = m + m - 1.0f;
+  } else {
+    m = m - 1.0f;
+  }
+  const float z = m * m;
+  float p = 7.0376836292e-2f;
+  p = fmaf(p, m, -1.1514610310e-1f);
+  p = fmaf(p, m, 1.1676998740e-1f);
+  p = fmaf(p, m, -1.2420140846e-1f);
+  p = fmaf(p, m, 1.4249322787e-1f);
+  p = fmaf(p, m, -1.6668057665e-1f);
+  p = fmaf(p, m, 2.0000714765e-1f);
+  p = fmaf(p, m, -2.4999993993e-1f);
+  p = fmaf(p, m, 3.3333331174e-1f);
+  float y = p * m * z;
+  const float fe = (float)e;
+  y = fmaf(fe, -2.12194440e-4f, y);
+  y = fmaf(z, -0.5f, y);
+  return fmaf(fe, 0.693359375f, m + y);
+}
+
+/* Counter-based random numbers for the lidar noise (obs/state_obs.py:172-182 draws from the process-global numpy
+ * generator, so only the distribution can be matched): a 32-bit mix of (seed, call, environment, beam), the same on
+ * the device and in the oracle. */
+PGD_MATH_FN uint32_t pgd_mix32(uint32_t h) {
+  h ^= h >> 16; h *= 0x7feb352du; h ^= h >> 15; h *= 0x846ca68bu; h ^= h >> 16;
+  return h;
+}
+PGD_MATH_FN uint32_t pgd_noise_key(uint32_t seed, uint32_t call, uint32_t env, uint32_t beam) {
+  return pgd_mix32(pgd_mix32(pgd_mix32(seed ^ 0x9e3779b9u) + call) * 0x85ebca6bu + env * 1025u + beam);
+}
+/* clip(p + N(0, sigma), 0, 1), then 0 with probability `dropout` -- the two steps of _add_noise_to_cloud_points */
+PGD_MATH_FN float pgd_lidar_noise(float p, float sigma, float dropout, uint32_t key) {
+  if (sigma > 0.0f) {
+    const uint32_t h1 = pgd_mix32(key + 0x68bc21ebu), h2 = pgd_mix32(key + 0x02e5be93u);
+    const float u1 = (float)((h1 >> 8) + 1u) * (1.0f / 16777216.0f);  /* (0, 1] */
+    const float u2 = (float)(h2 >> 8) * (1.0f / 16777216.0f);         /* [0, 1) */
+    float sn, cs;
+    pgd_sincosf(6.28318530717958647692f * u2, &sn, &cs);
+    const float z = sqrtf(-2.0f * pgd_logf(u1)) * cs;
+    p = fminf(fmaxf(p + sigma * z, 0.0f), 1.0f);
+  }
+  if (dropout > 0.0f) {
+    const float u = (float)(pgd_mix32(key + 0x3c6ef372u) >> 8) * (1.0f / 16777216.0f);
+    if (u < dropout) p = 0.0f;
+  }
+  return p;
+}
+
 /* x^10 by squaring (IDM free-road term (v / v0)^10, policy/idm_policy.py:254-262). */
 PGD_MATH_FN float pgd_pow10f(float x) {
   const float x2 = x * x, x4 = x2 * x2, x8 = x4 * x4;

@@ -136,6 +136,14 @@ typedef struct {
   /* envs/base_env.py:29, obs/state_obs.py:18-23,103-105: the ego is one of the five vehicle types (chosen per seed by
    * the host) and the observation gains LENGTH / 10 and WIDTH / 2.5 after the lane-line beams */
   int32_t random_agent_model;
+  /* obs/state_obs.py:165-182: clip(p + N(0, sigma), 0, 1) on the 240 lidar values, then each set to 0 with probability
+   * dropout.  The reference draws from numpy's process-global generator; here a counter-based generator keyed by
+   * (noise_seed, API call, environment, beam) -- include/pgd_math.h -- so only the distribution matches. */
+  float lidar_gaussian_noise, lidar_dropout_prob;
+  int32_t noise_seed;
+  /* base_vehicle.py:249,351-358 (vehicle_config.increment_steering): steering += action[0] * 0.05, clipped to [-1, 1];
+   * the raw steering action of the last step (observation value 5) is kept in the ego's otherwise unused pid_hp */
+  int32_t increment_steering;
 } PgdConfig;
 
 /* Observation length (obs/state_obs.py:18-23,108-115,125-130): (n_side or 2) + 6 + n_lane_line [+ 2 vehicle

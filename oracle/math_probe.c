@@ -9,3 +9,7 @@ void probe_exp(const float* a, float* r, int n) { for (int i = 0; i < n; ++i) r[
 void probe_pow10(const float* a, float* r, int n) { for (int i = 0; i < n; ++i) r[i] = pgd_pow10f(a[i]); }
 void probe_tan(const float* a, float* r, int n) { for (int i = 0; i < n; ++i) r[i] = pgd_tanf(a[i]); }
 void probe_asin(const float* a, float* r, int n) { for (int i = 0; i < n; ++i) r[i] = pgd_asinf(a[i]); }
+void probe_log(const float* a, float* r, int n) { for (int i = 0; i < n; ++i) r[i] = pgd_logf(a[i]); }
+void probe_noise(const float* p, float* r, int n, float sigma, float dropout, unsigned seed, unsigned call) {
+  for (int i = 0; i < n; ++i) r[i] = pgd_lidar_noise(p[i], sigma, dropout, pgd_noise_key(seed, call, (unsigned)(i / 240), (unsigned)(i % 240)));
+}

@@ -31,6 +31,7 @@ def lib():
         L.orc_create.restype = vp
         L.orc_create.argtypes = [C.POINTER(cabi.PgdTables), C.POINTER(cabi.PgdConfig)]
         L.orc_destroy.argtypes = [vp]
+        L.orc_set_call_index.argtypes = [vp, C.c_uint32]
         L.orc_reset.argtypes = [vp, i32, i32, vp, vp]
         L.orc_step.argtypes = [vp, i32, vp, vp, vp, vp, vp]
         L.orc_step_range.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp]
@@ -62,6 +63,11 @@ class Oracle:
         self.reward = np.zeros(num_envs, np.float32)
         self.done = np.zeros(num_envs, np.uint8)
         self.info = np.zeros(num_envs, cabi.INFO_DT)
+        self.calls = 0  # API calls so far, like pgd_abi.cu's call_index (one key component of the lidar noise)
+
+    def _count_call(self):
+        self.calls += 1
+        self.L.orc_set_call_index(self.h, self.calls)
 
     def close(self):
         if self.h:
@@ -69,11 +75,13 @@ class Oracle:
             self.h = None
 
     def reset(self, env_ids, episode_ids):
+        self._count_call()
         for e, ep in zip(env_ids, episode_ids):
             self.L.orc_reset(self.h, int(e), int(ep), self.obs[e].ctypes.data, self.info[e:e + 1].ctypes.data)
         return self.obs
 
     def step(self, actions, threads=1):
+        self._count_call()
         a = np.ascontiguousarray(actions, np.float32).reshape(self.n, 2)
         args = (a.ctypes.data, self.obs.ctypes.data, self.reward.ctypes.data, self.done.ctypes.data,
                 self.info.ctypes.data)

@@ -60,6 +60,7 @@ typedef struct {
   PgdTables t;
   PgdConfig cfg;
   Env* envs;
+  uint32_t call_index; /* API calls so far (set by the wrapper before each reset / step): lidar-noise key */
 } Oracle;
 
 static float clipf(float a, float lo, float hi) { return fminf(fmaxf(a, lo), hi); } /* cutils.pyx:153 */
@@ -667,6 +668,10 @@ static void post_step(Oracle* o, Env* e, float last_x, float last_y, float last_
       float dx = cs * LIDAR_RANGE, dy = sn * LIDAR_RANGE;
       float best = 1.0f;
       for (int j = 0; j < n_rects; ++j) best = fminf(best, ray_rect(ego->x, ego->y, dx, dy, &rects[j]));
+      /* _add_noise_to_cloud_points (obs/state_obs.py:172-182): Gaussian noise, clip, dropout */
+      if (c->lidar_gaussian_noise > 0.0f || c->lidar_dropout_prob > 0.0f)
+        best = pgd_lidar_noise(best, c->lidar_gaussian_noise, c->lidar_dropout_prob,
+                               pgd_noise_key((uint32_t)c->noise_seed, o->call_index, (uint32_t)(e - o->envs), (uint32_t)i));
       obs[34 + i] = best;
     }
   }
@@ -741,6 +746,8 @@ void* orc_create(const PgdTables* t, const PgdConfig* cfg) {
   return o;
 }
 
+void orc_set_call_index(void* h, uint32_t idx) { ((Oracle*)h)->call_index = idx; }
+
 void orc_destroy(void* h) {
   Oracle* o = (Oracle*)h;
   free(o->envs);
@@ -798,9 +805,15 @@ void orc_step(void* h, int env, const float* action, float* obs, float* reward, 
   /* EnvInputPolicy.act: clip, NaN -> -1 (env_input_policy.py:17-26, cutils.pyx:153) */
   float steer = clipf(action[0], -1.0f, 1.0f), throttle = clipf(action[1], -1.0f, 1.0f);
   float last_x = ego->x, last_y = ego->y, last_h = ego->h;
-  e->prev_steer = ego->steer; /* last_current_action[0] after the push (base_vehicle.py:248) */
-  e->prev_throttle = ego->throttle;
-  ego->steer = steer;
+  e->prev_throttle = ego->throttle; /* last_current_action[0] after the push (base_vehicle.py:248) */
+  if (c->increment_steering) { /* _set_incremental_action (base_vehicle.py:351-358); ego->hp keeps the raw action */
+    e->prev_steer = ego->hp;
+    ego->hp = steer;
+    ego->steer = clipf(ego->steer + steer * 0.05f, -1.0f, 1.0f);
+  } else {
+    e->prev_steer = ego->steer;
+    ego->steer = steer;
+  }
   ego->throttle = throttle;
   /* TrafficManager.before_step (traffic_manager.py:71-89): wake the next block's vehicles */
   if (e->next_group < ep->n_groups && lane_at(o, m, ego->lane)->road == ep->trigger_road[e->next_group]) {

@@ -15,6 +15,7 @@ struct HostStep {
   State S;
   PgdConfig cfg;
   int roles;
+  uint32_t call_index;  // API calls so far (pgd_abi.cu keeps the same count): lidar-noise key
 };
 
 template <int V, int R>
@@ -47,7 +48,8 @@ static void run_vr(HostStep* h, int mode, const float* actions, float* obs, floa
     ALL(phase_d(sm, t, h->T, h->S, h->cfg, traj));
     ALL(phase_d_traffic(sm, t, h->T, h->S, h->cfg, traj));
     ALL(phase_f(sm, t, h->T, h->S, h->cfg, mode, od, rows, vis, reward, done, info));
-    ALL(phase_l(sm, h->T, h->S, r, l, n, env0, od, rows, vis));
+    ALL(phase_l(sm, h->T, h->S, r, l, env0, od, rows, vis));
+    ALL(phase_n(sm, h->cfg, h->call_index, r, l, env0, od, rows));
 #undef ALL
     for (int l = 0; l < PGS_LANES; ++l)
       if (sm.wrote[l]) memcpy(obs + (size_t)(env0 + l) * od, rows + (size_t)l * od, (size_t)od * 4);
@@ -102,6 +104,7 @@ void sth_reset(void* p, const int32_t* env_ids, const int32_t* episode_ids, int 
     h->S.envi[e].x = episode_ids[i];
     h->S.envi[e].z = PGS_DONE_PENDING_RESET;
   }
+  h->call_index++;
   run(h, 1, nullptr, obs, nullptr, nullptr, info);
 }
 
@@ -129,6 +132,7 @@ void sth_get_state(void* p, int env, PgdEnvState* out) {
 }
 
 void sth_step(void* p, const float* actions, float* obs, float* reward, uint8_t* done, PgdInfo* info) {
+  ((HostStep*)p)->call_index++;
   run((HostStep*)p, 0, actions, obs, reward, done, info);
 }
 }

@@ -55,7 +55,8 @@ class PgdConfig(C.Structure):
         ("out_of_road_cost", C.c_float), ("crash_vehicle_cost", C.c_float), ("use_lateral", C.c_int32),
         ("out_of_route_done", C.c_int32), ("auto_reset", C.c_int32), ("n_side", C.c_int32),
         ("n_lane_line", C.c_int32), ("side_distance", C.c_float), ("lane_line_distance", C.c_float),
-        ("random_agent_model", C.c_int32)
+        ("random_agent_model", C.c_int32), ("lidar_gaussian_noise", C.c_float), ("lidar_dropout_prob", C.c_float),
+        ("noise_seed", C.c_int32), ("increment_steering", C.c_int32)
     ]
 
 
@@ -63,13 +64,16 @@ def make_config(num_envs, num_slots=16, decision_repeat=5, horizon=0, dt=0.02, s
                 out_of_road_penalty=5.0, crash_vehicle_penalty=5.0, driving_reward=1.0, speed_reward=0.1,
                 out_of_road_cost=1.0, crash_vehicle_cost=1.0, use_lateral=False, out_of_route_done=False,
                 auto_reset=True, n_side=0, side_distance=50.0, n_lane_line=0, lane_line_distance=20.0,
-                random_agent_model=False):
+                random_agent_model=False, lidar_gaussian_noise=0.0, lidar_dropout_prob=0.0, noise_seed=0,
+                increment_steering=False):
     if not (0 <= n_side <= MAX_DETECTOR_BEAMS and 0 <= n_lane_line <= MAX_DETECTOR_BEAMS):
         raise ValueError("side / lane-line detectors support 0..%d lasers" % MAX_DETECTOR_BEAMS)
     return PgdConfig(num_envs, num_slots, decision_repeat, int(horizon or 0), dt, success_reward, out_of_road_penalty,
                      crash_vehicle_penalty, driving_reward, speed_reward, out_of_road_cost, crash_vehicle_cost,
                      int(use_lateral), int(out_of_route_done), int(auto_reset), int(n_side), int(n_lane_line),
-                     float(side_distance), float(lane_line_distance), int(bool(random_agent_model)))
+                     float(side_distance), float(lane_line_distance), int(bool(random_agent_model)),
+                     float(lidar_gaussian_noise), float(lidar_dropout_prob), int(noise_seed),
+                     int(bool(increment_steering)))
 
 
 def obs_dim(cfg):

@@ -189,6 +189,7 @@ ENGINE_CONFIG = dict(
     num_slots=None,      # vehicle slots per env (16 / 24 / 32); None = smallest that fits the loaded seeds
     device=0,            # CUDA device ordinal
     auto_reset=True,     # VecPGDriveEnv only: a finished env restarts at its next step (action ignored)
+    noise_seed=0,        # key of the counter-based generator behind lidar gaussian_noise / dropout_prob
     device_mapgen=False,  # VecPGDriveEnv only: run the reset path (map search, tables, episode templates) on the GPU
 )
 
@@ -204,9 +205,20 @@ def default_config():
 UNSUPPORTED_IF_CHANGED = {
     "num_agents": 1, "is_multi_agent": False, "IDM_agent": False,
     "use_render": False, "manual_control": False, "use_topdown": False, "offscreen_render": False,
-    "random_traffic": False, "accident_prob": 0., "gaussian_noise": 0.0,
-    "dropout_prob": 0.0, "record_episode": False,
+    "random_traffic": False, "accident_prob": 0., "record_episode": False,
 }
+
+
+def post_process_config(cfg):
+    """PGDriveEnv._post_process_config (envs/pgdrive_env.py:131-157): the top-level gaussian_noise / dropout_prob fan out
+    to the three sensors' configs (asserting that those were left at 0)."""
+    vc = cfg["vehicle_config"]
+    for key in ("gaussian_noise", "dropout_prob"):
+        if cfg[key] > 0:
+            for sensor in ("lidar", "side_detector", "lane_line_detector"):
+                assert vc[sensor][key] == 0, "You already provide config!"
+                vc[sensor][key] = cfg[key]
+    return cfg
 
 
 def check_supported(cfg):
@@ -222,17 +234,23 @@ def check_supported(cfg):
     lid = vc["lidar"]
     if (lid["num_lasers"], lid["distance"], lid["num_others"]) != (240, 50, 4):
         raise NotImplementedError("lidar must be 240 beams x 50 m with 4 neighbours")
-    if lid["gaussian_noise"] or lid["dropout_prob"]:
-        raise NotImplementedError("lidar noise / dropout are not supported")
+    if lid["gaussian_noise"] < 0 or not 0 <= lid["dropout_prob"] <= 1:
+        raise ValueError("lidar gaussian_noise must be >= 0 and dropout_prob in [0, 1]")
     for name in ("side_detector", "lane_line_detector"):
         det = vc[name]
         if not 0 <= det["num_lasers"] <= 240:
             raise NotImplementedError("%s supports 0..240 lasers" % name)
-        if det["gaussian_noise"] or det["dropout_prob"]:
-            raise NotImplementedError("%s noise / dropout are not supported" % name)
+        # gaussian_noise / dropout_prob of the two detectors are accepted and unused, as in the reference: only the lidar's
+        # cloud points go through _add_noise_to_cloud_points (obs/state_obs.py:64-66,96-97,165-170)
         if det["num_lasers"] and det["distance"] <= 0:
             raise ValueError("%s distance must be positive" % name)
-    if vc["increment_steering"] or vc["enable_reverse"] or vc["extra_action_dim"]:
-        raise NotImplementedError("increment_steering / enable_reverse / extra_action_dim are not supported")
+    if vc["enable_reverse"]:
+        raise NotImplementedError("enable_reverse is not supported (the planar vehicle model has no reverse gear)")
+    if vc["overtake_stat"]:
+        # base_vehicle.py:702 calls the static Lidar.get_surrounding_vehicles() without its argument: the reference
+        # itself raises TypeError on the first step with this option
+        raise NotImplementedError("overtake_stat raises in the reference at this version (base_vehicle.py:702)")
+    if vc["extra_action_dim"] < 0:
+        raise ValueError("extra_action_dim must be >= 0")
     if cfg["decision_repeat"] < 1:
         raise ValueError("decision_repeat must be >= 1")

@@ -153,6 +153,7 @@ extern "C" int pgd_reset(PgdHandle* h, const int32_t* env_ids, const int32_t* ep
     if (env_ids && (env_ids[i] < 0 || env_ids[i] >= h->cfg.num_envs)) return fail(-1, "pgd_reset: env id out of range");
   }
   CU(cudaSetDevice(h->device));
+  h->call_index++;
   cudaStream_t st = (cudaStream_t)stream;
   if (n > h->scratch_cap) {
     cudaFree(h->d_ids); cudaFree(h->d_eps);
@@ -177,6 +178,7 @@ extern "C" int pgd_step(PgdHandle* h, const float* actions_dev, float* obs_dev, 
   if (!h || !actions_dev || !obs_dev || !reward_dev || !done_dev) return fail(-1, "pgd_step: null argument");
   if (!h->tables_loaded) return fail(-3, "pgd_step: no tables loaded");
   CU(cudaSetDevice(h->device));
+  h->call_index++;
   const int rc = launch_step(h, 0, 0, h->cfg.num_envs, actions_dev, obs_dev, reward_dev, done_dev, info_dev,
                              (cudaStream_t)stream);
   if (rc) return rc;
@@ -214,6 +216,7 @@ extern "C" int pgd_step_host(PgdHandle* h, const float* actions, float* obs, flo
   if (!h || !actions || !obs || !reward || !done) return fail(-1, "pgd_step_host: null argument");
   if (!h->tables_loaded) return fail(-3, "pgd_step_host: no tables loaded");
   CU(cudaSetDevice(h->device));
+  h->call_index++;
   int rc = ensure_staging(h);
   if (rc) return rc;
   const size_t n = (size_t)h->cfg.num_envs;

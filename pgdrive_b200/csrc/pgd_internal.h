@@ -54,6 +54,7 @@ struct PgdHandle {
   int n_episodes;
   DevState S;
   void* state_mem[7];
+  uint32_t call_index;  // API calls (reset / step) so far: one key component of the lidar-noise generator
   bool tables_loaded;
   int64_t launches;
   // reset scratch

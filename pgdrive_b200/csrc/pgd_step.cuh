@@ -540,10 +540,18 @@ PGS_HD void phase_a(Smem<V, R>& sm, Thr<V, R>& th, const State& S, const PgdConf
     P.x[0][ln] = q.x; P.y[0][ln] = q.y; P.hc[0][ln] = q.hc; P.hs[0][ln] = q.hs; P.v[0][ln] = q.v;
     P.lf[0][ln] = lf_pack(q.lane, q.vflags);
     if (th.stepping) {  // EnvInputPolicy.act (env_input_policy.py:17-26): clip; fminf / fmaxf turn NaN into -1
-      th.envf.x = q.steer;  // last_current_action[0] after the push (base_vehicle.py:248)
-      th.envf.y = q.throttle;
-      q.steer = clipf(actions[2 * (size_t)th.env], -1.0f, 1.0f);
-      q.throttle = clipf(actions[2 * (size_t)th.env + 1], -1.0f, 1.0f);
+      const float a0 = clipf(actions[2 * (size_t)th.env], -1.0f, 1.0f);
+      const float a1 = clipf(actions[2 * (size_t)th.env + 1], -1.0f, 1.0f);
+      th.envf.y = q.throttle;  // last_current_action[0] after the push (base_vehicle.py:248)
+      if (cfg.increment_steering) {  // _set_incremental_action (base_vehicle.py:351-358); q.hp = last raw action
+        th.envf.x = q.hp;
+        q.hp = a0;
+        q.steer = clipf(q.steer + a0 * 0.05f, -1.0f, 1.0f);
+      } else {
+        th.envf.x = q.steer;
+        q.steer = a0;
+      }
+      q.throttle = a1;
       if (th.trig >= 0) th.envi.y += 1;
     }
     return;
@@ -1449,19 +1457,14 @@ PGS_HD void lidar_min(float* cell, float t) {
 }
 
 template <int V, int R>
-PGS_HD void phase_l(const Smem<V, R>& sm, const Tables& T, const State& S, int role, int lane, int num_envs, int env0,
-                   int obs_dim, float* obs_rows, VisPtr vis) {
-  const Pub<V>& P = sm.p;
-  const int head = obs_dim - PGD_LIDAR_BEAMS;
-#pragma unroll 1
-  for (int e = role; e < PGS_LANES; e += R) {
-    if (!sm.wrote[e]) continue;
+PGS_HD void lidar_scatter(const Smem<V, R>& sm, const Tables& T, const State& S, const Pub<V>& P, int e, int lane,
+                         int env0, float* row_lidar, VisPtr vis) {
+  {
     const int nv = sm.n_vis[e];
-    if (nv == 0) continue;
     const F4 eg = sm.efin[e];
     const float ex = eg.x, ey = eg.y, eh = sm.ego_h[e];
-    float* row = obs_rows + (size_t)e * obs_dim + head;
-    const PgdSlot* tpl = T.slots + ldg(&T.episodes[S.envi[env0 + e].x].slot_off);
+    float* row = row_lidar;
+    const PgdSlot* tpl = T.slots + sm.ctx_slot_off[e];
 #pragma unroll 1
     for (int k = 0; k < nv; ++k) {
       const int w = vis[k][e];
@@ -1479,6 +1482,34 @@ PGS_HD void phase_l(const Smem<V, R>& sm, const Tables& T, const State& S, int r
         if (t < 1.0f) lidar_min(row + i, t);
       }
     }
+  }
+}
+
+template <int V, int R>
+PGS_HD void phase_l(const Smem<V, R>& sm, const Tables& T, const State& S, int role, int lane, int env0, int obs_dim,
+                   float* obs_rows, VisPtr vis) {
+  const int head = obs_dim - PGD_LIDAR_BEAMS;
+#pragma unroll 1
+  for (int e = role; e < PGS_LANES; e += R) {
+    if (!sm.wrote[e] || sm.n_vis[e] == 0) continue;
+    lidar_scatter<V, R>(sm, T, S, sm.p, e, lane, env0, obs_rows + (size_t)e * obs_dim + head, vis);
+  }
+}
+
+// ---- phase N: lidar noise on the finished rows (_add_noise_to_cloud_points, obs/state_obs.py:172-182); the warp that
+// scattered an environment's hits also adds its noise, so a warp-level barrier separates the two ------------------
+template <int V, int R>
+PGS_HD void phase_n(const Smem<V, R>& sm, const PgdConfig& cfg, uint32_t call_index, int role, int lane, int env0,
+                   int obs_dim, float* obs_rows) {
+  if (!(cfg.lidar_gaussian_noise > 0.0f || cfg.lidar_dropout_prob > 0.0f)) return;
+  const int head = obs_dim - PGD_LIDAR_BEAMS;
+#pragma unroll 1
+  for (int e = role; e < PGS_LANES; e += R) {
+    if (!sm.wrote[e]) continue;
+    float* row = obs_rows + (size_t)e * obs_dim + head;
+    for (int i = lane; i < PGD_LIDAR_BEAMS; i += PGS_LANES)
+      row[i] = pgd_lidar_noise(row[i], cfg.lidar_gaussian_noise, cfg.lidar_dropout_prob,
+                               pgd_noise_key((uint32_t)cfg.noise_seed, call_index, (uint32_t)(env0 + e), (uint32_t)i));
   }
 }
 

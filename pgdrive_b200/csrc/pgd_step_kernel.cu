@@ -43,6 +43,7 @@ extern "C" int pgd_debug_phase_clocks(unsigned long long* out, int reset) {
 
 template <int V, int R>
 __global__ void __launch_bounds__(R * 32, PGS_MIN_CTAS) pgd_step_kernel(Tables T, State S, PgdConfig cfg, int mode,
+                                                                         uint32_t call_index,
                                                                          int env_begin, int env_end,
                                                                          const float* __restrict__ actions,
                                                                          float* __restrict__ obs,
@@ -93,7 +94,9 @@ __global__ void __launch_bounds__(R * 32, PGS_MIN_CTAS) pgd_step_kernel(Tables T
   PGS_CLK(9);
   __syncthreads();
   PGS_CLK(10);
-  phase_l(sm, T, S, role, lane, cfg.num_envs, env0, obs_dim, rows, vis);
+  phase_l(sm, T, S, role, lane, env0, obs_dim, rows, vis);
+  __syncwarp();
+  phase_n(sm, cfg, call_index, role, lane, env0, obs_dim, rows);
   PGS_CLK(11);
   // ---- write-out -----------------------------------------------------------------------------------------------------
   const int all = __syncthreads_and(sm.wrote[lane]);
@@ -139,7 +142,7 @@ static int launch_one(PgdHandle* h, const Tables& T, const State& S, int mode, i
     configured = smem;
   }
   const int grid = (env_end - env_begin + PGS_LANES - 1) / PGS_LANES;
-  pgd_step_kernel<V, R><<<grid, R * 32, smem, st>>>(T, S, h->cfg, mode, env_begin, env_end, actions, obs, reward,
+  pgd_step_kernel<V, R><<<grid, R * 32, smem, st>>>(T, S, h->cfg, mode, h->call_index, env_begin, env_end, actions, obs, reward,
                                                        done, info);
   return 0;
 }

@@ -18,7 +18,7 @@ import pickle
 import numpy as np
 
 from . import cabi, devgen, episode, mapgen, tables
-from .config import ENGINE_CONFIG, Config, check_supported, default_config
+from .config import ENGINE_CONFIG, Config, check_supported, default_config, post_process_config
 from .spaces import Box, MultiDiscrete
 
 ENVIRONMENTS = {  # /root/reference/pgdrive/register.py:7-40
@@ -77,7 +77,8 @@ def make_action_space(cfg):
     """base_vehicle.py:721-727."""
     if cfg["discrete_action"]:
         return MultiDiscrete([cfg["discrete_steering_dim"], cfg["discrete_throttle_dim"]])
-    return Box(-1.0, 1.0, shape=(2, ), dtype=np.float32)
+    # extra_action_dim only widens the space; the vehicle reads action[0] and action[1] (base_vehicle.py:343-358)
+    return Box(-1.0, 1.0, shape=(2 + int(cfg["vehicle_config"]["extra_action_dim"]), ), dtype=np.float32)
 
 
 def discrete_to_continuous(actions, cfg):
@@ -253,7 +254,11 @@ class _Engine:
             side_distance=cfg["vehicle_config"]["side_detector"]["distance"],
             n_lane_line=cfg["vehicle_config"]["lane_line_detector"]["num_lasers"],
             lane_line_distance=cfg["vehicle_config"]["lane_line_detector"]["distance"],
-            random_agent_model=bool(cfg["random_agent_model"])
+            random_agent_model=bool(cfg["random_agent_model"]),
+            lidar_gaussian_noise=cfg["vehicle_config"]["lidar"]["gaussian_noise"],
+            lidar_dropout_prob=cfg["vehicle_config"]["lidar"]["dropout_prob"],
+            noise_seed=int(cfg.get("noise_seed", 0) or 0) + 7919 * int(device),
+            increment_steering=bool(cfg["vehicle_config"]["increment_steering"])
         )
         self.obs_dim = cabi.obs_dim(self.pcfg)
         self.h = C.c_void_p()
@@ -285,7 +290,7 @@ class VecPGDriveEnv:
     def __init__(self, config=None, tables_dict=None, obs_out=None):
         merged = default_config()
         merged.update(ENGINE_CONFIG)
-        self.config = merged.update(config or {}, allow_add_new_key=False)
+        self.config = post_process_config(merged.update(config or {}, allow_add_new_key=False))
         check_supported(self.config)
         cfg = self.config
         self.num_envs = int(cfg["num_envs"])
@@ -403,10 +408,12 @@ class VecPGDriveEnv:
         torch = e.torch
         if self.config["discrete_action"]:
             actions = discrete_to_continuous(actions, self.config)
+        extra = 0 if self.config["discrete_action"] else int(self.config["vehicle_config"]["extra_action_dim"])
         if isinstance(actions, torch.Tensor):
-            if actions.device != e.device or actions.dtype != torch.float32 or tuple(actions.shape) != (self.num_envs, 2):
-                raise ValueError("actions must be a float32 [num_envs, 2] tensor on %s" % e.device)
-            a = actions.contiguous()
+            if actions.device != e.device or actions.dtype != torch.float32 or \
+                    tuple(actions.shape) != (self.num_envs, 2 + extra):
+                raise ValueError("actions must be a float32 [num_envs, %d] tensor on %s" % (2 + extra, e.device))
+            a = (actions[:, :2] if extra else actions).contiguous()
             obs, reward, done = out if out is not None else (self.obs, self.reward, self.done)
             if out is not None:
                 n = self.num_envs
@@ -424,9 +431,10 @@ class VecPGDriveEnv:
             return obs, reward, done, self.info
         if out is not None:
             raise ValueError("out= is only supported with device actions")
-        a = np.ascontiguousarray(actions, dtype=np.float32)
-        if a.shape != (self.num_envs, 2):
-            raise ValueError("actions must have shape [num_envs, 2]")
+        a = np.asarray(actions, dtype=np.float32)
+        if a.shape != (self.num_envs, 2 + extra):
+            raise ValueError("actions must have shape [num_envs, %d]" % (2 + extra))
+        a = np.ascontiguousarray(a[:, :2])
         cabi.check(
             e.lib,
             e.lib.pgd_step_host(e.h, a.ctypes.data, self._h_obs.ctypes.data, self._h_reward.ctypes.data,
@@ -542,7 +550,7 @@ class PGDriveEnv:
         return default_config()
 
     def __init__(self, config=None):
-        self.config = self.default_config().update(config or {}, allow_add_new_key=False)
+        self.config = post_process_config(self.default_config().update(config or {}, allow_add_new_key=False))
         check_supported(self.config)
         self.start_seed, self.env_num = int(self.config["start_seed"]), int(self.config["environment_num"])
         self.map_config = parse_map_config(self.config)
@@ -666,7 +674,7 @@ class PGDriveEnv:
             raise RuntimeError("call reset() before step()")
         e = self._engine
         self.episode_steps += 1
-        raw = np.asarray(action, dtype=np.float32).reshape(2)
+        raw = np.asarray(action, dtype=np.float32).reshape(-1)[:2]
         a = discrete_to_continuous(raw, self.config) if self.config["discrete_action"] else raw
         self._act.copy_(e.torch.from_numpy(a).reshape(1, 2))
         cabi.check(

@@ -186,12 +186,16 @@ def test_abi_argument_errors_without_a_gpu():
 
 def test_vec_env_rejects_unsupported_options():
     from pgdrive_b200 import VecPGDriveEnv
-    for cfg in (dict(traffic_mode="respawn"), dict(random_traffic=True), dict(num_agents=2),
+    for cfg in (dict(random_traffic=True), dict(num_agents=2), dict(vehicle_config=dict(enable_reverse=True)),
+                dict(vehicle_config=dict(overtake_stat=True)),
                 dict(vehicle_config=dict(lidar=dict(num_lasers=120))),
-                dict(vehicle_config=dict(side_detector=dict(num_lasers=500))),
-                dict(vehicle_config=dict(lane_line_detector=dict(num_lasers=4, gaussian_noise=0.1)))):
+                dict(vehicle_config=dict(side_detector=dict(num_lasers=500)))):
         with pytest.raises(NotImplementedError):
             VecPGDriveEnv(cfg)
+    with pytest.raises(ValueError):
+        VecPGDriveEnv(dict(traffic_mode="no such mode"))  # traffic_manager.py:69
+    with pytest.raises(AssertionError):  # pgdrive_env.py:143-146: "You already provide config!"
+        VecPGDriveEnv(dict(gaussian_noise=0.1, vehicle_config=dict(lidar=dict(gaussian_noise=0.2))))
     with pytest.raises(KeyError):
         VecPGDriveEnv(dict(no_such_key=True))
 

