@@ -255,8 +255,9 @@ def run_own(args):
 
     done_ev = [None, None]      # per gather buffer: event after which it may be written again
     counter = [0]
-    consumed = torch.zeros(3, dtype=torch.float64, device=dev)   # rank 0: what the consumer read from the gathered batch
-    local_sum = torch.zeros(3, dtype=torch.float64, device=dev)  # every rank: the same sums over its own rows
+    consumed = torch.zeros(3, dtype=torch.float64, device=dev)   # rank 0: what the consumer read during the timed steps
+    verified = torch.zeros(3, dtype=torch.float64, device=dev)   # rank 0: the same sums over the verification steps
+    local_sum = torch.zeros(3, dtype=torch.float64, device=dev)  # every rank: sums over its OWN rows, same steps
 
     def checksum_into(acc, obs, reward, done):
         acc[0] += obs.sum(dtype=torch.float64)
@@ -278,7 +279,7 @@ def run_own(args):
         if peer is not None:
             direct = peer.mode == "peer" or rank == 0  # rank 0's own rows are local memory either way
             env.step_into(a, *(peer.pointers(i) if direct else peer.local_pointers(i)))
-            if check:
+            if check == "verify":  # untimed: this rank's own rows (read back over NVLink in peer mode)
                 checksum_into(local_sum, *peer.local_views(i, remote=direct))
             ready = torch.cuda.Event()
             ready.record(cur)
@@ -287,14 +288,14 @@ def run_own(args):
                 if not direct:
                     peer.push(i)  # copy engine: local rows -> rank 0's buffer over NVLink
                 peer.completion_barrier()
-                if rank == 0 and check:
-                    checksum_into(consumed, *peer.tensors(i))  # the consumer reads the whole gathered batch
+                if rank == 0 and check:  # the consumer reads the whole gathered batch, every step
+                    checksum_into(verified if check == "verify" else consumed, *peer.tensors(i))
                 done_ev[i] = torch.cuda.Event()
                 done_ev[i].record(side)
             return
         b = bufs[i]
         env.step(a, out=(b.local(b.obs), b.local(b.reward), b.local(b.done)))
-        if check:
+        if check == "verify":
             checksum_into(local_sum, b.local(b.obs), b.local(b.reward), b.local(b.done))
         ready = torch.cuda.Event()
         ready.record(cur)
@@ -302,7 +303,7 @@ def run_own(args):
         with torch.cuda.stream(side):
             b.all_gather(dist)
             if rank == 0 and check:
-                checksum_into(consumed, b.obs, b.reward, b.done)
+                checksum_into(verified if check == "verify" else consumed, b.obs, b.reward, b.done)
             done_ev[i] = torch.cuda.Event()
             done_ev[i].record(side)
 
@@ -346,6 +347,11 @@ def run_own(args):
     ms, kernel_ms = timed(actions[W:W + K], K, lambda a: step_and_gather(a, check=(world > 1)))
     launches = env.launch_count - launches0
     clk = clocks.stop() if rank == 0 else None
+    if world > 1:  # untimed: 4 more steps in which every rank also sums its own rows; rank 0's sums must equal their total
+        for t in range(4):
+            step_and_gather(actions[t], check="verify")
+        drain()
+        barrier()
     done_rate = float(env.done.float().mean().item()) if world == 1 else None
 
     # ---- N > 1: the same steps without the gather (does the kernel itself scale?) -----------------------------------
@@ -368,11 +374,11 @@ def run_own(args):
     e2e_steps = min(K, 64)
     h_actions = actions[W:W + e2e_steps].cpu().numpy()
     for t in range(min(W, 4)):
-        env.step(h_actions[t % e2e_steps])
+        env.step(h_actions[t % e2e_steps], copy=False)
     barrier()
     t0 = time.perf_counter()
     for t in range(e2e_steps):
-        o, r, d, i = env.step(h_actions[t])
+        o, r, d, i = env.step(h_actions[t], copy=False)  # pinned staging arrays: valid until the next step
     torch.cuda.synchronize()
     per_rank_e2e_s = time.perf_counter() - t0
     checksum = float(o[:, :8].sum())
@@ -451,10 +457,13 @@ def run_own(args):
     gather_check = None
     if world > 1:
         want = torch.stack(sums).sum(0).cpu().numpy()
-        got = consumed.cpu().numpy()
+        got = verified.cpu().numpy()
         gather_check = dict(
-            consumer="rank 0 sums obs / reward / done of the gathered batch after every step's gather",
-            consumed=[float(x) for x in got], sum_of_rank_local=[float(x) for x in want],
+            consumer="rank 0 sums obs / reward / done of the whole gathered batch after every step's gather (timed "
+                     "region: consumed_timed); over 4 more untimed steps every rank also sums its own rows and rank 0's "
+                     "sums must equal the total of the ranks' (verified vs sum_of_rank_local)",
+            consumed_timed=[float(x) for x in consumed.cpu().numpy()],
+            verified=[float(x) for x in got], sum_of_rank_local=[float(x) for x in want],
             ok=bool(np.allclose(got, want, rtol=1e-9, atol=1e-6)))
 
     # ---- the reset path: maps + episode templates of the workload's seeds generated ON the device -------------------

@@ -374,12 +374,13 @@ class VecPGDriveEnv:
         if env_ids is None:
             env_ids = np.arange(self.num_envs, dtype=np.int32)
         env_ids = np.ascontiguousarray(env_ids, dtype=np.int32)
-        if seeds is not None:
-            self.env_seeds[env_ids] = np.broadcast_to(np.asarray(seeds, dtype=np.int64), env_ids.shape)
-        try:
-            eps = np.array([self.episode_of_seed[int(s)] for s in self.env_seeds[env_ids]], dtype=np.int32)
+        new_seeds = self.env_seeds[env_ids] if seeds is None else \
+            np.broadcast_to(np.asarray(seeds, dtype=np.int64), env_ids.shape)
+        try:  # resolve first, assign after: a bad seed must not stick to the environment (base_env.py:451-458 asserts)
+            eps = np.array([self.episode_of_seed[int(s)] for s in new_seeds], dtype=np.int32)
         except KeyError as e:
             raise KeyError("seed %s is outside [start_seed, start_seed + environment_num)" % e)
+        self.env_seeds[env_ids] = new_seeds
         e = self.engine
         cabi.check(
             e.lib,
@@ -399,11 +400,15 @@ class VecPGDriveEnv:
                            e.stream())
         )
 
-    def step(self, actions, out=None):
+    def step(self, actions, out=None, copy=True):
         """``actions``: ``[N, 2]`` float32, either a CUDA tensor (device path: returns CUDA tensors, no
         synchronisation) or a numpy array (host path: pinned staging, returns numpy arrays).  ``out`` (device path
         only) = ``(obs, reward, done)`` tensors to write into instead of the environment's own buffers, e.g. this
-        rank's rows of an all-gather buffer."""
+        rank's rows of an all-gather buffer.
+
+        Host path: the results land in page-locked staging arrays that the NEXT step overwrites.  ``copy=True``
+        (default) returns fresh arrays, like the reference; ``copy=False`` returns the staging arrays themselves
+        (no 75 MB copy per step at 65 536 environments) -- valid only until the next ``step`` / ``reset``."""
         e = self.engine
         torch = e.torch
         if self.config["discrete_action"]:
@@ -440,6 +445,8 @@ class VecPGDriveEnv:
             e.lib.pgd_step_host(e.h, a.ctypes.data, self._h_obs.ctypes.data, self._h_reward.ctypes.data,
                                 self._h_done.ctypes.data, self._h_info.ctypes.data)
         )
+        if copy:
+            return self._h_obs.copy(), self._h_reward.copy(), self._h_done.copy(), self._h_info.copy()
         return self._h_obs, self._h_reward, self._h_done, self._h_info
 
     def info_numpy(self):
@@ -560,7 +567,7 @@ class PGDriveEnv:
                         (2 if self.config["random_agent_model"] else 0))
         self.observation_space = Box(-0.0, 1.0, shape=(self.obs_dim, ), dtype=np.float32)
         self.action_space = make_action_space(self.config)
-        self._parts, self._episode_of_seed = [], {}
+        self._parts, self._episode_of_seed, self._loaded_seed = {}, {}, None
         self._maps = {}
         self._stored = None
         if self.config["load_map_from_json"] and self.config["_load_map_from_json"] is not None:
@@ -574,19 +581,21 @@ class PGDriveEnv:
 
     # lazily create the engine the first time reset() runs (base_env.py:166-178)
     def _ensure_seed(self, seed):
-        if seed in self._episode_of_seed:
-            return
-        mc = seed_map_config(self.map_config, seed, self.config["random_lane_width"], self.config["random_lane_num"])
-        part = _seed_tables((seed, mc, self.config["traffic_density"], self._spawn, (self._stored or {}).get(seed),
-                             bool(self.config["random_agent_model"]), self.config["traffic_mode"]))
-        self._parts.append(part)
-        self._episode_of_seed[seed] = len(self._parts) - 1
-        T = merge_tables(self._parts)
-        need = int(T["max_slots"])
-        slots = pick_slots(need)
+        """Tables of ``seed`` (built once, kept on the host like the reference's map cache, map_manager.py:98-155) and an
+        engine that holds exactly the tables of the CURRENT seed: a visit uploads one map (tens of KB), not every map
+        seen so far."""
+        if seed not in self._parts:
+            mc = seed_map_config(self.map_config, seed, self.config["random_lane_width"], self.config["random_lane_num"])
+            self._parts[seed] = _seed_tables((seed, mc, self.config["traffic_density"], self._spawn,
+                                              (self._stored or {}).get(seed), bool(self.config["random_agent_model"]),
+                                              self.config["traffic_mode"]))
+            self._episode_of_seed[seed] = 0
+        part = self._parts[seed]
+        slots = pick_slots(int(part["max_slots"]))
         if self._engine is not None and self._engine.num_slots < slots:
             self._engine.close()
             self._engine = None
+            self._loaded_seed = None
         if self._engine is None:
             self._engine = _Engine(self.config, 1, slots, int(os.environ.get("PGDRIVE_B200_DEVICE", 0)), False,
                                    effective_horizon(self.config, self.map_config))
@@ -597,7 +606,9 @@ class PGDriveEnv:
             self._done = torch.zeros(1, dtype=torch.uint8, device=dev)
             self._info = torch.zeros((1, cabi.INFO_DT.itemsize // 4), dtype=torch.int32, device=dev)
             self._act = torch.zeros((1, 2), dtype=torch.float32, device=dev)
-        self._engine.load(T)
+        if self._loaded_seed != seed:
+            self._engine.load(part)
+            self._loaded_seed = seed
 
     # -- read-only views of the reference's object graph (envs/base_env.py:371-462) ----------------------------------
     def _map_of(self, seed):

@@ -87,6 +87,28 @@ def test_registered_ids():
     assert ENVIRONMENTS["PGDrive-1000envs-v0"] == dict(start_seed=1000, environment_num=1000)  # register.py:24-27
 
 
+def test_gym_registration_with_a_stand_in_registry(monkeypatch):
+    """register.py:42-43 of the reference: every id registered with kwargs=dict(config=...).  gym is not installed in
+    this image, so a stand-in module records the calls."""
+    import sys
+    import types
+    calls = {}
+    reg = types.ModuleType("gym.envs.registration")
+    reg.registry = {}
+    reg.register = lambda id, entry_point, kwargs: calls.__setitem__(id, (entry_point, kwargs))
+    gym = types.ModuleType("gym")
+    envs = types.ModuleType("gym.envs")
+    for name, mod in (("gym", gym), ("gym.envs", envs), ("gym.envs.registration", reg)):
+        monkeypatch.setitem(sys.modules, name, mod)
+    gym.envs, envs.registration = envs, reg
+    from pgdrive_b200 import register
+    monkeypatch.setattr(register, "registered_with", [])
+    assert "gym" in register.register_all()
+    assert set(calls) == set(register.get_env_list()) and len(calls) == 8
+    assert calls["PGDrive-1000envs-v0"] == ("pgdrive_b200.env:PGDriveEnv",
+                                            dict(config=dict(start_seed=1000, environment_num=1000)))
+
+
 def test_no_gpu_means_loud_failure():
     import torch
     if torch.cuda.is_available():
