@@ -215,7 +215,7 @@ def run_own(args):
         __graft_entry__.build()
     if world > 1:
         dist.barrier()
-    from pgdrive_b200 import VecPGDriveEnv
+    from pgdrive_b200 import VecPGDriveEnv, cabi
     from pgdrive_b200.sharding import GatherBuffers, PeerGather
     n, K, W = args.envs, args.steps, args.warmup
     first_seed, n_seeds, n_slots, desc = WORKLOADS[args.workload]
@@ -253,59 +253,99 @@ def run_own(args):
     fwd[..., 1] = fwd[..., 1].abs()
     fwd[..., 0] *= 0.1
 
-    done_ev = [None, None]      # per gather buffer: event after which it may be written again
+    # ---- gather plumbing.  The host enqueues every step's work in ~60 us (one kernel launch, three event operations,
+    # one 4-byte all-reduce, one consumer reduction): pre-created events, pre-resolved pointers, ONE reduction kernel
+    # for the consumer -- with 15+ torch calls per step the loop was bound by Python, not by the GPUs.
+    use_ev = [torch.cuda.Event(), torch.cuda.Event()]
+    ar_ev = [torch.cuda.Event(), torch.cuda.Event()]
+    ready_ev = [torch.cuda.Event(), torch.cuda.Event()]
+    armed = dict(use=[False, False], ar=[False, False])
     counter = [0]
-    consumed = torch.zeros(3, dtype=torch.float64, device=dev)   # rank 0: what the consumer read during the timed steps
-    verified = torch.zeros(3, dtype=torch.float64, device=dev)   # rank 0: the same sums over the verification steps
-    local_sum = torch.zeros(3, dtype=torch.float64, device=dev)  # every rank: sums over its OWN rows, same steps
+    consumed = torch.zeros(1, dtype=torch.int64, device=dev)   # rank 0: checksum of what the consumer read (timed steps)
+    verified = torch.zeros(1, dtype=torch.int64, device=dev)   # rank 0: the same over the verification steps
+    local_sum = torch.zeros(1, dtype=torch.int64, device=dev)  # every rank: checksum of its OWN rows, same steps
+    direct = peer is not None and (peer.mode == "peer" or rank == 0)  # rank 0's own rows are local memory either way
+    step_ptrs, whole = [None, None], [None, None]
+    if peer is not None:
+        for i in range(2):
+            step_ptrs[i] = peer.pointers(i) if direct else peer.local_pointers(i)
+            if rank == 0:
+                whole[i] = peer.words(i)  # the whole gathered buffer (obs | reward | done) as int32 words
+    elif world > 1:
+        for i in range(2):
+            whole[i] = [bufs[i].obs.view(torch.int32), bufs[i].reward.view(torch.int32), bufs[i].done.view(torch.int32)]
 
-    def checksum_into(acc, obs, reward, done):
-        acc[0] += obs.sum(dtype=torch.float64)
-        acc[1] += reward.sum(dtype=torch.float64)
-        acc[2] += done.sum(dtype=torch.float64)
+    def words_sum(acc, tensors):
+        """Integer checksum (sum of the buffer's 32-bit words, 64-bit accumulator; pgd_words_checksum reads at HBM speed):
+        exact and order-independent, so the consumer's sum over the whole gathered batch must EQUAL the total of the
+        ranks' sums over their own rows."""
+        e = env.engine
+        st = torch.cuda.current_stream(dev).cuda_stream
+        for t in tensors:
+            nbytes = t.numel() * t.element_size()
+            if nbytes % 16 == 0 and t.data_ptr() % 16 == 0:
+                cabi.check(e.lib, e.lib.pgd_words_checksum(e.h, t.data_ptr(), nbytes, acc.data_ptr(), st))
+            else:  # odd-sized views (never the whole-batch buffers)
+                acc += t.sum(dtype=torch.int64)
+
+    def own_rows(i):
+        if peer is not None:
+            return [t.view(torch.int32) for t in peer.local_views(i, remote=direct)]
+        b = bufs[i]
+        return [b.local(b.obs).view(torch.int32), b.local(b.reward).view(torch.int32), b.local(b.done).view(torch.int32)]
 
     def step_and_gather(a, check=False):
-        """One step of this rank + the gather of everybody's results to rank 0 (+ rank 0 reading the batch)."""
+        """One step of this rank + the gather of everybody's results to rank 0 (+ rank 0 reading the batch).
+
+        Two gather buffers alternate.  Before the kernel of step t writes buffer i = t % 2 it waits for
+          use_ev[i]     the last LOCAL reader of buffer i from step t - 2 (copy engine push / all-gather of this rank's
+                        rows; on rank 0 the consumer that read the whole batch), and -- only when the kernel stores
+                        straight into rank 0's memory (peer mode, ranks > 0) --
+          ar_ev[1 - i]  this rank's completion barrier of step t - 1: rank 0 enqueues its read of step t - 2 before it
+                        joins that barrier, so the barrier having completed means buffer i has been read.
+        Nothing else is ordered: the gather of step t overlaps the kernel of step t + 1."""
         if world == 1:
             env.step(a)
             return
-        i = counter[0] % 2
+        i = counter[0] & 1
         counter[0] += 1
         cur = torch.cuda.current_stream(dev)
-        if done_ev[1 - i] is not None:
-            # buffer i was last written two steps ago.  Waiting for the PREVIOUS step's barrier is what makes rewriting
-            # it safe: rank 0 enqueued its read of buffer i before it joined that barrier (sharding.PeerGather)
-            cur.wait_event(done_ev[1 - i])
+        if armed["use"][i]:
+            cur.wait_event(use_ev[i])
         if peer is not None:
-            direct = peer.mode == "peer" or rank == 0  # rank 0's own rows are local memory either way
-            env.step_into(a, *(peer.pointers(i) if direct else peer.local_pointers(i)))
+            if peer.mode == "peer" and rank != 0 and armed["ar"][1 - i]:
+                cur.wait_event(ar_ev[1 - i])
+            env.step_into(a, *step_ptrs[i])
             if check == "verify":  # untimed: this rank's own rows (read back over NVLink in peer mode)
-                checksum_into(local_sum, *peer.local_views(i, remote=direct))
-            ready = torch.cuda.Event()
-            ready.record(cur)
-            side.wait_event(ready)
+                words_sum(local_sum, own_rows(i))
+            ready_ev[i].record(cur)
             with torch.cuda.stream(side):
+                side.wait_event(ready_ev[i])
                 if not direct:
                     peer.push(i)  # copy engine: local rows -> rank 0's buffer over NVLink
+                    use_ev[i].record(side)
+                    armed["use"][i] = True
                 peer.completion_barrier()
-                if rank == 0 and check:  # the consumer reads the whole gathered batch, every step
-                    checksum_into(verified if check == "verify" else consumed, *peer.tensors(i))
-                done_ev[i] = torch.cuda.Event()
-                done_ev[i].record(side)
+                ar_ev[i].record(side)
+                armed["ar"][i] = True
+                if rank == 0:
+                    if check:  # the consumer reads the whole gathered batch, every step
+                        words_sum(verified if check == "verify" else consumed, whole[i])
+                    use_ev[i].record(side)
+                    armed["use"][i] = True
             return
         b = bufs[i]
         env.step(a, out=(b.local(b.obs), b.local(b.reward), b.local(b.done)))
         if check == "verify":
-            checksum_into(local_sum, b.local(b.obs), b.local(b.reward), b.local(b.done))
-        ready = torch.cuda.Event()
-        ready.record(cur)
-        side.wait_event(ready)
+            words_sum(local_sum, own_rows(i))
+        ready_ev[i].record(cur)
         with torch.cuda.stream(side):
+            side.wait_event(ready_ev[i])
             b.all_gather(dist)
             if rank == 0 and check:
-                checksum_into(verified if check == "verify" else consumed, b.obs, b.reward, b.done)
-            done_ev[i] = torch.cuda.Event()
-            done_ev[i].record(side)
+                words_sum(verified if check == "verify" else consumed, whole[i])
+            use_ev[i].record(side)
+            armed["use"][i] = True
 
     def drain():
         if side is not None:
@@ -456,15 +496,13 @@ def run_own(args):
 
     gather_check = None
     if world > 1:
-        want = torch.stack(sums).sum(0).cpu().numpy()
-        got = verified.cpu().numpy()
+        want = int(torch.stack(sums).sum().item())
+        got = int(verified.item())
         gather_check = dict(
-            consumer="rank 0 sums obs / reward / done of the whole gathered batch after every step's gather (timed "
-                     "region: consumed_timed); over 4 more untimed steps every rank also sums its own rows and rank 0's "
-                     "sums must equal the total of the ranks' (verified vs sum_of_rank_local)",
-            consumed_timed=[float(x) for x in consumed.cpu().numpy()],
-            verified=[float(x) for x in got], sum_of_rank_local=[float(x) for x in want],
-            ok=bool(np.allclose(got, want, rtol=1e-9, atol=1e-6)))
+            consumer="rank 0 reads the whole gathered batch after every step's gather: integer checksum = sum of its "
+                     "32-bit words (consumed_timed).  Over 4 more untimed steps every rank also sums its own rows; the "
+                     "consumer's checksum must EQUAL the total of the ranks' (verified == sum_of_rank_local)",
+            consumed_timed=int(consumed.item()), verified=got, sum_of_rank_local=want, ok=bool(got == want))
 
     # ---- the reset path: maps + episode templates of the workload's seeds generated ON the device -------------------
     reset_path = None

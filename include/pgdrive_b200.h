@@ -86,6 +86,10 @@ int pgd_peer_open(PgdHandle* h, const unsigned char handle[64], void** dev_ptr);
 int pgd_peer_release(PgdHandle* h, void* dev_ptr, int32_t is_owner);
 
 /* measurement helpers */
+/* *out_dev += sum of the 32-bit words of [dev_ptr, dev_ptr + bytes) (both multiples of 16), 64-bit accumulator: the
+ * stand-in for a consumer that reads the whole gathered batch every step (bench.py), exact and order-independent so
+ * that the consumer's checksum can be compared with the producers'. */
+int pgd_words_checksum(PgdHandle* h, const void* dev_ptr, uint64_t bytes, uint64_t* out_dev, void* stream);
 int64_t pgd_state_bytes_per_env(PgdHandle* h);   /* bytes of simulator state kept per environment */
 int64_t pgd_launch_count(PgdHandle* h);          /* kernels launched by this handle so far */
 int pgd_set_timing(PgdHandle* h, int32_t on);    /* bracket the step kernel with CUDA events */

@@ -361,6 +361,30 @@ extern "C" int pgd_peer_release(PgdHandle* h, void* dev_ptr, int32_t is_owner) {
   return 0;
 }
 
+// Sum of the 32-bit words of a device buffer into a 64-bit accumulator (*out_dev += sum): what a consumer of the gathered
+// batch does at the least -- touch every byte once, at HBM speed (16-byte loads, grid sized to the SM count).
+__global__ void __launch_bounds__(256) pgd_words_sum_kernel(const uint4* __restrict__ p, size_t n16,
+                                                            unsigned long long* __restrict__ out) {
+  unsigned long long acc = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+    const uint4 v = p[i];
+    acc += (unsigned long long)v.x + v.y + v.z + v.w;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, d);
+  if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}
+
+extern "C" int pgd_words_checksum(PgdHandle* h, const void* dev_ptr, uint64_t bytes, uint64_t* out_dev, void* stream) {
+  if (!h || !dev_ptr || !out_dev) return fail(-1, "pgd_words_checksum: null argument");
+  if ((bytes & 15) || ((uintptr_t)dev_ptr & 15)) return fail(-1, "pgd_words_checksum: pointer and size must be multiples of 16");
+  CU(cudaSetDevice(h->device));
+  pgd_words_sum_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>((const uint4*)dev_ptr, (size_t)(bytes / 16),
+                                                                  (unsigned long long*)out_dev);
+  CU(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int64_t pgd_state_bytes_per_env(PgdHandle* h) { return h ? (int64_t)h->cfg.num_slots * 80 + 32 : 0; }
 extern "C" int64_t pgd_launch_count(PgdHandle* h) { return h ? h->launches : 0; }
 extern "C" int pgd_set_timing(PgdHandle* h, int32_t on) {

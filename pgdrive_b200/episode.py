@@ -69,6 +69,80 @@ class VehicleSlot:
     __slots__ = ("type", "lane", "long", "seed", "params", "idm_seed", "overtake_timer", "checkpoints")
 
 
+class StaticObject:
+    """A traffic cone / warning tripod / barrier or a broken-down vehicle of an accident scene."""
+    __slots__ = ("kind", "type", "lane", "long", "lat", "seed", "params")
+
+
+# component/static_object/traffic_object.py:37-103: footprint (extent along the lane, across the lane) and mass.  Cones
+# and tripods are cylinders (radius 0.25 / 0.5): their footprint is the enclosing square.  A barrier's LENGTH (2.0) lies
+# ACROSS the lane: objects are oriented with setH(panda_heading(h)), vehicles with an extra -90 degrees
+# (base_vehicle.py:681).
+OBJECT_BODY = {"TrafficCone": (0.5, 0.5, 1.0), "TrafficWarning": (1.0, 1.0, 1.0), "TrafficBarrier": (0.3, 2.0, 10.0)}
+ACCIDENT_BLOCKS = ("S", "C", "r", "R")  # object_manager.py:51-53: Straight, Curve, InRampOnStraight, OutRampOnStraight
+ALERT_DIST, ACCIDENT_AREA_LEN, CONE_LONGITUDE, CONE_LATERAL, PROHIBIT_SCENE_PROB = 10, 10, 2, 1, 0.67
+
+
+def make_accidents(pgmap, seed, accident_prob, engine_rs, traffic_rs):
+    """TrafficObjectManager.reset (manager/object_manager.py:40-124) on its own stream of the seed; every spawned object
+    draws its seed from the ENGINE's stream (before the ego: the manager's PRIORITY is 9) and a broken-down vehicle's
+    type comes from the TRAFFIC manager's stream.  Returns (objects, accident_lanes)."""
+    objects, accident_lanes = [], []
+    if abs(accident_prob) < 1e-2:
+        return objects, accident_lanes
+    rs = rng.seeded(seed)
+    lane_width = pgmap.lane_width
+
+    def spawn(kind, lane, lon, lat, vtype=None):
+        o = StaticObject()
+        o.kind, o.type, o.lane, o.long, o.lat = kind, vtype, lane, float(lon), float(lat)
+        o.seed = rng.draw_seed(engine_rs)
+        o.params = sample_vehicle(vtype, o.seed) if vtype else None
+        objects.append(o)
+
+    for block in pgmap.blocks:
+        if block.id not in ACCIDENT_BLOCKS:
+            continue
+        if rs.rand() > accident_prob:
+            continue
+        road_1 = (block.pre_socket.pos[1], block.node(0, 0))
+        road_2 = (block.node(0, 0), block.node(0, 1)) if block.id != "S" else None
+        is_ramp = block.id in ("r", "R")
+        if rs.rand() > PROHIBIT_SCENE_PROB:  # a coned-off lane end
+            road = (road_1, road_2)[int(rs.choice(2))] if block.id != "C" else road_2
+            road = road_1 if road is None else road
+            on_left = bool(rs.rand() > 0.5 or (road is road_2 and is_ramp))
+            lanes = pgmap.net.lanes(road)
+            idx = 0 if on_left else len(lanes) - 1
+            lane = lanes[idx]
+            longitude = lane.length - ACCIDENT_AREA_LEN
+            accident_lanes += [(road[0], road[1], i) for i in range(len(lanes))]
+            lat_num = int(lane_width / CONE_LATERAL)
+            longitude_num = int(ACCIDENT_AREA_LEN / CONE_LONGITUDE)
+            lats = [k * CONE_LATERAL for k in range(lat_num)] + [lat_num * CONE_LATERAL] * (longitude_num + 1) + \
+                [(lat_num - k - 1) * CONE_LATERAL for k in range(lat_num)]
+            total = lat_num * 2 + longitude_num + 1
+            left = 1 if on_left else -1
+            for k, lat in zip(range(-int(total / 2), int(total / 2)), lats):
+                spawn("TrafficCone", (road[0], road[1], idx), k * CONE_LONGITUDE + longitude, left * (lat - lane.width / 2))
+        else:  # a broken-down vehicle with its warning tripod, or a barrier
+            road = (road_1, road_2)[int(rs.choice(2))]
+            road = road_1 if road is None else road
+            on_left = bool(rs.rand() > 0.5 or (road is road_2 and is_ramp))
+            lanes = pgmap.net.lanes(road)
+            idx = int(rs.randint(0, len(lanes) - 1)) if on_left else len(lanes) - 1
+            lane = lanes[idx]
+            longitude = rs.rand() * lane.length / 2 + lane.length / 2
+            if rs.rand() > 0.5:
+                vtype = TYPE_KEYS[int(traffic_rs.choice(len(TYPE_KEYS), p=TYPE_PROB))]
+                spawn("vehicle", (road[0], road[1], idx), longitude, 0.0, vtype)
+                spawn("TrafficWarning", (road[0], road[1], idx), longitude - ALERT_DIST, 0.0)
+            else:
+                spawn("TrafficBarrier", (road[0], road[1], idx), longitude, 0.0)
+    return objects, accident_lanes
+
+
+
 class EpisodeTemplate:
     def __init__(self, seed, density):
         self.seed = seed
@@ -78,6 +152,7 @@ class EpisodeTemplate:
         self.ego_params = None
         self.ego_checkpoints = None
         self.block_vehicles = []  # [(trigger_road, [VehicleSlot])], LAST element triggers first
+        self.objects = []         # [StaticObject]: accident scenes (SafePGDriveEnv)
 
 
 def respawn_lanes(pgmap):
@@ -95,7 +170,8 @@ def respawn_lanes(pgmap):
     return lanes
 
 
-def make_episode(pgmap, seed, density=0.1, spawn_lane=(">", ">>", 0), random_agent_model=False, traffic_mode="trigger"):
+def make_episode(pgmap, seed, density=0.1, spawn_lane=(">", ">>", 0), random_agent_model=False, traffic_mode="trigger",
+                 accident_prob=0.0):
     """``traffic_mode`` (traffic_manager.py:21-27): "trigger" and "hybrid" create every block's vehicles once and wake
     them when the ego reaches the block (in this version of the reference the two are the same code path, :63-69,
     :76-85); "respawn" fills every respawn lane with one vehicle per 10 m -- the density only switches traffic on --
@@ -110,6 +186,7 @@ def make_episode(pgmap, seed, density=0.1, spawn_lane=(">", ">>", 0), random_age
     ep.ego_type = "default"
     if random_agent_model:
         ep.ego_type = TYPE_KEYS[int(rng.seeded(seed).choice(len(TYPE_KEYS), p=[1 / len(TYPE_KEYS)] * len(TYPE_KEYS)))]
+    ep.objects, accident_lanes = make_accidents(pgmap, seed, accident_prob, engine_rs, traffic_rs)
     ep.ego_seed = rng.draw_seed(engine_rs)
     ep.ego_params = sample_vehicle(ep.ego_type, ep.ego_seed)
     ep.ego_checkpoints = route_for(pgmap, spawn_lane, seed)
@@ -144,6 +221,8 @@ def make_episode(pgmap, seed, density=0.1, spawn_lane=(">", ">>", 0), random_age
         cand = []
         for lanes in spawn:
             for ln in lanes:
+                if lane_index[id(ln)] in accident_lanes:  # traffic_manager.py:251-252
+                    continue
                 for k in range(int(ln.length / VEHICLE_GAP)):
                     cand.append((lane_index[id(ln)], k * VEHICLE_GAP))
         total_length = sum(ln.length for lanes in spawn for ln in lanes)

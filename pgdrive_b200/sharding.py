@@ -136,6 +136,13 @@ class PeerGather:
         return (self._wrap(b, (rows, self.obs_dim), "<f4"), self._wrap(b + self.obs_bytes, (rows, ), "<f4"),
                 self._wrap(b + self.obs_bytes + self.rew_bytes, (rows, ), "|u1"))
 
+    def words(self, i):
+        """Rank 0 only: buffer ``i`` (observations | rewards | dones + padding) as ONE int32 tensor -- a consumer that
+        wants to touch every byte of the gathered batch can do it with a single reduction."""
+        assert self.rank == 0
+        b = self.base + (i % self.depth) * self.stride
+        return [self._wrap(b, (self.stride // 4, ), "<i4")]
+
     def close(self):
         import ctypes as C
         if self.base:

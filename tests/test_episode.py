@@ -85,3 +85,32 @@ def test_respawn_traffic_mode_matches_reference():
         assert [(r, [(v.lane, v.long, v.seed) for v in vs]) for r, vs in hy.block_vehicles] == \
                [(r, [(v.lane, v.long, v.seed) for v in vs]) for r, vs in tr.block_vehicles]
     assert min(counts) >= 12 and max(counts) > 31  # some maps need more than the 32 vehicle slots the kernel has
+
+
+def test_accident_scenes_match_reference():
+    """SafePGDriveEnv's accident scenes (manager/object_manager.py:40-124): which blocks get one, cones / tripods /
+    barriers / broken-down vehicles with their lanes and Frenet coordinates, the engine seeds they consume before the ego
+    draws its own, the vehicle type taken from the traffic stream, and the traffic that avoids the coned-off lanes --
+    against the reference's own TrafficObjectManager.reset + TrafficManager (tests/golden/reset_accidents.json.gz)."""
+    from conftest import load_golden
+    gold = load_golden("reset_accidents.json.gz")
+    kinds = set()
+    for s, d in gold.items():
+        m = mapgen.generate_map(int(s))
+        ep = episode.make_episode(m, int(s), d["density"], accident_prob=d["accident_prob"])
+        assert len(ep.objects) == len(d["objects"]), s
+        for o, g in zip(ep.objects, d["objects"]):
+            assert (o.kind, list(o.lane), o.seed) == (g["kind"], g["lane"], g["seed"]), s
+            assert abs(o.long - g["long"]) < 1e-9 and abs(o.lat - g["lat"]) < 1e-9, s
+            if o.kind == "vehicle":
+                assert o.type == g["type"] and o.params == g["params"], s
+            kinds.add(o.kind)
+        assert ep.ego_seed == d["ego_seed"] and ep.ego_params == d["ego_params"], s
+        assert len(ep.block_vehicles) == len(d["block_vehicles"])
+        for (trigger, slots), g in zip(ep.block_vehicles, d["block_vehicles"]):
+            assert list(trigger) == g["trigger_road"] and len(slots) == len(g["vehicles"]), s
+            for v, gv in zip(slots, g["vehicles"]):
+                assert (v.type, list(v.lane), v.long, v.seed, v.idm_seed) == \
+                    (gv["type"], gv["lane"], gv["long"], gv["seed"], gv["idm_seed"]), s
+                assert v.params == gv["params"] and v.checkpoints == gv["checkpoints"], s
+    assert kinds == {"TrafficCone", "TrafficWarning", "TrafficBarrier", "vehicle"}

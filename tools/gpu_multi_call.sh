@@ -7,7 +7,7 @@ python -c "import __graft_entry__ as g; g.build()" > /dev/null 2>&1
 RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
 timeout 600 $RUN tools/mgpu_peer_check.py 2>&1 | grep -i "gather" | tee gpurun_out/${TAG}_peer_check_${N}gpu.log
 for mode in ${MODES:-peer copy}; do
-  NCCL_DEBUG=INFO timeout 900 $RUN bench.py --gpus $N --steps ${STEPS:-128} --warmup 8 --gather $mode \
+  NCCL_DEBUG=INFO PGDRIVE_B200_LIB=${LIB:-} timeout 900 $RUN bench.py --gpus $N --steps ${STEPS:-128} --warmup 8 --gather $mode \
     > gpurun_out/${TAG}_bench_${N}gpu_${mode}.json 2> gpurun_out/${TAG}_bench_${N}gpu_${mode}.err
   python - <<PY
 import json

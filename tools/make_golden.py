@@ -189,7 +189,7 @@ def sample_vehicle_params(vclass, seed):
     return {k: float(v) for k, v in obj.get_config().items()}
 
 
-def dump_reset(seed, density=0.1, mode="trigger"):
+def dump_reset(seed, density=0.1, mode="trigger", accident_prob=0.0):
     from pgdrive.component.vehicle_module.navigation import Navigation
     from pgdrive.component.vehicle.vehicle_type import vehicle_type, DefaultVehicle
     from pgdrive.manager.traffic_manager import TrafficManager
@@ -204,6 +204,44 @@ def dump_reset(seed, density=0.1, mode="trigger"):
                 l.index = (frm, to, i)
 
     rec = dict(seed=seed, density=density)
+    tm = TrafficManager.__new__(TrafficManager)  # created early: the object manager borrows its random_vehicle_type
+    tm.engine = eng
+    tm.random_seed = seed
+    tm.np_random = get_np_random(seed)
+    accident_lanes = []
+    if accident_prob > 0:
+        # --- accident scenes (manager/object_manager.py:40-124; PRIORITY 9: its reset runs before the agent manager's) ---
+        from pgdrive.manager.object_manager import TrafficObjectManager
+        om = TrafficObjectManager.__new__(TrafficObjectManager)
+        om.engine = eng
+        om.random_seed = seed
+        om.np_random = get_np_random(seed)
+        om.accident_prob = accident_prob
+        om.accident_lanes = []
+        om.spawned_objects = {}
+        objs = []
+
+        def om_spawn(cls, **kw):
+            oseed = eng.generate_seed()  # base_engine.py:102-103
+            name = cls.__name__
+            if "vehicle_config" in kw:
+                vc = kw["vehicle_config"]
+                r = dict(kind="vehicle", type={v: k for k, v in vehicle_type.items()}[cls], lane=list(vc["spawn_lane_index"]),
+                         long=float(vc["spawn_longitude"]), lat=0.0, seed=int(oseed),
+                         params=sample_vehicle_params(cls, oseed))
+            else:
+                r = dict(kind=name, lane=list(kw["lane"].index), long=float(kw["longitude"]), lat=float(kw["lateral"]),
+                         seed=int(oseed))
+            objs.append(r)
+            return type("Obj", (), dict(set_break_down=lambda self, *a: None))()
+
+        om.spawn_object = om_spawn
+        eng.traffic_manager = tm
+        om.reset()
+        rec["accident_prob"] = accident_prob
+        rec["objects"] = objs
+        rec["accident_lanes"] = [list(l.index) for l in om.accident_lanes]
+        accident_lanes = om.accident_lanes
     # --- ego (agent manager runs before traffic manager: PRIORITY tie, registration order) ---
     ego_seed = eng.generate_seed()
     rec["ego_seed"] = int(ego_seed)
@@ -213,10 +251,6 @@ def dump_reset(seed, density=0.1, mode="trigger"):
     rec["ego_checkpoints"] = list(nav.checkpoints)
 
     # --- traffic: run the reference's own _create_vehicles_once against a recording engine ---
-    tm = TrafficManager.__new__(TrafficManager)
-    tm.engine = eng
-    tm.random_seed = seed
-    tm.np_random = get_np_random(seed)
     tm.spawned_objects = {}
     tm._traffic_vehicles = []
     tm.block_triggered_vehicles = []
@@ -248,7 +282,7 @@ def dump_reset(seed, density=0.1, mode="trigger"):
         v.timer = int(policy.overtake_timer)
 
     eng.add_policy = add_policy
-    eng.object_manager = type("OM", (), dict(accident_lanes=[]))()
+    eng.object_manager = type("OM", (), dict(accident_lanes=accident_lanes))()
     type(eng).map_manager = property(lambda self: type("MM", (), dict(current_map=m))())
     if abs(density) >= 1e-2:
         if mode == "respawn":  # traffic_manager.py:63-66: every respawn lane is filled, all vehicles act from step 0
@@ -284,10 +318,10 @@ def dump_reset(seed, density=0.1, mode="trigger"):
     return rec
 
 
-def cmd_reset(seeds, tag, density=0.1, mode="trigger"):
+def cmd_reset(seeds, tag, density=0.1, mode="trigger", accident_prob=0.0):
     out = {}
     for s in seeds:
-        out[str(s)] = dump_reset(s, density, mode)
+        out[str(s)] = dump_reset(s, density, mode, accident_prob)
     path = os.path.join(GOLD, "reset_%s.json.gz" % tag)
     with gzip.open(path, "wt") as f:
         json.dump(out, f)
@@ -304,6 +338,9 @@ if __name__ == "__main__":
         cmd_reset([0, 1, 2, 99, 1500, 1999, 2999, 12345, 29999], "misc")
     elif what == "reset_respawn":  # traffic_mode="respawn" (traffic_manager.py:21-27,63-66,224-237)
         cmd_reset(list(range(1000, 1030)) + [0, 1, 2, 99], "respawn", mode="respawn")
+    elif what == "reset_accidents":  # SafePGDriveEnv: accident_prob 0.8, traffic_density 0.05 (safe_pgdrive_env.py:8-25)
+        cmd_reset(list(range(100, 140)) + [0, 1, 2, 1000, 1001, 1002, 1003, 1005], "accidents", density=0.05,
+                  accident_prob=0.8)
     elif what == "probe":
         print(json.dumps(dump_reset(int(sys.argv[2])), indent=1)[:6000])
 
