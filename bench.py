@@ -233,7 +233,9 @@ def run_own(args):
     if world > 1:
         gather_mode = args.gather
         if gather_mode == "auto":
-            gather_mode = "peer"
+            # copy engine push: 707 GB/s into rank 0 at 8 GPUs against 653 GB/s for the kernel's own remote row stores
+            # (profiles/r02q_bench_8gpu_*.json); at 2 GPUs the two tie
+            gather_mode = "copy"
         if gather_mode in ("peer", "copy"):
             ok = torch.ones(1, dtype=torch.int32, device=dev)
             try:
@@ -593,9 +595,10 @@ def main():
     ap.add_argument("--envs", type=int, default=65536, help="environments per GPU (4096 = BASELINE.json configs[1])")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--gather", default="auto", choices=["auto", "peer", "copy", "nccl"],
-                    help="N > 1: how rank 0 gets the whole batch (auto = peer: rows stored by the step kernel straight "
-                         "into rank 0's HBM; copy: local rows pushed by the copy engine on a side stream; nccl: in-place "
-                         "all-gather, also the fall-back when peer mapping is not permitted)")
+                    help="N > 1: how rank 0 gets the whole batch (auto = copy: local rows pushed into rank 0's HBM by the "
+                         "copy engine on a side stream while the next step's kernel runs; peer: rows stored by the step "
+                         "kernel straight into rank 0's HBM; nccl: in-place all-gather, also the fall-back when peer mapping "
+                         "is not permitted)")
     ap.add_argument("--workload", default="v0", choices=sorted(WORKLOADS), help="v0 = BASELINE.json configs[2] (the metric's "
                     "configuration); 1000envs = configs[3]")
     args = ap.parse_args()

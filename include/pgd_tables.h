@@ -63,8 +63,14 @@ typedef struct {          /* 64 B */
 } PgdMap;
 
 /* PgdSlot.group: >= 0 trigger group (woken when the ego reaches the group's road), -1 the ego, PGD_GROUP_AWAKE a
- * traffic vehicle that drives from the first step (traffic_mode "respawn", manager/traffic_manager.py:63-66,224-237) */
-enum { PGD_GROUP_AWAKE = -2 };
+ * traffic vehicle that drives from the first step (traffic_mode "respawn", manager/traffic_manager.py:63-66,224-237),
+ * PGD_GROUP_STATIC an object or broken-down vehicle of an accident scene (manager/object_manager.py:40-124) */
+enum { PGD_GROUP_AWAKE = -2, PGD_GROUP_STATIC = -3 };
+/* PgdSlot.type: 0..4 vehicle types s, m, l, xl, default (vehicle_type.py); >= PGD_TYPE_OBJECT a traffic cone / warning
+ * tripod / barrier of an accident scene (component/static_object/traffic_object.py:37-103), always PGD_GROUP_STATIC like a
+ * broken-down vehicle: present, an obstacle for IDM and the lidar, never driving.  Touching one sets crash_object (once
+ * per object: COST_ONCE), touching a vehicle crash_vehicle (engine/core/collision_callback.py:7-35). */
+enum { PGD_TYPE_OBJECT = 5, PGD_TYPE_CONE = 5, PGD_TYPE_WARNING = 6, PGD_TYPE_BARRIER = 7 };
 
 typedef struct {          /* 96 B */
   float x, y, heading;    /* spawn pose */
@@ -144,6 +150,10 @@ typedef struct {
   /* base_vehicle.py:249,351-358 (vehicle_config.increment_steering): steering += action[0] * 0.05, clipped to [-1, 1];
    * the raw steering action of the last step (observation value 5) is kept in the ego's otherwise unused pid_hp */
   int32_t increment_steering;
+  /* accident scenes (envs/safe_pgdrive_env.py:7-63, envs/pgdrive_env.py:197-258): reward / cost of touching a traffic
+   * object; safe_rl_env: an episode does not end on a crash (vehicle or object), it only costs */
+  float crash_object_penalty, crash_object_cost;
+  int32_t safe_rl_env;
 } PgdConfig;
 
 /* Observation length (obs/state_obs.py:18-23,108-115,125-130): (n_side or 2) + 6 + n_lane_line [+ 2 vehicle
@@ -157,7 +167,7 @@ static inline int32_t pgd_obs_dim(const PgdConfig* c) {
 enum {
   PGD_F_CRASH_VEHICLE = 1 << 0, PGD_F_OUT_OF_ROAD = 1 << 1, PGD_F_ARRIVE_DEST = 1 << 2, PGD_F_MAX_STEP = 1 << 3,
   PGD_F_ON_YELLOW = 1 << 4, PGD_F_ON_WHITE = 1 << 5, PGD_F_ON_BROKEN = 1 << 6, PGD_F_CRASH_SIDEWALK = 1 << 7,
-  PGD_F_ON_LANE = 1 << 8, PGD_F_OUT_OF_ROUTE = 1 << 9, PGD_F_WAS_RESET = 1 << 10
+  PGD_F_ON_LANE = 1 << 8, PGD_F_OUT_OF_ROUTE = 1 << 9, PGD_F_WAS_RESET = 1 << 10, PGD_F_CRASH_OBJECT = 1 << 11
 };
 typedef struct {          /* 40 B */
   float velocity, steering, acceleration, step_energy, episode_energy;
@@ -167,7 +177,7 @@ typedef struct {          /* 40 B */
 } PgdInfo;
 
 /* Exchange format for pgd_get_state / pgd_set_state (parity debugging; not the device layout). */
-enum { PGD_V_ALIVE = 1, PGD_V_ACTIVE = 2, PGD_V_ON_LANE = 4 };
+enum { PGD_V_ALIVE = 1, PGD_V_ACTIVE = 2, PGD_V_ON_LANE = 4, PGD_V_CRASHED = 16 /* object already charged (COST_ONCE) */ };
 typedef struct {          /* 80 B */
   float x, y, heading, speed;
   float steer, throttle;

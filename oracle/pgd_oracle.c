@@ -47,6 +47,7 @@ typedef struct {
   float target_speed;
   int lane, ck0, ck1, rt_lane, timer, rnd_n, airborne;
   int alive, active, on_lane;
+  int crashed; /* traffic object already charged (COST_ONCE, traffic_object.py:22) */
   const PgdSlot* s;
 } Veh;
 
@@ -542,11 +543,12 @@ static float detector_beam(const Oracle* o, const PgdMap* m, const Veh* ego, int
 }
 
 /* After-step bookkeeping + observation + reward + done for the ego.  `fresh` = called from reset. */
-static void post_step(Oracle* o, Env* e, float last_x, float last_y, float last_h, int crash_vehicle, int fresh,
+static void post_step(Oracle* o, Env* e, float last_x, float last_y, float last_h, int crash_bits, int fresh,
                       float* obs, float* reward, uint8_t* done, PgdInfo* info) {
   const PgdMap* m = map_of(o, e);
   const PgdConfig* c = &o->cfg;
   Veh* ego = &e->v[0];
+  const int crash_vehicle = crash_bits & 1, crash_object = (crash_bits >> 1) & 1;
   /* after_step of every moving vehicle (agent_manager.py:201-203, traffic_manager.py:91-109) */
   localize(o, m, ego);
   for (int i = 1; i < e->n_slots; ++i) {
@@ -570,6 +572,7 @@ static void post_step(Oracle* o, Env* e, float last_x, float last_y, float last_
   }
   if (ego->on_lane) flags |= PGD_F_ON_LANE;
   if (crash_vehicle) flags |= PGD_F_CRASH_VEHICLE;
+  if (crash_object) flags |= PGD_F_CRASH_OBJECT;
   /* route geometry */
   int cur_road_id = route_road(o, ego, ego->ck0);
   const PgdRoad* cur_road = road_at(o, m, cur_road_id);
@@ -628,6 +631,12 @@ static void post_step(Oracle* o, Env* e, float last_x, float last_y, float last_
   {
     int objs[PGD_MAX_SLOTS];
     int n = near_objects(e, 0, objs);
+    { /* get_surrounding_vehicles (lidar.py:46-54): cones and barriers are not vehicles */
+      int m = 0;
+      for (int k = 0; k < n; ++k)
+        if (e->v[objs[k]].s->type < PGD_TYPE_OBJECT) objs[m++] = objs[k];
+      n = m;
+    }
     float d2[PGD_MAX_SLOTS];
     for (int k = 0; k < n; ++k) {
       float dx = e->v[objs[k]].x - ego->x, dy = e->v[objs[k]].y - ego->y;
@@ -700,9 +709,13 @@ static void post_step(Oracle* o, Env* e, float last_x, float last_y, float last_
     if (flags & PGD_F_ARRIVE_DEST) r = c->success_reward;
     else if (out_of_road) r = -c->out_of_road_penalty;
     else if (crash_vehicle) r = -c->crash_vehicle_penalty;
+    else if (crash_object) r = -c->crash_object_penalty;
     if (out_of_road) cost = c->out_of_road_cost;
     else if (crash_vehicle) cost = c->crash_vehicle_cost;
-    is_done = (flags & PGD_F_ARRIVE_DEST) || out_of_road || crash_vehicle;
+    else if (crash_object) cost = c->crash_object_cost;
+    is_done = (flags & PGD_F_ARRIVE_DEST) || out_of_road || crash_vehicle || crash_object;
+    /* SafePGDriveEnv.done_function (safe_pgdrive_env.py:44-51), literally: a step with a crash never ends the episode */
+    if (c->safe_rl_env && (crash_vehicle || crash_object)) is_done = 0;
     float ddx = last_x - ego->x, ddy = last_y - ego->y; /* base_vehicle.py:278-290 */
     step_energy = 3.25f * pgd_expf(0.01f * sp) * (sqrtf(ddx * ddx + ddy * ddy) / 1000.0f) / 100.0f * 1000.0f;
     e->energy += step_energy;
@@ -829,15 +842,28 @@ void orc_step(void* h, int env, const float* action, float* obs, float* reward, 
   int overspeed[PGD_MAX_SLOTS];
   for (int i = 0; i < e->n_slots; ++i) overspeed[i] = speed_kmh(&e->v[i]) > MAX_SPEED_KMH;
   /* 5 x doPhysics(0.02) (base_engine.py:206-232); chassis contacts are sticky within the step */
-  int crash = 0;
+  int crash = 0; /* bit 0: a vehicle chassis, bit 1: a traffic object (collision_callback.py:13-30) */
+  int touched[PGD_MAX_SLOTS] = {0};
   for (int k = 0; k < c->decision_repeat; ++k) {
     for (int i = 0; i < e->n_slots; ++i)
-      if (e->v[i].alive) physics_substep(&e->v[i], c->dt, overspeed[i]);
+      if (e->v[i].alive && e->v[i].s->group != PGD_GROUP_STATIC) physics_substep(&e->v[i], c->dt, overspeed[i]);
+      else if (e->v[i].alive && e->v[i].airborne > 0) e->v[i].airborne--; /* a broken-down vehicle still drops */
     Rect er = veh_rect(ego);
     for (int i = 1; i < e->n_slots; ++i) {
       if (!e->v[i].alive) continue;
       Rect r = veh_rect(&e->v[i]);
-      if (rect_overlap(&er, &r)) crash = 1;
+      if (rect_overlap(&er, &r)) touched[i] = 1;
+    }
+  }
+  for (int i = 1; i < e->n_slots; ++i) {
+    if (!touched[i]) continue;
+    if (e->v[i].s->type >= PGD_TYPE_OBJECT) {
+      if (!e->v[i].crashed) { /* COST_ONCE */
+        crash |= 2;
+        e->v[i].crashed = 1;
+      }
+    } else {
+      crash |= 1;
     }
   }
   post_step(o, e, last_x, last_y, last_h, crash, 0, obs, reward, done, info);
@@ -870,7 +896,8 @@ void orc_get_state(void* h, int env, PgdEnvState* out) {
     s->target_speed = v->target_speed;
     s->lane = v->lane; s->ck0 = v->ck0; s->ck1 = v->ck1; s->rt_lane = v->rt_lane;
     s->timer = v->timer; s->rnd_n = v->rnd_n; s->airborne = v->airborne; s->yaw_rate = v->w;
-    s->flags = (v->alive ? PGD_V_ALIVE : 0) | (v->active ? PGD_V_ACTIVE : 0) | (v->on_lane ? PGD_V_ON_LANE : 0);
+    s->flags = (v->alive ? PGD_V_ALIVE : 0) | (v->active ? PGD_V_ACTIVE : 0) | (v->on_lane ? PGD_V_ON_LANE : 0) |
+               (v->crashed ? PGD_V_CRASHED : 0);
   }
 }
 
@@ -896,6 +923,7 @@ void orc_set_state(void* h, int env, const PgdEnvState* in) {
     v->timer = s->timer; v->rnd_n = s->rnd_n; v->airborne = s->airborne; v->w = s->yaw_rate;
     v->alive = !!(s->flags & PGD_V_ALIVE); v->active = !!(s->flags & PGD_V_ACTIVE);
     v->on_lane = !!(s->flags & PGD_V_ON_LANE);
+    v->crashed = !!(s->flags & PGD_V_CRASHED);
   }
 }
 

@@ -33,8 +33,8 @@ assert INFO_DT.itemsize == 40 and VEH_STATE_DT.itemsize == 80 and ENV_STATE_DT.i
 
 F_CRASH_VEHICLE, F_OUT_OF_ROAD, F_ARRIVE_DEST, F_MAX_STEP = 1, 2, 4, 8
 F_ON_YELLOW, F_ON_WHITE, F_ON_BROKEN, F_CRASH_SIDEWALK = 16, 32, 64, 128
-F_ON_LANE, F_OUT_OF_ROUTE, F_WAS_RESET = 256, 512, 1024
-V_ALIVE, V_ACTIVE, V_ON_LANE = 1, 2, 4
+F_ON_LANE, F_OUT_OF_ROUTE, F_WAS_RESET, F_CRASH_OBJECT = 256, 512, 1024, 2048
+V_ALIVE, V_ACTIVE, V_ON_LANE, V_CRASHED = 1, 2, 4, 16
 
 
 class PgdTables(C.Structure):
@@ -56,7 +56,8 @@ class PgdConfig(C.Structure):
         ("out_of_route_done", C.c_int32), ("auto_reset", C.c_int32), ("n_side", C.c_int32),
         ("n_lane_line", C.c_int32), ("side_distance", C.c_float), ("lane_line_distance", C.c_float),
         ("random_agent_model", C.c_int32), ("lidar_gaussian_noise", C.c_float), ("lidar_dropout_prob", C.c_float),
-        ("noise_seed", C.c_int32), ("increment_steering", C.c_int32)
+        ("noise_seed", C.c_int32), ("increment_steering", C.c_int32), ("crash_object_penalty", C.c_float),
+        ("crash_object_cost", C.c_float), ("safe_rl_env", C.c_int32)
     ]
 
 
@@ -65,7 +66,7 @@ def make_config(num_envs, num_slots=16, decision_repeat=5, horizon=0, dt=0.02, s
                 out_of_road_cost=1.0, crash_vehicle_cost=1.0, use_lateral=False, out_of_route_done=False,
                 auto_reset=True, n_side=0, side_distance=50.0, n_lane_line=0, lane_line_distance=20.0,
                 random_agent_model=False, lidar_gaussian_noise=0.0, lidar_dropout_prob=0.0, noise_seed=0,
-                increment_steering=False):
+                increment_steering=False, crash_object_penalty=5.0, crash_object_cost=1.0, safe_rl_env=False):
     if not (0 <= n_side <= MAX_DETECTOR_BEAMS and 0 <= n_lane_line <= MAX_DETECTOR_BEAMS):
         raise ValueError("side / lane-line detectors support 0..%d lasers" % MAX_DETECTOR_BEAMS)
     return PgdConfig(num_envs, num_slots, decision_repeat, int(horizon or 0), dt, success_reward, out_of_road_penalty,
@@ -73,7 +74,8 @@ def make_config(num_envs, num_slots=16, decision_repeat=5, horizon=0, dt=0.02, s
                      int(use_lateral), int(out_of_route_done), int(auto_reset), int(n_side), int(n_lane_line),
                      float(side_distance), float(lane_line_distance), int(bool(random_agent_model)),
                      float(lidar_gaussian_noise), float(lidar_dropout_prob), int(noise_seed),
-                     int(bool(increment_steering)))
+                     int(bool(increment_steering)), float(crash_object_penalty), float(crash_object_cost),
+                     int(bool(safe_rl_env)))
 
 
 def obs_dim(cfg):

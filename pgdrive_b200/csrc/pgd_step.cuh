@@ -1063,25 +1063,44 @@ PGS_HD void phase_d(Smem<V, R>& sm, Thr<V, R>& th, const Tables& T, const State&
     if (!((pmask >> s) & 1u)) continue;
     const size_t gi = (size_t)s * th.num_envs + th.env;
     const PgdSlot& t = th.tpl[s];
-    if (th.pre_air[k] > 0) {
-      const I4 m2 = {0, th.pre_air[k] > ns ? th.pre_air[k] - ns : 0, th.pre_fl[k], 0};  // parked: no IDM draw yet
-      S.misc[gi] = m2;
+    int air = th.pre_air[k], fl = th.pre_fl[k];
+    bool dirty = false;
+    if (air > 0) {
+      air = air > ns ? air - ns : 0;
+      dirty = true;
     }
     const float px = P.x[s][ln], py = P.y[s][ln];
     const float ddx0 = px - sm.last_x[ln], ddy0 = py - sm.last_y[ln];
     const float far = ehl + ehw + 8.0f + sm.ego_travel[ln];  // no chassis has an 8 m half-diagonal
-    if (ddx0 * ddx0 + ddy0 * ddy0 > far * far) continue;  // triangle inequality; the margin covers rounding
-    const float hl = t.length * 0.5f, hw = t.width * 0.5f;
-    const float reach = ehl + ehw + hl + hw;
+    if (!(ddx0 * ddx0 + ddy0 * ddy0 > far * far)) {  // else: triangle inequality; the margin covers rounding
+      const float hl = t.length * 0.5f, hw = t.width * 0.5f;
+      const float reach = ehl + ehw + hl + hw;
+      bool hit = false;
 #pragma unroll 1
-    for (int kk = 0; kk < ns; ++kk) {
-      const F4 e = traj[kk][ln];
-      const float ddx = px - e.x, ddy = py - e.y;
-      if (ddx * ddx + ddy * ddy <= reach * reach) {
-        const Rect me = {px, py, P.hc[s][ln], P.hs[s][ln], hl, hw};
-        const Rect eg = {e.x, e.y, e.z, e.w, ehl, ehw};
-        if (rect_overlap(eg, me)) crash = 1;
+      for (int kk = 0; kk < ns; ++kk) {
+        const F4 e = traj[kk][ln];
+        const float ddx = px - e.x, ddy = py - e.y;
+        if (ddx * ddx + ddy * ddy <= reach * reach) {
+          const Rect me = {px, py, P.hc[s][ln], P.hs[s][ln], hl, hw};
+          const Rect eg = {e.x, e.y, e.z, e.w, ehl, ehw};
+          if (rect_overlap(eg, me)) hit = true;
+        }
       }
+      if (hit) {  // collision_callback.py:13-30
+        if (t.type >= PGD_TYPE_OBJECT) {
+          if (!(fl & PGD_V_CRASHED)) {  // COST_ONCE: an object is charged the first time it is touched
+            crash |= 2;
+            fl |= PGD_V_CRASHED;
+            dirty = true;
+          }
+        } else {
+          crash |= 1;
+        }
+      }
+    }
+    if (dirty) {
+      const I4 m2 = {0, air, fl, 0};  // parked: no IDM draw yet
+      S.misc[gi] = m2;
     }
   }
   smem_or(&sm.crash[ln], crash);
@@ -1160,7 +1179,7 @@ PGS_HD void task_reward(Smem<V, R>& sm, Thr<V, R>& th, const Tables& T, const St
     obs[n_first + 6 + cfg.n_lane_line] = clipf(t0.length / 10.0f, 0.0f, 1.0f);
     obs[n_first + 6 + cfg.n_lane_line + 1] = clipf(t0.width / 2.5f, 0.0f, 1.0f);
   }
-  const int crash = sm.crash[ln];
+  const int crash = sm.crash[ln] & 1, crash_object = (sm.crash[ln] >> 1) & 1;
   const float last_x = sm.last_x[ln], last_y = sm.last_y[ln];
   const int cur_road_id = ldg(&rroads[ego.ck0]);
   const PgdRoad cur_road = load_rec(th.roads + cur_road_id);
@@ -1181,6 +1200,7 @@ PGS_HD void task_reward(Smem<V, R>& sm, Thr<V, R>& th, const Tables& T, const St
   }
   if (on_lane) flags |= PGD_F_ON_LANE;
   if (crash) flags |= PGD_F_CRASH_VEHICLE;
+  if (crash_object) flags |= PGD_F_CRASH_OBJECT;
   const float to_left = qlat0 + mp.lane_width / 2.0f;  // base_vehicle.py:383-388
   const float to_right = mp.lane_width * (float)n_ref - to_left;
   if (to_left < 0.0f || to_right < 0.0f) flags |= PGD_F_OUT_OF_ROUTE;
@@ -1218,9 +1238,13 @@ PGS_HD void task_reward(Smem<V, R>& sm, Thr<V, R>& th, const Tables& T, const St
     if (flags & PGD_F_ARRIVE_DEST) r = cfg.success_reward;
     else if (out_of_road) r = -cfg.out_of_road_penalty;
     else if (crash) r = -cfg.crash_vehicle_penalty;
+    else if (crash_object) r = -cfg.crash_object_penalty;
     if (out_of_road) cost = cfg.out_of_road_cost;
     else if (crash) cost = cfg.crash_vehicle_cost;
-    is_done = ((flags & PGD_F_ARRIVE_DEST) || out_of_road || crash) ? 1 : 0;
+    else if (crash_object) cost = cfg.crash_object_cost;
+    is_done = ((flags & PGD_F_ARRIVE_DEST) || out_of_road || crash || crash_object) ? 1 : 0;
+    // SafePGDriveEnv.done_function (safe_pgdrive_env.py:44-51), literally: a step with a crash never ends the episode
+    if (cfg.safe_rl_env && (crash || crash_object)) is_done = 0;
     const float ddx = last_x - ego.x, ddy = last_y - ego.y;  // base_vehicle.py:278-290
     step_energy = 3.25f * pgd_expf(0.01f * sp) * (sqrtf(ddx * ddx + ddy * ddy) / 1000.0f) / 100.0f * 1000.0f;
     th.envf.w += step_energy;
@@ -1316,7 +1340,8 @@ PGS_HD void task_neighbours(const Smem<V, R>& sm, const Thr<V, R>& th, const Pgd
   for (int s = 1; s < th.n_slots; ++s) {
     if (!(P.lf[s][ln] & PGD_V_ALIVE)) continue;
     const float dx = P.x[s][ln] - ex, dy = P.y[s][ln] - ey;
-    if (dx * dx + dy * dy < PGS_LIDAR_RANGE * PGS_LIDAR_RANGE) cand |= 1u << s;
+    if (dx * dx + dy * dy < PGS_LIDAR_RANGE * PGS_LIDAR_RANGE && ldg(&th.tpl[s].type) < PGD_TYPE_OBJECT)
+      cand |= 1u << s;  // get_surrounding_vehicles (lidar.py:46-54): cones and barriers are not vehicles
   }
 #pragma unroll 1
   for (int rank = 0; rank < 4; ++rank) {

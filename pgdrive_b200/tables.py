@@ -18,7 +18,7 @@ import math
 import numpy as np
 
 from . import rng
-from .episode import VEHICLE_BODY, make_episode
+from .episode import OBJECT_BODY, VEHICLE_BODY, make_episode
 from .roadnet import BROKEN, CONTINUOUS, DECO, NONE, SIDE, YELLOW, is_negative, norm2
 
 LANE_DT = np.dtype([
@@ -51,7 +51,7 @@ assert LANE_DT.itemsize == 64 and ROAD_DT.itemsize == 32 and BOX_DT.itemsize == 
 assert MAP_DT.itemsize == 64 and SLOT_DT.itemsize == 96 and EPISODE_DT.itemsize == 64
 
 BOX_LANE, BOX_WHITE, BOX_YELLOW, BOX_BROKEN, BOX_SIDEWALK = 0, 1, 2, 3, 4
-TYPE_ID = {"s": 0, "m": 1, "l": 2, "xl": 3, "default": 4}
+TYPE_ID = {"s": 0, "m": 1, "l": 2, "xl": 3, "default": 4, "TrafficCone": 5, "TrafficWarning": 6, "TrafficBarrier": 7}
 MAX_GROUPS = 11
 N_RND25 = 16
 
@@ -65,6 +65,7 @@ SIDEWALK_GAP = 0.6
 CELL = 4.0  # bucket size [m] (PGD_GRID_CELL, include/pgd_tables.h)
 GRID_MARGIN = 3.2  # PGD_GRID_MARGIN: >= half diagonal of the largest chassis (5.8 x 2.3 -> 3.12 m)
 ENTRY_NOT_LANE = 1 << 30  # PGD_ENTRY_NOT_LANE (include/pgd_tables.h)
+GROUP_STATIC = -3  # PGD_GROUP_STATIC: objects and broken-down vehicles of accident scenes
 GROUP_AWAKE = -2  # PGD_GROUP_AWAKE: PgdSlot.group of a vehicle that drives from the first step (traffic_mode respawn)
 
 GRAVITY = 9.81
@@ -279,6 +280,24 @@ class TableSet:
                            mi.lane_of[tuple(lane_index)], TYPE_ID[vtype], group, drop_substeps(vtype), timer, off, n, 0,
                            rnd))
 
+    def _static(self, pgmap, mi, obj):
+        """A cone / tripod / barrier or broken-down vehicle (episode.StaticObject) as a slot that never wakes."""
+        ln = pgmap.net.lanes((obj.lane[0], obj.lane[1]))[obj.lane[2]]
+        x, y = ln.position(obj.long, obj.lat)
+        heading = (ln.heading_at(obj.long) + math.pi) % (2 * math.pi) - math.pi
+        if obj.kind == "vehicle":
+            length, width, height, mass, lf, lr, tyre, track = VEHICLE_BODY[obj.type]
+            p, tid, drop = obj.params, TYPE_ID[obj.type], drop_substeps(obj.type)
+            eng, brk, steer, fric = p["max_engine_force"], p["max_brake_force"], math.radians(p["max_steering"]), \
+                p["wheel_friction"]
+        else:
+            length, width, mass = OBJECT_BODY[obj.kind]
+            lf = lr = length / 2
+            tid, drop, eng, brk, steer, fric = TYPE_ID[obj.kind], 0, 0.0, 0.0, 0.0, 0.9
+        self.slots.append((x, y, heading, length, width, mass, lf, lr, eng, brk, steer, fric,
+                           mi.lane_of[tuple(obj.lane)], tid, GROUP_STATIC, drop, 0, 0, 0, 0,
+                           np.zeros(N_RND25, dtype=np.uint8)))
+
     def add_episode(self, pgmap, map_id, ep, spawn_lane=(">", ">>", 0), spawn_long=5.0, spawn_lat=0.0):
         mi = self.index[map_id]
         slot_off = len(self.slots)
@@ -299,6 +318,8 @@ class TableSet:
             for v in vehicles:
                 self._slot(pgmap, mi, v.type, v.params, v.lane, v.long, 0.0, g, v.overtake_timer, v.idm_seed,
                            v.checkpoints)
+        for obj in getattr(ep, "objects", []):  # accident scenes last: traffic slots keep their numbers
+            self._static(pgmap, mi, obj)
         self.episodes.append((map_id, ep.seed, slot_off, len(self.slots) - slot_off, len(groups), trig))
         self.seeds.append(ep.seed)
         return len(self.episodes) - 1
