@@ -189,6 +189,13 @@ ENGINE_CONFIG = dict(
     num_slots=None,      # vehicle slots per env (16 / 24 / 32); None = smallest that fits the loaded seeds
     device=0,            # CUDA device ordinal
     auto_reset=True,     # VecPGDriveEnv only: a finished env restarts at its next step (action ignored)
+    # SafePGDriveEnv (envs/safe_pgdrive_env.py:7-63).  object_manager = its setup_engine registered the
+    # TrafficObjectManager: accident scenes are built with probability accident_prob per eligible block (without it
+    # accident_prob has no effect, exactly as in the reference's plain PGDriveEnv); safe_rl_env = a crash costs but does
+    # not end the episode; cost_to_reward = the costs are added to the penalties.
+    object_manager=False,
+    safe_rl_env=False,
+    cost_to_reward=False,
     noise_seed=0,        # key of the counter-based generator behind lidar gaussian_noise / dropout_prob
     device_mapgen=False,  # VecPGDriveEnv only: run the reset path (map search, tables, episode templates) on the GPU
 )
@@ -205,13 +212,17 @@ def default_config():
 UNSUPPORTED_IF_CHANGED = {
     "num_agents": 1, "is_multi_agent": False, "IDM_agent": False,
     "use_render": False, "manual_control": False, "use_topdown": False, "offscreen_render": False,
-    "random_traffic": False, "accident_prob": 0., "record_episode": False,
+    "random_traffic": False, "record_episode": False,
 }
 
 
 def post_process_config(cfg):
     """PGDriveEnv._post_process_config (envs/pgdrive_env.py:131-157): the top-level gaussian_noise / dropout_prob fan out
     to the three sensors' configs (asserting that those were left at 0)."""
+    if cfg.get("cost_to_reward", False):  # safe_pgdrive_env.py:36-42
+        cfg["crash_vehicle_penalty"] += cfg["crash_vehicle_cost"]
+        cfg["crash_object_penalty"] += cfg["crash_object_cost"]
+        cfg["out_of_road_penalty"] += cfg["out_of_road_cost"]
     vc = cfg["vehicle_config"]
     for key in ("gaussian_noise", "dropout_prob"):
         if cfg[key] > 0:

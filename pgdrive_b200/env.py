@@ -115,6 +115,7 @@ def _seed_tables(args):
     stored = args[4] if len(args) > 4 else None
     random_agent = bool(args[5]) if len(args) > 5 else False
     traffic_mode = args[6] if len(args) > 6 else "trigger"
+    accident_prob = float(args[7]) if len(args) > 7 else 0.0
     kw = dict(lane_num=mc["lane_num"], lane_width=mc["lane_width"], exit_length=mc["exit_length"])
     if stored is not None:  # restored from a map file: no block search (pg_map.py:48-71)
         pgmap = mapgen.build_from_sequence(seed, stored, **kw)
@@ -127,9 +128,8 @@ def _seed_tables(args):
     ts = tables.TableSet()
     mid = ts.add_map(pgmap)
     lane, lon, lat = spawn
-    ts.add_episode(pgmap, mid, episode.make_episode(pgmap, seed, density, tuple(lane), random_agent, traffic_mode), tuple(lane),
-                   lon,
-                   lat)
+    ts.add_episode(pgmap, mid, episode.make_episode(pgmap, seed, density, tuple(lane), random_agent, traffic_mode,
+                                                      accident_prob), tuple(lane), lon, lat)
     return ts.finish()
 
 
@@ -193,13 +193,13 @@ def dump_maps(seeds, map_config):
 
 
 def build_seed_tables(seeds, map_config, density, spawn, workers=None, stored=None, random_lane=(False, False),
-                      random_agent_model=False, traffic_mode="trigger"):
+                      random_agent_model=False, traffic_mode="trigger", accident_prob=0.0):
     """Tables for a list of seeds, built in worker processes when there are many, with an optional
     on-disk cache ($PGDRIVE_B200_CACHE) because map search costs ~50 ms per seed.  ``stored`` = {seed: block
     sequence} restored from a map file."""
     seeds = [int(s) for s in seeds]
     jobs = [(s, seed_map_config(map_config, s, *random_lane), density, spawn, (stored or {}).get(s),
-             bool(random_agent_model), traffic_mode) for s in seeds]
+             bool(random_agent_model), traffic_mode, float(accident_prob)) for s in seeds]
     cache_dir = os.environ.get("PGDRIVE_B200_CACHE")
     path = None
     if cache_dir:
@@ -225,6 +225,11 @@ def build_seed_tables(seeds, map_config, density, spawn, workers=None, stored=No
         with open(path, "wb") as f:
             pickle.dump(T, f)
     return T
+
+
+def accident_prob_of(cfg):
+    """Accident scenes exist only when the TrafficObjectManager is registered (SafePGDriveEnv.setup_engine)."""
+    return float(cfg["accident_prob"]) if cfg.get("object_manager", False) else 0.0
 
 
 def pick_slots(need):
@@ -258,7 +263,9 @@ class _Engine:
             lidar_gaussian_noise=cfg["vehicle_config"]["lidar"]["gaussian_noise"],
             lidar_dropout_prob=cfg["vehicle_config"]["lidar"]["dropout_prob"],
             noise_seed=int(cfg.get("noise_seed", 0) or 0) + 7919 * int(device),
-            increment_steering=bool(cfg["vehicle_config"]["increment_steering"])
+            increment_steering=bool(cfg["vehicle_config"]["increment_steering"]),
+            crash_object_penalty=cfg["crash_object_penalty"], crash_object_cost=cfg["crash_object_cost"],
+            safe_rl_env=bool(cfg.get("safe_rl_env", False))
         )
         self.obs_dim = cabi.obs_dim(self.pcfg)
         self.h = C.c_void_p()
@@ -308,6 +315,8 @@ class VecPGDriveEnv:
             raise NotImplementedError("device_mapgen spawns the default ego vehicle")
         if cfg["traffic_mode"] == "respawn" and cfg["device_mapgen"]:
             raise NotImplementedError("device_mapgen builds trigger-mode traffic")
+        if accident_prob_of(cfg) > 0 and cfg["device_mapgen"]:
+            raise NotImplementedError("device_mapgen builds no accident scenes")
         if cfg["device_mapgen"] and tables_dict is None and stored is None:
             # the whole reset path runs on the GPU (pgd_generate_tables); tables never visit the host
             gc = devgen.make_gen_config(self.map_config, cfg["traffic_density"], self._spawn, random_lane)
@@ -329,7 +338,8 @@ class VecPGDriveEnv:
         else:
             self._T = tables_dict if tables_dict is not None else build_seed_tables(
                 seeds, self.map_config, cfg["traffic_density"], self._spawn, stored=stored, random_lane=random_lane,
-                random_agent_model=cfg["random_agent_model"], traffic_mode=cfg["traffic_mode"]
+                random_agent_model=cfg["random_agent_model"], traffic_mode=cfg["traffic_mode"],
+                accident_prob=accident_prob_of(cfg)
             )
             self.episode_of_seed = {int(s): i for i, s in enumerate(self._T["episodes"]["seed"])}
             need = int(self._T["max_slots"])
@@ -588,7 +598,7 @@ class PGDriveEnv:
             mc = seed_map_config(self.map_config, seed, self.config["random_lane_width"], self.config["random_lane_num"])
             self._parts[seed] = _seed_tables((seed, mc, self.config["traffic_density"], self._spawn,
                                               (self._stored or {}).get(seed), bool(self.config["random_agent_model"]),
-                                              self.config["traffic_mode"]))
+                                              self.config["traffic_mode"], accident_prob_of(self.config)))
             self._episode_of_seed[seed] = 0
         part = self._parts[seed]
         slots = pick_slots(int(part["max_slots"]))
@@ -698,7 +708,8 @@ class PGDriveEnv:
         flags = int(rec["flags"])
         info = {k: bool(flags & bit) for k, bit in INFO_FLAGS.items()}
         info.update(
-            crash_object=False, crash_building=False, crash=bool(flags & cabi.F_CRASH_VEHICLE),
+            crash_object=bool(flags & cabi.F_CRASH_OBJECT), crash_building=False,
+            crash=bool(flags & (cabi.F_CRASH_VEHICLE | cabi.F_CRASH_OBJECT)),
             cost=float(rec["cost"]), velocity=float(rec["velocity"]), steering=float(rec["steering"]),
             acceleration=float(rec["acceleration"]), step_energy=float(rec["step_energy"]),
             episode_energy=float(rec["episode_energy"]), step_reward=float(rec["step_reward"]),
@@ -722,6 +733,33 @@ class PGDriveEnv:
         if self._engine is not None:
             self._engine.close()
             self._engine = None
+
+
+class SafePGDriveEnv(PGDriveEnv):
+    """envs/safe_pgdrive_env.py:7-63: accident scenes (cones, warning tripods, barriers, broken-down vehicles) on 80 % of
+    the eligible blocks, sparse traffic, and crashes that cost instead of ending the episode (``safe_rl_env``); ``info``
+    gains ``total_cost``."""
+    @classmethod
+    def default_config(cls):
+        config = default_config()
+        config.update(dict(environment_num=100, accident_prob=0.8, traffic_density=0.05, crash_vehicle_cost=1,
+                           crash_object_cost=1, out_of_road_cost=1., use_lateral=False))
+        config.update(dict(safe_rl_env=True, cost_to_reward=False, object_manager=True), allow_add_new_key=True)
+        return config
+
+    def __init__(self, config=None):
+        super(SafePGDriveEnv, self).__init__(config)
+        self.episode_cost = 0
+
+    def reset(self, *args, **kwargs):
+        self.episode_cost = 0
+        return super(SafePGDriveEnv, self).reset(*args, **kwargs)
+
+    def step(self, action):
+        obs, reward, done, info = super(SafePGDriveEnv, self).step(action)
+        self.episode_cost += info["cost"]
+        info["total_cost"] = self.episode_cost
+        return obs, reward, done, info
 
 
 def make(env_id, **overrides):

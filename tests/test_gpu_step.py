@@ -71,3 +71,63 @@ def test_step_full_size_throughput_smoke():
     print("role per warp: %.4f ms / step" % (e0.elapsed_time(e1) / 40))
     assert torch.equal(obs[:100], obs[100:200])
     env.close()
+
+
+def _free_run(env, ref, n, steps, act_fn):
+    import torch
+    from test_gpu_parity import FLAG_MASK
+    obs = env.reset().cpu().numpy().copy()
+    ro = ref.reset(range(n), [env.episode_of_seed[int(s)] for s in env.env_seeds]).copy()
+    assert np.array_equal(obs, ro)
+    seen = 0
+    for t in range(steps):
+        a = act_fn(t, ro).astype(np.float32)
+        o, r, d, _ = env.step(torch.from_numpy(a).cuda())
+        o, r, d = o.cpu().numpy(), r.cpu().numpy(), d.cpu().numpy()
+        info = env.info_numpy()
+        ro, rr, rd, rinfo = ref.step(a)
+        assert np.array_equal(d, rd) and np.array_equal(o, ro) and np.array_equal(r, rr), t
+        assert info.tobytes() == rinfo.tobytes(), t
+        seen |= int(np.bitwise_or.reduce(info["flags"]))
+        ro = ro.copy()
+    return seen
+
+
+def test_step_options_respawn_noise_increment_and_accident_scenes():
+    """The options added in round 2, on the GPU against the oracle bit for bit: traffic_mode="respawn" (all traffic awake
+    from step 0), lidar gaussian noise + dropout with increment_steering, SafePGDriveEnv's accident scenes with and
+    without safe_rl_env."""
+    from oracle.oracle import Oracle
+    from pgdrive_b200 import VecPGDriveEnv
+    rs = np.random.RandomState(5)
+
+    def hold_lane(t, obs):
+        a = np.zeros((obs.shape[0], 2))
+        a[:, 0] = np.clip((obs[:, 2] - 0.5) * 8.0 + rs.uniform(-0.02, 0.02, obs.shape[0]), -1, 1)
+        a[:, 1] = np.where(obs[:, 3] < 0.25, 0.5, 0.0)
+        return a
+
+    # respawn mode: seeds whose maps need at most 32 slots
+    n = 64
+    env = VecPGDriveEnv(dict(start_seed=1002, environment_num=3, num_envs=n, traffic_mode="respawn"))
+    ref = Oracle(env.T, n, auto_reset=True, num_slots=env.engine.num_slots)
+    _free_run(env, ref, n, 150, hold_lane)
+    env.close()
+    # lidar noise + dropout, incremental steering
+    env = VecPGDriveEnv(dict(start_seed=1000, environment_num=20, num_envs=n, noise_seed=5,
+                             vehicle_config=dict(increment_steering=True, lidar=dict(gaussian_noise=0.05, dropout_prob=0.1))))
+    ref = Oracle(env.T, n, auto_reset=True, num_slots=env.engine.num_slots, lidar_gaussian_noise=0.05,
+                 lidar_dropout_prob=0.1, noise_seed=5, increment_steering=True)
+    _free_run(env, ref, n, 150, lambda t, obs: np.c_[rs.uniform(-1, 1, n), rs.uniform(0, 1, n)])
+    assert float((env.obs[:, 34:] == 0).float().mean()) > 0.05
+    env.close()
+    # accident scenes
+    for safe in (False, True):
+        env = VecPGDriveEnv(dict(start_seed=100, environment_num=12, num_envs=n, traffic_density=0.05, accident_prob=0.8,
+                                 object_manager=True, safe_rl_env=safe,
+                                 vehicle_config=dict(spawn_lane_index=(">", ">>", 2))))
+        assert (env.T["slots"]["type"] >= 5).sum() > 40
+        ref = Oracle(env.T, n, auto_reset=True, num_slots=env.engine.num_slots, safe_rl_env=safe)
+        seen = _free_run(env, ref, n, 400, hold_lane)
+        assert seen & 2048, "no traffic object was touched"
+        env.close()

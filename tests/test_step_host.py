@@ -316,3 +316,43 @@ def test_lidar_noise_dropout_and_increment_steering():
     # the same call with another seed gives other noise; without noise the rows are the clean ones
     for x in (a, b, clean_a, clean_b):
         x.close()
+
+
+def test_accident_scenes_crash_object_and_safe_rl_env():
+    """SafePGDriveEnv's accident scenes as static slots (cones, tripods, barriers: PGD_TYPE_OBJECT; broken-down vehicles):
+    obstacles for IDM and the lidar, crash_object charged once per object, crash_vehicle for the broken-down vehicle,
+    and with safe_rl_env a crash costs but does not end the episode (safe_pgdrive_env.py:44-51)."""
+    from pgdrive_b200 import env as E
+    seeds = [100, 101, 104, 106, 110, 112, 0, 1000]
+    # half of the environments start on the right-most lane, where most coned-off lane ends and barriers are
+    T = E.merge_tables([E._seed_tables((s, V0, 0.05, ((">", ">>", 2 * (k % 2)), 5.0, 0.0), None, False, "trigger", 0.8))
+                        for k, s in enumerate(seeds + seeds)])
+    n_obj = int((T["slots"]["type"] >= 5).sum())
+    assert n_obj > 60 and (T["slots"]["group"] == -3).sum() >= n_obj and T["max_slots"] <= 32
+    n = 64
+    eps = [i % (2 * len(seeds)) for i in range(n)]
+    for safe in (False, True):
+        a, b = _pair(T, n, auto_reset=True, safe_rl_env=safe, crash_object_penalty=4.0, crash_object_cost=2.0)
+        assert np.array_equal(a.reset(range(n), eps), b.reset(range(n), eps))
+        rs = np.random.RandomState(17)
+        obs = a.obs.copy()
+        hits = done_on_hit = lidar_sees = 0
+        for t in range(500):
+            act = np.zeros((n, 2), np.float32)  # holds its lane (heading error only): drives into whatever blocks it
+            act[:, 0] = np.clip((obs[:, 2] - 0.5) * 8.0 + rs.uniform(-0.02, 0.02, n), -1, 1)
+            act[:, 1] = np.where(obs[:, 3] < 0.25, 0.5, 0.0)
+            ra, rb = a.step(act, threads=4), b.step(act)
+            assert _same(ra, rb), (safe, t)
+            obs = ra[0].copy()
+            fl = ra[3]["flags"]
+            hit = (fl & 2048) != 0
+            hits += int(hit.sum())
+            done_on_hit += int((ra[2][hit] != 0).sum())
+            if hit.any():
+                only = hit & ((fl & (2 | 1 | 4)) == 0)  # crash_object alone: its reward and cost
+                assert np.all(ra[1][only] == -4.0) and np.all(ra[3]["cost"][only] == 2.0)
+            lidar_sees += int((ra[0][:, 34:] < 1.0).any(axis=1).sum())
+        assert hits > 5 and lidar_sees > 100, (safe, hits, lidar_sees)
+        assert (done_on_hit == 0) if safe else (done_on_hit > 0), (safe, hits, done_on_hit)
+        a.close()
+        b.close()
