@@ -1050,3 +1050,37 @@ def cmd_random_agent(seeds, tag):
 
 if __name__ == "__main__" and sys.argv[1] == "random_agent":
     cmd_random_agent(list(range(1000, 1040)) + [0, 5, 77, 2500], "random_agent")
+
+
+def cmd_vehicle_types():
+    """The reference's vehicle-type table (component/vehicle/vehicle_type.py:7-86) and parameter spaces
+    (utils/space.py:219-255) as data, for tests/test_dynamics_pins.py."""
+    from pgdrive.component.vehicle.vehicle_type import vehicle_type
+    from pgdrive.component.vehicle.base_vehicle import BaseVehicle
+    from pgdrive.component.static_object.traffic_object import TrafficCone, TrafficWarning, TrafficBarrier
+    out = {}
+    for key, cls in vehicle_type.items():
+        from pgdrive.utils.space import VehicleParameterSpace
+        raw = dict(default=VehicleParameterSpace.DEFAULT_VEHICLE, s=VehicleParameterSpace.S_VEHICLE,
+                   m=VehicleParameterSpace.M_VEHICLE, l=VehicleParameterSpace.L_VEHICLE,
+                   xl=VehicleParameterSpace.XL_VEHICLE)[key]
+        space = {name: dict(type=type(sp).__name__, fields=[float(x) for x in sp]) for name, sp in raw.items()}
+        out[key] = dict(LENGTH=cls.LENGTH, WIDTH=cls.WIDTH, HEIGHT=cls.HEIGHT, MASS=cls.MASS, TIRE_RADIUS=cls.TIRE_RADIUS,
+                        FRONT_WHEELBASE=cls.FRONT_WHEELBASE, REAR_WHEELBASE=cls.REAR_WHEELBASE,
+                        LATERAL_TIRE_TO_CENTER=cls.LATERAL_TIRE_TO_CENTER,
+                        CHASSIS_TO_WHEEL_AXIS=getattr(cls, "CHASSIS_TO_WHEEL_AXIS", BaseVehicle.CHASSIS_TO_WHEEL_AXIS),
+                        space=space)
+    out["_base"] = dict(MAX_LENGTH=BaseVehicle.MAX_LENGTH, MAX_WIDTH=BaseVehicle.MAX_WIDTH,
+                        MAX_STEERING=BaseVehicle.MAX_STEERING, STEERING_INCREMENT=BaseVehicle.STEERING_INCREMENT)
+    out["_objects"] = dict(TrafficCone=dict(RADIUS=TrafficCone.RADIUS, MASS=TrafficCone.MASS),
+                           TrafficWarning=dict(RADIUS=TrafficWarning.RADIUS, MASS=TrafficWarning.MASS),
+                           TrafficBarrier=dict(LENGTH=TrafficBarrier.LENGTH, WIDTH=TrafficBarrier.WIDTH,
+                                               MASS=TrafficBarrier.MASS))
+    path = os.path.join(GOLD, "vehicle_types.json.gz")
+    with gzip.open(path, "wt") as f:
+        json.dump(out, f)
+    print("wrote", path, json.dumps(out["s"])[:300])
+
+
+if __name__ == "__main__" and sys.argv[1] == "vehicle_types":
+    cmd_vehicle_types()
