@@ -69,6 +69,12 @@ int pgd_set_state(PgdHandle* h, int32_t env, const PgdEnvState* in);
 int pgd_generate_tables(PgdHandle* h, const int32_t* seeds, int32_t n, const PgdGenConfig* gen, const PgdGenCaps* caps,
                         int32_t* status_out, int32_t* counts_out, void* stream);
 
+/* Replace map / episode `index` of tables made by pgd_generate_tables with a host-built table set of ONE seed (the
+ * reference's map cache filled from another source: manager/map_manager.py:134-155).  Used for the seeds on which the
+ * reference's own result hangs on the last bit of a libm call (pgdrive_b200/devgen_ties.json): those are built by the
+ * reference-pinned host path and patched in, so the device tables equal the host tables on every seed. */
+int pgd_patch_tables(PgdHandle* h, int32_t index, const PgdTables* tables, const PgdGenCaps* caps);
+
 /* Element counts of the handle's device tables, in the order of PgdTables (maps, lanes, roads, boxes, cell_start,
  * cell_entries, episodes, slots, route), and a device -> host copy of them into caller-owned buffers of those
  * sizes (component/map/base_map.py:103-118 save_map is the nearest reference interface; used by tests and to cache

@@ -143,9 +143,10 @@ def load_library():
     lib.pgd_peer_release.argtypes = [vp, vp, i32]
     lib.pgd_generate_tables.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp]
     lib.pgd_table_sizes.argtypes = [vp, vp]
+    lib.pgd_patch_tables.argtypes = [vp, i32, C.POINTER(PgdTables), vp]
     lib.pgd_download_tables.argtypes = [vp, C.POINTER(PgdTables)]
     for name in ("pgd_create", "pgd_destroy", "pgd_load_tables", "pgd_reset", "pgd_step", "pgd_step_host",
-                 "pgd_get_state", "pgd_set_state", "pgd_set_timing", "pgd_words_checksum", "pgd_peer_alloc", "pgd_peer_open",
+                 "pgd_get_state", "pgd_set_state", "pgd_set_timing", "pgd_words_checksum", "pgd_patch_tables", "pgd_peer_alloc", "pgd_peer_open",
                  "pgd_peer_release", "pgd_generate_tables", "pgd_table_sizes", "pgd_download_tables"):
         getattr(lib, name).restype = i32
     _LIB = lib

@@ -197,7 +197,10 @@ ENGINE_CONFIG = dict(
     safe_rl_env=False,
     cost_to_reward=False,
     noise_seed=0,        # key of the counter-based generator behind lidar gaussian_noise / dropout_prob
-    device_mapgen=False,  # VecPGDriveEnv only: run the reset path (map search, tables, episode templates) on the GPU
+    # VecPGDriveEnv: run the reset path (map search, tables, episode templates) on the GPU.  None (default) = whenever
+    # the device generator covers the configuration (default ego type, trigger / hybrid traffic, no accident scenes, no
+    # map file), else the host path; True = require it (raises otherwise); False = host path.
+    device_mapgen=None,
 )
 
 

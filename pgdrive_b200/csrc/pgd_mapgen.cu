@@ -176,6 +176,42 @@ extern "C" int pgd_generate_tables(PgdHandle* h, const int32_t* seeds, int32_t n
   return 0;
 }
 
+// Replace map / episode `index` of tables made by pgd_generate_tables (fixed stride per map: caps) with a host-built
+// single-seed table set (offsets from 0, as pgdrive_b200/tables.py makes them).
+extern "C" int pgd_patch_tables(PgdHandle* h, int32_t index, const PgdTables* t, const PgdGenCaps* caps) {
+  if (!h || !t || !caps) return fail(-1, "pgd_patch_tables: null argument");
+  if (!h->tables_loaded || index < 0 || index >= h->n_episodes) return fail(-1, "pgd_patch_tables: index out of range");
+  if (h->table_count[1] != (int64_t)h->n_episodes * caps->lanes || h->table_count[7] != (int64_t)h->n_episodes * PGD_MAX_SLOTS)
+    return fail(-1, "pgd_patch_tables: the handle's tables were not generated with these capacities");
+  if (t->n_maps != 1 || t->n_episodes != 1) return fail(-1, "pgd_patch_tables: expects exactly one map and one episode");
+  if (t->n_lanes > caps->lanes || t->n_roads > caps->roads || t->n_boxes > caps->boxes || t->n_cell_start > caps->cells ||
+      t->n_cell_entries > caps->entries || t->n_slots > PGD_MAX_SLOTS || t->n_route > caps->route)
+    return fail(-3, "pgd_patch_tables: the map does not fit the per-map capacities");
+  if (t->episodes[0].n_slots > h->cfg.num_slots) return fail(-3, "pgd_patch_tables: more vehicle slots than the handle has");
+  CU(cudaSetDevice(h->device));
+  CU(cudaDeviceSynchronize());
+  const size_t m = (size_t)index;
+  PgdMap mp = t->maps[0];
+  mp.lane_off = (int32_t)(m * caps->lanes); mp.road_off = (int32_t)(m * caps->roads); mp.box_off = (int32_t)(m * caps->boxes);
+  mp.cell_off = (int32_t)(m * caps->cells); mp.entry_off = (int32_t)(m * caps->entries);
+  PgdEpisode ep = t->episodes[0];
+  ep.map = index;
+  ep.slot_off = (int32_t)(m * PGD_MAX_SLOTS);
+  std::vector<PgdSlot> slots(t->slots, t->slots + t->n_slots);
+  for (auto& sl : slots) sl.route_off += (int32_t)(m * caps->route);
+  CU(cudaMemcpy((PgdMap*)h->table_mem[0] + m, &mp, sizeof(mp), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy((PgdLane*)h->table_mem[1] + mp.lane_off, t->lanes, (size_t)t->n_lanes * sizeof(PgdLane), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy((PgdRoad*)h->table_mem[2] + mp.road_off, t->roads, (size_t)t->n_roads * sizeof(PgdRoad), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy((PgdBox*)h->table_mem[3] + mp.box_off, t->boxes, (size_t)t->n_boxes * sizeof(PgdBox), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy((int32_t*)h->table_mem[4] + mp.cell_off, t->cell_start, (size_t)t->n_cell_start * 4, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy((int32_t*)h->table_mem[5] + mp.entry_off, t->cell_entries, (size_t)t->n_cell_entries * 4, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy((PgdEpisode*)h->table_mem[6] + m, &ep, sizeof(ep), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy((PgdSlot*)h->table_mem[7] + ep.slot_off, slots.data(), slots.size() * sizeof(PgdSlot), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy((int32_t*)h->table_mem[8] + m * caps->route, t->route_nodes, (size_t)t->n_route * 4, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy((int32_t*)h->table_mem[9] + m * caps->route, t->route_roads, (size_t)t->n_route * 4, cudaMemcpyHostToDevice));
+  return 0;
+}
+
 extern "C" int pgd_table_sizes(PgdHandle* h, int64_t sizes[9]) {
   if (!h || !sizes) return fail(-1, "pgd_table_sizes: null argument");
   if (!h->tables_loaded) return fail(-3, "pgd_table_sizes: no tables loaded");

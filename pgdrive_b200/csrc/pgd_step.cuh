@@ -118,10 +118,10 @@ __device__ __forceinline__ uint4 ldg16_keep(const void* p) {
 
 template <class T_>
 PGS_HD T_ ldg(const T_* p) {
-#ifdef __CUDA_ARCH__
+#if defined(__CUDA_ARCH__) && !defined(PGS_PLAIN_LOADS)
   return __ldg(p);
 #else
-  return *p;
+  return *p;  // PGS_PLAIN_LOADS (map-staging experiment): the pointer may lead into shared memory
 #endif
 }
 
@@ -134,7 +134,9 @@ PGS_HD T_ load_rec(const T_* p) {
   const uint4* src = reinterpret_cast<const uint4*>(p);
   uint4* dst = reinterpret_cast<uint4*>(&out);
 #pragma unroll
-#ifdef PGS_TABLE_EVICT_LAST
+#if defined(PGS_PLAIN_LOADS)
+  for (int i = 0; i < (int)(sizeof(T_) / 16); ++i) dst[i] = src[i];
+#elif defined(PGS_TABLE_EVICT_LAST)
   for (int i = 0; i < (int)(sizeof(T_) / 16); ++i) dst[i] = ldg16_keep(src + i);
 #else
   for (int i = 0; i < (int)(sizeof(T_) / 16); ++i) dst[i] = __ldg(src + i);
@@ -381,6 +383,7 @@ struct Thr {  // what a thread keeps across the phases
   const PgdBox* boxes;
   const PgdSlot* tpl;
   int n_slots, n_groups, trig;
+  const PgdLane* staged_lanes;  // map-staging experiment: the CTA's (single) map's lanes in shared memory, or null
   Veh ego;         // role 0
   uint32_t flags;  // role 0: PGD_F_* of the ego
   // loads that depend on nothing but the environment index, issued before the table look-ups they overlap with
@@ -459,6 +462,7 @@ PGS_HD void thread_init(Thr<V, R>& th, const Tables& T, const State& S, const Pg
   th.fresh = th.stepping = false;
   th.trig = -1;
   th.flags = 0;
+  th.staged_lanes = nullptr;
   if (!th.valid) return;
   th.envi = S.envi[env];
   // everything below that only needs the environment index is requested now, so that it is in flight while the
@@ -651,7 +655,7 @@ PGS_HD void item_context(const Smem<V, R>& sm, const Thr<V, R>& th, const Tables
   it.env = th.env - th.lane + e;
   it.num_envs = th.num_envs;
   it.mp = load_rec(T.maps + sm.ctx_map[e]);
-  it.lanes = T.lanes + it.mp.lane_off;
+  it.lanes = th.staged_lanes ? th.staged_lanes : T.lanes + it.mp.lane_off;
   it.roads = T.roads + it.mp.road_off;
   it.boxes = T.boxes + it.mp.box_off;
   it.tpl = T.slots + sm.ctx_slot_off[e];

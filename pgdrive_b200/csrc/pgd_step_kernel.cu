@@ -18,6 +18,7 @@ using namespace pgdstep;
 #ifndef PGS_OBS_EVICT_FIRST
 #define PGS_OBS_EVICT_FIRST 1
 #endif
+#define PGS_STAGE_MAX_LANES 210  // most lanes a 3-block map has
 
 #ifdef PGS_PHASE_CLOCKS  // diagnostic build: cycles between the CTA barriers, summed over CTAs (thread 0 of each)
 __device__ unsigned long long g_pgs_clk[16];
@@ -66,6 +67,43 @@ __global__ void __launch_bounds__(R * 32, PGS_MIN_CTAS) pgd_step_kernel(Tables T
   thread_init(th, T, S, cfg, mode, lane, role, env0 + lane, env_end);
   phase_0(sm, th);
   if (!__syncthreads_or(th.valid)) return;  // reset pass: no environment of this CTA is marked
+#ifdef PGS_STAGE_LANES
+  // EXPERIMENT (north_star: "lane / segment geometry TMA-staged into shared memory per block"): when the 32
+  // environments of the CTA play the same map, its lane table (<= 210 x 64 B) is brought into shared memory by one
+  // bulk (TMA) copy and every lane access of the step reads it there.  Measured against the same build without the
+  // staging in profiles/ (tools/kernel_variants.py: "plain" vs "stage", environments assigned to seeds in blocks of 32).
+  {
+    __shared__ __align__(8) unsigned long long stage_bar;
+    PgdLane* stage = reinterpret_cast<PgdLane*>(smem_raw + smem_bytes<V, R>(obs_dim, cfg.decision_repeat));
+    const int map0 = sm.ctx_map[0];
+    const bool same = __syncthreads_and(th.valid && sm.ctx_map[lane] == map0 && th.mp.n_lanes <= PGS_STAGE_MAX_LANES);
+    if (same) {
+      const uint32_t bytes = (uint32_t)th.mp.n_lanes * (uint32_t)sizeof(PgdLane);
+      const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&stage_bar);
+      if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         (uint32_t)__cvta_generic_to_shared(stage)),
+                     "l"(th.lanes), "r"(bytes), "r"(bar)
+                     : "memory");
+      }
+      uint32_t done = 0;
+      while (!done) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done)
+                     : "r"(bar)
+                     : "memory");
+      }
+      th.lanes = stage;
+      th.staged_lanes = stage;
+    }
+  }
+#endif
   PGS_CLK(0);
   phase_a(sm, th, S, cfg, actions);
   PGS_CLK(1);
@@ -136,7 +174,11 @@ template <int V, int R>
 static int launch_one(PgdHandle* h, const Tables& T, const State& S, int mode, int env_begin, int env_end,
                       const float* actions, float* obs, float* reward, uint8_t* done, PgdInfo* info, cudaStream_t st) {
   static int configured = 0;  // per instantiation: largest dynamic shared-memory size opted into so far
+#ifdef PGS_STAGE_LANES
+  const int smem = (int)smem_bytes<V, R>(obs_dim_of(h->cfg), h->cfg.decision_repeat) + PGS_STAGE_MAX_LANES * (int)sizeof(PgdLane);
+#else
   const int smem = (int)smem_bytes<V, R>(obs_dim_of(h->cfg), h->cfg.decision_repeat);
+#endif
   if (smem > configured) {
     CU(cudaFuncSetAttribute(pgd_step_kernel<V, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = smem;

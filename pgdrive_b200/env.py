@@ -311,31 +311,30 @@ class VecPGDriveEnv:
             stored = load_map_file(cfg["_load_map_from_json"], self.map_config, seeds)
         self._T = None
         random_lane = (bool(cfg["random_lane_width"]), bool(cfg["random_lane_num"]))
-        if cfg["random_agent_model"] and cfg["device_mapgen"]:
-            raise NotImplementedError("device_mapgen spawns the default ego vehicle")
-        if cfg["traffic_mode"] == "respawn" and cfg["device_mapgen"]:
-            raise NotImplementedError("device_mapgen builds trigger-mode traffic")
-        if accident_prob_of(cfg) > 0 and cfg["device_mapgen"]:
-            raise NotImplementedError("device_mapgen builds no accident scenes")
-        if cfg["device_mapgen"] and tables_dict is None and stored is None:
-            # the whole reset path runs on the GPU (pgd_generate_tables); tables never visit the host
-            gc = devgen.make_gen_config(self.map_config, cfg["traffic_density"], self._spawn, random_lane)
-            slots = cfg["num_slots"] or 16
-            while True:
-                self.engine = _Engine(cfg, self.num_envs, slots, int(cfg["device"]), bool(cfg["auto_reset"]),
-                                      effective_horizon(cfg, self.map_config))
-                try:
-                    devgen.generate(self.engine, seeds, gc)
-                    break
-                except RuntimeError:
-                    need = int(self.engine.gen_counts[:, 5].max())
-                    ok = (self.engine.gen_status == 0).all()
-                    self.engine.close()
-                    if not ok or cfg["num_slots"] or need <= slots or slots == 32:
-                        raise
-                    slots = 32  # some seed needs more than 16 vehicle slots
-            self.episode_of_seed = {int(s): i for i, s in enumerate(seeds)}
-        else:
+        why_not = None  # what the device generator (pgd_mapgen.cuh) does not cover
+        if cfg["random_agent_model"]:
+            why_not = "device_mapgen spawns the default ego vehicle"
+        elif cfg["traffic_mode"] == "respawn":
+            why_not = "device_mapgen builds trigger-mode traffic"
+        elif accident_prob_of(cfg) > 0:
+            why_not = "device_mapgen builds no accident scenes"
+        elif tuple(self._spawn[0][:2]) != (">", ">>"):
+            why_not = "device_mapgen spawns the ego on the first road"
+        elif tables_dict is not None or stored is not None:
+            why_not = "tables / a map file were given"
+        if cfg["device_mapgen"] and why_not and tables_dict is None and stored is None:
+            raise NotImplementedError(why_not)
+        use_device = (cfg["device_mapgen"] is None or cfg["device_mapgen"]) and why_not is None
+        self.reset_path = "host"
+        if use_device:
+            try:
+                self._build_on_device(cfg, seeds, random_lane)
+                self.reset_path = "device"
+            except (RuntimeError, ValueError):
+                if cfg["device_mapgen"]:  # required explicitly
+                    raise
+                # auto: a configuration outside the generator's table capacities (many lanes / blocks): host path
+        if self.reset_path == "host":
             self._T = tables_dict if tables_dict is not None else build_seed_tables(
                 seeds, self.map_config, cfg["traffic_density"], self._spawn, stored=stored, random_lane=random_lane,
                 random_agent_model=cfg["random_agent_model"], traffic_mode=cfg["traffic_mode"],
@@ -347,7 +346,7 @@ class VecPGDriveEnv:
             if need > slots:
                 raise ValueError("the loaded seeds need %d vehicle slots; num_slots=%d" % (need, slots))
             self.engine = _Engine(cfg, self.num_envs, slots, int(cfg["device"]), bool(cfg["auto_reset"]),
-                                      effective_horizon(cfg, self.map_config))
+                                  effective_horizon(cfg, self.map_config))
             self.engine.load(self._T)
         torch = self.engine.torch
         dev = self.engine.device
@@ -369,6 +368,33 @@ class VecPGDriveEnv:
         self.observation_space = Box(-0.0, 1.0, shape=(self.obs_dim, ), dtype=np.float32)
         self.action_space = make_action_space(cfg)
         self.env_seeds = np.array([self.start_seed + i % self.env_num for i in range(n)], dtype=np.int64)
+
+    def _build_on_device(self, cfg, seeds, random_lane):
+        """The whole reset path on the GPU (pgd_generate_tables: one warp per seed writes maps, collision primitives,
+        bucket grid, traffic slots and routes straight into the tables the step kernel reads; nothing visits the host).
+        The few seeds on which the reference's own result hangs on the last bit of a glibc call (devgen.tie_seeds) are
+        built by the reference-pinned host path and patched in, so device tables equal host tables on every seed."""
+        gc = devgen.make_gen_config(self.map_config, cfg["traffic_density"], self._spawn, random_lane)
+        slots = cfg["num_slots"] or 16
+        while True:
+            self.engine = _Engine(cfg, self.num_envs, slots, int(cfg["device"]), bool(cfg["auto_reset"]),
+                                  effective_horizon(cfg, self.map_config))
+            try:
+                devgen.generate(self.engine, seeds, gc)
+                break
+            except RuntimeError:
+                counts, status = getattr(self.engine, "gen_counts", None), getattr(self.engine, "gen_status", None)
+                self.engine.close()
+                need = int(counts[:, 5].max()) if counts is not None else 0
+                if status is None or not (status == 0).all() or cfg["num_slots"] or need <= slots or need > 32:
+                    raise
+                slots = pick_slots(need)  # some seed needs more vehicle slots than tried
+        ties = sorted(devgen.tie_seeds(self.map_config, cfg["traffic_density"], self._spawn, random_lane) & set(seeds))
+        for s in ties:
+            part = _seed_tables((s, seed_map_config(self.map_config, s, *random_lane), cfg["traffic_density"], self._spawn))
+            devgen.patch(self.engine, seeds.index(s), part, self.engine.gen_caps)
+        self.device_mapgen_patched = ties
+        self.episode_of_seed = {int(s): i for i, s in enumerate(seeds)}
 
     @property
     def T(self):

@@ -241,21 +241,21 @@ def test_device_tables_other_configs_and_1000_seeds():
 @pytest.mark.gpu
 def test_env_on_device_generated_maps_matches_env_on_host_tables():
     """Same seeds, same actions: an environment whose maps were generated on the GPU reproduces, bit for bit, the one
-    whose tables were built by the reference-pinned host path (1055, a libm tie seed, is left out), and the CPU
-    oracle agrees on the downloaded tables."""
+    whose tables were built by the reference-pinned host path -- including seed 1055, a libm tie seed, which the device
+    path takes from the host builder (devgen.tie_seeds) -- and the CPU oracle agrees on the downloaded tables."""
     import torch
     from oracle.oracle import Oracle
     from pgdrive_b200 import VecPGDriveEnv
     n, steps = 200, 150
-    common = dict(start_seed=1000, environment_num=50, num_envs=n, traffic_density=0.1)
-    dev = VecPGDriveEnv(dict(common, device_mapgen=True))
-    host = VecPGDriveEnv(dict(common))
+    common = dict(start_seed=1000, environment_num=100, num_envs=n, traffic_density=0.1)
+    dev = VecPGDriveEnv(dict(common))  # the default: maps and episode templates generated on the GPU
+    host = VecPGDriveEnv(dict(common, device_mapgen=False))
+    assert dev.reset_path == "device" and host.reset_path == "host" and dev.device_mapgen_patched == [1055]
     assert dev.engine.num_slots == host.engine.num_slots
     ref = Oracle(dev.T, n, auto_reset=True, num_slots=dev.engine.num_slots)
     o1, o2 = dev.reset().cpu().numpy(), host.reset().cpu().numpy()
     ro = ref.reset(range(n), [dev.episode_of_seed[int(s)] for s in dev.env_seeds])
-    assert np.array_equal(o1, o2)
-    assert np.abs(o1 - ro).max() < 1e-4
+    assert np.array_equal(o1, o2) and np.array_equal(o1, ro)
     rs = np.random.RandomState(1)
     for t in range(steps):
         a = rs.uniform(-1, 1, (n, 2)).astype(np.float32)
@@ -266,8 +266,7 @@ def test_env_on_device_generated_maps_matches_env_on_host_tables():
         for x, y in zip(r1, r2):
             assert np.array_equal(x, y), t
         oo, rr, dd, _ = ref.step(a)
-        assert np.array_equal(r1[2], dd), t
-        assert np.abs(r1[0][:, :34] - oo[:, :34]).max() < 1e-3, t
+        assert np.array_equal(r1[2], dd) and np.array_equal(r1[0], oo) and np.array_equal(r1[1], rr), t
     dev.close()
     host.close()
 

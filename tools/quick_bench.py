@@ -7,7 +7,10 @@ from pgdrive_b200 import VecPGDriveEnv
 n = int(os.environ.get("ENVS", 65536)); K = int(os.environ.get("STEPS", 200)); W = int(os.environ.get('WARM', 2048))  # steady state of the episode distribution (profiles/r02i_cost_curve_*.log)
 T = bench.build_tables()
 env = VecPGDriveEnv(dict(start_seed=1000, environment_num=100, num_envs=n, traffic_density=0.1, num_slots=16), tables_dict=T)
-env.reset()
+if os.environ.get("BLOCKED") == "1":  # one map per CTA of 32 environments (map-staging experiment)
+    env.reset(seeds=1000 + (np.arange(n) // 32) % 100)
+else:
+    env.reset()
 mode = os.environ.get("ACTIONS", "uniform")
 g = torch.Generator(device="cuda"); g.manual_seed(1)
 NA = 256
