@@ -122,7 +122,7 @@ def host_threads():
 def cpu_oracle_rate(T, n_envs, steps, warmup, threads, episode_ids, num_slots, seed=0):
     """env-steps/s of the CPU oracle on `threads` host threads (uniform [-1,1]^2 actions, auto-reset)."""
     from oracle.oracle import Oracle
-    ref = Oracle(T, n_envs, auto_reset=True, num_slots=num_slots)
+    ref = Oracle(T, n_envs, auto_reset=True, num_slots=num_slots, fast=True)  # bucket-grid queries: not a strawman
     ref.reset(range(n_envs), episode_ids)
     rs = np.random.RandomState(seed)
     acts = rs.uniform(-1, 1, (warmup + steps, n_envs, 2)).astype(np.float32)
@@ -539,7 +539,8 @@ def run_own(args):
         cn, cs = 32768, 128  # ~4.2M env-steps: 10-30 s of CPU work on a 16-thread host
         rate, dt = cpu_oracle_rate(T, cn, cs, 2, threads, [i % n_seeds for i in range(cn)], n_slots)
         cpu = dict(value=rate, unit="env-steps/s", cores=threads, kind="port",
-                   sample="%d of %d envs x %d steps (%.1f s), CPU oracle on %d host threads" % (cn, n, cs, dt, threads))
+                   sample="%d of %d envs x %d steps (%.1f s), CPU oracle (bucket-grid queries) on %d host threads" % (
+                       cn, n, cs, dt, threads))
 
     collective = {
         "none": "none",

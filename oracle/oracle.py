@@ -32,6 +32,7 @@ def lib():
         L.orc_create.argtypes = [C.POINTER(cabi.PgdTables), C.POINTER(cabi.PgdConfig)]
         L.orc_destroy.argtypes = [vp]
         L.orc_set_call_index.argtypes = [vp, C.c_uint32]
+        L.orc_set_fast.argtypes = [vp, i32]
         L.orc_reset.argtypes = [vp, i32, i32, vp, vp]
         L.orc_step.argtypes = [vp, i32, vp, vp, vp, vp, vp]
         L.orc_step_range.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp]
@@ -50,7 +51,9 @@ def lib():
 
 class Oracle:
     """N independent environments stepped one after the other on the CPU."""
-    def __init__(self, T, num_envs, **cfg):
+    def __init__(self, T, num_envs, fast=False, **cfg):
+        """``fast``: queries through the maps' bucket grids instead of over every primitive -- same results
+        (tests/test_oracle_golden.py); used when the oracle is timed as the CPU baseline."""
         self.L = lib()
         self.tables, self._keep = cabi.pack_tables(T)
         self.cfg = cabi.make_config(num_envs, **cfg)
@@ -58,6 +61,8 @@ class Oracle:
         self.h = self.L.orc_create(C.byref(self.tables), C.byref(self.cfg))
         if not self.h:
             raise ValueError("an episode needs more vehicle slots / trigger groups than the simulator has")
+        if fast:
+            self.L.orc_set_fast(self.h, 1)
         self.obs_dim = cabi.obs_dim(self.cfg)
         self.obs = np.zeros((num_envs, self.obs_dim), np.float32)
         self.reward = np.zeros(num_envs, np.float32)

@@ -61,6 +61,8 @@ typedef struct {
   PgdTables t;
   PgdConfig cfg;
   Env* envs;
+  int fast; /* orc_set_fast: queries go through the map's bucket grid instead of over every primitive (same results;
+               used when the oracle is TIMED as the CPU baseline, so that the baseline is not a strawman) */
   uint32_t call_index; /* API calls so far (set by the wrapper before each reset / step): lidar-noise key */
 } Oracle;
 
@@ -176,7 +178,24 @@ static void localize(const Oracle* o, const PgdMap* m, Veh* v) {
   int cur_road = route_road(o, v, v->ck0);
   int next_road = (v->ck0 == v->ck1) ? -1 : route_road(o, v, v->ck1);
   int first_any = -1, first_cur = -1, first_next = -1;
-  for (int b = 0; b < m->n_boxes; ++b) {
+  int n_cand = m->n_boxes, e0 = 0;
+  const int32_t* ent = NULL;
+  if (o->fast) { /* lane boxes of the bucket under the vehicle, ascending box id like the loop over all boxes */
+    n_cand = 0;
+    int cx = (int)floorf((v->x - m->x0) * m->inv_cell), cy = (int)floorf((v->y - m->y0) * m->inv_cell);
+    if (cx >= 0 && cy >= 0 && cx < m->nx && cy < m->ny) {
+      int cell = m->cell_off + cy * m->nx + cx;
+      e0 = o->t.cell_start[cell];
+      n_cand = o->t.cell_start[cell + 1] - e0;
+      ent = o->t.cell_entries + m->entry_off;
+    }
+  }
+  for (int k = 0; k < n_cand; ++k) {
+    int b = k;
+    if (ent) {
+      if (ent[e0 + k] >= PGD_ENTRY_NOT_LANE) break;
+      b = ent[e0 + k];
+    }
     const PgdBox* box = &o->t.boxes[m->box_off + b];
     if (box->kind != PGD_BOX_LANE || !rect_contains(box, v->x, v->y)) continue;
     const PgdLane* l = lane_at(o, m, box->lane);
@@ -560,7 +579,20 @@ static void post_step(Oracle* o, Env* e, float last_x, float last_y, float last_
   /* _state_check (base_vehicle.py:615-644): chassis rectangle against line ghosts and sidewalks */
   Rect er = veh_rect(ego);
   uint32_t flags = 0;
-  for (int b = 0; b < m->n_boxes; ++b) {
+  int n_cand = m->n_boxes, e0 = 0;
+  const int32_t* ent = NULL;
+  if (o->fast) { /* the bucket under the chassis centre lists every box the chassis can touch (PGD_GRID_MARGIN) */
+    n_cand = 0;
+    int cx = (int)floorf((ego->x - m->x0) * m->inv_cell), cy = (int)floorf((ego->y - m->y0) * m->inv_cell);
+    if (cx >= 0 && cy >= 0 && cx < m->nx && cy < m->ny) {
+      int cell = m->cell_off + cy * m->nx + cx;
+      e0 = o->t.cell_start[cell];
+      n_cand = o->t.cell_start[cell + 1] - e0;
+      ent = o->t.cell_entries + m->entry_off;
+    }
+  }
+  for (int k = 0; k < n_cand; ++k) {
+    int b = ent ? (ent[e0 + k] & PGD_ENTRY_ID_MASK) : k;
     const PgdBox* box = &o->t.boxes[m->box_off + b];
     if (box->kind == PGD_BOX_LANE) continue;
     Rect r = {box->cx, box->cy, box->ux, box->uy, box->hl, box->hw};
@@ -668,8 +700,16 @@ static void post_step(Oracle* o, Env* e, float last_x, float last_y, float last_
   {
     Rect rects[PGD_MAX_SLOTS];
     int n_rects = 0;
-    for (int j = 1; j < e->n_slots; ++j)
-      if (e->v[j].alive) rects[n_rects++] = veh_rect(&e->v[j]);
+    for (int j = 1; j < e->n_slots; ++j) {
+      if (!e->v[j].alive) continue;
+      if (o->fast) { /* a chassis further away than the range plus its half diagonal cannot be hit */
+        float dx = e->v[j].x - ego->x, dy = e->v[j].y - ego->y;
+        float hl = e->v[j].s->length * 0.5f, hw = e->v[j].s->width * 0.5f;
+        float reach = LIDAR_RANGE + sqrtf(hl * hl + hw * hw) * 1.001f + 1e-3f;
+        if (dx * dx + dy * dy > reach * reach) continue;
+      }
+      rects[n_rects++] = veh_rect(&e->v[j]);
+    }
     for (int i = 0; i < PGD_LIDAR_BEAMS; ++i) {
       float ang = (float)i * (TWO_PI_F / (float)PGD_LIDAR_BEAMS) + ego->h;
       float sn, cs;
@@ -760,6 +800,7 @@ void* orc_create(const PgdTables* t, const PgdConfig* cfg) {
 }
 
 void orc_set_call_index(void* h, uint32_t idx) { ((Oracle*)h)->call_index = idx; }
+void orc_set_fast(void* h, int on) { ((Oracle*)h)->fast = on; }
 
 void orc_destroy(void* h) {
   Oracle* o = (Oracle*)h;

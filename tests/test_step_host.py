@@ -356,3 +356,20 @@ def test_accident_scenes_crash_object_and_safe_rl_env():
         assert (done_on_hit == 0) if safe else (done_on_hit > 0), (safe, hits, done_on_hit)
         a.close()
         b.close()
+
+
+def test_oracle_fast_queries_equal_brute_force():
+    """The oracle's timed configuration (bucket-grid queries, bench.py's cpu_baseline / --impl reference) gives the same
+    bits as its brute-force loops over every primitive."""
+    from oracle.oracle import Oracle
+    T = _tables(range(1000, 1030))
+    n = 90
+    a, b = Oracle(T, n, auto_reset=True, num_slots=16), Oracle(T, n, auto_reset=True, num_slots=16, fast=True)
+    eps = [i % 30 for i in range(n)]
+    assert np.array_equal(a.reset(range(n), eps), b.reset(range(n), eps))
+    rs = np.random.RandomState(8)
+    for t in range(300):
+        act = _actions(rs, n, "forward" if t % 3 else "lane")
+        assert _same(a.step(act, threads=4), b.step(act, threads=4)), t
+    a.close()
+    b.close()
