@@ -3,13 +3,13 @@ import ctypes, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np
-from oracle import mapgen_host as mh, oracle as orc, step_host as v2
+from oracle import mapgen_host as mh, oracle as orc, step_host as sh
 SAN = os.path.join(ROOT, "oracle", "_san")
 mh.LIB = os.path.join(SAN, "libpgd_mapgen_host.so"); mh.build = lambda force=False: mh.LIB
 orc.LIB = os.path.join(SAN, "libpgd_oracle.so"); orc.build = lambda force=False: orc.LIB
-v2.LIB = os.path.join(SAN, "libpgd_step_host.so")
+sh.LIB = os.path.join(SAN, "libpgd_step_host.so")
 import subprocess
-v2.subprocess = type("S", (), {"check_call": staticmethod(lambda *a, **k: 0), "DEVNULL": None})
+sh.subprocess = type("S", (), {"check_call": staticmethod(lambda *a, **k: 0), "DEVNULL": None})
 from pgdrive_b200 import devgen, env as E
 V0 = dict(type="block_num", config=3, lane_num=3, lane_width=3.5, exit_length=50)
 SP = ((">", ">>", 0), 5.0, 0.0)
@@ -30,7 +30,7 @@ print("generator runs under sanitizers:", n)
 # step + oracle rollouts
 seeds = list(range(1000, 1030))
 T = E.merge_tables([E._seed_tables((s, V0, 0.1, SP)) for s in seeds])
-a = orc.Oracle(T, 90, auto_reset=True, num_slots=16); b = v2.HostStep(T, 90, auto_reset=True, num_slots=16)
+a = orc.Oracle(T, 90, auto_reset=True, num_slots=16); b = sh.HostStep(T, 90, auto_reset=True, num_slots=16)
 eps = [i % 30 for i in range(90)]
 a.reset(range(90), eps); b.reset(range(90), eps)
 rs = np.random.RandomState(0)
@@ -39,9 +39,9 @@ for t in range(250):
     r1 = a.step(act); r2 = b.step(act)
     assert np.array_equal(r1[0], r2[0])
 cfg = dict(auto_reset=True, n_side=12, side_distance=50.0, n_lane_line=8, lane_line_distance=20.0)
-a = orc.Oracle(T, 30, num_slots=16, **cfg); b = v2.HostStep(T, 30, num_slots=16, **cfg)
+a = orc.Oracle(T, 30, num_slots=16, **cfg); b = sh.HostStep(T, 30, num_slots=16, **cfg)
 a.reset(range(30), range(30)); b.reset(range(30), range(30))
 for t in range(100):
     act = rs.uniform(-1, 1, (30, 2)).astype(np.float32); act[:, 1] = np.abs(act[:, 1])
     assert np.array_equal(a.step(act)[0], b.step(act)[0])
-print("v2 / oracle rollouts under sanitizers: ok")
+print("step / oracle rollouts under sanitizers: ok")
