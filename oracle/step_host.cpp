@@ -15,6 +15,7 @@ struct HostStep {
   State S;
   PgdConfig cfg;
   int roles;
+  int envs_per_cta;  // lanes of every warp that carry an environment (the kernel launcher picks 2..32)
   uint32_t call_index;  // API calls so far (pgd_abi.cu keeps the same count): lidar-noise key
 };
 
@@ -29,25 +30,25 @@ static void run_vr(HostStep* h, int mode, const float* actions, float* obs, floa
   TrajPtr traj = reinterpret_cast<TrajPtr>(raw + smem_tv_offset<V, R>(od));
   VisPtr vis = reinterpret_cast<VisPtr>(raw + smem_tv_offset<V, R>(od));
   static Thr<V, R> th[R][PGS_LANES];
-  for (int env0 = 0; env0 < n; env0 += PGS_LANES) {
+  const int epc = h->envs_per_cta;
+  for (int env0 = 0; env0 < n; env0 += epc) {
     memset(raw, 0xff, bytes);  // shared memory starts as garbage on the device
     bool any = false;
+    const int cta_end = env0 + epc < n ? env0 + epc : n;
     for (int r = 0; r < R; ++r)
       for (int l = 0; l < PGS_LANES; ++l) {
-        thread_init(th[r][l], h->T, h->S, h->cfg, mode, l, r, env0 + l, n);
+        thread_init(th[r][l], h->T, h->S, h->cfg, mode, l, r, env0 + l, cta_end);
         any = any || th[r][l].valid;
       }
     if (!any) continue;
     for (int r = 0; r < R; ++r) for (int l = 0; l < PGS_LANES; ++l) phase_0(sm, th[r][l]);
 #define ALL(call) for (int r = 0; r < R; ++r) for (int l = 0; l < PGS_LANES; ++l) { Thr<V, R>& t = th[r][l]; (void)t; call; }
-    ALL(phase_a(sm, t, h->S, h->cfg, actions));
-    ALL(phase_b(sm, t, rows));
-    ALL(phase_c(sm, t, h->T, h->S, h->cfg, rows, traj));
-    ALL(phase_c_traffic(sm, t, h->T, h->S, rows));
-    for (int i = 0; i < PGS_LANES * od; ++i) rows[i] = 1.0f;
-    ALL(phase_d(sm, t, h->T, h->S, h->cfg, traj));
-    ALL(phase_d_traffic(sm, t, h->T, h->S, h->cfg, traj));
+    ALL(phase_a(sm, t, h->S, h->cfg, actions, rows));
+    ALL(phase_b(sm, t, h->T, rows));
+    ALL(phase_x(sm, t, h->T, h->S, h->cfg, rows, traj));  // role 0 (all its lanes) runs first: trajectories, lanes
+    memset(rows, 0xff, (size_t)PGS_LANES * od * 4);       // what is left of IDM's data is garbage to the observation
     ALL(phase_f(sm, t, h->T, h->S, h->cfg, mode, od, rows, vis, reward, done, info));
+    ALL(phase_l_fill(sm, r, l, od, rows));
     ALL(phase_l(sm, h->T, h->S, r, l, env0, od, rows, vis));
     ALL(phase_n(sm, h->cfg, h->call_index, r, l, env0, od, rows));
 #undef ALL
@@ -80,6 +81,7 @@ void* sth_create(const PgdTables* t, const PgdConfig* cfg, int roles) {
   HostStep* h = (HostStep*)calloc(1, sizeof(HostStep));
   h->cfg = *cfg;
   h->roles = roles;
+  h->envs_per_cta = PGS_LANES;
   h->T.maps = t->maps; h->T.lanes = t->lanes; h->T.roads = t->roads; h->T.boxes = t->boxes;
   h->T.cell_start = t->cell_start; h->T.cell_entries = t->cell_entries; h->T.episodes = t->episodes;
   h->T.slots = t->slots; h->T.route_nodes = t->route_nodes; h->T.route_roads = t->route_roads;
@@ -89,6 +91,8 @@ void* sth_create(const PgdTables* t, const PgdConfig* cfg, int roles) {
   h->S.envi = (I4*)calloc(n, 16); h->S.envf = (F4*)calloc(n, 16);
   return h;
 }
+
+void sth_set_envs_per_cta(void* p, int n) { ((HostStep*)p)->envs_per_cta = n >= 1 && n <= PGS_LANES ? n : PGS_LANES; }
 
 void sth_destroy(void* p) {
   HostStep* h = (HostStep*)p;

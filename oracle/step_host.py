@@ -23,6 +23,7 @@ def lib():
         L.sth_create.restype = vp
         L.sth_create.argtypes = [C.POINTER(cabi.PgdTables), C.POINTER(cabi.PgdConfig), C.c_int32]
         L.sth_destroy.argtypes = [vp]
+        L.sth_set_envs_per_cta.argtypes = [vp, C.c_int32]
         L.sth_reset.argtypes = [vp, vp, vp, C.c_int32, vp, vp]
         L.sth_step.argtypes = [vp, vp, vp, vp, vp, vp]
         L.sth_get_state.argtypes = [vp, C.c_int32, vp]
@@ -31,12 +32,13 @@ def lib():
 
 
 class HostStep:
-    def __init__(self, T, num_envs, roles=4, **cfg):
+    def __init__(self, T, num_envs, roles=4, envs_per_cta=32, **cfg):
         self.L = lib()
         self.tables, self._keep = cabi.pack_tables(T)
         self.cfg = cabi.make_config(num_envs, **cfg)
         self.n = num_envs
         self.h = self.L.sth_create(C.byref(self.tables), C.byref(self.cfg), int(roles))
+        self.L.sth_set_envs_per_cta(self.h, int(envs_per_cta))
         self.obs_dim = cabi.obs_dim(self.cfg)
         self.obs = np.zeros((num_envs, self.obs_dim), np.float32)
         self.reward = np.zeros(num_envs, np.float32)

@@ -44,10 +44,20 @@
 
 #ifdef __CUDACC__
 #define PGS_HD __host__ __device__ __forceinline__
+#ifdef PGS_OUTLINE_HELPERS  // experiment: sincos / arc projection as real calls (one copy each)
 #define PGS_HD_OUTLINE __host__ __device__ __noinline__
+#else
+#define PGS_HD_OUTLINE __host__ __device__ __forceinline__
+#endif
 #else
 #define PGS_HD inline
 #define PGS_HD_OUTLINE inline
+#endif
+
+#ifndef PGS_ITEM_CLK  // diagnostic build of the kernel only (pgd_step_kernel.cu, PGS_PHASE_CLOCKS)
+#define PGS_ITEM_CLK_BEGIN
+#define PGS_ITEM_CLK(i)
+#define PGS_ITEM_COUNT(i, n)
 #endif
 
 namespace pgdstep {
@@ -332,13 +342,17 @@ PGS_HD int lf_pack(int lane, int fl) { return (lane << 8) | (fl & 0xff); }
 PGS_HD int lf_lane(int lf) { return lf >> 8; }
 
 template <int V>
-struct IdmPub {  // IDM look-up data of every vehicle (phase B -> C); shares its storage with the observation rows
+struct IdmPub {  // what IDM reads of OTHER vehicles (phases A, B -> X); shares its storage with the observation rows
+  // coordinate of every vehicle on its own lane and that lane's ends / length (phase B)
   float olong[V][PGS_LANES], lsx[V][PGS_LANES], lsy[V][PGS_LANES], lex[V][PGS_LANES], ley[V][PGS_LANES],
       llen[V][PGS_LANES];
+  // start-of-step copy of the public state (phase A): phase X moves the vehicles in Smem::p while other vehicles'
+  // IDM still has to see where everybody was when the step began
+  Pub<V> start;
 };
 
-/* Dynamic shared memory: [Smem, fixed part][rows: 32 x obs_dim floats in HBM layout; phases B, C: IdmPub][tv: phases
- * C, D the ego's pose (x, y, cos, sin) after every sub-step, F4 [ns][32]; phases F, L the visible chassis, int [V][32]:
+/* Dynamic shared memory: [Smem, fixed part][rows: 32 x obs_dim floats in HBM layout; phases A .. X: IdmPub][tv: phase
+ * X the ego's pose (x, y, cos, sin) after every sub-step, F4 [ns][32]; phases F, L the visible chassis, int [V][32]:
  * slot | first beam << 8 | beam count << 16]. */
 typedef F4 (*TrajPtr)[PGS_LANES];
 typedef int (*VisPtr)[PGS_LANES];
@@ -346,14 +360,18 @@ template <int V, int R>
 struct Smem {
   Pub<V> p;
   F4 efin[PGS_LANES];                    // ego pose after the sub-steps (template pose when the episode restarts)
-  int scan[4][PGS_LANES];                // ego bucket scan, combined over the roles: b_any, b_cur, b_next (min), flags (or)
+  int ego_lane[PGS_LANES];               // the ego's lane after its localisation (phase X, role 0)
   int amask[PGS_LANES], pmask[PGS_LANES], crash[PGS_LANES];  // awake / parked traffic slots, chassis contact (or-ed in)
   float last_x[PGS_LANES], last_y[PGS_LANES], ego_travel[PGS_LANES], ego_h[PGS_LANES], ego_v[PGS_LANES],
       ego_hl[PGS_LANES], ego_hw[PGS_LANES];
   int ego_ck[PGS_LANES], n_vis[PGS_LANES], wrote[PGS_LANES];
-  int ctx_map[PGS_LANES], ctx_slot_off[PGS_LANES];  // map id / first template slot of each environment (for work items)
+  // table context of each environment (role 0 writes it before phase A): after phase A nobody keeps map offsets or
+  // table pointers in registers, they are read here where they are needed
+  float cx_x0[PGS_LANES], cx_y0[PGS_LANES], cx_inv_cell[PGS_LANES], cx_lane_width[PGS_LANES];
+  int cx_nx[PGS_LANES], cx_ny[PGS_LANES], cx_cell_off[PGS_LANES], cx_entry_off[PGS_LANES];
+  int cx_lane_off[PGS_LANES], cx_road_off[PGS_LANES], cx_box_off[PGS_LANES], cx_slot_off[PGS_LANES], cx_n_slots[PGS_LANES];
   int n_work;
-  int work[(V - 1) * PGS_LANES];         // awake traffic of the whole CTA: lane | slot << 8, dealt to all traffic threads
+  uint16_t work[(V - 1) * PGS_LANES];    // awake traffic of the whole CTA: lane | slot << 8, by environment then slot
 };
 
 template <int V, int R>
@@ -383,9 +401,12 @@ struct Thr {  // what a thread keeps across the phases
   const PgdBox* boxes;
   const PgdSlot* tpl;
   int n_slots, n_groups, trig;
-  const PgdLane* staged_lanes;  // map-staging experiment: the CTA's (single) map's lanes in shared memory, or null
   Veh ego;         // role 0
   uint32_t flags;  // role 0: PGD_F_* of the ego
+  // computed during phase X by warps that would otherwise wait, written to the observation row in phase F (the rows'
+  // storage holds IDM's data until phase X ends): role 0 -- keep[0..3] = lateral distances (obs 0, 1), driving reward,
+  // route sign; role R-1 -- keep[0..9] navigation info, keep[10] heading difference
+  float keep[11];
   // loads that depend on nothing but the environment index, issued before the table look-ups they overlap with
   F4 pre_pose, pre_ctrl, pre_pidl;  // role 0: the ego's record
   I4 pre_nav, pre_misc;             // role 0 (all roles: pre_nav.x = the ego's lane, for the trigger test)
@@ -462,7 +483,6 @@ PGS_HD void thread_init(Thr<V, R>& th, const Tables& T, const State& S, const Pg
   th.fresh = th.stepping = false;
   th.trig = -1;
   th.flags = 0;
-  th.staged_lanes = nullptr;
   if (!th.valid) return;
   th.envi = S.envi[env];
   // everything below that only needs the environment index is requested now, so that it is in flight while the
@@ -510,21 +530,35 @@ PGS_HD void phase_0(Smem<V, R>& sm, const Thr<V, R>& th) {
   const int ln = th.lane;
   sm.wrote[ln] = th.valid ? 1 : 0;
   sm.amask[ln] = sm.pmask[ln] = sm.crash[ln] = 0;
-  sm.scan[0][ln] = sm.scan[1][ln] = sm.scan[2][ln] = INT_MAX;
-  sm.scan[3][ln] = 0;
   sm.n_vis[ln] = 0;
   if (th.valid) {
-    sm.ctx_map[ln] = ldg(&th.ep->map);
-    sm.ctx_slot_off[ln] = ldg(&th.ep->slot_off);
+    const PgdMap& mp = th.mp;
+    sm.cx_x0[ln] = mp.x0; sm.cx_y0[ln] = mp.y0; sm.cx_inv_cell[ln] = mp.inv_cell; sm.cx_lane_width[ln] = mp.lane_width;
+    sm.cx_nx[ln] = mp.nx; sm.cx_ny[ln] = mp.ny; sm.cx_cell_off[ln] = mp.cell_off; sm.cx_entry_off[ln] = mp.entry_off;
+    sm.cx_lane_off[ln] = mp.lane_off; sm.cx_road_off[ln] = mp.road_off; sm.cx_box_off[ln] = mp.box_off;
+    sm.cx_slot_off[ln] = ldg(&th.ep->slot_off);
+    sm.cx_n_slots[ln] = th.n_slots;
   }
 }
 
+/* Table context of environment e of the CTA (any thread may work on any environment after phase A). */
+template <int V, int R>
+PGS_HD const PgdLane* lanes_of(const Smem<V, R>& sm, const Tables& T, int e) { return T.lanes + sm.cx_lane_off[e]; }
+template <int V, int R>
+PGS_HD const PgdRoad* roads_of(const Smem<V, R>& sm, const Tables& T, int e) { return T.roads + sm.cx_road_off[e]; }
+template <int V, int R>
+PGS_HD const PgdBox* boxes_of(const Smem<V, R>& sm, const Tables& T, int e) { return T.boxes + sm.cx_box_off[e]; }
+template <int V, int R>
+PGS_HD const PgdSlot* slots_of(const Smem<V, R>& sm, const Tables& T, int e) { return T.slots + sm.cx_slot_off[e]; }
+
 // ---- phase A: publish start-of-step state; ego action; traffic trigger ------------------------------------------
 template <int V, int R>
-PGS_HD void phase_a(Smem<V, R>& sm, Thr<V, R>& th, const State& S, const PgdConfig& cfg, const float* actions) {
+PGS_HD void phase_a(Smem<V, R>& sm, Thr<V, R>& th, const State& S, const PgdConfig& cfg, const float* actions,
+                   float* obs) {
   const int ln = th.lane;
   if (!th.valid) return;
   Pub<V>& P = sm.p;
+  Pub<V>& P0 = idm_of<V, R>(obs).start;  // what IDM reads while phase X moves the vehicles in P
   // TrafficManager.before_step (traffic_manager.py:71-89): the next group wakes when the ego is on its trigger road.
   // Every role evaluates the (cheap) test itself instead of waiting for role 0.
   if (th.stepping && th.envi.y < th.n_groups) {
@@ -543,6 +577,8 @@ PGS_HD void phase_a(Smem<V, R>& sm, Thr<V, R>& th, const State& S, const PgdConf
     sm.ego_ck[ln] = q.ck0 | (q.ck1 << 16);
     P.x[0][ln] = q.x; P.y[0][ln] = q.y; P.hc[0][ln] = q.hc; P.hs[0][ln] = q.hs; P.v[0][ln] = q.v;
     P.lf[0][ln] = lf_pack(q.lane, q.vflags);
+    P0.x[0][ln] = q.x; P0.y[0][ln] = q.y; P0.hc[0][ln] = q.hc; P0.hs[0][ln] = q.hs; P0.v[0][ln] = q.v;
+    P0.lf[0][ln] = lf_pack(q.lane, q.vflags);
     if (th.stepping) {  // EnvInputPolicy.act (env_input_policy.py:17-26): clip; fminf / fmaxf turn NaN into -1
       const float a0 = clipf(actions[2 * (size_t)th.env], -1.0f, 1.0f);
       const float a1 = clipf(actions[2 * (size_t)th.env + 1], -1.0f, 1.0f);
@@ -585,6 +621,7 @@ PGS_HD void phase_a(Smem<V, R>& sm, Thr<V, R>& th, const State& S, const PgdConf
       fl = th.pre_fl[k];
       if (!(fl & PGD_V_ALIVE)) {
         P.lf[s][ln] = 0;
+        P0.lf[s][ln] = 0;
         continue;
       }
       if (fl & PGD_V_ACTIVE) {
@@ -608,6 +645,8 @@ PGS_HD void phase_a(Smem<V, R>& sm, Thr<V, R>& th, const State& S, const PgdConf
     PGS_SINCOS(h, sn, cs);
     P.x[s][ln] = x; P.y[s][ln] = y; P.hc[s][ln] = cs; P.hs[s][ln] = sn; P.v[s][ln] = v;
     P.lf[s][ln] = lf_pack(lane, fl);
+    P0.x[s][ln] = x; P0.y[s][ln] = y; P0.hc[s][ln] = cs; P0.hs[s][ln] = sn; P0.v[s][ln] = v;
+    P0.lf[s][ln] = lf_pack(lane, fl);
     // an episode that restarts in this call does not act: its awake traffic (traffic_mode "respawn") is no work item
     if ((fl & PGD_V_ACTIVE) && th.stepping) amask |= 1u << s;
     else pmask |= 1u << s;
@@ -637,33 +676,20 @@ PGS_HD void build_work_list(Smem<V, R>& sm, int lane) {
     if (lane >= d) incl += up;
   }
   int at = incl - c;
-  for (uint32_t mm = m; mm; mm &= mm - 1) sm.work[at++] = lane | (ctz32(mm) << 8);
+  for (uint32_t mm = m; mm; mm &= mm - 1) sm.work[at++] = (uint16_t)(lane | (ctz32(mm) << 8));
   if (lane == 31) sm.n_work = incl;
 #else
   if (lane != 0) return;  // the host build runs the "warp" as one loop
   int at = 0;
   for (int e = 0; e < PGS_LANES; ++e)
-    for (uint32_t mm = (uint32_t)sm.amask[e]; mm; mm &= mm - 1) sm.work[at++] = e | (ctz32(mm) << 8);
+    for (uint32_t mm = (uint32_t)sm.amask[e]; mm; mm &= mm - 1) sm.work[at++] = (uint16_t)(e | (ctz32(mm) << 8));
   sm.n_work = at;
 #endif
 }
 
-/* The context of ANOTHER environment of the CTA (a work item), from what role 0 published for it. */
-template <int V, int R>
-PGS_HD void item_context(const Smem<V, R>& sm, const Thr<V, R>& th, const Tables& T, int e, Thr<V, R>& it) {
-  it.lane = e;
-  it.env = th.env - th.lane + e;
-  it.num_envs = th.num_envs;
-  it.mp = load_rec(T.maps + sm.ctx_map[e]);
-  it.lanes = th.staged_lanes ? th.staged_lanes : T.lanes + it.mp.lane_off;
-  it.roads = T.roads + it.mp.road_off;
-  it.boxes = T.boxes + it.mp.box_off;
-  it.tpl = T.slots + sm.ctx_slot_off[e];
-}
-
 // ---- phase B: IDM look-up data (only environments with awake traffic) --------------------------------------------
 template <int V, int R>
-PGS_HD void phase_b(Smem<V, R>& sm, Thr<V, R>& th, float* obs) {
+PGS_HD void phase_b(Smem<V, R>& sm, Thr<V, R>& th, const Tables& T, float* obs) {
   if (th.role == 1) build_work_list(sm, th.lane);  // every lane of the warp takes part (invalid lanes count 0)
   if (!th.valid || !th.stepping) return;
   const int ln = th.lane;
@@ -675,7 +701,7 @@ PGS_HD void phase_b(Smem<V, R>& sm, Thr<V, R>& th, float* obs) {
 #pragma unroll 1
   for (uint32_t m = drop_low(alive, th.role); m; m = drop_low(m, R)) {
     const int s = ctz32(m);
-    const PgdLane l = load_rec(th.lanes + lf_lane(P.lf[s][ln]));
+    const PgdLane l = load_rec(lanes_of(sm, T, ln) + lf_lane(P.lf[s][ln]));
     I.lsx[s][ln] = l.sx; I.lsy[s][ln] = l.sy; I.lex[s][ln] = l.ex; I.ley[s][ln] = l.ey; I.llen[s][ln] = l.length;
     float lon, lat;
     lane_local(l, P.x[s][ln], P.y[s][ln], lon, lat);
@@ -685,16 +711,18 @@ PGS_HD void phase_b(Smem<V, R>& sm, Thr<V, R>& th, float* obs) {
 
 // ---- IDM / PID action of one awake traffic vehicle (idm_policy.py:190-353) --------------------------------------
 template <int V, int R>
-PGS_HD void idm_act(const Smem<V, R>& sm, const Thr<V, R>& th, const Tables& T, const float* obs, uint32_t alive,
-                   Veh& q, int s) {
-  const int ln = th.lane;
-  const Pub<V>& P = sm.p;
+PGS_HD void idm_act(const Smem<V, R>& sm, const Tables& T, const float* obs, int ln, uint32_t alive, Veh& q, int s,
+                   int& cur_road_out, int& next_road_out) {
   const IdmPub<V>& I = idm_of<V, R>(obs);
-  const PgdSlot& t = th.tpl[s];
-  const PgdLane* lanes = th.lanes;
-  const PgdRoad* roads = th.roads;
+  const Pub<V>& P = I.start;  // everybody's pose at the start of the step
+  const PgdSlot& t = slots_of(sm, T, ln)[s];
+  const PgdLane* lanes = lanes_of(sm, T, ln);
+  const PgdRoad* roads = roads_of(sm, T, ln);
   const int32_t* rroads = T.route_roads + t.route_off;
   const int cur_road_id = ldg(&rroads[q.ck0]);
+  const int next_road_id = q.ck0 != q.ck1 ? ldg(&rroads[q.ck1]) : -1;
+  cur_road_out = cur_road_id;
+  next_road_out = next_road_id;
   const PgdRoad cur_road = load_rec(roads + cur_road_id);
   bool ok;  // move_to_next_road (:222-242)
   if (q.rt_lane < 0) {
@@ -766,7 +794,7 @@ PGS_HD void idm_act(const Smem<V, R>& sm, const Thr<V, R>& th, const Tables& T, 
     bool decided = false;
     const int idx = rl.idx;
     if (q.ck0 != q.ck1) {
-      const PgdRoad nxt = load_rec(roads + ldg(&rroads[q.ck1]));
+      const PgdRoad nxt = load_rec(roads + next_road_id);
       const int diff = n_cur - nxt.n_lanes;
       if (diff > 0) {
         const PgdLane* c0 = lanes + cur_road.first_lane;
@@ -851,91 +879,32 @@ PGS_HD void idm_act(const Smem<V, R>& sm, const Thr<V, R>& th, const Tables& T, 
   }
 }
 
-// ---- phase C: ego sub-steps (role 0)  |  IDM of the awake traffic (traffic roles) ----------------------------------
-/* Awake vehicles are dealt to the traffic roles by their RANK among the environment's awake vehicles (role r takes
- * the (r-1)-th, (r-1+R-1)-th ... set bit of the mask), not by slot number: every traffic thread of an environment
- * gets the same share, so a warp's lanes run the same number of iterations. */
-template <int V, int R>
-PGS_HD void phase_c(Smem<V, R>& sm, Thr<V, R>& th, const Tables& T, const State& S, const PgdConfig& cfg,
-                   const float* obs, TrajPtr traj) {
-  if (!th.valid) return;
-  const int ln = th.lane;
-  const int ns = cfg.decision_repeat < PGS_MAX_SUBSTEPS ? cfg.decision_repeat : PGS_MAX_SUBSTEPS;
-  if (th.role == 0) {
-    Veh& q = th.ego;
-    if (th.stepping) {  // 5 x doPhysics(0.02) of the ego (base_engine.py:206-232), remembering every pose
-      // A vehicle at rest with no yaw rate and no engine force is a fixed point of the sub-step (speed = max(0 - dv, 0)
-      // = 0, the pose does not move); only its drop counter runs.
-      const bool parked = q.v == 0.0f && q.yaw == 0.0f && !(q.throttle > 0.0f);
-      Sub sub;
-      if (!parked) sub = make_sub(q, th.tpl[0], cfg.dt);
-      float m2 = 0.0f;
-#pragma unroll 1
-      for (int k = 0; k < ns; ++k) {
-        if (q.airborne > 0) q.airborne--;  // placed 1 m above the road: no wheel contact while it drops
-        else if (!parked) substep(q, sub, cfg.dt);
-        const F4 p = {q.x, q.y, q.hc, q.hs};
-        traj[k][ln] = p;
-        const float ex = q.x - sm.last_x[ln], ey = q.y - sm.last_y[ln];
-        m2 = fmaxf(m2, ex * ex + ey * ey);
-      }
-      sm.ego_travel[ln] = sqrtf(m2) * 1.001f + 1e-3f;  // how far the ego gets from its start pose within the step
-    }
-    const F4 fin = {q.x, q.y, q.hc, q.hs};
-    sm.efin[ln] = fin;
-    sm.ego_h[ln] = q.h;
-    sm.ego_v[ln] = q.v;
-    return;
-  }
-  (void)ns;
-}
-
-/* Traffic half of phase C: IDM / PID of the CTA's awake vehicles, dealt to all traffic threads (any thread may get a
- * vehicle of any of the 32 environments).  Runs for every traffic thread, also those whose own lane is idle. */
-template <int V, int R>
-PGS_HD void phase_c_traffic(Smem<V, R>& sm, const Thr<V, R>& th, const Tables& T, const State& S, const float* obs) {
-  if (th.role == 0) return;
-  const Pub<V>& P = sm.p;
-  const int n_work = sm.n_work;
-#pragma unroll 1
-  for (int i = (th.role - 1) * PGS_LANES + th.lane; i < n_work; i += (R - 1) * PGS_LANES) {
-    const int e = sm.work[i] & 0xff, s = sm.work[i] >> 8;
-    Thr<V, R> it;
-    item_context(sm, th, T, e, it);
-    const uint32_t alive = env_amask(sm, e) | env_pmask(sm, e) | 1u;
-    const size_t gi = (size_t)s * it.num_envs + it.env;
-    Veh q;
-    veh_load(q, S, gi);
-    q.vflags = P.lf[s][e] & 0xff;  // a vehicle woken in this step carries ACTIVE only in shared memory so far
-    q.hc = P.hc[s][e]; q.hs = P.hs[s][e];
-    idm_act(sm, it, T, obs, alive, q, s);
-    // hand-over to phase D through the vehicle's own state record (the same thread picks it up)
-    const F4 c = {q.steer, q.throttle, q.hp, q.hi}, l = {q.lp, q.li, q.tspeed, q.yaw};
-    const I4 n = {q.lane, q.ck0 | (q.ck1 << 16), q.rt_lane, q.timer}, mm = {q.rnd_n, q.airborne, q.vflags, 0};
-    S.ctrl[gi] = c; S.pidl[gi] = l; S.nav[gi] = n; S.misc[gi] = mm;
-  }
-}
-
 // ---- localisation through the bucket grid (navigation.py:155-344, scene_utils.py:138-185) ------------------------
 struct ScanOut { int b_any, b_cur, b_next; uint32_t flags; };
+struct GridRef { float x0, y0, inv_cell; int nx, ny, cell_off, entry_off; };  // bucket grid of one map
+template <int V, int R>
+PGS_HD GridRef grid_of(const Smem<V, R>& sm, int e) {
+  const GridRef g = {sm.cx_x0[e], sm.cx_y0[e], sm.cx_inv_cell[e], sm.cx_nx[e], sm.cx_ny[e], sm.cx_cell_off[e],
+                     sm.cx_entry_off[e]};
+  return g;
+}
 
-/* Entries [first, ...) of the bucket of (x, y), `stride` groups of 4 apart: lane-surface boxes that contain the point
- * and run along the heading; with EGO also the chassis against line ghosts and sidewalks (base_vehicle.py:615-644). */
+/* The bucket of (x, y): lane-surface boxes that contain the point and run along the heading; with EGO also the chassis
+ * against line ghosts and sidewalks (base_vehicle.py:615-644). */
 template <bool EGO>
-PGS_HD void bucket_scan(const PgdMap& mp, const PgdLane* lanes, const PgdBox* boxes, const Tables& T, float x, float y,
-                       float hc, float hs, float hl, float hw, int cur_road, int next_road, int first, int stride,
-                       ScanOut& out) {
+PGS_HD void bucket_scan(const GridRef& gr, const PgdLane* lanes, const PgdBox* boxes, const Tables& T, float x, float y,
+                       float hc, float hs, float hl, float hw, int cur_road, int next_road, ScanOut& out) {
   out.b_any = out.b_cur = out.b_next = INT_MAX;
   out.flags = 0;
-  const int32_t* ent = T.cell_entries + mp.entry_off;
+  const int32_t* ent = T.cell_entries + gr.entry_off;
   const Rect er = {x, y, hc, hs, hl, hw};
-  const int cx = (int)floorf((x - mp.x0) * mp.inv_cell), cy = (int)floorf((y - mp.y0) * mp.inv_cell);
-  if (!(cx >= 0 && cy >= 0 && cx < mp.nx && cy < mp.ny)) return;
-  const int cell = mp.cell_off + cy * mp.nx + cx;
+  const int cx = (int)floorf((x - gr.x0) * gr.inv_cell), cy = (int)floorf((y - gr.y0) * gr.inv_cell);
+  if (!(cx >= 0 && cy >= 0 && cx < gr.nx && cy < gr.ny)) return;
+  const int cell = gr.cell_off + cy * gr.nx + cx;
   const int b0 = ldg(&T.cell_start[cell]), b1 = ldg(&T.cell_start[cell + 1]);
   // entries are fetched four at a time (indices, then records) so that their latencies overlap; inside a cell the
   // lane-surface boxes come first, everything else carries PGD_ENTRY_NOT_LANE: traffic stops there
-  for (int k0 = b0 + 4 * first; k0 < b1; k0 += 4 * stride) {
+  for (int k0 = b0; k0 < b1; k0 += 4) {
     int bb[4];
     PgdBox gg[4];
 #pragma unroll
@@ -981,17 +950,17 @@ PGS_HD void bucket_scan(const PgdMap& mp, const PgdLane* lanes, const PgdBox* bo
 /* What follows the scan: lane choice (current road, then next road, then any; lowest box id), checkpoint update
  * (_update_target_checkpoints), on-lane flag. */
 template <int V, int R>
-PGS_HD void after_scan(const Thr<V, R>& th, const Tables& T, const PgdSlot& t, const ScanOut& sc, float x, float y,
-                      int& lane, int& ck0, int& ck1, bool& on_lane) {
+PGS_HD void after_scan(const Smem<V, R>& sm, const Tables& T, int e, const PgdSlot& t, const ScanOut& sc, float x,
+                      float y, int& lane, int& ck0, int& ck1, bool& on_lane) {
   const int32_t* rnodes = T.route_nodes + t.route_off;
   const int nb = sc.b_cur != INT_MAX ? sc.b_cur : (sc.b_next != INT_MAX ? sc.b_next : sc.b_any);
   on_lane = nb != INT_MAX;
-  if (on_lane) lane = ldg(&th.boxes[nb].lane);
+  if (on_lane) lane = ldg(&boxes_of(sm, T, e)[nb].lane);
   if (ck0 != ck1) {
-    const PgdLane l = load_rec(th.lanes + lane);
+    const PgdLane l = load_rec(lanes_of(sm, T, e) + lane);
     float lon, lat;
     lane_local(l, x, y, lon, lat);
-    const int start = ldg(&th.roads[l.road].start_node);
+    const int start = ldg(&roads_of(sm, T, e)[l.road].start_node);
     if (lon < 5.0f) {
 #pragma unroll 1
       for (int j = ck1; j < t.route_len - 1; ++j) {
@@ -1005,69 +974,129 @@ PGS_HD void after_scan(const Thr<V, R>& th, const Tables& T, const PgdSlot& t, c
   }
 }
 
+/* cur_road / next_road: the roads of the vehicle's two checkpoints, looked up by idm_act (the checkpoints only change
+ * here, afterwards). */
 template <int V, int R>
-PGS_HD void localise_traffic(const Thr<V, R>& th, const Tables& T, Veh& q, int s) {
-  const PgdSlot& t = th.tpl[s];
-  const int32_t* rroads = T.route_roads + t.route_off;
-  const int cur_road = ldg(&rroads[q.ck0]);
-  const int next_road = q.ck0 != q.ck1 ? ldg(&rroads[q.ck1]) : -1;
+PGS_HD void localise_traffic(const Smem<V, R>& sm, const Tables& T, int e, const PgdSlot& t, int cur_road, int next_road,
+                            Veh& q) {
   ScanOut sc;
-  bucket_scan<false>(th.mp, th.lanes, th.boxes, T, q.x, q.y, q.hc, q.hs, q.hl, q.hw, cur_road, next_road, 0, 1, sc);
+  bucket_scan<false>(grid_of(sm, e), lanes_of(sm, T, e), boxes_of(sm, T, e), T, q.x, q.y, q.hc, q.hs, q.hl, q.hw, cur_road,
+                     next_road, sc);
   bool on_lane;
-  after_scan(th, T, t, sc, q.x, q.y, q.lane, q.ck0, q.ck1, on_lane);
+  after_scan(sm, T, e, t, sc, q.x, q.y, q.lane, q.ck0, q.ck1, on_lane);
   q.vflags = on_lane ? (q.vflags | PGD_V_ON_LANE) : (q.vflags & ~(PGD_V_ON_LANE | PGD_V_ALIVE));  // traffic_manager.py:91-109
 }
 
-/* The ego's share of phase F that every reader of its lane / checkpoints needs: combine the roles' scan shares. */
+// ---- phase X: everything that moves -------------------------------------------------------------------------------
+/* Role 0: the ego's sub-steps (trajectory -> shared memory, announced to the traffic warps through named barrier 1),
+ * then its localisation (navigation.py:155-211) and line / sidewalk contacts (base_vehicle.py:615-644), published for
+ * the last role through named barrier 2, then the table look-ups of the reward (phase F only adds what depends on the
+ * traffic: the crash flags).
+ * Traffic roles: work items = the CTA's awake traffic in batches of 32, dealt round-robin -- IDM / PID against the
+ * start-of-step copy of everybody's pose, then the sub-steps with the chassis test against the ego's trajectory,
+ * localisation, removal, and the final pose into Smem::p; then the parked vehicles of the thread's own environment
+ * against the ego's trajectory.  The last role finishes with the ego's navigation features.
+ * An item touches nothing another item reads, so the order in which the warps work does not matter. */
+PGS_HD void named_arrive(int id, int threads) {  // all 32 lanes of the warp
+#ifdef __CUDA_ARCH__
+  __syncwarp();
+  __threadfence_block();
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory");
+#else
+  (void)id; (void)threads;
+#endif
+}
+PGS_HD void named_wait(int id, int threads) {  // all 32 lanes of the warp
+#ifdef __CUDA_ARCH__
+  __syncwarp();
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+#else
+  (void)id; (void)threads;
+#endif
+}
 template <int V, int R>
-PGS_HD void ego_after_scan(const Smem<V, R>& sm, const Thr<V, R>& th, const Tables& T, int& lane, int& ck0, int& ck1,
-                          bool& on_lane, uint32_t& flags) {
+PGS_HD void reward_lookups(const Smem<V, R>& sm, Thr<V, R>& th, const Tables& T, const PgdConfig& cfg);
+template <int V, int R>
+PGS_HD void navi_lookups(const Smem<V, R>& sm, Thr<V, R>& th, const Tables& T);
+#define PGS_BAR_TRAJ 1  // role 0 arrives, the R - 1 traffic warps wait: the egos' trajectories are in shared memory
+#define PGS_BAR_LOC 2   // role 0 arrives, role R - 1 waits: the egos' lanes / checkpoints are in shared memory
+
+template <int V, int R>
+PGS_HD void phase_x_ego(Smem<V, R>& sm, Thr<V, R>& th, const Tables& T, const State& S, const PgdConfig& cfg,
+                        TrajPtr traj) {
   const int ln = th.lane;
-  const ScanOut sc = {sm.scan[0][ln], sm.scan[1][ln], sm.scan[2][ln], (uint32_t)sm.scan[3][ln]};
-  flags = sc.flags;
-  lane = lf_lane(sm.p.lf[0][ln]);  // the start-of-step lane stays when no lane box is under the vehicle
-  ck0 = sm.ego_ck[ln] & 0xffff;
-  ck1 = sm.ego_ck[ln] >> 16;
-  const F4 e = sm.efin[ln];
-  after_scan(th, T, th.tpl[0], sc, e.x, e.y, lane, ck0, ck1, on_lane);
+  const int ns = cfg.decision_repeat < PGS_MAX_SUBSTEPS ? cfg.decision_repeat : PGS_MAX_SUBSTEPS;
+  Veh& q = th.ego;
+  if (th.valid) {
+    if (th.stepping) {  // 5 x doPhysics(0.02) of the ego (base_engine.py:206-232), remembering every pose
+      // A vehicle at rest with no yaw rate and no engine force is a fixed point of the sub-step (speed = max(0 - dv, 0)
+      // = 0, the pose does not move); only its drop counter runs.
+      const bool parked = q.v == 0.0f && q.yaw == 0.0f && !(q.throttle > 0.0f);
+      Sub sub;
+      if (!parked) sub = make_sub(q, slots_of(sm, T, ln)[0], cfg.dt);
+      float m2 = 0.0f;
+#pragma unroll 1
+      for (int k = 0; k < ns; ++k) {
+        if (q.airborne > 0) q.airborne--;  // placed 1 m above the road: no wheel contact while it drops
+        else if (!parked) substep(q, sub, cfg.dt);
+        const F4 p = {q.x, q.y, q.hc, q.hs};
+        traj[k][ln] = p;
+        const float ex = q.x - sm.last_x[ln], ey = q.y - sm.last_y[ln];
+        m2 = fmaxf(m2, ex * ex + ey * ey);
+      }
+      sm.ego_travel[ln] = sqrtf(m2) * 1.001f + 1e-3f;  // how far the ego gets from its start pose within the step
+    }
+    const F4 fin = {q.x, q.y, q.hc, q.hs};
+    sm.efin[ln] = fin;
+    sm.ego_h[ln] = q.h;
+    sm.ego_v[ln] = q.v;
+  }
+  named_arrive(PGS_BAR_TRAJ, R * 32);
+  if (th.valid) {
+    // the record goes home now (phase F only adds what localisation changes: lane, checkpoints, on-lane flag), so that
+    // the warp does not carry it through the rest of the step
+    veh_store(q, S, (size_t)th.env);
+    // ego after_step, first half (navigation.py:155-211, base_vehicle.py:615-644)
+    const PgdSlot& t0 = slots_of(sm, T, ln)[0];
+    const int32_t* rroads = T.route_roads + t0.route_off;
+    const int cur_road = ldg(&rroads[q.ck0]);
+    const int next_road = q.ck0 != q.ck1 ? ldg(&rroads[q.ck1]) : -1;
+    ScanOut sc;
+    bucket_scan<true>(grid_of(sm, ln), lanes_of(sm, T, ln), boxes_of(sm, T, ln), T, q.x, q.y, q.hc, q.hs, q.hl, q.hw,
+                      cur_road, next_road, sc);
+    bool on_lane;  // the start-of-step lane stays when no lane box is under the vehicle
+    after_scan(sm, T, ln, t0, sc, q.x, q.y, q.lane, q.ck0, q.ck1, on_lane);
+    q.vflags = on_lane ? (q.vflags | PGD_V_ON_LANE) : (q.vflags & ~PGD_V_ON_LANE);
+    th.flags = sc.flags | (on_lane ? PGD_F_ON_LANE : 0);
+    sm.ego_lane[ln] = q.lane;
+    sm.ego_ck[ln] = q.ck0 | (q.ck1 << 16);
+  }
+  named_arrive(PGS_BAR_LOC, 2 * 32);
+  if (th.valid) reward_lookups(sm, th, T, cfg);
 }
 
-// ---- phase D: every role: its share of the ego's bucket scan;  traffic roles: sub-steps, chassis contact against
-// the ego's trajectory, after_step of their vehicles -----------------------------------------------------------------
+/* Parked traffic of the thread's own environment (the slots this role published in phase A, whose drop counters it
+ * already holds): only the drop counter runs and the (fixed) chassis is tested against the ego's pose of every
+ * sub-step. */
 template <int V, int R>
-PGS_HD void phase_d(Smem<V, R>& sm, Thr<V, R>& th, const Tables& T, const State& S, const PgdConfig& cfg,
-                   TrajPtr traj) {
-  if (!th.valid) return;
+PGS_HD void phase_x_parked(Smem<V, R>& sm, Thr<V, R>& th, const Tables& T, const State& S, const PgdConfig& cfg,
+                          TrajPtr traj) {
+  if (!th.valid || th.role == 0 || !th.stepping) return;
   const int ln = th.lane;
-  Pub<V>& P = sm.p;
+  const Pub<V>& P = sm.p;
   const float ehl = sm.ego_hl[ln], ehw = sm.ego_hw[ln];
-  {  // ego after_step, first half (navigation.py:155-211, base_vehicle.py:615-644), spread over the roles
-    const F4 e = sm.efin[ln];
-    const int ck0 = sm.ego_ck[ln] & 0xffff, ck1 = sm.ego_ck[ln] >> 16;
-    const int32_t* rroads = T.route_roads + th.tpl[0].route_off;
-    const int cur_road = ldg(&rroads[ck0]);
-    const int next_road = ck0 != ck1 ? ldg(&rroads[ck1]) : -1;
-    ScanOut sc;
-    bucket_scan<true>(th.mp, th.lanes, th.boxes, T, e.x, e.y, e.z, e.w, ehl, ehw, cur_road, next_road, th.role, R, sc);
-    if (sc.b_any != INT_MAX) smem_min(&sm.scan[0][ln], sc.b_any);
-    if (sc.b_cur != INT_MAX) smem_min(&sm.scan[1][ln], sc.b_cur);
-    if (sc.b_next != INT_MAX) smem_min(&sm.scan[2][ln], sc.b_next);
-    smem_or(&sm.scan[3][ln], (int)sc.flags);
-  }
-  if (th.role == 0 || !th.stepping) return;
   const int ns = cfg.decision_repeat < PGS_MAX_SUBSTEPS ? cfg.decision_repeat : PGS_MAX_SUBSTEPS;
   int crash = 0;
   const uint32_t pmask = env_pmask(sm, ln);
-  // parked traffic (the slots this role published in phase A, whose drop counters it already holds): only the drop
-  // counter runs and the (fixed) chassis is tested against the ego's pose of every sub-step
 #pragma unroll
   for (int k = 0; k < Thr<V, R>::MAXOWN; ++k) {
     const int s = th.role + k * (R - 1);
-    if (s >= th.n_slots) break;
+    if (s >= sm.cx_n_slots[ln]) break;
     if (!((pmask >> s) & 1u)) continue;
     const size_t gi = (size_t)s * th.num_envs + th.env;
-    const PgdSlot& t = th.tpl[s];
-    int air = th.pre_air[k], fl = th.pre_fl[k];
+    const PgdSlot& t = slots_of(sm, T, ln)[s];
+    const I4 m = S.misc[gi];  // (the thread's own write in phase A when the episode restarted)
+    int air = m.y, fl = m.z;
     bool dirty = false;
     if (air > 0) {
       air = air > ns ? air - ns : 0;
@@ -1110,48 +1139,86 @@ PGS_HD void phase_d(Smem<V, R>& sm, Thr<V, R>& th, const Tables& T, const State&
   smem_or(&sm.crash[ln], crash);
 }
 
-/* Traffic half of phase D: sub-steps, chassis contact against the ego's trajectory and after_step of the CTA's awake
- * vehicles, dealt to all traffic threads like phase C (the same thread gets the same vehicle). */
 template <int V, int R>
-PGS_HD void phase_d_traffic(Smem<V, R>& sm, const Thr<V, R>& th, const Tables& T, const State& S, const PgdConfig& cfg,
-                           TrajPtr traj) {
-  if (th.role == 0) return;
+PGS_HD void phase_x_items(Smem<V, R>& sm, const Thr<V, R>& th, const Tables& T, const State& S, const PgdConfig& cfg,
+                         const float* obs, TrajPtr traj) {
   Pub<V>& P = sm.p;
   const int ns = cfg.decision_repeat < PGS_MAX_SUBSTEPS ? cfg.decision_repeat : PGS_MAX_SUBSTEPS;
   const int n_work = sm.n_work;
+  bool traj_ready = false;  // warp-uniform
+  PGS_ITEM_CLK_BEGIN
+  PGS_ITEM_COUNT(8, n_work);
 #pragma unroll 1
-  for (int i = (th.role - 1) * PGS_LANES + th.lane; i < n_work; i += (R - 1) * PGS_LANES) {
-    const int e = sm.work[i] & 0xff, s = sm.work[i] >> 8;
-    Thr<V, R> it;
-    item_context(sm, th, T, e, it);
-    const float ehl = sm.ego_hl[e], ehw = sm.ego_hw[e];
-    const size_t gi = (size_t)s * it.num_envs + it.env;
-    const PgdSlot& t = it.tpl[s];
+  for (int base = (th.role - 1) * PGS_LANES; base < n_work; base += (R - 1) * PGS_LANES) {
+    PGS_ITEM_COUNT(10, 1);
+    PGS_ITEM_CLK(0);
+    const bool have = base + th.lane < n_work;
+    int e = 0, s = 0, cur_road = 0, next_road = -1;
+    size_t gi = 0;
     Veh q;
-    veh_load(q, S, gi);
-    q.hc = P.hc[s][e]; q.hs = P.hs[s][e]; q.hl = t.length * 0.5f; q.hw = t.width * 0.5f;
-    const float reach = ehl + ehw + q.hl + q.hw;
-    const bool at_rest = q.v == 0.0f && q.yaw == 0.0f && !(q.throttle > 0.0f);
-    Sub sub;
-    if (!at_rest) sub = make_sub(q, t, cfg.dt);
-    int crash = 0;
-#pragma unroll 1
-    for (int k = 0; k < ns; ++k) {
-      if (q.airborne > 0) q.airborne--;
-      else if (!at_rest) substep(q, sub, cfg.dt);
-      const F4 eg4 = traj[k][e];
-      const float ddx = q.x - eg4.x, ddy = q.y - eg4.y;
-      if (ddx * ddx + ddy * ddy <= reach * reach) {
-        const Rect me = {q.x, q.y, q.hc, q.hs, q.hl, q.hw};
-        const Rect eg = {eg4.x, eg4.y, eg4.z, eg4.w, ehl, ehw};
-        if (rect_overlap(eg, me)) crash = 1;
-      }
+    if (have) {
+      const int w = sm.work[base + th.lane];
+      e = w & 0xff; s = w >> 8;
+      gi = (size_t)s * th.num_envs + (th.env - th.lane + e);
+      const uint32_t alive = env_amask(sm, e) | env_pmask(sm, e) | 1u;
+      veh_load(q, S, gi);
+      q.vflags = P.lf[s][e] & 0xff;  // a vehicle woken in this step carries ACTIVE only in shared memory so far
+      q.hc = P.hc[s][e]; q.hs = P.hs[s][e];
+      PGS_ITEM_CLK(1);
+      idm_act(sm, T, obs, e, alive, q, s, cur_road, next_road);
     }
-    localise_traffic(it, T, q, s);
-    veh_store(q, S, gi);
-    P.x[s][e] = q.x; P.y[s][e] = q.y; P.hc[s][e] = q.hc; P.hs[s][e] = q.hs; P.v[s][e] = q.v;
-    P.lf[s][e] = lf_pack(q.lane, q.vflags);
-    smem_or(&sm.crash[e], crash);
+    PGS_ITEM_CLK(2);
+    if (!traj_ready) {  // the whole warp, once
+      named_wait(PGS_BAR_TRAJ, R * 32);
+      traj_ready = true;
+    }
+    if (have) {
+      const PgdSlot& t = slots_of(sm, T, e)[s];
+      const float ehl = sm.ego_hl[e], ehw = sm.ego_hw[e];
+      q.hl = t.length * 0.5f; q.hw = t.width * 0.5f;
+      const float reach = ehl + ehw + q.hl + q.hw;
+      const bool at_rest = q.v == 0.0f && q.yaw == 0.0f && !(q.throttle > 0.0f);
+      Sub sub;
+      if (!at_rest) sub = make_sub(q, t, cfg.dt);
+      int crash = 0;
+      PGS_ITEM_CLK(3);
+#pragma unroll 1
+      for (int k = 0; k < ns; ++k) {
+        if (q.airborne > 0) q.airborne--;
+        else if (!at_rest) substep(q, sub, cfg.dt);
+        const F4 eg4 = traj[k][e];
+        const float ddx = q.x - eg4.x, ddy = q.y - eg4.y;
+        if (ddx * ddx + ddy * ddy <= reach * reach) {
+          const Rect me = {q.x, q.y, q.hc, q.hs, q.hl, q.hw};
+          const Rect eg = {eg4.x, eg4.y, eg4.z, eg4.w, ehl, ehw};
+          if (rect_overlap(eg, me)) crash = 1;
+        }
+      }
+      PGS_ITEM_CLK(4);
+      localise_traffic(sm, T, e, t, cur_road, next_road, q);
+      PGS_ITEM_CLK(5);
+      veh_store(q, S, gi);
+      P.x[s][e] = q.x; P.y[s][e] = q.y; P.hc[s][e] = q.hc; P.hs[s][e] = q.hs; P.v[s][e] = q.v;
+      P.lf[s][e] = lf_pack(q.lane, q.vflags);
+      smem_or(&sm.crash[e], crash);
+    }
+    PGS_ITEM_CLK(6);
+  }
+  if (!traj_ready) named_wait(PGS_BAR_TRAJ, R * 32);
+}
+
+template <int V, int R>
+PGS_HD void phase_x(Smem<V, R>& sm, Thr<V, R>& th, const Tables& T, const State& S, const PgdConfig& cfg,
+                   const float* obs, TrajPtr traj) {
+  if (th.role == 0) {
+    phase_x_ego(sm, th, T, S, cfg, traj);
+    return;
+  }
+  phase_x_items(sm, th, T, S, cfg, obs, traj);
+  phase_x_parked(sm, th, T, S, cfg, traj);
+  if (th.role == R - 1) {
+    named_wait(PGS_BAR_LOC, 2 * 32);
+    if (th.valid) navi_lookups(sm, th, T);
   }
 }
 
@@ -1161,62 +1228,85 @@ PGS_HD int obs_dim_of(const PgdConfig& cfg) {
          PGD_LIDAR_BEAMS;
 }
 
-/* task 0 (role 0): lane + checkpoints, route distances, arrival, reward / cost / done, state observation, info, ego
- * state store */
+/* Role 0 while the traffic moves (phase X): the table look-ups of the ego's bookkeeping -- route distances, arrival,
+ * reward geometry (base_vehicle.py:383-388,738-745; pgdrive_env.py:162-258).  What phase F needs of them stays in
+ * registers: th.flags, th.keep[0..3]. */
 template <int V, int R>
-PGS_HD void task_reward(Smem<V, R>& sm, Thr<V, R>& th, const Tables& T, const State& S, const PgdConfig& cfg, int mode,
-                       float* obs, float* reward, uint8_t* done, PgdInfo* info) {
+PGS_HD void reward_lookups(const Smem<V, R>& sm, Thr<V, R>& th, const Tables& T, const PgdConfig& cfg) {
   const int ln = th.lane;
-  Veh& ego = th.ego;
-  const PgdMap& mp = th.mp;
-  const PgdSlot& t0 = th.tpl[0];
+  const float ex = sm.efin[ln].x, ey = sm.efin[ln].y;
+  const int lane = sm.ego_lane[ln], ck0 = sm.ego_ck[ln] & 0xffff;
+  const PgdSlot& t0 = slots_of(sm, T, ln)[0];
+  const PgdLane* lanes = lanes_of(sm, T, ln);
+  const PgdRoad* roads = roads_of(sm, T, ln);
+  const float lane_width = sm.cx_lane_width[ln];
   const int32_t* rroads = T.route_roads + t0.route_off;
-  const float last_h = th.fresh ? ego.h : th.pre_pose.z;
-  uint32_t flags;
-  bool on_lane;
-  ego_after_scan(sm, th, T, ego.lane, ego.ck0, ego.ck1, on_lane, flags);
-  ego.vflags = on_lane ? (ego.vflags | PGD_V_ON_LANE) : (ego.vflags & ~PGD_V_ON_LANE);
-  const int n_first = cfg.n_side > 0 ? cfg.n_side : 2;
-  float* const st = obs + n_first - 2;
-  const int n_extra = cfg.random_agent_model ? 2 : 0;
-  if (n_extra) {  // obs/state_obs.py:103-105: LENGTH / MAX_LENGTH, WIDTH / MAX_WIDTH (base_vehicle.py:83-84)
-    obs[n_first + 6 + cfg.n_lane_line] = clipf(t0.length / 10.0f, 0.0f, 1.0f);
-    obs[n_first + 6 + cfg.n_lane_line + 1] = clipf(t0.width / 2.5f, 0.0f, 1.0f);
-  }
-  const int crash = sm.crash[ln] & 1, crash_object = (sm.crash[ln] >> 1) & 1;
+  uint32_t flags = th.flags;
+  const bool on_lane = (flags & PGD_F_ON_LANE) != 0;
   const float last_x = sm.last_x[ln], last_y = sm.last_y[ln];
-  const int cur_road_id = ldg(&rroads[ego.ck0]);
-  const PgdRoad cur_road = load_rec(th.roads + cur_road_id);
-  const PgdRoad fr = load_rec(th.roads + ldg(&rroads[t0.route_len - 2]));
-  const int el_road = ldg(&th.lanes[ego.lane].road);
+  const int cur_road_id = ldg(&rroads[ck0]);
+  const PgdRoad cur_road = load_rec(roads + cur_road_id);
+  const PgdRoad fr = load_rec(roads + ldg(&rroads[t0.route_len - 2]));
+  const int el_road = ldg(&lanes[lane].road);
   const bool use_ego_lane = el_road == cur_road_id;
-  const int reward_lane = use_ego_lane ? ego.lane : cur_road.first_lane;
+  const int reward_lane = use_ego_lane ? lane : cur_road.first_lane;
   const int n_ref = cur_road.n_lanes;
-  const int sign_i = use_ego_lane ? 0 : (ldg(&th.roads[el_road].negative) ? -1 : 1);
+  const int sign_i = use_ego_lane ? 0 : (ldg(&roads[el_road].negative) ? -1 : 1);
   float qlon0, qlat0, qlon1, qlat1, long_last = 0.0f, lat_last, long_now = 0.0f, lat_now = 0.0f;
-  lane_local(load_rec(th.lanes + cur_road.first_lane), ego.x, ego.y, qlon0, qlat0);
-  const PgdLane final_lane = load_rec(th.lanes + (fr.first_lane + fr.n_lanes - 1));
-  lane_local(final_lane, ego.x, ego.y, qlon1, qlat1);
+  lane_local(load_rec(lanes + cur_road.first_lane), ex, ey, qlon0, qlat0);
+  const PgdLane final_lane = load_rec(lanes + (fr.first_lane + fr.n_lanes - 1));
+  lane_local(final_lane, ex, ey, qlon1, qlat1);
   if (!th.fresh) {
-    const PgdLane rl = load_rec(th.lanes + reward_lane);
+    const PgdLane rl = load_rec(lanes + reward_lane);
     lane_local(rl, last_x, last_y, long_last, lat_last);
-    lane_local(rl, ego.x, ego.y, long_now, lat_now);
+    lane_local(rl, ex, ey, long_now, lat_now);
   }
-  if (on_lane) flags |= PGD_F_ON_LANE;
-  if (crash) flags |= PGD_F_CRASH_VEHICLE;
-  if (crash_object) flags |= PGD_F_CRASH_OBJECT;
-  const float to_left = qlat0 + mp.lane_width / 2.0f;  // base_vehicle.py:383-388
-  const float to_right = mp.lane_width * (float)n_ref - to_left;
+  const float to_left = qlat0 + lane_width / 2.0f;  // base_vehicle.py:383-388
+  const float to_right = lane_width * (float)n_ref - to_left;
   if (to_left < 0.0f || to_right < 0.0f) flags |= PGD_F_OUT_OF_ROUTE;
   {  // arrive_destination (base_vehicle.py:738-745)
     const float flen = final_lane.length;
-    if (flen - 5.0f < qlon1 && qlon1 < flen + 5.0f && mp.lane_width / 2.0f >= qlat1 &&
-        qlat1 >= (0.5f - (float)n_ref) * mp.lane_width)
+    if (flen - 5.0f < qlon1 && qlon1 < flen + 5.0f && lane_width / 2.0f >= qlat1 &&
+        qlat1 >= (0.5f - (float)n_ref) * lane_width)
       flags |= PGD_F_ARRIVE_DEST;
   }
   bool out_of_road = (flags & (PGD_F_ON_YELLOW | PGD_F_ON_WHITE | PGD_F_CRASH_SIDEWALK)) || !on_lane;
   if (cfg.out_of_route_done && (flags & PGD_F_OUT_OF_ROUTE)) out_of_road = true;
   if (out_of_road) flags |= PGD_F_OUT_OF_ROAD;
+  const float sign = sign_i == 0 ? 1.0f : (float)sign_i;
+  float lateral_factor = 1.0f;
+  if (cfg.use_lateral) lateral_factor = clipf(1.0f - 2.0f * fabsf(lat_now) / lane_width, 0.0f, 1.0f);
+  th.flags = flags;
+  th.keep[0] = to_left;
+  th.keep[1] = to_right;
+  th.keep[2] = cfg.driving_reward * (long_now - long_last) * lateral_factor * sign;
+  th.keep[3] = sign;
+}
+
+/* task 0 (role 0): what the traffic decides -- crash flags -- then reward / cost / done, the ego's state features, info,
+ * and the words of the ego's record that localisation changed */
+template <int V, int R>
+PGS_HD void task_reward(Smem<V, R>& sm, Thr<V, R>& th, const Tables& T, const State& S, const PgdConfig& cfg, int mode,
+                       float* obs, float* reward, uint8_t* done, PgdInfo* info) {
+  const int ln = th.lane;
+  struct {  // what is left of the ego in registers (phase_x_ego stored the record)
+    float x, y, h, v, steer, throttle;
+  } ego = {sm.efin[ln].x, sm.efin[ln].y, sm.ego_h[ln], sm.ego_v[ln], th.ego.steer, th.ego.throttle};
+  const float last_h = th.fresh ? ego.h : th.pre_pose.z;
+  const int n_first = cfg.n_side > 0 ? cfg.n_side : 2;
+  float* const st = obs + n_first - 2;
+  if (cfg.random_agent_model) {  // obs/state_obs.py:103-105: LENGTH / MAX_LENGTH, WIDTH / MAX_WIDTH (base_vehicle.py:83-84)
+    const PgdSlot& t0 = slots_of(sm, T, ln)[0];
+    obs[n_first + 6 + cfg.n_lane_line] = clipf(t0.length / 10.0f, 0.0f, 1.0f);
+    obs[n_first + 6 + cfg.n_lane_line + 1] = clipf(t0.width / 2.5f, 0.0f, 1.0f);
+  }
+  const int crash = sm.crash[ln] & 1, crash_object = (sm.crash[ln] >> 1) & 1;
+  const float last_x = sm.last_x[ln], last_y = sm.last_y[ln];
+  uint32_t flags = th.flags;
+  if (crash) flags |= PGD_F_CRASH_VEHICLE;
+  if (crash_object) flags |= PGD_F_CRASH_OBJECT;
+  const bool out_of_road = (flags & PGD_F_OUT_OF_ROAD) != 0;
+  const float to_left = th.keep[0], to_right = th.keep[1];
 
   const float sp = kmh(ego.v);
   if (cfg.n_side <= 0) {
@@ -1233,10 +1323,8 @@ PGS_HD void task_reward(Smem<V, R>& sm, Thr<V, R>& th, const Tables& T, const St
   float r = 0.0f, step_reward = 0.0f, cost = 0.0f, step_energy = 0.0f;
   int is_done = 0;
   if (!th.fresh) {  // envs/pgdrive_env.py:162-258
-    const float sign = sign_i == 0 ? 1.0f : (float)sign_i;
-    float lateral_factor = 1.0f;
-    if (cfg.use_lateral) lateral_factor = clipf(1.0f - 2.0f * fabsf(lat_now) / mp.lane_width, 0.0f, 1.0f);
-    r += cfg.driving_reward * (long_now - long_last) * lateral_factor * sign;
+    const float sign = th.keep[3];
+    r += th.keep[2];  // driving_reward * (long_now - long_last) * lateral_factor * sign
     r += cfg.speed_reward * (sp / PGS_MAX_SPEED_KMH) * sign;
     step_reward = r;
     if (flags & PGD_F_ARRIVE_DEST) r = cfg.success_reward;
@@ -1274,30 +1362,29 @@ PGS_HD void task_reward(Smem<V, R>& sm, Thr<V, R>& th, const Tables& T, const St
   }
   S.envi[th.env] = th.envi;
   S.envf[th.env] = th.envf;
-  veh_store(ego, S, (size_t)th.env);
+  S.nav[th.env].x = sm.ego_lane[ln];
+  S.nav[th.env].y = sm.ego_ck[ln];
+  S.misc[th.env].z = th.ego.vflags;
 }
 
-/* task 1: navigation info of the two checkpoints (navigation.py:213-260) + heading_diff (base_vehicle.py:433-458) */
+/* Role R-1 at the end of phase X: navigation info of the two checkpoints (navigation.py:213-260) + heading_diff
+ * (base_vehicle.py:433-458) -> th.keep[0..10]; task_navi writes them to the row in phase F. */
 template <int V, int R>
-PGS_HD void task_navi(const Smem<V, R>& sm, const Thr<V, R>& th, const Tables& T, const PgdConfig& cfg, float* obs) {
+PGS_HD void navi_lookups(const Smem<V, R>& sm, Thr<V, R>& th, const Tables& T) {
   const int ln = th.lane;
-  const PgdMap& mp = th.mp;
   const F4 e = sm.efin[ln];
   const float ex = e.x, ey = e.y, ehc = e.z, ehs = e.w;
-  int lane, ck0, ck1;
-  bool on_lane;
-  uint32_t fl_unused;
-  ego_after_scan(sm, th, T, lane, ck0, ck1, on_lane, fl_unused);
-  const int32_t* rroads = T.route_roads + th.tpl[0].route_off;
-  const int n_first = cfg.n_side > 0 ? cfg.n_side : 2;
-  float* const st = obs + n_first - 2;
-  float* const ob = obs + n_first + cfg.n_lane_line + (cfg.random_agent_model ? 2 : 0) - 2;
-  const PgdRoad cur_road = load_rec(th.roads + ldg(&rroads[ck0]));
+  const int ck0 = sm.ego_ck[ln] & 0xffff, ck1 = sm.ego_ck[ln] >> 16;  // after the ego's localisation
+  const PgdLane* lanes = lanes_of(sm, T, ln);
+  const PgdRoad* roads = roads_of(sm, T, ln);
+  const float lane_width = sm.cx_lane_width[ln];
+  const int32_t* rroads = T.route_roads + slots_of(sm, T, ln)[0].route_off;
+  const PgdRoad cur_road = load_rec(roads + ldg(&rroads[ck0]));
   const int n_ref = cur_road.n_lanes;
-#pragma unroll 1
+#pragma unroll
   for (int c = 0; c < 2; ++c) {
-    const PgdLane l = load_rec(th.lanes + (c == 0 ? cur_road.first_lane : ldg(&th.roads[ldg(&rroads[ck1])].first_lane)));
-    const float later_middle = ((float)n_ref / 2.0f - 0.5f) * mp.lane_width;
+    const PgdLane l = load_rec(lanes + (c == 0 ? cur_road.first_lane : ldg(&roads[ldg(&rroads[ck1])].first_lane)));
+    const float later_middle = ((float)n_ref / 2.0f - 0.5f) * lane_width;
     float px, py;
     lane_position(l, l.length, later_middle, px, py);
     float dx = px - ex, dy = py - ey;
@@ -1307,31 +1394,41 @@ PGS_HD void task_navi(const Smem<V, R>& sm, const Thr<V, R>& th, const Tables& T
     project(ehc, ehs, dx, dy, ph, ps);
     float bend = 0.0f, dir = 0.0f, angle = 0.0f;
     if (l.kind == PGD_LANE_ARC) {
-      bend = l.radius / (60.0f + (float)n_ref * mp.lane_width);
+      bend = l.radius / (60.0f + (float)n_ref * lane_width);
       dir = l.dir;
       angle = l.length / l.radius;
     }
-    float* q = ob + 8 + 5 * c;
-    q[0] = clipf((ph / 50.0f + 1.0f) / 2.0f, 0.0f, 1.0f);
-    q[1] = clipf((ps / 50.0f + 1.0f) / 2.0f, 0.0f, 1.0f);
-    q[2] = clipf(bend, 0.0f, 1.0f);
-    q[3] = clipf((dir + 1.0f) / 2.0f, 0.0f, 1.0f);
-    q[4] = clipf((angle * (180.0f / PGS_PI) / 135.0f + 1.0f) / 2.0f, 0.0f, 1.0f);
+    th.keep[5 * c + 0] = clipf((ph / 50.0f + 1.0f) / 2.0f, 0.0f, 1.0f);
+    th.keep[5 * c + 1] = clipf((ps / 50.0f + 1.0f) / 2.0f, 0.0f, 1.0f);
+    th.keep[5 * c + 2] = clipf(bend, 0.0f, 1.0f);
+    th.keep[5 * c + 3] = clipf((dir + 1.0f) / 2.0f, 0.0f, 1.0f);
+    th.keep[5 * c + 4] = clipf((angle * (180.0f / PGS_PI) / 135.0f + 1.0f) / 2.0f, 0.0f, 1.0f);
   }
   {  // heading_diff against the right-most reference lane
-    const PgdLane l = load_rec(th.lanes + (cur_road.first_lane + cur_road.n_lanes - 1));
+    const PgdLane l = load_rec(lanes + (cur_road.first_lane + cur_road.n_lanes - 1));
     float lx, ly;
     if (l.kind == PGD_LANE_STRAIGHT) { lx = -l.ay; ly = l.ax; }
     else if (l.dir < 0.0f) { lx = ex - l.ax; ly = ey - l.ay; }
     else { lx = l.ax - ex; ly = l.ay - ey; }
     const float lnm = sqrtf(lx * lx + ly * ly);
-    st[2] = lnm > 0.0f ? clipf((ehc * lx + ehs * ly) / lnm, -1.0f, 1.0f) / 2.0f + 0.5f : 0.0f;
+    th.keep[10] = lnm > 0.0f ? clipf((ehc * lx + ehs * ly) / lnm, -1.0f, 1.0f) / 2.0f + 0.5f : 0.0f;
   }
+}
+
+template <int V, int R>
+PGS_HD void task_navi(const Thr<V, R>& th, const PgdConfig& cfg, float* obs) {
+  const int n_first = cfg.n_side > 0 ? cfg.n_side : 2;
+  float* const st = obs + n_first - 2;
+  float* const ob = obs + n_first + cfg.n_lane_line + (cfg.random_agent_model ? 2 : 0) - 2;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) ob[8 + i] = th.keep[i];
+  st[2] = th.keep[10];
 }
 
 /* task 2: the 4 nearest vehicles inside the 50 m cylinder (lidar.py:55-77; ties -> lower slot) */
 template <int V, int R>
-PGS_HD void task_neighbours(const Smem<V, R>& sm, const Thr<V, R>& th, const PgdConfig& cfg, float* obs) {
+PGS_HD void task_neighbours(const Smem<V, R>& sm, const Thr<V, R>& th, const Tables& T, const PgdConfig& cfg,
+                           float* obs) {
   const int ln = th.lane;
   const Pub<V>& P = sm.p;
   const F4 e = sm.efin[ln];
@@ -1341,10 +1438,10 @@ PGS_HD void task_neighbours(const Smem<V, R>& sm, const Thr<V, R>& th, const Pgd
   float* const ob = obs + n_first + cfg.n_lane_line + (cfg.random_agent_model ? 2 : 0) - 2;
   uint32_t cand = 0;  // alive vehicles inside the cylinder
 #pragma unroll 1
-  for (int s = 1; s < th.n_slots; ++s) {
+  for (int s = 1; s < sm.cx_n_slots[ln]; ++s) {
     if (!(P.lf[s][ln] & PGD_V_ALIVE)) continue;
     const float dx = P.x[s][ln] - ex, dy = P.y[s][ln] - ey;
-    if (dx * dx + dy * dy < PGS_LIDAR_RANGE * PGS_LIDAR_RANGE && ldg(&th.tpl[s].type) < PGD_TYPE_OBJECT)
+    if (dx * dx + dy * dy < PGS_LIDAR_RANGE * PGS_LIDAR_RANGE && ldg(&slots_of(sm, T, ln)[s].type) < PGD_TYPE_OBJECT)
       cand |= 1u << s;  // get_surrounding_vehicles (lidar.py:46-54): cones and barriers are not vehicles
   }
 #pragma unroll 1
@@ -1377,19 +1474,19 @@ PGS_HD void task_neighbours(const Smem<V, R>& sm, const Thr<V, R>& th, const Pgd
 
 /* task 3: which chassis the lidar can reach, and the (conservative) arc of beams that can hit each */
 template <int V, int R>
-PGS_HD void task_lidar_windows(Smem<V, R>& sm, const Thr<V, R>& th, VisPtr vis) {
+PGS_HD void task_lidar_windows(Smem<V, R>& sm, const Thr<V, R>& th, const Tables& T, VisPtr vis) {
   const int ln = th.lane;
   const Pub<V>& P = sm.p;
   const F4 e = sm.efin[ln];
   const float ex = e.x, ey = e.y, eh = sm.ego_h[ln];
   int n = 0;
 #pragma unroll 1
-  for (int s = 1; s < th.n_slots; ++s) {
+  for (int s = 1; s < sm.cx_n_slots[ln]; ++s) {
     if (!(P.lf[s][ln] & PGD_V_ALIVE)) continue;
     const float dx = P.x[s][ln] - ex, dy = P.y[s][ln] - ey;
     const float d2 = dx * dx + dy * dy;
     if (!(d2 < (PGS_LIDAR_RANGE + 8.0f) * (PGS_LIDAR_RANGE + 8.0f))) continue;  // no chassis has an 8 m half-diagonal
-    const PgdSlot& t = th.tpl[s];
+    const PgdSlot& t = slots_of(sm, T, ln)[s];
     const float hl = t.length * 0.5f, hw = t.width * 0.5f;
     const float hd = sqrtf(hl * hl + hw * hw);
     const float reach = PGS_LIDAR_RANGE + hd;
@@ -1419,11 +1516,11 @@ template <int V, int R>
 PGS_HD void task_detectors(const Smem<V, R>& sm, const Thr<V, R>& th, const Tables& T, const PgdConfig& cfg,
                           float* obs) {
   const int ln = th.lane;
-  const PgdMap& mp = th.mp;
   const F4 e = sm.efin[ln];
   const float ex = e.x, ey = e.y, eh = sm.ego_h[ln];
   const int n_first = cfg.n_side > 0 ? cfg.n_side : 2;
   const int n_rays = cfg.n_side + cfg.n_lane_line;
+  const GridRef mp = grid_of(sm, ln);
   const int32_t* ent = T.cell_entries + mp.entry_off;
 #pragma unroll 1
   for (int rI = th.role; rI < n_rays; rI += R) {
@@ -1448,7 +1545,7 @@ PGS_HD void task_detectors(const Smem<V, R>& sm, const Thr<V, R>& th, const Tabl
       for (int k = b0; k < b1; ++k) {
         const int en = ldg(&ent[k]);
         if (en < PGD_ENTRY_NOT_LANE) continue;  // lane-surface boxes are no ray targets
-        const PgdBox g = load_rec(th.boxes + (en & PGD_ENTRY_ID_MASK));
+        const PgdBox g = load_rec(boxes_of(sm, T, ln) + (en & PGD_ENTRY_ID_MASK));
         if (!(g.kind == PGD_BOX_WHITE || g.kind == PGD_BOX_YELLOW || (!side && g.kind == PGD_BOX_BROKEN))) continue;
         const Rect r = {g.cx, g.cy, g.ux, g.uy, g.hl, g.hw};
         best = fminf(best, ray_rect(ex, ey, dx, dy, r));
@@ -1464,13 +1561,12 @@ PGS_HD void phase_f(Smem<V, R>& sm, Thr<V, R>& th, const Tables& T, const State&
                    int obs_dim, float* obs_rows, VisPtr vis, float* reward, uint8_t* done, PgdInfo* info) {
   if (!th.valid) return;
   float* obs = obs_rows + (size_t)th.lane * obs_dim;
-#pragma unroll 1
-  for (int task = th.role; task < 4; task += R) {
-    if (task == 0) task_reward(sm, th, T, S, cfg, mode, obs, reward, done, info);
-    else if (task == 1) task_navi(sm, th, T, cfg, obs);
-    else if (task == 2) task_neighbours(sm, th, cfg, obs);
-    else task_lidar_windows(sm, th, vis);
-  }
+  // role 0 and role R-1 hold what they looked up during phase X; the two tasks that need the traffic's final poses go
+  // to role 1 and role 2 (or the last one)
+  if (th.role == 0) task_reward(sm, th, T, S, cfg, mode, obs, reward, done, info);
+  if (th.role == R - 1) task_navi(th, cfg, obs);
+  if (th.role == 1) task_neighbours(sm, th, T, cfg, obs);
+  if (th.role == (R > 2 ? 2 : 1)) task_lidar_windows(sm, th, T, vis);
   if (cfg.n_side > 0 || cfg.n_lane_line > 0) task_detectors(sm, th, T, cfg, obs);
 }
 
@@ -1493,7 +1589,7 @@ PGS_HD void lidar_scatter(const Smem<V, R>& sm, const Tables& T, const State& S,
     const F4 eg = sm.efin[e];
     const float ex = eg.x, ey = eg.y, eh = sm.ego_h[e];
     float* row = row_lidar;
-    const PgdSlot* tpl = T.slots + sm.ctx_slot_off[e];
+    const PgdSlot* tpl = slots_of(sm, T, e);
 #pragma unroll 1
     for (int k = 0; k < nv; ++k) {
       const int w = vis[k][e];
@@ -1511,6 +1607,19 @@ PGS_HD void lidar_scatter(const Smem<V, R>& sm, const Tables& T, const State& S,
         if (t < 1.0f) lidar_min(row + i, t);
       }
     }
+  }
+}
+
+/* The warp that scatters an environment's hits first fills its beams with 1.0 = "no hit" (the storage held IDM's
+ * look-up data until phase X ended); a warp-level barrier separates the two. */
+template <int V, int R>
+PGS_HD void phase_l_fill(const Smem<V, R>& sm, int role, int lane, int obs_dim, float* obs_rows) {
+  const int head = obs_dim - PGD_LIDAR_BEAMS;
+#pragma unroll 1
+  for (int e = role; e < PGS_LANES; e += R) {
+    if (!sm.wrote[e]) continue;
+    float* row = obs_rows + (size_t)e * obs_dim + head;
+    for (int i = lane; i < PGD_LIDAR_BEAMS; i += PGS_LANES) row[i] = 1.0f;
   }
 }
 

@@ -4,7 +4,34 @@
 // observation rows are assembled in shared memory in their HBM layout and leave with ONE bulk (TMA) copy per CTA
 // (cp.async.bulk.global.shared::cta, 35 KB at 274 floats per row); the destination may be a peer-mapped buffer on
 // another GPU.  CTAs that are not full (partial reset, tail) fall back to coalesced per-row stores.
+#include <stdlib.h>
+
 #include "pgd_internal.h"
+
+#ifdef PGS_PHASE_CLOCKS  // diagnostic build: cycles between the CTA barriers, summed over CTAs (thread 0 of each); inside
+// phase X the cycles of traffic warp 1's lane 0 per part of an item (slots 16..)
+__device__ unsigned long long g_pgs_clk[32];
+__host__ __device__ __forceinline__ long long pgs_item_now() {
+#ifdef __CUDA_ARCH__
+  return clock64();
+#else
+  return 0;
+#endif
+}
+__host__ __device__ __forceinline__ void pgs_item_add(int i, long long n) {
+#ifdef __CUDA_ARCH__
+  if (threadIdx.x == 32) atomicAdd(&g_pgs_clk[16 + i], (unsigned long long)n);
+#endif
+}
+#define PGS_ITEM_CLK_BEGIN long long iclk_ = pgs_item_now();
+#define PGS_ITEM_CLK(i)                      \
+  do {                                      \
+    const long long now_ = pgs_item_now();  \
+    pgs_item_add(i, now_ - iclk_);          \
+    iclk_ = now_;                           \
+  } while (0)
+#define PGS_ITEM_COUNT(i, n) pgs_item_add(i, n)
+#endif
 #include "pgd_step.cuh"
 
 using namespace pgdstep;
@@ -18,10 +45,8 @@ using namespace pgdstep;
 #ifndef PGS_OBS_EVICT_FIRST
 #define PGS_OBS_EVICT_FIRST 1
 #endif
-#define PGS_STAGE_MAX_LANES 210  // most lanes a 3-block map has
 
-#ifdef PGS_PHASE_CLOCKS  // diagnostic build: cycles between the CTA barriers, summed over CTAs (thread 0 of each)
-__device__ unsigned long long g_pgs_clk[16];
+#ifdef PGS_PHASE_CLOCKS
 #define PGS_CLK(i)                                                              \
   do {                                                                         \
     if (threadIdx.x == 0) {                                                    \
@@ -33,7 +58,7 @@ __device__ unsigned long long g_pgs_clk[16];
 extern "C" int pgd_debug_phase_clocks(unsigned long long* out, int reset) {
   cudaMemcpyFromSymbol(out, g_pgs_clk, sizeof(g_pgs_clk));
   if (reset) {
-    unsigned long long z[16] = {0};
+    unsigned long long z[32] = {0};
     cudaMemcpyToSymbol(g_pgs_clk, z, sizeof(z));
   }
   return 0;
@@ -45,7 +70,7 @@ extern "C" int pgd_debug_phase_clocks(unsigned long long* out, int reset) {
 template <int V, int R>
 __global__ void __launch_bounds__(R * 32, PGS_MIN_CTAS) pgd_step_kernel(Tables T, State S, PgdConfig cfg, int mode,
                                                                          uint32_t call_index,
-                                                                         int env_begin, int env_end,
+                                                                         int env_begin, int env_end, int envs_per_cta,
                                                                          const float* __restrict__ actions,
                                                                          float* __restrict__ obs,
                                                                          float* __restrict__ reward,
@@ -59,89 +84,49 @@ __global__ void __launch_bounds__(R * 32, PGS_MIN_CTAS) pgd_step_kernel(Tables T
   TrajPtr traj = reinterpret_cast<TrajPtr>(tv);
   VisPtr vis = reinterpret_cast<VisPtr>(tv);
   const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
-  const int env0 = env_begin + blockIdx.x * PGS_LANES;
+  // lanes [0, envs_per_cta) of every warp carry an environment (pgd_launch_step: fewer than 32 when that makes the grid
+  // a whole number of waves)
+  const int env0 = env_begin + blockIdx.x * envs_per_cta;
+  const int cta_end = env0 + envs_per_cta < env_end ? env0 + envs_per_cta : env_end;
 #ifdef PGS_PHASE_CLOCKS
   long long clk_ = clock64();
 #endif
   Thr<V, R> th;
-  thread_init(th, T, S, cfg, mode, lane, role, env0 + lane, env_end);
+  thread_init(th, T, S, cfg, mode, lane, role, env0 + lane, cta_end);
   phase_0(sm, th);
   if (!__syncthreads_or(th.valid)) return;  // reset pass: no environment of this CTA is marked
-#ifdef PGS_STAGE_LANES
-  // EXPERIMENT (north_star: "lane / segment geometry TMA-staged into shared memory per block"): when the 32
-  // environments of the CTA play the same map, its lane table (<= 210 x 64 B) is brought into shared memory by one
-  // bulk (TMA) copy and every lane access of the step reads it there.  Measured against the same build without the
-  // staging in profiles/ (tools/kernel_variants.py: "plain" vs "stage", environments assigned to seeds in blocks of 32).
-  {
-    __shared__ __align__(8) unsigned long long stage_bar;
-    PgdLane* stage = reinterpret_cast<PgdLane*>(smem_raw + smem_bytes<V, R>(obs_dim, cfg.decision_repeat));
-    const int map0 = sm.ctx_map[0];
-    const bool same = __syncthreads_and(th.valid && sm.ctx_map[lane] == map0 && th.mp.n_lanes <= PGS_STAGE_MAX_LANES);
-    if (same) {
-      const uint32_t bytes = (uint32_t)th.mp.n_lanes * (uint32_t)sizeof(PgdLane);
-      const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&stage_bar);
-      if (threadIdx.x == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-      }
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                         (uint32_t)__cvta_generic_to_shared(stage)),
-                     "l"(th.lanes), "r"(bytes), "r"(bar)
-                     : "memory");
-      }
-      uint32_t done = 0;
-      while (!done) {
-        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
-                     : "=r"(done)
-                     : "r"(bar)
-                     : "memory");
-      }
-      th.lanes = stage;
-      th.staged_lanes = stage;
-    }
-  }
-#endif
   PGS_CLK(0);
-  phase_a(sm, th, S, cfg, actions);
+  phase_a(sm, th, S, cfg, actions, rows);
   PGS_CLK(1);
   __syncthreads();
   PGS_CLK(2);
-  phase_b(sm, th, rows);
+  phase_b(sm, th, T, rows);
   __syncthreads();
   PGS_CLK(3);
-  phase_c(sm, th, T, S, cfg, rows, traj);
-  phase_c_traffic(sm, th, T, S, rows);
+  phase_x(sm, th, T, S, cfg, rows, traj);
   PGS_CLK(4);
-  __syncthreads();
   PGS_CLK(5);
-  {  // pre-fill the rows with 1.0 = "no hit" (the IDM look-up data that shared this storage is dead now)
-    float4* o4 = reinterpret_cast<float4*>(rows);
-    const int n4 = PGS_LANES * obs_dim / 4;  // 32 rows: a multiple of 4 floats for every row length
-    for (int i = threadIdx.x; i < n4; i += R * 32) o4[i] = make_float4(1.f, 1.f, 1.f, 1.f);
-  }
   PGS_CLK(6);
-  phase_d(sm, th, T, S, cfg, traj);
-  phase_d_traffic(sm, th, T, S, cfg, traj);
+  __syncthreads();  // everything has moved; the IDM look-up data that shared the rows' storage is dead
   PGS_CLK(7);
-  __syncthreads();
-  PGS_CLK(8);
   phase_f(sm, th, T, S, cfg, mode, obs_dim, rows, vis, reward, done, info);
-  PGS_CLK(9);
+  PGS_CLK(8);
   __syncthreads();
-  PGS_CLK(10);
+  PGS_CLK(9);
+  phase_l_fill(sm, role, lane, obs_dim, rows);
+  __syncwarp();
   phase_l(sm, T, S, role, lane, env0, obs_dim, rows, vis);
+  PGS_CLK(10);
   __syncwarp();
   phase_n(sm, cfg, call_index, role, lane, env0, obs_dim, rows);
   PGS_CLK(11);
   // ---- write-out -----------------------------------------------------------------------------------------------------
-  const int all = __syncthreads_and(sm.wrote[lane]);
+  const int n_rows = cta_end - env0;
+  const int all = __syncthreads_and(lane >= n_rows || sm.wrote[lane]);
   float* dst = obs + (size_t)env0 * obs_dim;
-  if (all && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+  const uint32_t bytes = (uint32_t)(n_rows * obs_dim * sizeof(float));
+  if (all && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && (bytes & 15) == 0) {
     if (threadIdx.x == 0) {
-      const uint32_t bytes = (uint32_t)(PGS_LANES * obs_dim * sizeof(float));
       const uint32_t src = (uint32_t)__cvta_generic_to_shared(rows);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 #if PGS_OBS_EVICT_FIRST
@@ -174,18 +159,22 @@ template <int V, int R>
 static int launch_one(PgdHandle* h, const Tables& T, const State& S, int mode, int env_begin, int env_end,
                       const float* actions, float* obs, float* reward, uint8_t* done, PgdInfo* info, cudaStream_t st) {
   static int configured = 0;  // per instantiation: largest dynamic shared-memory size opted into so far
-#ifdef PGS_STAGE_LANES
-  const int smem = (int)smem_bytes<V, R>(obs_dim_of(h->cfg), h->cfg.decision_repeat) + PGS_STAGE_MAX_LANES * (int)sizeof(PgdLane);
-#else
   const int smem = (int)smem_bytes<V, R>(obs_dim_of(h->cfg), h->cfg.decision_repeat);
-#endif
   if (smem > configured) {
     CU(cudaFuncSetAttribute(pgd_step_kernel<V, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = smem;
   }
-  const int grid = (env_end - env_begin + PGS_LANES - 1) / PGS_LANES;
-  pgd_step_kernel<V, R><<<grid, R * 32, smem, st>>>(T, S, h->cfg, mode, h->call_index, env_begin, env_end, actions, obs, reward,
-                                                       done, info);
+  // Environments per CTA: 32 (all lanes).  Fewer (an even number, so that the CTA's rows start on a 16-byte boundary)
+  // would make the grid a whole number of waves -- 2 048 CTAs on 592 slots are 3.46 -- but the CTAs do not run in
+  // lock-step and the step time follows the NUMBER of CTAs (profiles/r02y_sweep.log: 28 per CTA is 12 % slower).
+  const int n = env_end - env_begin;
+  int epc = PGS_LANES;
+  const char* fixed = getenv("PGDRIVE_B200_ENVS_PER_CTA");  // experiments (tools/gpu_epc_call.sh)
+  if (fixed) epc = atoi(fixed);
+  if (epc < 2 || epc > PGS_LANES) epc = PGS_LANES;
+  const int grid = (n + epc - 1) / epc;
+  pgd_step_kernel<V, R><<<grid, R * 32, smem, st>>>(T, S, h->cfg, mode, h->call_index, env_begin, env_end, epc, actions, obs,
+                                                       reward, done, info);
   return 0;
 }
 

@@ -8,6 +8,7 @@ import pytest
 V0 = dict(type="block_num", config=3, lane_num=3, lane_width=3.5, exit_length=50)
 SPAWN = ((">", ">>", 0), 5.0, 0.0)
 ROLES = [4]  # warps per CTA emulated by the host build (test_role_counts varies it)
+ENVS_PER_CTA = [32]  # lanes of a warp that carry an environment (the launcher picks fewer to fill whole waves)
 
 
 def _tables(seeds, density=0.1):
@@ -19,7 +20,7 @@ def _pair(T, n, **cfg):
     from oracle.oracle import Oracle
     from oracle.step_host import HostStep
     slots = 16 if T["max_slots"] <= 16 else 32
-    return Oracle(T, n, num_slots=slots, **cfg), HostStep(T, n, roles=ROLES[0], num_slots=slots, **cfg)
+    return Oracle(T, n, num_slots=slots, **cfg), HostStep(T, n, roles=ROLES[0], envs_per_cta=ENVS_PER_CTA[0], num_slots=slots, **cfg)
 
 
 def _actions(rs, n, mode):
@@ -252,6 +253,27 @@ def test_role_counts(roles):
         b.close()
     finally:
         ROLES[0] = 4
+
+
+@pytest.mark.parametrize("epc", [28, 6])
+def test_environments_per_cta(epc):
+    """pgd_launch_step gives a CTA fewer than 32 environments when that fills whole waves of the GPU; the unused lanes of
+    every warp then stay idle through all phases (work list, named barrier, lidar scatter, row store)."""
+    ENVS_PER_CTA[0] = epc
+    try:
+        T = _tables(range(1000, 1020))
+        n = 70
+        a, b = _pair(T, n, auto_reset=True)
+        eps = [i % 20 for i in range(n)]
+        assert np.array_equal(a.reset(range(n), eps), b.reset(range(n), eps))
+        rs = np.random.RandomState(13)
+        for t in range(250):
+            act = _actions(rs, n, "lane" if t % 2 else "forward")
+            assert _same(a.step(act), b.step(act)), t
+        a.close()
+        b.close()
+    finally:
+        ENVS_PER_CTA[0] = 32
 
 
 def test_respawn_traffic_mode_all_traffic_awake_from_the_first_step():

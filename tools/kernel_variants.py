@@ -13,9 +13,7 @@ sys.path.insert(0, ROOT)
 VARIANTS = {  # step kernel (pgd_step_kernel.cu): warps per CTA, resident CTAs the register budget is set for, L2 hints
     "clk": ["-DPGS_ROLES=4", "-DPGS_MIN_CTAS=4", "-DPGS_PHASE_CLOCKS"],
     "r4c3": ["-DPGS_ROLES=4", "-DPGS_MIN_CTAS=3"],
-    # map-staging experiment (run with BLOCKED=1: environments assigned to seeds in blocks of 32, one map per CTA)
-    "plain": ["-DPGS_PLAIN_LOADS", "-DPGS_MIN_CTAS=3"],
-    "stage": ["-DPGS_PLAIN_LOADS", "-DPGS_STAGE_LANES", "-DPGS_MIN_CTAS=3"],
+    "outline": ["-DPGS_OUTLINE_HELPERS"],
 }
 
 

@@ -26,12 +26,19 @@ e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / K
 print("%s actions=%s: %.4f ms/step, %.1f M env-steps/s" % (os.path.basename(os.environ.get("PGDRIVE_B200_LIB", "") or "default"), mode, ms, n / ms / 1e3))
 
-if hasattr(env.engine.lib, "pgd_debug_phase_clocks"):  # diagnostic build (-DV3_PHASE_CLOCKS): cycles per phase, thread 0
+if hasattr(env.engine.lib, "pgd_debug_phase_clocks"):  # diagnostic build (-DPGS_PHASE_CLOCKS)
     import ctypes
-    buf = (ctypes.c_ulonglong * 16)()
+    buf = (ctypes.c_ulonglong * 32)()
+    env.engine.lib.pgd_debug_phase_clocks(buf, 1)  # forget warm-up and the timed steps above
+    for t in range(K): env.step(a[(W + K + t) % NA])
+    torch.cuda.synchronize()
     env.engine.lib.pgd_debug_phase_clocks(buf, 1)
-    names = ["init", "A", "wait A", "B + wait", "C", "wait C", "fill", "D", "wait D", "F", "wait F", "L", "store"]
-    ctas = (n + 31) // 32 * (W + K + 1)
+    names = ["init", "A", "wait A", "B + wait", "X (role 0)", "-", "-", "wait X", "F", "wait F", "L", "N", "store"]
+    ctas = (n + 31) // 32 * K
     tot = sum(buf[:13])
     print("phase clocks (cycles per CTA, thread 0):", ", ".join("%s %.0f" % (nm, buf[i] / ctas) for i, nm in enumerate(names)),
-          "| total %.0f" % (tot / ctas))
+          "| total %.0f" % (tot / ctas), end=" || ")
+    nt, nsc = max(buf[16 + 10], 1), max(buf[16 + 11], 1)
+    parts = ["take", "load", "IDM", "wait ego + sub-step setup", "sub-steps", "localise", "store"]
+    print("traffic warp 1, cycles per batch of <= 32 vehicles:", ", ".join("%s %.0f" % (nm, buf[16 + i] / nt) for i, nm in enumerate(parts)),
+          "| awake vehicles per CTA %.1f, vehicle batches of warp 1 per CTA %.2f" % (buf[24] / ctas, nt / ctas))
