@@ -758,30 +758,43 @@ PGS_HD void idm_act(const Smem<V, R>& sm, const Tables& T, const float* obs, int
   int front[3], back[3];
   float fdist[3], bdist[3];
   const uint32_t others = alive & ~(1u << s);
+  // FrontBackObjects.get_find_front_back_objs (:83-133) for the three candidate lanes in ONE pass over the other vehicles
+  // (per candidate lane the reference's loop, vehicle by vehicle in ascending slot order)
+  bool on[3], found_front[3], found_back[3];
+  float cur_long[3], left_long[3], lsx[3], lsy[3], lex[3], ley[3];
 #pragma unroll
-  for (int i = 0; i < 3; ++i) {  // FrontBackObjects.get_find_front_back_objs (:83-133)
+  for (int i = 0; i < 3; ++i) {
     front[i] = back[i] = -1;
     fdist[i] = bdist[i] = PGS_IDM_MAX_LONG;
-    if (cand[i] < 0) continue;
+    found_front[i] = found_back[i] = false;
+    on[i] = cand[i] >= 0;
+    cur_long[i] = left_long[i] = lsx[i] = lsy[i] = lex[i] = ley[i] = 0.0f;
+    if (!on[i]) continue;
     const PgdLane l = (i == 1) ? rl : load_rec(lanes + cand[i]);
-    float cur_long, lat;
-    lane_local(l, q.x, q.y, cur_long, lat);
-    const float left_long = l.length - cur_long;
-    bool found_front = false, found_back = false;
+    float lat;
+    lane_local(l, q.x, q.y, cur_long[i], lat);
+    left_long[i] = l.length - cur_long[i];
+    lsx[i] = l.sx; lsy[i] = l.sy; lex[i] = l.ex; ley[i] = l.ey;
+  }
 #pragma unroll 1
-    for (uint32_t m = others; m; m &= m - 1) {  // ascending slot order, like the oracle's object list
-      const int j = ctz32(m);
-      const float ddx = P.x[j][ln] - q.x, ddy = P.y[j][ln] - q.y;
-      if (!(ddx * ddx + ddy * ddy < PGS_LIDAR_RANGE * PGS_LIDAR_RANGE)) continue;
-      if (lf_lane(P.lf[j][ln]) == cand[i]) {
-        const float lg = I.olong[j][ln] - cur_long;
-        if (fdist[i] > lg && lg > 0.0f) { fdist[i] = lg; front[i] = j; found_front = true; }
-        if (lg < 0.0f && fabsf(lg) < bdist[i]) { bdist[i] = fabsf(lg); back[i] = j; found_back = true; }
-      } else if (!found_front && precedes(l.ex, l.ey, I.lsx[j][ln], I.lsy[j][ln])) {
-        const float lg = I.olong[j][ln] + left_long;
+  for (uint32_t m = others; m; m &= m - 1) {  // ascending slot order, like the oracle's object list
+    const int j = ctz32(m);
+    const float ddx = P.x[j][ln] - q.x, ddy = P.y[j][ln] - q.y;
+    if (!(ddx * ddx + ddy * ddy < PGS_LIDAR_RANGE * PGS_LIDAR_RANGE)) continue;
+    const int lane_j = lf_lane(P.lf[j][ln]);
+    const float olong_j = I.olong[j][ln];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      if (!on[i]) continue;
+      if (lane_j == cand[i]) {
+        const float lg = olong_j - cur_long[i];
+        if (fdist[i] > lg && lg > 0.0f) { fdist[i] = lg; front[i] = j; found_front[i] = true; }
+        if (lg < 0.0f && fabsf(lg) < bdist[i]) { bdist[i] = fabsf(lg); back[i] = j; found_back[i] = true; }
+      } else if (!found_front[i] && precedes(lex[i], ley[i], I.lsx[j][ln], I.lsy[j][ln])) {
+        const float lg = olong_j + left_long[i];
         if (fdist[i] > lg && lg > 0.0f) { fdist[i] = lg; front[i] = j; }
-      } else if (!found_back && precedes(I.lex[j][ln], I.ley[j][ln], l.sx, l.sy)) {
-        const float lg = I.llen[j][ln] - I.olong[j][ln] + cur_long;
+      } else if (!found_back[i] && precedes(I.lex[j][ln], I.ley[j][ln], lsx[i], lsy[i])) {
+        const float lg = I.llen[j][ln] - olong_j + cur_long[i];
         if (bdist[i] > lg) { bdist[i] = lg; back[i] = j; }
       }
     }
@@ -880,7 +893,10 @@ PGS_HD void idm_act(const Smem<V, R>& sm, const Tables& T, const float* obs, int
 }
 
 // ---- localisation through the bucket grid (navigation.py:155-344, scene_utils.py:138-185) ------------------------
-struct ScanOut { int b_any, b_cur, b_next; uint32_t flags; };
+struct ScanOut {  // lowest box id (and its lane) over the point, per class of road; PGD_F_* contacts of the chassis
+  int b_any, b_cur, b_next, l_any, l_cur, l_next;
+  uint32_t flags;
+};
 struct GridRef { float x0, y0, inv_cell; int nx, ny, cell_off, entry_off; };  // bucket grid of one map
 template <int V, int R>
 PGS_HD GridRef grid_of(const Smem<V, R>& sm, int e) {
@@ -895,6 +911,7 @@ template <bool EGO>
 PGS_HD void bucket_scan(const GridRef& gr, const PgdLane* lanes, const PgdBox* boxes, const Tables& T, float x, float y,
                        float hc, float hs, float hl, float hw, int cur_road, int next_road, ScanOut& out) {
   out.b_any = out.b_cur = out.b_next = INT_MAX;
+  out.l_any = out.l_cur = out.l_next = -1;
   out.flags = 0;
   const int32_t* ent = T.cell_entries + gr.entry_off;
   const Rect er = {x, y, hc, hs, hl, hw};
@@ -932,9 +949,9 @@ PGS_HD void bucket_scan(const GridRef& gr, const PgdLane* lanes, const PgdBox* b
         }
         if (!(dot > 0.0f)) continue;
         const int lroad = ldg(&l->road);
-        if (b < out.b_any) out.b_any = b;
-        if (lroad == cur_road && b < out.b_cur) out.b_cur = b;
-        if (lroad == next_road && b < out.b_next) out.b_next = b;
+        if (b < out.b_any) { out.b_any = b; out.l_any = g.lane; }
+        if (lroad == cur_road && b < out.b_cur) { out.b_cur = b; out.l_cur = g.lane; }
+        if (lroad == next_road && b < out.b_next) { out.b_next = b; out.l_next = g.lane; }
       } else if (EGO) {
         const Rect r = {g.cx, g.cy, g.ux, g.uy, g.hl, g.hw};
         if (!rect_overlap(er, r)) continue;
@@ -943,7 +960,9 @@ PGS_HD void bucket_scan(const GridRef& gr, const PgdLane* lanes, const PgdBox* b
                    : g.kind == PGD_BOX_BROKEN ? PGD_F_ON_BROKEN : PGD_F_CRASH_SIDEWALK;
       }
     }
-    if (!EGO && bb[3] < 0) break;  // ran into the flagged part (or the end) of the cell
+    // traffic stops at the flagged part (or the end) of the cell -- and at the first box on its current road: the ids
+    // ascend within the cell (include/pgd_tables.h) and a box on the current road wins over every other class
+    if (!EGO && (bb[3] < 0 || out.b_cur != INT_MAX)) break;
   }
 }
 
@@ -953,9 +972,9 @@ template <int V, int R>
 PGS_HD void after_scan(const Smem<V, R>& sm, const Tables& T, int e, const PgdSlot& t, const ScanOut& sc, float x,
                       float y, int& lane, int& ck0, int& ck1, bool& on_lane) {
   const int32_t* rnodes = T.route_nodes + t.route_off;
-  const int nb = sc.b_cur != INT_MAX ? sc.b_cur : (sc.b_next != INT_MAX ? sc.b_next : sc.b_any);
-  on_lane = nb != INT_MAX;
-  if (on_lane) lane = ldg(&boxes_of(sm, T, e)[nb].lane);
+  const int nl = sc.b_cur != INT_MAX ? sc.l_cur : (sc.b_next != INT_MAX ? sc.l_next : sc.l_any);
+  on_lane = nl >= 0;
+  if (on_lane) lane = nl;
   if (ck0 != ck1) {
     const PgdLane l = load_rec(lanes_of(sm, T, e) + lane);
     float lon, lat;
@@ -1146,13 +1165,16 @@ PGS_HD void phase_x_items(Smem<V, R>& sm, const Thr<V, R>& th, const Tables& T, 
   const int ns = cfg.decision_repeat < PGS_MAX_SUBSTEPS ? cfg.decision_repeat : PGS_MAX_SUBSTEPS;
   const int n_work = sm.n_work;
   bool traj_ready = false;  // warp-uniform
+  // Batches of `per` vehicles, dealt round-robin to the traffic warps.  A list that fits one pass is split evenly over
+  // them: the time of a batch is the union of its lanes' paths through IDM and localisation, whatever their number.
+  const int per = n_work >= (R - 1) * PGS_LANES ? PGS_LANES : (n_work + R - 2) / (R - 1);
   PGS_ITEM_CLK_BEGIN
   PGS_ITEM_COUNT(8, n_work);
 #pragma unroll 1
-  for (int base = (th.role - 1) * PGS_LANES; base < n_work; base += (R - 1) * PGS_LANES) {
+  for (int base = (th.role - 1) * per; base < n_work; base += (R - 1) * per) {
     PGS_ITEM_COUNT(10, 1);
     PGS_ITEM_CLK(0);
-    const bool have = base + th.lane < n_work;
+    const bool have = th.lane < per && base + th.lane < n_work;
     int e = 0, s = 0, cur_road = 0, next_road = -1;
     size_t gi = 0;
     Veh q;
