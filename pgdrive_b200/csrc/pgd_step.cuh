@@ -58,6 +58,8 @@
 #define PGS_ITEM_CLK_BEGIN
 #define PGS_ITEM_CLK(i)
 #define PGS_ITEM_COUNT(i, n)
+#define PGS_EGO_CLK_BEGIN
+#define PGS_EGO_CLK(i)
 #endif
 
 namespace pgdstep {
@@ -1046,6 +1048,7 @@ PGS_HD void phase_x_ego(Smem<V, R>& sm, Thr<V, R>& th, const Tables& T, const St
   const int ln = th.lane;
   const int ns = cfg.decision_repeat < PGS_MAX_SUBSTEPS ? cfg.decision_repeat : PGS_MAX_SUBSTEPS;
   Veh& q = th.ego;
+  PGS_EGO_CLK_BEGIN
   if (th.valid) {
     if (th.stepping) {  // 5 x doPhysics(0.02) of the ego (base_engine.py:206-232), remembering every pose
       // A vehicle at rest with no yaw rate and no engine force is a fixed point of the sub-step (speed = max(0 - dv, 0)
@@ -1071,6 +1074,7 @@ PGS_HD void phase_x_ego(Smem<V, R>& sm, Thr<V, R>& th, const Tables& T, const St
     sm.ego_v[ln] = q.v;
   }
   named_arrive(PGS_BAR_TRAJ, R * 32);
+  PGS_EGO_CLK(13);
   if (th.valid) {
     // the record goes home now (phase F only adds what localisation changes: lane, checkpoints, on-lane flag), so that
     // the warp does not carry it through the rest of the step
@@ -1083,6 +1087,7 @@ PGS_HD void phase_x_ego(Smem<V, R>& sm, Thr<V, R>& th, const Tables& T, const St
     ScanOut sc;
     bucket_scan<true>(grid_of(sm, ln), lanes_of(sm, T, ln), boxes_of(sm, T, ln), T, q.x, q.y, q.hc, q.hs, q.hl, q.hw,
                       cur_road, next_road, sc);
+    PGS_EGO_CLK(14);
     bool on_lane;  // the start-of-step lane stays when no lane box is under the vehicle
     after_scan(sm, T, ln, t0, sc, q.x, q.y, q.lane, q.ck0, q.ck1, on_lane);
     q.vflags = on_lane ? (q.vflags | PGD_V_ON_LANE) : (q.vflags & ~PGD_V_ON_LANE);
@@ -1091,6 +1096,7 @@ PGS_HD void phase_x_ego(Smem<V, R>& sm, Thr<V, R>& th, const Tables& T, const St
     sm.ego_ck[ln] = q.ck0 | (q.ck1 << 16);
   }
   named_arrive(PGS_BAR_LOC, 2 * 32);
+  PGS_EGO_CLK(15);
   if (th.valid) reward_lookups(sm, th, T, cfg);
 }
 

@@ -31,6 +31,18 @@ __host__ __device__ __forceinline__ void pgs_item_add(int i, long long n) {
     iclk_ = now_;                           \
   } while (0)
 #define PGS_ITEM_COUNT(i, n) pgs_item_add(i, n)
+__host__ __device__ __forceinline__ void pgs_ego_add(int i, long long n) {
+#ifdef __CUDA_ARCH__
+  if (threadIdx.x == 0) atomicAdd(&g_pgs_clk[i], (unsigned long long)n);
+#endif
+}
+#define PGS_EGO_CLK_BEGIN long long eclk_ = pgs_item_now();
+#define PGS_EGO_CLK(i)                      \
+  do {                                     \
+    const long long now_ = pgs_item_now(); \
+    pgs_ego_add(i, now_ - eclk_);          \
+    eclk_ = now_;                          \
+  } while (0)
 #endif
 #include "pgd_step.cuh"
 

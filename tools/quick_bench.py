@@ -37,7 +37,8 @@ if hasattr(env.engine.lib, "pgd_debug_phase_clocks"):  # diagnostic build (-DPGS
     ctas = (n + 31) // 32 * K
     tot = sum(buf[:13])
     print("phase clocks (cycles per CTA, thread 0):", ", ".join("%s %.0f" % (nm, buf[i] / ctas) for i, nm in enumerate(names)),
-          "| total %.0f" % (tot / ctas), end=" || ")
+          "| total %.0f" % (tot / ctas),
+          "| role 0 in X: sub-steps %.0f, bucket scan %.0f, checkpoints %.0f, reward look-ups = the rest" % (buf[13] / ctas, buf[14] / ctas, buf[15] / ctas), end=" || ")
     nt, nsc = max(buf[16 + 10], 1), max(buf[16 + 11], 1)
     parts = ["take", "load", "IDM", "wait ego + sub-step setup", "sub-steps", "localise", "store"]
     print("traffic warp 1, cycles per batch of <= 32 vehicles:", ", ".join("%s %.0f" % (nm, buf[16 + i] / nt) for i, nm in enumerate(parts)),
