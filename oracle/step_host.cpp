@@ -45,8 +45,18 @@ static void run_vr(HostStep* h, int mode, const float* actions, float* obs, floa
 #define ALL(call) for (int r = 0; r < R; ++r) for (int l = 0; l < PGS_LANES; ++l) { Thr<V, R>& t = th[r][l]; (void)t; call; }
     ALL(phase_a(sm, t, h->S, h->cfg, actions, rows));
     ALL(phase_b(sm, t, h->T, rows));
-    ALL(phase_x(sm, t, h->T, h->S, h->cfg, rows, traj));  // role 0 (all its lanes) runs first: trajectories, lanes
-    memset(rows, 0xff, (size_t)PGS_LANES * od * 4);       // what is left of IDM's data is garbage to the observation
+    // phase X: role 0 (all its lanes) first -- trajectories, lanes --, then the traffic roles' first half, then (named
+    // barrier PGS_BAR_TRAFFIC on the device) their second half
+    for (int l = 0; l < PGS_LANES; ++l) phase_x(sm, th[0][l], h->T, h->S, h->cfg, od, rows, traj, vis);
+    for (int r = 1; r < R; ++r)
+      for (int l = 0; l < PGS_LANES; ++l) {
+        phase_x_items(sm, th[r][l], h->T, h->S, h->cfg, rows, traj);
+        phase_x_parked(sm, th[r][l], h->T, h->S, h->cfg, traj);
+      }
+    memset(rows, 0xff, (size_t)PGS_LANES * od * 4);  // what is left of IDM's data is garbage to the observation
+    memset(traj, 0xff, smem_bytes<V, R>(od, h->cfg.decision_repeat) - smem_tv_offset<V, R>(od));
+    for (int r = 1; r < R; ++r)
+      for (int l = 0; l < PGS_LANES; ++l) phase_x_tail(sm, th[r][l], h->T, h->cfg, od, rows, vis);
     ALL(phase_f(sm, t, h->T, h->S, h->cfg, mode, od, rows, vis, reward, done, info));
     ALL(phase_l_fill(sm, r, l, od, rows));
     ALL(phase_l(sm, h->T, h->S, r, l, env0, od, rows, vis));

@@ -215,7 +215,7 @@ def default_config():
 UNSUPPORTED_IF_CHANGED = {
     "num_agents": 1, "is_multi_agent": False, "IDM_agent": False,
     "use_render": False, "manual_control": False, "use_topdown": False, "offscreen_render": False,
-    "random_traffic": False, "record_episode": False,
+    "record_episode": False,
 }
 
 

@@ -363,6 +363,9 @@ struct Smem {
   Pub<V> p;
   F4 efin[PGS_LANES];                    // ego pose after the sub-steps (template pose when the episode restarts)
   int ego_lane[PGS_LANES];               // the ego's lane after its localisation (phase X, role 0)
+  I4 envi[PGS_LANES];                    // per-environment counters / sums after phase A, parked here until phase F
+  F4 envf[PGS_LANES];                    // (role 0 would carry them through phase X in registers, i.e. in local memory)
+  float last_h[PGS_LANES];               // the ego's heading at the start of the step
   int amask[PGS_LANES], pmask[PGS_LANES], crash[PGS_LANES];  // awake / parked traffic slots, chassis contact (or-ed in)
   float last_x[PGS_LANES], last_y[PGS_LANES], ego_travel[PGS_LANES], ego_h[PGS_LANES], ego_v[PGS_LANES],
       ego_hl[PGS_LANES], ego_hw[PGS_LANES];
@@ -406,9 +409,9 @@ struct Thr {  // what a thread keeps across the phases
   Veh ego;         // role 0
   uint32_t flags;  // role 0: PGD_F_* of the ego
   // computed during phase X by warps that would otherwise wait, written to the observation row in phase F (the rows'
-  // storage holds IDM's data until phase X ends): role 0 -- keep[0..3] = lateral distances (obs 0, 1), driving reward,
-  // route sign; role R-1 -- keep[0..9] navigation info, keep[10] heading difference
-  float keep[11];
+  // storage holds IDM's data until phase X ends), role 0: keep[0..9] navigation info, keep[10] heading difference,
+  // keep[11..14] lateral distances (obs 0, 1), driving reward, route sign
+  float keep[15];
   // loads that depend on nothing but the environment index, issued before the table look-ups they overlap with
   F4 pre_pose, pre_ctrl, pre_pidl;  // role 0: the ego's record
   I4 pre_nav, pre_misc;             // role 0 (all roles: pre_nav.x = the ego's lane, for the trigger test)
@@ -596,6 +599,9 @@ PGS_HD void phase_a(Smem<V, R>& sm, Thr<V, R>& th, const State& S, const PgdConf
       q.throttle = a1;
       if (th.trig >= 0) th.envi.y += 1;
     }
+    sm.envi[ln] = th.envi;
+    sm.envf[ln] = th.envf;
+    sm.last_h[ln] = th.fresh ? q.h : th.pre_pose.z;
     return;
   }
   uint32_t amask = 0, pmask = 0;
@@ -1010,13 +1016,13 @@ PGS_HD void localise_traffic(const Smem<V, R>& sm, const Tables& T, int e, const
 
 // ---- phase X: everything that moves -------------------------------------------------------------------------------
 /* Role 0: the ego's sub-steps (trajectory -> shared memory, announced to the traffic warps through named barrier 1),
- * then its localisation (navigation.py:155-211) and line / sidewalk contacts (base_vehicle.py:615-644), published for
- * the last role through named barrier 2, then the table look-ups of the reward (phase F only adds what depends on the
- * traffic: the crash flags).
- * Traffic roles: work items = the CTA's awake traffic in batches of 32, dealt round-robin -- IDM / PID against the
- * start-of-step copy of everybody's pose, then the sub-steps with the chassis test against the ego's trajectory,
- * localisation, removal, and the final pose into Smem::p; then the parked vehicles of the thread's own environment
- * against the ego's trajectory.  The last role finishes with the ego's navigation features.
+ * then its localisation (navigation.py:155-211) and line / sidewalk contacts (base_vehicle.py:615-644), then the table
+ * look-ups of the reward and of the navigation features (phase F only adds what depends on the traffic: the crash
+ * flags).
+ * Traffic roles: work items = the CTA's awake traffic in batches, dealt round-robin -- IDM / PID against the start-of-step
+ * copy of everybody's pose, then the sub-steps with the chassis test against the ego's trajectory, localisation, removal,
+ * and the final pose into Smem::p; then the parked vehicles of the thread's own environment against the ego's
+ * trajectory; then, once all traffic warps are there (named barrier 2), the ego's neighbour features and lidar windows.
  * An item touches nothing another item reads, so the order in which the warps work does not matter. */
 PGS_HD void named_arrive(int id, int threads) {  // all 32 lanes of the warp
 #ifdef __CUDA_ARCH__
@@ -1039,8 +1045,12 @@ template <int V, int R>
 PGS_HD void reward_lookups(const Smem<V, R>& sm, Thr<V, R>& th, const Tables& T, const PgdConfig& cfg);
 template <int V, int R>
 PGS_HD void navi_lookups(const Smem<V, R>& sm, Thr<V, R>& th, const Tables& T);
+template <int V, int R>
+PGS_HD void task_neighbours(const Smem<V, R>& sm, const Thr<V, R>& th, const Tables& T, const PgdConfig& cfg, float* obs);
+template <int V, int R>
+PGS_HD void task_lidar_windows(Smem<V, R>& sm, const Thr<V, R>& th, const Tables& T, VisPtr vis);
 #define PGS_BAR_TRAJ 1  // role 0 arrives, the R - 1 traffic warps wait: the egos' trajectories are in shared memory
-#define PGS_BAR_LOC 2   // role 0 arrives, role R - 1 waits: the egos' lanes / checkpoints are in shared memory
+#define PGS_BAR_TRAFFIC 2  // the R - 1 traffic warps among themselves: every vehicle has its final pose
 
 template <int V, int R>
 PGS_HD void phase_x_ego(Smem<V, R>& sm, Thr<V, R>& th, const Tables& T, const State& S, const PgdConfig& cfg,
@@ -1095,9 +1105,11 @@ PGS_HD void phase_x_ego(Smem<V, R>& sm, Thr<V, R>& th, const Tables& T, const St
     sm.ego_lane[ln] = q.lane;
     sm.ego_ck[ln] = q.ck0 | (q.ck1 << 16);
   }
-  named_arrive(PGS_BAR_LOC, 2 * 32);
   PGS_EGO_CLK(15);
-  if (th.valid) reward_lookups(sm, th, T, cfg);
+  if (th.valid) {
+    reward_lookups(sm, th, T, cfg);
+    navi_lookups(sm, th, T);
+  }
 }
 
 /* Parked traffic of the thread's own environment (the slots this role published in phase A, whose drop counters it
@@ -1236,18 +1248,30 @@ PGS_HD void phase_x_items(Smem<V, R>& sm, const Thr<V, R>& th, const Tables& T, 
 }
 
 template <int V, int R>
-PGS_HD void phase_x(Smem<V, R>& sm, Thr<V, R>& th, const Tables& T, const State& S, const PgdConfig& cfg,
-                   const float* obs, TrajPtr traj) {
+PGS_HD void phase_x_tail(Smem<V, R>& sm, Thr<V, R>& th, const Tables& T, const PgdConfig& cfg, int obs_dim,
+                        float* obs_rows, VisPtr vis) {
+  // the traffic has its final poses, IDM's data and the ego's trajectory (whose storage the rows and the list of visible
+  // chassis take over) are dead: what only needs the traffic and the ego's final pose starts now, while role 0 is
+  // still busy with the ego's look-ups
+  if (th.valid) {
+    if (th.role == 1) task_neighbours(sm, th, T, cfg, obs_rows + (size_t)th.lane * obs_dim);
+    if (th.role == (R > 2 ? 2 : 1)) task_lidar_windows(sm, th, T, vis);
+  }
+}
+
+/* Phase X of one thread.  (The host emulation runs the traffic roles' two halves one after the other over all of them,
+ * oracle/step_host.cpp: named barrier PGS_BAR_TRAFFIC.) */
+template <int V, int R>
+PGS_HD void phase_x(Smem<V, R>& sm, Thr<V, R>& th, const Tables& T, const State& S, const PgdConfig& cfg, int obs_dim,
+                   float* obs_rows, TrajPtr traj, VisPtr vis) {
   if (th.role == 0) {
     phase_x_ego(sm, th, T, S, cfg, traj);
     return;
   }
-  phase_x_items(sm, th, T, S, cfg, obs, traj);
+  phase_x_items(sm, th, T, S, cfg, obs_rows, traj);
   phase_x_parked(sm, th, T, S, cfg, traj);
-  if (th.role == R - 1) {
-    named_wait(PGS_BAR_LOC, 2 * 32);
-    if (th.valid) navi_lookups(sm, th, T);
-  }
+  named_wait(PGS_BAR_TRAFFIC, (R - 1) * 32);
+  phase_x_tail(sm, th, T, cfg, obs_dim, obs_rows, vis);
 }
 
 // ---- phase F: ego bookkeeping, one task per role ---------------------------------------------------------------------
@@ -1258,7 +1282,7 @@ PGS_HD int obs_dim_of(const PgdConfig& cfg) {
 
 /* Role 0 while the traffic moves (phase X): the table look-ups of the ego's bookkeeping -- route distances, arrival,
  * reward geometry (base_vehicle.py:383-388,738-745; pgdrive_env.py:162-258).  What phase F needs of them stays in
- * registers: th.flags, th.keep[0..3]. */
+ * registers: th.flags, th.keep[11..14]. */
 template <int V, int R>
 PGS_HD void reward_lookups(const Smem<V, R>& sm, Thr<V, R>& th, const Tables& T, const PgdConfig& cfg) {
   const int ln = th.lane;
@@ -1305,10 +1329,10 @@ PGS_HD void reward_lookups(const Smem<V, R>& sm, Thr<V, R>& th, const Tables& T,
   float lateral_factor = 1.0f;
   if (cfg.use_lateral) lateral_factor = clipf(1.0f - 2.0f * fabsf(lat_now) / lane_width, 0.0f, 1.0f);
   th.flags = flags;
-  th.keep[0] = to_left;
-  th.keep[1] = to_right;
-  th.keep[2] = cfg.driving_reward * (long_now - long_last) * lateral_factor * sign;
-  th.keep[3] = sign;
+  th.keep[11] = to_left;
+  th.keep[12] = to_right;
+  th.keep[13] = cfg.driving_reward * (long_now - long_last) * lateral_factor * sign;
+  th.keep[14] = sign;
 }
 
 /* task 0 (role 0): what the traffic decides -- crash flags -- then reward / cost / done, the ego's state features, info,
@@ -1320,7 +1344,9 @@ PGS_HD void task_reward(Smem<V, R>& sm, Thr<V, R>& th, const Tables& T, const St
   struct {  // what is left of the ego in registers (phase_x_ego stored the record)
     float x, y, h, v, steer, throttle;
   } ego = {sm.efin[ln].x, sm.efin[ln].y, sm.ego_h[ln], sm.ego_v[ln], th.ego.steer, th.ego.throttle};
-  const float last_h = th.fresh ? ego.h : th.pre_pose.z;
+  const float last_h = sm.last_h[ln];
+  th.envi = sm.envi[ln];
+  th.envf = sm.envf[ln];
   const int n_first = cfg.n_side > 0 ? cfg.n_side : 2;
   float* const st = obs + n_first - 2;
   if (cfg.random_agent_model) {  // obs/state_obs.py:103-105: LENGTH / MAX_LENGTH, WIDTH / MAX_WIDTH (base_vehicle.py:83-84)
@@ -1334,7 +1360,7 @@ PGS_HD void task_reward(Smem<V, R>& sm, Thr<V, R>& th, const Tables& T, const St
   if (crash) flags |= PGD_F_CRASH_VEHICLE;
   if (crash_object) flags |= PGD_F_CRASH_OBJECT;
   const bool out_of_road = (flags & PGD_F_OUT_OF_ROAD) != 0;
-  const float to_left = th.keep[0], to_right = th.keep[1];
+  const float to_left = th.keep[11], to_right = th.keep[12];
 
   const float sp = kmh(ego.v);
   if (cfg.n_side <= 0) {
@@ -1351,8 +1377,8 @@ PGS_HD void task_reward(Smem<V, R>& sm, Thr<V, R>& th, const Tables& T, const St
   float r = 0.0f, step_reward = 0.0f, cost = 0.0f, step_energy = 0.0f;
   int is_done = 0;
   if (!th.fresh) {  // envs/pgdrive_env.py:162-258
-    const float sign = th.keep[3];
-    r += th.keep[2];  // driving_reward * (long_now - long_last) * lateral_factor * sign
+    const float sign = th.keep[14];
+    r += th.keep[13];  // driving_reward * (long_now - long_last) * lateral_factor * sign
     r += cfg.speed_reward * (sp / PGS_MAX_SPEED_KMH) * sign;
     step_reward = r;
     if (flags & PGD_F_ARRIVE_DEST) r = cfg.success_reward;
@@ -1395,7 +1421,7 @@ PGS_HD void task_reward(Smem<V, R>& sm, Thr<V, R>& th, const Tables& T, const St
   S.misc[th.env].z = th.ego.vflags;
 }
 
-/* Role R-1 at the end of phase X: navigation info of the two checkpoints (navigation.py:213-260) + heading_diff
+/* Role 0 at the end of phase X: navigation info of the two checkpoints (navigation.py:213-260) + heading_diff
  * (base_vehicle.py:433-458) -> th.keep[0..10]; task_navi writes them to the row in phase F. */
 template <int V, int R>
 PGS_HD void navi_lookups(const Smem<V, R>& sm, Thr<V, R>& th, const Tables& T) {
@@ -1589,12 +1615,12 @@ PGS_HD void phase_f(Smem<V, R>& sm, Thr<V, R>& th, const Tables& T, const State&
                    int obs_dim, float* obs_rows, VisPtr vis, float* reward, uint8_t* done, PgdInfo* info) {
   if (!th.valid) return;
   float* obs = obs_rows + (size_t)th.lane * obs_dim;
-  // role 0 and role R-1 hold what they looked up during phase X; the two tasks that need the traffic's final poses go
-  // to role 1 and role 2 (or the last one)
-  if (th.role == 0) task_reward(sm, th, T, S, cfg, mode, obs, reward, done, info);
-  if (th.role == R - 1) task_navi(th, cfg, obs);
-  if (th.role == 1) task_neighbours(sm, th, T, cfg, obs);
-  if (th.role == (R > 2 ? 2 : 1)) task_lidar_windows(sm, th, T, vis);
+  // role 0 holds what it looked up during phase X (the neighbours and the lidar windows were done at its
+  // end, phase_x_tail); nothing here touches the lidar part of the rows, which phase L fills without a barrier in between
+  if (th.role == 0) {
+    task_reward(sm, th, T, S, cfg, mode, obs, reward, done, info);
+    task_navi(th, cfg, obs);
+  }
   if (cfg.n_side > 0 || cfg.n_lane_line > 0) task_detectors(sm, th, T, cfg, obs);
 }
 

@@ -115,15 +115,14 @@ __global__ void __launch_bounds__(R * 32, PGS_MIN_CTAS) pgd_step_kernel(Tables T
   phase_b(sm, th, T, rows);
   __syncthreads();
   PGS_CLK(3);
-  phase_x(sm, th, T, S, cfg, rows, traj);
+  phase_x(sm, th, T, S, cfg, obs_dim, rows, traj, vis);
   PGS_CLK(4);
   PGS_CLK(5);
   PGS_CLK(6);
-  __syncthreads();  // everything has moved; the IDM look-up data that shared the rows' storage is dead
+  __syncthreads();  // everything has moved, the ego's look-ups are done
   PGS_CLK(7);
   phase_f(sm, th, T, S, cfg, mode, obs_dim, rows, vis, reward, done, info);
   PGS_CLK(8);
-  __syncthreads();
   PGS_CLK(9);
   phase_l_fill(sm, role, lane, obs_dim, rows);
   __syncwarp();

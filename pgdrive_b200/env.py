@@ -116,6 +116,7 @@ def _seed_tables(args):
     random_agent = bool(args[5]) if len(args) > 5 else False
     traffic_mode = args[6] if len(args) > 6 else "trigger"
     accident_prob = float(args[7]) if len(args) > 7 else 0.0
+    traffic_rs = args[8] if len(args) > 8 else None  # random_traffic: the traffic manager's stream lives across resets
     kw = dict(lane_num=mc["lane_num"], lane_width=mc["lane_width"], exit_length=mc["exit_length"])
     if stored is not None:  # restored from a map file: no block search (pg_map.py:48-71)
         pgmap = mapgen.build_from_sequence(seed, stored, **kw)
@@ -129,7 +130,7 @@ def _seed_tables(args):
     mid = ts.add_map(pgmap)
     lane, lon, lat = spawn
     ts.add_episode(pgmap, mid, episode.make_episode(pgmap, seed, density, tuple(lane), random_agent, traffic_mode,
-                                                      accident_prob), tuple(lane), lon, lat)
+                                                      accident_prob, traffic_rs), tuple(lane), lon, lat)
     return ts.finish()
 
 
@@ -300,6 +301,10 @@ class VecPGDriveEnv:
         self.config = post_process_config(merged.update(config or {}, allow_add_new_key=False))
         check_supported(self.config)
         cfg = self.config
+        if cfg["random_traffic"]:
+            # the environments of a seed share one traffic template in HBM; PGDriveEnv (one environment) redraws it at
+            # every reset like the reference
+            raise NotImplementedError("random_traffic needs per-reset traffic templates: use PGDriveEnv")
         self.num_envs = int(cfg["num_envs"])
         self.start_seed, self.env_num = int(cfg["start_seed"]), int(cfg["environment_num"])
         self.map_config = parse_map_config(cfg)
@@ -612,6 +617,7 @@ class PGDriveEnv:
         self._engine = None
         self._seed = None
         self._rs = np.random.RandomState()
+        self._traffic_rs = np.random.RandomState() if self.config["random_traffic"] else None
         self.episode_steps = 0
         self._obs = self._reward = self._done = self._info = None
 
@@ -620,12 +626,17 @@ class PGDriveEnv:
         """Tables of ``seed`` (built once, kept on the host like the reference's map cache, map_manager.py:98-155) and an
         engine that holds exactly the tables of the CURRENT seed: a visit uploads one map (tens of KB), not every map
         seen so far."""
-        if seed not in self._parts:
+        if seed not in self._parts or self._traffic_rs is not None:
+            # random_traffic (traffic_manager.py:348-350): the traffic manager is not re-seeded at reset, every visit of a
+            # map draws new traffic from one stream -- the seed's tables are rebuilt and uploaded again
             mc = seed_map_config(self.map_config, seed, self.config["random_lane_width"], self.config["random_lane_num"])
             self._parts[seed] = _seed_tables((seed, mc, self.config["traffic_density"], self._spawn,
                                               (self._stored or {}).get(seed), bool(self.config["random_agent_model"]),
-                                              self.config["traffic_mode"], accident_prob_of(self.config)))
+                                              self.config["traffic_mode"], accident_prob_of(self.config),
+                                              self._traffic_rs))
             self._episode_of_seed[seed] = 0
+            if self._traffic_rs is not None:
+                self._loaded_seed = None
         part = self._parts[seed]
         slots = pick_slots(int(part["max_slots"]))
         if self._engine is not None and self._engine.num_slots < slots:

@@ -171,15 +171,20 @@ def respawn_lanes(pgmap):
 
 
 def make_episode(pgmap, seed, density=0.1, spawn_lane=(">", ">>", 0), random_agent_model=False, traffic_mode="trigger",
-                 accident_prob=0.0):
+                 accident_prob=0.0, traffic_rs=None):
     """``traffic_mode`` (traffic_manager.py:21-27): "trigger" and "hybrid" create every block's vehicles once and wake
     them when the ego reaches the block (in this version of the reference the two are the same code path, :63-69,
     :76-85); "respawn" fills every respawn lane with one vehicle per 10 m -- the density only switches traffic on --
-    and all of them drive from the first step (:224-237; the re-spawn itself is commented out at :100-105)."""
+    and all of them drive from the first step (:224-237; the re-spawn itself is commented out at :100-105).
+
+    ``traffic_rs``: the traffic manager's random stream.  None = a fresh stream of ``seed`` (the reference re-seeds every
+    manager at reset, base_engine.py:300-305); with ``random_traffic`` the traffic manager skips that re-seeding
+    (traffic_manager.py:348-350), i.e. the caller passes ONE generator that lives across resets."""
     if traffic_mode not in ("trigger", "hybrid", "respawn"):
         raise ValueError("No such mode named {}".format(traffic_mode))
     engine_rs = rng.seeded(seed)
-    traffic_rs = rng.seeded(seed)
+    if traffic_rs is None:
+        traffic_rs = rng.seeded(seed)
     ep = EpisodeTemplate(seed, density)
     # random_agent_model (manager/agent_manager.py:63-71, component/vehicle/vehicle_type.py:84-86): the agent manager's
     # own stream of the seed picks one of the five types with equal probability

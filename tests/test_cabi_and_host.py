@@ -208,7 +208,8 @@ def test_abi_argument_errors_without_a_gpu():
 
 def test_vec_env_rejects_unsupported_options():
     from pgdrive_b200 import VecPGDriveEnv
-    for cfg in (dict(random_traffic=True), dict(num_agents=2), dict(vehicle_config=dict(enable_reverse=True)),
+    for cfg in (dict(random_traffic=True),  # (PGDriveEnv supports it: the traffic templates are per reset there)
+                dict(num_agents=2), dict(vehicle_config=dict(enable_reverse=True)),
                 dict(vehicle_config=dict(overtake_stat=True)),
                 dict(vehicle_config=dict(lidar=dict(num_lasers=120))),
                 dict(vehicle_config=dict(side_detector=dict(num_lasers=500)))):

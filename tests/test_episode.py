@@ -114,3 +114,21 @@ def test_accident_scenes_match_reference():
                     (gv["type"], gv["lane"], gv["long"], gv["seed"], gv["idm_seed"]), s
                 assert v.params == gv["params"] and v.checkpoints == gv["checkpoints"], s
     assert kinds == {"TrafficCone", "TrafficWarning", "TrafficBarrier", "vehicle"}
+
+
+def test_random_traffic_draws_from_one_stream_across_resets():
+    """random_traffic (traffic_manager.py:348-350): the traffic manager is not re-seeded at reset, so every visit of a
+    map draws new traffic from the same generator; without it a seed always gives the same traffic
+    (test_random_engine.py:75-99 is the reference's own check of this)."""
+    import numpy as np
+    m = mapgen.generate_map(5)
+    fixed = [episode.make_episode(m, 5, 0.3, traffic_mode="respawn") for _ in range(2)]
+    place = lambda ep: [(v.lane, v.long, v.type) for _, vs in ep.block_vehicles for v in vs]
+    assert place(fixed[0]) == place(fixed[1])
+    rs = np.random.RandomState(123)
+    drawn = [place(episode.make_episode(m, 5, 0.3, traffic_mode="respawn", traffic_rs=rs)) for _ in range(4)]
+    assert all(len(d) == len(drawn[0]) > 0 for d in drawn)  # respawn mode: the number of slots per lane is fixed
+    assert len({tuple(d) for d in drawn}) == 4              # ... what stands on them is not
+    assert all(d != place(fixed[0]) for d in drawn)
+    # the ego does not depend on the traffic stream
+    assert episode.make_episode(m, 5, 0.3, traffic_rs=rs).ego_params == fixed[0].ego_params

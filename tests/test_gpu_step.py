@@ -131,3 +131,31 @@ def test_step_options_respawn_noise_increment_and_accident_scenes():
         seen = _free_run(env, ref, n, 400, hold_lane)
         assert seen & 2048, "no traffic object was touched"
         env.close()
+
+
+def test_random_traffic_redraws_the_traffic_at_every_reset():
+    """Mirrors test_random_engine.py:75-99: random_traffic + respawn mode, 20 resets of the same seed -- the traffic
+    vehicles do not stand where they stood the episode before."""
+    from pgdrive_b200 import PGDriveEnv
+    env = PGDriveEnv({"random_traffic": True, "traffic_mode": "respawn", "traffic_density": 0.3, "start_seed": 5})
+    try:
+        last, moved, has_traffic = None, 0, False
+        for i in range(20):
+            env.reset(force_seed=5)
+            st = env.get_state()["veh"][0]
+            n = int(env._parts[5]["max_slots"])
+            pos = [(float(v["x"]), float(v["y"])) for v in st[1:n]]
+            has_traffic = has_traffic or len(pos) > 0
+            if last is not None and len(pos) == len(last):
+                moved += sum(np.hypot(a[0] - b[0], a[1] - b[1]) >= 0.5 for a, b in zip(last, pos)) > 0
+            last = pos
+        assert has_traffic and moved >= 15
+        # without the option the same seed gives the same traffic
+        fixed = PGDriveEnv({"traffic_mode": "respawn", "traffic_density": 0.3, "start_seed": 5})
+        fixed.reset(force_seed=5)
+        a = fixed.get_state()["veh"][0][1:n]["x"].copy()
+        fixed.reset(force_seed=5)
+        assert np.array_equal(a, fixed.get_state()["veh"][0][1:n]["x"])
+        fixed.close()
+    finally:
+        env.close()
