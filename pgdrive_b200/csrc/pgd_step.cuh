@@ -176,7 +176,12 @@ PGS_HD_OUTLINE SinCos sincos_hd(float a) {
   } while (0)
 
 struct LonLat { float lon, lat; };
-PGS_HD_OUTLINE LonLat arc_local(float cx, float cy, float ph0, float dir, float radius, float x, float y) {
+#ifdef PGS_OUTLINE_ARC
+__host__ __device__ __noinline__
+#else
+PGS_HD_OUTLINE
+#endif
+LonLat arc_local(float cx, float cy, float ph0, float dir, float radius, float x, float y) {
   float dx = x - cx, dy = y - cy;
   float phi = pgd_atan2f(dy, dx);
   phi = ph0 + pgd_wrap_to_pi(phi - ph0);
@@ -415,7 +420,10 @@ struct Thr {  // what a thread keeps across the phases
   // loads that depend on nothing but the environment index, issued before the table look-ups they overlap with
   F4 pre_pose, pre_ctrl, pre_pidl;  // role 0: the ego's record
   I4 pre_nav, pre_misc;             // role 0 (all roles: pre_nav.x = the ego's lane, for the trigger test)
-  int pre_fl[MAXOWN], pre_air[MAXOWN];  // traffic roles: flags / drop counters of the slots they publish
+  // traffic roles: PGD_V_* flags (5 bits each) of the slots they publish, packed so that phase A's loop over them needs no
+  // register array, i.e. no unrolling (the kernel is as large as the instruction cache)
+  static constexpr int FLW = (MAXOWN + 11) / 12;  // 12 slots per word; one word for the 4 warps the kernel is built with
+  uint64_t pre_fl[FLW];
 };
 
 PGS_HD int imin(int a, int b) { return a < b ? a : b; }
@@ -493,6 +501,8 @@ PGS_HD void thread_init(Thr<V, R>& th, const Tables& T, const State& S, const Pg
   // everything below that only needs the environment index is requested now, so that it is in flight while the
   // episode -> map -> template look-ups (dependent loads) run
   th.pre_nav = S.nav[env];  // slot 0
+#pragma unroll
+  for (int w = 0; w < Thr<V, R>::FLW; ++w) th.pre_fl[w] = 0;
   if (role == 0) {
     th.envf = S.envf[env];
     th.pre_pose = S.pose[env]; th.pre_ctrl = S.ctrl[env]; th.pre_pidl = S.pidl[env]; th.pre_misc = S.misc[env];
@@ -502,8 +512,7 @@ PGS_HD void thread_init(Thr<V, R>& th, const Tables& T, const State& S, const Pg
       const int s = role + k * (R - 1);
       I4 m = {0, 0, 0, 0};
       if (s < V) m = S.misc[(size_t)s * cfg.num_envs + env];
-      th.pre_fl[k] = m.z;
-      th.pre_air[k] = m.y;
+      th.pre_fl[k / 12] |= (uint64_t)(m.z & 31) << (5 * (k % 12));
     }
   }
   const bool pending = th.envi.z == PGS_DONE_PENDING_RESET;
@@ -605,7 +614,7 @@ PGS_HD void phase_a(Smem<V, R>& sm, Thr<V, R>& th, const State& S, const PgdConf
     return;
   }
   uint32_t amask = 0, pmask = 0;
-#pragma unroll
+#pragma unroll 1
   for (int k = 0; k < Thr<V, R>::MAXOWN; ++k) {
     const int s = th.role + k * (R - 1);
     if (s >= V) break;
@@ -626,7 +635,7 @@ PGS_HD void phase_a(Smem<V, R>& sm, Thr<V, R>& th, const State& S, const PgdConf
       veh_store(q, S, gi);
       x = q.x; y = q.y; h = q.h; lane = q.lane; fl = q.vflags;
     } else {
-      fl = th.pre_fl[k];
+      fl = (int)(th.pre_fl[Thr<V, R>::FLW == 1 ? 0 : k / 12] >> (5 * (k % 12))) & 31;
       if (!(fl & PGD_V_ALIVE)) {
         P.lf[s][ln] = 0;
         P0.lf[s][ln] = 0;
@@ -1125,7 +1134,7 @@ PGS_HD void phase_x_parked(Smem<V, R>& sm, Thr<V, R>& th, const Tables& T, const
   const int ns = cfg.decision_repeat < PGS_MAX_SUBSTEPS ? cfg.decision_repeat : PGS_MAX_SUBSTEPS;
   int crash = 0;
   const uint32_t pmask = env_pmask(sm, ln);
-#pragma unroll
+#pragma unroll 1  // (one copy of the body: the kernel is as large as the instruction cache)
   for (int k = 0; k < Thr<V, R>::MAXOWN; ++k) {
     const int s = th.role + k * (R - 1);
     if (s >= sm.cx_n_slots[ln]) break;

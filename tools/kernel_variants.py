@@ -14,6 +14,7 @@ VARIANTS = {  # step kernel (pgd_step_kernel.cu): warps per CTA, resident CTAs t
     "clk": ["-DPGS_ROLES=4", "-DPGS_MIN_CTAS=4", "-DPGS_PHASE_CLOCKS"],
     "r4c3": ["-DPGS_ROLES=4", "-DPGS_MIN_CTAS=3"],
     "outline": ["-DPGS_OUTLINE_HELPERS"],
+    "arcout": ["-DPGS_OUTLINE_ARC"],
 }
 
 
