@@ -236,7 +236,7 @@ def run_own(args):
             # copy engine push: 707 GB/s into rank 0 at 8 GPUs against 653 GB/s for the kernel's own remote row stores
             # (profiles/r02q_bench_8gpu_*.json); at 2 GPUs the two tie
             gather_mode = "copy"
-        if gather_mode in ("peer", "copy"):
+        if gather_mode in ("peer", "copy", "sparse"):
             ok = torch.ones(1, dtype=torch.int32, device=dev)
             try:
                 peer = PeerGather(env, torch, dist, n, world, rank, mode=gather_mode)
@@ -324,13 +324,14 @@ def run_own(args):
             with torch.cuda.stream(side):
                 side.wait_event(ready_ev[i])
                 if not direct:
-                    peer.push(i)  # copy engine: local rows -> rank 0's buffer over NVLink
+                    peer.push(i)  # copy engine (or the packing kernel): local rows -> rank 0's buffer over NVLink
                     use_ev[i].record(side)
                     armed["use"][i] = True
                 peer.completion_barrier()
                 ar_ev[i].record(side)
                 armed["ar"][i] = True
                 if rank == 0:
+                    peer.expand(i)  # "sparse": packed rows of the other ranks -> the whole-batch buffer
                     if check:  # the consumer reads the whole gathered batch, every step
                         words_sum(verified if check == "verify" else consumed, whole[i])
                     use_ev[i].record(side)
@@ -549,6 +550,10 @@ def run_own(args):
                 "a side stream is the completion barrier; a buffer is rewritten only after rank 0 has read it",
         "copy": "kernel writes this rank's rows locally, the copy engine pushes them into rank 0's buffer (CUDA-IPC peer "
                 "mapping) on a side stream while the next step's kernel runs; 4-byte all-reduce as completion barrier",
+        "sparse": "kernel writes this rank's rows locally; on a side stream, while the next step's kernel runs, "
+                  "pgd_pack_rows stores them into rank 0's HBM (CUDA-IPC peer mapping) in the wire format head + 240-bit "
+                  "hit mask + beams that are not 1.0, and after the 4-byte all-reduce completion barrier rank 0's "
+                  "pgd_expand_rows restores them bit for bit into the whole-batch buffer, which rank 0 then reads",
     }.get(gather_mode, "in-place NCCL all-gather of obs/reward/done every step, double-buffered on a high-priority "
                        "side stream so that it overlaps the next step's kernel [%s]" % gather_mode)
     line = dict(
@@ -595,7 +600,7 @@ def main():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--envs", type=int, default=65536, help="environments per GPU (4096 = BASELINE.json configs[1])")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--gather", default="auto", choices=["auto", "peer", "copy", "nccl"],
+    ap.add_argument("--gather", default="auto", choices=["auto", "peer", "copy", "sparse", "nccl"],
                     help="N > 1: how rank 0 gets the whole batch (auto = copy: local rows pushed into rank 0's HBM by the "
                          "copy engine on a side stream while the next step's kernel runs; peer: rows stored by the step "
                          "kernel straight into rank 0's HBM; nccl: in-place all-gather, also the fall-back when peer mapping "

@@ -56,6 +56,11 @@ class PeerGather:
                      32 environments); no collective carries payload.
     ``mode="copy"``  the kernel writes local rows; ``push(i)`` copies them into rank 0's buffer with the copy engine
                      (enqueue it on a side stream: it overlaps the next step's kernel and the SMs are free meanwhile).
+    ``mode="sparse"`` like "copy", but the observation rows cross NVLink in the wire format of ``pgd_pack_rows``
+                     (head + 240-bit hit mask + the beams that are not 1.0: about a quarter of the bytes): ``push(i)``
+                     packs the local rows straight into a staging area in rank 0's HBM, ``expand(i)`` on rank 0
+                     restores them, bit for bit, into the whole-batch buffer.  With every result funnelled into one GPU
+                     the gather is bound by that GPU's NVLink ingress; this is what moves the bound.
 
     In both, ``completion_barrier`` (a 4-byte all-reduce) tells rank 0 that every rank's rows of that buffer have
     landed, and -- because rank 0 enqueues its reads of buffer i before it joins the barrier of step i + 1 -- a rank
@@ -63,14 +68,17 @@ class PeerGather:
     def __init__(self, env, torch, dist, n_local, world_size, rank, obs_dim=274, depth=2, mode="peer"):
         import ctypes as C
         from . import cabi
-        if mode not in ("peer", "copy"):
-            raise ValueError("mode must be 'peer' or 'copy'")
+        if mode not in ("peer", "copy", "sparse"):
+            raise ValueError("mode must be 'peer', 'copy' or 'sparse'")
         self.env, self.torch, self.dist, self.mode = env, torch, dist, mode
         self.n, self.world, self.rank, self.depth, self.obs_dim = n_local, world_size, rank, depth, obs_dim
         rows = world_size * n_local
         self.obs_bytes, self.rew_bytes = rows * obs_dim * 4, rows * 4
         self.done_bytes = (rows + 255) // 256 * 256
         self.stride = self.obs_bytes + self.rew_bytes + self.done_bytes
+        # "sparse": per buffer a staging area of packed rows (fixed stride obs_dim + 8 words) behind the dense batch
+        self.packed_bytes = (rows * (obs_dim + 8) * 4 + 255) // 256 * 256 if mode == "sparse" else 0
+        self.stride += self.packed_bytes
         e = env.engine
         self._lib, self._h = e.lib, e.h
         base = C.c_void_p()
@@ -85,7 +93,7 @@ class PeerGather:
         self.base = base.value
         self._flag = torch.zeros(1, dtype=torch.int32, device=e.device)
         self._local = None
-        if mode == "copy" and rank != 0:
+        if mode in ("copy", "sparse") and rank != 0:
             dev = e.device
             self._local = [(torch.empty((n_local, obs_dim), dtype=torch.float32, device=dev),
                             torch.empty(n_local, dtype=torch.float32, device=dev),
@@ -117,11 +125,35 @@ class PeerGather:
         """The rows this rank's kernel wrote for buffer ``i`` (local staging, or its rows of rank 0's buffer)."""
         return self.remote_views(i) if remote or self._local is None else self._local[i % self.depth]
 
+    def _packed_ptr(self, i, rank):
+        b = self.base + (i % self.depth) * self.stride + (self.stride - self.packed_bytes)
+        return b + rank * self.n * (self.obs_dim + 8) * 4
+
     def push(self, i):
-        """mode "copy", rank > 0: enqueue (current stream) the device-to-device copies of the local rows into rank 0's
-        buffer ``i`` -- contiguous, so the driver hands them to the copy engine."""
-        for dst, src in zip(self.remote_views(i), self._local[i % self.depth]):
+        """modes "copy" / "sparse", rank > 0: enqueue (current stream) the transfer of the local rows into rank 0's
+        buffer ``i``.  "copy": device-to-device copies -- contiguous, so the driver hands them to the copy engine.
+        "sparse": the observation rows are packed by a kernel that stores into rank 0's staging area."""
+        views, local = self.remote_views(i), self._local[i % self.depth]
+        if self.mode == "sparse":
+            from . import cabi
+            st = self.torch.cuda.current_stream(self.env.engine.device).cuda_stream
+            cabi.check(self._lib, self._lib.pgd_pack_rows(local[0].data_ptr(), self._packed_ptr(i, self.rank), self.n,
+                                                          self.obs_dim, st))
+            views, local = views[1:], local[1:]
+        for dst, src in zip(views, local):
             dst.copy_(src, non_blocking=True)
+
+    def expand(self, i):
+        """mode "sparse", rank 0, after the completion barrier of buffer ``i``: restore the rows of ranks 1.. from the
+        staging area into the whole-batch buffer (current stream)."""
+        if self.mode != "sparse" or self.world == 1:
+            return
+        assert self.rank == 0
+        from . import cabi
+        st = self.torch.cuda.current_stream(self.env.engine.device).cuda_stream
+        b = self.base + (i % self.depth) * self.stride
+        cabi.check(self._lib, self._lib.pgd_expand_rows(self._packed_ptr(i, 1), b + self.n * self.obs_dim * 4,
+                                                        (self.world - 1) * self.n, self.obs_dim, st))
 
     def completion_barrier(self):
         """Enqueue (on the current stream) a barrier after which rank 0 may read the buffer written last."""
@@ -141,7 +173,7 @@ class PeerGather:
         wants to touch every byte of the gathered batch can do it with a single reduction."""
         assert self.rank == 0
         b = self.base + (i % self.depth) * self.stride
-        return [self._wrap(b, (self.stride // 4, ), "<i4")]
+        return [self._wrap(b, ((self.stride - self.packed_bytes) // 4, ), "<i4")]
 
     def close(self):
         import ctypes as C

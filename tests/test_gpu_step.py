@@ -159,3 +159,47 @@ def test_random_traffic_redraws_the_traffic_at_every_reset():
         fixed.close()
     finally:
         env.close()
+
+
+def test_packed_rows_round_trip_bit_for_bit():
+    """pgd_pack_rows / pgd_expand_rows (the gather's wire format: head + 240-bit hit mask + beams that are not 1.0):
+    real observation rows, rows with every beam hit, rows with none, and special bit patterns come back exactly."""
+    import torch
+    from pgdrive_b200 import VecPGDriveEnv, cabi
+    env = VecPGDriveEnv(dict(num_envs=300, start_seed=1000, environment_num=20))
+    try:
+        env.reset()
+        g = torch.Generator(device="cuda"); g.manual_seed(3)
+        for t in range(150):
+            a = torch.rand((300, 2), generator=g, device="cuda") * 2 - 1
+            a[:, 1] = a[:, 1].abs(); a[:, 0] *= 0.1
+            obs = env.step(a)[0]
+        rows = obs.clone()
+        assert bool((rows[:, -240:] < 1.0).any()), "no lidar hit in 300 environments after 150 steps"
+        d = rows.shape[1]
+        extra = torch.rand((5, d), device="cuda")
+        extra[0, -240:] = 1.0                      # no hit at all
+        extra[1, -240:] = 0.25                     # every beam hit
+        extra[2, -240:] = torch.where(torch.arange(240, device="cuda") % 2 == 0, 1.0, 0.0)  # 0.0 is a hit
+        extra[3, -240:] = 1.0; extra[3, -1] = 0.5; extra[3, -240] = 0.75                    # first and last beam only
+        extra[4, -240:] = torch.nextafter(torch.ones(240, device="cuda"), torch.zeros(240, device="cuda"))  # 1 - ulp
+        rows = torch.cat([rows, extra]).contiguous()
+        n = rows.shape[0]
+        packed = torch.full((n, d + 8), float("nan"), device="cuda")
+        back = torch.full((n, d), float("nan"), device="cuda")
+        lib = env.engine.lib
+        st = torch.cuda.current_stream().cuda_stream
+        cabi.check(lib, lib.pgd_pack_rows(rows.data_ptr(), packed.data_ptr(), n, d, st))
+        cabi.check(lib, lib.pgd_expand_rows(packed.data_ptr(), back.data_ptr(), n, d, st))
+        torch.cuda.synchronize()
+        same = rows.view(torch.int32) == back.view(torch.int32)
+        assert bool(same.all()), "rows differ after the round trip: %s" % (~same).nonzero()[:8].tolist()
+        # what crosses the link: head + mask + hits
+        hits = (rows[:, -240:].view(torch.int32) != 0x3f800000).sum(1)
+        mask_words = packed[:, d - 240:d - 232].view(torch.int32)
+        pop = sum(((mask_words >> b) & 1) for b in range(32)).sum(1)
+        assert torch.equal(pop.to(torch.int64), hits.to(torch.int64)), (pop[:8].tolist(), hits[:8].tolist())
+        assert lib.pgd_pack_rows(None, packed.data_ptr(), n, d, st) == -1
+        assert lib.pgd_expand_rows(packed.data_ptr(), None, n, d, st) == -1
+    finally:
+        env.close()

@@ -11,7 +11,7 @@ from pgdrive_b200 import VecPGDriveEnv
 from pgdrive_b200.sharding import PeerGather
 n = 4096
 ok = True
-for mode in ("peer", "copy"):  # fused into the kernel's row stores / pushed by the copy engine (sharding.PeerGather)
+for mode in ("peer", "copy", "sparse"):  # kernel's row stores / copy engine / packed rows (sharding.PeerGather)
     env = VecPGDriveEnv(dict(start_seed=1000, environment_num=20, num_envs=n, device=lr))
     pg = PeerGather(env, torch, dist, n, world, rank, mode=mode)
     env.reset()
@@ -24,6 +24,8 @@ for mode in ("peer", "copy"):  # fused into the kernel's row stores / pushed by 
         if not direct:
             pg.push(t)
         pg.completion_barrier()
+        if rank == 0:
+            pg.expand(t)
         torch.cuda.synchronize()
         if rank == 0:
             obs, rew, done = pg.tensors(t)
