@@ -233,9 +233,11 @@ def run_own(args):
     if world > 1:
         gather_mode = args.gather
         if gather_mode == "auto":
-            # copy engine push: 707 GB/s into rank 0 at 8 GPUs against 653 GB/s for the kernel's own remote row stores
-            # (profiles/r02q_bench_8gpu_*.json); at 2 GPUs the two tie
-            gather_mode = "copy"
+            # With every result funnelled into rank 0 the dense gathers are bound by that GPU's NVLink ingress from 4
+            # GPUs on (copy engine 721 GB/s, the kernel's own remote row stores 653 GB/s: profiles/r03i_*, r03n_*), so
+            # the rows cross the link packed (profiles/r03o_*, r03p_*: 4 GPUs 792 -> 924 M, 8 GPUs 750 -> 1 153 M
+            # env-steps/s).  At 2 GPUs the link is not the bound and the packing kernels only cost SM time (679 vs 614 M).
+            gather_mode = "sparse" if world >= 3 else "copy"
         if gather_mode in ("peer", "copy", "sparse"):
             ok = torch.ones(1, dtype=torch.int32, device=dev)
             try:
@@ -601,10 +603,11 @@ def main():
     ap.add_argument("--envs", type=int, default=65536, help="environments per GPU (4096 = BASELINE.json configs[1])")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--gather", default="auto", choices=["auto", "peer", "copy", "sparse", "nccl"],
-                    help="N > 1: how rank 0 gets the whole batch (auto = copy: local rows pushed into rank 0's HBM by the "
-                         "copy engine on a side stream while the next step's kernel runs; peer: rows stored by the step "
-                         "kernel straight into rank 0's HBM; nccl: in-place all-gather, also the fall-back when peer mapping "
-                         "is not permitted)")
+                    help="N > 1: how rank 0 gets the whole batch (copy: local rows pushed into rank 0's HBM by the copy "
+                         "engine on a side stream while the next step's kernel runs; sparse: the same, but the rows cross "
+                         "NVLink packed -- head + hit mask + beams that are not 1.0 -- and rank 0 expands them; peer: rows "
+                         "stored by the step kernel straight into rank 0's HBM; nccl: in-place all-gather, also the "
+                         "fall-back when peer mapping is not permitted; auto = copy at 2 GPUs, sparse from 3 on)")
     ap.add_argument("--workload", default="v0", choices=sorted(WORKLOADS), help="v0 = BASELINE.json configs[2] (the metric's "
                     "configuration); 1000envs = configs[3]")
     args = ap.parse_args()
