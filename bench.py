@@ -216,20 +216,15 @@ def run_own(args):
     if world > 1:
         dist.barrier()
     from pgdrive_b200 import VecPGDriveEnv, cabi
-    from pgdrive_b200.sharding import GatherBuffers, PeerGather
-    n, K, W = args.envs, args.steps, args.warmup
+    from pgdrive_b200.sharding import GatherBuffers, PeerGather, balanced_sizes, sizes_with_rank0
+    K, W = args.steps, args.warmup
     first_seed, n_seeds, n_slots, desc = WORKLOADS[args.workload]
     T = build_tables(args.workload)
-    # weak scaling: rank r owns environments [r*n, (r+1)*n) of the global batch
-    bufs = [GatherBuffers(torch, n, world, rank, dev, obs_dim=OBS_DIM) for _ in range(2 if world > 1 else 1)]
-    side = torch.cuda.Stream(device=dev, priority=-1) if world > 1 else None
-    env = VecPGDriveEnv(
-        dict(start_seed=first_seed, environment_num=n_seeds, num_envs=n, traffic_density=0.1, device=local_rank,
-             num_slots=n_slots),
-        tables_dict=T, obs_out=bufs[0].local(bufs[0].obs)
-    )
-    peer = None
+    # ---- how the batch is cut.  Weak scaling: N ranks share N * --envs environments.  "Rank 0 holds the batch" gives
+    # rank 0 extra work every step (expanding the other ranks' packed rows, reading the whole gathered batch), so by
+    # default it simulates fewer environments than the others (sharding.balanced_sizes); --balance equal = N equal shards.
     gather_mode = "none"
+    sizes = [args.envs] * world
     if world > 1:
         gather_mode = args.gather
         if gather_mode == "auto":
@@ -239,15 +234,46 @@ def run_own(args):
             # env-steps/s).  At 2 GPUs the link is not the bound and the packing kernels only cost SM time (679 vs 614 M).
             gather_mode = "sparse" if world >= 3 else "copy"
         if gather_mode in ("peer", "copy", "sparse"):
-            ok = torch.ones(1, dtype=torch.int32, device=dev)
-            try:
-                peer = PeerGather(env, torch, dist, n, world, rank, mode=gather_mode)
-            except Exception as exc:  # noqa: BLE001
-                sys.stderr.write("rank %d: peer gather unavailable (%s)\n" % (rank, exc))
-                ok.zero_()
+            ok = torch.tensor([1 if local_rank == 0 or torch.cuda.can_device_access_peer(local_rank, 0) else 0],
+                              dtype=torch.int32, device=dev)
             dist.all_reduce(ok, op=dist.ReduceOp.MIN)
             if int(ok.item()) == 0:
-                peer, gather_mode = None, "nccl (peer mapping unavailable)"
+                gather_mode = "nccl (peer access unavailable)"
+        if gather_mode in ("peer", "copy", "sparse") and args.balance != "equal":
+            cost = dict(step=args.step_ns) if args.step_ns else None
+            if args.rank0_envs:
+                sizes = sizes_with_rank0(world * args.envs, world, args.rank0_envs)
+            else:
+                sizes = balanced_sizes(world * args.envs, world, gather_mode, cost=cost)
+    n, n_max, total_envs = sizes[rank], max(sizes), sum(sizes)
+    balance_note = "equal shards" if len(set(sizes)) == 1 else (
+        "rank 0 holds, expands and reads the whole batch every step, so it simulates fewer environments than the other "
+        "ranks (sharding.balanced_sizes: both sides of the gather on the same clock); total = N x envs_per_gpu")
+    peer_wanted = gather_mode in ("peer", "copy", "sparse")
+
+    def make_bufs():  # whole-batch buffers of the NCCL all-gather (equal shards); one local buffer at N = 1
+        return [GatherBuffers(torch, n, world, rank, dev, obs_dim=OBS_DIM) for _ in range(2 if world > 1 else 1)]
+
+    bufs = None if peer_wanted else make_bufs()
+    side = torch.cuda.Stream(device=dev, priority=-1) if world > 1 else None
+    env = VecPGDriveEnv(
+        dict(start_seed=first_seed, environment_num=n_seeds, num_envs=n, traffic_density=0.1, device=local_rank,
+             num_slots=n_slots),
+        tables_dict=T, obs_out=None if bufs is None else bufs[0].local(bufs[0].obs)
+    )
+    peer = None
+    if world > 1 and gather_mode in ("peer", "copy", "sparse"):
+        ok = torch.ones(1, dtype=torch.int32, device=dev)
+        try:
+            peer = PeerGather(env, torch, dist, sizes, world, rank, mode=gather_mode)
+        except Exception as exc:  # noqa: BLE001
+            sys.stderr.write("rank %d: peer gather unavailable (%s)\n" % (rank, exc))
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            if len(set(sizes)) > 1:
+                raise SystemExit("peer mapping failed with unequal shards: run with --balance equal (NCCL all-gather)")
+            peer, gather_mode, bufs = None, "nccl (peer mapping unavailable)", make_bufs()
 
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)  # Philox counter-based stream, one per rank
@@ -404,6 +430,22 @@ def run_own(args):
     if world > 1:
         sim_ms, _ = timed(actions[W:W + K], K, lambda a: env.step(a))
 
+    if args.headline_only:  # tuning aid (gather modes / shard sizes at N > 1): not a bench line
+        times = torch.tensor([ms, kernel_ms, sim_ms or 0.0], dtype=torch.float64, device=dev)
+        sums = [torch.zeros_like(local_sum) for _ in range(world)]
+        if world > 1:
+            dist.all_reduce(times, op=dist.ReduceOp.MAX)
+            dist.all_gather(sums, local_sum)
+        if rank == 0:
+            ms, kernel_ms, sim_ms = [float(x) for x in times.tolist()]
+            print(json.dumps(dict(headline_only=True, n_gpus=world, gather=gather_mode, shard_sizes=sizes,
+                                  value=total_envs * K / (ms * 1e-3), ms_per_step=ms / K, kernel_ms=kernel_ms,
+                                  sim_only_ms_per_step=sim_ms / K if sim_ms else None,
+                                  gather_ok=bool(int(verified.item()) == int(torch.stack(sums).sum().item())))))
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
     # ---- the same kernel under a policy that drives (own pre-roll, own roofline) -----------------------------------------
     env.reset()
     for t in range(PREROLL_DRIVING):
@@ -432,7 +474,7 @@ def run_own(args):
     if world > 1 and peer is not None:
         # north_star's path: the actions of the WHOLE batch start in rank 0's host memory, the gathered observation /
         # reward / done batch ends there.  H2D on rank 0, broadcast over NVLink, step + gather, one D2H on rank 0.
-        rows = world * n
+        rows, row0 = total_envs, sum(sizes[:rank])
         all_act_dev = torch.empty((rows, 2), dtype=torch.float32, device=dev)
         if rank == 0:
             h_all = torch.empty((rows, 2), dtype=torch.float32, pin_memory=True)
@@ -445,7 +487,7 @@ def run_own(args):
             if rank == 0:
                 all_act_dev.copy_(h_all, non_blocking=True)
             dist.broadcast(all_act_dev, src=0)
-            step_and_gather(all_act_dev[rank * n:(rank + 1) * n])
+            step_and_gather(all_act_dev[row0:row0 + n])
             drain()
             if rank == 0:
                 go, gr, gd = peer.tensors(counter[0] - 1)
@@ -479,7 +521,6 @@ def run_own(args):
             dist.destroy_process_group()
         return 0
 
-    total_envs = world * n
     value = total_envs * K / (ms * 1e-3)
     b_step = algorithmic_bytes_per_env_step(n_slots)
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -493,9 +534,9 @@ def run_own(args):
         traffic = json.load(open(tpath)).get("bytes_per_launch")
 
     def roofline(k_ms, policy):
-        achieved = b_step * n / (k_ms * 1e-3) / 1e9
+        achieved = b_step * n_max / (k_ms * 1e-3) / 1e9  # k_ms is the max over ranks: the largest shard's kernel
         return dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
-                    traffic=traffic if (policy == "random" and args.workload == "v0" and n == 65536) else None,
+                    traffic=traffic if (policy == "random" and args.workload == "v0" and n_max == 65536) else None,
                     kernel="pgd_step_kernel<%d, 4>" % n_slots, kernel_ms=k_ms, bytes_per_env_step=b_step,
                     peak_source=peak_src, issue=issue_bound(k_ms, (clk or {}).get("sm_mhz"), policy, args.workload))
 
@@ -543,7 +584,7 @@ def run_own(args):
         rate, dt = cpu_oracle_rate(T, cn, cs, 2, threads, [i % n_seeds for i in range(cn)], n_slots)
         cpu = dict(value=rate, unit="env-steps/s", cores=threads, kind="port",
                    sample="%d of %d envs x %d steps (%.1f s), CPU oracle (bucket-grid queries) on %d host threads" % (
-                       cn, n, cs, dt, threads))
+                       cn, args.envs, cs, dt, threads))
 
     collective = {
         "none": "none",
@@ -563,16 +604,18 @@ def run_own(args):
         ms_per_step=ms / K, higher_is_better=True, scaling="weak", vs_baseline=None,
         dtype="f32", data="synthetic",
         config=dict(
-            workload=desc % n, envs_per_gpu=n, total_envs=total_envs, parallelism="env-sharded x%d" % world,
+            workload=desc % args.envs, envs_per_gpu=args.envs, total_envs=total_envs,
+            parallelism="env-sharded x%d" % world, shard_sizes=sizes if world > 1 else None,
+            balance=None if world == 1 else balance_note,
             actions="uniform[-1,1]^2, Philox, pre-generated in HBM", preroll_steps=PREROLL,
             preroll_steps_driving=PREROLL_DRIVING,
             arithmetic="float32 throughout; the reference's Python side computes in float64, Bullet in float32",
             l2="no flush: state + observations touched per step = %.0f MB > 126 MB L2" % (
-                (2 * (80 * n_slots + 32) + 4 * OBS_DIM) * n / 1e6),
+                (2 * (80 * n_slots + 32) + 4 * OBS_DIM) * n_max / 1e6),
             collective=collective, done_rate_last_step=done_rate,
         ),
         roofline=roofline(kernel_ms, "random"),
-        driving=dict(value=n * fwd_k / (fwd_ms * 1e-3), unit="env-steps/s per GPU", steps=fwd_k,
+        driving=dict(value=n_max * fwd_k / (fwd_ms * 1e-3), unit="env-steps/s per GPU", steps=fwd_k,
                      policy="throttle |u|, steering 0.1 u: traffic awake, lidar hits, frequent resets",
                      done_rate_last_step=fwd_done_rate, roofline=roofline(fwd_kernel_ms, "driving")),
         cpu_baseline=cpu,
@@ -608,6 +651,14 @@ def main():
                          "NVLink packed -- head + hit mask + beams that are not 1.0 -- and rank 0 expands them; peer: rows "
                          "stored by the step kernel straight into rank 0's HBM; nccl: in-place all-gather, also the "
                          "fall-back when peer mapping is not permitted; auto = copy at 2 GPUs, sparse from 3 on)")
+    ap.add_argument("--headline-only", action="store_true", help="tuning aid: time the headline (and the simulation-only "
+                    "leg) and print a short record instead of the bench line")
+    ap.add_argument("--balance", default="auto", choices=["auto", "equal"],
+                    help="N > 1: auto = rank 0, which expands and reads the whole gathered batch every step, simulates fewer "
+                         "environments than the others (sharding.balanced_sizes); equal = N shards of --envs")
+    ap.add_argument("--rank0-envs", type=int, default=0, help="N > 1: fix rank 0's shard (multiple of 32); the rest is "
+                    "shared evenly")
+    ap.add_argument("--step-ns", type=float, default=0.0, help="override the cost model's ns per simulated env-step")
     ap.add_argument("--workload", default="v0", choices=sorted(WORKLOADS), help="v0 = BASELINE.json configs[2] (the metric's "
                     "configuration); 1000envs = configs[3]")
     args = ap.parse_args()

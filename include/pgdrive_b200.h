@@ -92,13 +92,15 @@ int pgd_peer_open(PgdHandle* h, const unsigned char handle[64], void** dev_ptr);
 int pgd_peer_release(PgdHandle* h, void* dev_ptr, int32_t is_owner);
 
 /* The gather's wire format for observation rows (no counterpart in the reference).  A row is [head | 240 lidar beams] and
- * most beams are exactly 1.0 ("no hit within 50 m").  pgd_pack_rows writes, per row and at a fixed stride of obs_dim + 8
- * floats, the head unchanged, a 240-bit hit mask (8 words) and the values of the beams that are not 1.0, in beam order;
- * pgd_expand_rows restores the rows bit for bit.  `packed_dev` of pgd_pack_rows may be peer memory (pgd_peer_open): a
+ * most beams are exactly 1.0 ("no hit within 50 m").  pgd_pack_rows writes, per row and at a fixed stride of
+ * pgd_packed_row_words(obs_dim) floats (obs_dim + 8 rounded up to a multiple of 32: 288 for 274, every packed row on its
+ * own 128-byte lines), the head unchanged, a 240-bit hit mask (8 words), the values of the beams that are not 1.0, in beam
+ * order, and zeros up to the next 32-byte boundary; pgd_expand_rows restores the rows bit for bit.  `packed_dev` of pgd_pack_rows may be peer memory (pgd_peer_open): a
  * rank packs its local rows straight into rank 0's HBM and only the bytes written cross NVLink -- about a quarter of
  * the 1 096-byte row --, rank 0 expands them into the whole-batch buffer.  Device pointers, asynchronous on `stream`. */
 int pgd_pack_rows(const float* dense_dev, float* packed_dev, int32_t n_rows, int32_t obs_dim, void* stream);
 int pgd_expand_rows(const float* packed_dev, float* dense_dev, int32_t n_rows, int32_t obs_dim, void* stream);
+int32_t pgd_packed_row_words(int32_t obs_dim);   /* stride of a packed row in floats; -1 when obs_dim < 240 */
 
 /* measurement helpers */
 /* *out_dev += sum of the 32-bit words of [dev_ptr, dev_ptr + bytes) (both multiples of 16), 64-bit accumulator: the

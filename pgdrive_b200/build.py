@@ -11,6 +11,7 @@ COMMON = ["pgd_internal.h", os.path.join(INC, "pgdrive_b200.h"), os.path.join(IN
 # translation unit -> extra dependencies
 UNITS = {
     "pgd_abi.cu": [],
+    "pgd_rows.cu": [],
     "pgd_step_kernel.cu": ["pgd_step.cuh"],
     "pgd_mapgen.cu": ["pgd_mapgen.cuh", "pgd_rng.cuh", "pgd_dd.cuh"],
 }

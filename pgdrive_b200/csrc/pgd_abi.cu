@@ -385,72 +385,6 @@ extern "C" int pgd_words_checksum(PgdHandle* h, const void* dev_ptr, uint64_t by
   return 0;
 }
 
-// ---- observation rows in the gather's wire format (include/pgdrive_b200.h: pgd_pack_rows / pgd_expand_rows) ------------
-// One warp per row.  A row is [head | 240 lidar beams]; most beams are exactly 1.0 ("no hit within 50 m").  Wire format,
-// fixed stride of obs_dim + 8 words per row: the head unchanged, a 240-bit hit mask (8 words), then the values of the
-// beams that are not 1.0, in beam order.  Only what is written crosses NVLink.
-__global__ void pgd_pack_rows_kernel(const float* __restrict__ dense, float* __restrict__ packed, int n_rows, int obs_dim) {
-  const int lane = threadIdx.x & 31, row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= n_rows) return;
-  const int head = obs_dim - PGD_LIDAR_BEAMS;
-  const float* src = dense + (size_t)row * obs_dim;
-  float* dst = packed + (size_t)row * (obs_dim + 8);
-  for (int i = lane; i < head; i += 32) dst[i] = src[i];
-  int base = 0;
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const int beam = c * 32 + lane;
-    const float v = beam < PGD_LIDAR_BEAMS ? src[head + beam] : 1.0f;
-    const bool hit = __float_as_uint(v) != 0x3f800000u;  // bit pattern: the row comes back exactly
-    const unsigned mask = __ballot_sync(0xffffffffu, hit);
-    if (lane == 0) dst[head + c] = __uint_as_float(mask);
-    if (hit) dst[head + 8 + base + __popc(mask & ((1u << lane) - 1u))] = v;
-    base += __popc(mask);
-  }
-}
-
-__global__ void pgd_expand_rows_kernel(const float* __restrict__ packed, float* __restrict__ dense, int n_rows, int obs_dim) {
-  const int lane = threadIdx.x & 31, row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= n_rows) return;
-  const int head = obs_dim - PGD_LIDAR_BEAMS;
-  const float* src = packed + (size_t)row * (obs_dim + 8);
-  float* dst = dense + (size_t)row * obs_dim;
-  for (int i = lane; i < head; i += 32) dst[i] = src[i];
-  const unsigned my_mask = lane < 8 ? __float_as_uint(src[head + lane]) : 0u;
-  int base = 0;
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const unsigned mask = __shfl_sync(0xffffffffu, my_mask, c);
-    const int beam = c * 32 + lane;
-    float v = 1.0f;
-    if ((mask >> lane) & 1u) v = src[head + 8 + base + __popc(mask & ((1u << lane) - 1u))];
-    if (beam < PGD_LIDAR_BEAMS) dst[head + beam] = v;
-    base += __popc(mask);
-  }
-}
-
-static int rows_args_ok(const char* who, const void* a, const void* b, int32_t n_rows, int32_t obs_dim) {
-  if (!a || !b || n_rows < 0 || obs_dim < PGD_LIDAR_BEAMS)
-    return fail(-1, std::string(who) + ": null pointer, negative row count or rows shorter than the lidar");
-  return 0;
-}
-
-extern "C" int pgd_pack_rows(const float* dense_dev, float* packed_dev, int32_t n_rows, int32_t obs_dim, void* stream) {
-  if (int rc = rows_args_ok("pgd_pack_rows", dense_dev, packed_dev, n_rows, obs_dim)) return rc;
-  if (n_rows == 0) return 0;
-  pgd_pack_rows_kernel<<<(n_rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(dense_dev, packed_dev, n_rows, obs_dim);
-  CU(cudaGetLastError());
-  return 0;
-}
-
-extern "C" int pgd_expand_rows(const float* packed_dev, float* dense_dev, int32_t n_rows, int32_t obs_dim, void* stream) {
-  if (int rc = rows_args_ok("pgd_expand_rows", packed_dev, dense_dev, n_rows, obs_dim)) return rc;
-  if (n_rows == 0) return 0;
-  pgd_expand_rows_kernel<<<(n_rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(packed_dev, dense_dev, n_rows, obs_dim);
-  CU(cudaGetLastError());
-  return 0;
-}
-
 extern "C" int64_t pgd_state_bytes_per_env(PgdHandle* h) { return h ? (int64_t)h->cfg.num_slots * 80 + 32 : 0; }
 extern "C" int64_t pgd_launch_count(PgdHandle* h) { return h ? h->launches : 0; }
 extern "C" int pgd_set_timing(PgdHandle* h, int32_t on) {

@@ -17,6 +17,49 @@ def shard_range(total_envs, world_size, rank):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
+# Cost of one row (= one environment's results of one step) on a B200, nanoseconds, steady state of the random policy:
+# simulate it (profiles/r03m_*); pack it into the wire format and store it into rank 0's HBM (r04d: 2 GPUs); expand it on
+# rank 0; have rank 0's consumer read it (profiles/r04d_rows_bench_v3.json).  "fixed": what rank 0's step costs beyond
+# its kernels (completion barrier, stream hand-overs), less the same on a sending rank (r04b / r04d shard sweeps).
+ROW_COST_NS = dict(step=2.3, pack=0.39, expand=0.29, consume=0.23, fixed=12000.0)
+
+
+def balanced_sizes(total_envs, world_size, mode="sparse", granule=32, min_rank0=4096, cost=None):
+    """Shard sizes for "rank 0 holds the batch": rank 0 simulates FEWER environments than the others, by as much as
+    its extra work per step -- expanding the other ranks' packed rows and reading the whole gathered batch -- takes.
+
+    With equal shards every rank finishes its step at the same time and then waits for rank 0 to expand and read
+    ``total_envs`` rows (8 GPUs: 0.15 ms of simulation, 0.27 ms of gather work on rank 0).  Solving
+    ``step*n0 + expand*(T - n0) + consume*T + fixed  =  (step + pack) * (T - n0) / (world - 1)`` for n0 puts both sides
+    on the same clock.  ``mode``: "sparse" (pack / expand kernels) or "copy" / "peer" (no SM work for the transfer itself).
+    Sizes are multiples of ``granule`` (32 = the environments of one CTA: every bulk row store stays whole and 16-byte
+    aligned); ranks 1.. differ by at most one granule; the sizes sum to ``total_envs``."""
+    if world_size < 1 or total_envs % granule or total_envs < world_size * granule:
+        raise ValueError("total_envs must be a multiple of %d with at least one granule per rank" % granule)
+    if world_size == 1:
+        return [total_envs]
+    c = dict(ROW_COST_NS, **(cost or {}))
+    pack, expand = (c["pack"], c["expand"]) if mode == "sparse" else (0.0, 0.0)
+    T, others = float(total_envs), world_size - 1
+    per_other = (c["step"] + pack) / others
+    n0 = ((per_other - expand - c["consume"]) * T - c["fixed"]) / (c["step"] - expand + per_other)
+    equal = total_envs // world_size
+    n0 = int(min(max(n0, min(min_rank0, equal)), equal) + 0.5 * granule) // granule * granule  # nearest granule
+    if n0 >= equal and total_envs % (world_size * granule) == 0:
+        return [equal] * world_size
+    return sizes_with_rank0(total_envs, world_size, max(n0, granule), granule)
+
+
+def sizes_with_rank0(total_envs, world_size, rank0_envs, granule=32):
+    """Rank 0 gets ``rank0_envs``; the other ranks share the rest in granules, sizes differing by at most one granule."""
+    others = world_size - 1
+    if world_size < 2 or rank0_envs % granule or total_envs % granule or rank0_envs <= 0 or \
+            total_envs - rank0_envs < others * granule:
+        raise ValueError("rank 0's shard and the total must be multiples of %d and leave a granule per rank" % granule)
+    base, extra = divmod((total_envs - rank0_envs) // granule, others)
+    return [rank0_envs] + [(base + (1 if r < extra else 0)) * granule for r in range(others)]
+
+
 def seed_of_env(global_env, start_seed, environment_num):
     """Seed played by a global environment index (env i -> start_seed + i mod environment_num)."""
     return start_seed + global_env % environment_num
@@ -66,21 +109,32 @@ class PeerGather:
     landed, and -- because rank 0 enqueues its reads of buffer i before it joins the barrier of step i + 1 -- a rank
     that waits for barrier i + 1 before writing buffer i again (step i + 2) never overwrites unread rows."""
     def __init__(self, env, torch, dist, n_local, world_size, rank, obs_dim=274, depth=2, mode="peer"):
+        """``n_local``: rows per rank -- one int (equal shards) or the list of every rank's size (``balanced_sizes``;
+        multiples of 32 so that every rank's rows start 16-byte aligned)."""
         import ctypes as C
         from . import cabi
         if mode not in ("peer", "copy", "sparse"):
             raise ValueError("mode must be 'peer', 'copy' or 'sparse'")
         self.env, self.torch, self.dist, self.mode = env, torch, dist, mode
-        self.n, self.world, self.rank, self.depth, self.obs_dim = n_local, world_size, rank, depth, obs_dim
-        rows = world_size * n_local
+        self.sizes = [int(n_local)] * world_size if isinstance(n_local, int) else [int(v) for v in n_local]
+        if len(self.sizes) != world_size or min(self.sizes) <= 0:
+            raise ValueError("one positive shard size per rank")
+        if len(set(self.sizes)) > 1 and any(v % 32 for v in self.sizes):
+            raise ValueError("unequal shard sizes must be multiples of 32")
+        self.first = [sum(self.sizes[:r]) for r in range(world_size)]  # first global row of every rank
+        self.n, self.row0 = self.sizes[rank], self.first[rank]
+        self.world, self.rank, self.depth, self.obs_dim = world_size, rank, depth, obs_dim
+        rows = sum(self.sizes)
+        self.rows = rows
         self.obs_bytes, self.rew_bytes = rows * obs_dim * 4, rows * 4
         self.done_bytes = (rows + 255) // 256 * 256
         self.stride = self.obs_bytes + self.rew_bytes + self.done_bytes
-        # "sparse": per buffer a staging area of packed rows (fixed stride obs_dim + 8 words) behind the dense batch
-        self.packed_bytes = (rows * (obs_dim + 8) * 4 + 255) // 256 * 256 if mode == "sparse" else 0
-        self.stride += self.packed_bytes
         e = env.engine
         self._lib, self._h = e.lib, e.h
+        # "sparse": per buffer a staging area of packed rows (fixed stride pgd_packed_row_words) behind the dense batch
+        self.packed_words = int(e.lib.pgd_packed_row_words(obs_dim)) if mode == "sparse" else 0
+        self.packed_bytes = (rows * self.packed_words * 4 + 255) // 256 * 256
+        self.stride += self.packed_bytes
         base = C.c_void_p()
         handle = C.create_string_buffer(64)
         if rank == 0:
@@ -95,14 +149,14 @@ class PeerGather:
         self._local = None
         if mode in ("copy", "sparse") and rank != 0:
             dev = e.device
-            self._local = [(torch.empty((n_local, obs_dim), dtype=torch.float32, device=dev),
-                            torch.empty(n_local, dtype=torch.float32, device=dev),
-                            torch.empty(n_local, dtype=torch.uint8, device=dev)) for _ in range(depth)]
+            self._local = [(torch.empty((self.n, obs_dim), dtype=torch.float32, device=dev),
+                            torch.empty(self.n, dtype=torch.float32, device=dev),
+                            torch.empty(self.n, dtype=torch.uint8, device=dev)) for _ in range(depth)]
 
     def _offsets(self, i):
         b = self.base + (i % self.depth) * self.stride
-        return (b + self.rank * self.n * self.obs_dim * 4, b + self.obs_bytes + self.rank * self.n * 4,
-                b + self.obs_bytes + self.rew_bytes + self.rank * self.n)
+        return (b + self.row0 * self.obs_dim * 4, b + self.obs_bytes + self.row0 * 4,
+                b + self.obs_bytes + self.rew_bytes + self.row0)
 
     def pointers(self, i):
         """(obs, reward, done) device pointers of THIS rank's rows in rank 0's buffer ``i``."""
@@ -127,7 +181,7 @@ class PeerGather:
 
     def _packed_ptr(self, i, rank):
         b = self.base + (i % self.depth) * self.stride + (self.stride - self.packed_bytes)
-        return b + rank * self.n * (self.obs_dim + 8) * 4
+        return b + self.first[rank] * self.packed_words * 4
 
     def push(self, i):
         """modes "copy" / "sparse", rank > 0: enqueue (current stream) the transfer of the local rows into rank 0's
@@ -152,8 +206,8 @@ class PeerGather:
         from . import cabi
         st = self.torch.cuda.current_stream(self.env.engine.device).cuda_stream
         b = self.base + (i % self.depth) * self.stride
-        cabi.check(self._lib, self._lib.pgd_expand_rows(self._packed_ptr(i, 1), b + self.n * self.obs_dim * 4,
-                                                        (self.world - 1) * self.n, self.obs_dim, st))
+        cabi.check(self._lib, self._lib.pgd_expand_rows(self._packed_ptr(i, 1), b + self.sizes[0] * self.obs_dim * 4,
+                                                        self.rows - self.sizes[0], self.obs_dim, st))
 
     def completion_barrier(self):
         """Enqueue (on the current stream) a barrier after which rank 0 may read the buffer written last."""
@@ -163,7 +217,7 @@ class PeerGather:
     def tensors(self, i):
         """Rank 0 only: the whole-batch (obs, reward, done) tensors of buffer ``i``."""
         assert self.rank == 0
-        rows = self.world * self.n
+        rows = self.rows
         b = self.base + (i % self.depth) * self.stride
         return (self._wrap(b, (rows, self.obs_dim), "<f4"), self._wrap(b + self.obs_bytes, (rows, ), "<f4"),
                 self._wrap(b + self.obs_bytes + self.rew_bytes, (rows, ), "|u1"))

@@ -140,6 +140,36 @@ def test_shard_ranges_cover_the_batch():
         shard_range(10, 2, 2)
 
 
+def test_balanced_shards_give_rank_0_less_to_simulate():
+    """sharding.balanced_sizes: sizes sum to the total, whole CTAs (multiples of 32), ranks 1.. within one granule of
+    each other, rank 0 never above an equal share and smaller the more ranks it gathers from."""
+    from pgdrive_b200.sharding import ROW_COST_NS, balanced_sizes, sizes_with_rank0
+    assert balanced_sizes(65536, 1) == [65536]
+    last = None
+    for world in (2, 3, 4, 8):
+        for mode in ("sparse", "copy", "peer"):
+            total = world * 65536
+            s = balanced_sizes(total, world, mode)
+            assert len(s) == world and sum(s) == total and all(v > 0 and v % 32 == 0 for v in s)
+            assert max(s[1:]) - min(s[1:]) <= 32 and s[0] <= 65536 <= min(s[1:])
+            c = ROW_COST_NS
+            pack, expand = (c["pack"], c["expand"]) if mode == "sparse" else (0.0, 0.0)
+            t0 = c["step"] * s[0] + expand * (total - s[0]) + c["consume"] * total + c["fixed"]
+            t1 = (c["step"] + pack) * max(s[1:])
+            assert t0 <= t1 * 1.01 or s[0] == 4096  # balanced, or rank 0 already at its floor
+        now = balanced_sizes(world * 65536, world, "sparse")[0]
+        assert last is None or now <= last
+        last = now
+    assert balanced_sizes(8 * 65536, 8, "sparse", cost=dict(step=1e6)) == [65536] * 8  # gather work negligible: equal
+    assert sizes_with_rank0(4 * 4096, 4, 1024) == [1024, 5120, 5120, 5120]
+    assert sum(sizes_with_rank0(8 * 65536, 8, 4096)) == 8 * 65536
+    for bad in ((100, 2), (64, 4)):
+        with pytest.raises(ValueError):
+            balanced_sizes(*bad)
+    with pytest.raises(ValueError):
+        sizes_with_rank0(4096, 2, 100)
+
+
 GLOO_WORKER = r"""
 import os, sys
 sys.path.insert(0, %r)

@@ -185,9 +185,11 @@ def test_packed_rows_round_trip_bit_for_bit():
         extra[4, -240:] = torch.nextafter(torch.ones(240, device="cuda"), torch.zeros(240, device="cuda"))  # 1 - ulp
         rows = torch.cat([rows, extra]).contiguous()
         n = rows.shape[0]
-        packed = torch.full((n, d + 8), float("nan"), device="cuda")
-        back = torch.full((n, d), float("nan"), device="cuda")
         lib = env.engine.lib
+        stride = lib.pgd_packed_row_words(d)
+        assert stride == (d + 8 + 31) // 32 * 32 and lib.pgd_packed_row_words(100) == -1
+        packed = torch.full((n, stride), float("nan"), device="cuda")
+        back = torch.full((n, d), float("nan"), device="cuda")
         st = torch.cuda.current_stream().cuda_stream
         cabi.check(lib, lib.pgd_pack_rows(rows.data_ptr(), packed.data_ptr(), n, d, st))
         cabi.check(lib, lib.pgd_expand_rows(packed.data_ptr(), back.data_ptr(), n, d, st))
@@ -199,6 +201,19 @@ def test_packed_rows_round_trip_bit_for_bit():
         mask_words = packed[:, d - 240:d - 232].view(torch.int32)
         pop = sum(((mask_words >> b) & 1) for b in range(32)).sum(1)
         assert torch.equal(pop.to(torch.int64), hits.to(torch.int64)), (pop[:8].tolist(), hits[:8].tolist())
+        # what is written: head + mask + hits, zero-filled to a 32-byte boundary; nothing behind it
+        used = d - 240 + 8 + hits
+        col = torch.arange(stride, device="cuda")[None, :]
+        pad = (col >= used[:, None]) & (col < ((used + 7) // 8 * 8)[:, None])
+        assert bool((packed[pad] == 0).all()) and bool(torch.isnan(packed[col >= ((used + 7) // 8 * 8)[:, None]]).all())
+        # the unaligned paths: rows that start 4 bytes off a 16-byte boundary on either side
+        flat_r = torch.empty(n * d + 1, device="cuda"); flat_p = torch.empty(n * stride + 1, device="cuda")
+        flat_b = torch.full((n * d + 1, ), float("nan"), device="cuda")
+        flat_r[1:] = rows.reshape(-1)
+        cabi.check(lib, lib.pgd_pack_rows(flat_r[1:].data_ptr(), flat_p[1:].data_ptr(), n, d, st))
+        cabi.check(lib, lib.pgd_expand_rows(flat_p[1:].data_ptr(), flat_b[1:].data_ptr(), n, d, st))
+        torch.cuda.synchronize()
+        assert torch.equal(flat_b[1:].view(torch.int32), rows.reshape(-1).view(torch.int32))
         assert lib.pgd_pack_rows(None, packed.data_ptr(), n, d, st) == -1
         assert lib.pgd_expand_rows(packed.data_ptr(), None, n, d, st) == -1
     finally:
