@@ -100,6 +100,13 @@ int pgd_peer_release(PgdHandle* h, void* dev_ptr, int32_t is_owner);
  * the 1 096-byte row --, rank 0 expands them into the whole-batch buffer.  Device pointers, asynchronous on `stream`. */
 int pgd_pack_rows(const float* dense_dev, float* packed_dev, int32_t n_rows, int32_t obs_dim, void* stream);
 int pgd_expand_rows(const float* packed_dev, float* dense_dev, int32_t n_rows, int32_t obs_dim, void* stream);
+/* Delta expansion into a buffer that still holds the rows of an earlier step: `mask_state_dev` (8 uint32 per row, owned by
+ * the caller, one per buffer) remembers the hit masks of the rows the buffer holds, and only the head, the beams that
+ * were or are hits, and the new mask are written -- a third of the traffic.  `full` != 0 writes every beam and
+ * initialises the state (first use of a buffer).  Bit-identical to pgd_expand_rows as long as nobody else writes the
+ * buffer's rows in between. */
+int pgd_expand_rows_delta(const float* packed_dev, float* dense_dev, uint32_t* mask_state_dev, int32_t n_rows,
+                          int32_t obs_dim, int32_t full, void* stream);
 int32_t pgd_packed_row_words(int32_t obs_dim);   /* stride of a packed row in floats; -1 when obs_dim < 240 */
 
 /* measurement helpers */

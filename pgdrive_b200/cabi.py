@@ -140,6 +140,7 @@ def load_library():
     lib.pgd_words_checksum.argtypes = [vp, vp, C.c_uint64, vp, vp]
     lib.pgd_pack_rows.argtypes = [vp, vp, i32, i32, vp]
     lib.pgd_expand_rows.argtypes = [vp, vp, i32, i32, vp]
+    lib.pgd_expand_rows_delta.argtypes = [vp, vp, vp, i32, i32, i32, vp]
     lib.pgd_packed_row_words.argtypes = [i32]
     lib.pgd_packed_row_words.restype = i32
     lib.pgd_peer_alloc.argtypes = [vp, C.c_uint64, C.POINTER(vp), C.c_char_p]
@@ -150,7 +151,8 @@ def load_library():
     lib.pgd_patch_tables.argtypes = [vp, i32, C.POINTER(PgdTables), vp]
     lib.pgd_download_tables.argtypes = [vp, C.POINTER(PgdTables)]
     for name in ("pgd_create", "pgd_destroy", "pgd_load_tables", "pgd_reset", "pgd_step", "pgd_step_host",
-                 "pgd_get_state", "pgd_set_state", "pgd_set_timing", "pgd_words_checksum", "pgd_pack_rows", "pgd_expand_rows", "pgd_packed_row_words", "pgd_patch_tables", "pgd_peer_alloc", "pgd_peer_open",
+                 "pgd_get_state", "pgd_set_state", "pgd_set_timing", "pgd_words_checksum", "pgd_pack_rows", "pgd_expand_rows",
+                 "pgd_expand_rows_delta", "pgd_packed_row_words", "pgd_patch_tables", "pgd_peer_alloc", "pgd_peer_open",
                  "pgd_peer_release", "pgd_generate_tables", "pgd_table_sizes", "pgd_download_tables"):
         getattr(lib, name).restype = i32
     _LIB = lib

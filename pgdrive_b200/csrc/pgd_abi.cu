@@ -366,8 +366,15 @@ extern "C" int pgd_peer_release(PgdHandle* h, void* dev_ptr, int32_t is_owner) {
 __global__ void __launch_bounds__(256) pgd_words_sum_kernel(const uint4* __restrict__ p, size_t n16,
                                                             unsigned long long* __restrict__ out) {
   unsigned long long acc = 0;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
-    const uint4 v = p[i];
+  const size_t step = (size_t)gridDim.x * blockDim.x;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * step < n16; i += 4 * step) {  // four independent 16-byte loads in flight per thread
+    const uint4 a = __ldcs(p + i), b = __ldcs(p + i + step), c = __ldcs(p + i + 2 * step), d = __ldcs(p + i + 3 * step);
+    acc += ((unsigned long long)a.x + a.y + a.z + a.w) + ((unsigned long long)b.x + b.y + b.z + b.w) +
+           ((unsigned long long)c.x + c.y + c.z + c.w) + ((unsigned long long)d.x + d.y + d.z + d.w);
+  }
+  for (; i < n16; i += step) {
+    const uint4 v = __ldcs(p + i);
     acc += (unsigned long long)v.x + v.y + v.z + v.w;
   }
 #pragma unroll

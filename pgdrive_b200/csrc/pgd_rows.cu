@@ -9,7 +9,8 @@
 // One warp per row, 8 rows per CTA.  The dense row (1 096 bytes, 8-byte aligned) is read and written with plain
 // coalesced 4-byte accesses -- measured against a variant that moved whole 32-row tiles through shared memory with 16-byte
 // accesses (profiles/r04c_rows_bench_*.json: the tiles were 25-45 % slower; a barrier per tile costs more than the
-// partial sectors).  The PACKED row is what crosses NVLink: it is assembled in shared memory and leaves as 16-byte stores of
+// partial sectors; r04f_rows_bench_v4.json: expanding PAIRS of rows -- 2 192 bytes = 137 x 16 -- with 16-byte stores of
+// whole sectors was 20 % slower as well).  The PACKED row is what crosses NVLink: it is assembled in shared memory and leaves as 16-byte stores of
 // whole 32-byte sectors -- one fully coalesced store instruction for a typical row instead of a dozen small ones.
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -78,6 +79,43 @@ pgd_expand_rows_kernel(const float* __restrict__ packed, float* __restrict__ den
   }
 }
 
+// Delta expansion.  Rank 0 expands step t's rows into the SAME whole-batch buffer that holds the rows of step t - depth,
+// and a lidar beam that was 1.0 then and is 1.0 now needs no store: with `mask_state` = the hit masks of the rows the
+// buffer holds (8 words per row, kept by the caller next to the buffer), a row costs its head, the beams that were or
+// are hits, and the new mask -- about 400 bytes of traffic instead of 1 300 (r04g_rows_bench_delta.json).  `full` != 0
+// writes every beam and only initialises the state (first use of a buffer).  The result is bit-identical to
+// pgd_expand_rows as long as nobody else writes the buffer's rows in between.
+__global__ void __launch_bounds__(ROWS_WARPS * 32)
+pgd_expand_rows_delta_kernel(const float* __restrict__ packed, float* __restrict__ dense, uint32_t* __restrict__ mask_state,
+                             int n_rows, int obs_dim, int full) {
+  const int stride = packed_words(obs_dim), head = obs_dim - PGD_LIDAR_BEAMS;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row = blockIdx.x * ROWS_WARPS + warp;
+  if (row >= n_rows) return;
+  const float* src = packed + (size_t)row * stride;
+  float* dst = dense + (size_t)row * obs_dim;
+  unsigned new_mask = 0u, old_mask = 0u;
+  if (lane < 8) {
+    new_mask = __float_as_uint(__ldcs(src + head + lane));
+    old_mask = full ? 0xffffffffu : mask_state[(size_t)row * 8 + lane];
+  }
+  for (int i = lane; i < head; i += 32) dst[i] = __ldcs(src + i);
+  int base = head + 8;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const unsigned nm = __shfl_sync(0xffffffffu, new_mask, c);
+    const unsigned touched = nm | __shfl_sync(0xffffffffu, old_mask, c);
+    if (touched) {  // uniform over the warp
+      const int beam = c * 32 + lane;
+      float v = 1.0f;
+      if ((nm >> lane) & 1u) v = src[min(base + __popc(nm & ((1u << lane) - 1u)), stride - 1)];
+      if (((touched >> lane) & 1u) && beam < PGD_LIDAR_BEAMS) dst[head + beam] = v;
+    }
+    base += __popc(nm);
+  }
+  if (lane < 8 && (full || new_mask != old_mask)) mask_state[(size_t)row * 8 + lane] = new_mask;
+}
+
 static int rows_args_ok(const char* who, const void* a, const void* b, int32_t n_rows, int32_t obs_dim) {
   if (!a || !b || n_rows < 0 || obs_dim < PGD_LIDAR_BEAMS)
     return fail(-1, std::string(who) + ": null pointer, negative row count or rows shorter than the lidar");
@@ -106,4 +144,15 @@ extern "C" int pgd_expand_rows(const float* packed_dev, float* dense_dev, int32_
   if (int rc = rows_args_ok("pgd_expand_rows", packed_dev, dense_dev, n_rows, obs_dim)) return rc;
   if (n_rows == 0) return 0;
   return rows_launch(pgd_expand_rows_kernel, packed_dev, dense_dev, n_rows, obs_dim, stream);
+}
+
+extern "C" int pgd_expand_rows_delta(const float* packed_dev, float* dense_dev, uint32_t* mask_state_dev, int32_t n_rows,
+                                     int32_t obs_dim, int32_t full, void* stream) {
+  if (int rc = rows_args_ok("pgd_expand_rows_delta", packed_dev, dense_dev, n_rows, obs_dim)) return rc;
+  if (!mask_state_dev || ((uintptr_t)mask_state_dev & 3)) return fail(-1, "pgd_expand_rows_delta: mask state missing or unaligned");
+  if (n_rows == 0) return 0;
+  pgd_expand_rows_delta_kernel<<<(n_rows + ROWS_WARPS - 1) / ROWS_WARPS, ROWS_WARPS * 32, 0, (cudaStream_t)stream>>>(
+      packed_dev, dense_dev, mask_state_dev, n_rows, obs_dim, full);
+  CU(cudaGetLastError());
+  return 0;
 }

@@ -19,9 +19,9 @@ def shard_range(total_envs, world_size, rank):
 
 # Cost of one row (= one environment's results of one step) on a B200, nanoseconds, steady state of the random policy:
 # simulate it (profiles/r03m_*); pack it into the wire format and store it into rank 0's HBM (r04d: 2 GPUs); expand it on
-# rank 0; have rank 0's consumer read it (profiles/r04d_rows_bench_v3.json).  "fixed": what rank 0's step costs beyond
+# rank 0 (delta expansion); have rank 0's consumer read it (profiles/r04g_rows_bench_delta.json).  "fixed": what rank 0's step costs beyond
 # its kernels (completion barrier, stream hand-overs), less the same on a sending rank (r04b / r04d shard sweeps).
-ROW_COST_NS = dict(step=2.3, pack=0.39, expand=0.29, consume=0.23, fixed=12000.0)
+ROW_COST_NS = dict(step=2.3, pack=0.39, expand=0.23, consume=0.19, fixed=12000.0)
 
 
 def balanced_sizes(total_envs, world_size, mode="sparse", granule=32, min_rank0=4096, cost=None):
@@ -108,9 +108,11 @@ class PeerGather:
     In both, ``completion_barrier`` (a 4-byte all-reduce) tells rank 0 that every rank's rows of that buffer have
     landed, and -- because rank 0 enqueues its reads of buffer i before it joins the barrier of step i + 1 -- a rank
     that waits for barrier i + 1 before writing buffer i again (step i + 2) never overwrites unread rows."""
-    def __init__(self, env, torch, dist, n_local, world_size, rank, obs_dim=274, depth=2, mode="peer"):
+    def __init__(self, env, torch, dist, n_local, world_size, rank, obs_dim=274, depth=2, mode="peer", delta=True):
         """``n_local``: rows per rank -- one int (equal shards) or the list of every rank's size (``balanced_sizes``;
-        multiples of 32 so that every rank's rows start 16-byte aligned)."""
+        multiples of 32 so that every rank's rows start 16-byte aligned).  ``delta`` (mode "sparse"): rank 0 expands
+        into a buffer that still holds the rows of ``depth`` steps ago and stores only what changed
+        (pgd_expand_rows_delta); needs every step's ``expand`` and nobody else writing the other ranks' rows."""
         import ctypes as C
         from . import cabi
         if mode not in ("peer", "copy", "sparse"):
@@ -146,6 +148,12 @@ class PeerGather:
             cabi.check(e.lib, e.lib.pgd_peer_open(e.h, blob[0], C.byref(base)))
         self.base = base.value
         self._flag = torch.zeros(1, dtype=torch.int32, device=e.device)
+        # delta expansion: per buffer, the hit masks (8 words per row) of the rows of ranks 1.. that the buffer holds
+        self._mask_state = None
+        if mode == "sparse" and delta and rank == 0 and world_size > 1:
+            self._mask_state = [torch.zeros((rows - self.sizes[0], 8), dtype=torch.int32, device=e.device)
+                                for _ in range(depth)]
+            self._state_valid = [False] * depth
         self._local = None
         if mode in ("copy", "sparse") and rank != 0:
             dev = e.device
@@ -199,15 +207,23 @@ class PeerGather:
 
     def expand(self, i):
         """mode "sparse", rank 0, after the completion barrier of buffer ``i``: restore the rows of ranks 1.. from the
-        staging area into the whole-batch buffer (current stream)."""
+        staging area into the whole-batch buffer (current stream).  With ``delta`` only the head, the beams that were
+        or are hits and the new hit mask of a row are stored: the buffer still holds the rows of step i - depth, and a
+        beam that was 1.0 then and is 1.0 now needs no store."""
         if self.mode != "sparse" or self.world == 1:
             return
         assert self.rank == 0
         from . import cabi
         st = self.torch.cuda.current_stream(self.env.engine.device).cuda_stream
         b = self.base + (i % self.depth) * self.stride
-        cabi.check(self._lib, self._lib.pgd_expand_rows(self._packed_ptr(i, 1), b + self.sizes[0] * self.obs_dim * 4,
-                                                        self.rows - self.sizes[0], self.obs_dim, st))
+        src, dst, n = self._packed_ptr(i, 1), b + self.sizes[0] * self.obs_dim * 4, self.rows - self.sizes[0]
+        if self._mask_state is None:
+            cabi.check(self._lib, self._lib.pgd_expand_rows(src, dst, n, self.obs_dim, st))
+            return
+        k = i % self.depth
+        cabi.check(self._lib, self._lib.pgd_expand_rows_delta(src, dst, self._mask_state[k].data_ptr(), n, self.obs_dim,
+                                                              0 if self._state_valid[k] else 1, st))
+        self._state_valid[k] = True
 
     def completion_barrier(self):
         """Enqueue (on the current stream) a barrier after which rank 0 may read the buffer written last."""

@@ -218,3 +218,47 @@ def test_packed_rows_round_trip_bit_for_bit():
         assert lib.pgd_expand_rows(packed.data_ptr(), None, n, d, st) == -1
     finally:
         env.close()
+
+
+def test_delta_expansion_equals_full_expansion():
+    """pgd_expand_rows_delta: expanding a sequence of steps into the SAME buffer, storing only what changed since the rows
+    the buffer holds, gives bit for bit what pgd_expand_rows gives -- hits appearing, moving and disappearing, rows with
+    every beam hit, and a buffer that starts as NaN (first use: full)."""
+    import torch
+    from pgdrive_b200 import VecPGDriveEnv, cabi
+    n = 1000
+    env = VecPGDriveEnv(dict(num_envs=n, start_seed=1000, environment_num=20))
+    try:
+        lib = env.engine.lib
+        st = torch.cuda.current_stream().cuda_stream
+        env.reset()
+        g = torch.Generator(device="cuda"); g.manual_seed(11)
+        d = env.obs.shape[1]
+        stride = lib.pgd_packed_row_words(d)
+        packed = torch.full((n, stride), float("nan"), device="cuda")
+        dense = torch.full((n, d), float("nan"), device="cuda")      # the buffer that is expanded into, again and again
+        want = torch.empty((n, d), device="cuda")
+        state = torch.zeros((n, 8), dtype=torch.int32, device="cuda")
+        seen_hits = 0
+        for t in range(120):
+            a = torch.rand((n, 2), generator=g, device="cuda") * 2 - 1
+            a[:, 1] = a[:, 1].abs(); a[:, 0] *= 0.1
+            rows = env.step(a)[0].clone()
+            if t % 10 == 3:
+                rows[::7, -240:] = torch.rand((len(rows[::7]), 240), generator=g, device="cuda")  # every beam a hit
+            if t % 10 == 4:
+                rows[::7, -240:] = 1.0                                                              # ... and gone again
+            seen_hits += int((rows[:, -240:] != 1.0).sum())
+            cabi.check(lib, lib.pgd_pack_rows(rows.data_ptr(), packed.data_ptr(), n, d, st))
+            cabi.check(lib, lib.pgd_expand_rows(packed.data_ptr(), want.data_ptr(), n, d, st))
+            cabi.check(lib, lib.pgd_expand_rows_delta(packed.data_ptr(), dense.data_ptr(), state.data_ptr(), n, d,
+                                                      1 if t == 0 else 0, st))
+            torch.cuda.synchronize()
+            assert torch.equal(want.view(torch.int32), rows.view(torch.int32))
+            same = dense.view(torch.int32) == rows.view(torch.int32)
+            assert bool(same.all()), "step %d: %s" % (t, (~same).nonzero()[:8].tolist())
+            assert torch.equal(state, packed[:, d - 240:d - 232].view(torch.int32))
+        assert seen_hits > 1000
+        assert lib.pgd_expand_rows_delta(packed.data_ptr(), dense.data_ptr(), None, n, d, 0, st) == -1
+    finally:
+        env.close()

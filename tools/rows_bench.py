@@ -22,6 +22,8 @@ def main():
         obs = env.step(acts[t % 256])[0]
     d = obs.shape[1]
     rows = obs.repeat((n_rows + n - 1) // n, 1)[:n_rows].contiguous()
+    env.step(acts[0])
+    rows2 = env.step(acts[1])[0].repeat((n_rows + n - 1) // n, 1)[:n_rows].contiguous()  # the same rows two steps on
     lib, h = env.engine.lib, env.engine.h
     stride = lib.pgd_packed_row_words(d)
     packed = torch.zeros((n_rows, stride), device="cuda")
@@ -45,6 +47,21 @@ def main():
 
     t_pack = timed(lambda: cabi.check(lib, lib.pgd_pack_rows(rows.data_ptr(), packed.data_ptr(), n_rows, d, st)))
     t_exp = timed(lambda: cabi.check(lib, lib.pgd_expand_rows(packed.data_ptr(), back.data_ptr(), n_rows, d, st)))
+    # delta expansion: the buffer holds the rows of two steps ago (two gather buffers alternate)
+    packed2 = torch.zeros((n_rows, stride), device="cuda")
+    state = torch.zeros((n_rows, 8), dtype=torch.int32, device="cuda")
+    cabi.check(lib, lib.pgd_pack_rows(rows2.data_ptr(), packed2.data_ptr(), n_rows, d, st))
+    cabi.check(lib, lib.pgd_expand_rows_delta(packed.data_ptr(), back.data_ptr(), state.data_ptr(), n_rows, d, 1, st))
+    flip = [0]
+
+    def delta():
+        flip[0] ^= 1
+        src = packed2 if flip[0] else packed
+        cabi.check(lib, lib.pgd_expand_rows_delta(src.data_ptr(), back.data_ptr(), state.data_ptr(), n_rows, d, 0, st))
+
+    t_delta = timed(delta)
+    ok_delta = torch.equal((rows2 if flip[0] else rows).view(torch.int32), back.view(torch.int32))
+    cabi.check(lib, lib.pgd_expand_rows(packed.data_ptr(), back.data_ptr(), n_rows, d, st))
     t_sum = timed(lambda: cabi.check(lib, lib.pgd_words_checksum(h, back.data_ptr(), n_rows * d * 4, acc.data_ptr(), st)))
     ok = torch.equal(rows.view(torch.int32), back.view(torch.int32))
     dense = n_rows * d * 4
@@ -53,6 +70,7 @@ def main():
         round_trip_bit_exact=ok,
         pack=dict(ms=t_pack, ns_per_row=t_pack * 1e6 / n_rows, gbs=(dense + wire * n_rows) / t_pack / 1e6),
         expand=dict(ms=t_exp, ns_per_row=t_exp * 1e6 / n_rows, gbs=(dense + wire * n_rows) / t_exp / 1e6),
+        expand_delta=dict(ms=t_delta, ns_per_row=t_delta * 1e6 / n_rows, bit_exact=ok_delta),
         consume=dict(ms=t_sum, ns_per_row=t_sum * 1e6 / n_rows, gbs=dense / t_sum / 1e6))))
     env.close()
 
