@@ -469,8 +469,11 @@ def run_own(args):
     torch.cuda.synchronize()
     per_rank_e2e_s = time.perf_counter() - t0
     checksum = float(o[:, :8].sum())
-    e2e_s, e2e_api = per_rank_e2e_s, "VecPGDriveEnv.step(numpy) -> pgd_step_host"
-    e2e_h2d, e2e_d2h = n * 8, n * (4 * OBS_DIM + 4 + 1 + INFO_BYTES)
+    e2e_s = per_rank_e2e_s
+    e2e_api = ("VecPGDriveEnv.step(numpy) -> pgd_step_host: observation rows cross PCIe packed (head + hit mask + beams "
+               "that are not 1.0) and host threads expand them into the caller's array, bit-identical to the dense copy")
+    e2e_h2d, e2e_d2h = env.host_transfer_bytes()  # counted by the library: the copies it enqueued in the last step
+    e2e_dense_d2h = n * (4 * OBS_DIM + 4 + 1 + INFO_BYTES)
     if world > 1 and peer is not None:
         # north_star's path: the actions of the WHOLE batch start in rank 0's host memory, the gathered observation /
         # reward / done batch ends there.  H2D on rank 0, broadcast over NVLink, step + gather, one D2H on rank 0.
@@ -622,7 +625,7 @@ def run_own(args):
         reset_path=reset_path,
         e2e=dict(value=total_envs * e2e_steps / (e2e_ms * 1e-3), unit="env-steps/s",
                  h2d_bytes_per_step=e2e_h2d, d2h_bytes_per_step=e2e_d2h, steps=e2e_steps, api=e2e_api,
-                 checksum=checksum,
+                 checksum=checksum, dense_d2h_bytes_per_step=e2e_dense_d2h if world == 1 else None,
                  per_rank=dict(value=total_envs * e2e_steps / (per_rank_e2e_ms * 1e-3),
                                api="every rank: VecPGDriveEnv.step(numpy) -> pgd_step_host on its own shard")),
         gpu_launches=int(launches), clocks=clk,

@@ -48,9 +48,27 @@ int pgd_reset(PgdHandle* h, const int32_t* env_ids, const int32_t* episode_ids, 
 int pgd_step(PgdHandle* h, const float* actions_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev,
              PgdInfo* info_dev, void* stream);
 
-/* Same step with HOST buffers (the call a gym user makes): actions are staged through pinned memory,
- * results copied back, and the call returns when they are valid. */
+/* Same step with HOST buffers (the call a gym user makes; envs/base_env.py:184-224 `step`): actions are staged through
+ * pinned memory and the call returns when the results are valid in the caller's arrays (page-locked or not).
+ * Observation rows cross PCIe packed -- head + 240-bit hit mask per row, the beams that are not 1.0 compacted per chunk
+ * -- and a pool of host threads expands them into `obs`.  When `obs` is the array of the previous call, only the head
+ * and the beams that were or are hits are written (the handle remembers the hit masks it left there), so the caller
+ * must not modify `obs` between calls -- or call pgd_host_invalidate, after which the next step rewrites every beam.
+ * The result is bit-identical to pgd_step + a dense copy.  PGDRIVE_B200_HOST_DENSE=1 (or lidar noise, which leaves no
+ * beam at 1.0) ships dense rows instead; PGDRIVE_B200_HOST_THREADS / PGDRIVE_B200_HOST_CHUNKS override the pool size
+ * (default: the CPUs of the process, at most 16) and the number of chunks per step. */
 int pgd_step_host(PgdHandle* h, const float* actions, float* obs, float* reward, uint8_t* done, PgdInfo* info);
+int pgd_host_invalidate(PgdHandle* h);
+int pgd_host_transfer_bytes(PgdHandle* h, uint64_t* h2d, uint64_t* d2h);  /* bytes over PCIe in the last pgd_step_host */
+/* The host half of that path, pure CPU code (exported for tests): expand `n_rows` rows of [head | 8 mask words] (`base`)
+ * plus their hit values, `hits[hit_offset...]` in row and beam order, into dense rows; `mask_state` (8 words per row)
+ * holds the masks of the rows `dense` held before and receives the new ones; `full` != 0 rewrites every beam.
+ * Returns the number of hit values consumed, or a negative error code. */
+int pgd_host_expand_rows(const float* base, const float* hits, int32_t hit_offset, int32_t n_rows, int32_t obs_dim,
+                         float* dense, uint32_t* mask_state, int32_t full);
+/* Self-test of the host thread pool (no GPU): `rounds` jobs of `items` items on `workers` threads; 0 when every item
+ * of every job ran exactly once. */
+int pgd_host_pool_selftest(int32_t workers, int32_t items, int32_t rounds);
 
 /* component/vehicle/base_vehicle.py:683-698 get_state / set_state, for the whole environment (debugging
  * and parity tests; synchronous). */

@@ -12,6 +12,7 @@ COMMON = ["pgd_internal.h", os.path.join(INC, "pgdrive_b200.h"), os.path.join(IN
 UNITS = {
     "pgd_abi.cu": [],
     "pgd_rows.cu": [],
+    "pgd_hostpath.cu": [],
     "pgd_step_kernel.cu": ["pgd_step.cuh"],
     "pgd_mapgen.cu": ["pgd_mapgen.cuh", "pgd_rng.cuh", "pgd_dd.cuh"],
 }
@@ -58,7 +59,7 @@ def build_cuda(force=False, verbose=False, out=OUT, defines=()):
         relink = True
     relink = relink or any(os.path.getmtime(o) > os.path.getmtime(out) for o in objs)
     if relink:
-        _run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out] + objs, verbose)
+        _run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out] + objs + ["-lpthread"], verbose)
     return out
 
 

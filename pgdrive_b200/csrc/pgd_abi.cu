@@ -78,9 +78,7 @@ extern "C" int pgd_destroy(PgdHandle* h) {
   for (int i = 0; i < 7; ++i) cudaFree(h->state_mem[i]);
   for (int i = 0; i < 10; ++i) cudaFree(h->table_mem[i]);
   cudaFree(h->d_ids); cudaFree(h->d_eps);
-  cudaFreeHost(h->h_act); cudaFreeHost(h->h_obs); cudaFreeHost(h->h_rew); cudaFreeHost(h->h_done);
-  cudaFreeHost(h->h_info);
-  cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_done); cudaFree(h->d_info);
+  pgd_hostpath_destroy(h);
   cudaStreamDestroy(h->own_stream);
   cudaStreamDestroy(h->own_stream2);
   cudaEventDestroy(h->ev_act);
@@ -183,83 +181,6 @@ extern "C" int pgd_step(PgdHandle* h, const float* actions_dev, float* obs_dev, 
                              (cudaStream_t)stream);
   if (rc) return rc;
   return note_caller_stream(h, (cudaStream_t)stream);
-}
-
-static int ensure_staging(PgdHandle* h) {
-  if (h->h_act) return 0;
-  const size_t n = (size_t)h->cfg.num_envs;
-  CU(cudaMallocHost(&h->h_act, n * 8));
-  const size_t od = (size_t)pgd_obs_dim(&h->cfg);
-  CU(cudaMallocHost(&h->h_obs, n * od * 4));
-  CU(cudaMallocHost(&h->h_rew, n * 4));
-  CU(cudaMallocHost(&h->h_done, n));
-  CU(cudaMallocHost(&h->h_info, n * sizeof(PgdInfo)));
-  CU(cudaMalloc(&h->d_act, n * 8));
-  CU(cudaMalloc(&h->d_obs, n * od * 4));
-  CU(cudaMalloc(&h->d_rew, n * 4));
-  CU(cudaMalloc(&h->d_done, n));
-  CU(cudaMalloc(&h->d_info, n * sizeof(PgdInfo)));
-  return 0;
-}
-
-static bool is_pinned(const void* p) {
-  cudaPointerAttributes a;
-  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
-    cudaGetLastError();
-    return false;
-  }
-  return a.type == cudaMemoryTypeHost;
-}
-
-extern "C" int pgd_step_host(PgdHandle* h, const float* actions, float* obs, float* reward, uint8_t* done,
-                             PgdInfo* info) {
-  if (!h || !actions || !obs || !reward || !done) return fail(-1, "pgd_step_host: null argument");
-  if (!h->tables_loaded) return fail(-3, "pgd_step_host: no tables loaded");
-  CU(cudaSetDevice(h->device));
-  h->call_index++;
-  int rc = ensure_staging(h);
-  if (rc) return rc;
-  const size_t n = (size_t)h->cfg.num_envs;
-  const size_t od = (size_t)pgd_obs_dim(&h->cfg);
-  cudaStream_t st = h->own_stream;
-  // Page-locked caller buffers are DMA targets themselves; pageable ones go through the handle's pinned staging.
-  const bool direct = is_pinned(obs) && is_pinned(reward) && is_pinned(done) && (!info || is_pinned(info));
-  float* o_dst = direct ? obs : h->h_obs;
-  float* r_dst = direct ? reward : h->h_rew;
-  uint8_t* d_dst = direct ? done : h->h_done;
-  PgdInfo* i_dst = direct ? info : h->h_info;
-  if (h->have_last) CU(cudaStreamWaitEvent(st, h->ev_last, 0));  // order after the caller-stream reset / step
-  memcpy(h->h_act, actions, n * 8);
-  CU(cudaMemcpyAsync(h->d_act, h->h_act, n * 8, cudaMemcpyHostToDevice, st));
-  // The step is cut into chunks of environments on two streams so that the device-to-host copy of one chunk (the
-  // PCIe-bound part: 1.1 KB per environment) overlaps the kernel of the next.
-  const int chunks = n >= 8192 ? 4 : 1;
-  if (chunks > 1) {
-    CU(cudaEventRecord(h->ev_act, st));
-    CU(cudaStreamWaitEvent(h->own_stream2, h->ev_act, 0));
-  }
-  const int per = (int)((n / chunks + 31) / 32 * 32);
-  for (int c = 0; c < chunks; ++c) {
-    const int b = c * per, e = (c == chunks - 1) ? (int)n : (c + 1) * per;
-    cudaStream_t cs = (c & 1) ? h->own_stream2 : st;
-    rc = launch_step(h, 0, b, e, h->d_act, h->d_obs, h->d_rew, h->d_done, info ? h->d_info : nullptr, cs);
-    if (rc) return rc;
-    const size_t m = (size_t)(e - b);
-    CU(cudaMemcpyAsync(o_dst + (size_t)b * od, h->d_obs + (size_t)b * od, m * od * 4,
-                       cudaMemcpyDeviceToHost, cs));
-    CU(cudaMemcpyAsync(r_dst + b, h->d_rew + b, m * 4, cudaMemcpyDeviceToHost, cs));
-    CU(cudaMemcpyAsync(d_dst + b, h->d_done + b, m, cudaMemcpyDeviceToHost, cs));
-    if (info) CU(cudaMemcpyAsync(i_dst + b, h->d_info + b, m * sizeof(PgdInfo), cudaMemcpyDeviceToHost, cs));
-  }
-  CU(cudaStreamSynchronize(st));
-  if (chunks > 1) CU(cudaStreamSynchronize(h->own_stream2));
-  if (!direct) {
-    memcpy(obs, h->h_obs, n * od * 4);
-    memcpy(reward, h->h_rew, n * 4);
-    memcpy(done, h->h_done, n);
-    if (info) memcpy(info, h->h_info, n * sizeof(PgdInfo));
-  }
-  return 0;
 }
 
 // the V per-slot records of one environment: strided by num_envs (state is [slot][env])

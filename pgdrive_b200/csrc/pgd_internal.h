@@ -61,13 +61,8 @@ struct PgdHandle {
   int32_t* d_ids;
   int32_t* d_eps;
   int scratch_cap;
-  // pinned staging + device buffers for the host-buffer step
-  float *h_act, *h_obs, *h_rew;
-  uint8_t* h_done;
-  PgdInfo* h_info;
-  float *d_act, *d_obs, *d_rew;
-  uint8_t* d_done;
-  PgdInfo* d_info;
+  // the host-buffer step (pgd_hostpath.cu): transfer buffers, delta state, thread pool; its two streams
+  void* hostpath;
   cudaStream_t own_stream, own_stream2;
   cudaEvent_t ev_act;
   cudaEvent_t ev_last;  // recorded after every enqueue on the caller's stream; the host-buffer step waits for it
@@ -80,4 +75,6 @@ struct PgdHandle {
 // pgd_step_kernel.cu: the fused environment step (mode 0) / the reset pass (mode 1) over environments [env_begin, env_end)
 int pgd_launch_step(PgdHandle* h, int mode, int env_begin, int env_end, const float* actions, float* obs,
                     float* reward, uint8_t* done, PgdInfo* info, cudaStream_t st);
+// pgd_hostpath.cu
+void pgd_hostpath_destroy(PgdHandle* h);
 #endif

@@ -449,7 +449,11 @@ class VecPGDriveEnv:
 
         Host path: the results land in page-locked staging arrays that the NEXT step overwrites.  ``copy=True``
         (default) returns fresh arrays, like the reference; ``copy=False`` returns the staging arrays themselves
-        (no 75 MB copy per step at 65 536 environments) -- valid only until the next ``step`` / ``reset``."""
+        (no 75 MB copy per step at 65 536 environments), read-only -- valid only until the next ``step`` / ``reset``.
+
+        Observation rows cross PCIe packed (head + lidar hit mask + the beams that are not 1.0) and are expanded by a
+        pool of host threads inside the library; the staging rows keep the previous step's content and only what
+        changed is rewritten (include/pgdrive_b200.h: pgd_step_host)."""
         e = self.engine
         torch = e.torch
         if self.config["discrete_action"]:
@@ -488,7 +492,19 @@ class VecPGDriveEnv:
         )
         if copy:
             return self._h_obs.copy(), self._h_reward.copy(), self._h_done.copy(), self._h_info.copy()
-        return self._h_obs, self._h_reward, self._h_done, self._h_info
+        # read-only views: the next step writes only what changed in the observation rows (pgd_step_host)
+        views = [a.view() for a in (self._h_obs, self._h_reward, self._h_done, self._h_info)]
+        for v in views:
+            v.flags.writeable = False
+        return tuple(views)
+
+    def host_transfer_bytes(self):
+        """(host-to-device, device-to-host) bytes the last host-path ``step`` moved over PCIe."""
+        import ctypes
+        a, b = ctypes.c_uint64(), ctypes.c_uint64()
+        e = self.engine
+        cabi.check(e.lib, e.lib.pgd_host_transfer_bytes(e.h, ctypes.byref(a), ctypes.byref(b)))
+        return int(a.value), int(b.value)
 
     def info_numpy(self):
         """Device info of the last device-path step/reset as a structured array (synchronises)."""

@@ -381,3 +381,56 @@ def test_long_soak_with_a_feedback_policy():
             seen["out"] += int(((fl & 2) != 0).sum())
     assert seen["arrive"] > 10 and seen["crash"] > 5 and seen["out"] > 50, seen
     env.close()
+
+
+@pytest.mark.parametrize("variant", ["default", "second_copy", "dense", "one_thread"])
+def test_host_buffer_step_variants_equal_device_step(variant, monkeypatch):
+    """pgd_step_host ships packed rows and expands them on the host as a delta against the previous step's rows.  Every
+    way through it gives the device step's results bit for bit: hits travelling with the first copy / fetched by a
+    second one, dense rows, one host thread, a changed destination array (full expansion), detector fans in the head,
+    and an invalidated state."""
+    import ctypes
+    import torch
+    from pgdrive_b200 import cabi
+    if variant == "second_copy":
+        monkeypatch.setenv("PGDRIVE_B200_HOST_FIRST_HITS", "0")
+        monkeypatch.setenv("PGDRIVE_B200_HOST_CHUNKS", "3")
+    if variant == "one_thread":
+        monkeypatch.setenv("PGDRIVE_B200_HOST_THREADS", "1")
+    n = 4096 + 40
+    det = (8, 50.0, 4, 20.0) if variant == "default" else None  # detector fans: a longer head
+    env_a, _ = _pair(n, [1000, 1001, 1002, 1003, 1004], detectors=det)
+    env_b, _ = _pair(n, [1000, 1001, 1002, 1003, 1004], detectors=det)
+    env_a.reset()
+    env_b.reset()
+    rs = np.random.RandomState(9)
+    other = np.full((n, env_a.obs_dim), np.nan, np.float32)  # a second destination, used through the C-ABI directly
+    rew, done = np.zeros(n, np.float32), np.zeros(n, np.uint8)
+    hits = 0
+    for t in range(60):
+        a = rs.uniform(-1, 1, (n, 2)).astype(np.float32)
+        a[:, 1] = np.abs(a[:, 1])
+        a[:, 0] *= 0.1
+        if variant == "dense" and t == 20:
+            monkeypatch.setenv("PGDRIVE_B200_HOST_DENSE", "1")
+        if variant == "dense" and t == 40:
+            monkeypatch.delenv("PGDRIVE_B200_HOST_DENSE")
+        if t % 13 == 5:  # another destination array: everything is rewritten there, and again when we come back
+            e = env_a.engine
+            cabi.check(e.lib, e.lib.pgd_step_host(e.h, a.ctypes.data, other.ctypes.data, rew.ctypes.data,
+                                                  done.ctypes.data, None))
+            o1, r1, d1 = other, rew, done
+        else:
+            if t % 13 == 9:
+                env_a._h_obs[::3] = -5.0  # the caller scribbled over the staging rows ... and says so
+                cabi.check(env_a.engine.lib, env_a.engine.lib.pgd_host_invalidate(env_a.engine.h))
+            o1, r1, d1, _ = env_a.step(a, copy=False)
+            assert not o1.flags.writeable
+        o2, r2, d2, _ = env_b.step(torch.from_numpy(a).cuda())
+        np.testing.assert_array_equal(o1.view(np.uint32), o2.cpu().numpy().view(np.uint32), err_msg="step %d" % t)
+        np.testing.assert_array_equal(r1, r2.cpu().numpy())
+        np.testing.assert_array_equal(d1, d2.cpu().numpy())
+        hits += int((o1[:, -240:] != 1.0).sum())
+    assert hits > 5 * n  # the lidar saw things: the hit path was exercised
+    env_a.close()
+    env_b.close()
