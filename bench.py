@@ -42,10 +42,12 @@ import numpy as np  # noqa: E402
 
 OBS_DIM = 274
 INFO_BYTES = 40
-PREROLL = 2048  # untimed random-policy steps before the timed region: the cost of a step climbs from 0.10 ms right
+# (PGDRIVE_B200_BENCH_PREROLL shortens both pre-rolls for the ncu launch-list run only: that run is about WHICH kernels
+# launch, never about a number)
+PREROLL = int(os.environ.get("PGDRIVE_B200_BENCH_PREROLL", 2048))  # untimed random-policy steps before the timed region: the cost of a step climbs from 0.10 ms right
 # after a reset to a 0.33 ms peak near step 400 and settles by step ~2000 (mean episode ~1000 steps,
 # profiles/r02i_cost_curve_*.log); the driving policy (mean episode ~50 steps) is steady after 256
-PREROLL_DRIVING = 256
+PREROLL_DRIVING = min(256, PREROLL)
 SMS, ISSUE_PER_SM_CLK = 148, 4  # B200: 148 SMs x 4 warp schedulers, one warp instruction per scheduler per clock
 
 WORKLOADS = {
@@ -171,7 +173,7 @@ def run_reference(args):
     return 0
 
 
-def issue_bound(kernel_ms, sm_mhz, policy, workload):
+def issue_bound(kernel_ms, sm_mhz, policy, workload, envs=65536):
     """Secondary (honest) bound, SURVEY 8(d): the kernel is latency / issue bound, not HBM bound.  Warp instructions
     per launch come from the committed ncu capture of this workload (profiles/issue_slots.json); the rate they are
     issued at is live: kernel time from this run, SM clock from nvidia-smi during it."""
@@ -182,9 +184,10 @@ def issue_bound(kernel_ms, sm_mhz, policy, workload):
     if not rec:
         return None
     peak = SMS * ISSUE_PER_SM_CLK * sm_mhz * 1e6  # warp instructions / s
-    achieved = rec["warp_instructions_per_launch"] / (kernel_ms * 1e-3)
+    insts = rec["warp_instructions_per_launch"] * envs / 65536.0  # the capture is of a 65 536-environment launch
+    achieved = insts / (kernel_ms * 1e-3)
     return dict(bound="issue", achieved=achieved / 1e9, peak=peak / 1e9, unit="G warp-inst/s", frac=achieved / peak,
-                warp_instructions_per_launch=rec["warp_instructions_per_launch"],
+                warp_instructions_per_launch=insts,
                 threads_per_instruction=rec.get("threads_per_instruction"), source=rec.get("source"))
 
 
@@ -541,7 +544,8 @@ def run_own(args):
         return dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
                     traffic=traffic if (policy == "random" and args.workload == "v0" and n_max == 65536) else None,
                     kernel="pgd_step_kernel<%d, 4>" % n_slots, kernel_ms=k_ms, bytes_per_env_step=b_step,
-                    peak_source=peak_src, issue=issue_bound(k_ms, (clk or {}).get("sm_mhz"), policy, args.workload))
+                    peak_source=peak_src,
+                    issue=issue_bound(k_ms, (clk or {}).get("sm_mhz"), policy, args.workload, envs=n_max))
 
     gather_check = None
     if world > 1:
@@ -617,7 +621,9 @@ def run_own(args):
                 (2 * (80 * n_slots + 32) + 4 * OBS_DIM) * n_max / 1e6),
             collective=collective, done_rate_last_step=done_rate,
         ),
-        roofline=roofline(kernel_ms, "random"),
+        # N > 1: the step kernel's own time is that of the simulation-only leg (largest shard); the per-step time of the
+        # gathered loop includes waiting for buffers
+        roofline=roofline(kernel_ms if world == 1 else sim_ms / K, "random"),
         driving=dict(value=n_max * fwd_k / (fwd_ms * 1e-3), unit="env-steps/s per GPU", steps=fwd_k,
                      policy="throttle |u|, steering 0.1 u: traffic awake, lidar hits, frequent resets",
                      done_rate_last_step=fwd_done_rate, roofline=roofline(fwd_kernel_ms, "driving")),
@@ -632,7 +638,8 @@ def run_own(args):
     )
     if world > 1:
         line["sim_only"] = dict(value=total_envs * K / (sim_ms * 1e-3), unit="env-steps/s", ms_per_step=sim_ms / K,
-                                note="the same K steps without the gather")
+                                note="the same K steps without the gather (with balanced shards rank 0 idles most of "
+                                     "this leg: the figure is that of the N - 1 larger shards)")
         line["gather_check"] = gather_check
     print(json.dumps(line))
     if world > 1:

@@ -56,7 +56,7 @@ int pgd_step(PgdHandle* h, const float* actions_dev, float* obs_dev, float* rewa
  * must not modify `obs` between calls -- or call pgd_host_invalidate, after which the next step rewrites every beam.
  * The result is bit-identical to pgd_step + a dense copy.  PGDRIVE_B200_HOST_DENSE=1 (or lidar noise, which leaves no
  * beam at 1.0) ships dense rows instead; PGDRIVE_B200_HOST_THREADS / PGDRIVE_B200_HOST_CHUNKS override the pool size
- * (default: the CPUs of the process, at most 16) and the number of chunks per step. */
+ * (default: the CPUs of the process -- divided by LOCAL_WORLD_SIZE under torchrun --, at most 16) and the number of chunks per step. */
 int pgd_step_host(PgdHandle* h, const float* actions, float* obs, float* reward, uint8_t* done, PgdInfo* info);
 int pgd_host_invalidate(PgdHandle* h);
 int pgd_host_transfer_bytes(PgdHandle* h, uint64_t* h2d, uint64_t* d2h);  /* bytes over PCIe in the last pgd_step_host */

@@ -317,6 +317,8 @@ static int hostpath_init(PgdHandle* h) {
   int workers = (int)std::thread::hardware_concurrency();
   cpu_set_t set;  // the CPUs this process may run on (a cpuset smaller than the machine)
   if (sched_getaffinity(0, sizeof(set), &set) == 0 && CPU_COUNT(&set) > 0) workers = CPU_COUNT(&set);
+  const char* lws = getenv("LOCAL_WORLD_SIZE");  // torchrun: the ranks of this node share its CPUs
+  if (lws && atoi(lws) > 1) workers /= atoi(lws);
   const char* w = getenv("PGDRIVE_B200_HOST_THREADS");
   if (w && atoi(w) > 0) workers = atoi(w);
   if (workers > 16) workers = 16;
