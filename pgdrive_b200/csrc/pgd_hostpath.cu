@@ -10,7 +10,8 @@
 // handle remembers the hit masks it left there; another destination, or pgd_host_invalidate, forces a full expansion).
 // The result is bit-identical to the dense copy (tests/test_gpu_step.py, tests/test_hostpath.py).
 //
-// Per step: the environments are cut into chunks on two streams; per chunk ONE device-to-host copy carries
+// Per step: the environments are cut into chunks; one stream runs their step + packing kernels back to back, a second
+// one copies (the kernels of chunk c + 1 never wait for the copy of chunk c); per chunk ONE device-to-host copy carries
 // [hit count | per-group offsets | rewards | dones | infos | head + mask rows | the first hits]; the host waits for
 // chunk c, expands it with the pool while chunks c + 1.. are still computing / copying.
 #include <cuda_runtime.h>
@@ -30,8 +31,8 @@
 #include "../../include/pgdrive_b200.h"
 #include "pgd_internal.h"
 
-#define HP_GROUP 128          // rows per group: one CTA of the packing kernel, one work item of the host pool
-#define HP_PACK_WARPS 16      // 8 rows per warp
+#define HP_GROUP 64           // rows per group: one CTA of the packing kernel, one work item of the host pool
+#define HP_PACK_WARPS 16      // 4 rows per warp
 
 // ---- device: dense rows -> [head + mask] rows + hit values compacted per group --------------------------------------
 // Group g of a chunk reserves its segment of `hits` with one atomicAdd on the chunk's counter (segments are in arrival
@@ -72,7 +73,7 @@ pgd_pack_compact_kernel(const float* __restrict__ dense, int row_begin, int m, i
     if (lane == 0) s_cnt[r] = cnt;
   }
   __syncthreads();
-  if (threadIdx.x < HP_GROUP) {  // exclusive scan of the group's 128 counts
+  if (threadIdx.x < HP_GROUP) {  // exclusive scan of the group's counts
     const int v = s_cnt[threadIdx.x];
     int inc = v;
 #pragma unroll
@@ -215,7 +216,7 @@ struct HostChunk {
   size_t off_total, off_seg, off_rew, off_done, off_info, off_base, off_hits, bytes;
   int expect;                                                  // hit values that travel with the first copy
   char *dev, *host;                                            // start of this chunk in the two buffers
-  cudaEvent_t ready;
+  cudaEvent_t packed, ready;                                   // results on the device / in host memory
 };
 
 struct HostPath {
@@ -308,6 +309,7 @@ static int hostpath_init(PgdHandle* h) {
     c.dev = hp->dev + o;
     c.host = hp->host + o;
     CU(cudaEventCreateWithFlags(&c.ready, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c.packed, cudaEventDisableTiming));
   }
   CU(cudaMallocHost(&hp->h_act, (size_t)n * 8));
   CU(cudaMalloc(&hp->d_act, (size_t)n * 8));
@@ -333,7 +335,10 @@ void pgd_hostpath_destroy(PgdHandle* h) {
   HostPath* hp = (HostPath*)h->hostpath;
   if (!hp) return;
   delete hp->pool;
-  for (auto& c : hp->chunks) cudaEventDestroy(c.ready);
+  for (auto& c : hp->chunks) {
+    cudaEventDestroy(c.ready);
+    cudaEventDestroy(c.packed);
+  }
   cudaFree(hp->dev);
   cudaFreeHost(hp->host);
   cudaFreeHost(hp->h_act);
@@ -375,38 +380,37 @@ extern "C" int pgd_step_host(PgdHandle* h, const float* actions, float* obs, flo
   // the hit counters of all chunks (first word of every chunk's buffer): one strided memset
   const size_t pitch = hp->chunks.size() > 1 ? (size_t)(hp->chunks[1].dev - hp->chunks[0].dev) : 16;
   CU(cudaMemset2DAsync(hp->dev, pitch, 0, 4, hp->chunks.size(), s0));
-  if (hp->chunks.size() > 1) {
-    CU(cudaEventRecord(h->ev_act, s0));
-    CU(cudaStreamWaitEvent(s1, h->ev_act, 0));
-  }
   hp->last_h2d = n * 8;
   hp->last_d2h = 0;
   // With lidar noise every beam differs from 1.0 and the packed row is longer than the dense one: ship dense rows.
   const bool dense_rows = h->cfg.lidar_gaussian_noise > 0.0f || getenv("PGDRIVE_B200_HOST_DENSE") != nullptr;
   for (size_t k = 0; k < hp->chunks.size(); ++k) {
     HostChunk& c = hp->chunks[k];
-    cudaStream_t cs = (k & 1) ? s1 : s0;
     const int m = c.e - c.b;
     // the kernel indexes its outputs by global environment: hand it bases that put [b, e) into this chunk's buffer
     float* rew = (float*)(c.dev + c.off_rew) - c.b;
     uint8_t* dn = (uint8_t*)(c.dev + c.off_done) - c.b;
     PgdInfo* inf = info ? (PgdInfo*)(c.dev + c.off_info) - c.b : nullptr;
-    if (int rc = pgd_launch_step(h, 0, c.b, c.e, hp->d_act, hp->d_obs, rew, dn, inf, cs)) return rc;
-    if (dense_rows) {
-      CU(cudaMemcpyAsync(c.host, c.dev, c.off_base, cudaMemcpyDeviceToHost, cs));
-      CU(cudaMemcpyAsync(obs + (size_t)c.b * od, hp->d_obs + (size_t)c.b * od, (size_t)m * od * 4,
-                         cudaMemcpyDeviceToHost, cs));
-      hp->last_d2h += c.off_base + (size_t)m * od * 4;
-    } else {
-      pgd_pack_compact_kernel<<<c.groups, HP_PACK_WARPS * 32, 0, cs>>>(
+    if (int rc = pgd_launch_step(h, 0, c.b, c.e, hp->d_act, hp->d_obs, rew, dn, inf, s0)) return rc;
+    if (!dense_rows) {
+      pgd_pack_compact_kernel<<<c.groups, HP_PACK_WARPS * 32, 0, s0>>>(
           hp->d_obs, c.b, m, od, (int*)(c.dev + c.off_total), (int*)(c.dev + c.off_seg), (float*)(c.dev + c.off_base),
           (float*)(c.dev + c.off_hits));
       h->launches++;
+    }
+    CU(cudaEventRecord(c.packed, s0));
+    CU(cudaStreamWaitEvent(s1, c.packed, 0));
+    if (dense_rows) {
+      CU(cudaMemcpyAsync(c.host, c.dev, c.off_base, cudaMemcpyDeviceToHost, s1));
+      CU(cudaMemcpyAsync(obs + (size_t)c.b * od, hp->d_obs + (size_t)c.b * od, (size_t)m * od * 4,
+                         cudaMemcpyDeviceToHost, s1));
+      hp->last_d2h += c.off_base + (size_t)m * od * 4;
+    } else {
       const size_t first_bytes = c.off_hits + up16((size_t)c.expect * 4);
-      CU(cudaMemcpyAsync(c.host, c.dev, first_bytes, cudaMemcpyDeviceToHost, cs));
+      CU(cudaMemcpyAsync(c.host, c.dev, first_bytes, cudaMemcpyDeviceToHost, s1));
       hp->last_d2h += first_bytes;
     }
-    CU(cudaEventRecord(c.ready, cs));
+    CU(cudaEventRecord(c.ready, s1));
   }
   CU(cudaGetLastError());
   const bool full = !(hp->state_valid && hp->last_obs == obs);
@@ -429,12 +433,11 @@ extern "C" int pgd_step_host(PgdHandle* h, const float* actions, float* obs, flo
       // the next step's first copy carries a quarter more than this step needed (hits change slowly between steps)
       if (hp->first_hits < 0) c.expect = std::min(m * PGD_LIDAR_BEAMS, total + total / 4 + 64);
       if (total > had) {  // more hits than travelled with the first copy: fetch the rest
-        cudaStream_t cs = (k & 1) ? s1 : s0;
         const size_t have = (size_t)had * 4;
         err = cudaMemcpyAsync(c.host + c.off_hits + have, c.dev + c.off_hits + have, (size_t)total * 4 - have,
-                              cudaMemcpyDeviceToHost, cs);
+                              cudaMemcpyDeviceToHost, s1);
         hp->last_d2h += (size_t)total * 4 - have;
-        if (err == cudaSuccess) err = cudaStreamSynchronize(cs);
+        if (err == cudaSuccess) err = cudaStreamSynchronize(s1);
         if (err != cudaSuccess) {
           rc = fail(-2, std::string("pgd_step_host: ") + cudaGetErrorString(err));
           break;
