@@ -145,6 +145,22 @@ def build_tables(workload="v0"):
                              ((">", ">>", 0), 5.0, 0.0))
 
 
+def line_config(args, n_gpus, n_slots, desc):
+    """The `config` object of the JSON line: names the workload; identical for both arms given the same arguments
+    (everything that describes HOW an arm ran it is in `details`)."""
+    return dict(
+        workload=desc % args.envs, envs_per_gpu=args.envs, total_envs=n_gpus * args.envs,
+        parallelism="env-sharded x%d" % n_gpus,
+        l2=l2_note((2 * (80 * n_slots + 32) + 4 * OBS_DIM) * args.envs / 1e6, args.envs))
+
+
+def l2_note(mb, envs):
+    if mb > 126:
+        return "no flush: state + observations touched per step = %.0f MB per %d environments > 126 MB L2" % (mb, envs)
+    return ("no flush: state + observations touched per step = %.0f MB per %d environments fit the 126 MB L2 -- an "
+            "L2-warm figure; the headline configuration (65 536 environments, 244 MB) does not fit") % (mb, envs)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -164,8 +180,9 @@ def run_reference(args):
         impl="reference", metric="env-steps/s", value=rate, unit="env-steps/s", n_gpus=args.gpus, steps=args.steps,
         warmup=args.warmup, ms_per_step=dt / args.steps * 1e3, higher_is_better=True, scaling="weak",
         vs_baseline=None, dtype="f32", data="synthetic",
-        config=dict(workload=desc % args.envs, envs_per_gpu=args.envs, actions="uniform[-1,1]^2, RandomState(0)",
-                    note="reference step needs Panda3D/Bullet (not installable offline): CPU oracle port timed instead"),
+        config=line_config(args, args.gpus, n_slots, desc),
+        details=dict(actions="uniform[-1,1]^2, RandomState(0)",
+                     note="reference step needs Panda3D/Bullet (not installable offline): CPU oracle port timed instead"),
         cpu_baseline=dict(value=rate, unit="env-steps/s", cores=threads, kind="port", sample=sample),
         e2e=dict(value=rate, unit="env-steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
     )
@@ -610,15 +627,12 @@ def run_own(args):
         metric="env-steps/s", value=value, unit="env-steps/s", n_gpus=world, steps=K, warmup=W,
         ms_per_step=ms / K, higher_is_better=True, scaling="weak", vs_baseline=None,
         dtype="f32", data="synthetic",
-        config=dict(
-            workload=desc % args.envs, envs_per_gpu=args.envs, total_envs=total_envs,
-            parallelism="env-sharded x%d" % world, shard_sizes=sizes if world > 1 else None,
-            balance=None if world == 1 else balance_note,
+        config=line_config(args, world, n_slots, desc),
+        details=dict(
+            shard_sizes=sizes if world > 1 else None, balance=None if world == 1 else balance_note,
             actions="uniform[-1,1]^2, Philox, pre-generated in HBM", preroll_steps=PREROLL,
             preroll_steps_driving=PREROLL_DRIVING,
             arithmetic="float32 throughout; the reference's Python side computes in float64, Bullet in float32",
-            l2="no flush: state + observations touched per step = %.0f MB > 126 MB L2" % (
-                (2 * (80 * n_slots + 32) + 4 * OBS_DIM) * n_max / 1e6),
             collective=collective, done_rate_last_step=done_rate,
         ),
         # N > 1: the step kernel's own time is that of the simulation-only leg (largest shard); the per-step time of the

@@ -13,7 +13,7 @@ try:
     d = json.load(open("gpurun_out/${TAG}_bench_${N}gpu_${mode}.json"))
     print("$mode N=$N: value %.1f M  ms/step %.4f  sim_only %.1f M  e2e %.1f M  gather_check %s  [%s]" % (
         d["value"] / 1e6, d["ms_per_step"], d["sim_only"]["value"] / 1e6, d["e2e"]["value"] / 1e6, d["gather_check"]["ok"],
-        d["config"]["collective"][:60]))
+        d["details"]["collective"][:60]))
 except Exception as e:
     print("$mode N=$N failed:", e)
 PY
