@@ -68,19 +68,25 @@ def algorithmic_bytes_per_env_step(num_slots):
 
 
 class ClockSampler:
-    """nvidia-smi clocks and throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks and throttle reasons under load (B200_PROFILING.md recipe).  nvidia-smi needs up to a second to
+    deliver its first line and the timed region is 40 ms, so the sampler starts early, `mark()` is called when the GPU
+    starts running the step kernel back to back (pre-roll -> warm-up -> timed steps, no idle gap), and only samples
+    that arrive between the mark and `stop()` -- called right after the timed region -- count."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+        self.rows, self.proc, self.index, self.t0 = [], None, index, None
+
+    def mark(self):
+        self.t0 = time.time()
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms",
-                 "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True
+                 "25"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True
             )
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -89,7 +95,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
 
     def stop(self):
         if not self.proc:
@@ -101,7 +107,12 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        t_end = time.time()
+        rows = [r for t, r in self.rows if self.t0 is None or self.t0 + 0.05 <= t <= t_end]
+        window = "pre-roll + warm-up + timed steps (the step kernel back to back)"
+        if not rows:  # nvidia-smi too slow to start: better the samples around the region than none
+            rows, window = [r for _, r in self.rows], "all samples of the run (none arrived inside the loaded window)"
+        for r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
                 continue
@@ -114,7 +125,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
-                    reasons=sorted(reasons), samples=len(sm))
+                    reasons=sorted(reasons), samples=len(sm), window=window)
 
 
 def host_threads():
@@ -295,6 +306,9 @@ def run_own(args):
                 raise SystemExit("peer mapping failed with unequal shards: run with --balance equal (NCCL all-gather)")
             peer, gather_mode, bufs = None, "nccl (peer mapping unavailable)", make_bufs()
 
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()  # early: nvidia-smi takes its time to deliver the first line (see ClockSampler)
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)  # Philox counter-based stream, one per rank
     n_act = max(W + K, 256)
@@ -424,16 +438,15 @@ def run_own(args):
 
     # ---- headline: BASELINE.md's random policy, gather included -------------------------------------------------------
     env.reset()
+    torch.cuda.synchronize()
+    if rank == 0:
+        clocks.mark()  # from here to the end of the timed region the GPU runs the step kernel back to back
     for t in range(PREROLL):  # untimed pre-roll: not tied to --steps / --warmup
         env.step(actions[t % n_act])
     for t in range(W):
         step_and_gather(actions[t])
     drain()
     barrier()
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
-        time.sleep(0.3)
     launches0 = env.launch_count
     ms, kernel_ms = timed(actions[W:W + K], K, lambda a: step_and_gather(a, check=(world > 1)))
     launches = env.launch_count - launches0
