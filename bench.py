@@ -519,6 +519,8 @@ def run_own(args):
             h_rew = torch.empty(rows, dtype=torch.float32, pin_memory=True)
             h_done = torch.empty(rows, dtype=torch.uint8, pin_memory=True)
 
+        packed_host = [True]
+
         def host_step():
             if rank == 0:
                 all_act_dev.copy_(h_all, non_blocking=True)
@@ -527,9 +529,16 @@ def run_own(args):
             drain()
             if rank == 0:
                 go, gr, gd = peer.tensors(counter[0] - 1)
-                h_obs.copy_(go, non_blocking=True)
-                h_rew.copy_(gr, non_blocking=True)
-                h_done.copy_(gd, non_blocking=True)
+                if packed_host[0]:
+                    try:  # the gathered batch crosses PCIe packed and is expanded by host threads (pgd_rows_to_host)
+                        env.rows_to_host(go, gr, gd, h_obs.numpy(), h_rew.numpy(), h_done.numpy())
+                    except Exception as exc:  # noqa: BLE001 -- fall back to dense copies, say so
+                        sys.stderr.write("pgd_rows_to_host failed (%s): dense copies\n" % exc)
+                        packed_host[0] = False
+                if not packed_host[0]:
+                    h_obs.copy_(go, non_blocking=True)
+                    h_rew.copy_(gr, non_blocking=True)
+                    h_done.copy_(gd, non_blocking=True)
             torch.cuda.synchronize()
 
         e2e_steps_n = min(e2e_steps, 16)
@@ -541,8 +550,11 @@ def run_own(args):
         barrier()
         e2e_s = (time.perf_counter() - t0) * e2e_steps / e2e_steps_n  # normalised to e2e_steps below
         e2e_api = ("rank 0 host actions [N*n, 2] -> H2D -> NCCL broadcast -> step + gather to rank 0 -> D2H of the "
-                   "gathered obs / reward / done to rank 0's host")
+                   "gathered obs / reward / done to rank 0's host" + (
+                       " (rows packed over PCIe, expanded by host threads: pgd_rows_to_host)" if packed_host[0] else ""))
         e2e_h2d, e2e_d2h = rows * 8, rows * (4 * OBS_DIM + 4 + 1)
+        if packed_host[0] and rank == 0:
+            e2e_d2h = env.host_transfer_bytes()[1]
 
     times = torch.tensor([ms, e2e_s * 1e3, kernel_ms, fwd_ms, fwd_kernel_ms, per_rank_e2e_s * 1e3, sim_ms or 0.0],
                          dtype=torch.float64, device=dev)

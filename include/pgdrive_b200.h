@@ -60,6 +60,12 @@ int pgd_step(PgdHandle* h, const float* actions_dev, float* obs_dev, float* rewa
 int pgd_step_host(PgdHandle* h, const float* actions, float* obs, float* reward, uint8_t* done, PgdInfo* info);
 int pgd_host_invalidate(PgdHandle* h);
 int pgd_host_transfer_bytes(PgdHandle* h, uint64_t* h2d, uint64_t* d2h);  /* bytes over PCIe in the last pgd_step_host */
+/* The same transfer for observation rows that are already in device memory -- e.g. the whole gathered batch in rank 0's
+ * HBM: packed over PCIe, expanded by the host threads into `obs` as a delta against the previous call with the same
+ * destination and row count.  `reward_dev` / `done_dev` (and their host arrays) may be NULL.  `stream`: the stream
+ * the rows were written on; returns when the host arrays are valid. */
+int pgd_rows_to_host(PgdHandle* h, const float* obs_dev, const float* reward_dev, const uint8_t* done_dev, int32_t n_rows,
+                     int32_t obs_dim, float* obs, float* reward, uint8_t* done, void* stream);
 /* The host half of that path, pure CPU code (exported for tests): expand `n_rows` rows of [head | 8 mask words] (`base`)
  * plus their hit values, `hits[hit_offset...]` in row and beam order, into dense rows; `mask_state` (8 words per row)
  * holds the masks of the rows `dense` held before and receives the new ones; `full` != 0 rewrites every beam.

@@ -129,6 +129,7 @@ def load_library():
     lib.pgd_step.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     lib.pgd_step_host.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.pgd_host_invalidate.argtypes = [vp]
+    lib.pgd_rows_to_host.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, vp, vp]
     lib.pgd_host_transfer_bytes.argtypes = [vp, vp, vp]
     lib.pgd_host_expand_rows.argtypes = [vp, vp, i32, i32, i32, vp, vp, i32]
     lib.pgd_host_pool_selftest.argtypes = [i32, i32, i32]
@@ -155,7 +156,7 @@ def load_library():
     lib.pgd_patch_tables.argtypes = [vp, i32, C.POINTER(PgdTables), vp]
     lib.pgd_download_tables.argtypes = [vp, C.POINTER(PgdTables)]
     for name in ("pgd_create", "pgd_destroy", "pgd_load_tables", "pgd_reset", "pgd_step", "pgd_step_host",
-                 "pgd_host_invalidate", "pgd_host_transfer_bytes", "pgd_host_expand_rows", "pgd_host_pool_selftest",
+                 "pgd_host_invalidate", "pgd_rows_to_host", "pgd_host_transfer_bytes", "pgd_host_expand_rows", "pgd_host_pool_selftest",
                  "pgd_get_state", "pgd_set_state", "pgd_set_timing", "pgd_words_checksum", "pgd_pack_rows", "pgd_expand_rows",
                  "pgd_expand_rows_delta", "pgd_packed_row_words", "pgd_patch_tables", "pgd_peer_alloc", "pgd_peer_open",
                  "pgd_peer_release", "pgd_generate_tables", "pgd_table_sizes", "pgd_download_tables"):

@@ -230,6 +230,7 @@ struct HostPath {
   float *h_act = nullptr, *d_act = nullptr;
   float* d_obs = nullptr;     // dense rows of the step kernel (device only)
   uint64_t last_h2d = 0, last_d2h = 0;  // bytes over PCIe in the last step
+  int rows = 0, obs_dim = 0;            // pgd_rows_to_host: the batch this instance was sized for
   int first_hits = -1;        // >= 0 (PGDRIVE_B200_HOST_FIRST_HITS, tests): hit values per row in a chunk's first copy
 };
 
@@ -283,6 +284,21 @@ extern "C" int pgd_host_expand_rows(const float* base, const float* hits, int32_
   return off - hit_offset;
 }
 
+// threads that expand rows (the caller's included): the CPUs this process may run on, at most 16
+static int pool_threads(int n_rows, bool every_rank_calls) {
+  int workers = (int)std::thread::hardware_concurrency();
+  cpu_set_t set;  // a cpuset smaller than the machine
+  if (sched_getaffinity(0, sizeof(set), &set) == 0 && CPU_COUNT(&set) > 0) workers = CPU_COUNT(&set);
+  const char* lws = getenv("LOCAL_WORLD_SIZE");  // torchrun: the ranks of this node share its CPUs
+  if (every_rank_calls && lws && atoi(lws) > 1) workers /= atoi(lws);
+  const char* w = getenv("PGDRIVE_B200_HOST_THREADS");
+  if (w && atoi(w) > 0) workers = atoi(w);
+  if (workers > 16) workers = 16;
+  if (workers < 1) workers = 1;
+  if (n_rows < 4096) workers = 1;  // a handful of rows: the caller's thread alone
+  return workers;
+}
+
 static int hostpath_init(PgdHandle* h) {
   if (h->hostpath) return 0;
   HostPath* hp = new HostPath();
@@ -331,23 +347,20 @@ static int hostpath_init(PgdHandle* h) {
   CU(cudaMalloc(&hp->d_obs, (size_t)n * od * 4));
   hp->mask = (uint32_t*)calloc((size_t)n * 8, 4);
   if (!hp->mask) return fail(-2, "pgd_step_host: out of host memory");
-  int workers = (int)std::thread::hardware_concurrency();
-  cpu_set_t set;  // the CPUs this process may run on (a cpuset smaller than the machine)
-  if (sched_getaffinity(0, sizeof(set), &set) == 0 && CPU_COUNT(&set) > 0) workers = CPU_COUNT(&set);
-  const char* lws = getenv("LOCAL_WORLD_SIZE");  // torchrun: the ranks of this node share its CPUs
-  if (lws && atoi(lws) > 1) workers /= atoi(lws);
-  const char* w = getenv("PGDRIVE_B200_HOST_THREADS");
-  if (w && atoi(w) > 0) workers = atoi(w);
-  if (workers > 16) workers = 16;
-  if (workers < 1) workers = 1;
-  if (n < 4096) workers = 1;  // a handful of rows: the caller's thread alone
-  hp->pool = new HostPool(workers - 1);
+  hp->pool = new HostPool(pool_threads(n, true) - 1);
   h->hostpath = hp;
   return 0;
 }
 
+static void hostpath_free(HostPath* hp);
+
 void pgd_hostpath_destroy(PgdHandle* h) {
-  HostPath* hp = (HostPath*)h->hostpath;
+  hostpath_free((HostPath*)h->hostpath);
+  hostpath_free((HostPath*)h->rowspath);
+  h->hostpath = h->rowspath = nullptr;
+}
+
+static void hostpath_free(HostPath* hp) {
   if (!hp) return;
   delete hp->pool;
   for (auto& c : hp->chunks) {
@@ -361,12 +374,12 @@ void pgd_hostpath_destroy(PgdHandle* h) {
   cudaFree(hp->d_obs);
   free(hp->mask);
   delete hp;
-  h->hostpath = nullptr;
 }
 
 extern "C" int pgd_host_transfer_bytes(PgdHandle* h, uint64_t* h2d, uint64_t* d2h) {
   if (!h || !h2d || !d2h) return fail(-1, "pgd_host_transfer_bytes: null argument");
   HostPath* hp = (HostPath*)h->hostpath;
+  if (h->last_host_call == 2) hp = (HostPath*)h->rowspath;
   *h2d = hp ? hp->last_h2d : 0;
   *d2h = hp ? hp->last_d2h : 0;
   return 0;
@@ -375,6 +388,7 @@ extern "C" int pgd_host_transfer_bytes(PgdHandle* h, uint64_t* h2d, uint64_t* d2
 extern "C" int pgd_host_invalidate(PgdHandle* h) {
   if (!h) return fail(-1, "pgd_host_invalidate: null handle");
   if (h->hostpath) ((HostPath*)h->hostpath)->state_valid = false;
+  if (h->rowspath) ((HostPath*)h->rowspath)->state_valid = false;
   return 0;
 }
 
@@ -384,6 +398,7 @@ extern "C" int pgd_step_host(PgdHandle* h, const float* actions, float* obs, flo
   if (!h->tables_loaded) return fail(-3, "pgd_step_host: no tables loaded");
   CU(cudaSetDevice(h->device));
   h->call_index++;
+  h->last_host_call = 1;
   if (int rc = hostpath_init(h)) return rc;
   HostPath* hp = (HostPath*)h->hostpath;
   const size_t n = (size_t)h->cfg.num_envs;
@@ -487,4 +502,139 @@ extern "C" int pgd_step_host(PgdHandle* h, const float* actions, float* obs, flo
     hp->state_valid = true;
   }
   return 0;
+}
+
+// ---- any batch of observation rows in HBM -> host arrays, packed over PCIe ------------------------------------------
+// The same transfer for rows that are already in device memory -- e.g. the whole gathered batch in rank 0's HBM
+// (bench.py's end-to-end leg at N > 1: 577 MB dense per step at 8 GPUs).  `stream`: the stream the rows were written
+// on; the call returns when the host arrays are valid.  Delta expansion as in pgd_step_host (same destination array as
+// in the previous call with the same number of rows; pgd_host_invalidate resets both).
+static int rowspath_init(PgdHandle* h, int n_rows, int od) {
+  HostPath* old = (HostPath*)h->rowspath;
+  if (old && old->rows == n_rows && old->obs_dim == od) return 0;
+  hostpath_free(old);
+  h->rowspath = nullptr;
+  HostPath* hp = new HostPath();
+  hp->rows = n_rows;
+  hp->obs_dim = od;
+  const int bw = od - PGD_LIDAR_BEAMS + 8;
+  const int per = n_rows >= 4 * 16384 ? 16384 * ((n_rows / 16384 + 15) / 16) : n_rows >= 8192 ?
+      (n_rows / 4 + HP_GROUP - 1) / HP_GROUP * HP_GROUP : n_rows;  // at most 16 chunks of >= 16 384 rows
+  size_t at = 0;
+  for (int b = 0; b < n_rows; b += per) {
+    HostChunk c;
+    memset(&c, 0, sizeof(c));
+    c.b = b;
+    c.e = b + per < n_rows ? b + per : n_rows;
+    const size_t m = (size_t)(c.e - c.b);
+    c.groups = (int)((m + HP_GROUP - 1) / HP_GROUP);
+    c.off_seg = 16;
+    c.off_rew = c.off_done = c.off_info = c.off_base = c.off_seg + up16((size_t)c.groups * 4);
+    c.off_hits = c.off_base + up16(m * bw * 4);
+    c.expect = (int)m * 4;
+    c.bytes = c.off_hits + up16(m * PGD_LIDAR_BEAMS * 4);
+    c.dev = (char*)at;
+    at += (c.bytes + 255) & ~(size_t)255;
+    hp->chunks.push_back(c);
+  }
+  hp->bytes = at;
+  h->rowspath = hp;  // from here on pgd_hostpath_destroy releases whatever was allocated
+  CU(cudaMalloc(&hp->dev, hp->bytes));
+  CU(cudaMallocHost(&hp->host, hp->bytes));
+  CU(cudaMemset(hp->dev, 0, hp->bytes));
+  for (auto& c : hp->chunks) {
+    const size_t o = (size_t)c.dev;
+    c.dev = hp->dev + o;
+    c.host = hp->host + o;
+    CU(cudaEventCreateWithFlags(&c.ready, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c.packed, cudaEventDisableTiming));
+  }
+  hp->mask = (uint32_t*)calloc((size_t)n_rows * 8, 4);
+  if (!hp->mask) return fail(-2, "pgd_rows_to_host: out of host memory");
+  hp->pool = new HostPool(pool_threads(n_rows, false) - 1);
+  return 0;
+}
+
+extern "C" int pgd_rows_to_host(PgdHandle* h, const float* obs_dev, const float* reward_dev, const uint8_t* done_dev,
+                                int32_t n_rows, int32_t obs_dim, float* obs, float* reward, uint8_t* done, void* stream) {
+  if (!h || !obs_dev || !obs || n_rows <= 0 || obs_dim < PGD_LIDAR_BEAMS)
+    return fail(-1, "pgd_rows_to_host: null pointer, no rows or rows shorter than the lidar");
+  if ((reward_dev == nullptr) != (reward == nullptr) || (done_dev == nullptr) != (done == nullptr))
+    return fail(-1, "pgd_rows_to_host: reward / done need both their device and their host array");
+  if ((uintptr_t)obs_dev & 3) return fail(-1, "pgd_rows_to_host: rows must be 4-byte aligned");
+  CU(cudaSetDevice(h->device));
+  h->last_host_call = 2;
+  if (int rc = rowspath_init(h, n_rows, obs_dim)) return rc;
+  HostPath* hp = (HostPath*)h->rowspath;
+  const int od = obs_dim, bw = od - PGD_LIDAR_BEAMS + 8;
+  cudaStream_t s0 = h->own_stream, s1 = h->own_stream2;
+  CU(cudaEventRecord(h->ev_act, (cudaStream_t)stream));  // the rows are complete when the caller's stream gets here
+  CU(cudaStreamWaitEvent(s0, h->ev_act, 0));
+  CU(cudaStreamWaitEvent(s1, h->ev_act, 0));
+  const size_t pitch = hp->chunks.size() > 1 ? (size_t)(hp->chunks[1].dev - hp->chunks[0].dev) : 16;
+  CU(cudaMemset2DAsync(hp->dev, pitch, 0, 4, hp->chunks.size(), s0));
+  hp->last_h2d = 0;
+  hp->last_d2h = 0;
+  for (size_t k = 0; k < hp->chunks.size(); ++k) {
+    HostChunk& c = hp->chunks[k];
+    const int m = c.e - c.b;
+    pgd_pack_compact_kernel<<<c.groups, HP_PACK_WARPS * 32, 0, s0>>>(
+        obs_dev, c.b, m, od, (int*)(c.dev + c.off_total), (int*)(c.dev + c.off_seg), (float*)(c.dev + c.off_base),
+        (float*)(c.dev + c.off_hits));
+    h->launches++;
+    CU(cudaEventRecord(c.packed, s0));
+    CU(cudaStreamWaitEvent(s1, c.packed, 0));
+    const size_t first_bytes = c.off_hits + up16((size_t)c.expect * 4);
+    CU(cudaMemcpyAsync(c.host, c.dev, first_bytes, cudaMemcpyDeviceToHost, s1));
+    hp->last_d2h += first_bytes;
+    CU(cudaEventRecord(c.ready, s1));
+  }
+  CU(cudaGetLastError());
+  const bool full = !(hp->state_valid && hp->last_obs == obs);
+  hp->pool->begin();
+  int rc = 0;
+  for (size_t k = 0; k < hp->chunks.size() && rc == 0; ++k) {
+    HostChunk& c = hp->chunks[k];
+    cudaError_t err;
+    while ((err = cudaEventQuery(c.ready)) == cudaErrorNotReady) cpu_relax();
+    const int m = c.e - c.b;
+    const int total = err == cudaSuccess ? *(const int*)(c.host + c.off_total) : 0;
+    const int had = c.expect;
+    c.expect = std::min(m * PGD_LIDAR_BEAMS, total + total / 4 + 64);
+    if (err == cudaSuccess && total > had) {  // more hits than travelled with the first copy: fetch the rest
+      // (s1 also carries the later chunks' copies: the wait below covers them too, which is rare and harmless)
+      const size_t have = (size_t)had * 4;
+      err = cudaMemcpyAsync(c.host + c.off_hits + have, c.dev + c.off_hits + have, (size_t)total * 4 - have,
+                            cudaMemcpyDeviceToHost, s1);
+      hp->last_d2h += (size_t)total * 4 - have;
+      if (err == cudaSuccess) err = cudaStreamSynchronize(s1);
+    }
+    if (err != cudaSuccess) {
+      rc = fail(-2, std::string("pgd_rows_to_host: ") + cudaGetErrorString(err));
+      break;
+    }
+    const float* c_hits = (const float*)(c.host + c.off_hits);
+    const std::function<void(int)> job = [&](int g) {
+      const int r0 = g * HP_GROUP, rows = m - r0 < HP_GROUP ? m - r0 : HP_GROUP;
+      const size_t row = (size_t)c.b + r0;
+      pgd_host_expand_rows((const float*)(c.host + c.off_base) + (size_t)r0 * bw, c_hits,
+                           ((const int*)(c.host + c.off_seg))[g], rows, od, obs + row * od, hp->mask + row * 8,
+                           full ? 1 : 0);
+    };
+    hp->pool->run(c.groups, job);
+  }
+  hp->pool->end();
+  // rewards and dones are 5 bytes per row: plain copies behind the rows (enqueued last: a copy into pageable memory
+  // blocks the calling thread until the stream gets there)
+  cudaError_t err = cudaSuccess;
+  if (rc == 0 && reward) err = cudaMemcpyAsync(reward, reward_dev, (size_t)n_rows * 4, cudaMemcpyDeviceToHost, s1);
+  if (rc == 0 && err == cudaSuccess && done)
+    err = cudaMemcpyAsync(done, done_dev, (size_t)n_rows, cudaMemcpyDeviceToHost, s1);
+  hp->last_d2h += (reward ? (size_t)n_rows * 4 : 0) + (done ? (size_t)n_rows : 0);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(s1);  // (after an error: whatever is still in flight)
+  cudaStreamSynchronize(s0);
+  if (rc == 0 && err != cudaSuccess) rc = fail(-2, std::string("pgd_rows_to_host: ") + cudaGetErrorString(err));
+  hp->state_valid = rc == 0;
+  hp->last_obs = obs;
+  return rc;
 }

@@ -63,6 +63,8 @@ struct PgdHandle {
   int scratch_cap;
   // the host-buffer step (pgd_hostpath.cu): transfer buffers, delta state, thread pool; its two streams
   void* hostpath;
+  void* rowspath;     // pgd_rows_to_host: the same machinery for rows that are already in HBM
+  int last_host_call;  // 1 pgd_step_host, 2 pgd_rows_to_host (pgd_host_transfer_bytes reports the last one)
   cudaStream_t own_stream, own_stream2;
   cudaEvent_t ev_act;
   cudaEvent_t ev_last;  // recorded after every enqueue on the caller's stream; the host-buffer step waits for it

@@ -498,6 +498,27 @@ class VecPGDriveEnv:
             v.flags.writeable = False
         return tuple(views)
 
+    def rows_to_host(self, obs, reward, done, obs_out, reward_out=None, done_out=None):
+        """Device rows -> host arrays through the packed PCIe path (pgd_rows_to_host): ``obs`` [R, obs_dim] float32 CUDA
+        tensor (any batch in this GPU's memory, e.g. the gathered batch on rank 0), ``reward`` / ``done`` CUDA tensors or
+        None; ``obs_out`` [R, obs_dim] float32 numpy array (C-contiguous; pass the same one every step: only what
+        changed is rewritten), ``reward_out`` / ``done_out`` numpy arrays.  Returns when the host arrays are valid."""
+        e = self.engine
+        rows, od = int(obs.shape[0]), int(obs.shape[1])
+        if not (obs.is_cuda and obs.is_contiguous() and obs.dtype == e.torch.float32):
+            raise ValueError("obs must be a contiguous float32 CUDA tensor")
+        if obs_out.shape != (rows, od) or obs_out.dtype != np.float32 or not obs_out.flags.c_contiguous:
+            raise ValueError("obs_out must be a C-contiguous float32 [%d, %d] array" % (rows, od))
+        for dev, host, dt, name in ((reward, reward_out, np.float32, "reward"), (done, done_out, np.uint8, "done")):
+            if (dev is None) != (host is None):
+                raise ValueError("%s needs both its device tensor and its host array" % name)
+            if dev is not None and (host.shape != (rows, ) or host.dtype != dt or not dev.is_contiguous()):
+                raise ValueError("%s: [%d] %s on both sides" % (name, rows, np.dtype(dt).name))
+        cabi.check(e.lib, e.lib.pgd_rows_to_host(
+            e.h, obs.data_ptr(), None if reward is None else reward.data_ptr(), None if done is None else done.data_ptr(),
+            rows, od, obs_out.ctypes.data, None if reward_out is None else reward_out.ctypes.data,
+            None if done_out is None else done_out.ctypes.data, e.stream()))
+
     def host_transfer_bytes(self):
         """(host-to-device, device-to-host) bytes the last host-path ``step`` moved over PCIe."""
         import ctypes

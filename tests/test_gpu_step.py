@@ -262,3 +262,48 @@ def test_delta_expansion_equals_full_expansion():
         assert lib.pgd_expand_rows_delta(packed.data_ptr(), dense.data_ptr(), None, n, d, 0, st) == -1
     finally:
         env.close()
+
+
+def test_rows_to_host_equals_dense_copy():
+    """pgd_rows_to_host (packed rows over PCIe, delta expansion on the host) for a batch that is already in HBM --
+    bit for bit what a dense copy gives: over many steps into one array, into a second array, with rows of many hits."""
+    import numpy as np
+    import torch
+    from pgdrive_b200 import VecPGDriveEnv
+    n = 20000 + 8  # 4 chunks, the last one partial
+    env = VecPGDriveEnv(dict(num_envs=n, start_seed=1000, environment_num=20))
+    try:
+        env.reset()
+        g = torch.Generator(device="cuda"); g.manual_seed(2)
+        host = np.full((n, env.obs_dim), np.nan, np.float32)
+        other = np.full((n, env.obs_dim), np.nan, np.float32)
+        hr, hd = np.zeros(n, np.float32), np.zeros(n, np.uint8)
+        for t in range(40):
+            a = torch.rand((n, 2), generator=g, device="cuda") * 2 - 1
+            a[:, 1] = a[:, 1].abs(); a[:, 0] *= 0.1
+            obs, rew, done, _ = env.step(a)
+            if t % 9 == 4:
+                obs = obs.clone()
+                obs[::5, -240:] = torch.rand((len(obs[::5]), 240), generator=g, device="cuda")  # more hits than expected
+            dst = other if t % 7 == 3 else host
+            env.rows_to_host(obs, rew, done, dst, hr, hd)
+            assert np.array_equal(dst.view(np.uint32), obs.cpu().numpy().view(np.uint32)), t
+            assert np.array_equal(hr, rew.cpu().numpy()) and np.array_equal(hd, done.cpu().numpy())
+            h2d, d2h = env.host_transfer_bytes()
+            assert h2d == 0 and 0 < d2h
+        env.rows_to_host(obs[:5000].contiguous(), None, None, host[:5000])  # another row count: new buffers, full
+        assert np.array_equal(host[:5000].view(np.uint32), obs[:5000].cpu().numpy().view(np.uint32))
+        # a gathered batch of eight shards: 17 chunks of 16 384 rows
+        big = obs.repeat(14, 1)[:270000].contiguous()
+        big_host = np.empty((270000, env.obs_dim), np.float32)
+        for rep in range(3):
+            if rep == 1:
+                big[1::3, -240:] = 1.0
+            if rep == 2:
+                big[:, :34] += 1.0
+            env.rows_to_host(big, None, None, big_host)
+            assert np.array_equal(big_host.view(np.uint32), big.cpu().numpy().view(np.uint32)), rep
+        with pytest.raises(ValueError):
+            env.rows_to_host(obs, rew, None, host, hr, hd)
+    finally:
+        env.close()
