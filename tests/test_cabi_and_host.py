@@ -303,3 +303,27 @@ def test_ego_view_and_map_views_mirror_the_reference_properties():
     assert s["done"] is False and s["destination"] == ("a", "b") and s["spawn_road"] == (">", ">>")
     assert m.num_blocks == 4 and m.road_network is m.net
     assert [b["id"] for b in m.save_map()["block_sequence"]] == [b.id for b in m.blocks]
+
+
+def test_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference (the CPU oracle port on the host cores): one JSON line with the contract's keys, the
+    SAME `config` object as the CUDA arm prints for the same arguments, `e2e` equal to the line's own value."""
+    import argparse
+    import json
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2",
+                          "--warmup", "1", "--envs", "1024"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                         timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["metric"] == "env-steps/s" and d["value"] > 0 and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == dict(value=d["value"], unit="env-steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0)
+    sys.path.insert(0, ROOT)
+    import bench
+    _, _, n_slots, desc = bench.WORKLOADS["v0"]
+    assert d["config"] == bench.line_config(argparse.Namespace(envs=1024), 1, n_slots, desc)
