@@ -156,10 +156,11 @@ def load_library():
     lib.pgd_patch_tables.argtypes = [vp, i32, C.POINTER(PgdTables), vp]
     lib.pgd_download_tables.argtypes = [vp, C.POINTER(PgdTables)]
     for name in ("pgd_create", "pgd_destroy", "pgd_load_tables", "pgd_reset", "pgd_step", "pgd_step_host",
-                 "pgd_host_invalidate", "pgd_rows_to_host", "pgd_host_transfer_bytes", "pgd_host_expand_rows", "pgd_host_pool_selftest",
-                 "pgd_get_state", "pgd_set_state", "pgd_set_timing", "pgd_words_checksum", "pgd_pack_rows", "pgd_expand_rows",
-                 "pgd_expand_rows_delta", "pgd_packed_row_words", "pgd_patch_tables", "pgd_peer_alloc", "pgd_peer_open",
-                 "pgd_peer_release", "pgd_generate_tables", "pgd_table_sizes", "pgd_download_tables"):
+                 "pgd_host_invalidate", "pgd_rows_to_host", "pgd_host_transfer_bytes", "pgd_host_expand_rows",
+                 "pgd_host_pool_selftest", "pgd_get_state", "pgd_set_state", "pgd_set_timing", "pgd_words_checksum",
+                 "pgd_pack_rows", "pgd_expand_rows", "pgd_expand_rows_delta", "pgd_packed_row_words",
+                 "pgd_patch_tables", "pgd_peer_alloc", "pgd_peer_open", "pgd_peer_release", "pgd_generate_tables",
+                 "pgd_table_sizes", "pgd_download_tables"):
         getattr(lib, name).restype = i32
     _LIB = lib
     return lib
