@@ -271,7 +271,9 @@ def run_own(args):
             if int(ok.item()) == 0:
                 gather_mode = "nccl (peer access unavailable)"
         if gather_mode in ("peer", "copy", "sparse") and args.balance != "equal":
-            cost = dict(step=args.step_ns) if args.step_ns else None
+            # ns per simulated env-step in the steady state of the random policy: 65 536 / 433 M (v0, 16 slots),
+            # 65 536 / 343 M (1000 maps, 24 slots) -- profiles/r03m_bench_*.json
+            cost = dict(step=args.step_ns or {"v0": 2.3, "1000envs": 2.9}[args.workload])
             if args.rank0_envs:
                 sizes = sizes_with_rank0(world * args.envs, world, args.rank0_envs)
             else:
