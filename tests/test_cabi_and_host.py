@@ -327,3 +327,34 @@ def test_reference_arm_prints_the_contract_line():
     import bench
     _, _, n_slots, desc = bench.WORKLOADS["v0"]
     assert d["config"] == bench.line_config(argparse.Namespace(envs=1024), 1, n_slots, desc)
+
+
+def test_clock_sampler_counts_the_samples_of_the_loaded_window():
+    """bench.ClockSampler: samples that arrive between mark() and stop() count; when none did (nvidia-smi too slow to
+    start) it falls back to all samples and says so; throttle reasons are collected."""
+    import time
+    sys.path.insert(0, ROOT)
+    import bench
+
+    class Proc:
+        def terminate(self):
+            pass
+
+        def wait(self, timeout=None):
+            pass
+
+    c = bench.ClockSampler(0)
+    assert c.stop()["reasons"] == ["nvidia-smi unavailable"]  # never started
+    c.proc = Proc()
+    now = time.time()
+    c.rows = [(now - 2.0, "1000, 1965, 300, Not Active, Not Active, Not Active, Not Active"),
+              (now - 0.5, "1965, 1965, 700, Not Active, Not Active, Not Active, Active"),
+              (now - 0.2, "1950, 1965, 700, Not Active, Not Active, Not Active, Not Active"),
+              (now - 0.1, "garbage")]
+    c.t0 = now - 1.0
+    r = c.stop()
+    assert r["samples"] == 2 and r["sm_mhz"] == 1957.5 and r["sm_max_mhz"] == 1965.0 and r["reasons"] == ["sw_power_cap"]
+    assert r["window"].startswith("pre-roll")
+    c.t0 = now + 60
+    r = c.stop()
+    assert r["samples"] == 3 and r["window"].startswith("all samples")
