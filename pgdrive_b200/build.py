@@ -12,7 +12,7 @@ COMMON = ["pgd_internal.h", os.path.join(INC, "pgdrive_b200.h"), os.path.join(IN
 UNITS = {
     "pgd_abi.cu": [],
     "pgd_rows.cu": [],
-    "pgd_hostpath.cu": [],
+    "pgd_hostpath.cu": ["pgd_hostpool.h"],
     "pgd_step_kernel.cu": ["pgd_step.cuh"],
     "pgd_mapgen.cu": ["pgd_mapgen.cuh", "pgd_rng.cuh", "pgd_dd.cuh"],
 }

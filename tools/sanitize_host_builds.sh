@@ -12,3 +12,8 @@ gcc $FLAGS -shared -o _san/libpgd_oracle.so pgd_oracle.c -lm
 cd ..
 ASAN_OPTIONS=detect_leaks=0:halt_on_error=0 UBSAN_OPTIONS=print_stacktrace=1 \
   LD_PRELOAD=$(gcc -print-file-name=libasan.so):$(gcc -print-file-name=libubsan.so) python tools/sanitize_run.py
+# the thread pool of pgd_step_host (pgdrive_b200/csrc/pgd_hostpool.h) under ThreadSanitizer and ASan / UBSan
+g++ -std=c++17 -O1 -g -fsanitize=thread -o oracle/_san/hostpool_tsan oracle/hostpool_check.cpp -lpthread
+oracle/_san/hostpool_tsan
+g++ -std=c++17 -O1 -g -fsanitize=address,undefined -o oracle/_san/hostpool_asan oracle/hostpool_check.cpp -lpthread
+oracle/_san/hostpool_asan
