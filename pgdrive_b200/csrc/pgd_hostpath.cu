@@ -212,7 +212,11 @@ static int pool_threads(int n_rows, bool every_rank_calls) {
   cpu_set_t set;  // a cpuset smaller than the machine
   if (sched_getaffinity(0, sizeof(set), &set) == 0 && CPU_COUNT(&set) > 0) workers = CPU_COUNT(&set);
   const char* lws = getenv("LOCAL_WORLD_SIZE");  // torchrun: the ranks of this node share its CPUs
-  if (every_rank_calls && lws && atoi(lws) > 1) workers /= atoi(lws);
+  if (lws && atoi(lws) > 1) {
+    // every rank expands its own shard at the same time: share the CPUs; only one rank expands (the gathered batch on
+    // rank 0): leave a CPU to each of the others, which wait in a barrier meanwhile
+    workers = every_rank_calls ? workers / atoi(lws) : workers - (atoi(lws) - 1);
+  }
   const char* w = getenv("PGDRIVE_B200_HOST_THREADS");
   if (w && atoi(w) > 0) workers = atoi(w);
   if (workers > 16) workers = 16;
